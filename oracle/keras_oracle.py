@@ -1,0 +1,688 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for the network half of the hot path.
+
+torch-CPU (float64 by default) restatement of the Keras 2.2.4 / TensorFlow 1.12
+semantics the reference's builders and ``train_on_batch`` loops rely on
+(requirements.txt:16,47).  Keras/TF are third-party and absent from the
+checkout and from this image, so these semantics are restated from the
+published Keras 2.2.4 sources ([A1]-[A12] in SURVEY.md section 8c):
+**parity unpinned** for this file -- no reference test or fixture holds expected
+network outputs.  Autograd supplies the gradients; nothing here is used by the
+product.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import it.
+
+Builders cite the reference lines whose layer list they reproduce.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-7  # K.epsilon()
+
+
+def same_pad(L, k, s):
+    """TF 'SAME': out=ceil(L/s), total=max((out-1)s+k-L,0), left=total//2 [A2]."""
+    out = -(-L // s)
+    total = max((out - 1) * s + k - L, 0)
+    return total // 2, total - total // 2
+
+
+class Layer:
+    kind = 'layer'
+
+    def __init__(self):
+        self.trainable = True
+        self.weights = []        # trainable tensors, Keras order
+        self.state = []          # non-trainable tensors (BN moving stats)
+        self.name = None
+
+    def build(self, in_shape, gen, dtype):
+        return in_shape
+
+    def forward(self, x, training, noise):
+        raise NotImplementedError
+
+    def all_layers(self):
+        return [self]
+
+
+def glorot_uniform(shape, fan_in, fan_out, gen, dtype):
+    lim = math.sqrt(6.0 / (fan_in + fan_out))  # [A12]
+    return ((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * lim).to(dtype).requires_grad_(True)
+
+
+class Dense(Layer):
+    kind = 'dense'
+
+    def __init__(self, units, activation=None):
+        super().__init__()
+        self.units, self.activation = units, activation
+
+    def build(self, in_shape, gen, dtype):
+        fin = in_shape[-1]
+        self.weights = [glorot_uniform((fin, self.units), fin, self.units, gen, dtype),
+                        torch.zeros(self.units, dtype=dtype, requires_grad=True)]
+        return in_shape[:-1] + (self.units,)
+
+    def forward(self, x, training, noise):
+        return apply_activation(x @ self.weights[0] + self.weights[1], self.activation)
+
+
+class Conv1D(Layer):
+    kind = 'conv1d'
+
+    def __init__(self, filters, kernel_size, strides=1, padding='valid', activation=None):
+        super().__init__()
+        self.filters, self.k, self.s, self.padding, self.activation = filters, kernel_size, strides, padding, activation
+
+    def build(self, in_shape, gen, dtype):
+        L, cin = in_shape
+        k = self.k
+        self.weights = [glorot_uniform((k, cin, self.filters), k * cin, k * self.filters, gen, dtype),
+                        torch.zeros(self.filters, dtype=dtype, requires_grad=True)]
+        if self.padding == 'same':
+            Lo = -(-L // self.s)
+        else:
+            Lo = (L - k) // self.s + 1
+        return (Lo, self.filters)
+
+    def forward(self, x, training, noise):        # x (B, L, Cin) NLC [A1]
+        xt = x.permute(0, 2, 1)
+        if self.padding == 'same':
+            xt = F.pad(xt, same_pad(x.shape[1], self.k, self.s))
+        y = F.conv1d(xt, self.weights[0].permute(2, 1, 0), self.weights[1], stride=self.s)
+        return apply_activation(y.permute(0, 2, 1), self.activation)
+
+
+class Conv2D(Layer):
+    kind = 'conv2d'
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid'):
+        super().__init__()
+        self.filters, self.k, self.s, self.padding = filters, tuple(kernel_size), tuple(strides), padding
+
+    def build(self, in_shape, gen, dtype):
+        H, W, cin = in_shape
+        kh, kw = self.k
+        self.weights = [glorot_uniform((kh, kw, cin, self.filters), kh * kw * cin, kh * kw * self.filters, gen, dtype),
+                        torch.zeros(self.filters, dtype=dtype, requires_grad=True)]
+        if self.padding == 'same':
+            return (-(-H // self.s[0]), -(-W // self.s[1]), self.filters)
+        return ((H - kh) // self.s[0] + 1, (W - kw) // self.s[1] + 1, self.filters)
+
+    def forward(self, x, training, noise):        # x (B,H,W,C) NHWC
+        xt = x.permute(0, 3, 1, 2)
+        if self.padding == 'same':
+            ph = same_pad(x.shape[1], self.k[0], self.s[0])
+            pw = same_pad(x.shape[2], self.k[1], self.s[1])
+            xt = F.pad(xt, (pw[0], pw[1], ph[0], ph[1]))
+        y = F.conv2d(xt, self.weights[0].permute(3, 2, 0, 1), self.weights[1], stride=self.s)
+        return y.permute(0, 2, 3, 1)
+
+
+class BatchNormalization(Layer):
+    """[A5] eps 1e-3, axis -1, batch mean + biased var in training, moving stats in
+    inference; moving_var is fed the n/(n-(1+eps)) 'sample variance'."""
+    kind = 'bn'
+
+    def __init__(self, momentum=0.99, epsilon=1e-3):
+        super().__init__()
+        self.momentum, self.epsilon = momentum, epsilon
+
+    def build(self, in_shape, gen, dtype):
+        c = in_shape[-1]
+        self.weights = [torch.ones(c, dtype=dtype, requires_grad=True), torch.zeros(c, dtype=dtype, requires_grad=True)]
+        self.state = [torch.zeros(c, dtype=dtype), torch.ones(c, dtype=dtype)]
+        return in_shape
+
+    def forward(self, x, training, noise):
+        g, b = self.weights
+        if training:
+            axes = tuple(range(x.dim() - 1))
+            mean = x.mean(dim=axes)
+            var = ((x - mean) ** 2).mean(dim=axes)
+            n = x.numel() / x.shape[-1]
+            with torch.no_grad():
+                m = self.momentum
+                self.state[0] = self.state[0] * m + mean.detach() * (1 - m)
+                self.state[1] = self.state[1] * m + var.detach() * (n / (n - (1.0 + self.epsilon))) * (1 - m)
+        else:
+            mean, var = self.state
+        return (x - mean) / torch.sqrt(var + self.epsilon) * g + b
+
+
+def apply_activation(x, act):
+    if act in (None, 'linear'):
+        return x
+    if act == 'relu':
+        return torch.relu(x)
+    if act == 'tanh':
+        return torch.tanh(x)
+    if act == 'sigmoid':
+        return torch.sigmoid(x)
+    raise ValueError(act)
+
+
+class Activation(Layer):
+    kind = 'act'
+
+    def __init__(self, act):
+        super().__init__()
+        self.act = act
+
+    def forward(self, x, training, noise):
+        return apply_activation(x, self.act)
+
+
+class LeakyReLU(Layer):
+    kind = 'act'
+
+    def __init__(self, alpha=0.3):
+        super().__init__()
+        self.alpha = alpha
+
+    def forward(self, x, training, noise):
+        return torch.where(x >= 0, x, x * self.alpha)  # [A7]
+
+
+class ReLU(Layer):
+    kind = 'act'
+
+    def __init__(self, max_value=None):
+        super().__init__()
+        self.max_value = max_value
+
+    def forward(self, x, training, noise):
+        y = torch.relu(x)
+        return y if self.max_value is None else torch.clamp(y, max=self.max_value)
+
+
+class _NoiseLayer(Layer):
+    """Dropout family [A6]; the random tensor is taken from ``noise[name]`` when
+    given, else drawn and recorded in ``noise[name]`` for the caller to reuse."""
+    kind = 'noise'
+
+    def draw(self, x, gen):
+        raise NotImplementedError
+
+    def forward(self, x, training, noise):
+        if not training:
+            return x
+        r = noise.get(self.name)
+        if r is None:
+            r = self.draw(x, noise.get('__gen__'))
+            noise[self.name] = r
+        return self.apply(x, r.to(x.dtype))
+
+
+class Dropout(_NoiseLayer):
+    def __init__(self, rate):
+        super().__init__()
+        self.rate = rate
+
+    def draw(self, x, gen):   # keep mask (1 = keep)
+        return (torch.rand(x.shape, generator=gen, dtype=torch.float64) >= self.rate).to(torch.float64)
+
+    def apply(self, x, r):
+        return x * r / (1.0 - self.rate)
+
+
+class GaussianDropout(_NoiseLayer):
+    def __init__(self, rate):
+        super().__init__()
+        self.rate = rate
+
+    def draw(self, x, gen):   # standard normals
+        return torch.randn(x.shape, generator=gen, dtype=torch.float64)
+
+    def apply(self, x, r):
+        return x * (1.0 + r * math.sqrt(self.rate / (1.0 - self.rate)))
+
+
+class GaussianNoise(_NoiseLayer):
+    def __init__(self, stddev):
+        super().__init__()
+        self.stddev = stddev
+
+    def draw(self, x, gen):
+        return torch.randn(x.shape, generator=gen, dtype=torch.float64)
+
+    def apply(self, x, r):
+        return x + r * self.stddev
+
+
+class Reshape(Layer):
+    kind = 'shape'
+
+    def __init__(self, target):
+        super().__init__()
+        self.target = tuple(target)
+
+    def build(self, in_shape, gen, dtype):
+        n = int(np.prod(in_shape))
+        t = list(self.target)
+        if -1 in t:
+            t[t.index(-1)] = n // int(-np.prod(t))
+        self.out = tuple(t)
+        return self.out
+
+    def forward(self, x, training, noise):
+        return x.reshape((x.shape[0],) + self.out)   # row-major [A3]
+
+
+class Flatten(Layer):
+    kind = 'shape'
+
+    def build(self, in_shape, gen, dtype):
+        return (int(np.prod(in_shape)),)
+
+    def forward(self, x, training, noise):
+        return x.reshape(x.shape[0], -1)
+
+
+class UpSampling1D(Layer):
+    kind = 'shape'
+
+    def __init__(self, size=2):
+        super().__init__()
+        self.size = size
+
+    def build(self, in_shape, gen, dtype):
+        return (in_shape[0] * self.size, in_shape[1])
+
+    def forward(self, x, training, noise):
+        return x.repeat_interleave(self.size, dim=1)   # [A4]
+
+
+class MaxPooling1D(Layer):
+    kind = 'shape'
+
+    def __init__(self, pool_size=2):
+        super().__init__()
+        self.p = pool_size
+
+    def build(self, in_shape, gen, dtype):
+        return (in_shape[0] // self.p, in_shape[1])
+
+    def forward(self, x, training, noise):
+        return F.max_pool1d(x.permute(0, 2, 1), self.p).permute(0, 2, 1)
+
+
+class StackResidual(Layer):
+    """bbhMahoGANy.py:164-188 MyLayer: stack([x, const-x], axis=2) -> (B,L,2,1)."""
+    kind = 'mylayer'
+
+    def __init__(self, const):
+        super().__init__()
+        self.const = torch.as_tensor(np.asarray(const))
+
+    def build(self, in_shape, gen, dtype):
+        self.const = self.const.to(dtype).reshape(in_shape)
+        return (in_shape[0], 2, 1)
+
+    def forward(self, x, training, noise):
+        return torch.stack([x, self.const - x], dim=2)
+
+
+class ResidualMoments(Layer):
+    """tests/burstMahoGANy.py:100-125 MyLayer: stack([mean(d), mean(d^2)]), d=const-x,
+    batch-global scalars, output shape (2,)."""
+    kind = 'mylayer'
+
+    def __init__(self, const):
+        super().__init__()
+        self.const = torch.as_tensor(np.asarray(const))
+
+    def build(self, in_shape, gen, dtype):
+        self.const = self.const.to(dtype).reshape(in_shape)
+        return (2,)
+
+    def forward(self, x, training, noise):
+        d = self.const - x
+        return torch.stack([d.mean(), (d * d).mean()])
+
+
+class Sequential(Layer):
+    kind = 'model'
+
+    def __init__(self, layers=None):
+        super().__init__()
+        self.layers = []
+        self.in_shape = None
+        self.out_shape = None
+        for l in layers or []:
+            self.add(l)
+
+    def add(self, layer):
+        self.layers.append(layer)
+
+    def all_layers(self):
+        out = []
+        for l in self.layers:
+            out += l.all_layers()
+        return out
+
+    def build(self, in_shape, gen=None, dtype=torch.float64):
+        if self.out_shape is not None:      # already built (shared sub-model)
+            return self.out_shape
+        self.in_shape = tuple(in_shape)
+        s = tuple(in_shape)
+        for l in self.layers:
+            s = tuple(l.build(s, gen, dtype))
+        self.out_shape = s
+        _name_layers(self)
+        return s
+
+    def forward(self, x, training, noise):
+        for l in self.layers:
+            x = l.forward(x, training, noise)
+        return x
+
+    # ---- Keras protocol -------------------------------------------------
+    def compile(self, loss, optimizer, metrics=None):
+        _compile(self, loss, optimizer)
+
+    def predict(self, x):
+        with torch.no_grad():
+            y = self.forward(_t(x, self), False, {})
+        return _np(y)
+
+    def train_on_batch(self, x, y, noise=None):
+        return _train_on_batch(self, x, y, noise)
+
+    def get_weights(self):
+        out = []
+        for l in self.all_layers():
+            out += [w.detach().numpy().copy() for w in l.weights] + [s.numpy().copy() for s in l.state]
+        return out
+
+    def set_weights(self, ws):
+        i = 0
+        for l in self.all_layers():
+            for w in l.weights:
+                w.data = torch.as_tensor(np.asarray(ws[i])).to(w.dtype).reshape(w.shape).clone()
+                i += 1
+            for k in range(len(l.state)):
+                l.state[k] = torch.as_tensor(np.asarray(ws[i])).to(l.state[k].dtype).clone()
+                i += 1
+        assert i == len(ws)
+
+
+class BranchModel(Sequential):
+    """Functional ``Model(inputs, [out_a, out_b])`` with branches sharing the input
+    (bbhMahoGANy.py:357-404)."""
+
+    def __init__(self, branches):
+        Layer.__init__(self)
+        self.branches = branches
+        self.layers = [l for b in branches for l in b]
+        self.in_shape = self.out_shape = None
+
+    def build(self, in_shape, gen=None, dtype=torch.float64):
+        self.in_shape = tuple(in_shape)
+        outs = []
+        for b in self.branches:
+            s = tuple(in_shape)
+            for l in b:
+                s = tuple(l.build(s, gen, dtype))
+            outs.append(s)
+        self.out_shape = outs
+        _name_layers(self)
+        return outs
+
+    def forward(self, x, training, noise):
+        outs = []
+        for b in self.branches:
+            h = x
+            for l in b:
+                h = l.forward(h, training, noise)
+            outs.append(h)
+        return outs
+
+    def predict(self, x):
+        with torch.no_grad():
+            ys = self.forward(_t(x, self), False, {})
+        return [_np(y) for y in ys]
+
+
+_PREFIX = {Dense: 'dense', Conv1D: 'conv1d', Conv2D: 'conv2d', BatchNormalization: 'batch_normalization',
+           Activation: 'activation', LeakyReLU: 'leaky_re_lu', ReLU: 're_lu', Dropout: 'dropout',
+           GaussianDropout: 'gaussian_dropout', GaussianNoise: 'gaussian_noise', Reshape: 'reshape',
+           Flatten: 'flatten', UpSampling1D: 'up_sampling1d', MaxPooling1D: 'max_pooling1d',
+           StackResidual: 'my_layer', ResidualMoments: 'my_layer'}
+
+
+_NAME_COUNTS = {}
+
+
+def clear_session():
+    """Reset Keras' per-session layer-name counters."""
+    _NAME_COUNTS.clear()
+
+
+def _name_layers(model):
+    cnt = _NAME_COUNTS          # names are unique per session, as in Keras
+    for l in model.all_layers():
+        if l.name is None:
+            p = _PREFIX.get(type(l), 'layer')
+            cnt[p] = cnt.get(p, 0) + 1
+            l.name = '%s_%d' % (p, cnt[p])
+
+
+def _dtype(model):
+    for l in model.all_layers():
+        if l.weights:
+            return l.weights[0].dtype
+    return torch.float64
+
+
+def _t(x, model):
+    return torch.as_tensor(np.asarray(x)).to(_dtype(model))
+
+
+def _np(y):
+    return y.detach().numpy()
+
+
+# ---- optimizers [A8] ---------------------------------------------------------
+
+class Adam:
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=EPS, decay=0.0):
+        self.lr, self.b1, self.b2, self.eps, self.decay = lr, beta_1, beta_2, epsilon, decay
+        self.iterations = 0
+        self.m, self.v = {}, {}
+
+    def step(self, params, grads):
+        lr = self.lr
+        if self.decay > 0:
+            lr = lr * (1.0 / (1.0 + self.decay * self.iterations))
+        t = self.iterations + 1
+        lr_t = lr * (math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t))
+        with torch.no_grad():
+            for p, g in zip(params, grads):
+                k = id(p)
+                m = self.m.get(k, torch.zeros_like(p))
+                v = self.v.get(k, torch.zeros_like(p))
+                m = self.b1 * m + (1 - self.b1) * g
+                v = self.b2 * v + (1 - self.b2) * g * g
+                p -= lr_t * m / (torch.sqrt(v) + self.eps)
+                self.m[k], self.v[k] = m, v
+        self.iterations += 1
+
+
+class SGD:
+    def __init__(self, lr=0.01, decay=0.0):
+        self.lr, self.decay, self.iterations = lr, decay, 0
+
+    def step(self, params, grads):
+        lr = self.lr
+        if self.decay > 0:
+            lr = lr * (1.0 / (1.0 + self.decay * self.iterations))
+        with torch.no_grad():
+            for p, g in zip(params, grads):
+                p -= lr * g
+        self.iterations += 1
+
+
+# ---- losses / metrics [A9][A10] ------------------------------------------------
+
+def binary_crossentropy(y_true, y_pred):
+    p = torch.clamp(y_pred, EPS, 1 - EPS)
+    x = torch.log(p / (1 - p))
+    l = torch.clamp(x, min=0) - x * y_true + torch.log1p(torch.exp(-torch.abs(x)))
+    return l.mean(dim=-1)
+
+
+def mean_squared_error(y_true, y_pred):
+    return ((y_pred - y_true) ** 2).mean(dim=-1)
+
+
+def chisquare_loss(n_sig):
+    """bbhMahoGANy.py:146-162."""
+    return lambda y_true, y_pred: (((y_true - y_pred) ** 2) / (n_sig ** 2)).sum(dim=-1)
+
+
+LOSSES = {'binary_crossentropy': binary_crossentropy, 'mean_squared_error': mean_squared_error, 'mse': mean_squared_error}
+
+
+def accuracy(y_true, y_pred, loss_name):
+    if y_pred.shape[-1] == 1 or loss_name == 'binary_crossentropy':
+        return (y_true == torch.round(y_pred)).to(y_pred.dtype).mean()
+    yt = y_true if y_true.dim() > 1 else y_true[None]
+    yp = y_pred if y_pred.dim() > 1 else y_pred[None].expand_as(yt)
+    return (yt.argmax(-1) == yp.argmax(-1)).to(y_pred.dtype).mean()
+
+
+def _compile(model, loss, optimizer):
+    model.loss_name = loss if isinstance(loss, str) else 'custom'
+    model.loss_fn = LOSSES[loss] if isinstance(loss, str) else loss
+    model.optimizer = optimizer
+    # trainable set is frozen at compile time [A11]
+    model.collected = [w for l in model.all_layers() if l.trainable for w in l.weights]
+
+
+def _labels(y, like):
+    y = torch.as_tensor(np.asarray(y, dtype=np.float64)).to(like.dtype)
+    if y.dim() == 1 and like.dim() == 2:
+        y = y[:, None]
+    return y
+
+
+def _train_on_batch(model, x, y, noise=None):
+    noise = {} if noise is None else noise
+    out = model.forward(_t(x, model), True, noise)
+    outs = out if isinstance(out, list) else [out]
+    ys = y if isinstance(out, list) else [y]
+    losses, accs = [], []
+    for o, yy in zip(outs, ys):
+        yt = _labels(yy, o)
+        losses.append(model.loss_fn(yt, o).mean())
+        accs.append(accuracy(yt, o.detach(), model.loss_name))
+    total = sum(losses)
+    grads = torch.autograd.grad(total, model.collected, allow_unused=True)
+    grads = [torch.zeros_like(p) if g is None else g for p, g in zip(model.collected, grads)]
+    model.last_grads = [g.detach().numpy().copy() for g in grads]
+    model.optimizer.step(model.collected, grads)
+    if len(outs) == 1:
+        return [float(total.detach()), float(accs[0])]
+    return [float(total.detach())] + [float(l.detach()) for l in losses] + [float(a) for a in accs]
+
+
+def set_trainable(model, trainable):
+    """bbhMahoGANy.py:797-809."""
+    model.trainable = trainable
+    for l in model.all_layers():
+        l.trainable = trainable
+
+
+# =============================================================================
+# Builders
+# =============================================================================
+
+def bbh_generator_model(n_pix=1024):
+    """bbhMahoGANy.py:212-295."""
+    act, mom, dr = 'tanh', 0.99, 0.2
+    L = [Dense(256 * int(n_pix / 2)), BatchNormalization(mom), Activation(act), Dropout(dr), Reshape((int(n_pix / 2), 256))]
+    for i, (f, s, up) in enumerate([(64, 2, True), (128, 1, True), (256, 1, False), (512, 1, False), (1024, 1, False)]):
+        if up:
+            L.append(UpSampling1D(2))
+        L += [Conv1D(f, 5, strides=s, padding='same'), BatchNormalization(mom), Activation(act), Dropout(dr)]
+    L += [Conv1D(1, 5, padding='same'), Activation('linear')]
+    m = Sequential(L)
+    m.input_shape = (100,)
+    return m
+
+
+def bbh_signal_pe_model(n_pix=1024):
+    """bbhMahoGANy.py:356-404 (comb_pe_model=False branch)."""
+    mc = [Conv1D(64, 5, strides=2, padding='same'), Activation('relu')]
+    for f in (128, 256, 512):
+        mc += [Conv1D(f, 5, strides=2), Activation('relu')]
+    mc += [Flatten(), Dense(1), Activation('relu')]
+    q = [Conv1D(64, 5, strides=1, padding='same'), Activation('relu')]
+    for f, s in ((128, 1), (256, 1), (512, 2), (1024, 2)):
+        q += [Conv1D(f, 5, strides=s), Activation('relu')]
+    q += [Flatten(), Dense(1), ReLU(max_value=1.0)]
+    # Keras creates layers in call order: mc branch first, then q branch
+    m = BranchModel([mc, q])
+    m.input_shape = (n_pix, 1)
+    return m
+
+
+def bbh_signal_discriminator_model(n_pix=1024):
+    """bbhMahoGANy.py:408-498."""
+    L = [Conv2D(256, (5, 5), strides=(2, 1), padding='same'), LeakyReLU(0.2), Dropout(0.4),
+         Conv2D(512, (5, 5), strides=(2, 1), padding='same'), LeakyReLU(0.2), Dropout(0.4),
+         Flatten(), Dense(1), Activation('sigmoid')]
+    m = Sequential(L)
+    m.input_shape = (n_pix, 2, 1)
+    return m
+
+
+def burst_generator_model(n_pix=512):
+    """tests/burstMahoGANy.py:127-251."""
+    L = [Dense(256 * int(n_pix / 2)), Activation('relu'), Reshape((int(n_pix / 2), 256)), UpSampling1D(2)]
+    for f in (64, 64, 256, 512):
+        L += [Conv1D(f, 5, strides=1, padding='same'), Activation('relu'), GaussianDropout(0.3)]
+    L += [Conv1D(1, 5, padding='same'), Activation('tanh')]
+    m = Sequential(L)
+    m.input_shape = (100,)
+    return m
+
+
+def burst_signal_pe_model(n_pix=512):
+    """tests/burstMahoGANy.py:263-293."""
+    m = Sequential([Conv1D(64, 5, strides=2, padding='same'), Activation('relu'), Conv1D(128, 5, strides=2),
+                    Activation('relu'), Flatten(), Dense(1024), Activation('relu'), Dense(2), Activation('linear')])
+    m.input_shape = (n_pix, 1)
+    return m
+
+
+def burst_signal_discriminator_model(n_pix=512):
+    """tests/burstMahoGANy.py:295-402."""
+    m = Sequential([Conv1D(64, 5, strides=1, padding='same'), Activation('tanh'), MaxPooling1D(2),
+                    Conv1D(128, 5, strides=1), Activation('tanh'), MaxPooling1D(2), Flatten(),
+                    Dense(1024), Activation('tanh'), Dense(1), Activation('sigmoid')])
+    m.input_shape = (n_pix, 1)
+    return m
+
+
+def wvf_get_generative(noise_dim=10, dense_dim=300, out_dim=8192):
+    """train_on_wvf_version/nn.py:72-81."""
+    m = Sequential([Dense(dense_dim), Activation('relu'), Dense(150), Activation('relu'), Dense(out_dim, activation='tanh')])
+    m.input_shape = (noise_dim,)
+    return m
+
+
+def wvf_get_discriminative(in_dim=8192, drate=.25, n_channels=25, conv_sz=5):
+    """train_on_wvf_version/nn.py:83-93."""
+    m = Sequential([Reshape((-1, 1)), Conv1D(n_channels, conv_sz, activation='relu'), Dropout(drate), Flatten(),
+                    Dense(n_channels), Dense(2, activation='sigmoid')])
+    m.input_shape = (in_dim,)
+    return m
+
+
+def build(model, seed=0, dtype=torch.float64):
+    gen = torch.Generator().manual_seed(seed)
+    model.build(model.input_shape, gen, dtype)
+    return model
