@@ -1,0 +1,170 @@
+"""Model builders and training steps of BBH_version/bbhMahoGANy.py, same names and layer lists.
+
+The module-level globals mirror the reference's config block (bbhMahoGANy.py:84-113); builders read
+``n_pix`` at call time exactly as the reference's do, so ``bbh.n_pix = 2048`` selects BASELINE configs 2/3.
+"""
+import numpy as np
+import torch
+
+from . import nn
+from .nn import (Activation, BatchNormalization, Conv1D, Conv2D, Dense, Dropout, Flatten, Input, LeakyReLU, Model,
+                 ReLU, Reshape, Sequential, UpSampling1D, Adam, set_trainable, chisquare_Loss)
+from ._lib import call, ptr, stream
+
+# bbhMahoGANy.py:84-113
+n_pix = 1024
+n_sig = 1.0
+batch_size = 8
+pe_batch_size = 8
+lr = 9e-5
+chi_loss = False
+comb_pe_model = False
+n_noise_real = 1
+cnn_noise_frac = 1.0 / 8.0
+
+
+class MyLayer(nn.StackResidual):
+    """bbhMahoGANy.py:164-188."""
+
+
+def data_subtraction_model(noise_signal, npix):
+    """bbhMahoGANy.py:190-210."""
+    model = Sequential()
+    model.add(MyLayer(noise_signal, input_shape=(npix, 1)))
+    return model
+
+
+def generator_model():
+    """bbhMahoGANy.py:212-295."""
+    model = Sequential()
+    act, momentum, drate, padding, weights, filtsize = 'tanh', 0.99, 0.2, 'same', 'glorot_uniform', 5
+    model.add(Dense(256 * 1 * int(n_pix / 2), kernel_initializer=weights, input_shape=(100,)))
+    model.add(BatchNormalization(momentum=momentum))
+    model.add(Activation(act))
+    model.add(Dropout(drate))
+    model.add(Reshape((int(n_pix / 2), 256)))
+    for filters, strides, up in ((64, 2, True), (128, 1, True), (256, 1, False), (512, 1, False), (1024, 1, False)):
+        if up:
+            model.add(UpSampling1D(size=2))
+        model.add(Conv1D(filters, filtsize, kernel_initializer=weights, strides=strides, padding=padding))
+        model.add(BatchNormalization(momentum=momentum))
+        model.add(Activation(act))
+        model.add(Dropout(drate))
+    model.add(Conv1D(1, filtsize, padding=padding))
+    model.add(Activation('linear'))
+    return model
+
+
+def signal_pe_model():
+    """bbhMahoGANy.py:297-406, the shipped ``comb_pe_model = False`` branch (:356-404).  The
+    ``comb_pe_model`` branch references an undefined ``batchnorm`` (:318) and cannot run in the reference."""
+    if comb_pe_model:
+        raise NotImplementedError('comb_pe_model=True is dead code in the reference (NameError at bbhMahoGANy.py:318)')
+    inputs = Input(shape=(n_pix, 1))
+    act = 'relu'
+    mc_branch = Conv1D(64, 5, strides=2, padding='same')(inputs)
+    mc_branch = Activation(act)(mc_branch)
+    for f in (128, 256, 512):
+        mc_branch = Conv1D(f, 5, strides=2)(mc_branch)
+        mc_branch = Activation(act)(mc_branch)
+    mc_branch = Flatten()(mc_branch)
+    mc_branch = Dense(1)(mc_branch)
+    mc_branch = Activation('relu')(mc_branch)
+
+    q_branch = Conv1D(64, 5, strides=1, padding='same')(inputs)
+    q_branch = Activation(act)(q_branch)
+    for f, s in ((128, 1), (256, 1), (512, 2), (1024, 2)):
+        q_branch = Conv1D(f, 5, strides=s)(q_branch)
+        q_branch = Activation(act)(q_branch)
+    q_branch = Flatten()(q_branch)
+    q_branch = Dense(1)(q_branch)
+    q_branch = ReLU(max_value=1.0)(q_branch)
+    return Model(inputs=inputs, outputs=[mc_branch, q_branch], name='pe net')
+
+
+def signal_discriminator_model():
+    """bbhMahoGANy.py:408-498 (num_lays = 2, no batchnorm, no maxpool)."""
+    weights, drate, alpha, padding, filtsize, n_neuron_scale = 'glorot_uniform', 0.4, 0.2, 'same', (5, 5), 4
+    model = Sequential()
+    model.add(Conv2D(64 * n_neuron_scale, filtsize, kernel_initializer=weights, input_shape=(n_pix, 2, 1),
+                     strides=(2, 1), padding=padding))
+    model.add(LeakyReLU(alpha=alpha))
+    model.add(Dropout(drate))
+    model.add(Conv2D(128 * n_neuron_scale, filtsize, kernel_initializer=weights, strides=(2, 1), padding=padding))
+    model.add(LeakyReLU(alpha=alpha))
+    model.add(Dropout(drate))
+    model.add(Flatten())
+    model.add(Dense(1))
+    model.add(Activation('sigmoid'))
+    return model
+
+
+def generator_after_subtracting_noise(generator, data_subtraction):
+    """bbhMahoGANy.py:500-519."""
+    model = Sequential()
+    model.add(generator)
+    model.add(data_subtraction)
+    return model
+
+
+def generator_containing_signal_discriminator(generator, signal_discriminator):
+    """bbhMahoGANy.py:521-539."""
+    model = Sequential()
+    model.add(generator)
+    model.add(signal_discriminator)
+    return model
+
+
+def build_gan(noise_signal):
+    """Model set-up of main(), bbhMahoGANy.py:1088-1119: returns the compiled
+    (generator, signal_discriminator, signal_discriminator_on_generator, data_subtraction_on_generator)."""
+    generator = generator_model()
+    signal_discriminator = signal_discriminator_model()
+    data_subtraction = data_subtraction_model(noise_signal, n_pix)
+    data_subtraction_on_generator = generator_after_subtracting_noise(generator, data_subtraction)
+    data_subtraction_on_generator.compile(loss='binary_crossentropy', optimizer=Adam(lr=lr, beta_1=0.5),
+                                          metrics=['accuracy'])
+    signal_discriminator_on_generator = generator_containing_signal_discriminator(data_subtraction_on_generator,
+                                                                                  signal_discriminator)
+    set_trainable(signal_discriminator, False)
+    loss = chisquare_Loss(n_sig) if chi_loss else 'binary_crossentropy'
+    signal_discriminator_on_generator.compile(loss=loss, optimizer=Adam(lr=lr, beta_1=0.5), metrics=['accuracy'])
+    set_trainable(signal_discriminator, True)
+    signal_discriminator.compile(loss='binary_crossentropy', optimizer=Adam(lr=lr, beta_1=0.5), metrics=['accuracy'])
+    return generator, signal_discriminator, signal_discriminator_on_generator, data_subtraction_on_generator
+
+
+def pe_train_step(signal_pe, templates, pars, idx, noise, sigma):
+    """One iteration of the CNN loop, bbhMahoGANy.py:1153-1166, with the batch assembled on the device:
+    templates (n, n_pix) CUDA f32, pars (n, 2) CUDA f32, idx (B,) CUDA int32, noise (B//8, n_pix) CUDA f32
+    standard normals, sigma = the np.random.uniform(0,5) draw of :1161."""
+    B = idx.shape[0]
+    L = templates.shape[1]
+    batch = torch.empty((B, L), dtype=torch.float32, device=templates.device)
+    call('gn_gather_rows_f32', ptr(templates), ptr(idx, torch.int32), ptr(batch), B, L, stream())
+    nn_rows = int(B * cnn_noise_frac)
+    if nn_rows > 0:
+        call('gn_add_scaled_f32', ptr(batch), ptr(noise), float(sigma), nn_rows * L, stream())
+    p = torch.empty((B, 2), dtype=torch.float32, device=templates.device)
+    call('gn_gather_rows_f32', ptr(pars), ptr(idx, torch.int32), ptr(p), B, 2, stream())
+    return signal_pe.train_on_batch(batch.reshape(B, L, 1), [p[:, 0].contiguous(), p[:, 1].contiguous()])
+
+
+def gan_train_step(generator, signal_discriminator, signal_discriminator_on_generator, noise_signal_dev,
+                   real, z1, real_noise, z2, _noise_d=None, _noise_g=None):
+    """One iteration of the GAN loop, bbhMahoGANy.py:1241-1299, on device-resident inputs:
+    real (B, n_pix) templates, z1/z2 (B,100) U(-1,1) latents, real_noise (B, n_pix) N(0,1).
+    Returns (sd_loss, sg_loss) as the reference's [loss, acc] lists."""
+    B, L = real.shape
+    dev = real.device
+    fake = generator.forward(z1, nn.Ctx(False))                              # generator.predict (:1248)
+    sX = torch.empty((2 * B, L, 2, 1), dtype=torch.float32, device=dev)
+    # real images: stack(template, N(0,1)) (:1276-1284); fake: stack(G(z), noise_signal - G(z)) (:1268-1272)
+    sX[:B, :, 0, 0] = real
+    sX[:B, :, 1, 0] = real_noise
+    call('gn_stack_residual_fwd_f32', ptr(fake.reshape(B, L).contiguous()), ptr(noise_signal_dev), ptr(sX[B:]), B, L,
+         stream())
+    sy = torch.cat([torch.ones(B, device=dev), torch.zeros(B, device=dev)])
+    sd_loss = signal_discriminator.train_on_batch(sX, sy, _noise=_noise_d)           # :1292
+    sg_loss = signal_discriminator_on_generator.train_on_batch(z2, torch.ones(B, device=dev), _noise=_noise_g)  # :1296
+    return sd_loss, sg_loss

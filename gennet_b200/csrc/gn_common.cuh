@@ -1,0 +1,100 @@
+// Shared helpers for the gennet_b200 sm_100a kernels and their C-ABI wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gennet_b200.h"
+
+namespace gn {
+
+extern thread_local char g_err[512];
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+    return code;
+}
+
+inline int cuda_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+        return GN_ERR_CUDA;
+    }
+    return GN_OK;
+}
+
+#define GN_REQUIRE(cond, msg)                                                          \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            snprintf(gn::g_err, sizeof(gn::g_err), "%s: invalid argument: %s", __func__, msg); \
+            return GN_ERR_ARG;                                                         \
+        }                                                                              \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in thread 0 (blockDim.x multiple of 32, <= 1024)
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem32) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    T r = 0;
+    if (w == 0) {
+        r = (lane < (int)((blockDim.x + 31) >> 5)) ? smem32[lane] : (T)0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// activation codes shared by fused epilogues and the elementwise kernels
+__device__ __forceinline__ float act_fwd(float x, int kind, float a) {
+    switch (kind) {
+        case GN_ACT_RELU: return x > 0.f ? x : 0.f;
+        case GN_ACT_TANH: return tanhf(x);
+        case GN_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+        case GN_ACT_LEAKY: return x >= 0.f ? x : a * x;
+        case GN_ACT_RELU_MAX: return fminf(fmaxf(x, 0.f), a);
+        default: return x;
+    }
+}
+// derivative expressed through the OUTPUT y (all supported activations allow it)
+__device__ __forceinline__ float act_bwd_from_y(float y, int kind, float a) {
+    switch (kind) {
+        case GN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case GN_ACT_TANH: return 1.f - y * y;
+        case GN_ACT_SIGMOID: return y * (1.f - y);
+        case GN_ACT_LEAKY: return y >= 0.f ? 1.f : a;
+        case GN_ACT_RELU_MAX: return (y > 0.f && y < a) ? 1.f : 0.f;
+        default: return 1.f;
+    }
+}
+
+}  // namespace gn

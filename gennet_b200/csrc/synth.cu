@@ -1,0 +1,625 @@
+// Sample synthesis kernels: PSD-coloured noise, Tukey-windowed rFFT whitening, injection, crop.
+//
+// One CTA owns one time series end to end: the N-point real transforms are done as M=N/2-point
+// complex Stockham FFTs held in shared memory (radix-16 register butterflies, M/16 threads,
+// 16 points per thread), so a series is read from HBM once and written once.
+//   gn_whiten_td_f32 : window -> rfft -> x weights -> irfft -> crop -> scale
+//   gn_irfft_f32     : x weights -> irfft -> roll -> scale
+//   gn_synth_f32     : normals x amp -> irfft (coloured noise) -> + template -> whiten_td -> crop -> scale
+// Reference arithmetic: BBH_version/gw_template_maker.py:161-193 (gen_noise), :243-286 (whiten_data),
+// :695 (crop), :813-814 (norm constant).  Algorithmic HBM bytes per series: 8N (whiten), 8N+4L (synth,
+// normals fed in), 4N+4L (synth, Philox normals).
+#include "gn_common.cuh"
+#include "philox.cuh"
+
+#include <math.h>
+#include <vector>
+
+struct gn_fft_plan {
+    int N;
+    int log2M;
+    float2* tw;  // device, exp(-2*pi*i*j/N), j in [0,N)
+};
+
+namespace gn {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by exp(DIR*i*pi/2): DIR<0 -> -i, DIR>0 -> +i
+template <int DIR>
+__device__ __forceinline__ float2 mul_wi(float2 a) {
+    return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+
+template <int DIR>
+__device__ __forceinline__ void fft2(float2& a0, float2& a1) {
+    float2 t = a0;
+    a0 = cadd(t, a1);
+    a1 = csub(t, a1);
+}
+template <int DIR>
+__device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_wi<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+// In-register DFT of R points. After run(v), output bin r lives in v[out_reg(r)].
+template <int R, int DIR>
+struct Dft;
+
+template <int DIR>
+struct Dft<2, DIR> {
+    static __device__ __forceinline__ void run(float2* v) { fft2<DIR>(v[0], v[1]); }
+    static __device__ __forceinline__ constexpr int out_reg(int r) { return r; }
+};
+template <int DIR>
+struct Dft<4, DIR> {
+    static __device__ __forceinline__ void run(float2* v) { fft4<DIR>(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ constexpr int out_reg(int r) { return r; }
+};
+template <int DIR>
+struct Dft<8, DIR> {
+    static __device__ __forceinline__ void run(float2* v) {
+        const float h = 0.70710678118654752440f;
+        fft4<DIR>(v[0], v[2], v[4], v[6]);
+        fft4<DIR>(v[1], v[3], v[5], v[7]);
+        // v[2k1+1] *= W8^{k1}
+        v[3] = cmul(v[3], make_float2(h, DIR * h));
+        v[5] = mul_wi<DIR>(v[5]);
+        v[7] = cmul(v[7], make_float2(-h, DIR * h));
+        fft2<DIR>(v[0], v[1]);
+        fft2<DIR>(v[2], v[3]);
+        fft2<DIR>(v[4], v[5]);
+        fft2<DIR>(v[6], v[7]);
+    }
+    static __device__ __forceinline__ constexpr int out_reg(int r) { return r < 4 ? 2 * r : 2 * (r - 4) + 1; }
+};
+template <int DIR>
+struct Dft<16, DIR> {
+    static __device__ __forceinline__ void run(float2* v) {
+        const float h = 0.70710678118654752440f;
+        const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;  // cos, sin(pi/8)
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) fft4<DIR>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+        // v[4*k1+n2] *= W16^{n2*k1},  W16 = exp(DIR*2*pi*i/16)
+        v[5] = cmul(v[5], make_float2(c1, DIR * s1));    // 1
+        v[6] = cmul(v[6], make_float2(h, DIR * h));      // 2
+        v[7] = cmul(v[7], make_float2(s1, DIR * c1));    // 3
+        v[9] = cmul(v[9], make_float2(h, DIR * h));      // 2
+        v[10] = mul_wi<DIR>(v[10]);                      // 4
+        v[11] = cmul(v[11], make_float2(-h, DIR * h));   // 6
+        v[13] = cmul(v[13], make_float2(s1, DIR * c1));  // 3
+        v[14] = cmul(v[14], make_float2(-h, DIR * h));   // 6
+        v[15] = cmul(v[15], make_float2(-c1, -DIR * s1));  // 9
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) fft4<DIR>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+    }
+    // X[k1 + 4*k2] sits in v[4*k1 + k2]
+    static __device__ __forceinline__ constexpr int out_reg(int r) { return 4 * (r & 3) + (r >> 2); }
+};
+
+// shared-memory index with one pad slot per 16 complex values (kills the stride-R store conflicts)
+__device__ __forceinline__ int PADI(int i) { return i + (i >> 4); }
+
+// One Stockham pass of radix R over the M-point array; each thread owns 16/R butterflies (16 points).
+// LOAD(idx)->float2 fetches logical element idx of the pass input; STORE(idx, val) writes logical
+// element idx of the pass output. A __syncthreads separates the loads from the stores so that the
+// pass may run in place.
+template <int R, int DIR, int LOG2M, class LOAD, class STORE>
+__device__ __forceinline__ void fft_pass(int p, const float2* __restrict__ tw, int tw_stride_log2, LOAD load,
+                                         STORE store, bool sync_before_store) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int T = M / R;
+    constexpr int NT = M / 16;
+    constexpr int IT = 16 / R;
+    float2 v[IT][R];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int i = tid + it * NT;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[it][r] = load(i + r * T);
+        if (p > 1) {
+            const int k = i & (p - 1);
+            // exp(DIR*2*pi*i*r*k/(p*R)) = tw_M[r*k*M/(p*R)], tw_M[j] = tw_N[2j]
+            const int step = (M / R) / p;
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                float2 w = __ldg(&tw[(size_t)(r * k * step) << tw_stride_log2]);
+                if (DIR > 0) w.y = -w.y;
+                v[it][r] = cmul(v[it][r], w);
+            }
+        }
+        Dft<R, DIR>::run(v[it]);
+    }
+    if (sync_before_store) __syncthreads();
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int i = tid + it * NT;
+        const int k = i & (p - 1);
+        const int base = (i - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) store(base + r * p, v[it][Dft<R, DIR>::out_reg(r)]);
+    }
+}
+
+// remainder radix so that M = REM * 16^a
+template <int LOG2M>
+struct Plan {
+    static constexpr int REM = 1 << (LOG2M & 3);
+    static constexpr int N16 = LOG2M >> 2;
+};
+
+// Full M-point complex FFT.  first_load reads the logical input; the result ends in smem `buf`
+// (padded natural order) unless last_store is used for the final pass (LAST_TO_CUSTOM).
+template <int DIR, int LOG2M, class LOAD0, class STOREL>
+__device__ __forceinline__ void fft_full(float2* buf, const float2* __restrict__ tw, LOAD0 first_load,
+                                         bool first_from_smem, STOREL last_store, bool last_custom) {
+    constexpr int REM = Plan<LOG2M>::REM;
+    constexpr int N16 = Plan<LOG2M>::N16;
+    auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
+    auto sm_store = [&](int idx, float2 val) { buf[PADI(idx)] = val; };
+    int p = 1;
+    bool first = true;
+    if (REM > 1) {
+        // a REM pass is never the last one (N16 >= 1 for every supported size)
+        fft_pass<(REM > 1 ? REM : 2), DIR, LOG2M>(p, tw, 1, first_load, sm_store, first_from_smem);
+        __syncthreads();
+        p *= REM;
+        first = false;
+    }
+#pragma unroll
+    for (int j = 0; j < N16; ++j) {
+        const bool last = (j == N16 - 1);
+        if (first) {
+            if (last && last_custom)
+                fft_pass<16, DIR, LOG2M>(p, tw, 1, first_load, last_store, first_from_smem);
+            else
+                fft_pass<16, DIR, LOG2M>(p, tw, 1, first_load, sm_store, first_from_smem);
+        } else {
+            if (last && last_custom)
+                fft_pass<16, DIR, LOG2M>(p, tw, 1, sm_load, last_store, false);
+            else
+                fft_pass<16, DIR, LOG2M>(p, tw, 1, sm_load, sm_store, true);
+        }
+        if (!(last && last_custom)) __syncthreads();
+        p *= 16;
+        first = false;
+    }
+}
+
+// rfft-of-packed post-processing, spectral weighting and irfft pre-processing for the pair (k, M-k):
+// in: Z = FFT_M(x[2n] + i x[2n+1]); out: Z' with IFFT_M(Z') = y[2n] + i y[2n+1], y = irfft(rfft(x)*w)*M
+template <int LOG2M>
+__device__ __forceinline__ void whiten_pointwise(float2* buf, const float2* __restrict__ tw,
+                                                 const float* __restrict__ wts) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int NT = M / 16;
+    for (int k = threadIdx.x; k <= M / 2; k += NT) {
+        if (k == 0) {
+            float2 z = buf[0];
+            float y0 = __ldg(&wts[0]) * (z.x + z.y);
+            float yM = __ldg(&wts[M]) * (z.x - z.y);
+            buf[0] = make_float2(0.5f * (y0 + yM), 0.5f * (y0 - yM));
+            continue;
+        }
+        const int mk = M - k;
+        float2 zk = buf[PADI(k)], zm = buf[PADI(mk)];
+        // A = (Zk + conj(Zm))/2 ; O = (Zk - conj(Zm))/(2i)
+        float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        float2 t = __ldg(&tw[k]);  // exp(-2*pi*i*k/N)
+        float2 Bt = cmul(t, O);
+        float wk = __ldg(&wts[k]), wm = __ldg(&wts[mk]);
+        float2 P = cscale(cadd(A, Bt), wk);   // Y[k]
+        float2 Q = cscale(csub(A, Bt), wm);   // conj(Y[M-k])
+        float2 E = cscale(cadd(P, Q), 0.5f);
+        float2 Op = cmul(cconj(t), cscale(csub(P, Q), 0.5f));
+        // Z'[k] = E + i*Op ; Z'[M-k] = conj(E) + i*conj(Op)
+        buf[PADI(k)] = make_float2(E.x - Op.y, E.y + Op.x);
+        buf[PADI(mk)] = make_float2(E.x + Op.y, -E.y + Op.x);
+    }
+}
+
+// irfft pre-processing from an explicit half spectrum Y[0..M] (weights applied on load).
+template <int LOG2M, class SPEC>
+__device__ __forceinline__ void irfft_pre(float2* buf, const float2* __restrict__ tw, SPEC Y, bool drop_dc) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int NT = M / 16;
+    for (int k = threadIdx.x; k <= M / 2; k += NT) {
+        if (k == 0) {
+            float y0 = drop_dc ? 0.f : Y(0).x;
+            float yM = Y(M).x;
+            buf[0] = make_float2(0.5f * (y0 + yM), 0.5f * (y0 - yM));
+            continue;
+        }
+        const int mk = M - k;
+        float2 P = Y(k), Q = cconj(Y(mk));
+        float2 t = __ldg(&tw[k]);
+        float2 E = cscale(cadd(P, Q), 0.5f);
+        float2 Op = cmul(cconj(t), cscale(csub(P, Q), 0.5f));
+        buf[PADI(k)] = make_float2(E.x - Op.y, E.y + Op.x);
+        buf[PADI(mk)] = make_float2(E.x + Op.y, -E.y + Op.x);
+    }
+}
+
+// resident CTAs per SM the register allocator must allow (<= ~85 registers per thread)
+#define GN_SYNTH_MINB(L2) (((1 << (L2)) / 16) >= 512 ? 1 : (65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * 80) > 8 ? 8 : 65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * 80)))
+constexpr int MODE_WHITEN = 0, MODE_IRFFT = 1, MODE_SYNTH = 2;
+
+struct SynthArgs {
+    const float* x;          // WHITEN: (batch,N) input; IRFFT: (batch,Nf) complex; SYNTH: normals (batch,2,Nf) or null
+    const float* amp;        // SYNTH: (Nf)
+    const float* templates;  // SYNTH: (n_templates,N) or null
+    const int* tidx;         // SYNTH: (batch) or null
+    const float* window;     // (N)
+    const float* weights;    // (Nf) (IRFFT: may be null)
+    float* y;
+    const float2* tw;
+    int batch, n_templates, crop_lo, crop_len, roll, drop_dc;
+    float noise_scale, out_scale;
+    unsigned long long seed, sample_offset;
+};
+
+template <int LOG2M, int MODE>
+__global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth_kernel(SynthArgs a) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int N = 2 * M;
+    constexpr int Nf = M + 1;
+    extern __shared__ float2 buf[];  // PADI(M) complex
+    const float2* __restrict__ tw = a.tw;
+
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        // output of the final inverse pass: packed (y[2j], y[2j+1]) at logical index j
+        float* __restrict__ yb = a.y + (size_t)b * (MODE == MODE_IRFFT ? N : a.crop_len);
+        const float oscale = a.out_scale;
+        auto out_store = [&](int j, float2 val) {
+            if (MODE == MODE_IRFFT) {
+                int n0 = (2 * j + a.roll) & (N - 1);
+                if ((a.roll & 1) == 0) {
+                    *reinterpret_cast<float2*>(yb + n0) = make_float2(val.x * oscale, val.y * oscale);
+                } else {
+                    yb[n0] = val.x * oscale;
+                    yb[(n0 + 1) & (N - 1)] = val.y * oscale;
+                }
+            } else {
+                int n0 = 2 * j - a.crop_lo;
+                if (((a.crop_lo | a.crop_len) & 1) == 0) {
+                    if (n0 >= 0 && n0 < a.crop_len) {
+                        if (n0 + 1 < a.crop_len)
+                            *reinterpret_cast<float2*>(yb + n0) = make_float2(val.x * oscale, val.y * oscale);
+                        else
+                            yb[n0] = val.x * oscale;
+                    }
+                } else {
+                    if (n0 >= 0 && n0 < a.crop_len) yb[n0] = val.x * oscale;
+                    if (n0 + 1 >= 0 && n0 + 1 < a.crop_len) yb[n0 + 1] = val.y * oscale;
+                }
+            }
+        };
+
+        if (MODE == MODE_IRFFT) {
+            const float2* __restrict__ xf = reinterpret_cast<const float2*>(a.x) + (size_t)b * Nf;
+            const float* __restrict__ w = a.weights;
+            auto spec = [&](int k) {
+                float2 v = __ldg(&xf[k]);
+                float s = w ? __ldg(&w[k]) : 1.f;
+                return make_float2(v.x * s, v.y * s);
+            };
+            irfft_pre<LOG2M>(buf, tw, spec, a.drop_dc != 0);
+            __syncthreads();
+            auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
+            fft_full<+1, LOG2M>(buf, tw, sm_load, true, out_store, true);
+            __syncthreads();
+            continue;
+        }
+
+        if (MODE == MODE_SYNTH) {
+            // coloured noise: Y[k] = amp[k]*(re[k] + i*im[k]), DC dropped (gen_noise :187-190)
+            const float* __restrict__ amp = a.amp;
+            if (a.x != nullptr) {
+                const float* __restrict__ nre = a.x + (size_t)b * 2 * Nf;
+                const float* __restrict__ nim = nre + Nf;
+                auto spec = [&](int k) {
+                    float s = __ldg(&amp[k]);
+                    return make_float2(__ldg(&nre[k]) * s, __ldg(&nim[k]) * s);
+                };
+                irfft_pre<LOG2M>(buf, tw, spec, true);
+            } else {
+                const unsigned long long sample = a.sample_offset + (unsigned long long)b;
+                auto spec = [&](int k) {
+                    float2 g = philox_normal2(a.seed, sample, (unsigned)k);
+                    float s = __ldg(&amp[k]);
+                    return make_float2(g.x * s, g.y * s);
+                };
+                irfft_pre<LOG2M>(buf, tw, spec, true);
+            }
+            __syncthreads();
+            auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
+            auto sm_store = [&](int idx, float2 val) { buf[PADI(idx)] = val; };
+            fft_full<+1, LOG2M>(buf, tw, sm_load, true, sm_store, false);
+            // fft_full ends with a __syncthreads when the last pass goes to smem
+        }
+
+        // forward transform of window * (noise + template | input)
+        {
+            const float* __restrict__ src = nullptr;
+            if (MODE == MODE_WHITEN) {
+                src = a.x + (size_t)b * N;
+            } else if (a.templates != nullptr) {
+                int t = a.tidx ? __ldg(&a.tidx[b]) : b;
+                t = min(max(t, 0), a.n_templates - 1);
+                src = a.templates + (size_t)t * N;
+            }
+            const float2* __restrict__ win2 = reinterpret_cast<const float2*>(a.window);
+            const float2* __restrict__ src2 = reinterpret_cast<const float2*>(src);
+            const float nscale = a.noise_scale;
+            auto first_load = [&](int idx) {
+                float2 v = make_float2(0.f, 0.f);
+                if (MODE == MODE_SYNTH) {
+                    float2 n = buf[PADI(idx)];
+                    v = make_float2(n.x * nscale, n.y * nscale);
+                }
+                if (src2 != nullptr) {
+                    float2 s = __ldg(&src2[idx]);
+                    v.x += s.x;
+                    v.y += s.y;
+                }
+                float2 w = __ldg(&win2[idx]);
+                return make_float2(v.x * w.x, v.y * w.y);
+            };
+            auto sm_store = [&](int idx, float2 val) { buf[PADI(idx)] = val; };
+            fft_full<-1, LOG2M>(buf, tw, first_load, MODE == MODE_SYNTH, sm_store, false);
+        }
+        whiten_pointwise<LOG2M>(buf, tw, a.weights);
+        __syncthreads();
+        {
+            auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
+            fft_full<+1, LOG2M>(buf, tw, sm_load, true, out_store, true);
+        }
+        __syncthreads();
+    }
+}
+
+template <int MODE>
+static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
+    a.tw = plan->tw;
+    const int M = plan->N / 2;
+    const size_t smem = (size_t)(M + (M >> 4) + 1) * sizeof(float2);
+    const int threads = M / 16;
+    int grid = a.batch;
+#define GN_SYNTH_CASE(L2)                                                                                   \
+    case L2: {                                                                                              \
+        auto kfn = synth_kernel<L2, MODE>;                                                                  \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kfn<<<grid, threads, smem, st>>>(a);                                                                \
+        break;                                                                                              \
+    }
+    switch (plan->log2M) {
+        GN_SYNTH_CASE(8)
+        GN_SYNTH_CASE(9)
+        GN_SYNTH_CASE(10)
+        GN_SYNTH_CASE(11)
+        GN_SYNTH_CASE(12)
+        GN_SYNTH_CASE(13)
+        GN_SYNTH_CASE(14)
+        default:
+            return fail(GN_ERR_UNSUPPORTED, "synth: unsupported FFT length N=%s%lld", "", plan->N);
+    }
+#undef GN_SYNTH_CASE
+    return cuda_status("synth_kernel");
+}
+
+__global__ void mean_std_kernel(const float* __restrict__ x, long long n, float* out) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i];
+    double tot = block_sum(s, sm);
+    __shared__ double mean_s;
+    if (threadIdx.x == 0) mean_s = tot / (double)n;
+    __syncthreads();
+    const double mean = mean_s;
+    double q = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        double d = (double)x[i] - mean;
+        q += d * d;
+    }
+    double qt = block_sum(q, sm);
+    if (threadIdx.x == 0) {
+        out[0] = (float)mean;
+        out[1] = (float)sqrt(qt / (double)n);
+    }
+}
+
+__global__ void add_scaled_kernel(float* __restrict__ x, const float* __restrict__ r, float sigma, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) x[i] = fmaf(sigma, r[i], x[i]);
+}
+
+__global__ void burst_kernel(const float* __restrict__ pars, float* __restrict__ out, int n, int N, float amp,
+                             float freq, float dt, float phi) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * N) return;
+    int s = (int)(i / N), j = (int)(i - (long long)s * N);
+    // double precision: the reference evaluates this in float64 (burstMahoGANy.py:90-93) and the phase
+    // 2*pi*f*(t-t0) reaches ~300 rad, where float32 sin would lose 1e-5
+    double t0 = pars[2 * s], tau = pars[2 * s + 1];
+    double t = (double)dt * j - t0;
+    out[i] = (float)((double)amp * sin(2.0 * 3.14159265358979323846 * (double)freq * t + (double)phi) *
+                     exp(-(t * t) / (tau * tau)));
+}
+
+
+// gen_bbh tail (gw_template_maker.py:528-571): ref_idx = argmax(hp^2+hc^2) (first maximum), ht = Fp*hp + Fc*hc,
+// ts[:len] = ht[ref_idx-idx-lead:] with Python's negative-start semantics, ts *= win, then crop + scale.
+__global__ void __launch_bounds__(256) bbh_assemble_kernel(const float* __restrict__ hp, const float* __restrict__ hc,
+                                                           const float* __restrict__ Fp, const float* __restrict__ Fc,
+                                                           const int* __restrict__ idx, int lead,
+                                                           const float* __restrict__ win, float* __restrict__ out,
+                                                           int* __restrict__ ref_out, int N, int crop_lo, int crop_len,
+                                                           float scale) {
+    __shared__ float sv[256];
+    __shared__ int si[256];
+    const int b = blockIdx.x;
+    const float* p = hp + (size_t)b * N;
+    const float* c = hc + (size_t)b * N;
+    float best = -1.f;
+    int bi = 0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float v = p[j] * p[j] + c[j] * c[j];
+        if (v > best) { best = v; bi = j; }
+    }
+    sv[threadIdx.x] = best;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            float v2 = sv[threadIdx.x + o];
+            int i2 = si[threadIdx.x + o];
+            if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+                sv[threadIdx.x] = v2;
+                si[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    const int ref = si[0];
+    if (threadIdx.x == 0 && ref_out != nullptr) ref_out[b] = ref;
+    int start = ref - idx[b] - lead;
+    int s0 = start >= 0 ? start : (start < -N ? 0 : N + start);
+    if (s0 > N) s0 = N;
+    const float fp = Fp[b], fc = Fc[b];
+    float* o = out + (size_t)b * crop_len;
+    for (int j = threadIdx.x; j < crop_len; j += blockDim.x) {
+        int t = crop_lo + j;
+        int src = s0 + t;
+        float v = 0.f;
+        if (src < N) v = (fp * p[src] + fc * c[src]) * win[t];
+        o[j] = v * scale;
+    }
+}
+
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
+    GN_REQUIRE(out != nullptr, "plan pointer is null");
+    GN_REQUIRE(N >= 512 && N <= 32768 && (N & (N - 1)) == 0, "N must be a power of two in [512, 32768]");
+    gn_fft_plan* p = new gn_fft_plan;
+    p->N = N;
+    int l = 0;
+    while ((1 << l) < N / 2) ++l;
+    p->log2M = l;
+    std::vector<float2> h(N);
+    for (int j = 0; j < N; ++j) {
+        double ang = -2.0 * 3.14159265358979323846264338327950288 * (double)j / (double)N;
+        h[j] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    if (cudaMalloc(&p->tw, sizeof(float2) * N) != cudaSuccess) {
+        delete p;
+        return cuda_status("gn_fft_plan_create(cudaMalloc)") == GN_OK ? GN_ERR_CUDA : GN_ERR_CUDA;
+    }
+    if (cudaMemcpy(p->tw, h.data(), sizeof(float2) * N, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(p->tw);
+        delete p;
+        cuda_status("gn_fft_plan_create(cudaMemcpy)");
+        return GN_ERR_CUDA;
+    }
+    *out = p;
+    return GN_OK;
+}
+
+extern "C" int gn_fft_plan_destroy(gn_fft_plan* p) {
+    if (p == nullptr) return GN_OK;
+    cudaFree(p->tw);
+    delete p;
+    return GN_OK;
+}
+
+extern "C" int gn_whiten_td_f32(const gn_fft_plan* plan, const float* x, const float* window, const float* weights,
+                                float* y, int batch, int crop_lo, int crop_len, float scale, void* stream) {
+    GN_REQUIRE(plan && x && window && weights && y, "null pointer");
+    GN_REQUIRE(batch >= 0, "batch < 0");
+    GN_REQUIRE(crop_lo >= 0 && crop_len > 0 && crop_lo + crop_len <= plan->N, "crop window outside the series");
+    if (batch == 0) return GN_OK;
+    SynthArgs a{};
+    a.x = x; a.window = window; a.weights = weights; a.y = y; a.batch = batch;
+    a.crop_lo = crop_lo; a.crop_len = crop_len; a.out_scale = scale / (float)(plan->N / 2);
+    return launch_synth<MODE_WHITEN>(plan, a, as_stream(stream));
+}
+
+extern "C" int gn_irfft_f32(const gn_fft_plan* plan, const float* xf, const float* weights, float* y, int batch,
+                            float scale, int roll, int drop_dc, void* stream) {
+    GN_REQUIRE(plan && xf && y, "null pointer");
+    GN_REQUIRE(batch >= 0, "batch < 0");
+    if (batch == 0) return GN_OK;
+    SynthArgs a{};
+    a.x = xf; a.weights = weights; a.y = y; a.batch = batch; a.drop_dc = drop_dc;
+    a.roll = ((roll % plan->N) + plan->N) % plan->N;
+    a.out_scale = scale / (float)(plan->N / 2);
+    return launch_synth<MODE_IRFFT>(plan, a, as_stream(stream));
+}
+
+extern "C" int gn_synth_f32(const gn_fft_plan* plan, const float* normals, const float* amp, const float* templates,
+                            const int* tidx, const float* window, const float* weights, float* out, int batch,
+                            int n_templates, int crop_lo, int crop_len, float noise_scale, float out_scale,
+                            uint64_t seed, uint64_t sample_offset, void* stream) {
+    GN_REQUIRE(plan && amp && window && weights && out, "null pointer");
+    GN_REQUIRE(batch >= 0, "batch < 0");
+    GN_REQUIRE(templates == nullptr || n_templates > 0, "n_templates must be > 0 when templates are given");
+    GN_REQUIRE(crop_lo >= 0 && crop_len > 0 && crop_lo + crop_len <= plan->N, "crop window outside the series");
+    if (batch == 0) return GN_OK;
+    SynthArgs a{};
+    a.x = normals; a.amp = amp; a.templates = templates; a.tidx = tidx; a.window = window; a.weights = weights;
+    a.y = out; a.batch = batch; a.n_templates = n_templates; a.crop_lo = crop_lo; a.crop_len = crop_len;
+    // irfft of the noise spectrum: unnormalised inverse / M ; gen_noise multiplies by N*df (= noise_scale)
+    a.noise_scale = noise_scale / (float)(plan->N / 2);
+    a.out_scale = out_scale / (float)(plan->N / 2);
+    a.seed = seed; a.sample_offset = sample_offset;
+    return launch_synth<MODE_SYNTH>(plan, a, as_stream(stream));
+}
+
+extern "C" int gn_mean_std_f32(const float* x, long long n, float* out, void* stream) {
+    GN_REQUIRE(x && out && n > 0, "null pointer or n <= 0");
+    mean_std_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, out);
+    return cuda_status("mean_std_kernel");
+}
+
+extern "C" int gn_add_scaled_f32(float* x, const float* r, float sigma, long long n, void* stream) {
+    GN_REQUIRE(x && r && n >= 0, "null pointer or n < 0");
+    if (n == 0) return GN_OK;
+    int grid = (int)((n + 255) / 256 < (long long)num_sms() * 8 ? (n + 255) / 256 : (long long)num_sms() * 8);
+    add_scaled_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, r, sigma, n);
+    return cuda_status("add_scaled_kernel");
+}
+
+extern "C" int gn_burst_waveforms_f32(const float* pars, float* out, int n, int N, float amp, float freq, float dt,
+                                      float phi, void* stream) {
+    GN_REQUIRE(pars && out && n >= 0 && N > 0, "null pointer or bad size");
+    if (n == 0) return GN_OK;
+    long long tot = (long long)n * N;
+    burst_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(pars, out, n, N, amp, freq, dt, phi);
+    return cuda_status("burst_kernel");
+}
+
+extern "C" int gn_bbh_assemble_f32(const float* hp, const float* hc, const float* Fp, const float* Fc, const int* idx,
+                                   int lead, const float* win, float* out, int* ref_idx, int batch, int N, int crop_lo,
+                                   int crop_len, float scale, void* stream) {
+    GN_REQUIRE(hp && hc && Fp && Fc && idx && win && out, "null pointer");
+    GN_REQUIRE(batch >= 0 && N > 0, "bad size");
+    GN_REQUIRE(crop_lo >= 0 && crop_len > 0 && crop_lo + crop_len <= N, "crop window outside the series");
+    if (batch == 0) return GN_OK;
+    bbh_assemble_kernel<<<batch, 256, 0, as_stream(stream)>>>(hp, hc, Fp, Fc, idx, lead, win, out, ref_idx, N, crop_lo,
+                                                             crop_len, scale);
+    return cuda_status("bbh_assemble_kernel");
+}

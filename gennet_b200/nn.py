@@ -1,0 +1,1103 @@
+"""Host-side mirror of the Keras object protocol the reference scripts use.
+
+Same class / function names, argument meaning and return shapes as Keras 2.2.4 so that
+``bbhMahoGANy.py``-style code (``Sequential().add(Dense(...))``, functional ``Model(inputs, outputs)``,
+``compile`` / ``train_on_batch`` / ``predict`` / ``save_weights``) runs unchanged, but every layer's
+forward, backward and optimizer update is a hand-written sm_100a kernel reached through the C ABI
+(``include/gennet_b200.h``).  There is no autograd and no CPU path: backward is explicit.
+
+Layout: activations are channels-last float32 CUDA tensors (B, L, C); parameters of a compiled model
+live in one flat arena (weights / gradients / Adam moments) so the optimizer step is one launch and a
+data-parallel gradient all-reduce is one NCCL call.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+# ----------------------------------------------------------------------------- session state
+_NAME_COUNTS = {}
+_STATE = {'seed': 1234, 'noise_counter': 0, 'init_rng': np.random.RandomState(1234), 'dp': None}
+
+
+def clear_session():
+    _NAME_COUNTS.clear()
+
+
+def set_seed(seed):
+    """Seed for weight initialisation (host MT19937, as Keras) and the device Philox streams."""
+    _STATE['seed'] = int(seed)
+    _STATE['noise_counter'] = 0
+    _STATE['init_rng'] = np.random.RandomState(int(seed))
+
+
+def _uid(prefix):
+    _NAME_COUNTS[prefix] = _NAME_COUNTS.get(prefix, 0) + 1
+    return '%s_%d' % (prefix, _NAME_COUNTS[prefix])
+
+
+def device():
+    _lib.require_device()
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _empty(shape):
+    return torch.empty(shape, dtype=torch.float32, device=device())
+
+
+def _same_pad(L, k, s):
+    out = -(-L // s)
+    total = max((out - 1) * s + k - L, 0)
+    return total // 2, out
+
+
+_ACTS = {None: _lib.ACT_NONE, 'linear': _lib.ACT_NONE, 'relu': _lib.ACT_RELU, 'tanh': _lib.ACT_TANH,
+         'sigmoid': _lib.ACT_SIGMOID}
+
+
+class Param:
+    """A weight tensor + its gradient; both may be re-homed into a flat arena at compile()."""
+
+    def __init__(self, name, value, trainable=True):
+        self.name = name
+        self.trainable = trainable
+        self.data = torch.as_tensor(np.ascontiguousarray(value, dtype=np.float32)).to(device())
+        self.grad = None
+        self.arena = None
+        self.offset = 0
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    def numel(self):
+        return self.data.numel()
+
+
+class Ctx:
+    """Per-call execution context."""
+
+    def __init__(self, training, trainable_ids=None, noise=None):
+        self.training = training
+        self.trainable_ids = trainable_ids or set()
+        self.noise = noise if noise is not None else {}
+        dp = _STATE['dp']
+        self.world = dp.world if dp is not None else 1
+        self.dp = dp
+
+
+# ----------------------------------------------------------------------------- symbolic graph
+class KTensor:
+    def __init__(self, shape, node):
+        self.shape = tuple(shape)          # without the batch axis
+        self.node = node
+
+    @property
+    def _keras_shape(self):
+        return (None,) + self.shape
+
+
+class Node:
+    def __init__(self, layer, inputs):
+        self.layer = layer
+        self.inputs = inputs               # list of Nodes
+
+
+class Layer:
+    prefix = 'layer'
+
+    def __init__(self, name=None, input_shape=None, trainable=True, **kwargs):
+        self.name = name
+        self.trainable = trainable
+        self._input_shape_arg = tuple(input_shape) if input_shape is not None else None
+        self.params = []
+        self.built = False
+        self.input_shape = None
+        self.output_shape = None
+
+    # Keras-style properties
+    @property
+    def weights(self):
+        return self.params
+
+    @property
+    def trainable_weights(self):
+        return [p for p in self.params if p.trainable and self.trainable]
+
+    def get_weights(self):
+        return [p.data.detach().cpu().numpy().copy() for p in self.params]
+
+    def set_weights(self, ws):
+        assert len(ws) == len(self.params), '%s expects %d arrays' % (self.name, len(self.params))
+        for p, w in zip(self.params, ws):
+            w = np.asarray(w, dtype=np.float32)
+            assert tuple(w.shape) == p.shape, 'shape mismatch for %s: %s vs %s' % (p.name, w.shape, p.shape)
+            p.data.copy_(torch.from_numpy(np.ascontiguousarray(w)))
+
+    def count_params(self):
+        return sum(p.numel() for p in self.params)
+
+    def _ensure_built(self, in_shape):
+        if not self.built:
+            if self.name is None:
+                self.name = _uid(self.prefix)
+            self.input_shape = tuple(in_shape)
+            self.output_shape = tuple(self.build(tuple(in_shape)))
+            self.built = True
+        return self.output_shape
+
+    def build(self, in_shape):
+        return in_shape
+
+    def __call__(self, x):
+        out_shape = self._ensure_built(x.shape)
+        return KTensor(out_shape, Node(self, [x.node]))
+
+    def all_layers(self):
+        return [self]
+
+    def forward(self, x, ctx):
+        raise NotImplementedError
+
+    def backward(self, dy, ctx, need_dx=True):
+        raise NotImplementedError
+
+
+class InputLayer(Layer):
+    prefix = 'input'
+
+    def __init__(self, shape, name=None):
+        super().__init__(name=name)
+        self._ensure_built(tuple(shape))
+
+
+def Input(shape=None, name=None, **kwargs):
+    layer = InputLayer(tuple(shape), name=name)
+    return KTensor(tuple(shape), Node(layer, []))
+
+
+def _glorot(shape, fan_in, fan_out):
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return _STATE['init_rng'].uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+class Dense(Layer):
+    """Keras Dense: kernel (in, out), bias (out); y = act(x @ kernel + bias)."""
+    prefix = 'dense'
+
+    def __init__(self, units, activation=None, kernel_initializer='glorot_uniform', **kw):
+        super().__init__(**kw)
+        self.units = int(units)
+        self.activation = activation
+
+    def build(self, in_shape):
+        assert len(in_shape) == 1, 'Dense expects a flat input, got %s' % (in_shape,)
+        fin = in_shape[0]
+        self.params = [Param(self.name + '/kernel:0', _glorot((fin, self.units), fin, self.units)),
+                       Param(self.name + '/bias:0', np.zeros(self.units, np.float32))]
+        return (self.units,)
+
+    def forward(self, x, ctx):
+        B, K = x.shape
+        y = _empty((B, self.units))
+        call('gn_dense_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B, K,
+             self.units, _ACTS[self.activation], 0.0, stream())
+        self._x, self._y = x, y
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        x = self._x
+        B, K = x.shape
+        if _ACTS[self.activation] != _lib.ACT_NONE:
+            g = _empty(dy.shape)
+            call('gn_act_bwd_f32', ptr(dy), ptr(self._y), ptr(g), dy.numel(), _ACTS[self.activation], 0.0, stream())
+            dy = g
+        if id(self) in ctx.trainable_ids:
+            call('gn_dense_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad), ptr(self.params[1].grad), B, K,
+                 self.units, stream())
+        dx = None
+        if need_dx:
+            dx = _empty((B, K))
+            call('gn_dense_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, K, self.units, stream())
+        self._x = self._y = None
+        return dx
+
+
+class Conv1D(Layer):
+    """Keras Conv1D (channels_last): kernel (k, Cin, Cout), bias (Cout), 'valid' | 'same' (TF rule)."""
+    prefix = 'conv1d'
+
+    def __init__(self, filters, kernel_size, strides=1, padding='valid', activation=None,
+                 kernel_initializer='glorot_uniform', **kw):
+        super().__init__(**kw)
+        self.filters = int(filters)
+        self.k = int(kernel_size[0] if isinstance(kernel_size, (tuple, list)) else kernel_size)
+        self.s = int(strides[0] if isinstance(strides, (tuple, list)) else strides)
+        self.padding = padding
+        self.activation = activation
+        self.fused_up = 1        # set to 2 by Sequential when an UpSampling1D(2) directly precedes
+
+    def build(self, in_shape):
+        L, cin = in_shape
+        k = self.k
+        self.params = [Param(self.name + '/kernel:0', _glorot((k, cin, self.filters), k * cin, k * self.filters)),
+                       Param(self.name + '/bias:0', np.zeros(self.filters, np.float32))]
+        if self.padding == 'same':
+            self.pad, self.Lout = _same_pad(L, k, self.s)
+        else:
+            self.pad, self.Lout = 0, (L - k) // self.s + 1
+        return (self.Lout, self.filters)
+
+    def forward(self, x, ctx):
+        B = x.shape[0]
+        L, cin = self.input_shape
+        y = _empty((B, self.Lout, self.filters))
+        call('gn_conv1d_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B, L, cin,
+             self.Lout, self.filters, self.k, self.s, self.pad, self.fused_up, _ACTS[self.activation], 0.0, stream())
+        self._x, self._y = x, y
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        x = self._x
+        B = x.shape[0]
+        L, cin = self.input_shape
+        if _ACTS[self.activation] != _lib.ACT_NONE:
+            g = _empty(dy.shape)
+            call('gn_act_bwd_f32', ptr(dy), ptr(self._y), ptr(g), dy.numel(), _ACTS[self.activation], 0.0, stream())
+            dy = g
+        if id(self) in ctx.trainable_ids:
+            call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad), ptr(self.params[1].grad), B, L,
+                 cin, self.Lout, self.filters, self.k, self.s, self.pad, self.fused_up, stream())
+        dx = None
+        if need_dx:
+            dx = _empty(x.shape)
+            call('gn_conv1d_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, L, cin, self.Lout,
+                 self.filters, self.k, self.s, self.pad, self.fused_up, stream())
+        self._x = self._y = None
+        return dx
+
+
+class Conv2D(Layer):
+    """Keras Conv2D restricted to the reference's discriminator shape (bbhMahoGANy.py:439,447): input
+    (L, 2, C), kernel (kh, kw) with 'same' padding and strides (s, 1).  Because the width is 2, it is
+    executed as a Conv1D over L with 2C input and 2*filters output channels (only min(kw,3) of the kw
+    kernel columns ever touch data); the Keras kernel layout (kh, kw, Cin, Cout) is kept externally."""
+    prefix = 'conv2d'
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', kernel_initializer='glorot_uniform',
+                 **kw):
+        super().__init__(**kw)
+        self.filters = int(filters)
+        self.kh, self.kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        self.sh, self.sw = (strides, strides) if isinstance(strides, int) else tuple(strides)
+        self.padding = padding
+
+    def build(self, in_shape):
+        H, W, cin = in_shape
+        if not (W == 2 and self.padding == 'same' and self.sw == 1):
+            raise NotImplementedError('Conv2D is implemented for the reference discriminator geometry only '
+                                      '(width 2, padding same, width stride 1); got input %s' % (in_shape,))
+        kh, kw = self.kh, self.kw
+        self.params = [Param(self.name + '/kernel:0', _glorot((kh, kw, cin, self.filters), kh * kw * cin,
+                                                              kh * kw * self.filters)),
+                       Param(self.name + '/bias:0', np.zeros(self.filters, np.float32))]
+        self.pad, self.Lout = _same_pad(H, kh, self.sh)
+        self.pw = max(kw - 1, 0) // 2      # TF same: total = kw-1 (stride 1), left = total//2
+        return (self.Lout, 2, self.filters)
+
+    def _pack(self):
+        H, W, cin = self.input_shape
+        w1 = _empty((self.kh, 2 * cin, 2 * self.filters))
+        b1 = _empty((2 * self.filters,))
+        call('gn_conv2d_w2_pack_f32', ptr(self.params[0].data), ptr(self.params[1].data), ptr(w1), ptr(b1), self.kh,
+             self.kw, cin, self.filters, self.pw, stream())
+        return w1, b1
+
+    def forward(self, x, ctx):
+        B = x.shape[0]
+        H, W, cin = self.input_shape
+        w1, b1 = self._pack()
+        y = _empty((B, self.Lout, 2, self.filters))
+        call('gn_conv1d_fwd_f32', ptr(x), ptr(w1), ptr(b1), ptr(y), B, H, 2 * cin, self.Lout, 2 * self.filters,
+             self.kh, self.sh, self.pad, 1, _lib.ACT_NONE, 0.0, stream())
+        self._x, self._w1 = x, w1
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        x, w1 = self._x, self._w1
+        B = x.shape[0]
+        H, W, cin = self.input_shape
+        if id(self) in ctx.trainable_ids:
+            dw1 = _empty(w1.shape)
+            db1 = _empty((2 * self.filters,))
+            call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(dw1), ptr(db1), B, H, 2 * cin, self.Lout,
+                 2 * self.filters, self.kh, self.sh, self.pad, 1, stream())
+            call('gn_conv2d_w2_unpack_f32', ptr(dw1), ptr(db1), ptr(self.params[0].grad), ptr(self.params[1].grad),
+                 self.kh, self.kw, cin, self.filters, self.pw, stream())
+        dx = None
+        if need_dx:
+            dx = _empty(x.shape)
+            call('gn_conv1d_dgrad_f32', ptr(dy), ptr(w1), ptr(dx), B, H, 2 * cin, self.Lout, 2 * self.filters,
+                 self.kh, self.sh, self.pad, 1, stream())
+        self._x = self._w1 = None
+        return dx
+
+
+class BatchNormalization(Layer):
+    """Keras 2.2.4 BatchNormalization(axis=-1): gamma, beta, moving_mean, moving_variance."""
+    prefix = 'batch_normalization'
+
+    def __init__(self, momentum=0.99, epsilon=1e-3, axis=-1, **kw):
+        super().__init__(**kw)
+        assert axis == -1
+        self.momentum, self.epsilon = float(momentum), float(epsilon)
+
+    def build(self, in_shape):
+        c = in_shape[-1]
+        n = self.name
+        self.params = [Param(n + '/gamma:0', np.ones(c, np.float32)), Param(n + '/beta:0', np.zeros(c, np.float32)),
+                       Param(n + '/moving_mean:0', np.zeros(c, np.float32), trainable=False),
+                       Param(n + '/moving_variance:0', np.ones(c, np.float32), trainable=False)]
+        return in_shape
+
+    def forward(self, x, ctx):
+        C = x.shape[-1]
+        rows = x.numel() // C
+        g, b, mm, mv = [p.data for p in self.params]
+        y = _empty(x.shape)
+        if not ctx.training:
+            call('gn_bn_apply_f32', ptr(x), ptr(mm), ptr(mv), ptr(g), ptr(b), ptr(y), rows, C, self.epsilon, 1,
+                 stream())
+            return y
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        stats = _empty((2 * C,))
+        n_total = float(rows * ctx.world)
+        call('gn_bn_stats_f32', ptr(x), rows, C, ptr(sums, torch.float64), None, stream())
+        if ctx.world > 1:
+            ctx.dp.all_reduce(sums)
+        call('gn_bn_finalize_f32', ptr(sums, torch.float64), None, n_total, C, self.epsilon, self.momentum,
+             ptr(stats), None, None, 0, stream())
+        call('gn_bn_stats_f32', ptr(x), rows, C, ptr(sums, torch.float64), ptr(stats), stream())
+        if ctx.world > 1:
+            ctx.dp.all_reduce(sums)
+        call('gn_bn_finalize_f32', None, ptr(sums[C:], torch.float64), n_total, C, self.epsilon, self.momentum,
+             ptr(stats), ptr(mm), ptr(mv), 1, stream())
+        call('gn_bn_apply_f32', ptr(x), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), ptr(y), rows, C,
+             self.epsilon, 0, stream())
+        self._x, self._stats, self._n = x, stats, n_total
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        x, stats = self._x, self._stats
+        C = x.shape[-1]
+        rows = x.numel() // C
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        call('gn_bn_bwd_sums_f32', ptr(x), ptr(dy), ptr(stats), rows, C, ptr(sums, torch.float64), stream())
+        if ctx.world > 1:
+            ctx.dp.all_reduce(sums)
+        dx = _empty(x.shape)
+        tr = id(self) in ctx.trainable_ids
+        # dgamma/dbeta written here are GLOBAL sums when data-parallel: scale so the later
+        # gradient all-reduce(sum) does not count them world times
+        call('gn_bn_bwd_apply_f32', ptr(x), ptr(dy), ptr(stats), ptr(self.params[0].data), ptr(sums, torch.float64),
+             self._n, ptr(dx), ptr(self.params[0].grad) if tr else None, ptr(self.params[1].grad) if tr else None,
+             rows, C, stream())
+        if tr and ctx.world > 1:
+            self.params[0].grad.mul_(1.0 / ctx.world)
+            self.params[1].grad.mul_(1.0 / ctx.world)
+        self._x = self._stats = None
+        return dx
+
+
+class _ActLayer(Layer):
+    code, param = _lib.ACT_NONE, 0.0
+
+    def forward(self, x, ctx):
+        if self.code == _lib.ACT_NONE:
+            return x
+        y = _empty(x.shape)
+        call('gn_act_fwd_f32', ptr(x), ptr(y), x.numel(), self.code, self.param, stream())
+        self._y = y
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        if self.code == _lib.ACT_NONE or not need_dx:
+            return dy
+        dx = _empty(dy.shape)
+        call('gn_act_bwd_f32', ptr(dy), ptr(self._y), ptr(dx), dy.numel(), self.code, self.param, stream())
+        self._y = None
+        return dx
+
+
+class Activation(_ActLayer):
+    prefix = 'activation'
+
+    def __init__(self, activation, **kw):
+        super().__init__(**kw)
+        self.activation = activation
+        self.code = _ACTS[activation]
+
+
+class LeakyReLU(_ActLayer):
+    prefix = 'leaky_re_lu'
+
+    def __init__(self, alpha=0.3, **kw):
+        super().__init__(**kw)
+        self.code, self.param = _lib.ACT_LEAKY, float(alpha)
+
+
+class ReLU(_ActLayer):
+    prefix = 're_lu'
+
+    def __init__(self, max_value=None, **kw):
+        super().__init__(**kw)
+        if max_value is None:
+            self.code = _lib.ACT_RELU
+        else:
+            self.code, self.param = _lib.ACT_RELU_MAX, float(max_value)
+
+
+class _NoiseLayer(Layer):
+    """Dropout family; active only in training mode.  The random tensor comes from ``ctx.noise[name]``
+    when a caller feeds it (parity tests), else from the device Philox stream."""
+    kind = _lib.NOISE_DROPOUT
+
+    def __init__(self, rate, **kw):
+        super().__init__(**kw)
+        self.rate = float(rate)
+
+    def forward(self, x, ctx):
+        if not ctx.training:
+            self._r = None
+            return x
+        fed = ctx.noise.get(self.name)
+        if fed is not None:
+            r = torch.as_tensor(np.ascontiguousarray(fed, dtype=np.float32)).to(x.device).reshape(x.shape).contiguous()
+        else:
+            r = _empty(x.shape)
+            n = x.numel()
+            off = _STATE['noise_counter']
+            _STATE['noise_counter'] += (n + 3) // 4 * 4
+            rank_off = (ctx.dp.rank << 48) if ctx.dp is not None else 0
+            call('gn_noise_draw_f32', ptr(r), n, self.kind, self.rate, _STATE['seed'], off + rank_off, stream())
+        y = _empty(x.shape)
+        call('gn_noise_fwd_f32', ptr(x), ptr(r), ptr(y), x.numel(), self.kind, self.rate, stream())
+        self._r = r
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        if self._r is None or not need_dx:
+            return dy
+        dx = _empty(dy.shape)
+        call('gn_noise_bwd_f32', ptr(dy), ptr(self._r), ptr(dx), dy.numel(), self.kind, self.rate, stream())
+        self._r = None
+        return dx
+
+
+class Dropout(_NoiseLayer):
+    prefix = 'dropout'
+    kind = _lib.NOISE_DROPOUT
+
+
+class GaussianDropout(_NoiseLayer):
+    prefix = 'gaussian_dropout'
+    kind = _lib.NOISE_GDROPOUT
+
+
+class GaussianNoise(_NoiseLayer):
+    prefix = 'gaussian_noise'
+    kind = _lib.NOISE_GNOISE
+
+
+class Reshape(Layer):
+    prefix = 'reshape'
+
+    def __init__(self, target_shape, **kw):
+        super().__init__(**kw)
+        self.target = tuple(target_shape)
+
+    def build(self, in_shape):
+        n = int(np.prod(in_shape))
+        t = list(self.target)
+        if -1 in t:
+            t[t.index(-1)] = n // int(-np.prod(t))
+        assert int(np.prod(t)) == n, 'cannot reshape %s to %s' % (in_shape, self.target)
+        return tuple(t)
+
+    def forward(self, x, ctx):
+        return x.reshape((x.shape[0],) + self.output_shape)
+
+    def backward(self, dy, ctx, need_dx=True):
+        return dy.reshape((dy.shape[0],) + self.input_shape)
+
+
+class Flatten(Reshape):
+    prefix = 'flatten'
+
+    def __init__(self, **kw):
+        Layer.__init__(self, **kw)
+
+    def build(self, in_shape):
+        return (int(np.prod(in_shape)),)
+
+
+class UpSampling1D(Layer):
+    prefix = 'up_sampling1d'
+
+    def __init__(self, size=2, **kw):
+        super().__init__(**kw)
+        self.size = int(size)
+        self.fused = False       # True when the following Conv1D reads through the upsampling
+
+    def build(self, in_shape):
+        return (in_shape[0] * self.size, in_shape[1])
+
+    def forward(self, x, ctx):
+        if self.fused:
+            return x
+        B, L, C = x.shape
+        y = _empty((B, L * self.size, C))
+        call('gn_upsample1d_fwd_f32', ptr(x), ptr(y), B, L, C, self.size, stream())
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        if self.fused:
+            return dy
+        B = dy.shape[0]
+        L, C = self.input_shape
+        dx = _empty((B, L, C))
+        call('gn_upsample1d_bwd_f32', ptr(dy), ptr(dx), B, L, C, self.size, stream())
+        return dx
+
+
+class MaxPooling1D(Layer):
+    prefix = 'max_pooling1d'
+
+    def __init__(self, pool_size=2, **kw):
+        super().__init__(**kw)
+        self.pool = int(pool_size)
+
+    def build(self, in_shape):
+        return (in_shape[0] // self.pool, in_shape[1])
+
+    def forward(self, x, ctx):
+        B, L, C = x.shape
+        y = _empty((B, L // self.pool, C))
+        call('gn_maxpool1d_fwd_f32', ptr(x), ptr(y), B, L, C, self.pool, stream())
+        self._x, self._y = x, y
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        x = self._x
+        B, L, C = x.shape
+        dx = _empty(x.shape)
+        call('gn_maxpool1d_bwd_f32', ptr(x), ptr(self._y), ptr(dy), ptr(dx), B, L, C, self.pool, stream())
+        self._x = self._y = None
+        return dx
+
+
+class StackResidual(Layer):
+    """bbhMahoGANy.py:164-188 ``MyLayer``: stack([x, const - x], axis=2) -> (B, n_pix, 2, 1)."""
+    prefix = 'my_layer'
+
+    def __init__(self, const, **kw):
+        super().__init__(**kw)
+        self._const_host = np.asarray(const, dtype=np.float32)
+
+    def build(self, in_shape):
+        L = in_shape[0]
+        self.const = torch.from_numpy(np.ascontiguousarray(self._const_host.reshape(L))).to(device())
+        return (L, 2, 1)
+
+    def forward(self, x, ctx):
+        B = x.shape[0]
+        L = self.input_shape[0]
+        y = _empty((B, L, 2, 1))
+        call('gn_stack_residual_fwd_f32', ptr(x), ptr(self.const), ptr(y), B, L, stream())
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        B = dy.shape[0]
+        L = self.input_shape[0]
+        dx = _empty((B,) + self.input_shape)
+        call('gn_stack_residual_bwd_f32', ptr(dy), ptr(dx), B, L, stream())
+        return dx
+
+
+class ResidualMoments(Layer):
+    """tests/burstMahoGANy.py:100-125 ``MyLayer``: [mean(const-x), mean((const-x)^2)] over the whole
+    batch; the output has shape (2,) (no batch axis), as in the reference."""
+    prefix = 'my_layer'
+    batch_global = True
+
+    def __init__(self, const, **kw):
+        super().__init__(**kw)
+        self._const_host = np.asarray(const, dtype=np.float32)
+
+    def build(self, in_shape):
+        L = int(np.prod(in_shape))
+        self.const = torch.from_numpy(np.ascontiguousarray(self._const_host.reshape(L))).to(device())
+        return (2,)
+
+    def forward(self, x, ctx):
+        B = x.shape[0]
+        L = x.numel() // B
+        sums = torch.empty(2, dtype=torch.float64, device=x.device)
+        call('gn_residual_moments_fwd_f32', ptr(x), ptr(self.const), ptr(sums, torch.float64), B, L, stream())
+        if ctx.world > 1:
+            ctx.dp.all_reduce(sums)
+        self._n = float(B * L * ctx.world)
+        self._x = x
+        return (sums / self._n).to(torch.float32)
+
+    def backward(self, dy, ctx, need_dx=True):
+        x = self._x
+        B = x.shape[0]
+        L = x.numel() // B
+        dx = _empty(x.shape)
+        call('gn_residual_moments_bwd_f32', ptr(x), ptr(self.const), ptr(dy.contiguous()), ptr(dx), B, L, self._n,
+             stream())
+        self._x = None
+        return dx
+
+
+# ----------------------------------------------------------------------------- optimizers
+class Optimizer:
+    def __init__(self):
+        self.iterations = 0
+        self.slots = {}
+
+    def get_config(self):
+        return {}
+
+
+class Adam(Optimizer):
+    """Keras 2.2.4 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps), eps = 1e-7."""
+
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=None, decay=0.0, **kw):
+        super().__init__()
+        self.lr, self.beta_1, self.beta_2 = float(lr), float(beta_1), float(beta_2)
+        self.epsilon = 1e-7 if epsilon is None else float(epsilon)
+        self.decay = float(decay)
+
+    def apply(self, segments, grad_scale):
+        lr = self.lr
+        if self.decay > 0:
+            lr = lr * (1.0 / (1.0 + self.decay * self.iterations))
+        t = self.iterations + 1
+        lr_t = lr * (math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t))
+        for key, p, g in segments:
+            if key not in self.slots:
+                self.slots[key] = (torch.zeros_like(p), torch.zeros_like(p))
+            m, v = self.slots[key]
+            call('gn_adam_step_f32', ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr_t, self.beta_1, self.beta_2,
+                 self.epsilon, grad_scale, stream())
+        self.iterations += 1
+
+
+class SGD(Optimizer):
+    def __init__(self, lr=0.01, momentum=0.0, decay=0.0, nesterov=False, **kw):
+        super().__init__()
+        assert momentum == 0.0 and not nesterov, 'the reference uses plain SGD (nn.py:79)'
+        self.lr, self.decay = float(lr), float(decay)
+
+    def apply(self, segments, grad_scale):
+        lr = self.lr
+        if self.decay > 0:
+            lr = lr * (1.0 / (1.0 + self.decay * self.iterations))
+        for key, p, g in segments:
+            call('gn_sgd_step_f32', ptr(p), ptr(g), p.numel(), lr, grad_scale, stream())
+        self.iterations += 1
+
+
+# ----------------------------------------------------------------------------- losses
+class _LossSpec:
+    def __init__(self, loss):
+        self.param = 0.0
+        if callable(loss) and getattr(loss, 'gn_kind', None) is not None:
+            self.kind, self.param, self.name = loss.gn_kind, float(loss.gn_param), 'chisquare_Loss'
+        elif loss in ('binary_crossentropy',):
+            self.kind, self.name = _lib.LOSS_BCE, loss
+        elif loss in ('mean_squared_error', 'mse'):
+            self.kind, self.name = _lib.LOSS_MSE, 'mean_squared_error'
+        else:
+            raise ValueError('unsupported loss %r (the reference uses binary_crossentropy, mean_squared_error '
+                             'and chisquare_Loss)' % (loss,))
+
+
+def chisquare_Loss(n_sig=1.0):
+    """bbhMahoGANy.py:146-162: K.sum(K.square(yTrue - yPred)/n_sig**2, axis=-1)."""
+    def loss(y_true, y_pred):
+        raise RuntimeError('chisquare_Loss is evaluated on the device')
+    loss.gn_kind, loss.gn_param = _lib.LOSS_CHISQ, n_sig
+    return loss
+
+
+# ----------------------------------------------------------------------------- models
+class Model(Layer):
+    """Functional model: ``Model(inputs, outputs)``.  Also the base of Sequential."""
+    prefix = 'model'
+
+    def __init__(self, inputs=None, outputs=None, name=None):
+        super().__init__(name=name)
+        self._compiled = None
+        self.optimizer = None
+        if inputs is not None:
+            self._init_graph(inputs, outputs)
+
+    def _init_graph(self, inputs, outputs):
+        self._multi_out = isinstance(outputs, (list, tuple))
+        ins = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+        outs = list(outputs) if self._multi_out else [outputs]
+        assert len(ins) == 1, 'single-input models only (all reference models are)'
+        self._in_node = ins[0].node
+        self._out_nodes = [o.node for o in outs]
+        order, seen = [], set()
+
+        def visit(n):
+            if id(n) in seen:
+                return
+            seen.add(id(n))
+            for i in n.inputs:
+                visit(i)
+            order.append(n)
+        for o in self._out_nodes:
+            visit(o)
+        assert id(self._in_node) in seen, 'outputs do not depend on the input'
+        self._order = [n for n in order if n is not self._in_node and not isinstance(n.layer, InputLayer)]
+        self.layers = []
+        for n in self._order:
+            if n.layer not in self.layers:
+                self.layers.append(n.layer)
+        if self.name is None:
+            self.name = _uid(self.prefix)
+        self.input_shape = ins[0].shape
+        self.output_shape = [o.shape for o in outs] if self._multi_out else outs[0].shape
+        self.built = True
+        self._fuse()
+
+    def _fuse(self):
+        """UpSampling1D(2) feeding exactly one Conv1D is folded into the convolution's loader."""
+        users = {}
+        for n in self._order:
+            for i in n.inputs:
+                users.setdefault(id(i), []).append(n)
+        for n in self._order:
+            if isinstance(n.layer, UpSampling1D) and n.layer.size == 2:
+                u = users.get(id(n), [])
+                if len(u) == 1 and type(u[0].layer) is Conv1D and n not in self._out_nodes:
+                    n.layer.fused = True
+                    u[0].layer.fused_up = 2
+
+    # a model can be used as a layer
+    def __call__(self, x):
+        assert self.built, 'model has no input shape yet'
+        return KTensor(self.output_shape, Node(self, [x.node]))
+
+    def _ensure_built(self, in_shape):
+        assert self.built
+        return self.output_shape
+
+    def all_layers(self):
+        out = []
+        for l in self.layers:
+            for s in l.all_layers():
+                if s not in out:
+                    out.append(s)
+        return out
+
+    @property
+    def params(self):
+        return [p for l in self.all_layers() for p in l.params]
+
+    @params.setter
+    def params(self, v):
+        pass
+
+    def get_weights(self):
+        return [w for l in self.all_layers() for w in l.get_weights()]
+
+    def set_weights(self, ws):
+        i = 0
+        for l in self.all_layers():
+            n = len(l.params)
+            l.set_weights(ws[i:i + n])
+            i += n
+        assert i == len(ws), 'expected %d arrays, got %d' % (i, len(ws))
+
+    def count_params(self):
+        return sum(l.count_params() for l in self.all_layers())
+
+    def summary(self, print_fn=print):
+        print_fn('_' * 65)
+        print_fn('%-30s%-22s%-13s' % ('Layer (type)', 'Output Shape', 'Param #'))
+        print_fn('=' * 65)
+        for l in self.layers:
+            shp = l.output_shape
+            print_fn('%-30s%-22s%-13d' % ('%s (%s)' % (l.name, type(l).__name__), str((None,) + tuple(shp)) if not
+                                          isinstance(shp, list) else str(shp), l.count_params()))
+        tot = self.count_params()
+        tr = sum(p.numel() for l in self.all_layers() if l.trainable for p in l.params if p.trainable)
+        print_fn('=' * 65)
+        print_fn('Total params: {:,}'.format(tot))
+        print_fn('Trainable params: {:,}'.format(tr))
+        print_fn('Non-trainable params: {:,}'.format(tot - tr))
+        print_fn('_' * 65)
+
+    # ---- execution ------------------------------------------------------------
+    def forward(self, x, ctx):
+        vals = {id(self._in_node): x}
+        for n in self._order:
+            vals[id(n)] = n.layer.forward(vals[id(n.inputs[0])], ctx)
+        outs = [vals[id(o)] for o in self._out_nodes]
+        return outs if self._multi_out else outs[0]
+
+    def backward(self, dy, ctx, need_dx=True):
+        dys = dy if self._multi_out else [dy]
+        grads = {}
+        for o, g in zip(self._out_nodes, dys):
+            grads[id(o)] = g
+        first_users = self._nodes_needing_dx(ctx, need_dx)
+        for n in reversed(self._order):
+            g = grads.pop(id(n), None)
+            if g is None:
+                continue
+            src = n.inputs[0]
+            want = id(n) in first_users
+            dx = n.layer.backward(g, ctx, want)
+            if not want or dx is None:
+                continue
+            if id(src) in grads:
+                call('gn_axpy_f32', ptr(grads[id(src)].reshape(-1)), ptr(dx.reshape(-1).contiguous()), 1.0,
+                     dx.numel(), stream())
+            else:
+                grads[id(src)] = dx
+        return grads.get(id(self._in_node))
+
+    def _nodes_needing_dx(self, ctx, need_dx):
+        """A node must produce dx iff something upstream of it has trainable parameters (or the
+        caller wants the model's input gradient)."""
+        need = set()
+        upstream_trainable = {id(self._in_node): need_dx}
+        for n in self._order:
+            src = n.inputs[0]
+            up = upstream_trainable.get(id(src), False)
+            if up:
+                need.add(id(n))
+            own = any(id(l) in ctx.trainable_ids and l.params for l in n.layer.all_layers())
+            upstream_trainable[id(n)] = up or own
+        return need
+
+    # ---- Keras protocol ---------------------------------------------------------
+    def compile(self, loss=None, optimizer=None, metrics=None, **kw):
+        self.loss = loss
+        self.optimizer = optimizer
+        self.metrics = metrics or []
+        spec = _LossSpec(loss)
+        train_layers = [l for l in self.all_layers() if l.trainable and l.params]
+        tparams = [p for l in train_layers for p in l.params if p.trainable]
+        _home_params(tparams)
+        self._compiled = {'loss': spec, 'trainable_ids': set(id(l) for l in train_layers),
+                          'segments': _segments(tparams)}
+        self.metrics_names = ['loss'] + (['acc'] if self.metrics else [])
+
+    def predict(self, x, batch_size=1024, verbose=0):
+        ctx = Ctx(False)
+        xs = _to_device(x)
+        outs = None
+        for i in range(0, xs.shape[0], batch_size):
+            o = self.forward(xs[i:i + batch_size].contiguous(), ctx)
+            o = o if isinstance(o, list) else [o]
+            if outs is None:
+                outs = [[] for _ in o]
+            for k, t in enumerate(o):
+                outs[k].append(t)
+        # batch-global outputs (burst MyLayer) have no batch axis to concatenate along
+        res = [ts[0] if ts[0].dim() == 1 else torch.cat(ts, 0) for ts in outs]
+        res = [r.detach().cpu().numpy() for r in res]
+        return res if self._multi_out else res[0]
+
+    def train_on_batch(self, x, y, sample_weight=None, class_weight=None, _noise=None, _return_device=False):
+        """One optimizer step; returns [loss, acc] (single output) or [total, loss_1.., acc_1..]."""
+        assert self._compiled is not None, 'compile() the model first'
+        c = self._compiled
+        ctx = Ctx(True, c['trainable_ids'], _noise)
+        xs = _to_device(x)
+        B = xs.shape[0]
+        out = self.forward(xs, ctx)
+        outs = out if isinstance(out, list) else [out]
+        ys = y if self._multi_out else [y]
+        assert len(ys) == len(outs), 'expected %d target arrays' % len(outs)
+        inv_batch = 1.0 / (B * ctx.world)
+        res = torch.zeros(2 * len(outs), dtype=torch.float32, device=xs.device)
+        dys = []
+        for k, (o, t) in enumerate(zip(outs, ys)):
+            vec = o.dim() == 1           # batch-global output (burst MyLayer)
+            D = o.shape[-1]
+            tt = _to_device(t).reshape(B, -1)
+            assert tt.shape[1] == D, 'target shape %s does not match output %s' % (tuple(tt.shape), tuple(o.shape))
+            d = torch.zeros_like(o) if vec else _empty(o.shape)
+            metric_kind = 0 if (D == 1 or c['loss'].kind == _lib.LOSS_BCE) else 1
+            call('gn_loss_fwd_bwd_f32', ptr(o.contiguous()), ptr(tt.contiguous()), ptr(res[2 * k:2 * k + 2]), ptr(d),
+                 B, D, c['loss'].kind, c['loss'].param, inv_batch, 1 if vec else 0, metric_kind, stream())
+            if vec and ctx.world > 1:
+                ctx.dp.all_reduce(d)
+            dys.append(d)
+        self.backward(dys if self._multi_out else dys[0], ctx, need_dx=False)
+        segs = c['segments']
+        if ctx.world > 1:
+            for _, p, g in segs:
+                ctx.dp.all_reduce(g)
+            ctx.dp.all_reduce(res)
+        self.optimizer.apply(segs, 1.0)
+        res = res * inv_batch
+        if _return_device:
+            return res
+        r = res.detach().cpu().numpy().astype(np.float64)      # the D2H read of the step's loss / metric
+        losses = [float(r[2 * k]) for k in range(len(outs))]
+        accs = [float(r[2 * k + 1]) for k in range(len(outs))]
+        if len(outs) == 1:
+            return [losses[0], accs[0]] if self.metrics else losses[0]
+        return [float(sum(losses))] + losses + (accs if self.metrics else [])
+
+    def fit(self, x, y, batch_size=32, epochs=1, verbose=0, shuffle=True, **kw):
+        x = np.asarray(x)
+        y = np.asarray(y)
+        n = x.shape[0]
+        hist = []
+        rs = np.random.RandomState(_STATE['seed'])
+        for e in range(epochs):
+            idx = rs.permutation(n) if shuffle else np.arange(n)
+            for i in range(0, n, batch_size):
+                j = idx[i:i + batch_size]
+                hist.append(self.train_on_batch(x[j], y[j]))
+        return hist
+
+    def get_gradients(self):
+        """Gradients of the last train_on_batch, Keras weight order (parity-test hook)."""
+        return [p.grad.detach().cpu().numpy().copy() for l in self.all_layers() if id(l) in
+                self._compiled['trainable_ids'] for p in l.params if p.trainable]
+
+    # persistence: see gennet_b200.io (Keras HDF5 layout)
+    def save_weights(self, path, overwrite=True):
+        from . import io
+        io.save_weights(self, path, overwrite)
+
+    def load_weights(self, path):
+        from . import io
+        io.load_weights(self, path)
+
+    def save(self, path, overwrite=True):
+        from . import io
+        io.save_model(self, path, overwrite)
+
+
+class Sequential(Model):
+    prefix = 'sequential'
+
+    def __init__(self, layers=None, name=None):
+        Layer.__init__(self, name=name)
+        self._compiled = None
+        self.optimizer = None
+        self._pending = []
+        self._tensor = None
+        self._input = None
+        for l in layers or []:
+            self.add(l)
+
+    def add(self, layer):
+        if self._tensor is None:
+            shape = None
+            if isinstance(layer, Model):
+                shape = layer.input_shape if layer.built else None
+            elif layer._input_shape_arg is not None:
+                shape = layer._input_shape_arg
+            if shape is None:
+                raise ValueError('the first layer of a Sequential model needs input_shape=...')
+            self._input = Input(shape=shape)
+            self._tensor = self._input
+        self._tensor = layer(self._tensor)
+        self._init_graph(self._input, self._tensor)
+
+
+def set_trainable(model, trainable):
+    """bbhMahoGANy.py:797-809 / nn.py:95-98 (set_trainability)."""
+    model.trainable = trainable
+    for l in model.all_layers():
+        l.trainable = trainable
+
+
+set_trainability = set_trainable
+
+
+def load_model(path, custom_objects=None):
+    from . import io
+    return io.load_model(path, custom_objects)
+
+
+# ----------------------------------------------------------------------------- parameter arenas
+def _home_params(params):
+    """Move parameters that are not yet in an arena into one new flat arena (values preserved)."""
+    fresh = [p for p in params if p.arena is None]
+    if not fresh:
+        return
+    n = sum(p.numel() for p in fresh)
+    # keep every tensor 16-byte aligned inside the arena
+    offs, tot = [], 0
+    for p in fresh:
+        offs.append(tot)
+        tot += (p.numel() + 3) // 4 * 4
+    data = torch.zeros(tot, dtype=torch.float32, device=device())
+    grad = torch.zeros(tot, dtype=torch.float32, device=device())
+    arena = {'data': data, 'grad': grad}
+    for p, o in zip(fresh, offs):
+        view = data[o:o + p.numel()].view(p.shape)
+        view.copy_(p.data)
+        p.data = view
+        p.grad = grad[o:o + p.numel()].view(p.shape)
+        p.arena, p.offset = arena, o
+
+
+def _segments(params):
+    """Maximal runs of parameters that are adjacent in the same arena -> [(key, data, grad)]."""
+    segs = []
+    cur = None
+    for p in params:
+        end = p.offset + (p.numel() + 3) // 4 * 4
+        if cur is not None and cur[0] is p.arena and cur[2] == p.offset:
+            cur[2] = end
+        else:
+            if cur is not None:
+                segs.append(cur)
+            cur = [p.arena, p.offset, end]
+    if cur is not None:
+        segs.append(cur)
+    return [((id(a), lo, hi), a['data'][lo:hi], a['grad'][lo:hi]) for a, lo, hi in segs]
+
+
+_PINNED = {}
+
+
+def _to_device(x):
+    """NumPy / list / tensor -> contiguous float32 CUDA tensor (pinned staging for host arrays)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+        if not t.is_cuda:
+            t = t.to(device(), non_blocking=True)
+        return t.to(torch.float32).contiguous()
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    key = a.shape
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) > 64:
+            _PINNED.clear()
+        buf = torch.empty(a.shape, dtype=torch.float32).pin_memory()
+        _PINNED[key] = buf
+    # the previous async copy out of this staging buffer must have completed
+    torch.cuda.current_stream().synchronize()
+    buf.copy_(torch.from_numpy(a))
+    return buf.to(device(), non_blocking=True)

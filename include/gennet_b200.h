@@ -1,0 +1,207 @@
+/*
+ * gennet_b200 -- C ABI of the B200 (sm_100a) hot path of hagabbar/GenNet.
+ *
+ * The reference has no FFI of its own (it is pure Python on Keras/TensorFlow/NumPy),
+ * so each entry point names the reference call site (file:line, relative to the
+ * reference checkout) whose arithmetic it replaces.  A maintainer binds these
+ * with ctypes; gennet_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is caller-owned DEVICE memory unless the name ends in _host;
+ *   - tensors are dense row-major; activations are channels-last (NLC / NHWC) as in
+ *     Keras; weights use the Keras layouts (Dense (in,out); Conv1D (k,Cin,Cout));
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and
+ *     nothing synchronises the device;
+ *   - return value: GN_OK, or a negative GN_ERR_* with a message in gn_last_error()
+ *     (thread-local).  The library never falls back to the CPU.
+ */
+#ifndef GENNET_B200_H
+#define GENNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GN_OK 0
+#define GN_ERR_ARG (-1)         /* invalid argument / shape */
+#define GN_ERR_UNSUPPORTED (-2) /* valid but not implemented for this shape */
+#define GN_ERR_CUDA (-3)        /* CUDA runtime / driver error */
+
+/* activation codes (Keras Activation / LeakyReLU / ReLU(max_value), bbhMahoGANy.py:238,363,400,440,495) */
+#define GN_ACT_NONE 0
+#define GN_ACT_RELU 1
+#define GN_ACT_TANH 2
+#define GN_ACT_SIGMOID 3
+#define GN_ACT_LEAKY 4    /* param = alpha */
+#define GN_ACT_RELU_MAX 5 /* param = max_value */
+
+/* dropout-family codes (Keras Dropout / GaussianDropout / GaussianNoise) */
+#define GN_NOISE_DROPOUT 0   /* r = keep mask (0/1):  y = x*r/(1-rate)              */
+#define GN_NOISE_GDROPOUT 1  /* r = N(0,1):           y = x*(1+r*sqrt(rate/(1-rate))) */
+#define GN_NOISE_GNOISE 2    /* r = N(0,1):           y = x + r*rate (rate = stddev) */
+
+/* loss codes (Keras 'binary_crossentropy', 'mean_squared_error', chisquare_Loss bbhMahoGANy.py:146-162) */
+#define GN_LOSS_BCE 0
+#define GN_LOSS_MSE 1
+#define GN_LOSS_CHISQ 2 /* param = n_sig */
+
+const char* gn_last_error(void);
+int gn_version(void);
+/* 1 if the visible device is sm_100 (B200) and the kernels can run, else 0 with gn_last_error() set */
+int gn_device_ok(void);
+
+/* ---------------------------------------------------------------------------
+ * Sample synthesis  (BBH_version/gw_template_maker.py)
+ * ------------------------------------------------------------------------- */
+
+typedef struct gn_fft_plan gn_fft_plan;
+
+/* Twiddle tables for real FFTs of length N (power of two, 512 <= N <= 32768). */
+int gn_fft_plan_create(int N, gn_fft_plan** plan);
+int gn_fft_plan_destroy(gn_fft_plan* plan);
+
+/* whiten_data(x, T, fs, psd, 'td')  gw_template_maker.py:243-286, batched, + crop (:695) + scale (:813-814):
+ *   y[b, j] = scale * irfft( rfft(window * x[b]) * weights )[crop_lo + j],  j < crop_len
+ * x (batch,N) f32; window (N) f32 = tukey(N,1/8); weights (N/2+1) f32 = sqrt(2/(S*fs)), 0 where S<=0, [0]=0. */
+int gn_whiten_td_f32(const gn_fft_plan* plan, const float* x, const float* window, const float* weights,
+                     float* y, int batch, int crop_lo, int crop_len, float scale, void* stream);
+
+/* scale * irfft(xf * weights) rolled by `roll` samples (np.roll semantics), batched.
+ * Covers whiten_data(...,'fd') + np.fft.irfft + np.roll of gen_bbh (:518-522, roll=-fs),
+ * main()'s event whitening (:774-777) and gen_noise (:184-191; weights=amp, scale=N*df).
+ * xf (batch, N/2+1) interleaved complex f32; weights may be NULL (all ones). Imag of the DC and
+ * Nyquist bins is ignored as numpy's irfft does; drop_dc!=0 zeroes the DC bin (:189-190,:279). */
+int gn_irfft_f32(const gn_fft_plan* plan, const float* xf, const float* weights, float* y, int batch,
+                 float scale, int roll, int drop_dc, void* stream);
+
+/* Fused per-batch training-sample synthesis (sim_data noise branch :685-691 as restated in SURVEY a7):
+ *   n      = fs * irfft(amp * (normals_re + i normals_im)), DC = 0            (gen_noise :184-191)
+ *   out[b] = out_scale * whiten_td(n + templates[tidx[b]])[crop_lo : crop_lo+crop_len]
+ * normals (batch,2,N/2+1) f32 standard normals (re row then im row, the order of :187-188), or NULL to draw
+ * them in-kernel with Philox4x32-10 keyed by (seed, sample_offset+b); amp (N/2+1) = sqrt(T*S/4);
+ * templates (n_templates,N) f32 or NULL (noise only); tidx (batch) int32 or NULL (template b). */
+int gn_synth_f32(const gn_fft_plan* plan, const float* normals, const float* amp, const float* templates,
+                 const int* tidx, const float* window, const float* weights, float* out, int batch,
+                 int n_templates, int crop_lo, int crop_len, float noise_scale, float out_scale,
+                 uint64_t seed, uint64_t sample_offset, void* stream);
+
+/* Tail of gen_bbh (gw_template_maker.py:528-571) + crop (:695) + norm (:813-814), batched:
+ *   ref = argmax(hp^2+hc^2); ht = Fp*hp + Fc*hc; ts[:len] = ht[ref-idx-lead:] (Python slice semantics,
+ *   negative start wraps); ts *= win; out = scale * ts[crop_lo : crop_lo+crop_len].
+ * hp, hc (batch,N) whitened rolled polarisations (gn_irfft_f32 with roll=-fs); Fp, Fc (batch) antenna factors
+ * (pylal.antenna.response is not restated: the caller supplies them); ref_idx (batch) int32 out or NULL. */
+int gn_bbh_assemble_f32(const float* hp, const float* hc, const float* Fp, const float* Fc, const int* idx,
+                        int lead, const float* win, float* out, int* ref_idx, int batch, int N, int crop_lo,
+                        int crop_len, float scale, void* stream);
+
+/* mean and population std of n floats (np.std, gw_template_maker.py:782); out_host-free: out (2) f32 on device */
+int gn_mean_std_f32(const float* x, long long n, float* out, void* stream);
+
+/* x[r, :] += sigma * normals[r, :] for r < rows  (on-the-fly noise, bbhMahoGANy.py:1161,1277,1030) */
+int gn_add_scaled_f32(float* x, const float* r, float sigma, long long n, void* stream);
+
+/* sine-Gaussian bursts, tests/burstMahoGANy.py:76-98: out[i,j] = amp*sin(2*pi*freq*(t_j-t0_i)+phi)*exp(-(t_j-t0_i)^2/tau_i^2)
+ * pars (n,2) f32 = (t0, tau) */
+int gn_burst_waveforms_f32(const float* pars, float* out, int n, int N, float amp, float freq, float dt,
+                           float phi, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Network layers (Keras semantics; bbhMahoGANy.py:212-539, tests/burstMahoGANy.py:127-423,
+ * train_on_wvf_version/nn.py:72-106)
+ * ------------------------------------------------------------------------- */
+
+/* Conv1D, NLC, kernel (k,Cin,Cout), zero padding pad_left (TF 'SAME' rule computed by the caller), stride s.
+ * up = 1, or 2 to read the input through a fused UpSampling1D(2) (bbhMahoGANy.py:249-250,258-259):
+ * x is then the (B, L/2, Cin) tensor before upsampling and L the upsampled length.
+ * y = act(conv(x) + bias). */
+int gn_conv1d_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int L, int Cin,
+                      int Lout, int Cout, int k, int stride, int pad_left, int up, int act, float act_param,
+                      void* stream);
+/* dx (B, L/up, Cin) = conv-transpose(dy, w); overwrites dx */
+int gn_conv1d_dgrad_f32(const float* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int Cout,
+                        int k, int stride, int pad_left, int up, void* stream);
+/* dw (k,Cin,Cout) and db (Cout) OVERWRITTEN with the batch gradient (db may be NULL) */
+int gn_conv1d_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
+                        int Cout, int k, int stride, int pad_left, int up, void* stream);
+
+/* Conv2D(5x5, strides (2,1), 'same') over an (L,2,C) image (bbhMahoGANy.py:439,447) is a Conv1D with
+ * Cin'=2Cin, Cout'=2Cout: w1 (kh, 2Cin, 2Cout) [kh,(wi,ci),(wo,co)] = w2 (kh,kw,Cin,Cout) [kh, wi-wo+pw, ci, co];
+ * pw = left width pad (2 for kw=5). pack: w2->w1, b (Cout)->b1 (2Cout); unpack: dw1->dw2, db1->db (overwrite). */
+int gn_conv2d_w2_pack_f32(const float* w2, const float* b, float* w1, float* b1, int kh, int kw, int Cin,
+                          int Cout, int pw, void* stream);
+int gn_conv2d_w2_unpack_f32(const float* dw1, const float* db1, float* dw2, float* db, int kh, int kw, int Cin,
+                            int Cout, int pw, void* stream);
+
+/* Dense: y (M,N) = act(x (M,K) @ w (K,N) + bias) */
+int gn_dense_fwd_f32(const float* x, const float* w, const float* bias, float* y, int M, int K, int N, int act,
+                     float act_param, void* stream);
+int gn_dense_dgrad_f32(const float* dy, const float* w, float* dx, int M, int K, int N, void* stream);
+int gn_dense_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int M, int K, int N, void* stream);
+
+/* BatchNormalization(axis=-1) over `rows` x C (Keras 2.2.4: eps 1e-3, biased batch variance for the
+ * normalisation, moving_var fed var*n/(n-(1+eps)), bbhMahoGANy.py:235,251).
+ * stats: f32 workspace (2*C): on return [0:C]=batch mean, [C:2C]=1/sqrt(var+eps) (kept for backward).
+ * stats_only!=0 stops after the per-channel sums so a data-parallel caller can all-reduce them:
+ *   step 0: gn_bn_sums(x) -> sums (2C) = (sum x, sum x^2 about `shift`)  ... see gn_bn_* below. */
+int gn_bn_stats_f32(const float* x, long long rows, int C, double* sums /* (2C): sum(x), sum((x-shift)^2) */,
+                    const float* shift /* (C) or NULL */, void* stream);
+int gn_bn_finalize_f32(const double* sum_x, const double* sum_sq, double n_total, int C, float eps, float momentum,
+                       float* stats, float* moving_mean, float* moving_var, int phase, void* stream);
+int gn_bn_apply_f32(const float* x, const float* mean, const float* invstd_or_var, const float* gamma,
+                    const float* beta, float* y, long long rows, int C, float eps, int use_var, void* stream);
+/* backward sums: sums (2C) double = (sum dy, sum dy*xhat) with xhat=(x-mean)*invstd */
+int gn_bn_bwd_sums_f32(const float* x, const float* dy, const float* stats, long long rows, int C, double* sums,
+                       void* stream);
+/* dx = gamma*invstd*(dy - sum_dy/n - xhat*sum_dyxhat/n); dgamma=sum_dyxhat, dbeta=sum_dy (overwrite) */
+int gn_bn_bwd_apply_f32(const float* x, const float* dy, const float* stats, const float* gamma, const double* sums,
+                        double n_total, float* dx, float* dgamma, float* dbeta, long long rows, int C,
+                        void* stream);
+
+/* elementwise */
+int gn_act_fwd_f32(const float* x, float* y, long long n, int act, float param, void* stream);
+int gn_act_bwd_f32(const float* dy, const float* y, float* dx, long long n, int act, float param, void* stream);
+int gn_noise_fwd_f32(const float* x, const float* r, float* y, long long n, int kind, float rate, void* stream);
+int gn_noise_bwd_f32(const float* dy, const float* r, float* dx, long long n, int kind, float rate, void* stream);
+/* fill r for the dropout family with Philox4x32-10 (kind DROPOUT: keep mask with P(keep)=1-rate; else N(0,1)) */
+int gn_noise_draw_f32(float* r, long long n, int kind, float rate, uint64_t seed, uint64_t offset, void* stream);
+int gn_uniform_f32(float* r, long long n, float lo, float hi, uint64_t seed, uint64_t offset, void* stream);
+int gn_normal_f32(float* r, long long n, float mean, float std, uint64_t seed, uint64_t offset, void* stream);
+int gn_upsample1d_fwd_f32(const float* x, float* y, int B, int L, int C, int size, void* stream);
+int gn_upsample1d_bwd_f32(const float* dy, float* dx, int B, int L, int C, int size, void* stream);
+int gn_maxpool1d_fwd_f32(const float* x, float* y, int B, int L, int C, int pool, void* stream);
+int gn_maxpool1d_bwd_f32(const float* x, const float* y, const float* dy, float* dx, int B, int L, int C, int pool,
+                         void* stream);
+/* a += b (gradient accumulation where two branches share an input, bbhMahoGANy.py:362,382) */
+int gn_axpy_f32(float* a, const float* b, float alpha, long long n, void* stream);
+/* gather rows: out[i,:] = src[idx[i],:]  (template batch assembly, bbhMahoGANy.py:1156-1158,1244) */
+int gn_gather_rows_f32(const float* src, const int* idx, float* out, int n, long long row_len, void* stream);
+
+/* MyLayer, bbhMahoGANy.py:164-188: y (B,L,2) = stack([x, const - x], axis=2); bwd dx = dy[...,0]-dy[...,1] */
+int gn_stack_residual_fwd_f32(const float* x, const float* cst, float* y, int B, int L, void* stream);
+int gn_stack_residual_bwd_f32(const float* dy, float* dx, int B, int L, void* stream);
+/* MyLayer, tests/burstMahoGANy.py:100-125: out (2) = [mean(c-x), mean((c-x)^2)] over the whole batch;
+ * sums (2) double workspace = un-normalised sums (for data-parallel all-reduce) */
+int gn_residual_moments_fwd_f32(const float* x, const float* cst, double* sums, int B, int L, void* stream);
+int gn_residual_moments_bwd_f32(const float* x, const float* cst, const float* dout /* (2) */, float* dx, int B,
+                                int L, double n_total, void* stream);
+
+/* losses: pred (B,D), target (B,D) or (B) broadcast... all as (B,D) f32.
+ * out (2) f32: [0] += sum_b mean_d loss, [1] += sum_b metric hits  (caller zeroes, divides by global B)
+ * dpred (B,D) = d(mean_b loss)/dpred using inv_batch = 1/global batch. pred_is_vec: pred is (D) broadcast over B
+ * (burst MyLayer output), dpred then (D) accumulated. */
+int gn_loss_fwd_bwd_f32(const float* pred, const float* target, float* out, float* dpred, int B, int D, int kind,
+                        float param, float inv_batch, int pred_is_vec, int metric_kind, void* stream);
+
+/* Keras optimizers over a flat parameter arena (one launch per model):
+ * Adam (Keras 2.2.4): m=b1 m+(1-b1)g; v=b2 v+(1-b2)g^2; p-=lr_t*m/(sqrt(v)+eps), lr_t computed by the caller */
+int gn_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                     float eps, float grad_scale, void* stream);
+int gn_sgd_step_f32(float* p, const float* g, long long n, float lr, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENNET_B200_H */

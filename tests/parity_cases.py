@@ -1,0 +1,209 @@
+"""Shared parity scaffolding: build the same network in the product (gennet_b200) and in the float64
+oracle with identical weights, inputs and dropout draws, run one Keras-style step in both and compare
+forward outputs, losses, gradients, updated weights and BatchNorm moving statistics.
+
+Used by the CPU host-logic tests (product routed to tests/fake_backend.py) and by the `-m gpu` parity
+tests (product on the real sm_100a kernels).  Tolerance: rtol 1e-4 of the tensor's max magnitude (float32
+product vs float64 oracle), as BASELINE.json's north_star states.
+"""
+import numpy as np
+import torch
+
+from oracle import keras_oracle as ko
+
+RTOL = 1e-4
+
+
+def assert_close(got, ref, what, rtol=RTOL, floor=1e-30):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, '%s: shape %s vs %s' % (what, got.shape, ref.shape)
+    scale = max(np.abs(ref).max(), floor)
+    err = np.abs(got - ref).max() / scale
+    assert np.isfinite(got).all(), '%s: non-finite values' % what
+    assert err <= rtol, '%s: max error %.3e of scale %.3e exceeds rtol %.1e' % (what, err, scale, rtol)
+    return err
+
+
+def noise_layers(model):
+    return [l for l in model.all_layers() if type(l).__name__ in ('Dropout', 'GaussianDropout', 'GaussianNoise')]
+
+
+def sync_weights(product, oracle):
+    ws = oracle.get_weights()
+    product.set_weights([w.astype(np.float32) for w in ws])
+    # the oracle continues from the float32-rounded values so both start identically
+    oracle.set_weights([w.astype(np.float32).astype(np.float64) for w in ws])
+
+
+def draw_noise(oracle_model, x, seed):
+    """Run the oracle forward once in training mode to draw every dropout tensor; returns {oracle_name: tensor}."""
+    noise = {'__gen__': torch.Generator().manual_seed(seed)}
+    st = [[s.clone() for s in l.state] for l in oracle_model.all_layers()]
+    with torch.no_grad():
+        oracle_model.forward(torch.as_tensor(np.asarray(x, dtype=np.float64)), True, noise)
+    for l, s in zip(oracle_model.all_layers(), st):      # undo the BN moving-average side effect
+        l.state = s
+    noise.pop('__gen__')
+    return noise
+
+
+def map_noise(noise, oracle_model, product_model):
+    on, pn = noise_layers(oracle_model), noise_layers(product_model)
+    assert len(on) == len(pn)
+    return {p.name: noise[o.name].numpy().astype(np.float32) for o, p in zip(on, pn) if o.name in noise}
+
+
+def compare_step(product, oracle, x, y, seed=0, rtol=RTOL, check_predict=True):
+    """One train_on_batch in both; returns dict of observed relative errors."""
+    errs = {}
+    if check_predict:
+        po, oo = product.predict(x), oracle.predict(x)
+        if isinstance(oo, list):
+            for k, (a, b) in enumerate(zip(po, oo)):
+                errs['predict%d' % k] = assert_close(a, b, 'predict[%d]' % k, rtol)
+        else:
+            errs['predict'] = assert_close(po, oo, 'predict', rtol)
+    noise = draw_noise(oracle, x, seed)
+    pnoise = map_noise(noise, oracle, product)
+    w_before = [w.copy() for w in oracle.get_weights()]
+    ro = oracle.train_on_batch(x, y, noise=dict(noise))
+    rp = product.train_on_batch(x, y, _noise=pnoise)
+    if not isinstance(rp, list):          # compiled without metrics: Keras returns the scalar loss
+        ro = ro[0]
+    errs['loss'] = assert_close(rp, ro, 'train_on_batch return', max(rtol, 2e-4))
+    gp = product.get_gradients()
+    # structurally-zero gradients (e.g. a bias feeding BatchNorm) are compared against the largest
+    # gradient of the step instead of their own rounding noise
+    gfloor = 1e-3 * max(np.abs(b).max() for b in oracle.last_grads)
+    for i, (a, b) in enumerate(zip(gp, oracle.last_grads)):
+        errs['grad%d' % i] = assert_close(a, b, 'gradient %d %s' % (i, b.shape), rtol, floor=gfloor)
+    assert len(gp) == len(oracle.last_grads)
+    return errs, w_before
+
+
+def compare_weights(product, oracle, w_before, rtol=RTOL):
+    """Updated weights: compare the UPDATE (w_after - w_before) so that a no-op cannot pass."""
+    pw, ow = product.get_weights(), oracle.get_weights()
+    gmax = max(np.abs(b - w0).max() for b, w0 in zip(ow, w_before))
+    for i, (a, b, w0) in enumerate(zip(pw, ow, w_before)):
+        if np.abs(b - w0).max() == 0:
+            assert np.abs(a - w0).max() == 0, 'weight %d should be unchanged' % i
+            continue
+        # float32 storage rounds each weight to ~6e-8 relative, and Adam's m/(sqrt(v)+eps) amplifies the
+        # relative error of gradients that are small against eps: allow 5e-3 of the update scale + 2 ulp
+        upd = np.abs(b - w0).max()
+        err = np.abs(a.astype(np.float64) - b).max()
+        bound = 5e-3 * upd + 2.4e-7 * np.abs(b).max() + 1e-3 * gmax   # last term: structurally-zero gradients
+        assert err <= bound, 'weight update %d %s: error %.3e exceeds %.3e (update scale %.3e)' % (
+            i, b.shape, err, bound, upd)
+
+
+# ---- case builders ----------------------------------------------------------------------------------
+def pe_case(n_pix, B, seed=0):
+    from gennet_b200 import nn, bbh
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(seed)
+    bbh.n_pix = n_pix
+    prod = bbh.signal_pe_model()
+    prod.compile(loss='mean_squared_error', optimizer=nn.Adam(lr=9e-5, beta_1=0.5), metrics=['accuracy'])
+    orc = ko.build(ko.bbh_signal_pe_model(n_pix), seed=seed + 1)
+    # positive head biases keep the ReLU heads active so the gradient check is not vacuous
+    orc.branches[0][-2].weights[1].data += 0.5
+    orc.branches[1][-2].weights[1].data += 0.5
+    orc.compile('mean_squared_error', ko.Adam(9e-5, beta_1=0.5))
+    sync_weights(prod, orc)
+    rs = np.random.RandomState(seed)
+    x = rs.normal(size=(B, n_pix, 1)).astype(np.float32)
+    y = [rs.uniform(0.2, 1.0, B).astype(np.float32), rs.uniform(0.5, 1.0, B).astype(np.float32)]
+    return prod, orc, x, y
+
+
+def gan_case(n_pix, B, seed=0):
+    """bbhMahoGANy.py GAN wiring: returns product and oracle (G, D, D_on_G) + inputs."""
+    from gennet_b200 import nn, bbh
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(seed)
+    bbh.n_pix = n_pix
+    rs = np.random.RandomState(seed)
+    noise_signal = rs.normal(size=(n_pix, 1)).astype(np.float32)
+    g, d, dg, sub_g = bbh.build_gan(noise_signal)
+    og = ko.build(ko.bbh_generator_model(n_pix), seed=seed + 1)
+    od = ko.build(ko.bbh_signal_discriminator_model(n_pix), seed=seed + 2)
+    osub = ko.Sequential([ko.StackResidual(noise_signal.astype(np.float64))])
+    ocomp = ko.Sequential([ko.Sequential([og, osub]), od])
+    ocomp.build((100,))
+    ko.set_trainable(od, False)
+    ocomp.compile('binary_crossentropy', ko.Adam(9e-5, beta_1=0.5))
+    ko.set_trainable(od, True)
+    od.compile('binary_crossentropy', ko.Adam(9e-5, beta_1=0.5))
+    sync_weights(g, og)
+    sync_weights(d, od)
+    z = rs.uniform(-1, 1, (B, 100)).astype(np.float32)
+    sX = rs.normal(size=(2 * B, n_pix, 2, 1)).astype(np.float32)
+    sy = np.array([1.0] * B + [0.0] * B, dtype=np.float32)
+    return (g, d, dg), (og, od, ocomp), z, sX, sy
+
+
+def burst_case(n_pix, B, seed=0):
+    from gennet_b200 import nn, burst
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(seed)
+    burst.n_pix = n_pix
+    rs = np.random.RandomState(seed)
+    noise_signal = rs.normal(size=(n_pix, 1)).astype(np.float32) * 0.25
+    g, d, dg, sub_g = burst.build_gan(noise_signal)
+    og = ko.build(ko.burst_generator_model(n_pix), seed=seed + 1)
+    od = ko.build(ko.burst_signal_discriminator_model(n_pix), seed=seed + 2)
+    osub = ko.Sequential([og, ko.Sequential([ko.ResidualMoments(noise_signal.astype(np.float64))])])
+    osub.build((100,))
+    osub.compile('mean_squared_error', ko.Adam(2e-4, beta_1=0.5))
+    ocomp = ko.Sequential([og, od])
+    ocomp.build((100,))
+    ko.set_trainable(od, False)
+    ocomp.compile('binary_crossentropy', ko.Adam(2e-4, beta_1=0.5))
+    ko.set_trainable(od, True)
+    od.compile('binary_crossentropy', ko.Adam(2e-4, beta_1=0.5))
+    sync_weights(g, og)
+    sync_weights(d, od)
+    z = rs.uniform(-1, 1, (B, 100)).astype(np.float32)
+    sX = rs.normal(size=(2 * B, n_pix, 1)).astype(np.float32)
+    sy = np.array([1.0] * B + [0.0] * B, dtype=np.float32)
+    ny = np.zeros((B, 2), dtype=np.float32)
+    ny[:, 1] = 0.25 ** 2
+    return (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny
+
+
+def wvf_case(out_dim, B, seed=0):
+    from gennet_b200 import nn, wvf
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(seed)
+    G_in = nn.Input(shape=[10])
+    G, _ = wvf.get_generative(G_in, out_dim=out_dim)
+    D_in = nn.Input(shape=[out_dim])
+    D, _ = wvf.get_discriminative(D_in)
+    GAN_in = nn.Input(shape=[10])
+    GAN, _ = wvf.make_gan(GAN_in, G, D)
+    og = ko.build(ko.wvf_get_generative(10, 300, out_dim), seed=seed + 1)
+    og.compile('binary_crossentropy', ko.SGD(0.425e-1))
+    od = ko.build(ko.wvf_get_discriminative(out_dim), seed=seed + 2)
+    od.compile('binary_crossentropy', ko.Adam(1e-6))
+    ogan = ko.Sequential([og, od])
+    ogan.build((10,))
+    ko.set_trainable(od, False)
+    ogan.compile('binary_crossentropy', og.optimizer)
+    sync_weights(G, og)
+    sync_weights(D, od)
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(0, 1, (2 * B, out_dim)).astype(np.float32)
+    y = np.zeros((2 * B, 2), np.float32)
+    y[:B, 1] = 1
+    y[B:, 0] = 1
+    z = rs.uniform(0, 1, (B, 10)).astype(np.float32)
+    yz = np.zeros((B, 2), np.float32)
+    yz[:, 1] = 1
+    return (G, D, GAN), (og, od, ogan), X, y, z, yz

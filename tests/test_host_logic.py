@@ -1,0 +1,99 @@
+"""Host-side logic (graph executor, Keras protocol, trainable sets, arenas, optimizer wiring) checked on
+the CPU against the float64 oracle, with the C ABI answered by tests/fake_backend.py."""
+import numpy as np
+import pytest
+
+from tests import fake_backend, parity_cases as pc
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    return fake_backend.install(monkeypatch)
+
+
+def test_pe_model_step_matches_oracle(fake):
+    prod, orc, x, y = pc.pe_case(128, 4)
+    out = prod.predict(x)
+    assert isinstance(out, list) and out[0].shape == (4, 1) and out[1].shape == (4, 1)
+    errs, w0 = pc.compare_step(prod, orc, x, y)
+    pc.compare_weights(prod, orc, w0)
+    # second step exercises Adam's t=2 bias correction and the persistent moments
+    errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)
+    pc.compare_weights(prod, orc, w0)
+
+
+def test_pe_returns_keras_shaped_list(fake):
+    prod, orc, x, y = pc.pe_case(128, 4)
+    r = prod.train_on_batch(x, y)
+    assert len(r) == 5          # [total, mc_loss, q_loss, mc_acc, q_acc]
+    assert abs(r[0] - (r[1] + r[2])) < 1e-6 * max(1.0, abs(r[0]))
+
+
+def test_gan_wiring_matches_oracle(fake):
+    (g, d, dg), (og, od, ocomp), z, sX, sy = pc.gan_case(64, 4)
+    # generator.predict uses BN moving statistics and no dropout
+    pc.assert_close(g.predict(z), og.predict(z), 'generator.predict')
+    dw0 = [w.copy() for w in d.get_weights()]
+    errs, w0 = pc.compare_step(d, od, sX, sy)
+    pc.compare_weights(d, od, w0)
+    assert any(np.abs(a - b).max() > 0 for a, b in zip(dw0, d.get_weights()))
+    # G step through the frozen D: D's weights must not move, G's must, BN moving stats must update
+    dw1 = [w.copy() for w in d.get_weights()]
+    gw1 = [w.copy() for w in g.get_weights()]
+    errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 4, check_predict=False)
+    assert all(np.array_equal(a, b) for a, b in zip(dw1, d.get_weights()))
+    assert any(not np.array_equal(a, b) for a, b in zip(gw1, g.get_weights()))
+    pc.compare_weights(g, og, [w for w in w0[:len(gw1)]])
+
+
+def test_burst_three_step_iteration(fake):
+    (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny = pc.burst_case(64, 4)
+    errs, w0 = pc.compare_step(d, od, sX, sy)
+    pc.compare_weights(d, od, w0)
+    errs, w0 = pc.compare_step(sub_g, osub, z, ny, check_predict=False)     # MSE on batch-global residual moments
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+    errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 4, check_predict=False)
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+
+
+def test_wvf_functional_models(fake):
+    (G, D, GAN), (og, od, ogan), X, y, z, yz = pc.wvf_case(256, 4)
+    pc.assert_close(G.predict(z), og.predict(z), 'G.predict')
+    errs, w0 = pc.compare_step(D, od, X, y)
+    pc.compare_weights(D, od, w0)
+    errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
+    pc.compare_weights(G, og, w0[:len(G.get_weights())])
+
+
+def test_upsampling_is_fused_into_following_conv(fake):
+    from gennet_b200 import nn, bbh
+    nn.clear_session()
+    bbh.n_pix = 64
+    g = bbh.generator_model()
+    ups = [l for l in g.layers if isinstance(l, nn.UpSampling1D)]
+    convs = [l for l in g.layers if isinstance(l, nn.Conv1D)]
+    assert len(ups) == 2 and all(u.fused for u in ups)
+    assert [c.fused_up for c in convs] == [2, 2, 1, 1, 1, 1]
+    assert g.output_shape == (64, 1)
+
+
+def test_param_arena_is_contiguous_and_shared(fake):
+    (g, d, dg), _, z, sX, sy = pc.gan_case(64, 2)
+    segs_g = dg._compiled['segments']
+    assert len(segs_g) == 1, 'all generator parameters should form one flat segment'
+    n_train = sum(p.numel() for l in g.all_layers() for p in l.params if p.trainable)
+    assert segs_g[0][1].numel() >= n_train
+    # the discriminator's parameters live in a different arena and form one segment of their own
+    assert len(d._compiled['segments']) == 1
+    assert d._compiled['segments'][0][0] != segs_g[0][0]
+
+
+def test_summary_and_counts(fake):
+    from gennet_b200 import nn, bbh
+    nn.clear_session()
+    bbh.n_pix = 1024
+    pe = bbh.signal_pe_model()
+    assert abs(pe.count_params() - 4.63e6) < 0.02e6
+    lines = []
+    pe.summary(print_fn=lines.append)
+    assert any('Total params' in l for l in lines)
