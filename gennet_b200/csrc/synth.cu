@@ -445,7 +445,7 @@ __global__ void add_scaled_kernel(float* __restrict__ x, const float* __restrict
     for (; i < n; i += stride) x[i] = fmaf(sigma, r[i], x[i]);
 }
 
-__global__ void burst_kernel(const float* __restrict__ pars, float* __restrict__ out, int n, int N, float amp,
+__global__ void burst_kernel(const double* __restrict__ pars, float* __restrict__ out, int n, int N, float amp,
                              float freq, float dt, float phi) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n * N) return;
@@ -603,7 +603,7 @@ extern "C" int gn_add_scaled_f32(float* x, const float* r, float sigma, long lon
     return cuda_status("add_scaled_kernel");
 }
 
-extern "C" int gn_burst_waveforms_f32(const float* pars, float* out, int n, int N, float amp, float freq, float dt,
+extern "C" int gn_burst_waveforms_f32(const double* pars, float* out, int n, int N, float amp, float freq, float dt,
                                       float phi, void* stream) {
     GN_REQUIRE(pars && out && n >= 0 && N > 0, "null pointer or bad size");
     if (n == 0) return GN_OK;

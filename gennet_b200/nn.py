@@ -932,21 +932,24 @@ class Model(Layer):
         outs = out if isinstance(out, list) else [out]
         ys = y if self._multi_out else [y]
         assert len(ys) == len(outs), 'expected %d target arrays' % len(outs)
-        inv_batch = 1.0 / (B * ctx.world)
         res = torch.zeros(2 * len(outs), dtype=torch.float32, device=xs.device)
-        dys = []
+        dys, invs = [], []
         for k, (o, t) in enumerate(zip(outs, ys)):
             vec = o.dim() == 1           # batch-global output (burst MyLayer)
             D = o.shape[-1]
-            tt = _to_device(t).reshape(B, -1)
+            # Keras: mean over the last axis, then over every remaining axis (batch and, e.g., time)
+            rows = B if vec else o.numel() // D
+            tt = _to_device(t).reshape(rows, -1)
             assert tt.shape[1] == D, 'target shape %s does not match output %s' % (tuple(tt.shape), tuple(o.shape))
+            inv_rows = 1.0 / (rows * ctx.world)
             d = torch.zeros_like(o) if vec else _empty(o.shape)
             metric_kind = 0 if (D == 1 or c['loss'].kind == _lib.LOSS_BCE) else 1
             call('gn_loss_fwd_bwd_f32', ptr(o.contiguous()), ptr(tt.contiguous()), ptr(res[2 * k:2 * k + 2]), ptr(d),
-                 B, D, c['loss'].kind, c['loss'].param, inv_batch, 1 if vec else 0, metric_kind, stream())
+                 rows, D, c['loss'].kind, c['loss'].param, inv_rows, 1 if vec else 0, metric_kind, stream())
             if vec and ctx.world > 1:
                 ctx.dp.all_reduce(d)
             dys.append(d)
+            invs += [inv_rows, inv_rows]
         self.backward(dys if self._multi_out else dys[0], ctx, need_dx=False)
         segs = c['segments']
         if ctx.world > 1:
@@ -954,7 +957,10 @@ class Model(Layer):
                 ctx.dp.all_reduce(g)
             ctx.dp.all_reduce(res)
         self.optimizer.apply(segs, 1.0)
-        res = res * inv_batch
+        if len(set(invs)) == 1:
+            res = res * invs[0]
+        else:
+            res = res * torch.tensor(invs, dtype=torch.float32, device=res.device)
         if _return_device:
             return res
         r = res.detach().cpu().numpy().astype(np.float64)      # the D2H read of the step's loss / metric

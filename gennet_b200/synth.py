@@ -202,8 +202,12 @@ class Synthesizer:
         lo, ln = (self.crop_lo, self.crop_len) if crop else (0, self.N)
         out = torch.empty((B, ln), dtype=torch.float32, device=hp.device)
         ref = torch.empty(B, dtype=torch.int32, device=hp.device)
-        call('gn_bbh_assemble_f32', ptr(hp), ptr(hc), ptr(_dev(np.broadcast_to(Fp, (B,)))),
-             ptr(_dev(np.broadcast_to(Fc, (B,)))), ptr(_dev(np.broadcast_to(idx, (B,)), torch.int32), torch.int32),
+        # keep the staged arguments alive until the launch is enqueued (a freed temporary's block could be
+        # handed to the next staging copy before the kernel reads it)
+        fp_d = _dev(np.broadcast_to(np.asarray(Fp, np.float32), (B,)))
+        fc_d = _dev(np.broadcast_to(np.asarray(Fc, np.float32), (B,)))
+        idx_d = _dev(np.broadcast_to(np.asarray(idx, np.int32), (B,)), torch.int32)
+        call('gn_bbh_assemble_f32', ptr(hp), ptr(hc), ptr(fp_d), ptr(fc_d), ptr(idx_d, torch.int32),
              self.lead, ptr(self.signal_window), ptr(out), ptr(ref, torch.int32), B, self.N, lo, ln, float(scale),
              stream())
         return out, ref
@@ -332,7 +336,8 @@ def make_burst_waveforms(N_sig, amp=1, freq=100, dt=1.0 / 512, N=512, t_0=0.5, p
             tau = r.uniform(1.0 / 60.0, 1.0 / 15.0)
         pars[i] = (t_0, tau)
     out = torch.empty((N_sig, N), dtype=torch.float32, device=device())
-    call('gn_burst_waveforms_f32', ptr(_dev(pars)), ptr(out), N_sig, N, float(amp), float(freq), float(dt),
+    pars_d = _dev(pars, torch.float64)
+    call('gn_burst_waveforms_f32', ptr(pars_d, torch.float64), ptr(out), N_sig, N, float(amp), float(freq), float(dt),
          float(phi), stream())
     return out.cpu().numpy().astype(np.float64), pars
 

@@ -104,8 +104,8 @@ int gn_mean_std_f32(const float* x, long long n, float* out, void* stream);
 int gn_add_scaled_f32(float* x, const float* r, float sigma, long long n, void* stream);
 
 /* sine-Gaussian bursts, tests/burstMahoGANy.py:76-98: out[i,j] = amp*sin(2*pi*freq*(t_j-t0_i)+phi)*exp(-(t_j-t0_i)^2/tau_i^2)
- * pars (n,2) f32 = (t0, tau) */
-int gn_burst_waveforms_f32(const float* pars, float* out, int n, int N, float amp, float freq, float dt,
+ * pars (n,2) f64 = (t0, tau): kept in double because the phase 2*pi*f*(t-t0) reaches ~300 rad */
+int gn_burst_waveforms_f32(const double* pars, float* out, int n, int N, float amp, float freq, float dt,
                            float phi, void* stream);
 
 /* ---------------------------------------------------------------------------

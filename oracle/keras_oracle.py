@@ -46,6 +46,11 @@ class Layer:
         return [self]
 
 
+def _kink(noise, layer):
+    k = noise.get('__kinks__') if isinstance(noise, dict) else None
+    return None if k is None else k.get(layer.name)
+
+
 def glorot_uniform(shape, fan_in, fan_out, gen, dtype):
     lim = math.sqrt(6.0 / (fan_in + fan_out))  # [A12]
     return ((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * lim).to(dtype).requires_grad_(True)
@@ -65,7 +70,7 @@ class Dense(Layer):
         return in_shape[:-1] + (self.units,)
 
     def forward(self, x, training, noise):
-        return apply_activation(x @ self.weights[0] + self.weights[1], self.activation)
+        return apply_activation(x @ self.weights[0] + self.weights[1], self.activation, _kink(noise, self))
 
 
 class Conv1D(Layer):
@@ -91,7 +96,7 @@ class Conv1D(Layer):
         if self.padding == 'same':
             xt = F.pad(xt, same_pad(x.shape[1], self.k, self.s))
         y = F.conv1d(xt, self.weights[0].permute(2, 1, 0), self.weights[1], stride=self.s)
-        return apply_activation(y.permute(0, 2, 1), self.activation)
+        return apply_activation(y.permute(0, 2, 1), self.activation, _kink(noise, self))
 
 
 class Conv2D(Layer):
@@ -151,11 +156,49 @@ class BatchNormalization(Layer):
         return (x - mean) / torch.sqrt(var + self.epsilon) * g + b
 
 
-def apply_activation(x, act):
+KINK_TOL = 2e-6
+
+
+def _fed_mask(x, own, ykink, cond):
+    """Piecewise-linear activations have kinks where float32 and float64 can land on different sides.
+    Like RNG draws, the side taken by the implementation under test may be fed in (its OUTPUT `ykink`):
+    the oracle then differentiates the same linear piece -- but only where its own pre-activation is
+    within rounding distance (KINK_TOL of the tensor's scale) of the kink; any other disagreement is an
+    error of the implementation and raises."""
+    fed = cond(torch.as_tensor(np.asarray(ykink)).reshape(x.shape))
+    diff = fed != own
+    if diff.any():
+        lim = KINK_TOL * max(float(x.detach().abs().max()), 1e-30)
+        worst = float(x.detach()[diff].abs().max())
+        return fed, worst, lim
+    return fed, 0.0, 1.0
+
+
+def relu_like(x, lo_slope=0.0, max_value=None, ykink=None):
+    """max(x,0) (or leaky) optionally clipped at max_value, with optionally fed kink decisions."""
+    pos = x > 0 if lo_slope == 0.0 else x >= 0
+    if ykink is not None:
+        pos, worst, lim = _fed_mask(x, pos, ykink, (lambda y: y > 0) if lo_slope == 0.0 else (lambda y: y >= 0))
+        assert worst <= lim, 'activation sign disagrees with the oracle away from the kink (|x|=%g > %g)' % (worst, lim)
+    y = torch.where(pos, x, x * lo_slope)
+    if max_value is not None:
+        below = x < max_value
+        if ykink is not None:
+            fed = torch.as_tensor(np.asarray(ykink)).reshape(x.shape) < max_value
+            diff = fed != below
+            if diff.any():
+                worst = float((x.detach()[diff] - max_value).abs().max())
+                assert worst <= KINK_TOL * max(float(x.detach().abs().max()), 1e-30), 'clip side disagrees'
+            below = fed
+        y = torch.where(below, y, torch.full_like(y, max_value))
+    return y
+
+
+def apply_activation(x, act, ykink=None):
     if act in (None, 'linear'):
         return x
     if act == 'relu':
-        return torch.relu(x)
+        return relu_like(x, ykink=ykink)
     if act == 'tanh':
         return torch.tanh(x)
     if act == 'sigmoid':
@@ -171,7 +214,7 @@ class Activation(Layer):
         self.act = act
 
     def forward(self, x, training, noise):
-        return apply_activation(x, self.act)
+        return apply_activation(x, self.act, _kink(noise, self))
 
 
 class LeakyReLU(Layer):
@@ -182,7 +225,7 @@ class LeakyReLU(Layer):
         self.alpha = alpha
 
     def forward(self, x, training, noise):
-        return torch.where(x >= 0, x, x * self.alpha)  # [A7]
+        return relu_like(x, lo_slope=self.alpha, ykink=_kink(noise, self))  # [A7]
 
 
 class ReLU(Layer):
@@ -193,8 +236,7 @@ class ReLU(Layer):
         self.max_value = max_value
 
     def forward(self, x, training, noise):
-        y = torch.relu(x)
-        return y if self.max_value is None else torch.clamp(y, max=self.max_value)
+        return relu_like(x, max_value=self.max_value, ykink=_kink(noise, self))
 
 
 class _NoiseLayer(Layer):

@@ -14,7 +14,8 @@ def test_pe_step_parity():
     prod, orc, x, y = pc.pe_case(256, 8)
     errs, w0 = pc.compare_step(prod, orc, x, y)
     pc.compare_weights(prod, orc, w0)
-    errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)
+    pc.resync([(prod, orc)])
+    errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)      # t=2: bias correction, persistent moments
     pc.compare_weights(prod, orc, w0)
 
 
@@ -23,11 +24,13 @@ def test_gan_steps_parity():
     pc.assert_close(g.predict(z), og.predict(z), 'generator.predict')
     errs, w0 = pc.compare_step(d, od, sX, sy)
     pc.compare_weights(d, od, w0)
+    pc.resync([(d, od)])
     dw = [w.copy() for w in d.get_weights()]
     errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 8, check_predict=False)
     assert all(np.array_equal(a, b) for a, b in zip(dw, d.get_weights()))
     pc.compare_weights(g, og, w0[:len(g.get_weights())])
     # moving statistics were updated by the training-mode pass and drive the next predict
+    pc.resync([(g, og)])
     pc.assert_close(g.predict(z), og.predict(z), 'generator.predict after step')
 
 
@@ -35,8 +38,10 @@ def test_burst_iteration_parity():
     (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny = pc.burst_case(64, 8)
     errs, w0 = pc.compare_step(d, od, sX, sy)
     pc.compare_weights(d, od, w0)
+    pc.resync([(d, od)])
     errs, w0 = pc.compare_step(sub_g, osub, z, ny, check_predict=False)
     pc.compare_weights(g, og, w0[:len(g.get_weights())])
+    pc.resync([(g, og)])
     errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 8, check_predict=False)
     pc.compare_weights(g, og, w0[:len(g.get_weights())])
 
@@ -46,6 +51,7 @@ def test_wvf_models_parity():
     pc.assert_close(G.predict(z), og.predict(z), 'G.predict')
     errs, w0 = pc.compare_step(D, od, X, y)
     pc.compare_weights(D, od, w0)
+    pc.resync([(D, od)])
     errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
     pc.compare_weights(G, og, w0[:len(G.get_weights())])
 

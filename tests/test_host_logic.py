@@ -18,6 +18,7 @@ def test_pe_model_step_matches_oracle(fake):
     errs, w0 = pc.compare_step(prod, orc, x, y)
     pc.compare_weights(prod, orc, w0)
     # second step exercises Adam's t=2 bias correction and the persistent moments
+    pc.resync([(prod, orc)])
     errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)
     pc.compare_weights(prod, orc, w0)
 
@@ -38,6 +39,7 @@ def test_gan_wiring_matches_oracle(fake):
     pc.compare_weights(d, od, w0)
     assert any(np.abs(a - b).max() > 0 for a, b in zip(dw0, d.get_weights()))
     # G step through the frozen D: D's weights must not move, G's must, BN moving stats must update
+    pc.resync([(d, od)])
     dw1 = [w.copy() for w in d.get_weights()]
     gw1 = [w.copy() for w in g.get_weights()]
     errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 4, check_predict=False)
@@ -50,8 +52,10 @@ def test_burst_three_step_iteration(fake):
     (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny = pc.burst_case(64, 4)
     errs, w0 = pc.compare_step(d, od, sX, sy)
     pc.compare_weights(d, od, w0)
+    pc.resync([(d, od)])
     errs, w0 = pc.compare_step(sub_g, osub, z, ny, check_predict=False)     # MSE on batch-global residual moments
     pc.compare_weights(g, og, w0[:len(g.get_weights())])
+    pc.resync([(g, og)])
     errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 4, check_predict=False)
     pc.compare_weights(g, og, w0[:len(g.get_weights())])
 
@@ -61,6 +65,7 @@ def test_wvf_functional_models(fake):
     pc.assert_close(G.predict(z), og.predict(z), 'G.predict')
     errs, w0 = pc.compare_step(D, od, X, y)
     pc.compare_weights(D, od, w0)
+    pc.resync([(D, od)])
     errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
     pc.compare_weights(G, og, w0[:len(G.get_weights())])
 
