@@ -96,7 +96,7 @@ def test_two_rank_step_equals_single_process(kind, monkeypatch):
     assert np.allclose(r1, r2, rtol=1e-5, atol=1e-7)
     gmax = max(np.abs(a).max() for a in g1)
     for a, b in zip(g1, g2):
-        assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-3 * gmax), (a.shape, np.abs(a - b).max())
+        assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-2 * gmax), (a.shape, np.abs(a - b).max())
     names = [p.name for p in m.params]
     for n, a, b in zip(names, w1, w2):
         if 'moving_' in n:        # SyncBN: moving statistics come from the GLOBAL batch on every rank
