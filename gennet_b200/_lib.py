@@ -34,6 +34,12 @@ _SIGS = {
     'gn_conv1d_fwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_dgrad_f32': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_wgrad_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv_w_to_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    'gn_cast_f32_to_bf16': [c_p, c_p, c_ll, c_p],
+    'gn_cast_bf16_to_f32': [c_p, c_p, c_ll, c_p],
+    'gn_conv1d_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_conv1d_dgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_conv1d_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv2d_w2_pack_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv2d_w2_unpack_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_dense_fwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],

@@ -1,0 +1,655 @@
+// Conv1D as implicit GEMM on the 5th-generation tensor cores (tcgen05) -- the throughput path.
+//
+//   bf16 activations (channels-last) and weights, fp32 accumulation in tensor memory (TMEM).
+//   Operand tiles are fetched by TMA (cp.async.bulk.tensor, SWIZZLE_128B) straight out of the NLC
+//   activation tensor: one (tap, 64-channel) slab per pipeline stage, zero padding / sample boundaries /
+//   ragged tails come from TMA out-of-bounds zero fill, stride-2 convolutions from the TMA traversal stride.
+//   Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+//   tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld -> bias / activation / mask -> bf16 global store).
+//
+//   forward : Y[b,l,co]  = act( sum_{t,ci} X[b, l*s+t-p, ci] * W[t,ci,co] + bias[co] )      A=X   (K-major)  B=Wt[t][co][ci]
+//   dgrad   : dX[b,j,ci] = act'(Xin[b,j,ci]) * sum_{t,co} dY[b,(j+p-t)/s,co] * W[t,ci,co]    A=dY  (K-major)  B=W [t][ci][co]
+//   wgrad   : dW[t,ci,co] = sum_{b,l} X[b,l*s+t-p,ci] * dY[b,l,co]                           A=X^T, B=dY (both MN-major)
+//
+// Reference call sites: Conv1D layers of bbhMahoGANy.py:250-292,362-395 (cuDNN fp32 in the reference).
+#include "gn_common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace gn {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i of the warp = lane base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (SM100 UMMA): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 =1), majors (15,16), N>>3 (17-22), M>>4 (24-28)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int TC_BM = 128;          // rows of an output tile (UMMA M)
+constexpr int TC_BK = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+struct TcArgs {
+    int B, L, Lout, Cin, Cout, k, s, p;   // convolution geometry (L = input length, Lout = output length)
+    int mode;                              // 0 fwd, 1 dgrad
+    int act;                               // fwd: output activation; dgrad: derivative mask of `aux` (input activation)
+    float act_param;
+    const float* bias;                     // fwd
+    const __nv_bfloat16* aux;              // dgrad: the conv's own input X (post-activation of the previous layer) or null
+    __nv_bfloat16* out;                    // fwd: Y (B,Lout,Cout); dgrad: dX (B,L,Cin)
+    int m_tiles;                           // tiles of 128 rows per (sample, parity)
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+    static constexpr int A_BYTES = TC_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ fwd / dgrad
+// grid: x = m-tile (within a sample and parity class), y = n-tile, z = sample * n_parity + parity
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = TcSmem<BN, STAGES>;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npar = (a.mode == 1) ? a.s : 1;
+    const int b = blockIdx.z / npar, par = blockIdx.z - b * npar;
+    const int m0 = blockIdx.x * TC_BM;      // first output row of this tile (within sample & parity class)
+    const int n0 = blockIdx.y * BN;
+    const int kdim = (a.mode == 0) ? a.Cin : a.Cout;   // contraction channels
+    const int nkb = kdim / TC_BK;
+
+    // taps that contribute: fwd all; dgrad those with (par + p - t) % s == 0
+    int tap_first = 0, tap_step = 1, ntaps = a.k;
+    if (a.mode == 1) {
+        tap_first = (par + a.p) % a.s;
+        tap_step = a.s;
+        ntaps = (a.k - tap_first + a.s - 1) / a.s;
+    }
+    const int niter = ntaps * nkb;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < niter; ++it) {
+                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                const int ti = it / nkb, kb = it - ti * nkb;
+                const int tap = tap_first + ti * tap_step;
+                uint8_t* sA = tiles + st * S::STAGE_BYTES;
+                uint8_t* sB = sA + S::A_BYTES;
+                mbar_expect_tx(&full[st], S::STAGE_BYTES);
+                int rowc;    // first row coordinate (global, pre-stride) along the length axis of A
+                if (a.mode == 0) rowc = m0 * a.s + tap - a.p;
+                else rowc = m0 + (par + a.p - tap) / a.s;
+                tma_load_3d(sA, &mapA, &full[st], kb * TC_BK, rowc, b);
+                tma_load_3d(sB, &mapB, &full[st], kb * TC_BK, n0, tap);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+            for (int it = 0; it < niter; ++it) {
+                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t sA = base + st * S::STAGE_BYTES;
+                const uint32_t sB = sA + S::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    uint64_t da = make_desc(sA + k * 32, 16, 1024);
+                    uint64_t db = make_desc(sB + k * 32, 16, 1024);
+                    tc_mma_bf16(tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(&empty[st]);      // frees the smem stage once the MMAs have read it
+            }
+            tc_commit(tmem_full);           // accumulator complete
+        }
+    } else {
+        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (rows of the tile)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int r = m0 + row;              // row index within (sample, parity)
+        bool valid;
+        size_t off;                          // element offset of (row, n0) in the output tensor
+        int ncols;                           // channels of the output tensor
+        if (a.mode == 0) {
+            valid = r < a.Lout;
+            ncols = a.Cout;
+            off = ((size_t)b * a.Lout + r) * a.Cout + n0;
+        } else {
+            const int j = r * a.s + par;
+            valid = j < a.L;
+            ncols = a.Cin;
+            off = ((size_t)b * a.L + j) * a.Cin + n0;
+        }
+        (void)ncols;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (valid) {
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (a.mode == 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float t = f[i] + (a.bias ? __ldg(&a.bias[n0 + c0 + i]) : 0.f);
+                        f[i] = act_fwd(t, a.act, a.act_param);
+                    }
+                } else if (a.aux != nullptr && a.act != GN_ACT_NONE) {
+                    const uint4* xin = reinterpret_cast<const uint4*>(a.aux + off + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 pk = __ldg(&xin[g]);
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 y = __bfloat1622float2(h[e]);
+                            f[g * 8 + 2 * e] *= act_bwd_from_y(y.x, a.act, a.act_param);
+                            f[g * 8 + 2 * e + 1] *= act_bwd_from_y(y.y, a.act, a.act_param);
+                        }
+                    }
+                }
+                uint4* dst = reinterpret_cast<uint4*>(a.out + off + c0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    dst[g] = pk;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// dW[t, ci, co] (fp32, atomically accumulated; caller zeroes) = sum over (b, l) of X[b, l*s+t-p, ci] * dY[b, l, co]
+// grid: x = tap, y = (ci tile of 128) * n_co_tiles + (co tile of BN), z = split over (b, l-block of 64)
+// SWAP (Cin == 64): the 128-row operand is dY (co) and the BN(=64)-column operand is X (ci).
+struct TcWgradArgs {
+    int B, L, Lout, Cin, Cout, k, s, p;
+    int lblocks;        // ceil(Lout / 64)
+    int iters_total;    // B * lblocks
+    int iters_per_split;
+    int n_tiles_n;      // number of N tiles
+    float* dw;          // (k, Cin, Cout) fp32
+};
+
+template <int BN, int STAGES, bool SWAP>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                     TcWgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int A_BYTES = TC_BM * 128;      // 128 (MN) x 64 (K) bf16 = two 64x64 MN-major blocks of 8 KB
+    constexpr int B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.x;
+    const int mt = blockIdx.y / a.n_tiles_n, nt = blockIdx.y - mt * a.n_tiles_n;
+    const int m0 = mt * TC_BM, n0 = nt * BN;       // m: 128-row operand channel offset, n: BN-col operand offset
+    const int it0 = blockIdx.z * a.iters_per_split;
+    const int it1 = min(a.iters_total, it0 + a.iters_per_split);
+    const int niter = max(it1 - it0, 0);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapDY);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < niter; ++i) {
+                const int st = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                const int it = it0 + i;
+                const int bb = it / a.lblocks, lb = it - bb * a.lblocks;
+                const int l0 = lb * 64;
+                uint8_t* sA = tiles + st * STAGE_BYTES;
+                uint8_t* sB = sA + A_BYTES;
+                mbar_expect_tx(&full[st], STAGE_BYTES);
+                const int xrow = l0 * a.s + tap - a.p;     // X position of output position l0 for this tap
+                // 128-row operand: two 64-channel blocks; BN-column operand: BN/64 blocks
+                if (!SWAP) {
+                    tma_load_3d(sA, &mapX, &full[st], m0, xrow, bb);
+                    tma_load_3d(sA + 8192, &mapX, &full[st], m0 + 64, xrow, bb);
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h) tma_load_3d(sB + h * 8192, &mapDY, &full[st], n0 + h * 64, l0, bb);
+                } else {
+                    tma_load_3d(sA, &mapDY, &full[st], m0, l0, bb);
+                    tma_load_3d(sA + 8192, &mapDY, &full[st], m0 + 64, l0, bb);
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h) tma_load_3d(sB + h * 8192, &mapX, &full[st], n0 + h * 64, xrow, bb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TC_BM, BN, 1, 1);     // both operands MN-major
+            for (int i = 0; i < niter; ++i) {
+                const int st = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t sA = base + st * STAGE_BYTES;
+                const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 64 / 16; ++k) {
+                    // MN-major SW128: 64-element MN blocks LBO = 8192 B apart, 8-row K groups SBO = 1024 B apart;
+                    // 16 K rows per instruction = 2048 B
+                    uint64_t da = make_desc(sA + k * 2048, 8192, 1024);
+                    uint64_t db = make_desc(sB + k * 2048, 8192, 1024);
+                    tc_mma_bf16(tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(&empty[st]);
+            }
+            tc_commit(tmem_full);
+        }
+    } else if (niter > 0) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float f = __uint_as_float(v[i]);
+                int ci, co;
+                if (!SWAP) { ci = m0 + row; co = n0 + c0 + i; } else { co = m0 + row; ci = n0 + c0 + i; }
+                atomicAdd(&a.dw[((size_t)tap * a.Cin + ci) * a.Cout + co], f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+// weights: f32 (k,Cin,Cout) -> bf16 same layout (dgrad B operand: K = co contiguous) and bf16 transposed
+// (k,Cout,Cin) (forward B operand: K = ci contiguous)
+__global__ void __launch_bounds__(256) conv_w_cast_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wk,
+                                                          __nv_bfloat16* __restrict__ wt, int k, int Cin, int Cout) {
+    const long long n = (long long)k * Cin * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int co = (int)(i % Cout);
+        long long r = i / Cout;
+        int ci = (int)(r % Cin);
+        int t = (int)(r / Cin);
+        __nv_bfloat16 h = __float2bfloat16_rn(w[i]);
+        wk[i] = h;
+        wt[((size_t)t * Cout + co) * Cin + ci] = h;
+    }
+}
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                                            long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __bfloat162float(x[i]);
+}
+// per-channel sum of a (rows, C) bf16 matrix -> f32 (bias gradient); out must be zeroed by the caller
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
+                                                          long long rows_per_split, float* __restrict__ out) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
+    float s = 0.f;
+    if (c < C)
+        for (long long r = r0 + ry; r < r1; r += 8) s += __bfloat162float(x[r * C + c]);
+    sm[ry][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+        atomicAdd(&out[c], t);
+    }
+}
+
+// ---- host side: tensor maps -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D bf16 tensor map: dims (d0 contiguous, d1, d2), strides in elements for d1, d2; box (b0, b1, 1); traversal
+// stride es1 along d1 (box extent b1*es1 in global coordinates -> b1 rows in shared memory)
+static int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t st1, uint64_t st2,
+                     uint32_t b0, uint32_t b1, uint32_t es1) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return fail(GN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s", "");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {st1 * 2, st2 * 2};
+    cuuint32_t box[3] = {b0, b1 * es1, 1};
+    cuuint32_t estr[3] = {1, es1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%s code %lld)", "", (long long)r);
+    return GN_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, dim3 grid, cudaStream_t st) {
+    auto kfn = conv_tc_kernel<BN, STAGES>;
+    constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    kfn<<<grid, TC_THREADS, smem, st>>>(mA, mB, a);
+    return cuda_status("conv_tc_kernel");
+}
+
+template <int BN, int STAGES, bool SWAP>
+static int launch_wgrad_tc(const CUtensorMap& mX, const CUtensorMap& mDY, const TcWgradArgs& a, dim3 grid,
+                           cudaStream_t st) {
+    auto kfn = conv_tc_wgrad_kernel<BN, STAGES, SWAP>;
+    constexpr int smem = STAGES * (TC_BM * 128 + BN * 128) + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    kfn<<<grid, TC_THREADS, smem, st>>>(mX, mDY, a);
+    return cuda_status("conv_tc_wgrad_kernel");
+}
+
+static int check_tc_geom(int B, int L, int Cin, int Lout, int Cout, int k, int s, int p) {
+    GN_REQUIRE(B > 0 && L > 0 && Lout > 0 && k > 0 && k <= 16 && (s == 1 || s == 2) && p >= 0 && p < k, "bad geometry");
+    GN_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tensor-core path needs Cin and Cout to be multiples of 64");
+    GN_REQUIRE(B <= 65535, "batch too large for one launch");
+    return GN_OK;
+}
+
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" int gn_conv_w_to_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, void* stream) {
+    GN_REQUIRE(w && wk && wt && k > 0 && Cin > 0 && Cout > 0, "null pointer or bad size");
+    long long n = (long long)k * Cin * Cout;
+    unsigned grid = (unsigned)((n + 255) / 256 < 8LL * num_sms() ? (n + 255) / 256 : 8LL * num_sms());
+    conv_w_cast_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
+    return cuda_status("conv_w_cast_kernel");
+}
+
+extern "C" int gn_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
+    GN_REQUIRE(x && y && n >= 0, "null pointer or n < 0");
+    if (n == 0) return GN_OK;
+    unsigned grid = (unsigned)((n + 255) / 256 < 16LL * num_sms() ? (n + 255) / 256 : 16LL * num_sms());
+    cast_f32_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)y, n);
+    return cuda_status("cast_f32_bf16_kernel");
+}
+
+extern "C" int gn_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream) {
+    GN_REQUIRE(x && y && n >= 0, "null pointer or n < 0");
+    if (n == 0) return GN_OK;
+    unsigned grid = (unsigned)((n + 255) / 256 < 16LL * num_sms() ? (n + 255) / 256 : 16LL * num_sms());
+    cast_bf16_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, y, n);
+    return cuda_status("cast_bf16_f32_kernel");
+}
+
+extern "C" int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bias, void* y, int B, int L, int Cin,
+                                  int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param,
+                                  void* stream) {
+    GN_REQUIRE(x && wt && y, "null pointer");
+    int rc = check_tc_geom(B, L, Cin, Lout, Cout, k, stride, pad_left);
+    if (rc != GN_OK) return rc;
+    CUtensorMap mA, mB;
+    const int BN = (Cout % 128 == 0) ? 128 : 64;
+    // A: X viewed as (Cin, L, B); 128 output rows per tile, traversal stride = conv stride
+    rc = make_map3(&mA, x, Cin, L, B, Cin, (uint64_t)L * Cin, TC_BK, TC_BM, stride);
+    if (rc != GN_OK) return rc;
+    // B: Wt (k, Cout, Cin) viewed as (Cin, Cout, k)
+    rc = make_map3(&mB, wt, Cin, Cout, k, Cin, (uint64_t)Cout * Cin, TC_BK, BN, 1);
+    if (rc != GN_OK) return rc;
+    TcArgs a{};
+    a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
+    a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = (__nv_bfloat16*)y;
+    a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
+    dim3 grid(a.m_tiles, Cout / BN, B);
+    if (BN == 128) return launch_conv_tc<128, 4>(mA, mB, a, grid, as_stream(stream));
+    return launch_conv_tc<64, 4>(mA, mB, a, grid, as_stream(stream));
+}
+
+extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, int B, int L, int Cin,
+                                    int Lout, int Cout, int k, int stride, int pad_left, int in_act, float in_act_param,
+                                    void* stream) {
+    GN_REQUIRE(dy && wk && dx, "null pointer");
+    int rc = check_tc_geom(B, L, Cin, Lout, Cout, k, stride, pad_left);
+    if (rc != GN_OK) return rc;
+    CUtensorMap mA, mB;
+    const int BN = (Cin % 128 == 0) ? 128 : 64;
+    // A: dY viewed as (Cout, Lout, B), 128 rows, unit traversal stride (parity classes handle the conv stride)
+    rc = make_map3(&mA, dy, Cout, Lout, B, Cout, (uint64_t)Lout * Cout, TC_BK, TC_BM, 1);
+    if (rc != GN_OK) return rc;
+    // B: W (k, Cin, Cout) viewed as (Cout, Cin, k)
+    rc = make_map3(&mB, wk, Cout, Cin, k, Cout, (uint64_t)Cin * Cout, TC_BK, BN, 1);
+    if (rc != GN_OK) return rc;
+    TcArgs a{};
+    a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
+    a.mode = 1; a.act = in_act; a.act_param = in_act_param; a.aux = (const __nv_bfloat16*)x_in;
+    a.out = (__nv_bfloat16*)dx;
+    const int rows = (L + stride - 1) / stride;      // rows of the largest parity class
+    a.m_tiles = (rows + TC_BM - 1) / TC_BM;
+    GN_REQUIRE((long long)B * stride <= 65535, "batch too large for one launch");
+    dim3 grid(a.m_tiles, Cin / BN, B * stride);
+    if (BN == 128) return launch_conv_tc<128, 4>(mA, mB, a, grid, as_stream(stream));
+    return launch_conv_tc<64, 4>(mA, mB, a, grid, as_stream(stream));
+}
+
+extern "C" int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
+                                    int Cout, int k, int stride, int pad_left, void* stream) {
+    GN_REQUIRE(x && dy && dw, "null pointer");
+    int rc = check_tc_geom(B, L, Cin, Lout, Cout, k, stride, pad_left);
+    if (rc != GN_OK) return rc;
+    GN_REQUIRE(Cin % 128 == 0 || (Cin == 64 && Cout % 128 == 0), "wgrad needs Cin % 128 == 0, or Cin == 64 with Cout % 128 == 0");
+    cudaStream_t st = as_stream(stream);
+    CUtensorMap mX, mDY;
+    // X (Cin, L, B): 64 channels x 64 positions (traversal stride = conv stride); dY (Cout, Lout, B): 64 x 64
+    rc = make_map3(&mX, x, Cin, L, B, Cin, (uint64_t)L * Cin, 64, 64, stride);
+    if (rc != GN_OK) return rc;
+    rc = make_map3(&mDY, dy, Cout, Lout, B, Cout, (uint64_t)Lout * Cout, 64, 64, 1);
+    if (rc != GN_OK) return rc;
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin * Cout, st);
+    TcWgradArgs a{};
+    a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
+    a.lblocks = (Lout + 63) / 64;
+    a.iters_total = B * a.lblocks;
+    a.dw = dw;
+    const bool swap = (Cin == 64);
+    int m_tiles, BN;
+    if (!swap) { m_tiles = Cin / 128; BN = (Cout % 128 == 0) ? 128 : 64; a.n_tiles_n = Cout / BN; }
+    else { m_tiles = Cout / 128; BN = 64; a.n_tiles_n = 1; }
+    const int out_tiles = k * m_tiles * a.n_tiles_n;
+    int splits = (2 * num_sms() + out_tiles - 1) / out_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > a.iters_total) splits = a.iters_total;
+    a.iters_per_split = (a.iters_total + splits - 1) / splits;
+    splits = (a.iters_total + a.iters_per_split - 1) / a.iters_per_split;
+    dim3 grid(k, m_tiles * a.n_tiles_n, splits);
+    if (swap) rc = launch_wgrad_tc<64, 4, true>(mX, mDY, a, grid, st);
+    else if (BN == 128) rc = launch_wgrad_tc<128, 4, false>(mX, mDY, a, grid, st);
+    else rc = launch_wgrad_tc<64, 4, false>(mX, mDY, a, grid, st);
+    if (rc != GN_OK) return rc;
+    if (db != nullptr) {
+        cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);
+        const long long rows = (long long)B * Lout;
+        int cb = (Cout + 31) / 32;
+        long long sp = (4LL * num_sms() + cb - 1) / cb;
+        if (sp > (rows + 63) / 64) sp = (rows + 63) / 64;
+        if (sp < 1) sp = 1;
+        long long per = (rows + sp - 1) / sp;
+        sp = (rows + per - 1) / per;
+        colsum_bf16_kernel<<<dim3(cb, (unsigned)sp), 256, 0, st>>>((const __nv_bfloat16*)dy, rows, Cout, per, db);
+        return cuda_status("colsum_bf16_kernel");
+    }
+    return GN_OK;
+}

@@ -127,6 +127,25 @@ int gn_conv1d_dgrad_f32(const float* dy, const float* w, float* dx, int B, int L
 int gn_conv1d_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
                         int Cout, int k, int stride, int pad_left, int up, void* stream);
 
+/* ---- tensor-core (tcgen05 + TMA) Conv1D, bf16 activations/weights, fp32 accumulation --------------------
+ * Same semantics as gn_conv1d_*_f32 for k <= 16, stride 1 or 2, Cin % 64 == 0 and Cout % 64 == 0 (the first,
+ * Cin=1, and last, Cout=1, layers of the reference networks are bandwidth-bound and stay on the SIMT kernels).
+ * All activation / weight pointers are bf16 device memory, 16-byte aligned.
+ *   gn_conv_w_to_bf16 : w f32 (k,Cin,Cout) -> wk bf16 (k,Cin,Cout) [dgrad operand] and wt bf16 (k,Cout,Cin) [fwd operand]
+ *   fwd   : y = act(conv(x, w) + bias)                      x (B,L,Cin), y (B,Lout,Cout)
+ *   dgrad : dx = act'(x_in) * conv_transpose(dy, w)         x_in = this conv's input (or NULL): fuses the backward
+ *           of the activation layer that produced x_in (in_act = its GN_ACT_* code)
+ *   wgrad : dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN  (needs Cin % 128 == 0, or Cin == 64 and Cout % 128 == 0) */
+int gn_conv_w_to_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, void* stream);
+int gn_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+int gn_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
+int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bias, void* y, int B, int L, int Cin, int Lout,
+                       int Cout, int k, int stride, int pad_left, int act, float act_param, void* stream);
+int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, int B, int L, int Cin, int Lout,
+                         int Cout, int k, int stride, int pad_left, int in_act, float in_act_param, void* stream);
+int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
+                         int Cout, int k, int stride, int pad_left, void* stream);
+
 /* Conv2D(5x5, strides (2,1), 'same') over an (L,2,C) image (bbhMahoGANy.py:439,447) is a Conv1D with
  * Cin'=2Cin, Cout'=2Cout: w1 (kh, 2Cin, 2Cout) [kh,(wi,ci),(wo,co)] = w2 (kh,kw,Cin,Cout) [kh, wi-wo+pw, ci, co];
  * pw = left width pad (2 for kw=5). pack: w2->w1, b (Cout)->b1 (2Cout); unpack: dw1->dw2, db1->db (overwrite). */

@@ -1,0 +1,87 @@
+"""GPU parity of the tcgen05/TMA Conv1D kernels (bf16 in, fp32 accumulate) against float64 math on the SAME
+bf16-rounded inputs: products of bf16 values are exact in fp32, so only the accumulation order and the bf16
+rounding of the stored outputs differ (tolerance 2^-8 of the tensor scale for bf16 outputs, 1e-4 for the fp32
+weight gradient)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import keras_oracle as ko
+from tests.parity_cases import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda().to(torch.bfloat16).contiguous()
+
+
+CASES = [
+    # B, L, Cin, Cout, k, s, padding
+    (2, 200, 64, 128, 5, 1, 'valid'),     # q tower conv2 geometry (ragged tail tile)
+    (2, 256, 64, 128, 5, 2, 'valid'),     # mc tower conv2 geometry (traversal stride 2)
+    (3, 130, 128, 256, 5, 1, 'same'),     # 'same' padding: negative / overflowing TMA coordinates
+    (2, 253, 256, 512, 5, 2, 'valid'),    # odd length, stride 2
+    (2, 64, 512, 64, 5, 1, 'same'),       # BN = 64 path, many K blocks
+    (1, 1018, 512, 1024, 5, 2, 'valid'),  # q tower conv5 geometry
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_tc_conv_fwd_dgrad_wgrad(case):
+    from gennet_b200 import _lib as L_
+    B, L, Cin, Cout, k, s, padding = case
+    rs = np.random.RandomState(abs(hash(case)) % 2 ** 31)
+    x = bf(rs.normal(size=(B, L, Cin)))
+    w32 = (rs.normal(size=(k, Cin, Cout)) / math.sqrt(k * Cin)).astype(np.float32)
+    bias = torch.as_tensor(rs.normal(size=Cout).astype(np.float32)).cuda()
+    w_dev = torch.as_tensor(w32).cuda()
+    wk = torch.empty(k, Cin, Cout, dtype=torch.bfloat16, device='cuda')
+    wt = torch.empty(k, Cout, Cin, dtype=torch.bfloat16, device='cuda')
+    st = L_.stream()
+    L_.call('gn_conv_w_to_bf16', L_.ptr(w_dev), L_.ptr(wk, torch.bfloat16), L_.ptr(wt, torch.bfloat16), k, Cin, Cout, st)
+    assert torch.equal(wt, wk.permute(0, 2, 1).contiguous())
+    # float64 reference on the bf16-rounded operands
+    xr = x.float().cpu().double().requires_grad_(True)
+    wr = wk.float().cpu().double().requires_grad_(True)
+    br = bias.cpu().double()
+    xp = xr.permute(0, 2, 1)
+    pad = 0
+    if padding == 'same':
+        pl, pr = ko.same_pad(L, k, s)
+        xp = F.pad(xp, (pl, pr))
+        pad = pl
+    yr = F.conv1d(xp, wr.permute(2, 1, 0), br, stride=s).permute(0, 2, 1)
+    Lout = yr.shape[1]
+    y = torch.empty(B, Lout, Cout, dtype=torch.bfloat16, device='cuda')
+    L_.call('gn_conv1d_fwd_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(wt, torch.bfloat16), L_.ptr(bias), L_.ptr(y, torch.bfloat16),
+            B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_NONE, 0.0, st)
+    torch.cuda.synchronize()
+    assert_close(y.float().cpu().numpy(), yr.detach().numpy(), 'tc conv fwd', 2 ** -8)
+    # fused ReLU epilogue
+    L_.call('gn_conv1d_fwd_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(wt, torch.bfloat16), L_.ptr(bias), L_.ptr(y, torch.bfloat16),
+            B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_RELU, 0.0, st)
+    assert_close(y.float().cpu().numpy(), torch.relu(yr).detach().numpy(), 'tc conv fwd+relu', 2 ** -8)
+    # backward
+    dy = bf(rs.normal(size=(B, Lout, Cout)))
+    (yr * dy.float().cpu().double()).sum().backward()
+    dx = torch.full((B, L, Cin), float('nan'), dtype=torch.bfloat16, device='cuda')
+    L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, torch.bfloat16), L_.ptr(wk, torch.bfloat16), None, L_.ptr(dx, torch.bfloat16),
+            B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_NONE, 0.0, st)
+    torch.cuda.synchronize()
+    assert_close(dx.float().cpu().numpy(), xr.grad.numpy(), 'tc conv dgrad', 2 ** -8)
+    # dgrad with the fused ReLU mask of the conv input
+    L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, torch.bfloat16), L_.ptr(wk, torch.bfloat16), L_.ptr(x, torch.bfloat16),
+            L_.ptr(dx, torch.bfloat16), B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_RELU, 0.0, st)
+    mask = (x.float().cpu().numpy() > 0)
+    assert_close(dx.float().cpu().numpy(), xr.grad.numpy() * mask, 'tc conv dgrad*relu mask', 2 ** -8)
+    dw = torch.empty(k, Cin, Cout, device='cuda')
+    db = torch.empty(Cout, device='cuda')
+    L_.call('gn_conv1d_wgrad_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(dy, torch.bfloat16), L_.ptr(dw), L_.ptr(db), B, L, Cin, Lout,
+            Cout, k, s, pad, st)
+    torch.cuda.synchronize()
+    assert_close(dw.cpu().numpy(), wr.grad.numpy(), 'tc conv wgrad', 1e-4)
+    assert_close(db.cpu().numpy(), dy.float().cpu().double().sum((0, 1)).numpy(), 'tc conv bias grad', 1e-4)
