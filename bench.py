@@ -135,6 +135,7 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     dp = parallel.init_data_parallel('nccl') if world > 1 else None
     nn.set_seed(1)
+    nn.set_compute_dtype('bfloat16' if args.mode == 'bf16' else 'float32')
     bbh.n_pix = FS
     synth_obj, templates, labels = make_inputs(7, dev)
     pe = bbh.signal_pe_model()
@@ -218,12 +219,15 @@ def run_ours(args):
 
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'vs_baseline': None, 'dtype': 'bf16' if args.mode == 'bf16' else 'f32', 'data': 'synthetic',
            'config': {'workload': 'bbhMahoGANy.py CNN point estimator (signal_pe_model), fs 2048 Hz, N=8192 -> '
                                   'n_pix 2048, batch %d per GPU, synthetic TaylorF2-style chirps + analytic aLIGO-like '
                                   'PSD, random-init weights' % B,
                       'batch_per_gpu': B, 'global_batch': B * world, 'n_pix': L, 'fft_len': N,
-                      'parallelism': 'dp%d' % world, 'precision': 'fp32 SIMT (exact-parity path)',
+                      'parallelism': 'dp%d' % world,
+                      'precision': ('bf16 activations / conv operands on tcgen05 tensor cores, fp32 accumulation, fp32 '
+                                    'master weights, gradients and Adam' if args.mode == 'bf16' else
+                                    'fp32 SIMT (exact-parity path)'),
                       'l2': 'no flush: per-step working set (~4 GB activations) >> 126 MB L2'},
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                    'steps': n_e2e, 'what': 'pinned host strain (B,N) f32 -> H2D -> whiten_td+crop -> '
@@ -259,7 +263,9 @@ def profile_pass(one_step, args, B, L, N):
         d[0] += a.elapsed_time(b)
         d[1] += 1
     step_ms = sum(v[0] for v in tot.values()) / n
-    conv_names = ('gn_conv1d_fwd_f32', 'gn_conv1d_dgrad_f32', 'gn_conv1d_wgrad_f32')
+    conv_names = ('gn_conv1d_fwd_f32', 'gn_conv1d_dgrad_f32', 'gn_conv1d_wgrad_f32', 'gn_conv1d_fwd_bf16',
+                  'gn_conv1d_dgrad_bf16', 'gn_conv1d_wgrad_bf16', 'gn_conv1d_smallcin_fwd_bf16',
+                  'gn_conv1d_smallcin_wgrad_bf16')
     conv_ms = sum(tot[k][0] for k in conv_names if k in tot) / n
     conv_launches = sum(tot[k][1] for k in conv_names if k in tot) / n
     flops = step_flops() * B
@@ -351,6 +357,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mode', default='bf16', choices=['bf16', 'fp32'],
+                    help='bf16: tensor-core throughput path (default); fp32: exact-parity SIMT path')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

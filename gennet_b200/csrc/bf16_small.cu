@@ -1,0 +1,338 @@
+// Bandwidth-bound companions of the tensor-core path (bf16 activations): the first convolution of every
+// network (Cin = 1 or 2: K = 5..10, no GEMM worth the name) and the Dense heads with <= 4 outputs over the
+// flattened feature map (a GEMV over up to 519 168 features).  HBM-bound streaming kernels: 128-bit accesses,
+// warp-shuffle reductions, one pass over the big operand.
+// Reference layers: bbhMahoGANy.py:362,382 (first Conv1D of both PE towers), :439 (first D conv, Cin'=2),
+// :377,399,494 (Dense(1) heads); burstMahoGANy.py:272,310.
+#include "gn_common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace gn {
+
+// ---- first-layer convolution: x f32 (B,L,CIN), w f32 (k,CIN,Cout) -> y bf16 (B,Lout,Cout), fused bias + act ----
+// thread = (row, 8 consecutive output channels); weights (<= 16*2*256 floats) live in shared memory
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_smallcin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias,
+                                                                __nv_bfloat16* __restrict__ y, int B, int L, int Lout,
+                                                                int Cout, int k, int s, int p, int act, float ap) {
+    extern __shared__ float sw[];     // k*CIN*Cout weights then Cout bias
+    const int nw = k * CIN * Cout;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int groups = Cout / 8;
+    const long long total = (long long)B * Lout * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long long row = i / groups;
+        const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sw[nw + g * 8 + j];
+        for (int t = 0; t < k; ++t) {
+            const int pos = l * s + t - p;
+            if (pos < 0 || pos >= L) continue;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float xv = __ldg(&x[((size_t)b * L + pos) * CIN + c]);
+                const float* wr = &sw[(t * CIN + c) * Cout + g * 8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+            }
+        }
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            h[j] = __floats2bfloat162_rn(act_fwd(acc[2 * j], act, ap), act_fwd(acc[2 * j + 1], act, ap));
+        *reinterpret_cast<uint4*>(y + (size_t)row * Cout + g * 8) = *reinterpret_cast<uint4*>(h);
+    }
+}
+
+// ---- first-layer weight gradient: dw f32 (k,CIN,Cout), db f32 (Cout) from x f32 and dy bf16 (pre-activation grad) ----
+// block = Cout threads x RY row lanes; each thread keeps k*CIN (+1 bias) partial sums for its channel
+template <int CIN, int KMAX>
+__global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* __restrict__ x,
+                                                                  const __nv_bfloat16* __restrict__ dy,
+                                                                  float* __restrict__ dw, float* __restrict__ db, int B,
+                                                                  int L, int Lout, int Cout, int k, int s, int p,
+                                                                  long long rows_per_block) {
+    const int co = threadIdx.x % Cout;
+    const int ry = threadIdx.x / Cout, nry = blockDim.x / Cout;
+    float acc[KMAX * CIN];
+    float accb = 0.f;
+#pragma unroll
+    for (int i = 0; i < KMAX * CIN; ++i) acc[i] = 0.f;
+    const long long rows = (long long)B * Lout;
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (long long row = r0 + ry; row < r1; row += nry) {
+        const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
+        const float g = __bfloat162float(dy[(size_t)row * Cout + co]);
+        accb += g;
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+            if (t >= k) break;
+            const int pos = l * s + t - p;
+            if (pos < 0 || pos >= L) continue;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) acc[t * CIN + c] = fmaf(__ldg(&x[((size_t)b * L + pos) * CIN + c]), g, acc[t * CIN + c]);
+        }
+    }
+    for (int t = 0; t < k; ++t)
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) atomicAdd(&dw[((size_t)t * CIN + c) * Cout + co], acc[t * CIN + c]);
+    if (db != nullptr) atomicAdd(&db[co], accb);
+}
+
+// ---- Dense with N <= 4 outputs over bf16 features -------------------------------------------------------------
+// fwd: y[m, j] = act(sum_k x[m,k] w[k,j] + b[j]) : one CTA per row m, 128-bit loads, block reduction
+template <int NS>
+__global__ void __launch_bounds__(512) dense_small_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, float* __restrict__ y,
+                                                                   int K, int act, float ap) {
+    __shared__ float sm[32];
+    const int m = blockIdx.x;
+    const __nv_bfloat16* xr = x + (size_t)m * K;
+    float acc[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acc[j] = 0.f;
+    const int K8 = K / 8;
+    for (int i = threadIdx.x; i < K8; i += blockDim.x) {
+        uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr) + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 v = __bfloat1622float2(h[e]);
+            const int kk = i * 8 + 2 * e;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                acc[j] = fmaf(v.x, __ldg(&w[(size_t)kk * NS + j]), acc[j]);
+                acc[j] = fmaf(v.y, __ldg(&w[(size_t)(kk + 1) * NS + j]), acc[j]);
+            }
+        }
+    }
+    for (int kk = K8 * 8 + threadIdx.x; kk < K; kk += blockDim.x) {
+        float v = __bfloat162float(xr[kk]);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) acc[j] = fmaf(v, __ldg(&w[(size_t)kk * NS + j]), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        float t = block_sum(acc[j], sm);
+        if (threadIdx.x == 0) y[(size_t)m * NS + j] = act_fwd(t + (bias ? bias[j] : 0.f), act, ap);
+    }
+}
+
+// dgrad: dx[m,k] (bf16) = act'(x[m,k]) * sum_j dy[m,j] w[k,j]   (x = the layer's own input, post-activation)
+template <int NS>
+__global__ void __launch_bounds__(256) dense_small_dgrad_bf16_kernel(const float* __restrict__ dy,
+                                                                     const float* __restrict__ w,
+                                                                     const __nv_bfloat16* __restrict__ xin,
+                                                                     __nv_bfloat16* __restrict__ dx, int M, int K,
+                                                                     int in_act, float ap) {
+    const long long total = (long long)M * (K / 8);
+    const int K8 = K / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / K8), c = (int)(i - (long long)m * K8);
+        float g[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) g[j] = __ldg(&dy[(size_t)m * NS + j]);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) sacc = fmaf(g[j], __ldg(&w[(size_t)(c * 8 + e) * NS + j]), sacc);
+            o[e] = sacc;
+        }
+        if (xin != nullptr && in_act != GN_ACT_NONE) {
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)m * K) + c);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 v = __bfloat1622float2(h[e]);
+                o[2 * e] *= act_bwd_from_y(v.x, in_act, ap);
+                o[2 * e + 1] *= act_bwd_from_y(v.y, in_act, ap);
+            }
+        }
+        __nv_bfloat162 h2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+        *(reinterpret_cast<uint4*>(dx + (size_t)m * K) + c) = *reinterpret_cast<uint4*>(h2);
+    }
+}
+
+// wgrad: dw[k,j] = sum_m x[m,k] dy[m,j] : thread = 8 consecutive k, loop over a slice of m, atomics across slices
+template <int NS>
+__global__ void __launch_bounds__(256) dense_small_wgrad_bf16_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                     const float* __restrict__ dy,
+                                                                     float* __restrict__ dw, int M, int K,
+                                                                     int m_per_split) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;   // chunk of 8 features
+    if (c >= K / 8) return;
+    const int mb = blockIdx.y * m_per_split, me = min(M, mb + m_per_split);
+    float acc[8][NS];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) acc[e][j] = 0.f;
+    for (int m = mb; m < me; ++m) {
+        uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)m * K) + c);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        float g[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) g[j] = __ldg(&dy[(size_t)m * NS + j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 v = __bfloat1622float2(h[e]);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                acc[2 * e][j] = fmaf(v.x, g[j], acc[2 * e][j]);
+                acc[2 * e + 1][j] = fmaf(v.y, g[j], acc[2 * e + 1][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) atomicAdd(&dw[(size_t)(c * 8 + e) * NS + j], acc[e][j]);
+}
+
+__global__ void dense_small_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int N) {
+    const int j = threadIdx.x;
+    if (j >= N) return;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += dy[(size_t)m * N + j];
+    db[j] = s;
+}
+
+// elementwise act backward on bf16 tensors (used when the consumer could not fuse the mask)
+__global__ void __launch_bounds__(256) act_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                           const __nv_bfloat16* __restrict__ y,
+                                                           __nv_bfloat16* __restrict__ dx, long long n, int act, float ap) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * act_bwd_from_y(__bfloat162float(y[i]), act, ap));
+}
+
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const float* bias, void* y, int B, int L,
+                                           int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
+                                           float act_param, void* stream) {
+    GN_REQUIRE(x && w && y, "null pointer");
+    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 16 && stride > 0 && pad_left >= 0, "bad geometry");
+    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout % 8 == 0 && Cout <= 1024, "needs Cin in {1,2} and Cout % 8 == 0");
+    if (B == 0) return GN_OK;
+    const size_t smem = sizeof(float) * ((size_t)k * Cin * Cout + Cout);
+    GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
+    long long total = (long long)B * Lout * (Cout / 8);
+    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    if (Cin == 1)
+        conv_smallcin_fwd_kernel<1><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, L, Lout, Cout,
+                                                                           k, stride, pad_left, act, act_param);
+    else
+        conv_smallcin_fwd_kernel<2><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, L, Lout, Cout,
+                                                                           k, stride, pad_left, act, act_param);
+    return cuda_status("conv_smallcin_fwd_kernel");
+}
+
+extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, float* db, int B, int L, int Cin,
+                                             int Lout, int Cout, int k, int stride, int pad_left, void* stream) {
+    GN_REQUIRE(x && dy && dw, "null pointer");
+    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 8 && stride > 0 && pad_left >= 0, "bad geometry (k <= 8)");
+    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout <= 256 && 256 % Cout == 0, "needs Cin in {1,2} and Cout dividing 256");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin * Cout, st);
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);
+    if (B == 0) return GN_OK;
+    const long long rows = (long long)B * Lout;
+    long long blocks = 8LL * num_sms();
+    long long per = (rows + blocks - 1) / blocks;
+    if (per < 64) per = 64;
+    blocks = (rows + per - 1) / per;
+    if (Cin == 1)
+        conv_smallcin_wgrad_kernel<1, 8><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
+                                                                         Cout, k, stride, pad_left, per);
+    else
+        conv_smallcin_wgrad_kernel<2, 8><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
+                                                                         Cout, k, stride, pad_left, per);
+    return cuda_status("conv_smallcin_wgrad_kernel");
+}
+
+extern "C" int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N,
+                                       int act, float act_param, void* stream) {
+    GN_REQUIRE(x && w && y, "null pointer");
+    GN_REQUIRE(M >= 0 && K > 0 && N >= 1 && N <= 4 && K % 8 == 0, "needs 1 <= N <= 4 and K % 8 == 0");
+    if (M == 0) return GN_OK;
+    cudaStream_t st = as_stream(stream);
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    switch (N) {
+        case 1: dense_small_fwd_bf16_kernel<1><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+        case 2: dense_small_fwd_bf16_kernel<2><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+        case 3: dense_small_fwd_bf16_kernel<3><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+        default: dense_small_fwd_bf16_kernel<4><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+    }
+    return cuda_status("dense_small_fwd_bf16_kernel");
+}
+
+extern "C" int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, int M, int K, int N,
+                                         int in_act, float in_act_param, void* stream) {
+    GN_REQUIRE(dy && w && dx, "null pointer");
+    GN_REQUIRE(M >= 0 && K > 0 && N >= 1 && N <= 4 && K % 8 == 0, "needs 1 <= N <= 4 and K % 8 == 0");
+    if (M == 0) return GN_OK;
+    cudaStream_t st = as_stream(stream);
+    long long total = (long long)M * (K / 8);
+    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    const __nv_bfloat16* xi = (const __nv_bfloat16*)x_in;
+    __nv_bfloat16* d = (__nv_bfloat16*)dx;
+    switch (N) {
+        case 1: dense_small_dgrad_bf16_kernel<1><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
+        case 2: dense_small_dgrad_bf16_kernel<2><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
+        case 3: dense_small_dgrad_bf16_kernel<3><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
+        default: dense_small_dgrad_bf16_kernel<4><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
+    }
+    return cuda_status("dense_small_dgrad_bf16_kernel");
+}
+
+extern "C" int gn_dense_small_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int M, int K, int N,
+                                         void* stream) {
+    GN_REQUIRE(x && dy && dw, "null pointer");
+    GN_REQUIRE(M >= 0 && K > 0 && N >= 1 && N <= 4 && K % 8 == 0, "needs 1 <= N <= 4 and K % 8 == 0");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)K * N, st);
+    if (M > 0) {
+        const int chunks = K / 8;
+        const int bx = (chunks + 255) / 256;
+        int splits = (int)((4LL * num_sms() + bx - 1) / bx);
+        if (splits > M) splits = M;
+        if (splits < 1) splits = 1;
+        if (splits > 65535) splits = 65535;
+        int per = (M + splits - 1) / splits;
+        splits = (M + per - 1) / per;
+        dim3 grid(bx, splits);
+        const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+        switch (N) {
+            case 1: dense_small_wgrad_bf16_kernel<1><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+            case 2: dense_small_wgrad_bf16_kernel<2><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+            case 3: dense_small_wgrad_bf16_kernel<3><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+            default: dense_small_wgrad_bf16_kernel<4><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+        }
+    }
+    if (db != nullptr) dense_small_bias_grad_kernel<<<1, 32, 0, st>>>(dy, db, M, N);
+    return cuda_status("dense_small_wgrad_bf16_kernel");
+}
+
+extern "C" int gn_act_bwd_bf16(const void* dy, const void* y, void* dx, long long n, int act, float param, void* stream) {
+    GN_REQUIRE(dy && y && dx && n >= 0, "null pointer or n < 0");
+    if (n == 0) return GN_OK;
+    unsigned grid = (unsigned)((n + 255) / 256 < 16LL * num_sms() ? (n + 255) / 256 : 16LL * num_sms());
+    act_bwd_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+                                                            (__nv_bfloat16*)dx, n, act, param);
+    return cuda_status("act_bwd_bf16_kernel");
+}

@@ -129,11 +129,35 @@ struct TcSmem {
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // ------------------------------------------------------------------------------------------------ fwd / dgrad
-// grid: x = m-tile (within a sample and parity class), y = n-tile, z = sample * n_parity + parity
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles tile = blockIdx.x + i*gridDim.x with
+// n-tile fastest (CTAs running side by side share the activation tile through L2).  Two pipelines:
+//   shared-memory ring  (full/empty mbarriers, STAGES deep)  TMA producer  -> MMA issuer
+//   TMEM accumulator ring (2 x BN fp32 columns)               MMA issuer   -> epilogue warps
+// so the epilogue of tile i (TMEM -> registers -> bias/act/mask -> bf16 -> HBM) overlaps the MMAs of tile i+1.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+    int b, par, m0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int tile, int n_nt, int m_tiles, int npar, int BN) {
+    TileCoord c;
+    int nt = tile % n_nt;
+    int r = tile / n_nt;
+    int mt = r % m_tiles;
+    int r2 = r / m_tiles;
+    c.par = r2 % npar;
+    c.b = r2 / npar;
+    c.m0 = mt * TC_BM;
+    c.n0 = nt * BN;
+    return c;
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
@@ -143,25 +167,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * S::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npar = (a.mode == 1) ? a.s : 1;
-    const int b = blockIdx.z / npar, par = blockIdx.z - b * npar;
-    const int m0 = blockIdx.x * TC_BM;      // first output row of this tile (within sample & parity class)
-    const int n0 = blockIdx.y * BN;
     const int kdim = (a.mode == 0) ? a.Cin : a.Cout;   // contraction channels
     const int nkb = kdim / TC_BK;
-
-    // taps that contribute: fwd all; dgrad those with (par + p - t) % s == 0
-    int tap_first = 0, tap_step = 1, ntaps = a.k;
-    if (a.mode == 1) {
-        tap_first = (par + a.p) % a.s;
-        tap_step = a.s;
-        ntaps = (a.k - tap_first + a.s - 1) / a.s;
-    }
-    const int niter = ntaps * nkb;
+    const int n_nt = ((a.mode == 0) ? a.Cout : a.Cin) / BN;
+    const int total_tiles = a.B * npar * a.m_tiles * n_nt;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
@@ -170,10 +185,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);      // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,102 +199,134 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int it = 0; it < niter; ++it) {
-                const int st = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&empty[st], ph ^ 1);
-                const int ti = it / nkb, kb = it - ti * nkb;
-                const int tap = tap_first + ti * tap_step;
-                uint8_t* sA = tiles + st * S::STAGE_BYTES;
-                uint8_t* sB = sA + S::A_BYTES;
-                mbar_expect_tx(&full[st], S::STAGE_BYTES);
-                int rowc;    // first row coordinate (global, pre-stride) along the length axis of A
-                if (a.mode == 0) rowc = m0 * a.s + tap - a.p;
-                else rowc = m0 + (par + a.p - tap) / a.s;
-                tma_load_3d(sA, &mapA, &full[st], kb * TC_BK, rowc, b);
-                tma_load_3d(sB, &mapB, &full[st], kb * TC_BK, n0, tap);
+            int g = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
+                int tap_first = 0, tap_step = 1, ntaps = a.k;
+                if (a.mode == 1) {
+                    tap_first = (c.par + a.p) % a.s;
+                    tap_step = a.s;
+                    ntaps = (a.k - tap_first + a.s - 1) / a.s;
+                }
+                for (int ti = 0; ti < ntaps; ++ti) {
+                    const int tap = tap_first + ti * tap_step;
+                    // first row coordinate (global, pre-stride) along the length axis of A
+                    const int rowc = (a.mode == 0) ? (c.m0 * a.s + tap - a.p) : (c.m0 + (c.par + a.p - tap) / a.s);
+                    for (int kb = 0; kb < nkb; ++kb, ++g) {
+                        const int st = g % STAGES, ph = (g / STAGES) & 1;
+                        mbar_wait(&empty[st], ph ^ 1);
+                        uint8_t* sA = tiles + st * S::STAGE_BYTES;
+                        uint8_t* sB = sA + S::A_BYTES;
+                        mbar_expect_tx(&full[st], S::STAGE_BYTES);
+                        tma_load_3d(sA, &mapA, &full[st], kb * TC_BK, rowc, c.b);
+                        tma_load_3d(sB, &mapB, &full[st], kb * TC_BK, c.n0, tap);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
-            for (int it = 0; it < niter; ++it) {
-                const int st = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&full[st], ph);
-                tc_fence_after();
-                const uint32_t sA = base + st * S::STAGE_BYTES;
-                const uint32_t sB = sA + S::A_BYTES;
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    uint64_t da = make_desc(sA + k * 32, 16, 1024);
-                    uint64_t db = make_desc(sB + k * 32, 16, 1024);
-                    tc_mma_bf16(tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            int g = 0, ti_local = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti_local) {
+                const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
+                int ntaps = a.k;
+                if (a.mode == 1) {
+                    const int tap_first = (c.par + a.p) % a.s;
+                    ntaps = (a.k - tap_first + a.s - 1) / a.s;
                 }
-                tc_commit(&empty[st]);      // frees the smem stage once the MMAs have read it
+                const int niter = ntaps * nkb;
+                const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+                for (int it = 0; it < niter; ++it, ++g) {
+                    const int st = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t sA = base + st * S::STAGE_BYTES;
+                    const uint32_t sB = sA + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        uint64_t da = make_desc(sA + k * 32, 16, 1024);
+                        uint64_t db = make_desc(sB + k * 32, 16, 1024);
+                        tc_mma_bf16(tacc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[st]);      // frees the smem stage once the MMAs have read it
+                }
+                tc_commit(&tmem_full[acc]);     // accumulator complete
             }
-            tc_commit(tmem_full);           // accumulator complete
         }
     } else {
         // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (rows of the tile)
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int r = m0 + row;              // row index within (sample, parity)
-        bool valid;
-        size_t off;                          // element offset of (row, n0) in the output tensor
-        int ncols;                           // channels of the output tensor
-        if (a.mode == 0) {
-            valid = r < a.Lout;
-            ncols = a.Cout;
-            off = ((size_t)b * a.Lout + r) * a.Cout + n0;
-        } else {
-            const int j = r * a.s + par;
-            valid = j < a.L;
-            ncols = a.Cin;
-            off = ((size_t)b * a.L + j) * a.Cin + n0;
-        }
-        (void)ncols;
+        int ti_local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti_local) {
+            const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
+            const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+            const int r = c.m0 + row;            // row index within (sample, parity)
+            bool valid;
+            size_t off;                          // element offset of (row, n0) in the output tensor
+            if (a.mode == 0) {
+                valid = r < a.Lout;
+                off = ((size_t)c.b * a.Lout + r) * a.Cout + c.n0;
+            } else {
+                const int j = r * a.s + c.par;
+                valid = j < a.L;
+                off = ((size_t)c.b * a.L + j) * a.Cin + c.n0;
+            }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (valid) {
-                float f[32];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tacc + (uint32_t)c0, v);
+                if (c0 + 32 >= BN) {
+                    // all of this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                if (valid) {
+                    float f[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                if (a.mode == 0) {
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (a.mode == 0) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float t = f[i] + (a.bias ? __ldg(&a.bias[n0 + c0 + i]) : 0.f);
-                        f[i] = act_fwd(t, a.act, a.act_param);
-                    }
-                } else if (a.aux != nullptr && a.act != GN_ACT_NONE) {
-                    const uint4* xin = reinterpret_cast<const uint4*>(a.aux + off + c0);
+                        for (int i = 0; i < 32; ++i) {
+                            float t = f[i] + (a.bias ? __ldg(&a.bias[c.n0 + c0 + i]) : 0.f);
+                            f[i] = act_fwd(t, a.act, a.act_param);
+                        }
+                    } else if (a.aux != nullptr && a.act != GN_ACT_NONE) {
+                        const uint4* xin = reinterpret_cast<const uint4*>(a.aux + off + c0);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 pk = __ldg(&xin[g]);
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            uint4 pk = __ldg(&xin[g4]);
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float2 y = __bfloat1622float2(h[e]);
-                            f[g * 8 + 2 * e] *= act_bwd_from_y(y.x, a.act, a.act_param);
-                            f[g * 8 + 2 * e + 1] *= act_bwd_from_y(y.y, a.act, a.act_param);
+                            for (int e = 0; e < 4; ++e) {
+                                float2 y = __bfloat1622float2(h[e]);
+                                f[g4 * 8 + 2 * e] *= act_bwd_from_y(y.x, a.act, a.act_param);
+                                f[g4 * 8 + 2 * e + 1] *= act_bwd_from_y(y.y, a.act, a.act_param);
+                            }
                         }
                     }
-                }
-                uint4* dst = reinterpret_cast<uint4*>(a.out + off + c0);
+                    uint4* dst = reinterpret_cast<uint4*>(a.out + off + c0);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
-                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
-                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                    dst[g] = pk;
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g4 * 8 + 0], f[g4 * 8 + 1]);
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g4 * 8 + 2], f[g4 * 8 + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 4], f[g4 * 8 + 5]);
+                        __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g4 * 8 + 6], f[g4 * 8 + 7]);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        dst[g4] = pk;
+                    }
                 }
             }
         }
@@ -285,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem);
+        tmem_dealloc<2 * BN>(tmem);
     }
 }
 
@@ -495,7 +545,8 @@ static int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
 }
 
 template <int BN, int STAGES>
-static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, dim3 grid, cudaStream_t st) {
+static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, long long total_tiles,
+                          cudaStream_t st) {
     auto kfn = conv_tc_kernel<BN, STAGES>;
     constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
     static bool attr_set = false;
@@ -503,9 +554,18 @@ static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const Tc
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
+    const int grid = (int)(total_tiles < (long long)num_sms() ? total_tiles : (long long)num_sms());
     kfn<<<grid, TC_THREADS, smem, st>>>(mA, mB, a);
     return cuda_status("conv_tc_kernel");
 }
+
+static int dispatch_conv_tc(int BN, const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, long long tiles,
+                            cudaStream_t st) {
+    if (BN == 256) return launch_conv_tc<256, 4>(mA, mB, a, tiles, st);
+    if (BN == 128) return launch_conv_tc<128, 6>(mA, mB, a, tiles, st);
+    return launch_conv_tc<64, 8>(mA, mB, a, tiles, st);
+}
+static int pick_bn(int C) { return (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : 64); }
 
 template <int BN, int STAGES, bool SWAP>
 static int launch_wgrad_tc(const CUtensorMap& mX, const CUtensorMap& mDY, const TcWgradArgs& a, dim3 grid,
@@ -563,7 +623,7 @@ extern "C" int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bi
     int rc = check_tc_geom(B, L, Cin, Lout, Cout, k, stride, pad_left);
     if (rc != GN_OK) return rc;
     CUtensorMap mA, mB;
-    const int BN = (Cout % 128 == 0) ? 128 : 64;
+    const int BN = pick_bn(Cout);
     // A: X viewed as (Cin, L, B); 128 output rows per tile, traversal stride = conv stride
     rc = make_map3(&mA, x, Cin, L, B, Cin, (uint64_t)L * Cin, TC_BK, TC_BM, stride);
     if (rc != GN_OK) return rc;
@@ -574,9 +634,7 @@ extern "C" int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bi
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
     a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = (__nv_bfloat16*)y;
     a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
-    dim3 grid(a.m_tiles, Cout / BN, B);
-    if (BN == 128) return launch_conv_tc<128, 4>(mA, mB, a, grid, as_stream(stream));
-    return launch_conv_tc<64, 4>(mA, mB, a, grid, as_stream(stream));
+    return dispatch_conv_tc(BN, mA, mB, a, (long long)B * a.m_tiles * (Cout / BN), as_stream(stream));
 }
 
 extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, int B, int L, int Cin,
@@ -586,7 +644,7 @@ extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* 
     int rc = check_tc_geom(B, L, Cin, Lout, Cout, k, stride, pad_left);
     if (rc != GN_OK) return rc;
     CUtensorMap mA, mB;
-    const int BN = (Cin % 128 == 0) ? 128 : 64;
+    const int BN = pick_bn(Cin);
     // A: dY viewed as (Cout, Lout, B), 128 rows, unit traversal stride (parity classes handle the conv stride)
     rc = make_map3(&mA, dy, Cout, Lout, B, Cout, (uint64_t)Lout * Cout, TC_BK, TC_BM, 1);
     if (rc != GN_OK) return rc;
@@ -599,10 +657,7 @@ extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* 
     a.out = (__nv_bfloat16*)dx;
     const int rows = (L + stride - 1) / stride;      // rows of the largest parity class
     a.m_tiles = (rows + TC_BM - 1) / TC_BM;
-    GN_REQUIRE((long long)B * stride <= 65535, "batch too large for one launch");
-    dim3 grid(a.m_tiles, Cin / BN, B * stride);
-    if (BN == 128) return launch_conv_tc<128, 4>(mA, mB, a, grid, as_stream(stream));
-    return launch_conv_tc<64, 4>(mA, mB, a, grid, as_stream(stream));
+    return dispatch_conv_tc(BN, mA, mB, a, (long long)B * stride * a.m_tiles * (Cin / BN), as_stream(stream));
 }
 
 extern "C" int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,

@@ -21,7 +21,8 @@ from ._lib import call, ptr, stream
 
 # ----------------------------------------------------------------------------- session state
 _NAME_COUNTS = {}
-_STATE = {'seed': 1234, 'noise_counter': 0, 'init_rng': np.random.RandomState(1234), 'dp': None}
+_STATE = {'seed': 1234, 'noise_counter': 0, 'init_rng': np.random.RandomState(1234), 'dp': None,
+          'dtype': 'float32', 'wver': 0}
 
 
 def clear_session():
@@ -33,6 +34,17 @@ def set_seed(seed):
     _STATE['seed'] = int(seed)
     _STATE['noise_counter'] = 0
     _STATE['init_rng'] = np.random.RandomState(int(seed))
+
+
+def set_compute_dtype(name):
+    """'float32': exact-parity SIMT path (default).  'bfloat16': activations and conv operands in bf16 with
+    fp32 accumulation on the tcgen05 tensor cores, fp32 master weights / gradients / optimizer."""
+    assert name in ('float32', 'bfloat16')
+    _STATE['dtype'] = name
+
+
+def compute_dtype():
+    return _STATE['dtype']
 
 
 def _uid(prefix):
@@ -47,6 +59,42 @@ def device():
 
 def _empty(shape):
     return torch.empty(shape, dtype=torch.float32, device=device())
+
+
+BF16 = torch.bfloat16
+
+
+def _empty_bf16(shape):
+    return torch.empty(shape, dtype=BF16, device=device())
+
+
+def _as_f32(x):
+    """bf16 activations entering a layer that only has a float32 kernel are widened on the device."""
+    if x is None or x.dtype == torch.float32:
+        return x
+    y = _empty(x.shape)
+    call('gn_cast_bf16_to_f32', ptr(x.contiguous(), BF16), ptr(y), x.numel(), stream())
+    return y
+
+
+def _as_bf16(x):
+    if x.dtype == BF16:
+        return x
+    y = _empty_bf16(x.shape)
+    call('gn_cast_f32_to_bf16', ptr(x.contiguous()), ptr(y, BF16), x.numel(), stream())
+    return y
+
+
+def _act_bwd(dy, y, code, param):
+    """dy * act'(y) in the dtype the tensors are in."""
+    if dy.dtype == BF16 and y.dtype == BF16:
+        g = _empty_bf16(dy.shape)
+        call('gn_act_bwd_bf16', ptr(dy, BF16), ptr(y, BF16), ptr(g, BF16), dy.numel(), code, param, stream())
+        return g
+    dy, y = _as_f32(dy), _as_f32(y)
+    g = _empty(dy.shape)
+    call('gn_act_bwd_f32', ptr(dy), ptr(y), ptr(g), dy.numel(), code, param, stream())
+    return g
 
 
 def _same_pad(L, k, s):
@@ -137,6 +185,7 @@ class Layer:
             w = np.asarray(w, dtype=np.float32)
             assert tuple(w.shape) == p.shape, 'shape mismatch for %s: %s vs %s' % (p.name, w.shape, p.shape)
             p.data.copy_(torch.from_numpy(np.ascontiguousarray(w)))
+        _STATE['wver'] += 1
 
     def count_params(self):
         return sum(p.numel() for p in self.params)
@@ -193,6 +242,7 @@ class Dense(Layer):
         super().__init__(**kw)
         self.units = int(units)
         self.activation = activation
+        self.in_act = None           # (code, param) of the fused activation that produced our input (set by _fuse)
 
     def build(self, in_shape):
         assert len(in_shape) == 1, 'Dense expects a flat input, got %s' % (in_shape,)
@@ -204,31 +254,54 @@ class Dense(Layer):
     def forward(self, x, ctx):
         B, K = x.shape
         y = _empty((B, self.units))
-        call('gn_dense_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B, K,
-             self.units, _ACTS[self.activation], 0.0, stream())
+        self._bf16 = x.dtype == BF16 and self.units <= 4 and K % 8 == 0
+        if self._bf16:
+            call('gn_dense_small_fwd_bf16', ptr(x, BF16), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B,
+                 K, self.units, _ACTS[self.activation], 0.0, stream())
+        else:
+            x = _as_f32(x)
+            call('gn_dense_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B, K,
+                 self.units, _ACTS[self.activation], 0.0, stream())
         self._x, self._y = x, y
         return y
 
     def backward(self, dy, ctx, need_dx=True):
         x = self._x
         B, K = x.shape
+        dy = _as_f32(dy)
         if _ACTS[self.activation] != _lib.ACT_NONE:
-            g = _empty(dy.shape)
-            call('gn_act_bwd_f32', ptr(dy), ptr(self._y), ptr(g), dy.numel(), _ACTS[self.activation], 0.0, stream())
-            dy = g
-        if id(self) in ctx.trainable_ids:
-            call('gn_dense_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad), ptr(self.params[1].grad), B, K,
-                 self.units, stream())
+            dy = _act_bwd(dy, self._y, _ACTS[self.activation], 0.0)
+        tr = id(self) in ctx.trainable_ids
         dx = None
-        if need_dx:
-            dx = _empty((B, K))
-            call('gn_dense_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, K, self.units, stream())
+        if self._bf16:
+            if tr:
+                call('gn_dense_small_wgrad_bf16', ptr(x, BF16), ptr(dy), ptr(self.params[0].grad),
+                     ptr(self.params[1].grad), B, K, self.units, stream())
+            if need_dx:
+                dx = _empty_bf16((B, K))
+                code, par = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
+                call('gn_dense_small_dgrad_bf16', ptr(dy), ptr(self.params[0].data), ptr(x, BF16), ptr(dx, BF16), B, K,
+                     self.units, code, par, stream())
+                dx._gn_preact = self.in_act is not None
+        else:
+            if tr:
+                call('gn_dense_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad), ptr(self.params[1].grad), B, K,
+                     self.units, stream())
+            if need_dx:
+                dx = _empty((B, K))
+                call('gn_dense_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, K, self.units, stream())
         self._x = self._y = None
         return dx
 
 
 class Conv1D(Layer):
-    """Keras Conv1D (channels_last): kernel (k, Cin, Cout), bias (Cout), 'valid' | 'same' (TF rule)."""
+    """Keras Conv1D (channels_last): kernel (k, Cin, Cout), bias (Cout), 'valid' | 'same' (TF rule).
+
+    Execution paths (all CUDA): float32 SIMT implicit GEMM (exact parity); under
+    ``set_compute_dtype('bfloat16')`` the tcgen05/TMA kernels when Cin and Cout are multiples of 64, and the
+    bandwidth-bound first-layer kernel when Cin <= 2.  A directly following Activation/LeakyReLU/ReLU layer is
+    folded into the epilogue (``post_act``); its backward is folded into the consumer's data-gradient epilogue
+    when the consumer can do it (``in_act``), else applied here."""
     prefix = 'conv1d'
 
     def __init__(self, filters, kernel_size, strides=1, padding='valid', activation=None,
@@ -239,7 +312,10 @@ class Conv1D(Layer):
         self.s = int(strides[0] if isinstance(strides, (tuple, list)) else strides)
         self.padding = padding
         self.activation = activation
-        self.fused_up = 1        # set to 2 by Sequential when an UpSampling1D(2) directly precedes
+        self.fused_up = 1        # set to 2 by Model._fuse when an UpSampling1D(2) directly precedes
+        self.post_act = None     # (code, param) of a following activation layer folded into the epilogue
+        self.in_act = None       # (code, param) of the fused activation that produced our input
+        self._wcache = None
 
     def build(self, in_shape):
         L, cin = in_shape
@@ -252,12 +328,53 @@ class Conv1D(Layer):
             self.pad, self.Lout = 0, (L - k) // self.s + 1
         return (self.Lout, self.filters)
 
+    def _act(self):
+        if self.post_act is not None:
+            return self.post_act
+        return (_ACTS[self.activation], 0.0)
+
+    def _path(self):
+        L, cin = self.input_shape
+        co = self.filters
+        if _STATE['dtype'] != 'bfloat16' or self.fused_up != 1 or self.k > 8 or self.s > 2:
+            return 'f32'
+        if cin % 64 == 0 and co % 64 == 0 and (cin % 128 == 0 or (cin == 64 and co % 128 == 0)):
+            return 'tc'
+        if cin <= 2 and co % 8 == 0 and 256 % co == 0:
+            return 'smallcin'
+        return 'f32'
+
+    def _bf16_weights(self):
+        if self._wcache is None or self._wcache[0] != _STATE['wver']:
+            L, cin = self.input_shape
+            wk = _empty_bf16((self.k, cin, self.filters))
+            wt = _empty_bf16((self.k, self.filters, cin))
+            call('gn_conv_w_to_bf16', ptr(self.params[0].data), ptr(wk, BF16), ptr(wt, BF16), self.k, cin, self.filters,
+                 stream())
+            self._wcache = (_STATE['wver'], wk, wt)
+        return self._wcache[1], self._wcache[2]
+
     def forward(self, x, ctx):
         B = x.shape[0]
         L, cin = self.input_shape
-        y = _empty((B, self.Lout, self.filters))
-        call('gn_conv1d_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B, L, cin,
-             self.Lout, self.filters, self.k, self.s, self.pad, self.fused_up, _ACTS[self.activation], 0.0, stream())
+        code, par = self._act()
+        self._mode = self._path()
+        if self._mode == 'tc':
+            x = _as_bf16(x)
+            wk, wt = self._bf16_weights()
+            y = _empty_bf16((B, self.Lout, self.filters))
+            call('gn_conv1d_fwd_bf16', ptr(x, BF16), ptr(wt, BF16), ptr(self.params[1].data), ptr(y, BF16), B, L, cin,
+                 self.Lout, self.filters, self.k, self.s, self.pad, code, par, stream())
+        elif self._mode == 'smallcin':
+            x = _as_f32(x)
+            y = _empty_bf16((B, self.Lout, self.filters))
+            call('gn_conv1d_smallcin_fwd_bf16', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y, BF16),
+                 B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad, code, par, stream())
+        else:
+            x = _as_f32(x)
+            y = _empty((B, self.Lout, self.filters))
+            call('gn_conv1d_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B, L, cin,
+                 self.Lout, self.filters, self.k, self.s, self.pad, self.fused_up, code, par, stream())
         self._x, self._y = x, y
         return y
 
@@ -265,18 +382,42 @@ class Conv1D(Layer):
         x = self._x
         B = x.shape[0]
         L, cin = self.input_shape
-        if _ACTS[self.activation] != _lib.ACT_NONE:
-            g = _empty(dy.shape)
-            call('gn_act_bwd_f32', ptr(dy), ptr(self._y), ptr(g), dy.numel(), _ACTS[self.activation], 0.0, stream())
-            dy = g
-        if id(self) in ctx.trainable_ids:
-            call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad), ptr(self.params[1].grad), B, L,
-                 cin, self.Lout, self.filters, self.k, self.s, self.pad, self.fused_up, stream())
+        code, par = self._act()
+        if code != _lib.ACT_NONE and not getattr(dy, '_gn_preact', False):
+            dy = _act_bwd(dy.contiguous(), self._y, code, par)
+        tr = id(self) in ctx.trainable_ids
         dx = None
-        if need_dx:
-            dx = _empty(x.shape)
-            call('gn_conv1d_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, L, cin, self.Lout,
-                 self.filters, self.k, self.s, self.pad, self.fused_up, stream())
+        if self._mode == 'tc':
+            dy = _as_bf16(dy.contiguous())
+            if tr:
+                call('gn_conv1d_wgrad_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(self.params[0].grad),
+                     ptr(self.params[1].grad), B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad, stream())
+            if need_dx:
+                wk, wt = self._bf16_weights()
+                dx = _empty_bf16(x.shape)
+                icode, ipar = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
+                call('gn_conv1d_dgrad_bf16', ptr(dy, BF16), ptr(wk, BF16), ptr(x, BF16), ptr(dx, BF16), B, L, cin,
+                     self.Lout, self.filters, self.k, self.s, self.pad, icode, ipar, stream())
+                dx._gn_preact = self.in_act is not None
+        elif self._mode == 'smallcin':
+            dy = _as_bf16(dy.contiguous())
+            if tr:
+                call('gn_conv1d_smallcin_wgrad_bf16', ptr(x), ptr(dy, BF16), ptr(self.params[0].grad),
+                     ptr(self.params[1].grad), B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad, stream())
+            if need_dx:
+                dyf = _as_f32(dy)
+                dx = _empty(x.shape)
+                call('gn_conv1d_dgrad_f32', ptr(dyf), ptr(self.params[0].data), ptr(dx), B, L, cin, self.Lout,
+                     self.filters, self.k, self.s, self.pad, 1, stream())
+        else:
+            dy = _as_f32(dy.contiguous())
+            if tr:
+                call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad), ptr(self.params[1].grad), B, L,
+                     cin, self.Lout, self.filters, self.k, self.s, self.pad, self.fused_up, stream())
+            if need_dx:
+                dx = _empty(x.shape)
+                call('gn_conv1d_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, L, cin, self.Lout,
+                     self.filters, self.k, self.s, self.pad, self.fused_up, stream())
         self._x = self._y = None
         return dx
 
@@ -318,6 +459,7 @@ class Conv2D(Layer):
         return w1, b1
 
     def forward(self, x, ctx):
+        x = _as_f32(x)
         B = x.shape[0]
         H, W, cin = self.input_shape
         w1, b1 = self._pack()
@@ -328,6 +470,7 @@ class Conv2D(Layer):
         return y
 
     def backward(self, dy, ctx, need_dx=True):
+        dy = _as_f32(dy)
         x, w1 = self._x, self._w1
         B = x.shape[0]
         H, W, cin = self.input_shape
@@ -365,6 +508,7 @@ class BatchNormalization(Layer):
         return in_shape
 
     def forward(self, x, ctx):
+        x = _as_f32(x)
         C = x.shape[-1]
         rows = x.numel() // C
         g, b, mm, mv = [p.data for p in self.params]
@@ -392,6 +536,7 @@ class BatchNormalization(Layer):
         return y
 
     def backward(self, dy, ctx, need_dx=True):
+        dy = _as_f32(dy)
         x, stats = self._x, self._stats
         C = x.shape[-1]
         rows = x.numel() // C
@@ -415,20 +560,21 @@ class BatchNormalization(Layer):
 
 class _ActLayer(Layer):
     code, param = _lib.ACT_NONE, 0.0
+    fused = False        # True when the preceding Conv1D applies this activation in its epilogue
 
     def forward(self, x, ctx):
-        if self.code == _lib.ACT_NONE:
+        if self.code == _lib.ACT_NONE or self.fused:
             return x
+        x = _as_f32(x)
         y = _empty(x.shape)
         call('gn_act_fwd_f32', ptr(x), ptr(y), x.numel(), self.code, self.param, stream())
         self._y = y
         return y
 
     def backward(self, dy, ctx, need_dx=True):
-        if self.code == _lib.ACT_NONE or not need_dx:
+        if self.code == _lib.ACT_NONE or self.fused or not need_dx:
             return dy
-        dx = _empty(dy.shape)
-        call('gn_act_bwd_f32', ptr(dy), ptr(self._y), ptr(dx), dy.numel(), self.code, self.param, stream())
+        dx = _act_bwd(dy, self._y, self.code, self.param)
         self._y = None
         return dx
 
@@ -474,6 +620,7 @@ class _NoiseLayer(Layer):
         if not ctx.training:
             self._r = None
             return x
+        x = _as_f32(x)
         fed = ctx.noise.get(self.name)
         if fed is not None:
             r = torch.as_tensor(np.ascontiguousarray(fed, dtype=np.float32)).to(x.device).reshape(x.shape).contiguous()
@@ -492,6 +639,7 @@ class _NoiseLayer(Layer):
     def backward(self, dy, ctx, need_dx=True):
         if self._r is None or not need_dx:
             return dy
+        dy = _as_f32(dy)
         dx = _empty(dy.shape)
         call('gn_noise_bwd_f32', ptr(dy), ptr(self._r), ptr(dx), dy.numel(), self.kind, self.rate, stream())
         self._r = None
@@ -532,7 +680,10 @@ class Reshape(Layer):
         return x.reshape((x.shape[0],) + self.output_shape)
 
     def backward(self, dy, ctx, need_dx=True):
-        return dy.reshape((dy.shape[0],) + self.input_shape)
+        dx = dy.reshape((dy.shape[0],) + self.input_shape)
+        if getattr(dy, '_gn_preact', False):
+            dx._gn_preact = True
+        return dx
 
 
 class Flatten(Reshape):
@@ -559,6 +710,7 @@ class UpSampling1D(Layer):
     def forward(self, x, ctx):
         if self.fused:
             return x
+        x = _as_f32(x)
         B, L, C = x.shape
         y = _empty((B, L * self.size, C))
         call('gn_upsample1d_fwd_f32', ptr(x), ptr(y), B, L, C, self.size, stream())
@@ -567,6 +719,7 @@ class UpSampling1D(Layer):
     def backward(self, dy, ctx, need_dx=True):
         if self.fused:
             return dy
+        dy = _as_f32(dy)
         B = dy.shape[0]
         L, C = self.input_shape
         dx = _empty((B, L, C))
@@ -585,6 +738,7 @@ class MaxPooling1D(Layer):
         return (in_shape[0] // self.pool, in_shape[1])
 
     def forward(self, x, ctx):
+        x = _as_f32(x)
         B, L, C = x.shape
         y = _empty((B, L // self.pool, C))
         call('gn_maxpool1d_fwd_f32', ptr(x), ptr(y), B, L, C, self.pool, stream())
@@ -593,6 +747,7 @@ class MaxPooling1D(Layer):
 
     def backward(self, dy, ctx, need_dx=True):
         x = self._x
+        dy = _as_f32(dy)
         B, L, C = x.shape
         dx = _empty(x.shape)
         call('gn_maxpool1d_bwd_f32', ptr(x), ptr(self._y), ptr(dy), ptr(dx), B, L, C, self.pool, stream())
@@ -614,6 +769,7 @@ class StackResidual(Layer):
         return (L, 2, 1)
 
     def forward(self, x, ctx):
+        x = _as_f32(x)
         B = x.shape[0]
         L = self.input_shape[0]
         y = _empty((B, L, 2, 1))
@@ -621,6 +777,7 @@ class StackResidual(Layer):
         return y
 
     def backward(self, dy, ctx, need_dx=True):
+        dy = _as_f32(dy)
         B = dy.shape[0]
         L = self.input_shape[0]
         dx = _empty((B,) + self.input_shape)
@@ -644,6 +801,7 @@ class ResidualMoments(Layer):
         return (2,)
 
     def forward(self, x, ctx):
+        x = _as_f32(x)
         B = x.shape[0]
         L = x.numel() // B
         sums = torch.empty(2, dtype=torch.float64, device=x.device)
@@ -697,6 +855,7 @@ class Adam(Optimizer):
             call('gn_adam_step_f32', ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr_t, self.beta_1, self.beta_2,
                  self.epsilon, grad_scale, stream())
         self.iterations += 1
+        _STATE['wver'] += 1
 
 
 class SGD(Optimizer):
@@ -712,6 +871,7 @@ class SGD(Optimizer):
         for key, p, g in segments:
             call('gn_sgd_step_f32', ptr(p), ptr(g), p.numel(), lr, grad_scale, stream())
         self.iterations += 1
+        _STATE['wver'] += 1
 
 
 # ----------------------------------------------------------------------------- losses
@@ -792,6 +952,26 @@ class Model(Layer):
                 if len(u) == 1 and type(u[0].layer) is Conv1D and n not in self._out_nodes:
                     n.layer.fused = True
                     u[0].layer.fused_up = 2
+        # Conv1D -> (Activation | LeakyReLU | ReLU) with a single user: the activation runs in the conv epilogue
+        for n in self._order:
+            if type(n.layer) is Conv1D and n.layer.activation is None and n not in self._out_nodes:
+                u = users.get(id(n), [])
+                if len(u) == 1 and isinstance(u[0].layer, _ActLayer) and u[0].layer.code != _lib.ACT_NONE:
+                    n.layer.post_act = (u[0].layer.code, u[0].layer.param)
+                    u[0].layer.fused = True
+        # consumer of a fused conv+activation (through views / the now-identity activation layer): it may apply
+        # the activation derivative in its own data-gradient epilogue, using its input as the mask source
+        for n in self._order:
+            if type(n.layer) in (Conv1D, Dense):
+                src = n.inputs[0]
+                ok = True
+                while ok and src is not self._in_node and (
+                        (isinstance(src.layer, _ActLayer) and src.layer.fused) or isinstance(src.layer, Reshape)):
+                    ok = len(users.get(id(src), [])) == 1 and src not in self._out_nodes
+                    src = src.inputs[0]
+                if ok and src is not self._in_node and type(src.layer) is Conv1D and src.layer.post_act is not None \
+                        and len(users.get(id(src), [])) == 1:
+                    n.layer.in_act = src.layer.post_act
 
     # a model can be used as a layer
     def __call__(self, x):
@@ -872,7 +1052,10 @@ class Model(Layer):
             if not want or dx is None:
                 continue
             if id(src) in grads:
-                call('gn_axpy_f32', ptr(grads[id(src)].reshape(-1)), ptr(dx.reshape(-1).contiguous()), 1.0,
+                acc = grads[id(src)]
+                if acc.dtype != torch.float32:
+                    acc = grads[id(src)] = _as_f32(acc)
+                call('gn_axpy_f32', ptr(acc.reshape(-1)), ptr(_as_f32(dx).reshape(-1).contiguous()), 1.0,
                      dx.numel(), stream())
             else:
                 grads[id(src)] = dx

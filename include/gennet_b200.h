@@ -146,6 +146,24 @@ int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void*
 int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
                          int Cout, int k, int stride, int pad_left, void* stream);
 
+/* Bandwidth-bound companions of the bf16 path.
+ *   smallcin fwd  : first convolution of a network, Cin in {1,2}: x f32 (B,L,Cin) -> y bf16 (B,Lout,Cout), bias+act fused
+ *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 8, Cout | 256)
+ *   dense_small_* : Dense with N <= 4 outputs over bf16 features (K % 8 == 0): fwd y f32 (M,N); dgrad dx bf16 (M,K)
+ *                   = act'(x_in) * dy w^T (x_in = the layer's input or NULL); wgrad dw f32 (K,N), db f32 (N) OVERWRITTEN
+ *   gn_act_bwd_bf16: dx = dy * act'(y) on bf16 tensors */
+int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const float* bias, void* y, int B, int L, int Cin,
+                                int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param,
+                                void* stream);
+int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
+                                  int Cout, int k, int stride, int pad_left, void* stream);
+int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N, int act,
+                            float act_param, void* stream);
+int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, int M, int K, int N,
+                              int in_act, float in_act_param, void* stream);
+int gn_dense_small_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int M, int K, int N, void* stream);
+int gn_act_bwd_bf16(const void* dy, const void* y, void* dx, long long n, int act, float param, void* stream);
+
 /* Conv2D(5x5, strides (2,1), 'same') over an (L,2,C) image (bbhMahoGANy.py:439,447) is a Conv1D with
  * Cin'=2Cin, Cout'=2Cout: w1 (kh, 2Cin, 2Cout) [kh,(wi,ci),(wo,co)] = w2 (kh,kw,Cin,Cout) [kh, wi-wo+pw, ci, co];
  * pw = left width pad (2 for kw=5). pack: w2->w1, b (Cout)->b1 (2Cout); unpack: dw1->dw2, db1->db (overwrite). */

@@ -78,7 +78,7 @@ def record_kinks(product_model):
 
         def fw(x, ctx, _l=l, _orig=orig):
             y = _orig(x, ctx)
-            _l._pc_rec[_l.name] = y.detach().cpu().numpy().copy()
+            _l._pc_rec[_l.name] = y.detach().float().cpu().numpy().copy()
             return y
         l.forward = fw
         l._pc_wrapped = True

@@ -83,3 +83,33 @@ def test_device_resident_steps_and_on_device_dropout():
     rn = torch.randn(8, 128, device='cuda', generator=g)
     sd, sg = bbh.gan_train_step(G, D, DG, ns, real, z1, rn, z2)
     assert len(sd) == 2 and len(sg) == 2 and np.isfinite(sd + sg).all()
+
+
+def test_pe_step_bf16_within_stated_tolerance():
+    """Throughput mode (bf16 operands on the tcgen05 tensor cores, fp32 accumulation / weights / optimizer).
+    Stated tolerance vs the float64 oracle: forward outputs 2e-2 of the output scale, losses 3e-2, every one-step
+    gradient 1e-1 relative L2 and 3e-1 of its max.  (bf16 carries 8 mantissa bits; activations AND back-propagated
+    gradients are rounded at each of the five stacked layers, and weight gradients are cancellation-heavy sums, so
+    the first layer sees ~7e-2.  The kernels themselves are pinned to 2^-8 / 1e-4 on bf16-rounded operands in
+    tests/test_gpu_conv_tc.py; this test pins the wiring of the bf16 graph.)"""
+    from gennet_b200 import nn
+    try:
+        nn.set_compute_dtype('bfloat16')
+        prod, orc, x, y = pc.pe_case(256, 8)
+        po, oo = prod.predict(x), orc.predict(x)
+        for a, b in zip(po, oo):
+            assert np.abs(a - b).max() <= 2e-2 * max(np.abs(b).max(), 1e-6)
+        ro = orc.train_on_batch(x, y)
+        rp = prod.train_on_batch(x, y)
+        assert np.allclose(rp[:3], ro[:3], rtol=3e-2, atol=1e-4)
+        gp = prod.get_gradients()
+        gmax = max(np.abs(g).max() for g in orc.last_grads)
+        for i, (a, b) in enumerate(zip(gp, orc.last_grads)):
+            el2 = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-3 * gmax * np.sqrt(b.size))
+            emax = np.abs(a - b).max() / max(np.abs(b).max(), 1e-3 * gmax)
+            assert np.isfinite(a).all() and el2 <= 1e-1 and emax <= 3e-1, (i, b.shape, el2, emax)
+        # the tensor-core kernels were really used
+        convs = [l for l in prod.all_layers() if isinstance(l, nn.Conv1D)]
+        assert [c._path() for c in convs] == ['smallcin', 'tc', 'tc', 'tc', 'smallcin', 'tc', 'tc', 'tc', 'tc']
+    finally:
+        nn.set_compute_dtype('float32')
