@@ -51,6 +51,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
@@ -111,7 +126,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 constexpr int TC_BM = 128;          // rows of an output tile (UMMA M)
 constexpr int TC_BK = 64;           // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;     // warps: 0 TMA producer, 1 MMA, 2-5 epilogue, 6 aux (mask) producer
+constexpr int TC_WG_THREADS = 192;  // wgrad kernel: warps 0 TMA producer, 1 MMA, 2-5 epilogue
 
 struct TcArgs {
     int B, L, Lout, Cin, Cout, k, s, p;   // convolution geometry (L = input length, Lout = output length)
@@ -124,12 +140,14 @@ struct TcArgs {
     int m_tiles;                           // tiles of 128 rows per (sample, parity)
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool AUX>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+    static constexpr int EPI_BYTES = 2 * TC_BM * 128;      // two 128-row x 64-column bf16 staging slabs
+    static constexpr int AUX_BYTES = AUX ? 2 * TC_BM * 128 : 0;   // two slabs of the mask source (dgrad)
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + AUX_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // ------------------------------------------------------------------------------------------------ fwd / dgrad
@@ -158,18 +176,24 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int n_nt, int m_tiles
     return c;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool AUX>
 __global__ void __launch_bounds__(TC_THREADS)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1,
+               const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1, TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    using S = TcSmem<BN, STAGES>;
+    using S = TcSmem<BN, STAGES, AUX>;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * S::STAGE_BYTES);
+    uint8_t* epi = tiles + STAGES * S::STAGE_BYTES;            // 1024-byte aligned (stage sizes are multiples of 1 KB)
+    uint8_t* auxs = epi + S::EPI_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(auxs + S::AUX_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;      // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* aux_full = tmem_empty + 2;       // [2]
+    uint64_t* aux_empty = aux_full + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npar = (a.mode == 1) ? a.s : 1;
@@ -188,6 +212,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);      // one arrival per epilogue warp
+            mbar_init(&aux_full[i], 1);
+            mbar_init(&aux_empty[i], 4);
         }
         fence_barrier_init();
     }
@@ -257,11 +283,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tc_commit(&tmem_full[acc]);     // accumulator complete
             }
         }
+    } else if (warp == 6) {
+        // aux producer: streams the mask source (the conv's own input, same shape as the output) slab by slab
+        if (AUX && lane == 0) {
+            int sc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
+                const CUtensorMap* xmap = (c.par == 0) ? &mapX0 : &mapX1;
+                for (int sl = 0; sl < BN / 64; ++sl, ++sc) {
+                    const int bi = sc & 1, ph = (sc >> 1) & 1;
+                    mbar_wait(&aux_empty[bi], ph ^ 1);
+                    mbar_expect_tx(&aux_full[bi], TC_BM * 128);
+                    tma_load_3d(auxs + bi * (TC_BM * 128), xmap, &aux_full[bi], c.n0 + sl * 64, c.m0, c.b);
+                }
+            }
+        }
     } else {
-        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (rows of the tile)
+        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (rows of the tile).  Each 64-column slab goes
+        // TMEM -> registers -> bias / activation / mask -> bf16 -> swizzled shared-memory slab -> TMA store
+        // (coalesced 128-byte rows; rows past the end of the sample are clipped by the tensor map).
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        int ti_local = 0;
+        const int epi_tid = threadIdx.x - 64;
+        int ti_local = 0, slab_ctr = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti_local) {
             const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
             const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
@@ -269,67 +313,87 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_after();
             const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
             const int r = c.m0 + row;            // row index within (sample, parity)
-            bool valid;
-            size_t off;                          // element offset of (row, n0) in the output tensor
-            if (a.mode == 0) {
-                valid = r < a.Lout;
-                off = ((size_t)c.b * a.Lout + r) * a.Cout + c.n0;
-            } else {
-                const int j = r * a.s + c.par;
-                valid = j < a.L;
-                off = ((size_t)c.b * a.L + j) * a.Cin + c.n0;
-            }
+            (void)r;
+            const CUtensorMap* omap = (c.par == 0) ? &mapO0 : &mapO1;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tacc + (uint32_t)c0, v);
-                if (c0 + 32 >= BN) {
+            for (int sl = 0; sl < BN / 64; ++sl, ++slab_ctr) {
+                uint32_t v[64];
+                {
+                    uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                    uint32_t (&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                    tmem_ld32(tacc + (uint32_t)(sl * 64), v0);
+                    tmem_ld32(tacc + (uint32_t)(sl * 64 + 32), v1);
+                }
+                if (sl == BN / 64 - 1) {
                     // all of this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                if (valid) {
-                    float f[32];
+                float f[64];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    if (a.mode == 0) {
+                for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(v[i]);
+                if (a.mode == 0) {
+                    if (a.bias != nullptr) {
+                        const float4* bp = reinterpret_cast<const float4*>(a.bias + c.n0 + sl * 64);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float t = f[i] + (a.bias ? __ldg(&a.bias[c.n0 + c0 + i]) : 0.f);
-                            f[i] = act_fwd(t, a.act, a.act_param);
-                        }
-                    } else if (a.aux != nullptr && a.act != GN_ACT_NONE) {
-                        const uint4* xin = reinterpret_cast<const uint4*>(a.aux + off + c0);
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            uint4 pk = __ldg(&xin[g4]);
-                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 y = __bfloat1622float2(h[e]);
-                                f[g4 * 8 + 2 * e] *= act_bwd_from_y(y.x, a.act, a.act_param);
-                                f[g4 * 8 + 2 * e + 1] *= act_bwd_from_y(y.y, a.act, a.act_param);
-                            }
+                        for (int g4 = 0; g4 < 16; ++g4) {
+                            float4 bv = __ldg(&bp[g4]);
+                            f[4 * g4 + 0] += bv.x; f[4 * g4 + 1] += bv.y; f[4 * g4 + 2] += bv.z; f[4 * g4 + 3] += bv.w;
                         }
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(a.out + off + c0);
+                    if (a.act == GN_ACT_RELU) {
 #pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4) {
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g4 * 8 + 0], f[g4 * 8 + 1]);
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g4 * 8 + 2], f[g4 * 8 + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 4], f[g4 * 8 + 5]);
-                        __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g4 * 8 + 6], f[g4 * 8 + 7]);
-                        uint4 pk;
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        dst[g4] = pk;
+                        for (int i = 0; i < 64; ++i) f[i] = fmaxf(f[i], 0.f);
+                    } else if (a.act != GN_ACT_NONE) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) f[i] = act_fwd(f[i], a.act, a.act_param);
                     }
+                } else if (AUX) {
+                    const int bi = slab_ctr & 1, ph = (slab_ctr >> 1) & 1;
+                    mbar_wait(&aux_full[bi], ph);
+                    const uint8_t* xs = auxs + bi * (TC_BM * 128) + row * 128;
+#pragma unroll
+                    for (int g8 = 0; g8 < 8; ++g8) {
+                        uint4 pk = *reinterpret_cast<const uint4*>(xs + ((g8 ^ (row & 7)) << 4));
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 y = __bfloat1622float2(h[e]);
+                            f[g8 * 8 + 2 * e] *= act_bwd_from_y(y.x, a.act, a.act_param);
+                            f[g8 * 8 + 2 * e + 1] *= act_bwd_from_y(y.y, a.act, a.act_param);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&aux_empty[bi]);
+                }
+                uint8_t* slab = epi + (slab_ctr & 1) * (TC_BM * 128);
+                // the TMA store that last read this slab (two slabs ago) must have finished reading it
+                if (epi_tid == 0) tma_store_wait_read<1>();
+                named_bar_sync(1, 128);
+#pragma unroll
+                for (int g8 = 0; g8 < 8; ++g8) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g8 * 8 + 0], f[g8 * 8 + 1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g8 * 8 + 2], f[g8 * 8 + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g8 * 8 + 4], f[g8 * 8 + 5]);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g8 * 8 + 6], f[g8 * 8 + 7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+                    *reinterpret_cast<uint4*>(slab + row * 128 + ((g8 ^ (row & 7)) << 4)) = pk;
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (epi_tid == 0) {
+                    tma_store_3d(omap, slab, c.n0 + sl * 64, c.m0, c.b);
+                    tma_store_commit();
                 }
             }
         }
+        if (epi_tid == 0) tma_store_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -353,7 +417,7 @@ struct TcWgradArgs {
 };
 
 template <int BN, int STAGES, bool SWAP>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_WG_THREADS)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
                      TcWgradArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -544,26 +608,34 @@ static int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
     return GN_OK;
 }
 
-template <int BN, int STAGES>
-static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, long long total_tiles,
+template <int BN, int STAGES, bool AUX>
+static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO0, const CUtensorMap& mO1,
+                          const CUtensorMap& mX0, const CUtensorMap& mX1, const TcArgs& a, long long total_tiles,
                           cudaStream_t st) {
-    auto kfn = conv_tc_kernel<BN, STAGES>;
-    constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
+    auto kfn = conv_tc_kernel<BN, STAGES, AUX>;
+    constexpr int smem = TcSmem<BN, STAGES, AUX>::TOTAL;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
     const int grid = (int)(total_tiles < (long long)num_sms() ? total_tiles : (long long)num_sms());
-    kfn<<<grid, TC_THREADS, smem, st>>>(mA, mB, a);
+    kfn<<<grid, TC_THREADS, smem, st>>>(mA, mB, mO0, mO1, mX0, mX1, a);
     return cuda_status("conv_tc_kernel");
 }
 
-static int dispatch_conv_tc(int BN, const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, long long tiles,
-                            cudaStream_t st) {
-    if (BN == 256) return launch_conv_tc<256, 4>(mA, mB, a, tiles, st);
-    if (BN == 128) return launch_conv_tc<128, 6>(mA, mB, a, tiles, st);
-    return launch_conv_tc<64, 8>(mA, mB, a, tiles, st);
+static int dispatch_conv_tc(int BN, bool aux, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO0,
+                            const CUtensorMap& mO1, const CUtensorMap& mX0, const CUtensorMap& mX1, const TcArgs& a,
+                            long long tiles, cudaStream_t st) {
+    if (!aux) {
+        if (BN == 256) return launch_conv_tc<256, 4, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+        if (BN == 128) return launch_conv_tc<128, 6, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+        return launch_conv_tc<64, 8, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+    }
+    if (BN == 256) return launch_conv_tc<256, 3, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+    if (BN == 128) return launch_conv_tc<128, 5, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+    return launch_conv_tc<64, 6, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
 }
 static int pick_bn(int C) { return (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : 64); }
 
@@ -577,7 +649,7 @@ static int launch_wgrad_tc(const CUtensorMap& mX, const CUtensorMap& mDY, const 
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
-    kfn<<<grid, TC_THREADS, smem, st>>>(mX, mDY, a);
+    kfn<<<grid, TC_WG_THREADS, smem, st>>>(mX, mDY, a);
     return cuda_status("conv_tc_wgrad_kernel");
 }
 
@@ -634,7 +706,11 @@ extern "C" int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bi
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
     a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = (__nv_bfloat16*)y;
     a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
-    return dispatch_conv_tc(BN, mA, mB, a, (long long)B * a.m_tiles * (Cout / BN), as_stream(stream));
+    // output: Y viewed as (Cout, Lout, B), 64-channel x 128-row store boxes
+    CUtensorMap mO;
+    rc = make_map3(&mO, y, Cout, Lout, B, Cout, (uint64_t)Lout * Cout, 64, TC_BM, 1);
+    if (rc != GN_OK) return rc;
+    return dispatch_conv_tc(BN, false, mA, mB, mO, mO, mO, mO, a, (long long)B * a.m_tiles * (Cout / BN), as_stream(stream));
 }
 
 extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, int B, int L, int Cin,
@@ -657,7 +733,22 @@ extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* 
     a.out = (__nv_bfloat16*)dx;
     const int rows = (L + stride - 1) / stride;      // rows of the largest parity class
     a.m_tiles = (rows + TC_BM - 1) / TC_BM;
-    return dispatch_conv_tc(BN, mA, mB, a, (long long)B * stride * a.m_tiles * (Cin / BN), as_stream(stream));
+    // output: one map per parity class r: rows j = i*stride + r of dX, viewed as (Cin, rows_r, B)
+    CUtensorMap mO[2], mX[2];
+    const bool aux = (x_in != nullptr && in_act != GN_ACT_NONE);
+    for (int r = 0; r < 2; ++r) {
+        const int rr = (r < stride) ? r : 0;
+        const int rows_r = (L - rr + stride - 1) / stride;
+        rc = make_map3(&mO[r], (const __nv_bfloat16*)dx + (size_t)rr * Cin, Cin, rows_r, B, (uint64_t)stride * Cin,
+                       (uint64_t)L * Cin, 64, TC_BM, 1);
+        if (rc != GN_OK) return rc;
+        // the mask source has the shape of dx: same parity views
+        rc = make_map3(&mX[r], (const __nv_bfloat16*)(aux ? x_in : dx) + (size_t)rr * Cin, Cin, rows_r, B,
+                       (uint64_t)stride * Cin, (uint64_t)L * Cin, 64, TC_BM, 1);
+        if (rc != GN_OK) return rc;
+    }
+    return dispatch_conv_tc(BN, aux, mA, mB, mO[0], mO[1], mX[0], mX[1], a,
+                            (long long)B * stride * a.m_tiles * (Cin / BN), as_stream(stream));
 }
 
 extern "C" int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
@@ -681,7 +772,7 @@ extern "C" int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, fl
     a.dw = dw;
     const bool swap = (Cin == 64);
     int m_tiles, BN;
-    if (!swap) { m_tiles = Cin / 128; BN = (Cout % 128 == 0) ? 128 : 64; a.n_tiles_n = Cout / BN; }
+    if (!swap) { m_tiles = Cin / 128; BN = pick_bn(Cout); a.n_tiles_n = Cout / BN; }
     else { m_tiles = Cout / 128; BN = 64; a.n_tiles_n = 1; }
     const int out_tiles = k * m_tiles * a.n_tiles_n;
     int splits = (2 * num_sms() + out_tiles - 1) / out_tiles;
@@ -691,7 +782,8 @@ extern "C" int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, fl
     splits = (a.iters_total + a.iters_per_split - 1) / a.iters_per_split;
     dim3 grid(k, m_tiles * a.n_tiles_n, splits);
     if (swap) rc = launch_wgrad_tc<64, 4, true>(mX, mDY, a, grid, st);
-    else if (BN == 128) rc = launch_wgrad_tc<128, 4, false>(mX, mDY, a, grid, st);
+    else if (BN == 256) rc = launch_wgrad_tc<256, 4, false>(mX, mDY, a, grid, st);
+    else if (BN == 128) rc = launch_wgrad_tc<128, 6, false>(mX, mDY, a, grid, st);
     else rc = launch_wgrad_tc<64, 4, false>(mX, mDY, a, grid, st);
     if (rc != GN_OK) return rc;
     if (db != nullptr) {
