@@ -52,38 +52,82 @@ __global__ void __launch_bounds__(256) conv_smallcin_fwd_kernel(const float* __r
 }
 
 // ---- first-layer weight gradient: dw f32 (k,CIN,Cout), db f32 (Cout) from x f32 and dy bf16 (pre-activation grad) ----
-// block = Cout threads x RY row lanes; each thread keeps k*CIN (+1 bias) partial sums for its channel
+// thread = 8 consecutive output channels (one 128-bit dy load per row) x one row lane; k*CIN*8 (+8 bias) partial sums
 template <int CIN, int KMAX>
 __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* __restrict__ x,
                                                                   const __nv_bfloat16* __restrict__ dy,
                                                                   float* __restrict__ dw, float* __restrict__ db, int B,
                                                                   int L, int Lout, int Cout, int k, int s, int p,
                                                                   long long rows_per_block) {
-    const int co = threadIdx.x % Cout;
-    const int ry = threadIdx.x / Cout, nry = blockDim.x / Cout;
-    float acc[KMAX * CIN];
-    float accb = 0.f;
+    const int groups = Cout / 8;
+    const int g = threadIdx.x % groups;
+    const int ry = threadIdx.x / groups, nry = blockDim.x / groups;
+    float acc[KMAX * CIN][8];
+    float accb[8];
 #pragma unroll
-    for (int i = 0; i < KMAX * CIN; ++i) acc[i] = 0.f;
+    for (int i = 0; i < KMAX * CIN; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accb[j] = 0.f;
     const long long rows = (long long)B * Lout;
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-    for (long long row = r0 + ry; row < r1; row += nry) {
-        const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
-        const float g = __bfloat162float(dy[(size_t)row * Cout + co]);
-        accb += g;
+    if (ry < nry) {
+        for (long long row = r0 + ry; row < r1; row += nry) {
+            const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * Cout) + g);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+            float gv[8];
 #pragma unroll
-        for (int t = 0; t < KMAX; ++t) {
-            if (t >= k) break;
-            const int pos = l * s + t - p;
-            if (pos < 0 || pos >= L) continue;
+            for (int e = 0; e < 4; ++e) {
+                float2 v = __bfloat1622float2(h[e]);
+                gv[2 * e] = v.x;
+                gv[2 * e + 1] = v.y;
+            }
 #pragma unroll
-            for (int c = 0; c < CIN; ++c) acc[t * CIN + c] = fmaf(__ldg(&x[((size_t)b * L + pos) * CIN + c]), g, acc[t * CIN + c]);
+            for (int j = 0; j < 8; ++j) accb[j] += gv[j];
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) {
+                if (t < k) {
+                    const int pos = l * s + t - p;
+                    if (pos >= 0 && pos < L) {
+#pragma unroll
+                        for (int c = 0; c < CIN; ++c) {
+                            const float xv = __ldg(&x[((size_t)b * L + pos) * CIN + c]);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[t * CIN + c][j] = fmaf(xv, gv[j], acc[t * CIN + c][j]);
+                        }
+                    }
+                }
+            }
         }
     }
-    for (int t = 0; t < k; ++t)
+    // combine: row lanes that share a warp by shuffles, the 8 warps through shared memory, then one atomic per
+    // (tap, cin, channel) and block
+    constexpr int NV = KMAX * CIN + 1;
+    __shared__ float sm[8][NV][128];            // Cout <= 128
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) atomicAdd(&dw[((size_t)t * CIN + c) * Cout + co], acc[t * CIN + c]);
-    if (db != nullptr) atomicAdd(&db[co], accb);
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = (i < KMAX * CIN) ? acc[i < KMAX * CIN ? i : 0][j] : accb[j];
+            for (int o = groups; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane < groups && groups <= 32) sm[warp][i][(lane % groups) * 8 + j] = v;
+        }
+    }
+    __syncthreads();
+    const int gpw = groups < 32 ? groups : 32;       // column groups held by one warp's lanes
+    (void)gpw;
+    for (int e = threadIdx.x; e < NV * Cout; e += blockDim.x) {
+        const int i = e / Cout, co = e - i * Cout;
+        if (i < KMAX * CIN && i >= k * CIN) continue;
+        float t = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) t += sm[w8][i][co];
+        if (i < KMAX * CIN) atomicAdd(&dw[(size_t)i * Cout + co], t);
+        else if (db != nullptr) atomicAdd(&db[co], t);
+    }
 }
 
 // ---- Dense with N <= 4 outputs over bf16 features -------------------------------------------------------------
@@ -103,14 +147,21 @@ __global__ void __launch_bounds__(512) dense_small_fwd_bf16_kernel(const __nv_bf
     for (int i = threadIdx.x; i < K8; i += blockDim.x) {
         uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr) + i);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        // the 8*NS weights of this chunk are contiguous: NS*2 128-bit loads
+        float wv[8 * NS];
+        const float4* wp = reinterpret_cast<const float4*>(w + (size_t)i * 8 * NS);
+#pragma unroll
+        for (int q4 = 0; q4 < 2 * NS; ++q4) {
+            float4 t4 = __ldg(&wp[q4]);
+            wv[4 * q4] = t4.x; wv[4 * q4 + 1] = t4.y; wv[4 * q4 + 2] = t4.z; wv[4 * q4 + 3] = t4.w;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float2 v = __bfloat1622float2(h[e]);
-            const int kk = i * 8 + 2 * e;
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                acc[j] = fmaf(v.x, __ldg(&w[(size_t)kk * NS + j]), acc[j]);
-                acc[j] = fmaf(v.y, __ldg(&w[(size_t)(kk + 1) * NS + j]), acc[j]);
+                acc[j] = fmaf(v.x, wv[(2 * e) * NS + j], acc[j]);
+                acc[j] = fmaf(v.y, wv[(2 * e + 1) * NS + j], acc[j]);
             }
         }
     }
@@ -142,11 +193,18 @@ __global__ void __launch_bounds__(256) dense_small_dgrad_bf16_kernel(const float
 #pragma unroll
         for (int j = 0; j < NS; ++j) g[j] = __ldg(&dy[(size_t)m * NS + j]);
         float o[8];
+        float wv[8 * NS];
+        const float4* wp = reinterpret_cast<const float4*>(w + (size_t)c * 8 * NS);
+#pragma unroll
+        for (int q4 = 0; q4 < 2 * NS; ++q4) {
+            float4 t4 = __ldg(&wp[q4]);
+            wv[4 * q4] = t4.x; wv[4 * q4 + 1] = t4.y; wv[4 * q4 + 2] = t4.z; wv[4 * q4 + 3] = t4.w;
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float sacc = 0.f;
 #pragma unroll
-            for (int j = 0; j < NS; ++j) sacc = fmaf(g[j], __ldg(&w[(size_t)(c * 8 + e) * NS + j]), sacc);
+            for (int j = 0; j < NS; ++j) sacc = fmaf(g[j], wv[e * NS + j], sacc);
             o[e] = sacc;
         }
         if (xin != nullptr && in_act != GN_ACT_NONE) {
@@ -245,22 +303,23 @@ extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const
 extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, float* db, int B, int L, int Cin,
                                              int Lout, int Cout, int k, int stride, int pad_left, void* stream) {
     GN_REQUIRE(x && dy && dw, "null pointer");
-    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 8 && stride > 0 && pad_left >= 0, "bad geometry (k <= 8)");
-    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout <= 256 && 256 % Cout == 0, "needs Cin in {1,2} and Cout dividing 256");
+    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 5 && stride > 0 && pad_left >= 0, "bad geometry (k <= 5)");
+    GN_REQUIRE((Cin == 1 || Cin == 2) && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128),
+               "needs Cin in {1,2} and Cout in {8,16,32,64,128}");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin * Cout, st);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);
     if (B == 0) return GN_OK;
     const long long rows = (long long)B * Lout;
-    long long blocks = 8LL * num_sms();
+    long long blocks = 4LL * num_sms();
     long long per = (rows + blocks - 1) / blocks;
     if (per < 64) per = 64;
     blocks = (rows + per - 1) / per;
     if (Cin == 1)
-        conv_smallcin_wgrad_kernel<1, 8><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
+        conv_smallcin_wgrad_kernel<1, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
                                                                          Cout, k, stride, pad_left, per);
     else
-        conv_smallcin_wgrad_kernel<2, 8><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
+        conv_smallcin_wgrad_kernel<2, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
                                                                          Cout, k, stride, pad_left, per);
     return cuda_status("conv_smallcin_wgrad_kernel");
 }

@@ -554,23 +554,42 @@ __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16*
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __bfloat162float(x[i]);
 }
-// per-channel sum of a (rows, C) bf16 matrix -> f32 (bias gradient); out must be zeroed by the caller
+// per-channel sum of a (rows, C) bf16 matrix -> f32 (bias gradient); out must be zeroed by the caller.
+// thread = 8 consecutive channels (one 128-bit load per row), RL row lanes per block, shared-memory combine.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
-                                                          long long rows_per_split, float* __restrict__ out) {
-    __shared__ float sm[8][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ry = threadIdx.x >> 5;
-    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
-    float s = 0.f;
-    if (c < C)
-        for (long long r = r0 + ry; r < r1; r += 8) s += __bfloat162float(x[r * C + c]);
-    sm[ry][threadIdx.x & 31] = s;
-    __syncthreads();
-    if (ry == 0 && c < C) {
-        float t = 0.f;
+                                                          long long rows_per_block, float* __restrict__ out) {
+    __shared__ float sm[256][9];
+    const int groups = C / 8;                       // C % 8 == 0
+    const int g = threadIdx.x % groups;
+    const int rl = threadIdx.x / groups, nrl = blockDim.x / groups;
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float acc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
-        atomicAdd(&out[c], t);
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (rl < nrl) {
+        for (long long r = r0 + rl; r < r1; r += nrl) {
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + r * C) + g);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 v = __bfloat1622float2(h[e]);
+                acc[2 * e] += v.x;
+                acc[2 * e + 1] += v.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+        for (int l = 0; l < nrl; ++l)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] += sm[l * groups + threadIdx.x][j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&out[threadIdx.x * 8 + j], t[j]);
     }
 }
 
@@ -789,13 +808,13 @@ extern "C" int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, fl
     if (db != nullptr) {
         cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);
         const long long rows = (long long)B * Lout;
-        int cb = (Cout + 31) / 32;
-        long long sp = (4LL * num_sms() + cb - 1) / cb;
-        if (sp > (rows + 63) / 64) sp = (rows + 63) / 64;
-        if (sp < 1) sp = 1;
-        long long per = (rows + sp - 1) / sp;
-        sp = (rows + per - 1) / per;
-        colsum_bf16_kernel<<<dim3(cb, (unsigned)sp), 256, 0, st>>>((const __nv_bfloat16*)dy, rows, Cout, per, db);
+        // Cout is a multiple of 64 and <= 2048 here: Cout/8 column groups per block, 256/(Cout/8) row lanes
+        GN_REQUIRE(Cout / 8 <= 256, "Cout too large for the bias-gradient kernel");
+        long long blocks = 4LL * num_sms();
+        long long per = (rows + blocks - 1) / blocks;
+        if (per < 32) per = 32;
+        blocks = (rows + per - 1) / per;
+        colsum_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, Cout, per, db);
         return cuda_status("colsum_bf16_kernel");
     }
     return GN_OK;

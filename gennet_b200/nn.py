@@ -340,7 +340,7 @@ class Conv1D(Layer):
             return 'f32'
         if cin % 64 == 0 and co % 64 == 0 and (cin % 128 == 0 or (cin == 64 and co % 128 == 0)):
             return 'tc'
-        if cin <= 2 and co % 8 == 0 and 256 % co == 0:
+        if cin <= 2 and co in (8, 16, 32, 64, 128) and self.k <= 5:
             return 'smallcin'
         return 'f32'
 

@@ -148,7 +148,7 @@ int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, in
 
 /* Bandwidth-bound companions of the bf16 path.
  *   smallcin fwd  : first convolution of a network, Cin in {1,2}: x f32 (B,L,Cin) -> y bf16 (B,Lout,Cout), bias+act fused
- *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 8, Cout | 256)
+ *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 5, Cout in {8,..,128})
  *   dense_small_* : Dense with N <= 4 outputs over bf16 features (K % 8 == 0): fwd y f32 (M,N); dgrad dx bf16 (M,K)
  *                   = act'(x_in) * dy w^T (x_in = the layer's input or NULL); wgrad dw f32 (K,N), db f32 (N) OVERWRITTEN
  *   gn_act_bwd_bf16: dx = dy * act'(y) on bf16 tensors */

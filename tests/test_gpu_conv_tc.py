@@ -85,3 +85,63 @@ def test_tc_conv_fwd_dgrad_wgrad(case):
     torch.cuda.synchronize()
     assert_close(dw.cpu().numpy(), wr.grad.numpy(), 'tc conv wgrad', 1e-4)
     assert_close(db.cpu().numpy(), dy.float().cpu().double().sum((0, 1)).numpy(), 'tc conv bias grad', 1e-4)
+
+
+@pytest.mark.parametrize('case', [(3, 200, 1, 64, 5, 2, 'same'), (2, 256, 1, 64, 5, 1, 'same'), (2, 100, 2, 128, 5, 2, 'same'),
+                                  (2, 77, 1, 32, 3, 1, 'valid')])
+def test_first_layer_kernels(case):
+    from gennet_b200 import _lib as L_
+    B, L, Cin, Cout, k, s, padding = case
+    rs = np.random.RandomState(abs(hash(case)) % 2 ** 31)
+    x = torch.as_tensor(rs.normal(size=(B, L, Cin)).astype(np.float32)).cuda()
+    w = torch.as_tensor((rs.normal(size=(k, Cin, Cout)) / math.sqrt(k * Cin)).astype(np.float32)).cuda()
+    bias = torch.as_tensor(rs.normal(size=Cout).astype(np.float32)).cuda()
+    xr = x.cpu().double()
+    wr = w.cpu().double().requires_grad_(True)
+    br = bias.cpu().double().requires_grad_(True)
+    xp = xr.permute(0, 2, 1)
+    pad = 0
+    if padding == 'same':
+        pl, pr = ko.same_pad(L, k, s)
+        xp = F.pad(xp, (pl, pr))
+        pad = pl
+    yr = F.conv1d(xp, wr.permute(2, 1, 0), br, stride=s).permute(0, 2, 1)
+    Lout = yr.shape[1]
+    y = torch.empty(B, Lout, Cout, dtype=torch.bfloat16, device='cuda')
+    st = L_.stream()
+    L_.call('gn_conv1d_smallcin_fwd_bf16', L_.ptr(x), L_.ptr(w), L_.ptr(bias), L_.ptr(y, torch.bfloat16), B, L, Cin, Lout, Cout,
+            k, s, pad, L_.ACT_RELU, 0.0, st)
+    assert_close(y.float().cpu().numpy(), torch.relu(yr).detach().numpy(), 'smallcin fwd', 2 ** -8)
+    dy = bf(rs.normal(size=(B, Lout, Cout)))
+    (yr * dy.float().cpu().double()).sum().backward()
+    dw = torch.full((k, Cin, Cout), float('nan'), device='cuda')
+    db = torch.full((Cout,), float('nan'), device='cuda')
+    L_.call('gn_conv1d_smallcin_wgrad_bf16', L_.ptr(x), L_.ptr(dy, torch.bfloat16), L_.ptr(dw), L_.ptr(db), B, L, Cin, Lout, Cout,
+            k, s, pad, st)
+    assert_close(dw.cpu().numpy(), wr.grad.numpy(), 'smallcin wgrad', 1e-4)
+    assert_close(db.cpu().numpy(), br.grad.numpy(), 'smallcin bias grad', 1e-4)
+
+
+@pytest.mark.parametrize('M,K,N', [(5, 64000, 1), (3, 4096, 2), (9, 1000 * 8, 4)])
+def test_dense_small_bf16(M, K, N):
+    from gennet_b200 import _lib as L_
+    rs = np.random.RandomState(M * 7 + N)
+    x = bf(np.maximum(rs.normal(size=(M, K)), 0))            # post-ReLU features
+    w = torch.as_tensor((rs.normal(size=(K, N)) / math.sqrt(K)).astype(np.float32)).cuda()
+    b = torch.as_tensor(rs.normal(size=N).astype(np.float32)).cuda()
+    dy = torch.as_tensor(rs.normal(size=(M, N)).astype(np.float32)).cuda()
+    xr, wr = x.float().cpu().double(), w.cpu().double()
+    st = L_.stream()
+    y = torch.empty(M, N, device='cuda')
+    L_.call('gn_dense_small_fwd_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(w), L_.ptr(b), L_.ptr(y), M, K, N, L_.ACT_NONE, 0.0, st)
+    assert_close(y.cpu().numpy(), (xr @ wr + b.cpu().double()).numpy(), 'dense small fwd', 1e-5)
+    dx = torch.empty(M, K, dtype=torch.bfloat16, device='cuda')
+    L_.call('gn_dense_small_dgrad_bf16', L_.ptr(dy), L_.ptr(w), L_.ptr(x, torch.bfloat16), L_.ptr(dx, torch.bfloat16), M, K, N,
+            L_.ACT_RELU, 0.0, st)
+    ref = (dy.cpu().double() @ wr.t()) * (xr > 0)
+    assert_close(dx.float().cpu().numpy(), ref.numpy(), 'dense small dgrad*mask', 2 ** -8)
+    dw = torch.full((K, N), float('nan'), device='cuda')
+    db = torch.full((N,), float('nan'), device='cuda')
+    L_.call('gn_dense_small_wgrad_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(dy), L_.ptr(dw), L_.ptr(db), M, K, N, st)
+    assert_close(dw.cpu().numpy(), (xr.t() @ dy.cpu().double()).numpy(), 'dense small wgrad', 1e-5)
+    assert_close(db.cpu().numpy(), dy.cpu().double().sum(0).numpy(), 'dense small bias grad', 1e-6)
