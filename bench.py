@@ -238,8 +238,9 @@ def run_ours(args):
                                            'train_on_batch -> D2H [loss, acc]'},
            'gpu_launches': launches, 'clocks': clocks}
 
+    prof = profile_pass(one_step, args, B, L, N)      # every rank: the steps contain collectives
     if rank == 0:
-        out.update(profile_pass(one_step, args, B, L, N))
+        out.update(prof)
         if world == 1:
             out['cpu_baseline'] = cpu_baseline(steps=3, warmup=1)
         print(json.dumps(out))
