@@ -18,7 +18,9 @@
 struct gn_fft_plan {
     int N;
     int log2M;
-    float2* tw;  // device, exp(-2*pi*i*j/N), j in [0,N)
+    float2* tw;   // device, exp(-2*pi*i*j/N), j in [0,N)   (real-FFT packing twiddles)
+    float2* ptw;  // device, per-pass Stockham twiddles laid out [pass][r-1][k] = exp(-2*pi*i*r*k/(p*R)), k < p,
+                  // so that the lanes of a warp (consecutive k) read consecutive 8-byte entries
 };
 
 namespace gn {
@@ -109,13 +111,50 @@ struct Dft<16, DIR> {
 // shared-memory index with one pad slot per 16 complex values (kills the stride-R store conflicts)
 __device__ __forceinline__ int PADI(int i) { return i + (i >> 4); }
 
-// One Stockham pass of radix R over the M-point array; each thread owns 16/R butterflies (16 points).
-// LOAD(idx)->float2 fetches logical element idx of the pass input; STORE(idx, val) writes logical
-// element idx of the pass output. A __syncthreads separates the loads from the stores so that the
-// pass may run in place.
-template <int R, int DIR, int LOG2M, class LOAD, class STORE>
-__device__ __forceinline__ void fft_pass(int p, const float2* __restrict__ tw, int tw_stride_log2, LOAD load,
-                                         STORE store, bool sync_before_store) {
+// Shared-memory views with compile-time strides: element (i + r*T) of the padded array is PADI(i) + r*(T + T/16)
+// whenever T is a multiple of 16, so every access of a thread is base + immediate.
+template <int STRIDE>
+__device__ __forceinline__ int padi_off(int base_idx, int r) {
+    if (STRIDE % 16 == 0) return PADI(base_idx) + r * (STRIDE + STRIDE / 16);
+    return PADI(base_idx + r * STRIDE);
+}
+
+struct SmemIn {
+    const float2* buf;
+    template <int T>
+    __device__ __forceinline__ float2 get(int i, int r) const { return buf[padi_off<T>(i, r)]; }
+};
+struct SmemOut {
+    float2* buf;
+    template <int P>
+    __device__ __forceinline__ void put(int base, int r, float2 v) const { buf[padi_off<P>(base, r)] = v; }
+};
+
+// adapters for pass inputs/outputs expressed on the logical index
+template <class F>
+struct IdxIn {
+    F f;
+    template <int T>
+    __device__ __forceinline__ float2 get(int i, int r) const { return f(i + r * T); }
+};
+template <class F>
+struct IdxOut {
+    F f;
+    template <int P>
+    __device__ __forceinline__ void put(int base, int r, float2 v) const { f(base + r * P, v); }
+};
+template <class F>
+__device__ __forceinline__ IdxIn<F> make_in(F f) { return IdxIn<F>{f}; }
+template <class F>
+__device__ __forceinline__ IdxOut<F> make_out(F f) { return IdxOut<F>{f}; }
+
+// One Stockham pass of radix R with sub-transform length P over the M-point array; each thread owns 16/R
+// butterflies (16 points).  IN::get<T>(i, r) fetches logical element i + r*T of the pass input, OUT::put<P>(base, r, v)
+// writes logical element base + r*P of the pass output.  A __syncthreads separates loads from stores so that the
+// pass may run in place.  ptw = this pass's twiddle table [r-1][k].
+template <int R, int P, int DIR, int LOG2M, class IN, class OUT>
+__device__ __forceinline__ void fft_pass(const float2* __restrict__ ptw, const IN& in, const OUT& out,
+                                         bool sync_before_store) {
     constexpr int M = 1 << LOG2M;
     constexpr int T = M / R;
     constexpr int NT = M / 16;
@@ -126,14 +165,12 @@ __device__ __forceinline__ void fft_pass(int p, const float2* __restrict__ tw, i
     for (int it = 0; it < IT; ++it) {
         const int i = tid + it * NT;
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[it][r] = load(i + r * T);
-        if (p > 1) {
-            const int k = i & (p - 1);
-            // exp(DIR*2*pi*i*r*k/(p*R)) = tw_M[r*k*M/(p*R)], tw_M[j] = tw_N[2j]
-            const int step = (M / R) / p;
+        for (int r = 0; r < R; ++r) v[it][r] = in.template get<T>(i, r);
+        if (P > 1) {
+            const int k = i & (P - 1);
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                float2 w = __ldg(&tw[(size_t)(r * k * step) << tw_stride_log2]);
+                float2 w = __ldg(&ptw[(r - 1) * P + k]);
                 if (DIR > 0) w.y = -w.y;
                 v[it][r] = cmul(v[it][r], w);
             }
@@ -144,10 +181,10 @@ __device__ __forceinline__ void fft_pass(int p, const float2* __restrict__ tw, i
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
         const int i = tid + it * NT;
-        const int k = i & (p - 1);
+        const int k = i & (P - 1);
         const int base = (i - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) store(base + r * p, v[it][Dft<R, DIR>::out_reg(r)]);
+        for (int r = 0; r < R; ++r) out.template put<P>(base, r, v[it][Dft<R, DIR>::out_reg(r)]);
     }
 }
 
@@ -156,43 +193,56 @@ template <int LOG2M>
 struct Plan {
     static constexpr int REM = 1 << (LOG2M & 3);
     static constexpr int N16 = LOG2M >> 2;
+    // offset (in entries) of the twiddle table of the j-th radix-16 pass (sub-transform length p = REM*16^j)
+    static constexpr int table_offset(int j) {
+        int off = 0, p = REM;
+        for (int q = 0; q < j; ++q) {
+            if (p > 1) off += 15 * p;
+            p *= 16;
+        }
+        return off;
+    }
+    static constexpr int table_size() { return table_offset(N16); }
 };
 
-// Full M-point complex FFT.  first_load reads the logical input; the result ends in smem `buf`
-// (padded natural order) unless last_store is used for the final pass (LAST_TO_CUSTOM).
-template <int DIR, int LOG2M, class LOAD0, class STOREL>
-__device__ __forceinline__ void fft_full(float2* buf, const float2* __restrict__ tw, LOAD0 first_load,
-                                         bool first_from_smem, STOREL last_store, bool last_custom) {
+template <int DIR, int LOG2M, int J, class IN, class OUTL>
+__device__ __forceinline__ void fft16_passes(float2* buf, const float2* __restrict__ ptw, const IN& first_in,
+                                             bool first_is_custom, bool first_from_smem, const OUTL& last_out,
+                                             bool last_custom) {
     constexpr int REM = Plan<LOG2M>::REM;
     constexpr int N16 = Plan<LOG2M>::N16;
-    auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
-    auto sm_store = [&](int idx, float2 val) { buf[PADI(idx)] = val; };
-    int p = 1;
-    bool first = true;
-    if (REM > 1) {
-        // a REM pass is never the last one (N16 >= 1 for every supported size)
-        fft_pass<(REM > 1 ? REM : 2), DIR, LOG2M>(p, tw, 1, first_load, sm_store, first_from_smem);
-        __syncthreads();
-        p *= REM;
-        first = false;
-    }
-#pragma unroll
-    for (int j = 0; j < N16; ++j) {
-        const bool last = (j == N16 - 1);
-        if (first) {
-            if (last && last_custom)
-                fft_pass<16, DIR, LOG2M>(p, tw, 1, first_load, last_store, first_from_smem);
-            else
-                fft_pass<16, DIR, LOG2M>(p, tw, 1, first_load, sm_store, first_from_smem);
+    if constexpr (J < N16) {
+        constexpr int P = REM << (4 * J);
+        const float2* tab = ptw + Plan<LOG2M>::table_offset(J);
+        constexpr bool last = (J == N16 - 1);
+        SmemIn sin{buf};
+        SmemOut sout{buf};
+        if (J == 0 && first_is_custom) {
+            if (last && last_custom) fft_pass<16, P, DIR, LOG2M>(tab, first_in, last_out, first_from_smem);
+            else fft_pass<16, P, DIR, LOG2M>(tab, first_in, sout, first_from_smem);
         } else {
-            if (last && last_custom)
-                fft_pass<16, DIR, LOG2M>(p, tw, 1, sm_load, last_store, false);
-            else
-                fft_pass<16, DIR, LOG2M>(p, tw, 1, sm_load, sm_store, true);
+            if (last && last_custom) fft_pass<16, P, DIR, LOG2M>(tab, sin, last_out, false);
+            else fft_pass<16, P, DIR, LOG2M>(tab, sin, sout, true);
         }
         if (!(last && last_custom)) __syncthreads();
-        p *= 16;
-        first = false;
+        fft16_passes<DIR, LOG2M, J + 1>(buf, ptw, first_in, first_is_custom, first_from_smem, last_out, last_custom);
+    }
+}
+
+// Full M-point complex FFT.  first_in reads the logical input of the first pass; the result ends in smem `buf`
+// (padded natural order) unless last_out is used for the final pass (last_custom).
+template <int DIR, int LOG2M, class IN, class OUTL>
+__device__ __forceinline__ void fft_full(float2* buf, const float2* __restrict__ ptw, const IN& first_in,
+                                         bool first_from_smem, const OUTL& last_out, bool last_custom) {
+    constexpr int REM = Plan<LOG2M>::REM;
+    if constexpr (REM > 1) {
+        // a REM pass is never the last one (N16 >= 1 for every supported size); it has P = 1: no twiddles
+        SmemOut sout{buf};
+        fft_pass<REM, 1, DIR, LOG2M>(ptw, first_in, sout, first_from_smem);
+        __syncthreads();
+        fft16_passes<DIR, LOG2M, 0>(buf, ptw, first_in, false, false, last_out, last_custom);
+    } else {
+        fft16_passes<DIR, LOG2M, 0>(buf, ptw, first_in, true, first_from_smem, last_out, last_custom);
     }
 }
 
@@ -264,6 +314,7 @@ struct SynthArgs {
     const float* weights;    // (Nf) (IRFFT: may be null)
     float* y;
     const float2* tw;
+    const float2* ptw;
     int batch, n_templates, crop_lo, crop_len, roll, drop_dc;
     float noise_scale, out_scale;
     unsigned long long seed, sample_offset;
@@ -276,6 +327,7 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
     constexpr int Nf = M + 1;
     extern __shared__ float2 buf[];  // PADI(M) complex
     const float2* __restrict__ tw = a.tw;
+    const float2* __restrict__ ptw = a.ptw;
 
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         // output of the final inverse pass: packed (y[2j], y[2j+1]) at logical index j
@@ -316,8 +368,7 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
             };
             irfft_pre<LOG2M>(buf, tw, spec, a.drop_dc != 0);
             __syncthreads();
-            auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
-            fft_full<+1, LOG2M>(buf, tw, sm_load, true, out_store, true);
+            fft_full<+1, LOG2M>(buf, ptw, SmemIn{buf}, true, make_out(out_store), true);
             __syncthreads();
             continue;
         }
@@ -343,9 +394,7 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
                 irfft_pre<LOG2M>(buf, tw, spec, true);
             }
             __syncthreads();
-            auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
-            auto sm_store = [&](int idx, float2 val) { buf[PADI(idx)] = val; };
-            fft_full<+1, LOG2M>(buf, tw, sm_load, true, sm_store, false);
+            fft_full<+1, LOG2M>(buf, ptw, SmemIn{buf}, true, SmemOut{buf}, false);
             // fft_full ends with a __syncthreads when the last pass goes to smem
         }
 
@@ -376,15 +425,11 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
                 float2 w = __ldg(&win2[idx]);
                 return make_float2(v.x * w.x, v.y * w.y);
             };
-            auto sm_store = [&](int idx, float2 val) { buf[PADI(idx)] = val; };
-            fft_full<-1, LOG2M>(buf, tw, first_load, MODE == MODE_SYNTH, sm_store, false);
+            fft_full<-1, LOG2M>(buf, ptw, make_in(first_load), MODE == MODE_SYNTH, SmemOut{buf}, false);
         }
         whiten_pointwise<LOG2M>(buf, tw, a.weights);
         __syncthreads();
-        {
-            auto sm_load = [&](int idx) { return buf[PADI(idx)]; };
-            fft_full<+1, LOG2M>(buf, tw, sm_load, true, out_store, true);
-        }
+        fft_full<+1, LOG2M>(buf, ptw, SmemIn{buf}, true, make_out(out_store), true);
         __syncthreads();
     }
 }
@@ -392,10 +437,17 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
 template <int MODE>
 static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
     a.tw = plan->tw;
+    a.ptw = plan->ptw;
     const int M = plan->N / 2;
     const size_t smem = (size_t)(M + (M >> 4) + 1) * sizeof(float2);
     const int threads = M / 16;
+    // persistent CTAs: a multiple of the SM count, at most the batch
     int grid = a.batch;
+    {
+        const int per_sm = threads >= 512 ? 1 : (threads >= 256 ? 3 : 6);
+        const int cap = num_sms() * per_sm * 4;      // a few series per CTA slot keeps the tail short
+        if (grid > cap) grid = cap;
+    }
 #define GN_SYNTH_CASE(L2)                                                                                   \
     case L2: {                                                                                              \
         auto kfn = synth_kernel<L2, MODE>;                                                                  \
@@ -535,6 +587,32 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
         cuda_status("gn_fft_plan_create(cudaMemcpy)");
         return GN_ERR_CUDA;
     }
+    // per-pass Stockham twiddles: M = REM * 16^a; radix-16 pass j has sub-transform length pj = REM*16^j
+    {
+        const int M = N / 2;
+        const int rem = 1 << (p->log2M & 3), n16 = p->log2M >> 2;
+        std::vector<float2> t;
+        int pj = rem;
+        for (int j = 0; j < n16; ++j) {
+            if (pj > 1) {
+                for (int r = 1; r < 16; ++r)
+                    for (int k = 0; k < pj; ++k) {
+                        double ang = -2.0 * 3.14159265358979323846264338327950288 * (double)r * (double)k / ((double)pj * 16.0);
+                        t.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+                    }
+            }
+            pj *= 16;
+        }
+        (void)M;
+        if (t.empty()) t.push_back(make_float2(1.f, 0.f));
+        if (cudaMalloc(&p->ptw, sizeof(float2) * t.size()) != cudaSuccess ||
+            cudaMemcpy(p->ptw, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(p->tw);
+            delete p;
+            cuda_status("gn_fft_plan_create(twiddle tables)");
+            return GN_ERR_CUDA;
+        }
+    }
     *out = p;
     return GN_OK;
 }
@@ -542,6 +620,7 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
 extern "C" int gn_fft_plan_destroy(gn_fft_plan* p) {
     if (p == nullptr) return GN_OK;
     cudaFree(p->tw);
+    cudaFree(p->ptw);
     delete p;
     return GN_OK;
 }
