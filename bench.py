@@ -36,56 +36,74 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region (NVML from a thread;
+    `nvidia-smi -lms` block-buffers its stdout into a pipe, so short regions would see no samples)."""
+    BITS = (('hw_slowdown', 0x8), ('sw_power_cap', 0x4), ('sw_thermal_slowdown', 0x20),
+            ('hw_thermal_slowdown', 0x40), ('hw_power_brake', 0x80))
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_s=0.02):
+        self.index, self.period, self.samples, self.h, self.nv = index, period_s, [], None, None
+        self._stop = threading.Event()
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:                                   # honour CUDA_VISIBLE_DEVICES remapping
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()
+            self.samples.clear()
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-            t0 = time.time()
-            while not self.lines and time.time() - t0 < 3.0:     # nvidia-smi takes a moment to start sampling
-                time.sleep(0.01)
-            self.lines.clear()
-        except Exception:
-            self.proc = None
+        except Exception as e:                     # pragma: no cover (no NVML on the CPU container)
+            self.h, self.err = None, repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _sample(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        try:
+            power = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+        except Exception:
+            power = None
+        self.samples.append((mhz, reasons, power))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.h is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: %s' % getattr(self, 'err', '')],
+                    'samples': 0}
+        self._stop.set()
+        self.t.join(timeout=2)
         try:
-            self.proc.wait(timeout=2)
+            self._sample()                         # at least one sample even for a very short region
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for l in self.lines:
-            f = [x.strip() for x in l.split(',')]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+            pass
+        sm = [s[0] for s in self.samples]
+        mask = 0
+        for s in self.samples:
+            mask |= s[1]
+        pw = [s[2] for s in self.samples if s[2] is not None]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(n for n, b in self.BITS if mask & b), 'samples': len(sm),
+                'power_w_max': max(pw) if pw else None}
 
 
 def make_inputs(seed, device):
