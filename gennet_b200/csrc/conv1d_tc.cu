@@ -126,7 +126,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 constexpr int TC_BM = 128;          // rows of an output tile (UMMA M)
 constexpr int TC_BK = 64;           // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 224;     // warps: 0 TMA producer, 1 MMA, 2-5 epilogue, 6 aux (mask) producer
+constexpr int TC_THREADS = 224;     // warps: 0 TMA producer, 1 MMA, 2-5 epilogue, 6 I/O (bulk stores + mask loads)
 constexpr int TC_WG_THREADS = 192;  // wgrad kernel: warps 0 TMA producer, 1 MMA, 2-5 epilogue
 
 struct TcArgs {
@@ -140,22 +140,29 @@ struct TcArgs {
     int m_tiles;                           // tiles of 128 rows per (sample, parity)
 };
 
-template <int BN, int STAGES, bool AUX>
+constexpr int TC_SLAB_COLS = 32;                          // channels per epilogue slab (64-byte rows, SWIZZLE_64B)
+constexpr int TC_SLAB_BYTES = TC_BM * TC_SLAB_COLS * 2;   // 8 KB
+constexpr int TC_RING = 4;                                // slabs in the epilogue ring
+
+template <int BN, int STAGES>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 2 * TC_BM * 128;      // two 128-row x 64-column bf16 staging slabs
-    static constexpr int AUX_BYTES = AUX ? 2 * TC_BM * 128 : 0;   // two slabs of the mask source (dgrad)
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + AUX_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+    static constexpr int RING_BYTES = TC_RING * TC_SLAB_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + RING_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // ------------------------------------------------------------------------------------------------ fwd / dgrad
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles tile = blockIdx.x + i*gridDim.x with
-// n-tile fastest (CTAs running side by side share the activation tile through L2).  Two pipelines:
-//   shared-memory ring  (full/empty mbarriers, STAGES deep)  TMA producer  -> MMA issuer
-//   TMEM accumulator ring (2 x BN fp32 columns)               MMA issuer   -> epilogue warps
-// so the epilogue of tile i (TMEM -> registers -> bias/act/mask -> bf16 -> HBM) overlaps the MMAs of tile i+1.
+// n-tile fastest (CTAs running side by side share the activation tile through L2).  Three pipelines:
+//   shared-memory ring   (full/empty mbarriers, STAGES deep)   TMA producer -> MMA issuer
+//   TMEM accumulator ring (2 x BN fp32 columns)                 MMA issuer   -> epilogue warps
+//   epilogue slab ring   (4 x [128 rows x 32 channels] bf16)    I/O thread  <-> epilogue warps
+// The epilogue of tile i (TMEM -> registers -> bias/act/mask -> bf16 -> slab -> TMA store) overlaps the MMAs of
+// tile i+1.  For dgrad the epilogue threads read the mask source (the conv's own input, same shape as the
+// output: 64 contiguous bytes per thread and slab) straight from global memory, prefetched into L2 one tile
+// ahead and into registers one slab ahead, so its latency never sits on the epilogue's critical path.
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -176,24 +183,42 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int n_nt, int m_tiles
     return c;
 }
 
+// walks the (tile, slab) sequence of one CTA
+template <int BN>
+struct SlabIter {
+    int tile, sl, total, step, n_nt, m_tiles, npar;
+    TileCoord c;
+    __device__ __forceinline__ void init(int first, int total_, int step_, int n_nt_, int m_tiles_, int npar_) {
+        tile = first; sl = 0; total = total_; step = step_; n_nt = n_nt_; m_tiles = m_tiles_; npar = npar_;
+        if (tile < total) c = decode_tile(tile, n_nt, m_tiles, npar, BN);
+    }
+    __device__ __forceinline__ bool valid() const { return tile < total; }
+    __device__ __forceinline__ void next() {
+        if (++sl == BN / TC_SLAB_COLS) {
+            sl = 0;
+            tile += step;
+            if (tile < total) c = decode_tile(tile, n_nt, m_tiles, npar, BN);
+        }
+    }
+};
+
 template <int BN, int STAGES, bool AUX>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1,
                const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1, TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    using S = TcSmem<BN, STAGES, AUX>;
+    using S = TcSmem<BN, STAGES>;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-    uint8_t* epi = tiles + STAGES * S::STAGE_BYTES;            // 1024-byte aligned (stage sizes are multiples of 1 KB)
-    uint8_t* auxs = epi + S::EPI_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(auxs + S::AUX_BYTES);
+    uint8_t* ring = tiles + STAGES * S::STAGE_BYTES;            // 1024-byte aligned (stage sizes are multiples of 1 KB)
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + S::RING_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;      // [2]
-    uint64_t* tmem_empty = tmem_full + 2;      // [2]
-    uint64_t* aux_full = tmem_empty + 2;       // [2]
-    uint64_t* aux_empty = aux_full + 2;        // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 2);
+    uint64_t* tmem_full = empty + STAGES;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint64_t* slab_ready = tmem_empty + 2;         // [TC_RING]  I/O thread -> epilogue: slab free (and mask landed)
+    uint64_t* slab_done = slab_ready + TC_RING;    // [TC_RING]  epilogue -> I/O thread: slab holds the bf16 result
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_done + TC_RING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npar = (a.mode == 1) ? a.s : 1;
@@ -212,8 +237,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);      // one arrival per epilogue warp
-            mbar_init(&aux_full[i], 1);
-            mbar_init(&aux_empty[i], 4);
+        }
+        for (int i = 0; i < TC_RING; ++i) {
+            mbar_init(&slab_ready[i], 1);
+            mbar_init(&slab_done[i], 4);
         }
         fence_barrier_init();
     }
@@ -284,95 +311,122 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
     } else if (warp == 6) {
-        // aux producer: streams the mask source (the conv's own input, same shape as the output) slab by slab
-        if (AUX && lane == 0) {
-            int sc = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
-                const CUtensorMap* xmap = (c.par == 0) ? &mapX0 : &mapX1;
-                for (int sl = 0; sl < BN / 64; ++sl, ++sc) {
-                    const int bi = sc & 1, ph = (sc >> 1) & 1;
-                    mbar_wait(&aux_empty[bi], ph ^ 1);
-                    mbar_expect_tx(&aux_full[bi], TC_BM * 128);
-                    tma_load_3d(auxs + bi * (TC_BM * 128), xmap, &aux_full[bi], c.n0 + sl * 64, c.m0, c.b);
+        // I/O thread: owns every bulk store (bulk groups are per thread) and, for dgrad, the mask loads.
+        // Slab step s uses ring buffer s % 4.  After committing store s, store s-1 has been read out of shared
+        // memory once at most one group is pending, which frees buffer (s-1) % 4 == (s+3) % 4 for slab s+3.
+        if (lane == 0) {
+            SlabIter<BN> ld, st;
+            ld.init(blockIdx.x, total_tiles, gridDim.x, n_nt, a.m_tiles, npar);
+            st = ld;
+            auto prepare = [&](int s_idx) {
+                mbar_arrive(&slab_ready[s_idx & (TC_RING - 1)]);
+                ld.next();
+            };
+            for (int i = 0; i < TC_RING - 1 && ld.valid(); ++i) prepare(i);
+            for (int s = 0; st.valid(); ++s, st.next()) {
+                const int b = s & (TC_RING - 1);
+                mbar_wait(&slab_done[b], (s / TC_RING) & 1);
+                tma_store_3d((st.c.par == 0) ? &mapO0 : &mapO1, ring + b * TC_SLAB_BYTES, st.c.n0 + st.sl * TC_SLAB_COLS,
+                             st.c.m0, st.c.b);
+                tma_store_commit();
+                if (ld.valid()) {
+                    tma_store_wait_read<1>();
+                    prepare(s + TC_RING - 1);
                 }
             }
+            tma_store_wait_read<0>();
         }
     } else {
-        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (rows of the tile).  Each 64-column slab goes
-        // TMEM -> registers -> bias / activation / mask -> bf16 -> swizzled shared-memory slab -> TMA store
-        // (coalesced 128-byte rows; rows past the end of the sample are clipped by the tensor map).
+        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (rows of the tile).  Each 32-column slab goes
+        // TMEM -> registers -> bias / activation / mask -> bf16 -> swizzled slab -> (I/O thread) TMA store;
+        // rows past the end of the sample are clipped by the tensor map.
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int epi_tid = threadIdx.x - 64;
-        int ti_local = 0, slab_ctr = 0;
+        const uint32_t sw = (uint32_t)(row >> 1) & 3u;          // SWIZZLE_64B: 16-byte chunk index XOR address bits 7-8
+        constexpr int NS = BN / TC_SLAB_COLS;
+        // dgrad mask source: row (m0 + row) of parity class par of sample b is position j = (m0 + row) * s + par
+        // of the conv's own input; this thread needs BN consecutive channels of it (n0 ..), 64 bytes per slab
+        auto mask_row = [&](const TileCoord& c) -> const uint8_t* {
+            const int j = (c.m0 + row) * npar + c.par;
+            if (!AUX || j >= a.L) return nullptr;
+            return reinterpret_cast<const uint8_t*>(a.aux + ((size_t)c.b * a.L + j) * a.Cin + c.n0);
+        };
+        auto mask_prefetch_l2 = [&](const uint8_t* p) {
+            if (p != nullptr) {
+#pragma unroll
+                for (int i = 0; i < BN * 2 / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+            }
+        };
+        auto mask_load = [&](uint4 (&m)[4], const uint8_t* p, int sl) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                m[i] = (p != nullptr) ? __ldg(reinterpret_cast<const uint4*>(p + sl * 64) + i) : make_uint4(0, 0, 0, 0);
+        };
+        int ti_local = 0, s = 0;
+        if (AUX && (int)blockIdx.x < total_tiles) mask_prefetch_l2(mask_row(decode_tile(blockIdx.x, n_nt, a.m_tiles, npar, BN)));
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti_local) {
             const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
+            const uint8_t* mrow = mask_row(c);
+            uint4 mk[4];
+            if (AUX) {
+                mask_load(mk, mrow, 0);
+                // pull the next tile's mask rows into L2 while this tile is being processed
+                if (tile + (int)gridDim.x < total_tiles)
+                    mask_prefetch_l2(mask_row(decode_tile(tile + gridDim.x, n_nt, a.m_tiles, npar, BN)));
+            }
             const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
             const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-            const int r = c.m0 + row;            // row index within (sample, parity)
-            (void)r;
-            const CUtensorMap* omap = (c.par == 0) ? &mapO0 : &mapO1;
 #pragma unroll 1
-            for (int sl = 0; sl < BN / 64; ++sl, ++slab_ctr) {
-                uint32_t v[64];
-                {
-                    uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-                    uint32_t (&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-                    tmem_ld32(tacc + (uint32_t)(sl * 64), v0);
-                    tmem_ld32(tacc + (uint32_t)(sl * 64 + 32), v1);
-                }
-                if (sl == BN / 64 - 1) {
+            for (int sl = 0; sl < NS; ++sl, ++s) {
+                uint4 mk_next[4];
+                if (AUX && sl + 1 < NS) mask_load(mk_next, mrow, sl + 1);
+                uint32_t v[32];
+                tmem_ld32(tacc + (uint32_t)(sl * TC_SLAB_COLS), v);
+                if (sl == NS - 1) {
                     // all of this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                float f[64];
+                float f[32];
 #pragma unroll
-                for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(v[i]);
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                const int b = s & (TC_RING - 1);
+                uint8_t* srow = ring + b * TC_SLAB_BYTES + row * 64;
                 if (a.mode == 0) {
                     if (a.bias != nullptr) {
-                        const float4* bp = reinterpret_cast<const float4*>(a.bias + c.n0 + sl * 64);
+                        const float4* bp = reinterpret_cast<const float4*>(a.bias + c.n0 + sl * TC_SLAB_COLS);
 #pragma unroll
-                        for (int g4 = 0; g4 < 16; ++g4) {
+                        for (int g4 = 0; g4 < 8; ++g4) {
                             float4 bv = __ldg(&bp[g4]);
                             f[4 * g4 + 0] += bv.x; f[4 * g4 + 1] += bv.y; f[4 * g4 + 2] += bv.z; f[4 * g4 + 3] += bv.w;
                         }
                     }
-                    if (a.act == GN_ACT_RELU) {
+                    act_dispatch(a.act, [&](auto tag) {
 #pragma unroll
-                        for (int i = 0; i < 64; ++i) f[i] = fmaxf(f[i], 0.f);
-                    } else if (a.act != GN_ACT_NONE) {
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) f[i] = act_fwd(f[i], a.act, a.act_param);
-                    }
+                        for (int i = 0; i < 32; ++i) f[i] = act_fwd_t<decltype(tag)::kind>(f[i], a.act_param);
+                    });
                 } else if (AUX) {
-                    const int bi = slab_ctr & 1, ph = (slab_ctr >> 1) & 1;
-                    mbar_wait(&aux_full[bi], ph);
-                    const uint8_t* xs = auxs + bi * (TC_BM * 128) + row * 128;
+                    act_dispatch(a.act, [&](auto tag) {
 #pragma unroll
-                    for (int g8 = 0; g8 < 8; ++g8) {
-                        uint4 pk = *reinterpret_cast<const uint4*>(xs + ((g8 ^ (row & 7)) << 4));
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&mk[g8]);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float2 y = __bfloat1622float2(h[e]);
-                            f[g8 * 8 + 2 * e] *= act_bwd_from_y(y.x, a.act, a.act_param);
-                            f[g8 * 8 + 2 * e + 1] *= act_bwd_from_y(y.y, a.act, a.act_param);
+                            for (int e = 0; e < 4; ++e) {
+                                float2 y = __bfloat1622float2(h[e]);
+                                f[g8 * 8 + 2 * e] *= act_bwd_t<decltype(tag)::kind>(y.x, a.act_param);
+                                f[g8 * 8 + 2 * e + 1] *= act_bwd_t<decltype(tag)::kind>(y.y, a.act_param);
+                            }
                         }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&aux_empty[bi]);
-                }
-                uint8_t* slab = epi + (slab_ctr & 1) * (TC_BM * 128);
-                // the TMA store that last read this slab (two slabs ago) must have finished reading it
-                if (epi_tid == 0) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
+                    });
 #pragma unroll
-                for (int g8 = 0; g8 < 8; ++g8) {
+                    for (int i = 0; i < 4; ++i) mk[i] = mk_next[i];
+                }
+                mbar_wait(&slab_ready[b], (s / TC_RING) & 1);
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
                     __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g8 * 8 + 0], f[g8 * 8 + 1]);
                     __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g8 * 8 + 2], f[g8 * 8 + 3]);
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g8 * 8 + 4], f[g8 * 8 + 5]);
@@ -382,18 +436,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     pk.y = *reinterpret_cast<uint32_t*>(&h1);
                     pk.z = *reinterpret_cast<uint32_t*>(&h2);
                     pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                    // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
-                    *reinterpret_cast<uint4*>(slab + row * 128 + ((g8 ^ (row & 7)) << 4)) = pk;
+                    *reinterpret_cast<uint4*>(srow + (((uint32_t)g8 ^ sw) << 4)) = pk;
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (epi_tid == 0) {
-                    tma_store_3d(omap, slab, c.n0 + sl * 64, c.m0, c.b);
-                    tma_store_commit();
-                }
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&slab_done[b]);
             }
         }
-        if (epi_tid == 0) tma_store_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -405,16 +454,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[t, ci, co] (fp32, atomically accumulated; caller zeroes) = sum over (b, l) of X[b, l*s+t-p, ci] * dY[b, l, co]
-// grid: x = tap, y = (ci tile of 128) * n_co_tiles + (co tile of BN), z = split over (b, l-block of 64)
+// Persistent split-K: a work unit is (K chunk, output tile) with the output tile = (tap, 128 x BN block of
+// (ci, co)) varying fastest, so the CTAs running at any moment cover every output tile of the same one or two
+// K chunks and the activations / gradients of that chunk are read from HBM once and shared through L2.
+// The number of K chunks is chosen on the host so that the unit count fills whole waves of the grid.
+// TMEM is double buffered: the fp32 red.add epilogue of unit i overlaps the MMAs of unit i+1.
 // SWAP (Cin == 64): the 128-row operand is dY (co) and the BN(=64)-column operand is X (ci).
 struct TcWgradArgs {
     int B, L, Lout, Cin, Cout, k, s, p;
     int lblocks;        // ceil(Lout / 64)
     int iters_total;    // B * lblocks
-    int iters_per_split;
+    int iters_per_chunk;
+    int n_chunks;
     int n_tiles_n;      // number of N tiles
+    int out_tiles;      // k * m_tiles * n_tiles_n
     float* dw;          // (k, Cin, Cout) fp32
 };
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct WgUnit {
+    int tap, m0, n0, it0, niter;
+};
+template <int BN>
+__device__ __forceinline__ WgUnit decode_wg_unit(int u, const TcWgradArgs& a) {
+    WgUnit w;
+    const int kc = u / a.out_tiles, t = u - kc * a.out_tiles;
+    w.tap = t % a.k;
+    const int r = t / a.k;
+    const int mt = r / a.n_tiles_n, nt = r - mt * a.n_tiles_n;
+    w.m0 = mt * TC_BM;
+    w.n0 = nt * BN;
+    w.it0 = kc * a.iters_per_chunk;
+    w.niter = min(a.iters_total - w.it0, a.iters_per_chunk);
+    return w;
+}
 
 template <int BN, int STAGES, bool SWAP>
 __global__ void __launch_bounds__(TC_WG_THREADS)
@@ -428,16 +504,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tap = blockIdx.x;
-    const int mt = blockIdx.y / a.n_tiles_n, nt = blockIdx.y - mt * a.n_tiles_n;
-    const int m0 = mt * TC_BM, n0 = nt * BN;       // m: 128-row operand channel offset, n: BN-col operand offset
-    const int it0 = blockIdx.z * a.iters_per_split;
-    const int it1 = min(a.iters_total, it0 + a.iters_per_split);
-    const int niter = max(it1 - it0, 0);
+    const int n_units = a.out_tiles * a.n_chunks;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapX);
@@ -446,10 +518,13 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -457,66 +532,97 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < niter; ++i) {
-                const int st = i % STAGES, ph = (i / STAGES) & 1;
-                mbar_wait(&empty[st], ph ^ 1);
-                const int it = it0 + i;
-                const int bb = it / a.lblocks, lb = it - bb * a.lblocks;
-                const int l0 = lb * 64;
-                uint8_t* sA = tiles + st * STAGE_BYTES;
-                uint8_t* sB = sA + A_BYTES;
-                mbar_expect_tx(&full[st], STAGE_BYTES);
-                const int xrow = l0 * a.s + tap - a.p;     // X position of output position l0 for this tap
-                // 128-row operand: two 64-channel blocks; BN-column operand: BN/64 blocks
-                if (!SWAP) {
-                    tma_load_3d(sA, &mapX, &full[st], m0, xrow, bb);
-                    tma_load_3d(sA + 8192, &mapX, &full[st], m0 + 64, xrow, bb);
+            int g = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const WgUnit w = decode_wg_unit<BN>(u, a);
+                int bb = w.it0 / a.lblocks, lb = w.it0 - bb * a.lblocks;
+                for (int i = 0; i < w.niter; ++i, ++g) {
+                    const int st = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&empty[st], ph ^ 1);
+                    const int l0 = lb * 64;
+                    uint8_t* sA = tiles + st * STAGE_BYTES;
+                    uint8_t* sB = sA + A_BYTES;
+                    mbar_expect_tx(&full[st], STAGE_BYTES);
+                    const int xrow = l0 * a.s + w.tap - a.p;     // X position of output position l0 for this tap
+                    // 128-row operand: two 64-channel blocks; BN-column operand: BN/64 blocks
+                    if (!SWAP) {
+                        tma_load_3d(sA, &mapX, &full[st], w.m0, xrow, bb);
+                        tma_load_3d(sA + 8192, &mapX, &full[st], w.m0 + 64, xrow, bb);
 #pragma unroll
-                    for (int h = 0; h < BN / 64; ++h) tma_load_3d(sB + h * 8192, &mapDY, &full[st], n0 + h * 64, l0, bb);
-                } else {
-                    tma_load_3d(sA, &mapDY, &full[st], m0, l0, bb);
-                    tma_load_3d(sA + 8192, &mapDY, &full[st], m0 + 64, l0, bb);
+                        for (int h = 0; h < BN / 64; ++h)
+                            tma_load_3d(sB + h * 8192, &mapDY, &full[st], w.n0 + h * 64, l0, bb);
+                    } else {
+                        tma_load_3d(sA, &mapDY, &full[st], w.m0, l0, bb);
+                        tma_load_3d(sA + 8192, &mapDY, &full[st], w.m0 + 64, l0, bb);
 #pragma unroll
-                    for (int h = 0; h < BN / 64; ++h) tma_load_3d(sB + h * 8192, &mapX, &full[st], n0 + h * 64, xrow, bb);
+                        for (int h = 0; h < BN / 64; ++h)
+                            tma_load_3d(sB + h * 8192, &mapX, &full[st], w.n0 + h * 64, xrow, bb);
+                    }
+                    if (++lb == a.lblocks) { lb = 0; ++bb; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(TC_BM, BN, 1, 1);     // both operands MN-major
-            for (int i = 0; i < niter; ++i) {
-                const int st = i % STAGES, ph = (i / STAGES) & 1;
-                mbar_wait(&full[st], ph);
+            int g = 0, ul = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+                const WgUnit w = decode_wg_unit<BN>(u, a);
+                const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
                 tc_fence_after();
-                const uint32_t sA = base + st * STAGE_BYTES;
-                const uint32_t sB = sA + A_BYTES;
+                const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+                for (int i = 0; i < w.niter; ++i, ++g) {
+                    const int st = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t sA = base + st * STAGE_BYTES;
+                    const uint32_t sB = sA + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < 64 / 16; ++k) {
-                    // MN-major SW128: 64-element MN blocks LBO = 8192 B apart, 8-row K groups SBO = 1024 B apart;
-                    // 16 K rows per instruction = 2048 B
-                    uint64_t da = make_desc(sA + k * 2048, 8192, 1024);
-                    uint64_t db = make_desc(sB + k * 2048, 8192, 1024);
-                    tc_mma_bf16(tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 64 / 16; ++k) {
+                        // MN-major SW128: 64-element MN blocks LBO = 8192 B apart, 8-row K groups SBO = 1024 B apart;
+                        // 16 K rows per instruction = 2048 B
+                        uint64_t da = make_desc(sA + k * 2048, 8192, 1024);
+                        uint64_t db = make_desc(sB + k * 2048, 8192, 1024);
+                        tc_mma_bf16(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[st]);
                 }
-                tc_commit(&empty[st]);
+                tc_commit(&tmem_full[acc]);
             }
-            tc_commit(tmem_full);
         }
-    } else if (niter > 0) {
+    } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
+        int ul = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+            const WgUnit w = decode_wg_unit<BN>(u, a);
+            const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tacc + (uint32_t)c0, v);
+                if (c0 + 32 >= BN) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!SWAP) {
+                    // thread = input channel, 32 consecutive output channels: eight 16-byte vector reductions
+                    float* dst = a.dw + ((size_t)w.tap * a.Cin + (w.m0 + row)) * a.Cout + w.n0 + c0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float f = __uint_as_float(v[i]);
-                int ci, co;
-                if (!SWAP) { ci = m0 + row; co = n0 + c0 + i; } else { co = m0 + row; ci = n0 + c0 + i; }
-                atomicAdd(&a.dw[((size_t)tap * a.Cin + ci) * a.Cout + co], f);
+                    for (int i = 0; i < 32; i += 4)
+                        red_add_v4(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                   __uint_as_float(v[i + 3]));
+                } else {
+                    // thread = output channel (consecutive across the warp), columns = input channels
+                    float* dst = a.dw + ((size_t)w.tap * a.Cin + (w.n0 + c0)) * a.Cout + w.m0 + row;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * a.Cout, __uint_as_float(v[i]));
+                }
             }
         }
     }
@@ -524,7 +630,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem);
+        tmem_dealloc<2 * BN>(tmem);
     }
 }
 
@@ -613,7 +719,7 @@ static EncodeTiledFn encode_fn() {
 // 3-D bf16 tensor map: dims (d0 contiguous, d1, d2), strides in elements for d1, d2; box (b0, b1, 1); traversal
 // stride es1 along d1 (box extent b1*es1 in global coordinates -> b1 rows in shared memory)
 static int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t st1, uint64_t st2,
-                     uint32_t b0, uint32_t b1, uint32_t es1) {
+                     uint32_t b0, uint32_t b1, uint32_t es1, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return fail(GN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s", "");
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -621,7 +727,7 @@ static int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
     cuuint32_t box[3] = {b0, b1 * es1, 1};
     cuuint32_t estr[3] = {1, es1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(GN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%s code %lld)", "", (long long)r);
     return GN_OK;
@@ -632,7 +738,7 @@ static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CU
                           const CUtensorMap& mX0, const CUtensorMap& mX1, const TcArgs& a, long long total_tiles,
                           cudaStream_t st) {
     auto kfn = conv_tc_kernel<BN, STAGES, AUX>;
-    constexpr int smem = TcSmem<BN, STAGES, AUX>::TOTAL;
+    constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
     static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr_set = false;
     if (!attr_set) {
@@ -652,17 +758,18 @@ static int dispatch_conv_tc(int BN, bool aux, const CUtensorMap& mA, const CUten
         if (BN == 128) return launch_conv_tc<128, 6, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
         return launch_conv_tc<64, 8, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
     }
-    if (BN == 256) return launch_conv_tc<256, 3, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
-    if (BN == 128) return launch_conv_tc<128, 5, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
-    return launch_conv_tc<64, 6, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+    if (BN == 256) return launch_conv_tc<256, 4, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+    if (BN == 128) return launch_conv_tc<128, 6, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+    return launch_conv_tc<64, 8, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
 }
 static int pick_bn(int C) { return (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : 64); }
 
 template <int BN, int STAGES, bool SWAP>
-static int launch_wgrad_tc(const CUtensorMap& mX, const CUtensorMap& mDY, const TcWgradArgs& a, dim3 grid,
+static int launch_wgrad_tc(const CUtensorMap& mX, const CUtensorMap& mDY, const TcWgradArgs& a, int grid,
                            cudaStream_t st) {
     auto kfn = conv_tc_wgrad_kernel<BN, STAGES, SWAP>;
     constexpr int smem = STAGES * (TC_BM * 128 + BN * 128) + 1024 + 256;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -670,6 +777,26 @@ static int launch_wgrad_tc(const CUtensorMap& mX, const CUtensorMap& mDY, const 
     }
     kfn<<<grid, TC_WG_THREADS, smem, st>>>(mX, mDY, a);
     return cuda_status("conv_tc_wgrad_kernel");
+}
+
+// number of K chunks of the persistent split-K wgrad: minimise  waves * (iterations per chunk + fixed cost per unit)
+static int pick_wgrad_chunks(int out_tiles, int iters_total, int grid) {
+    const int ovh = 6;                                   // pipeline refill + epilogue hand-over, in K iterations
+    int lo = (iters_total + 511) / 512, hi = (iters_total + 23) / 24;
+    if (lo < 1) lo = 1;
+    if (hi < lo) hi = lo;
+    if (hi > 4096) hi = 4096;
+    long long best_cost = -1;
+    int best = lo;
+    for (int nk = lo; nk <= hi; ++nk) {
+        const int ipc = (iters_total + nk - 1) / nk;
+        const int nk_eff = (iters_total + ipc - 1) / ipc;
+        const long long units = (long long)out_tiles * nk_eff;
+        const long long waves = (units + grid - 1) / grid;
+        const long long cost = waves * (ipc + ovh);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nk_eff; }
+    }
+    return best;
 }
 
 static int check_tc_geom(int B, int L, int Cin, int Lout, int Cout, int k, int s, int p) {
@@ -725,9 +852,9 @@ extern "C" int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bi
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
     a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = (__nv_bfloat16*)y;
     a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
-    // output: Y viewed as (Cout, Lout, B), 64-channel x 128-row store boxes
+    // output: Y viewed as (Cout, Lout, B), 32-channel x 128-row store boxes (SWIZZLE_64B slabs)
     CUtensorMap mO;
-    rc = make_map3(&mO, y, Cout, Lout, B, Cout, (uint64_t)Lout * Cout, 64, TC_BM, 1);
+    rc = make_map3(&mO, y, Cout, Lout, B, Cout, (uint64_t)Lout * Cout, TC_SLAB_COLS, TC_BM, 1, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc != GN_OK) return rc;
     return dispatch_conv_tc(BN, false, mA, mB, mO, mO, mO, mO, a, (long long)B * a.m_tiles * (Cout / BN), as_stream(stream));
 }
@@ -759,11 +886,11 @@ extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* 
         const int rr = (r < stride) ? r : 0;
         const int rows_r = (L - rr + stride - 1) / stride;
         rc = make_map3(&mO[r], (const __nv_bfloat16*)dx + (size_t)rr * Cin, Cin, rows_r, B, (uint64_t)stride * Cin,
-                       (uint64_t)L * Cin, 64, TC_BM, 1);
+                       (uint64_t)L * Cin, TC_SLAB_COLS, TC_BM, 1, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != GN_OK) return rc;
         // the mask source has the shape of dx: same parity views
         rc = make_map3(&mX[r], (const __nv_bfloat16*)(aux ? x_in : dx) + (size_t)rr * Cin, Cin, rows_r, B,
-                       (uint64_t)stride * Cin, (uint64_t)L * Cin, 64, TC_BM, 1);
+                       (uint64_t)stride * Cin, (uint64_t)L * Cin, TC_SLAB_COLS, TC_BM, 1, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != GN_OK) return rc;
     }
     return dispatch_conv_tc(BN, aux, mA, mB, mO[0], mO[1], mX[0], mX[1], a,
@@ -793,17 +920,17 @@ extern "C" int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, fl
     int m_tiles, BN;
     if (!swap) { m_tiles = Cin / 128; BN = pick_bn(Cout); a.n_tiles_n = Cout / BN; }
     else { m_tiles = Cout / 128; BN = 64; a.n_tiles_n = 1; }
-    const int out_tiles = k * m_tiles * a.n_tiles_n;
-    int splits = (2 * num_sms() + out_tiles - 1) / out_tiles;
-    if (splits < 1) splits = 1;
-    if (splits > a.iters_total) splits = a.iters_total;
-    a.iters_per_split = (a.iters_total + splits - 1) / splits;
-    splits = (a.iters_total + a.iters_per_split - 1) / a.iters_per_split;
-    dim3 grid(k, m_tiles * a.n_tiles_n, splits);
-    if (swap) rc = launch_wgrad_tc<64, 4, true>(mX, mDY, a, grid, st);
+    a.out_tiles = k * m_tiles * a.n_tiles_n;
+    const int nsm = num_sms();
+    int nk = pick_wgrad_chunks(a.out_tiles, a.iters_total, nsm);
+    a.iters_per_chunk = (a.iters_total + nk - 1) / nk;
+    a.n_chunks = (a.iters_total + a.iters_per_chunk - 1) / a.iters_per_chunk;
+    const long long units = (long long)a.out_tiles * a.n_chunks;
+    const int grid = (int)(units < nsm ? units : nsm);
+    if (swap) rc = launch_wgrad_tc<64, 8, true>(mX, mDY, a, grid, st);
     else if (BN == 256) rc = launch_wgrad_tc<256, 4, false>(mX, mDY, a, grid, st);
     else if (BN == 128) rc = launch_wgrad_tc<128, 6, false>(mX, mDY, a, grid, st);
-    else rc = launch_wgrad_tc<64, 4, false>(mX, mDY, a, grid, st);
+    else rc = launch_wgrad_tc<64, 8, false>(mX, mDY, a, grid, st);
     if (rc != GN_OK) return rc;
     if (db != nullptr) {
         cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);

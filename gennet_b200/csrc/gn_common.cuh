@@ -74,27 +74,57 @@ __device__ __forceinline__ T block_sum(T v, T* smem32) {
     return r;
 }
 
-// activation codes shared by fused epilogues and the elementwise kernels
-__device__ __forceinline__ float act_fwd(float x, int kind, float a) {
-    switch (kind) {
-        case GN_ACT_RELU: return x > 0.f ? x : 0.f;
-        case GN_ACT_TANH: return tanhf(x);
-        case GN_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
-        case GN_ACT_LEAKY: return x >= 0.f ? x : a * x;
-        case GN_ACT_RELU_MAX: return fminf(fmaxf(x, 0.f), a);
-        default: return x;
-    }
+// activation codes shared by fused epilogues and the elementwise kernels.  The *_t forms take the code at
+// compile time; act_dispatch() turns a run-time code into one uniform branch OUTSIDE the element loops (a
+// per-element `switch` compiles to an indirect branch per element, which serialises a fused epilogue).
+template <int KIND>
+__device__ __forceinline__ float act_fwd_t(float x, float a) {
+    if (KIND == GN_ACT_RELU) return x > 0.f ? x : 0.f;
+    if (KIND == GN_ACT_TANH) return tanhf(x);
+    if (KIND == GN_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+    if (KIND == GN_ACT_LEAKY) return x >= 0.f ? x : a * x;
+    if (KIND == GN_ACT_RELU_MAX) return fminf(fmaxf(x, 0.f), a);
+    return x;
 }
 // derivative expressed through the OUTPUT y (all supported activations allow it)
+template <int KIND>
+__device__ __forceinline__ float act_bwd_t(float y, float a) {
+    if (KIND == GN_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+    if (KIND == GN_ACT_TANH) return 1.f - y * y;
+    if (KIND == GN_ACT_SIGMOID) return y * (1.f - y);
+    if (KIND == GN_ACT_LEAKY) return y >= 0.f ? 1.f : a;
+    if (KIND == GN_ACT_RELU_MAX) return (y > 0.f && y < a) ? 1.f : 0.f;
+    return 1.f;
+}
+template <int K>
+struct ActTag {
+    static constexpr int kind = K;
+};
+template <typename F>
+__device__ __forceinline__ void act_dispatch(int kind, F&& f) {
+    if (kind == GN_ACT_RELU) f(ActTag<GN_ACT_RELU>());
+    else if (kind == GN_ACT_TANH) f(ActTag<GN_ACT_TANH>());
+    else if (kind == GN_ACT_SIGMOID) f(ActTag<GN_ACT_SIGMOID>());
+    else if (kind == GN_ACT_LEAKY) f(ActTag<GN_ACT_LEAKY>());
+    else if (kind == GN_ACT_RELU_MAX) f(ActTag<GN_ACT_RELU_MAX>());
+    else f(ActTag<GN_ACT_NONE>());
+}
+// run-time code, one element (compare chain, no jump table); prefer act_dispatch around a loop
+__device__ __forceinline__ float act_fwd(float x, int kind, float a) {
+    if (kind == GN_ACT_RELU) return act_fwd_t<GN_ACT_RELU>(x, a);
+    if (kind == GN_ACT_TANH) return act_fwd_t<GN_ACT_TANH>(x, a);
+    if (kind == GN_ACT_SIGMOID) return act_fwd_t<GN_ACT_SIGMOID>(x, a);
+    if (kind == GN_ACT_LEAKY) return act_fwd_t<GN_ACT_LEAKY>(x, a);
+    if (kind == GN_ACT_RELU_MAX) return act_fwd_t<GN_ACT_RELU_MAX>(x, a);
+    return x;
+}
 __device__ __forceinline__ float act_bwd_from_y(float y, int kind, float a) {
-    switch (kind) {
-        case GN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-        case GN_ACT_TANH: return 1.f - y * y;
-        case GN_ACT_SIGMOID: return y * (1.f - y);
-        case GN_ACT_LEAKY: return y >= 0.f ? 1.f : a;
-        case GN_ACT_RELU_MAX: return (y > 0.f && y < a) ? 1.f : 0.f;
-        default: return 1.f;
-    }
+    if (kind == GN_ACT_RELU) return act_bwd_t<GN_ACT_RELU>(y, a);
+    if (kind == GN_ACT_TANH) return act_bwd_t<GN_ACT_TANH>(y, a);
+    if (kind == GN_ACT_SIGMOID) return act_bwd_t<GN_ACT_SIGMOID>(y, a);
+    if (kind == GN_ACT_LEAKY) return act_bwd_t<GN_ACT_LEAKY>(y, a);
+    if (kind == GN_ACT_RELU_MAX) return act_bwd_t<GN_ACT_RELU_MAX>(y, a);
+    return 1.f;
 }
 
 }  // namespace gn
