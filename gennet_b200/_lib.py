@@ -38,12 +38,12 @@ _SIGS = {
     'gn_cast_f32_to_bf16': [c_p, c_p, c_ll, c_p],
     'gn_cast_bf16_to_f32': [c_p, c_p, c_ll, c_p],
     'gn_conv1d_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
-    'gn_conv1d_dgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_conv1d_dgrad_bf16': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_smallcin_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_dense_small_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
-    'gn_dense_small_dgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_dense_small_dgrad_bf16': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_dense_small_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_act_bwd_bf16': [c_p, c_p, c_p, c_ll, c_i, c_f, c_p],
     'gn_conv2d_w2_pack_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],

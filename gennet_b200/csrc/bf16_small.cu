@@ -178,28 +178,35 @@ __global__ void __launch_bounds__(512) dense_small_fwd_bf16_kernel(const __nv_bf
 }
 
 // dgrad: dx[m,k] (bf16) = act'(x[m,k]) * sum_j dy[m,j] w[k,j]   (x = the layer's own input, post-activation)
-template <int NS>
+// thread = 8 consecutive features (its 8*NS weights stay in registers) x a slice of the rows; optionally the
+// per-channel sum of dx (feature k belongs to channel k % C: the flattened (L, C) output of a convolution), which
+// is the bias gradient of that convolution, accumulated with one atomic per thread and channel.
+template <int NS, int KIND>
 __global__ void __launch_bounds__(256) dense_small_dgrad_bf16_kernel(const float* __restrict__ dy,
                                                                      const float* __restrict__ w,
                                                                      const __nv_bfloat16* __restrict__ xin,
                                                                      __nv_bfloat16* __restrict__ dx, int M, int K,
-                                                                     int in_act, float ap) {
-    const long long total = (long long)M * (K / 8);
-    const int K8 = K / 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int m = (int)(i / K8), c = (int)(i - (long long)m * K8);
+                                                                     int m_per_split, float ap,
+                                                                     float* __restrict__ colsum, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;   // chunk of 8 features
+    const bool live = c < K / 8;
+    const int mb = blockIdx.y * m_per_split, me = live ? min(M, mb + m_per_split) : mb;
+    float wv[8 * NS];
+    const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(live ? c : 0) * 8 * NS);
+#pragma unroll
+    for (int q4 = 0; q4 < 2 * NS; ++q4) {
+        float4 t4 = __ldg(&wp[q4]);
+        wv[4 * q4] = t4.x; wv[4 * q4 + 1] = t4.y; wv[4 * q4 + 2] = t4.z; wv[4 * q4 + 3] = t4.w;
+    }
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+#pragma unroll 4
+    for (int m = mb; m < me; ++m) {
         float g[NS];
 #pragma unroll
         for (int j = 0; j < NS; ++j) g[j] = __ldg(&dy[(size_t)m * NS + j]);
         float o[8];
-        float wv[8 * NS];
-        const float4* wp = reinterpret_cast<const float4*>(w + (size_t)c * 8 * NS);
-#pragma unroll
-        for (int q4 = 0; q4 < 2 * NS; ++q4) {
-            float4 t4 = __ldg(&wp[q4]);
-            wv[4 * q4] = t4.x; wv[4 * q4 + 1] = t4.y; wv[4 * q4 + 2] = t4.z; wv[4 * q4 + 3] = t4.w;
-        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float sacc = 0.f;
@@ -207,20 +214,46 @@ __global__ void __launch_bounds__(256) dense_small_dgrad_bf16_kernel(const float
             for (int j = 0; j < NS; ++j) sacc = fmaf(g[j], wv[e * NS + j], sacc);
             o[e] = sacc;
         }
-        if (xin != nullptr && in_act != GN_ACT_NONE) {
+        if (KIND != GN_ACT_NONE) {
             uint4 pk = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)m * K) + c);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float2 v = __bfloat1622float2(h[e]);
-                o[2 * e] *= act_bwd_from_y(v.x, in_act, ap);
-                o[2 * e + 1] *= act_bwd_from_y(v.y, in_act, ap);
+                o[2 * e] *= act_bwd_t<KIND>(v.x, ap);
+                o[2 * e + 1] *= act_bwd_t<KIND>(v.y, ap);
             }
         }
         __nv_bfloat162 h2[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+        for (int e = 0; e < 4; ++e) {
+            h2[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+            float2 r = __bfloat1622float2(h2[e]);      // the sum is over the values as stored
+            cs[2 * e] += r.x;
+            cs[2 * e + 1] += r.y;
+        }
         *(reinterpret_cast<uint4*>(dx + (size_t)m * K) + c) = *reinterpret_cast<uint4*>(h2);
+    }
+    if (colsum != nullptr) {
+        // same-address atomics serialise in L2 (~tens of ns each), so fold inside the block first: the block's
+        // 2048 consecutive features wrap around the C channels 2048/C times
+        __shared__ float red[2048];
+        const bool fold = (2048 % C) == 0;       // block-uniform
+        if (fold) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = (c < K / 8) ? cs[e] : 0.f;
+            __syncthreads();
+            const int f0 = blockIdx.x * 2048;    // first feature of the block; f0 % C == 0
+            for (int ch = threadIdx.x; ch < C; ch += 256) {
+                float t = 0.f;
+                for (int f = ch; f < 2048; f += C) t += red[f];
+                if (f0 + ch < K) atomicAdd(&colsum[ch], t);
+            }
+        } else if (c < K / 8) {
+            const int ch = (c * 8) % C;          // C % 8 == 0: the 8 features of a chunk are 8 consecutive channels
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&colsum[ch + e], cs[e]);
+        }
     }
 }
 
@@ -340,21 +373,48 @@ extern "C" int gn_dense_small_fwd_bf16(const void* x, const float* w, const floa
     return cuda_status("dense_small_fwd_bf16_kernel");
 }
 
-extern "C" int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, int M, int K, int N,
-                                         int in_act, float in_act_param, void* stream) {
+template <int NS>
+static void launch_dense_small_dgrad(dim3 grid, cudaStream_t st, const float* dy, const float* w, const __nv_bfloat16* xi,
+                                     __nv_bfloat16* d, int M, int K, int per, int in_act, float ap, float* colsum, int C) {
+    if (xi == nullptr) in_act = GN_ACT_NONE;
+#define GN_DSD(KIND) dense_small_dgrad_bf16_kernel<NS, KIND><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, per, ap, colsum, C)
+    switch (in_act) {
+        case GN_ACT_RELU: GN_DSD(GN_ACT_RELU); break;
+        case GN_ACT_TANH: GN_DSD(GN_ACT_TANH); break;
+        case GN_ACT_SIGMOID: GN_DSD(GN_ACT_SIGMOID); break;
+        case GN_ACT_LEAKY: GN_DSD(GN_ACT_LEAKY); break;
+        case GN_ACT_RELU_MAX: GN_DSD(GN_ACT_RELU_MAX); break;
+        default: GN_DSD(GN_ACT_NONE); break;
+    }
+#undef GN_DSD
+}
+
+extern "C" int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, float* dx_colsum,
+                                         int colsum_channels, int M, int K, int N, int in_act, float in_act_param,
+                                         void* stream) {
     GN_REQUIRE(dy && w && dx, "null pointer");
     GN_REQUIRE(M >= 0 && K > 0 && N >= 1 && N <= 4 && K % 8 == 0, "needs 1 <= N <= 4 and K % 8 == 0");
-    if (M == 0) return GN_OK;
+    GN_REQUIRE(dx_colsum == nullptr || (colsum_channels > 0 && colsum_channels % 8 == 0 && K % colsum_channels == 0),
+               "column sums need channels % 8 == 0 and K % channels == 0");
     cudaStream_t st = as_stream(stream);
-    long long total = (long long)M * (K / 8);
-    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    if (dx_colsum != nullptr) cudaMemsetAsync(dx_colsum, 0, sizeof(float) * (size_t)colsum_channels, st);
+    if (M == 0) return GN_OK;
+    const int chunks = K / 8;
+    const int bx = (chunks + 255) / 256;
+    int splits = (int)((3LL * num_sms() + bx - 1) / bx);      // ~3 blocks per SM keeps the atomic count low
+    if (splits > M) splits = M;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    int per = (M + splits - 1) / splits;
+    splits = (M + per - 1) / per;
+    dim3 grid(bx, splits);
     const __nv_bfloat16* xi = (const __nv_bfloat16*)x_in;
     __nv_bfloat16* d = (__nv_bfloat16*)dx;
     switch (N) {
-        case 1: dense_small_dgrad_bf16_kernel<1><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
-        case 2: dense_small_dgrad_bf16_kernel<2><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
-        case 3: dense_small_dgrad_bf16_kernel<3><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
-        default: dense_small_dgrad_bf16_kernel<4><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, in_act, in_act_param); break;
+        case 1: launch_dense_small_dgrad<1>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
+        case 2: launch_dense_small_dgrad<2>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
+        case 3: launch_dense_small_dgrad<3>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
+        default: launch_dense_small_dgrad<4>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
     }
     return cuda_status("dense_small_dgrad_bf16_kernel");
 }

@@ -126,7 +126,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 constexpr int TC_BM = 128;          // rows of an output tile (UMMA M)
 constexpr int TC_BK = 64;           // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 224;     // warps: 0 TMA producer, 1 MMA, 2-5 epilogue, 6 I/O (bulk stores + mask loads)
+constexpr int TC_THREADS = 256;     // warps: 0 TMA producer, 1 MMA, 2-5 epilogue, 6 I/O (bulk stores), 7 column sums
 constexpr int TC_WG_THREADS = 192;  // wgrad kernel: warps 0 TMA producer, 1 MMA, 2-5 epilogue
 
 struct TcArgs {
@@ -137,6 +137,8 @@ struct TcArgs {
     const float* bias;                     // fwd
     const __nv_bfloat16* aux;              // dgrad: the conv's own input X (post-activation of the previous layer) or null
     __nv_bfloat16* out;                    // fwd: Y (B,Lout,Cout); dgrad: dX (B,L,Cin)
+    float* colsum;                         // dgrad: per-channel sum of dX over (b, l) (= bias gradient of the layer that
+                                           // produced x_in), accumulated with atomics; null = not wanted
     int m_tiles;                           // tiles of 128 rows per (sample, parity)
 };
 
@@ -205,8 +207,7 @@ struct SlabIter {
 template <int BN, int STAGES, bool AUX>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1,
-               const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1, TcArgs a) {
+               const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1, TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     using S = TcSmem<BN, STAGES>;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -218,7 +219,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* slab_ready = tmem_empty + 2;         // [TC_RING]  I/O thread -> epilogue: slab free (and mask landed)
     uint64_t* slab_done = slab_ready + TC_RING;    // [TC_RING]  epilogue -> I/O thread: slab holds the bf16 result
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_done + TC_RING);
+    uint64_t* slab_summed = slab_done + TC_RING;   // [TC_RING]  column-sum warp -> I/O thread: slab has been read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_summed + TC_RING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npar = (a.mode == 1) ? a.s : 1;
@@ -241,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < TC_RING; ++i) {
             mbar_init(&slab_ready[i], 1);
             mbar_init(&slab_done[i], 4);
+            mbar_init(&slab_summed[i], 1);
         }
         fence_barrier_init();
     }
@@ -331,10 +334,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 tma_store_commit();
                 if (ld.valid()) {
                     tma_store_wait_read<1>();
+                    // the buffer about to be handed out again held slab s-1: the column-sum warp must be done with it
+                    if (a.colsum != nullptr && s >= 1) mbar_wait(&slab_summed[(s - 1) & (TC_RING - 1)], ((s - 1) / TC_RING) & 1);
                     prepare(s + TC_RING - 1);
                 }
             }
             tma_store_wait_read<0>();
+        }
+    } else if (warp == 7) {
+        // column sums of the finished bf16 slabs (dgrad only): the per-channel sum of dX over (b, l) is the bias
+        // gradient of the layer that produced this conv's input, so that layer needs no separate pass over dX.
+        // lane = (row parity, channel pair): 64 conflict-free 4-byte loads per slab, rows past the end excluded.
+        if (a.colsum != nullptr) {
+            SlabIter<BN> it;
+            it.init(blockIdx.x, total_tiles, gridDim.x, n_nt, a.m_tiles, npar);
+            const int pr = lane & 15, half = lane >> 4;
+            for (int s = 0; it.valid(); ++s, it.next()) {
+                const int b = s & (TC_RING - 1);
+                const int rows_class = (a.L - it.c.par + npar - 1) / npar;       // rows of this parity class
+                const int nrows = min(TC_BM, rows_class - it.c.m0);
+                mbar_wait(&slab_done[b], (s / TC_RING) & 1);
+                const uint8_t* slab = ring + b * TC_SLAB_BYTES;
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                for (int r = half; r < nrows; r += 2) {
+                    const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)pr >> 2) ^ (((uint32_t)r >> 1) & 3u)) << 4) +
+                                         (((uint32_t)pr & 3u) << 2);
+                    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(slab + off));
+                    s0 += v.x;
+                    s1 += v.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&slab_summed[b]);
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                if (half == 0) {
+                    float* dst = a.colsum + it.c.n0 + it.sl * TC_SLAB_COLS + 2 * pr;
+                    atomicAdd(dst, s0);
+                    atomicAdd(dst + 1, s1);
+                }
+            }
         }
     } else {
         // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (rows of the tile).  Each 32-column slab goes
@@ -735,8 +774,7 @@ static int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
 
 template <int BN, int STAGES, bool AUX>
 static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO0, const CUtensorMap& mO1,
-                          const CUtensorMap& mX0, const CUtensorMap& mX1, const TcArgs& a, long long total_tiles,
-                          cudaStream_t st) {
+                          const TcArgs& a, long long total_tiles, cudaStream_t st) {
     auto kfn = conv_tc_kernel<BN, STAGES, AUX>;
     constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
     static_assert(smem <= 232448, "shared memory budget exceeded");
@@ -746,21 +784,20 @@ static int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, const CU
         attr_set = true;
     }
     const int grid = (int)(total_tiles < (long long)num_sms() ? total_tiles : (long long)num_sms());
-    kfn<<<grid, TC_THREADS, smem, st>>>(mA, mB, mO0, mO1, mX0, mX1, a);
+    kfn<<<grid, TC_THREADS, smem, st>>>(mA, mB, mO0, mO1, a);
     return cuda_status("conv_tc_kernel");
 }
 
 static int dispatch_conv_tc(int BN, bool aux, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO0,
-                            const CUtensorMap& mO1, const CUtensorMap& mX0, const CUtensorMap& mX1, const TcArgs& a,
-                            long long tiles, cudaStream_t st) {
+                            const CUtensorMap& mO1, const TcArgs& a, long long tiles, cudaStream_t st) {
     if (!aux) {
-        if (BN == 256) return launch_conv_tc<256, 4, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
-        if (BN == 128) return launch_conv_tc<128, 6, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
-        return launch_conv_tc<64, 8, false>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+        if (BN == 256) return launch_conv_tc<256, 4, false>(mA, mB, mO0, mO1, a, tiles, st);
+        if (BN == 128) return launch_conv_tc<128, 6, false>(mA, mB, mO0, mO1, a, tiles, st);
+        return launch_conv_tc<64, 8, false>(mA, mB, mO0, mO1, a, tiles, st);
     }
-    if (BN == 256) return launch_conv_tc<256, 4, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
-    if (BN == 128) return launch_conv_tc<128, 6, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
-    return launch_conv_tc<64, 8, true>(mA, mB, mO0, mO1, mX0, mX1, a, tiles, st);
+    if (BN == 256) return launch_conv_tc<256, 4, true>(mA, mB, mO0, mO1, a, tiles, st);
+    if (BN == 128) return launch_conv_tc<128, 6, true>(mA, mB, mO0, mO1, a, tiles, st);
+    return launch_conv_tc<64, 8, true>(mA, mB, mO0, mO1, a, tiles, st);
 }
 static int pick_bn(int C) { return (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : 64); }
 
@@ -856,12 +893,12 @@ extern "C" int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bi
     CUtensorMap mO;
     rc = make_map3(&mO, y, Cout, Lout, B, Cout, (uint64_t)Lout * Cout, TC_SLAB_COLS, TC_BM, 1, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc != GN_OK) return rc;
-    return dispatch_conv_tc(BN, false, mA, mB, mO, mO, mO, mO, a, (long long)B * a.m_tiles * (Cout / BN), as_stream(stream));
+    return dispatch_conv_tc(BN, false, mA, mB, mO, mO, a, (long long)B * a.m_tiles * (Cout / BN), as_stream(stream));
 }
 
-extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, int B, int L, int Cin,
-                                    int Lout, int Cout, int k, int stride, int pad_left, int in_act, float in_act_param,
-                                    void* stream) {
+extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, float* dx_colsum, int B,
+                                    int L, int Cin, int Lout, int Cout, int k, int stride, int pad_left, int in_act,
+                                    float in_act_param, void* stream) {
     GN_REQUIRE(dy && wk && dx, "null pointer");
     int rc = check_tc_geom(B, L, Cin, Lout, Cout, k, stride, pad_left);
     if (rc != GN_OK) return rc;
@@ -877,10 +914,12 @@ extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* 
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
     a.mode = 1; a.act = in_act; a.act_param = in_act_param; a.aux = (const __nv_bfloat16*)x_in;
     a.out = (__nv_bfloat16*)dx;
+    a.colsum = dx_colsum;
+    if (dx_colsum != nullptr) cudaMemsetAsync(dx_colsum, 0, sizeof(float) * (size_t)Cin, as_stream(stream));
     const int rows = (L + stride - 1) / stride;      // rows of the largest parity class
     a.m_tiles = (rows + TC_BM - 1) / TC_BM;
     // output: one map per parity class r: rows j = i*stride + r of dX, viewed as (Cin, rows_r, B)
-    CUtensorMap mO[2], mX[2];
+    CUtensorMap mO[2];
     const bool aux = (x_in != nullptr && in_act != GN_ACT_NONE);
     for (int r = 0; r < 2; ++r) {
         const int rr = (r < stride) ? r : 0;
@@ -888,12 +927,8 @@ extern "C" int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* 
         rc = make_map3(&mO[r], (const __nv_bfloat16*)dx + (size_t)rr * Cin, Cin, rows_r, B, (uint64_t)stride * Cin,
                        (uint64_t)L * Cin, TC_SLAB_COLS, TC_BM, 1, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != GN_OK) return rc;
-        // the mask source has the shape of dx: same parity views
-        rc = make_map3(&mX[r], (const __nv_bfloat16*)(aux ? x_in : dx) + (size_t)rr * Cin, Cin, rows_r, B,
-                       (uint64_t)stride * Cin, (uint64_t)L * Cin, TC_SLAB_COLS, TC_BM, 1, CU_TENSOR_MAP_SWIZZLE_64B);
-        if (rc != GN_OK) return rc;
     }
-    return dispatch_conv_tc(BN, aux, mA, mB, mO[0], mO[1], mX[0], mX[1], a,
+    return dispatch_conv_tc(BN, aux, mA, mB, mO[0], mO[1], a,
                             (long long)B * stride * a.m_tiles * (Cin / BN), as_stream(stream));
 }
 

@@ -31,6 +31,10 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 // multiply by exp(DIR*i*pi/2): DIR<0 -> -i, DIR>0 -> +i
@@ -171,9 +175,8 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ ptw, const I
             const int k = i & (P - 1);
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                float2 w = __ldg(&ptw[(r - 1) * P + k]);
-                if (DIR > 0) w.y = -w.y;
-                v[it][r] = cmul(v[it][r], w);
+                const float2 w = __ldg(&ptw[(r - 1) * P + k]);
+                v[it][r] = DIR > 0 ? cmulc(v[it][r], w) : cmul(v[it][r], w);
             }
         }
         Dft<R, DIR>::run(v[it]);
@@ -264,16 +267,17 @@ __device__ __forceinline__ void whiten_pointwise(float2* buf, const float2* __re
         }
         const int mk = M - k;
         float2 zk = buf[PADI(k)], zm = buf[PADI(mk)];
-        // A = (Zk + conj(Zm))/2 ; O = (Zk - conj(Zm))/(2i)
-        float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-        float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-        float2 t = __ldg(&tw[k]);  // exp(-2*pi*i*k/N)
-        float2 Bt = cmul(t, O);
-        float wk = __ldg(&wts[k]), wm = __ldg(&wts[mk]);
-        float2 P = cscale(cadd(A, Bt), wk);   // Y[k]
-        float2 Q = cscale(csub(A, Bt), wm);   // conj(Y[M-k])
-        float2 E = cscale(cadd(P, Q), 0.5f);
-        float2 Op = cmul(cconj(t), cscale(csub(P, Q), 0.5f));
+        // with A = (Zk + conj(Zm))/2, O = (Zk - conj(Zm))/(2i), t = exp(-2*pi*i*k/N):  Y[k] = wk (A + tO),
+        // conj(Y[M-k]) = wm (A - tO);  E = (Y[k] + conj(Y[M-k]))/2 = s A + d tO,  Op = conj(t) (Y[k] - conj(Y[M-k]))/2
+        // = s O + d conj(t) A  with s = (wk+wm)/2, d = (wk-wm)/2  (|t| = 1).  The halves fold into s, d.
+        const float2 A2 = make_float2(zk.x + zm.x, zk.y - zm.y);
+        const float2 O2 = make_float2(zk.y + zm.y, zm.x - zk.x);
+        const float2 t = __ldg(&tw[k]);  // exp(-2*pi*i*k/N)
+        const float wk = __ldg(&wts[k]), wm = __ldg(&wts[mk]);
+        const float s = 0.25f * (wk + wm), d = 0.25f * (wk - wm);
+        const float2 tO = cmul(t, O2), ctA = cmulc(A2, t);
+        const float2 E = make_float2(fmaf(s, A2.x, d * tO.x), fmaf(s, A2.y, d * tO.y));
+        const float2 Op = make_float2(fmaf(s, O2.x, d * ctA.x), fmaf(s, O2.y, d * ctA.y));
         // Z'[k] = E + i*Op ; Z'[M-k] = conj(E) + i*conj(Op)
         buf[PADI(k)] = make_float2(E.x - Op.y, E.y + Op.x);
         buf[PADI(mk)] = make_float2(E.x + Op.y, -E.y + Op.x);
@@ -303,7 +307,10 @@ __device__ __forceinline__ void irfft_pre(float2* buf, const float2* __restrict_
 }
 
 // resident CTAs per SM the register allocator must allow (<= ~85 registers per thread)
-#define GN_SYNTH_MINB(L2) (((1 << (L2)) / 16) >= 512 ? 1 : (65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * 80) > 8 ? 8 : 65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * 80)))
+#ifndef GN_SYNTH_REGS
+#define GN_SYNTH_REGS 64
+#endif
+#define GN_SYNTH_MINB(L2) (((1 << (L2)) / 16) >= 512 ? 1 : (65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * GN_SYNTH_REGS) > 8 ? 8 : 65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * GN_SYNTH_REGS)))
 constexpr int MODE_WHITEN = 0, MODE_IRFFT = 1, MODE_SYNTH = 2;
 
 struct SynthArgs {
@@ -404,6 +411,13 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
             const float* __restrict__ src = nullptr;
             if (MODE == MODE_WHITEN) {
                 src = a.x + (size_t)b * N;
+                // pull the series this CTA handles next into L2 while this one is being transformed
+                const int bn = b + gridDim.x;
+                if (bn < a.batch) {
+                    const char* nx = reinterpret_cast<const char*>(a.x + (size_t)bn * N);
+                    for (int ln = threadIdx.x; ln < N * 4 / 128; ln += blockDim.x)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)ln * 128));
+                }
             } else if (a.templates != nullptr) {
                 int t = a.tidx ? __ldg(&a.tidx[b]) : b;
                 t = min(max(t, 0), a.n_templates - 1);
@@ -445,7 +459,7 @@ static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
     // persistent CTAs: a multiple of the SM count, at most the batch
     int grid = a.batch;
     {
-        const int per_sm = threads >= 512 ? 1 : (threads >= 256 ? 3 : 6);
+        const int per_sm = threads >= 512 ? 1 : (threads >= 256 ? 65536 / (256 * GN_SYNTH_REGS) : 6);
         const int cap = num_sms() * per_sm * 4;      // a few series per CTA slot keeps the tail short
         if (grid > cap) grid = cap;
     }

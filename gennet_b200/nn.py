@@ -77,6 +77,19 @@ def _as_f32(x):
     return y
 
 
+def _bias_sink(layer, ctx, features):
+    """(pointer, channels) of the bias-gradient buffer of the tensor-core Conv1D feeding `layer`, when `layer`'s
+    data-gradient kernel can produce it as the per-channel sum of its output (fused activation mask, the
+    producer is trainable and ran on the tensor-core path); else (None, 0)."""
+    src = layer.bias_src
+    if src is None or layer.in_act is None or id(src) not in ctx.trainable_ids or getattr(src, '_mode', None) != 'tc':
+        return None, 0
+    C = src.filters
+    if C % 8 != 0 or features % C != 0:
+        return None, 0
+    return ptr(src.params[1].grad), C
+
+
 def _as_bf16(x):
     if x.dtype == BF16:
         return x
@@ -243,6 +256,7 @@ class Dense(Layer):
         self.units = int(units)
         self.activation = activation
         self.in_act = None           # (code, param) of the fused activation that produced our input (set by _fuse)
+        self.bias_src = None         # the Conv1D that produced our input when in_act is fused (set by _fuse)
 
     def build(self, in_shape):
         assert len(in_shape) == 1, 'Dense expects a flat input, got %s' % (in_shape,)
@@ -280,9 +294,11 @@ class Dense(Layer):
             if need_dx:
                 dx = _empty_bf16((B, K))
                 code, par = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
-                call('gn_dense_small_dgrad_bf16', ptr(dy), ptr(self.params[0].data), ptr(x, BF16), ptr(dx, BF16), B, K,
+                sink, C = _bias_sink(self, ctx, K)
+                call('gn_dense_small_dgrad_bf16', ptr(dy), ptr(self.params[0].data), ptr(x, BF16), ptr(dx, BF16), sink, C, B, K,
                      self.units, code, par, stream())
                 dx._gn_preact = self.in_act is not None
+                dx._gn_db_done = sink is not None
         else:
             if tr:
                 call('gn_dense_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad), ptr(self.params[1].grad), B, K,
@@ -315,6 +331,7 @@ class Conv1D(Layer):
         self.fused_up = 1        # set to 2 by Model._fuse when an UpSampling1D(2) directly precedes
         self.post_act = None     # (code, param) of a following activation layer folded into the epilogue
         self.in_act = None       # (code, param) of the fused activation that produced our input
+        self.bias_src = None     # the Conv1D that produced our input when in_act is fused (set by _fuse)
         self._wcache = None
 
     def build(self, in_shape):
@@ -383,6 +400,7 @@ class Conv1D(Layer):
         B = x.shape[0]
         L, cin = self.input_shape
         code, par = self._act()
+        db_done = getattr(dy, '_gn_db_done', False)
         if code != _lib.ACT_NONE and not getattr(dy, '_gn_preact', False):
             dy = _act_bwd(dy.contiguous(), self._y, code, par)
         tr = id(self) in ctx.trainable_ids
@@ -390,15 +408,19 @@ class Conv1D(Layer):
         if self._mode == 'tc':
             dy = _as_bf16(dy.contiguous())
             if tr:
-                call('gn_conv1d_wgrad_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(self.params[0].grad),
-                     ptr(self.params[1].grad), B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad, stream())
+                # the bias gradient may already have been taken by the consumer's data-gradient epilogue
+                db = None if db_done else ptr(self.params[1].grad)
+                call('gn_conv1d_wgrad_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(self.params[0].grad), db, B, L, cin,
+                     self.Lout, self.filters, self.k, self.s, self.pad, stream())
             if need_dx:
                 wk, wt = self._bf16_weights()
                 dx = _empty_bf16(x.shape)
                 icode, ipar = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
-                call('gn_conv1d_dgrad_bf16', ptr(dy, BF16), ptr(wk, BF16), ptr(x, BF16), ptr(dx, BF16), B, L, cin,
+                sink, _ = _bias_sink(self, ctx, cin)
+                call('gn_conv1d_dgrad_bf16', ptr(dy, BF16), ptr(wk, BF16), ptr(x, BF16), ptr(dx, BF16), sink, B, L, cin,
                      self.Lout, self.filters, self.k, self.s, self.pad, icode, ipar, stream())
                 dx._gn_preact = self.in_act is not None
+                dx._gn_db_done = sink is not None
         elif self._mode == 'smallcin':
             dy = _as_bf16(dy.contiguous())
             if tr:
@@ -683,6 +705,8 @@ class Reshape(Layer):
         dx = dy.reshape((dy.shape[0],) + self.input_shape)
         if getattr(dy, '_gn_preact', False):
             dx._gn_preact = True
+        if getattr(dy, '_gn_db_done', False):
+            dx._gn_db_done = True
         return dx
 
 
@@ -972,6 +996,7 @@ class Model(Layer):
                 if ok and src is not self._in_node and type(src.layer) is Conv1D and src.layer.post_act is not None \
                         and len(users.get(id(src), [])) == 1:
                     n.layer.in_act = src.layer.post_act
+                    n.layer.bias_src = src.layer     # its bias gradient = column sums of our data gradient
 
     # a model can be used as a layer
     def __call__(self, x):

@@ -134,15 +134,19 @@ int gn_conv1d_wgrad_f32(const float* x, const float* dy, float* dw, float* db, i
  *   gn_conv_w_to_bf16 : w f32 (k,Cin,Cout) -> wk bf16 (k,Cin,Cout) [dgrad operand] and wt bf16 (k,Cout,Cin) [fwd operand]
  *   fwd   : y = act(conv(x, w) + bias)                      x (B,L,Cin), y (B,Lout,Cout)
  *   dgrad : dx = act'(x_in) * conv_transpose(dy, w)         x_in = this conv's input (or NULL): fuses the backward
- *           of the activation layer that produced x_in (in_act = its GN_ACT_* code)
+ *           of the activation layer that produced x_in (in_act = its GN_ACT_* code).  dx_colsum (f32 (Cin),
+ *           OVERWRITTEN, or NULL): per-channel sum of dx over (b, l) = the bias gradient of the convolution
+ *           that produced x_in (dL/db = sum of its pre-activation output gradient), taken from the epilogue's
+ *           shared-memory slabs so that layer's wgrad call can pass db = NULL and skip a pass over dx
  *   wgrad : dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN  (needs Cin % 128 == 0, or Cin == 64 and Cout % 128 == 0) */
 int gn_conv_w_to_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, void* stream);
 int gn_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 int gn_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
 int gn_conv1d_fwd_bf16(const void* x, const void* wt, const float* bias, void* y, int B, int L, int Cin, int Lout,
                        int Cout, int k, int stride, int pad_left, int act, float act_param, void* stream);
-int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, int B, int L, int Cin, int Lout,
-                         int Cout, int k, int stride, int pad_left, int in_act, float in_act_param, void* stream);
+int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void* dx, float* dx_colsum, int B, int L,
+                         int Cin, int Lout, int Cout, int k, int stride, int pad_left, int in_act, float in_act_param,
+                         void* stream);
 int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
                          int Cout, int k, int stride, int pad_left, void* stream);
 
@@ -150,7 +154,10 @@ int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, in
  *   smallcin fwd  : first convolution of a network, Cin in {1,2}: x f32 (B,L,Cin) -> y bf16 (B,Lout,Cout), bias+act fused
  *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 5, Cout in {8,..,128})
  *   dense_small_* : Dense with N <= 4 outputs over bf16 features (K % 8 == 0): fwd y f32 (M,N); dgrad dx bf16 (M,K)
- *                   = act'(x_in) * dy w^T (x_in = the layer's input or NULL); wgrad dw f32 (K,N), db f32 (N) OVERWRITTEN
+ *                   = act'(x_in) * dy w^T (x_in = the layer's input or NULL), dx_colsum f32 (colsum_channels)
+ *                   OVERWRITTEN or NULL: sum of dx over rows and over features k with equal k % colsum_channels
+ *                   (bias gradient of the convolution whose flattened (L, C) output feeds this layer);
+ *                   wgrad dw f32 (K,N), db f32 (N) OVERWRITTEN
  *   gn_act_bwd_bf16: dx = dy * act'(y) on bf16 tensors */
 int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const float* bias, void* y, int B, int L, int Cin,
                                 int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param,
@@ -159,8 +166,8 @@ int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, flo
                                   int Cout, int k, int stride, int pad_left, void* stream);
 int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N, int act,
                             float act_param, void* stream);
-int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, int M, int K, int N,
-                              int in_act, float in_act_param, void* stream);
+int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, float* dx_colsum,
+                              int colsum_channels, int M, int K, int N, int in_act, float in_act_param, void* stream);
 int gn_dense_small_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int M, int K, int N, void* stream);
 int gn_act_bwd_bf16(const void* dy, const void* y, void* dx, long long n, int act, float param, void* stream);
 

@@ -25,15 +25,15 @@ for (L, Cin, Cout, s) in layers:
     bias = torch.zeros(Cout, device='cuda')
     y = torch.empty(B, Lout, Cout, dtype=torch.bfloat16, device='cuda')
     dx = torch.empty(B, L, Cin, dtype=torch.bfloat16, device='cuda')
-    dw = torch.empty(k, Cin, Cout, device='cuda'); db = torch.empty(Cout, device='cuda')
+    dw = torch.empty(k, Cin, Cout, device='cuda'); db = torch.empty(Cout, device='cuda'); db0 = torch.empty(Cin, device='cuda')
     st = L_.stream()
     bf = torch.bfloat16
     flops = 2.0 * B * Lout * k * Cin * Cout
     t1 = timeit(lambda: L_.call('gn_conv1d_fwd_bf16', L_.ptr(x, bf), L_.ptr(wt, bf), L_.ptr(bias), L_.ptr(y, bf), B, L, Cin, Lout, Cout, k, s, 0, 1, 0.0, st))
     t1b = timeit(lambda: L_.call('gn_conv1d_fwd_bf16', L_.ptr(x, bf), L_.ptr(wt, bf), None, L_.ptr(y, bf), B, L, Cin, Lout, Cout, k, s, 0, 0, 0.0, st))
     print('   fwd no-bias/no-act %.3f ms' % t1b)
-    t2 = timeit(lambda: L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, bf), L_.ptr(wk, bf), L_.ptr(x, bf), L_.ptr(dx, bf), B, L, Cin, Lout, Cout, k, s, 0, 1, 0.0, st))
-    t2b = timeit(lambda: L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, bf), L_.ptr(wk, bf), None, L_.ptr(dx, bf), B, L, Cin, Lout, Cout, k, s, 0, 0, 0.0, st))
+    t2 = timeit(lambda: L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, bf), L_.ptr(wk, bf), L_.ptr(x, bf), L_.ptr(dx, bf), L_.ptr(db0), B, L, Cin, Lout, Cout, k, s, 0, 1, 0.0, st))
+    t2b = timeit(lambda: L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, bf), L_.ptr(wk, bf), None, L_.ptr(dx, bf), None, B, L, Cin, Lout, Cout, k, s, 0, 0, 0.0, st))
     print('   dgrad no-mask %.3f ms' % t2b)
     t3 = timeit(lambda: L_.call('gn_conv1d_wgrad_bf16', L_.ptr(x, bf), L_.ptr(dy, bf), L_.ptr(dw), L_.ptr(db), B, L, Cin, Lout, Cout, k, s, 0, st))
     print('L=%4d %4d->%4d s%d  GF=%7.1f  fwd %.3f ms %6.1f TF | dgrad %.3f ms %6.1f TF | wgrad %.3f ms %6.1f TF' % (

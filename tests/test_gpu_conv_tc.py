@@ -70,14 +70,21 @@ def test_tc_conv_fwd_dgrad_wgrad(case):
     (yr * dy.float().cpu().double()).sum().backward()
     dx = torch.full((B, L, Cin), float('nan'), dtype=torch.bfloat16, device='cuda')
     L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, torch.bfloat16), L_.ptr(wk, torch.bfloat16), None, L_.ptr(dx, torch.bfloat16),
-            B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_NONE, 0.0, st)
+            None, B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_NONE, 0.0, st)
     torch.cuda.synchronize()
     assert_close(dx.float().cpu().numpy(), xr.grad.numpy(), 'tc conv dgrad', 2 ** -8)
-    # dgrad with the fused ReLU mask of the conv input
+    # dgrad with the fused ReLU mask of the conv input, and the fused per-channel sum of dx (= bias gradient of the
+    # layer that produced x): must equal the sum of the bf16 values actually stored
+    cs = torch.full((Cin,), float('nan'), device='cuda')
     L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, torch.bfloat16), L_.ptr(wk, torch.bfloat16), L_.ptr(x, torch.bfloat16),
-            L_.ptr(dx, torch.bfloat16), B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_RELU, 0.0, st)
+            L_.ptr(dx, torch.bfloat16), L_.ptr(cs), B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_RELU, 0.0, st)
     mask = (x.float().cpu().numpy() > 0)
     assert_close(dx.float().cpu().numpy(), xr.grad.numpy() * mask, 'tc conv dgrad*relu mask', 2 ** -8)
+    assert_close(cs.cpu().numpy(), dx.float().cpu().double().sum((0, 1)).numpy(), 'tc conv dgrad column sums', 1e-5)
+    # column sums without a mask (rows in the right padding of a SAME convolution must not leak in)
+    L_.call('gn_conv1d_dgrad_bf16', L_.ptr(dy, torch.bfloat16), L_.ptr(wk, torch.bfloat16), None, L_.ptr(dx, torch.bfloat16),
+            L_.ptr(cs), B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_NONE, 0.0, st)
+    assert_close(cs.cpu().numpy(), dx.float().cpu().double().sum((0, 1)).numpy(), 'tc conv dgrad column sums (no mask)', 1e-5)
     dw = torch.empty(k, Cin, Cout, device='cuda')
     db = torch.empty(Cout, device='cuda')
     L_.call('gn_conv1d_wgrad_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(dy, torch.bfloat16), L_.ptr(dw), L_.ptr(db), B, L, Cin, Lout,
@@ -136,10 +143,17 @@ def test_dense_small_bf16(M, K, N):
     L_.call('gn_dense_small_fwd_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(w), L_.ptr(b), L_.ptr(y), M, K, N, L_.ACT_NONE, 0.0, st)
     assert_close(y.cpu().numpy(), (xr @ wr + b.cpu().double()).numpy(), 'dense small fwd', 1e-5)
     dx = torch.empty(M, K, dtype=torch.bfloat16, device='cuda')
-    L_.call('gn_dense_small_dgrad_bf16', L_.ptr(dy), L_.ptr(w), L_.ptr(x, torch.bfloat16), L_.ptr(dx, torch.bfloat16), M, K, N,
-            L_.ACT_RELU, 0.0, st)
+    C = 64
+    cs = torch.full((C,), float('nan'), device='cuda')
+    L_.call('gn_dense_small_dgrad_bf16', L_.ptr(dy), L_.ptr(w), L_.ptr(x, torch.bfloat16), L_.ptr(dx, torch.bfloat16),
+            L_.ptr(cs), C, M, K, N, L_.ACT_RELU, 0.0, st)
     ref = (dy.cpu().double() @ wr.t()) * (xr > 0)
     assert_close(dx.float().cpu().numpy(), ref.numpy(), 'dense small dgrad*mask', 2 ** -8)
+    assert_close(cs.cpu().numpy(), dx.float().cpu().double().reshape(M, K // C, C).sum((0, 1)).numpy(),
+                 'dense small dgrad column sums', 1e-5)
+    L_.call('gn_dense_small_dgrad_bf16', L_.ptr(dy), L_.ptr(w), None, L_.ptr(dx, torch.bfloat16), None, 0, M, K, N,
+            L_.ACT_NONE, 0.0, st)
+    assert_close(dx.float().cpu().numpy(), (dy.cpu().double() @ wr.t()).numpy(), 'dense small dgrad', 2 ** -8)
     dw = torch.full((K, N), float('nan'), device='cuda')
     db = torch.full((N,), float('nan'), device='cuda')
     L_.call('gn_dense_small_wgrad_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(dy), L_.ptr(dw), L_.ptr(db), M, K, N, st)
