@@ -106,6 +106,21 @@ class ClockSampler:
                 'power_w_max': max(pw) if pw else None}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel family from the latest committed `ncu --set full` capture
+    (profiles/rNN_conv_tc_step_traffic.json, written by profiles/summarize_step_traffic.py); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_conv_tc_step_traffic.json')))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        return d['dram_bytes_per_launch'], os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def make_inputs(seed, device):
     """Synthetic chirp bank of BASELINE config 2: unwhitened time-domain templates (n,N) f32 in HBM,
     labels (mc/35, q), analytic PSD."""
@@ -297,10 +312,11 @@ def profile_pass(one_step, args, B, L, N):
     syn_ms = syn[0] / max(syn[1], 1)
     syn_bytes = B * (4 * N + 4 * L)
     syn_gbs = syn_bytes / (syn_ms / 1e3) / 1e9 if syn_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic()
     return {
         'roofline': {'bound': 'tensor', 'kernel': 'Conv1D implicit GEMM (fwd+dgrad+wgrad launches of one step)',
                      'achieved': ach, 'peak': tf_sust, 'unit': 'TFLOP/s', 'frac': ach / tf_sust,
-                     'traffic': None, 'peak_source': which + ' (sustained bf16 cuBLAS; kernel timed inside a long step)',
+                     'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': which + ' (sustained bf16 cuBLAS; kernel timed inside a long step)',
                      'avg_launch_ms': conv_ms / max(conv_launches, 1), 'share_of_step': conv_ms / step_ms if step_ms else None,
                      'algorithmic_flops_per_step': flops},
         'roofline_synth': {'bound': 'hbm', 'kernel': 'synth_kernel (Philox noise + inject + whiten + crop)',
