@@ -9,6 +9,7 @@ the reference.  LALSuite is not restated: FD waveforms, PSDs and antenna factors
 callables.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -321,6 +322,60 @@ def sim_data(fs, T_obs, psds, dets=['H1'], Nnoise=25, size=1000, mdist='astro', 
         pars.append(p)
         yval = np.append(yval, 1)
     return [ts, yval], pars
+
+
+def make_template_bank(event_fd, event_noise_fd, psd, fs=1024, T_obs=2, Nsamp=1000, Nblock=1000, Nnoise=0,
+                       dets=['H1'], mdist='astro', oversamp=True, basename='templates/', event_name='gw150914',
+                       sample_num=None, tag='', waveform=None, antenna=None, rng=np.random, write=True):
+    """The generation loop of ``main()`` (gw_template_maker.py:742-849) with the lalinference text files replaced
+    by arrays on the rfft grid of N = safe*T_obs*fs samples: ``event_fd`` = event in noise
+    (``...freqDataWithInjection.dat``), ``event_noise_fd`` = noise alone (``...freqData.dat``), ``psd`` (``...PSD.dat``
+    column 1).  Whitens the event FD -> TD (:774-777), takes ``gw_norm_constant = 1/std`` of the whitened event over
+    the full segment (:782), generates ``ceil(Nsamp/Nblock)`` blocks with :func:`sim_data` (``hunt_constrain`` prior
+    when ``oversamp``, beta [0.45, 0.55], :806-808), scales every template by the constant (:813-814), drops the
+    appended GW150914-like template from all but the last block (:817-819) and pickles each block the way
+    ``cPickle.dump(.., protocol=HIGHEST_PROTOCOL)`` did (:840-849):
+        <basename><event>_ts_<i>_<sample_num>Samp<tag>.sav       [ts (n,1,fs) float64, yval]
+        <basename><event>_params_<i>_<sample_num>Samp<tag>.sav   list[bbhparams]
+    Returns a dict with the norm constant, the cropped whitened event / noise-free event, and the file names."""
+    from . import io as gio
+    safeT = safe * T_obs
+    N = int(fs * safeT)
+    event_fd = np.array(event_fd, dtype=np.complex128)
+    noise_fd = np.array(event_noise_fd, dtype=np.complex128)
+    event_fd[np.isnan(event_fd)] = 0
+    noise_fd[np.isnan(noise_fd)] = 0
+    h_fd = event_fd - noise_fd
+    s = _synth_for(fs, safeT, psd)
+    # whiten_data(.., 'fd') then np.fft.irfft(.., N): spectral weights (DC zeroed) fused into the inverse transform
+    wht = s.irfft(np.stack([event_fd, h_fd]), weights=s.weights).cpu().numpy().astype(np.float64)
+    wht_wvf, h_t = wht[0], wht[1]
+    gw_norm_constant = 1.0 / np.std(wht_wvf)
+    lo, hi = int((safeT / 2) * fs - fs / 2.0), int((safeT / 2) * fs + fs / 2.0)
+    wht_wvf, h_t = wht_wvf[lo:hi], h_t[lo:hi]
+    nblock = int(np.ceil(float(Nsamp) / float(Nblock)))
+    sample_num = Nsamp if sample_num is None else sample_num
+    files = []
+    last = None
+    for i in range(nblock):
+        ts, par = sim_data(fs, safeT, psd, dets, Nnoise, size=Nblock, mdist='hunt_constrain' if oversamp else mdist,
+                           beta=[0.45, 0.55], waveform=waveform, antenna=antenna, rng=rng)
+        ts[0] = ts[0] * gw_norm_constant
+        if i != nblock - 1:
+            ts[0] = ts[0][:-1]
+            par = par[:-1]
+        if write:
+            f_ts = '%s%s_ts_%d_%sSamp%s.sav' % (basename, event_name, i, sample_num, tag)
+            f_par = '%s%s_params_%d_%sSamp%s.sav' % (basename, event_name, i, sample_num, tag)
+            d = os.path.dirname(f_ts)
+            if d and not os.path.isdir(d):
+                os.makedirs(d)
+            gio.dump_pickle(ts, f_ts)
+            gio.dump_pickle(par, f_par)
+            files.append((f_ts, f_par))
+        last = (ts, par)
+    return {'gw_norm_constant': gw_norm_constant, 'event': wht_wvf, 'event_noise_free': h_t, 'files': files,
+            'last_block': last}
 
 
 def make_burst_waveforms(N_sig, amp=1, freq=100, dt=1.0 / 512, N=512, t_0=0.5, phi=2 * np.pi, tau=1.0 / 25.0,

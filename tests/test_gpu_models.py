@@ -113,3 +113,24 @@ def test_pe_step_bf16_within_stated_tolerance():
         assert [c._path() for c in convs] == ['smallcin', 'tc', 'tc', 'tc', 'smallcin', 'tc', 'tc', 'tc', 'tc']
     finally:
         nn.set_compute_dtype('float32')
+
+
+@pytest.mark.gpu
+def test_keras_hdf5_roundtrip_on_device(tmp_path):
+    """save -> load_model on the GPU path: identical predictions, optimizer state carried over (bbhMahoGANy.py:1173,1135)."""
+    from gennet_b200 import nn
+    prod, orc, x, y = pc.pe_case(256, 4)
+    prod.train_on_batch(x, y)
+    p = str(tmp_path / 'signal_pe.h5')
+    prod.save(p, True)
+    m2 = nn.load_model(p)
+    for a, b in zip(prod.predict(x), m2.predict(x)):
+        assert np.array_equal(a, b)
+    r1, r2 = prod.train_on_batch(x, y), m2.train_on_batch(x, y)
+    assert np.allclose(r1, r2, rtol=1e-5, atol=1e-7)
+    for a, b in zip(prod.get_weights(), m2.get_weights()):
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-7)
+    prod.save_weights(str(tmp_path / 'w.h5'), True)
+    m2.load_weights(str(tmp_path / 'w.h5'))
+    for a, b in zip(prod.get_weights(), m2.get_weights()):
+        assert np.array_equal(a, b)

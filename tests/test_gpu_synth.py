@@ -1,6 +1,8 @@
 """GPU parity: synthesis kernels (through the C ABI) vs the float64 oracle and the golden vectors that the
 reference's own source produced.  Tolerance: 1e-6 of the series' peak (north_star: 'templates and whitened
 series within 1e-6 relative'); float32 FFT round-off at N<=32768 is ~3e-7."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -182,3 +184,41 @@ def test_invalid_arguments_raise(gs):
         gs.Synthesizer(1000, 1, np.ones(501))       # N not a power of two
     with pytest.raises(GennetError):
         s.whiten_td(torch.zeros(2, fs * T))[0] if False else gs._lib.ptr(torch.zeros(3))  # CPU tensor refused
+
+
+@pytest.mark.gpu
+def test_template_bank_generator_end_to_end(tmp_path):
+    """main() of gw_template_maker.py (:742-849) on arrays: whitened event, norm constant, blocks of templates
+    pickled in the reference's .sav layout, re-read and compared with the oracle's whitening of the same FD data."""
+    from gennet_b200 import synth, io as gio
+    from oracle import synth_oracle as so
+    fs, T = 1024, 2
+    N = fs * T * synth.safe
+    psd = so.analytic_psd(fs, T * synth.safe)
+    rs = np.random.RandomState(3)
+    noise_fd = (rs.normal(size=N // 2 + 1) + 1j * rs.normal(size=N // 2 + 1)) * np.sqrt(psd) * 10
+    hp, _ = so.newtonian_chirp_fd(36.0, 29.0, fs, T * synth.safe)
+    event_fd = noise_fd + hp
+
+    def waveform(par, fs_, T_):
+        return so.newtonian_chirp_fd(par.m1, par.m2, fs_, T_)
+    base = str(tmp_path / 'bank') + '/'
+    res = synth.make_template_bank(event_fd, noise_fd, psd, fs=fs, T_obs=T, Nsamp=12, Nblock=6, Nnoise=0, basename=base,
+                                   tag='_srate-1024hz', waveform=waveform, rng=np.random.RandomState(5))
+    # oracle: whiten_data(.., 'fd') -> irfft -> 1/std over the full segment -> central second
+    w = so.whiten_data(event_fd.copy(), T * synth.safe, fs, psd, 'fd')
+    wt = np.fft.irfft(w, N)
+    assert abs(res['gw_norm_constant'] - 1.0 / np.std(wt)) < 2e-6 / np.std(wt)
+    assert rel_err(res['event'], wt[N // 2 - fs // 2:N // 2 + fs // 2]) < 2e-6
+    assert len(res['files']) == 2
+    ts0, y0, par0 = gio.load_template_bank(*res['files'][0])
+    ts1, y1, par1 = gio.load_template_bank(*res['files'][1])
+    assert ts0.shape == (5, 1, fs) and ts1.shape == (6, 1, fs) and ts0.dtype == np.float64      # last block keeps the
+    assert len(par0) == 5 and len(par1) == 6 and (par1[-1].m1, par1[-1].m2) == (36.0, 29.0)     # GW150914-like template
+    assert all(20.0 <= p.mc <= 35.0 and p.m2 / p.m1 >= 0.5 for p in par0)                         # hunt_constrain prior
+    assert os.path.basename(res['files'][0][0]) == 'gw150914_ts_0_12Samp_srate-1024hz.sav'
+    # a template of the bank = oracle's whitened, windowed, cropped template x the norm constant
+    p = par1[-1]
+    ref, _ = so.gen_bbh_from_fd(*so.newtonian_chirp_fd(p.m1, p.m2, fs, T * synth.safe), fs, T * synth.safe, psd, p.idx,
+                                1.0, 0.0)
+    assert rel_err(ts1[-1, 0], so.crop_central(ref, fs, T * synth.safe) * res['gw_norm_constant']) < 3e-6
