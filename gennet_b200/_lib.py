@@ -69,6 +69,7 @@ _SIGS = {
     'gn_maxpool1d_bwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_axpy_f32': [c_p, c_p, c_f, c_ll, c_p],
     'gn_gather_rows_f32': [c_p, c_p, c_p, c_i, c_ll, c_p],
+    'gn_maxnorm_roll_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
     'gn_stack_residual_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
     'gn_stack_residual_bwd_f32': [c_p, c_p, c_i, c_i, c_p],
     'gn_residual_moments_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
@@ -96,7 +97,7 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise GennetError('%s is missing: build it with `python -m gennet_b200.build` '
+        raise GennetError('%s is missing: build it with `python gennet_b200/build.py` '
                           '(there is no CPU fallback)' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     lib.gn_last_error.restype = ctypes.c_char_p

@@ -529,6 +529,41 @@ extern "C" int gn_axpy_f32(float* a, const float* b, float alpha, long long n, v
     axpy_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(a, b, alpha, n);
     return cuda_status("axpy_kernel");
 }
+// waveform ingest (train_on_wvf_version/load_txtwfs.py:47-50,66-69): y = roll(x / max(x), offset) per row.
+// One CTA per waveform: block max (plain maximum, as np.max -- not the absolute value), then the rotated store.
+namespace gn {
+__global__ void __launch_bounds__(256) maxnorm_roll_kernel(const float* __restrict__ x, const int* __restrict__ off,
+                                                           float* __restrict__ y, int N) {
+    __shared__ float sm[8];
+    const float* xr = x + (size_t)blockIdx.x * N;
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) m = fmaxf(m, xr[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = sm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+    int sh = off ? off[blockIdx.x] % N : 0;
+    if (sh < 0) sh += N;
+    float* yr = y + (size_t)blockIdx.x * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        int d = j + sh;
+        if (d >= N) d -= N;
+        yr[d] = xr[j] / m;
+    }
+}
+}  // namespace gn
+
+extern "C" int gn_maxnorm_roll_f32(const float* x, const int* offsets, float* y, int B, int N, void* stream) {
+    GN_REQUIRE(x && y && B >= 0 && N > 0, "null pointer or bad size");
+    GN_REQUIRE(x != y, "in-place rotation is not supported");
+    if (B == 0) return GN_OK;
+    gn::maxnorm_roll_kernel<<<B, 256, 0, as_stream(stream)>>>(x, offsets, y, N);
+    return cuda_status("maxnorm_roll_kernel");
+}
+
 extern "C" int gn_gather_rows_f32(const float* src, const int* idx, float* out, int n, long long row_len,
                                   void* stream) {
     GN_REQUIRE(src && idx && out && n >= 0 && row_len > 0, "null pointer or bad size");

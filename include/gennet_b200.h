@@ -223,6 +223,12 @@ int gn_axpy_f32(float* a, const float* b, float alpha, long long n, void* stream
 /* gather rows: out[i,:] = src[idx[i],:]  (template batch assembly, bbhMahoGANy.py:1156-1158,1244) */
 int gn_gather_rows_f32(const float* src, const int* idx, float* out, int n, long long row_len, void* stream);
 
+/* waveform ingest, train_on_wvf_version/load_txtwfs.py:47-50,66-69: y[b, (j + offsets[b]) mod N] = x[b, j] / max_j x[b, j]
+ * (np.max then np.roll; offsets may be negative or NULL = no shift).  The FFT resampling step before it
+ * (scipy.signal.resample(data, 512)) is a fixed linear map for a given input length and runs as gn_dense_fwd_f32
+ * against the precomputed (Nx, 512) Dirichlet-kernel matrix. */
+int gn_maxnorm_roll_f32(const float* x, const int* offsets, float* y, int B, int N, void* stream);
+
 /* MyLayer, bbhMahoGANy.py:164-188: y (B,L,2) = stack([x, const - x], axis=2); bwd dx = dy[...,0]-dy[...,1] */
 int gn_stack_residual_fwd_f32(const float* x, const float* cst, float* y, int B, int L, void* stream);
 int gn_stack_residual_bwd_f32(const float* dy, float* dx, int B, int L, void* stream);

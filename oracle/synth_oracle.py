@@ -284,3 +284,26 @@ def newtonian_chirp_fd(m1, m2, fs, T_obs, iota=2.5, phi=1.5, f_low=40.0, dist_mp
     h[band] = amp * np.exp(-1j * psi)
     ci = np.cos(iota)
     return 0.5 * (1 + ci ** 2) * h, -1j * ci * h
+
+
+def resample_fft(x, num):
+    """``scipy.signal.resample(x, num)`` as scipy 1.1.0 (the version the reference pins, requirements.txt:42)
+    computes it for a real 1-D series: FFT, keep bins [0, (N+1)//2) and the last (N-1)//2 with N = min(num, Nx)
+    -- for even N the bin N/2 is NOT carried over, unlike scipy >= 1.4 -- inverse FFT, scale num/Nx.
+    Call site: train_on_wvf_version/load_txtwfs.py:48,66."""
+    x = np.asarray(x, dtype=np.float64)
+    Nx = x.shape[-1]
+    X = np.fft.fft(x, axis=-1)
+    N = int(min(num, Nx))
+    Y = np.zeros(x.shape[:-1] + (num,), dtype=np.complex128)
+    Y[..., 0:(N + 1) // 2] = X[..., 0:(N + 1) // 2]
+    if (N - 1) // 2 > 0:
+        Y[..., -((N - 1) // 2):] = X[..., -((N - 1) // 2):]
+    return (np.fft.ifft(Y, axis=-1) * (float(num) / float(Nx))).real
+
+
+def ingest_waveform(x, offset, num=512):
+    """load_txtwfs.py:47-50: resample to `num` points, divide by the maximum, roll by `offset`."""
+    d = resample_fft(x, num)
+    d = d / np.max(d)
+    return np.roll(d, offset)

@@ -215,6 +215,12 @@ class Fake:
     def gn_gather_rows_f32(self, src, idx, out, n, row_len, st):
         out.reshape(n, row_len).copy_(src.reshape(-1, row_len)[idx.long()])
 
+    def gn_maxnorm_roll_f32(self, x, off, y, B, N, st):
+        xv = x.reshape(B, N)
+        for b in range(B):
+            sh = int(off[b]) if off is not None else 0
+            y.reshape(B, N)[b].copy_(torch.roll(xv[b] / xv[b].max(), sh))
+
     def gn_add_scaled_f32(self, x, r, sigma, n, st):
         x.reshape(-1)[:n].add_(r.reshape(-1)[:n], alpha=sigma)
 
@@ -277,7 +283,10 @@ def install(monkeypatch):
     fake = Fake()
     cpu = torch.device('cpu')
     monkeypatch.setattr(_lib, 'require_device', lambda: None)
-    for mod in (nn, bbh):
+    import gennet_b200.wvf as wvf
+    monkeypatch.setattr(wvf, 'device', lambda: cpu)
+    wvf._RESAMPLE_OPS.clear()
+    for mod in (nn, bbh, wvf):
         monkeypatch.setattr(mod, 'call', fake.call)
         monkeypatch.setattr(mod, 'ptr', fake.ptr)
         monkeypatch.setattr(mod, 'stream', fake.stream)

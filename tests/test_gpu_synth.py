@@ -222,3 +222,24 @@ def test_template_bank_generator_end_to_end(tmp_path):
     ref, _ = so.gen_bbh_from_fd(*so.newtonian_chirp_fd(p.m1, p.m2, fs, T * synth.safe), fs, T * synth.safe, psd, p.idx,
                                 1.0, 0.0)
     assert rel_err(ts1[-1, 0], so.crop_central(ref, fs, T * synth.safe) * res['gw_norm_constant']) < 3e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('Nx', [4096, 16000, 3001])
+def test_waveform_ingest_matches_oracle(Nx):
+    """GPU resample (dense operator) + max-normalise + roll vs the float64 restatement of load_txtwfs.py:47-50."""
+    from gennet_b200 import wvf
+    rs = np.random.RandomState(Nx)
+    t = np.arange(Nx) / float(Nx)
+    x = np.stack([np.sin(2 * np.pi * (20 + 3 * i) * t) * np.exp(-((t - 0.5) / 0.1) ** 2) + 0.01 * rs.normal(size=Nx)
+                  for i in range(7)])
+    offs = rs.randint(-100, 100, size=7)
+    got = wvf.ingest_waveforms(x, offs).cpu().numpy()
+    ref = np.stack([so.ingest_waveform(x[i], int(offs[i])) for i in range(7)])
+    assert got.shape == (7, 512)
+    # float32 operator and a float32 running sum over Nx terms: ~sqrt(Nx) * 2^-24 of the peak (documented tolerance;
+    # this ingest path is outside the north star's 1e-6 synthesis bar)
+    assert rel_err(got, ref) < 2e-5
+    # no offsets: plain resample / max
+    got0 = wvf.ingest_waveforms(x[:2]).cpu().numpy()
+    assert rel_err(got0, np.stack([so.ingest_waveform(x[i], 0) for i in range(2)])) < 2e-5

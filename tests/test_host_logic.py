@@ -102,3 +102,21 @@ def test_summary_and_counts(fake):
     lines = []
     pe.summary(print_fn=lines.append)
     assert any('Total params' in l for l in lines)
+
+
+def test_waveform_ingest_host_logic(fake, tmp_path):
+    """load_txtwfs.py:31-77 mirror: files -> resample operator -> max-normalise -> roll, grouped by input length."""
+    from gennet_b200 import wvf
+    from oracle import synth_oracle as so
+    rs = np.random.RandomState(2)
+    series = [rs.normal(size=n) for n in (3000, 3000, 2048)]
+    for i, s_ in enumerate(series):
+        np.savetxt(str(tmp_path / ('wf%d.txt' % i)), s_)
+    data, pars = wvf.load_data(str(tmp_path), 10, frequencies=[70.0, 70.0, 70.0], rng=np.random.RandomState(4))
+    assert data.shape == (3, 512) and pars.shape == (3, 2)
+    import glob
+    files = list(glob.iglob('%s/*.txt' % str(tmp_path)))
+    for row, p, f in zip(data, pars, files):
+        ref = so.ingest_waveform(np.loadtxt(f), int(p[0] - 256))
+        assert np.abs(row - ref).max() < 5e-5          # float32 operator in the stand-in backend
+        assert p[1] == 70.0 and -100 <= p[0] - 256 < 100

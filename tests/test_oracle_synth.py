@@ -90,3 +90,26 @@ def test_gen_bbh_tail_pipeline_shapes():
     peak = int(np.argmax(np.abs(ts)))
     assert abs(peak - lo) < 64          # peak lands at the requested index (within the 11-sample lead + envelope)
     assert np.all(ts[: fs // 2] == 0)   # aggressive window zeroes the safe margins
+
+
+def test_resample_restatement_against_scipy():
+    """oracle.resample_fft restates scipy 1.1.0's resample (requirements.txt:42).  Current SciPy differs only in the
+    new-Nyquist bin (carried over since 1.4), so it must agree exactly on input band-limited below it, and the
+    restatement must drop that bin on broadband input."""
+    import scipy.signal
+    from oracle import synth_oracle as so
+    rs = np.random.RandomState(0)
+    for Nx in (2000, 4096, 3001, 700):
+        x = rs.normal(size=Nx)
+        X = np.fft.rfft(x)
+        X[200:] = 0
+        xb = np.fft.irfft(X, Nx)
+        assert np.abs(so.resample_fft(xb, 512) - scipy.signal.resample(xb, 512)).max() < 1e-12
+        y = so.resample_fft(x, 512)
+        assert abs(np.fft.fft(y)[256]) < 1e-9 * np.abs(np.fft.fft(y)).max()
+    # upsampling branch (Nx < num) and the full ingest: max-normalised, rolled
+    x = rs.normal(size=300)
+    assert np.abs(so.resample_fft(x, 512)[::1].mean() - x.mean()) < 1e-9 * 512
+    d = so.ingest_waveform(rs.normal(size=5000), -37)
+    assert d.shape == (512,) and abs(d.max() - 1.0) < 1e-12
+    assert np.argmax(d) == (np.argmax(np.roll(d, 37)) - 37) % 512
