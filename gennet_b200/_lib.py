@@ -70,6 +70,7 @@ _SIGS = {
     'gn_axpy_f32': [c_p, c_p, c_f, c_ll, c_p],
     'gn_gather_rows_f32': [c_p, c_p, c_p, c_i, c_ll, c_p],
     'gn_maxnorm_roll_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
+    'gn_flip_transpose_f32': [c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_stack_residual_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
     'gn_stack_residual_bwd_f32': [c_p, c_p, c_i, c_i, c_p],
     'gn_residual_moments_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],

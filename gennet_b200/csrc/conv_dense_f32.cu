@@ -354,3 +354,31 @@ extern "C" int gn_dense_wgrad_f32(const float* x, const float* dy, float* dw, fl
     if (db != nullptr) return launch_colsum(dy, (long long)M, N, db, st);
     return GN_OK;
 }
+
+
+// ---- Conv2DTranspose with a (1, kw) kernel, unit strides, 'valid' (2_model_version generators) -----------------
+// y[w, co] = sum_{j, ci} x[w - j, ci] K[0, j, co, ci]  is the Conv1D  y[w] = sum_t x[w + t - (kw-1)] W1[t]  with
+// W1[t, ci, co] = K[0, kw-1-t, co, ci], left padding kw-1 and Lout = L + kw - 1, so the layer runs on the Conv1D
+// kernels; this helper converts weights (and, with the roles of the two inner axes swapped, weight gradients)
+// between the Keras layout (kw, Cout, Cin) and the Conv1D layout (kw, Cin, Cout):  out[t, a, b] = in[k-1-t, b, a].
+namespace gn {
+__global__ void __launch_bounds__(256) flip_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int k,
+                                                             int A, int Bn) {
+    const long long n = (long long)k * A * Bn;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i % Bn);
+        const long long r = i / Bn;
+        const int a = (int)(r % A);
+        const int t = (int)(r / A);
+        out[i] = in[((size_t)(k - 1 - t) * Bn + b) * A + a];
+    }
+}
+}  // namespace gn
+
+extern "C" int gn_flip_transpose_f32(const float* in, float* out, int k, int A, int B, void* stream) {
+    GN_REQUIRE(in && out && k > 0 && A > 0 && B > 0, "null pointer or bad size");
+    const long long n = (long long)k * A * B;
+    unsigned grid = (unsigned)((n + 255) / 256 < 8LL * num_sms() ? (n + 255) / 256 : 8LL * num_sms());
+    gn::flip_transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, out, k, A, B);
+    return cuda_status("flip_transpose_kernel");
+}

@@ -165,6 +165,11 @@ def layer_config(layer):
                    padding=layer.padding, data_format='channels_last', dilation_rate=[1, 1], activation='linear',
                    **_kernel_cfg(layer))
         return 'Conv2D', cfg
+    if t is nn.Conv2DTranspose:
+        cfg.update(filters=layer.filters, kernel_size=[layer.kh, layer.kw], strides=[layer.sh, layer.sw],
+                   padding=layer.padding, data_format='channels_last', activation=layer.activation or 'linear',
+                   **_kernel_cfg(layer))
+        return 'Conv2DTranspose', cfg
     if t is nn.BatchNormalization:
         cfg.update(axis=-1, momentum=layer.momentum, epsilon=layer.epsilon, center=True, scale=True,
                    beta_initializer=_ZEROS, gamma_initializer=_ONES, moving_mean_initializer=_ZEROS,
@@ -255,6 +260,9 @@ def _layer_from_config(class_name, cfg, custom_objects):
     if class_name in ('Conv2D', 'Convolution2D'):
         return nn.Conv2D(cfg['filters'], tuple(cfg['kernel_size']), strides=tuple(cfg.get('strides', (1, 1))),
                          padding=cfg.get('padding', 'valid'), **kw)
+    if class_name in ('Conv2DTranspose', 'Deconvolution2D'):
+        return nn.Conv2DTranspose(cfg['filters'], tuple(cfg['kernel_size']), strides=tuple(cfg.get('strides', (1, 1))),
+                                  padding=cfg.get('padding', 'valid'), activation=act(cfg.get('activation')), **kw)
     if class_name == 'BatchNormalization':
         return nn.BatchNormalization(momentum=cfg.get('momentum', 0.99), epsilon=cfg.get('epsilon', 1e-3), **kw)
     if class_name == 'Activation':

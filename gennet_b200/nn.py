@@ -512,6 +512,74 @@ class Conv2D(Layer):
         return dx
 
 
+class Conv2DTranspose(Layer):
+    """Keras Conv2DTranspose (channels_last), kernel (kh, kw, Cout, Cin), for the geometry the reference uses
+    (2_model_version/*/no_mode_collapse_network.py:79-90): kh = 1, strides (1, 1), padding 'valid'.  Every image
+    row is a full 1-D convolution along W, so the layer runs on the Conv1D kernels (see gn_flip_transpose_f32)."""
+    prefix = 'conv2d_transpose'
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', activation=None,
+                 kernel_initializer='glorot_uniform', **kw):
+        super().__init__(**kw)
+        self.filters = int(filters)
+        self.kh, self.kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        self.sh, self.sw = (strides, strides) if isinstance(strides, int) else tuple(strides)
+        self.padding = padding
+        self.activation = activation
+
+    def build(self, in_shape):
+        H, W, cin = in_shape
+        if not (self.kh == 1 and self.sh == 1 and self.sw == 1 and self.padding == 'valid'):
+            raise NotImplementedError('Conv2DTranspose is implemented for the reference generator geometry only '
+                                      '(kernel (1, kw), strides (1, 1), padding valid)')
+        kw = self.kw
+        # Keras fan computation for a transposed kernel (kh, kw, out, in): fan_in = kh*kw*in ... via _compute_fans on
+        # the stored shape: receptive field * shape[-2] and * shape[-1]
+        self.params = [Param(self.name + '/kernel:0', _glorot((1, kw, self.filters, cin), kw * self.filters, kw * cin)),
+                       Param(self.name + '/bias:0', np.zeros(self.filters, np.float32))]
+        self.Wout = W + kw - 1
+        return (H, self.Wout, self.filters)
+
+    def _w1(self):
+        H, W, cin = self.input_shape
+        w1 = _empty((self.kw, cin, self.filters))
+        call('gn_flip_transpose_f32', ptr(self.params[0].data), ptr(w1), self.kw, cin, self.filters, stream())
+        return w1
+
+    def forward(self, x, ctx):
+        x = _as_f32(x).contiguous()
+        B = x.shape[0]
+        H, W, cin = self.input_shape
+        w1 = self._w1()
+        y = _empty((B, H, self.Wout, self.filters))
+        code = _ACTS[self.activation]
+        call('gn_conv1d_fwd_f32', ptr(x), ptr(w1), ptr(self.params[1].data), ptr(y), B * H, W, cin, self.Wout,
+             self.filters, self.kw, 1, self.kw - 1, 1, code, 0.0, stream())
+        self._x, self._y, self._w = x, y, w1
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        x, w1 = self._x, self._w
+        B = x.shape[0]
+        H, W, cin = self.input_shape
+        dy = _as_f32(dy).contiguous()
+        code = _ACTS[self.activation]
+        if code != _lib.ACT_NONE:
+            dy = _act_bwd(dy, self._y, code, 0.0)
+        if id(self) in ctx.trainable_ids:
+            dw1 = _empty(w1.shape)
+            call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(dw1), ptr(self.params[1].grad), B * H, W, cin, self.Wout,
+                 self.filters, self.kw, 1, self.kw - 1, 1, stream())
+            call('gn_flip_transpose_f32', ptr(dw1), ptr(self.params[0].grad), self.kw, self.filters, cin, stream())
+        dx = None
+        if need_dx:
+            dx = _empty(x.shape)
+            call('gn_conv1d_dgrad_f32', ptr(dy), ptr(w1), ptr(dx), B * H, W, cin, self.Wout, self.filters, self.kw, 1,
+                 self.kw - 1, 1, stream())
+        self._x = self._y = self._w = None
+        return dx
+
+
 class BatchNormalization(Layer):
     """Keras 2.2.4 BatchNormalization(axis=-1): gamma, beta, moving_mean, moving_variance."""
     prefix = 'batch_normalization'

@@ -223,6 +223,12 @@ int gn_axpy_f32(float* a, const float* b, float alpha, long long n, void* stream
 /* gather rows: out[i,:] = src[idx[i],:]  (template batch assembly, bbhMahoGANy.py:1156-1158,1244) */
 int gn_gather_rows_f32(const float* src, const int* idx, float* out, int n, long long row_len, void* stream);
 
+/* Conv2DTranspose((1,kw), strides (1,1), 'valid') of the 2_model_version generators
+ * (2_model_version/weight_version/no_mode_collapse_network.py:79-90) runs on the Conv1D entry points with
+ * pad_left = kw-1, Lout = L+kw-1 and the kernel W1[t,ci,co] = K[0,kw-1-t,co,ci]; this converts between the two
+ * layouts (weights: A=Cin,B=Cout from Keras (kw,Cout,Cin); gradients: A=Cout,B=Cin back): out[t,a,b] = in[k-1-t,b,a]. */
+int gn_flip_transpose_f32(const float* in, float* out, int k, int A, int B, void* stream);
+
 /* waveform ingest, train_on_wvf_version/load_txtwfs.py:47-50,66-69: y[b, (j + offsets[b]) mod N] = x[b, j] / max_j x[b, j]
  * (np.max then np.roll; offsets may be negative or NULL = no shift).  The FFT resampling step before it
  * (scipy.signal.resample(data, 512)) is a fixed linear map for a given input length and runs as gn_dense_fwd_f32

@@ -125,6 +125,29 @@ class Conv2D(Layer):
         return y.permute(0, 2, 3, 1)
 
 
+class Conv2DTranspose(Layer):
+    """Keras Conv2DTranspose, channels_last, kernel (kh, kw, Cout, Cin), 'valid': out = (in-1)*s + k
+    (2_model_version/weight_version/no_mode_collapse_network.py:79-90).  TF's conv2d_transpose is the gradient of
+    conv2d w.r.t. its input, i.e. torch's conv_transpose2d with weight (Cin, Cout, kh, kw)."""
+    kind = 'conv2d_transpose'
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', activation=None):
+        super().__init__()
+        assert padding == 'valid'
+        self.filters, self.k, self.s, self.activation = filters, tuple(kernel_size), tuple(strides), activation
+
+    def build(self, in_shape, gen, dtype):
+        H, W, cin = in_shape
+        kh, kw = self.k
+        self.weights = [glorot_uniform((kh, kw, self.filters, cin), kh * kw * self.filters, kh * kw * cin, gen, dtype),
+                        torch.zeros(self.filters, dtype=dtype, requires_grad=True)]
+        return ((H - 1) * self.s[0] + kh, (W - 1) * self.s[1] + kw, self.filters)
+
+    def forward(self, x, training, noise):        # x (B,H,W,C) NHWC
+        y = F.conv_transpose2d(x.permute(0, 3, 1, 2), self.weights[0].permute(3, 2, 0, 1), self.weights[1], stride=self.s)
+        return apply_activation(y.permute(0, 2, 3, 1), self.activation, _kink(noise, self))
+
+
 class BatchNormalization(Layer):
     """[A5] eps 1e-3, axis -1, batch mean + biased var in training, moving stats in
     inference; moving_var is fed the n/(n-(1+eps)) 'sample variance'."""
@@ -487,7 +510,7 @@ class BranchModel(Sequential):
         return [_np(y) for y in ys]
 
 
-_PREFIX = {Dense: 'dense', Conv1D: 'conv1d', Conv2D: 'conv2d', BatchNormalization: 'batch_normalization',
+_PREFIX = {Dense: 'dense', Conv1D: 'conv1d', Conv2D: 'conv2d', Conv2DTranspose: 'conv2d_transpose', BatchNormalization: 'batch_normalization',
            Activation: 'activation', LeakyReLU: 'leaky_re_lu', ReLU: 're_lu', Dropout: 'dropout',
            GaussianDropout: 'gaussian_dropout', GaussianNoise: 'gaussian_noise', Reshape: 'reshape',
            Flatten: 'flatten', UpSampling1D: 'up_sampling1d', MaxPooling1D: 'max_pooling1d',
@@ -720,6 +743,25 @@ def wvf_get_discriminative(in_dim=8192, drate=.25, n_channels=25, conv_sz=5):
     """train_on_wvf_version/nn.py:83-93."""
     m = Sequential([Reshape((-1, 1)), Conv1D(n_channels, conv_sz, activation='relu'), Dropout(drate), Flatten(),
                     Dense(n_channels), Dense(2, activation='sigmoid')])
+    m.input_shape = (in_dim,)
+    return m
+
+
+def two_model_get_generative(noise_dim=1, out_dim=50):
+    """2_model_version/weight_version/no_mode_collapse_network.py:62-106 (the transposed-convolution network)."""
+    L = [Reshape((-1, 1, 1)), BatchNormalization()]
+    for f, k in ((128, 4), (64, 8), (32, 16), (16, 32)):
+        L += [Conv2DTranspose(f, (1, k), strides=(1, 1), padding='valid', activation='relu'), BatchNormalization()]
+    L += [Flatten(), BatchNormalization(), Dense(out_dim, activation='relu'), BatchNormalization(), Dense(out_dim)]
+    m = Sequential(L)
+    m.input_shape = (1, noise_dim)
+    return m
+
+
+def two_model_get_discriminative(in_dim=50, n_channels=50, conv_sz=16, leak=0.2):
+    """The discriminator stored in 2_model_version/weight_version/d_model.hdf5 (model_config attribute)."""
+    m = Sequential([Reshape((-1, 1)), Conv1D(n_channels, conv_sz), LeakyReLU(leak), Flatten(), Dense(50, activation='tanh'),
+                    Dense(2, activation='sigmoid')])
     m.input_shape = (in_dim,)
     return m
 

@@ -215,6 +215,9 @@ class Fake:
     def gn_gather_rows_f32(self, src, idx, out, n, row_len, st):
         out.reshape(n, row_len).copy_(src.reshape(-1, row_len)[idx.long()])
 
+    def gn_flip_transpose_f32(self, src, out, k, A, Bn, st):
+        out.reshape(k, A, Bn).copy_(src.reshape(k, Bn, A).flip(0).permute(0, 2, 1))
+
     def gn_maxnorm_roll_f32(self, x, off, y, B, N, st):
         xv = x.reshape(B, N)
         for b in range(B):

@@ -268,3 +268,38 @@ def wvf_case(out_dim, B, seed=0):
     yz = np.zeros((B, 2), np.float32)
     yz[:, 1] = 1
     return (G, D, GAN), (og, od, ogan), X, y, z, yz
+
+
+def two_model_case(B, seed=0, out_dim=50):
+    """2_model_version (BASELINE config 5) wiring: transposed-conv generator, Conv1D discriminator, stacked GAN."""
+    from gennet_b200 import nn, twomodel
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(seed)
+    G_in = nn.Input(shape=(1, 1))
+    G, _ = twomodel.get_generative(G_in, out_dim=out_dim, lr=4e-3)
+    D_in = nn.Input(shape=(out_dim,))
+    D, _ = twomodel.get_discriminative(D_in, lr=4e-3)
+    GAN_in = nn.Input((1, 1))
+    GAN, _ = twomodel.make_gan(GAN_in, G, D)
+    og = ko.build(ko.two_model_get_generative(1, out_dim), seed=seed + 1)
+    og.compile('binary_crossentropy', ko.SGD(4e-3))
+    od = ko.build(ko.two_model_get_discriminative(out_dim), seed=seed + 2)
+    od.layers[-2].activation = None          # the script's Dense(n_channels) is linear (the shipped file has tanh)
+    od.compile('binary_crossentropy', ko.Adam(4e-3, beta_1=0.5))
+    ogan = ko.Sequential([og, od])
+    ogan.build((1, 1))
+    ko.set_trainable(od, False)
+    ogan.compile('binary_crossentropy', og.optimizer)
+    ko.set_trainable(od, True)
+    sync_weights(G, og)
+    sync_weights(D, od)
+    rs = np.random.RandomState(seed)
+    X = rs.normal(size=(2 * B, out_dim)).astype(np.float32)
+    y = np.zeros((2 * B, 2), np.float32)
+    y[:B, 1] = 1
+    y[B:, 0] = 1
+    z = rs.uniform(-5, 5, (B, 1, 1)).astype(np.float32)
+    yz = np.zeros((B, 2), np.float32)
+    yz[:, 1] = 1
+    return (G, D, GAN), (og, od, ogan), X, y, z, yz

@@ -134,3 +134,17 @@ def test_keras_hdf5_roundtrip_on_device(tmp_path):
     m2.load_weights(str(tmp_path / 'w.h5'))
     for a, b in zip(prod.get_weights(), m2.get_weights()):
         assert np.array_equal(a, b)
+
+
+def test_two_model_version_parity():
+    """BASELINE config 5 (2_model_version): Conv2DTranspose generator (widths 1->4->11->26->57), Conv1D discriminator:
+    predict, D step, G step through the frozen D -- outputs, losses, every gradient, updates vs the float64 oracle."""
+    (G, D, GAN), (og, od, ogan), X, y, z, yz = pc.two_model_case(16)
+    pc.assert_close(G.predict(z), og.predict(z), 'G.predict')
+    errs, w0 = pc.compare_step(D, od, X, y)
+    pc.compare_weights(D, od, w0)
+    pc.resync([(D, od)])
+    dw = [w.copy() for w in D.get_weights()]
+    errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
+    assert all(np.array_equal(a, b) for a, b in zip(dw, D.get_weights()))
+    pc.compare_weights(G, og, w0[:len(G.get_weights())])

@@ -120,3 +120,19 @@ def test_waveform_ingest_host_logic(fake, tmp_path):
         ref = so.ingest_waveform(np.loadtxt(f), int(p[0] - 256))
         assert np.abs(row - ref).max() < 5e-5          # float32 operator in the stand-in backend
         assert p[1] == 70.0 and -100 <= p[0] - 256 < 100
+
+
+def test_two_model_version_wiring(fake):
+    """BASELINE config 5: Conv2DTranspose generator + Conv1D discriminator, D step then G step through the frozen D."""
+    (G, D, GAN), (og, od, ogan), X, y, z, yz = pc.two_model_case(8)
+    assert G.output_shape == (50,) and G.count_params() == sum(int(np.prod(w.shape)) for w in og.get_weights())
+    widths = [l.output_shape[1] for l in G.layers if type(l).__name__ == 'Conv2DTranspose']
+    assert widths == [4, 11, 26, 57]                              # no_mode_collapse_network.py:79-90
+    pc.assert_close(G.predict(z), og.predict(z), 'G.predict')
+    errs, w0 = pc.compare_step(D, od, X, y)
+    pc.compare_weights(D, od, w0)
+    pc.resync([(D, od)])
+    dw = [w.copy() for w in D.get_weights()]
+    errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
+    assert all(np.array_equal(a, b) for a, b in zip(dw, D.get_weights()))
+    pc.compare_weights(G, og, w0[:len(G.get_weights())])

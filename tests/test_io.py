@@ -237,3 +237,46 @@ def test_writer_encodings_equal_libhdf5_bytes():
     assert W.vlen_str_msg(utf8=False).hex() == '1901000010000000100000000100000000000800'    # attr keras_version
     assert W.space_msg((50,)).hex() == '010101000000000032000000000000003200000000000000'
     assert W.space_msg(()).hex() == '0100000000000000'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DIR), reason='reference checkout not mounted')
+@pytest.mark.parametrize('fname', ['g_model.hdf5', 'd_model.hdf5'])
+def test_load_reference_keras_models(fake, fname):
+    """keras.models.load_model on the two full models the reference ships (Keras 2.1.x files): the architecture is
+    rebuilt from model_config, weights land by Keras' topological order, the optimizer comes back from
+    training_config / optimizer_weights, and predict() agrees with the float64 oracle carrying the same weights."""
+    import torch
+    from gennet_b200 import nn, hdf5
+    from oracle import keras_oracle as ko
+    nn.clear_session()
+    ko.clear_session()
+    m = nn.load_model(os.path.join(REF_DIR, fname))
+    f = hdf5.File(os.path.join(REF_DIR, fname))
+    rs = np.random.RandomState(0)
+    if fname == 'g_model.hdf5':
+        assert [type(l).__name__ for l in m.layers].count('Conv2DTranspose') == 4 and m.output_shape == (50,)
+        assert type(m.optimizer).__name__ == 'SGD' and abs(m.optimizer.lr - 0.004) < 1e-8
+        orc = ko.build(ko.two_model_get_generative(1, 50))
+        x = rs.uniform(-5, 5, (6, 1, 1)).astype(np.float32)
+        k = np.asarray(f['model_weights/conv2d_transpose_2/conv2d_transpose_2/kernel:0'][...])
+        tl = [l for l in m.layers if type(l).__name__ == 'Conv2DTranspose'][1]
+        assert np.array_equal(tl.get_weights()[0], k) and k.shape == (1, 8, 64, 128)          # (kh, kw, Cout, Cin)
+    else:
+        assert type(m.optimizer).__name__ == 'Adam' and m.optimizer.iterations == 2532 and m.optimizer.beta_1 == 0.5
+        orc = ko.build(ko.two_model_get_discriminative(50))
+        x = rs.normal(size=(6, 50)).astype(np.float32)
+        # the file was saved after set_trainability(D, False) (make_gan): every layer comes back frozen, as in Keras,
+        # so there is nothing for the stored Adam moments to attach to until the model is unfrozen and recompiled
+        assert not any(l.trainable for l in m.layers if l.params)
+        from gennet_b200 import io as gio
+        nn.set_trainability(m, True)
+        m.compile(loss='binary_crossentropy', optimizer=m.optimizer)
+        gio._restore_optimizer(m, f['optimizer_weights'])
+        mom = np.asarray(f['optimizer_weights/training/Adam/Variable:0'][...])       # first moment of the conv kernel
+        vel = np.asarray(f['optimizer_weights/training/Adam/Variable_6:0'][...])     # its second moment (6 weights)
+        got_m, got_v = gio._param_slots(m, m.optimizer, m.layers[1].params[0])
+        assert np.array_equal(got_m, mom) and np.array_equal(got_v, vel) and m.optimizer.iterations == 2532
+    orc.set_weights([w.astype(np.float64) for w in m.get_weights()])
+    got, ref = m.predict(x), orc.predict(x)
+    assert got.shape == ref.shape and np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-3)
