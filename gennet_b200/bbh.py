@@ -168,3 +168,40 @@ def gan_train_step(generator, signal_discriminator, signal_discriminator_on_gene
     sd_loss = signal_discriminator.train_on_batch(sX, sy, _noise=_noise_d)           # :1292
     sg_loss = signal_discriminator_on_generator.train_on_batch(z2, torch.ones(B, device=dev), _noise=_noise_g)  # :1296
     return sd_loss, sg_loss
+
+
+def posterior_samples(generator, signal_pe, n=4000, seed=0, batch=1000, z=None):
+    """The evaluation stage of the GAN loop, bbhMahoGANy.py:1311-1343: ``generator.predict`` of ``n`` latents
+    ~U(-1,1)^100 followed by ``signal_pe.predict`` of the generated waveforms, chained on the device (no host round
+    trip between the two networks; latents from the Philox stream unless ``z`` (n,100) is fed in).
+    Returns ``(pe_samples, generated)``: ``pe_samples`` = [mc (n,1), q (n,1)] NumPy arrays as ``signal_pe.predict``
+    gives them, ``generated`` (n, n_pix, 1) NumPy."""
+    dev = nn.device()
+    ctx = nn.Ctx(False)
+    outs, gens = None, []
+    for i in range(0, n, batch):
+        b = min(batch, n - i)
+        if z is None:
+            zz = torch.empty((b, 100), dtype=torch.float32, device=dev)
+            call('gn_uniform_f32', ptr(zz), zz.numel(), -1.0, 1.0, int(seed), int(i) * 100, stream())
+        else:
+            zz = nn._to_device(z[i:i + b])
+        g = generator.forward(zz, ctx)
+        o = signal_pe.forward(g.reshape(b, -1, 1).contiguous(), ctx)
+        o = o if isinstance(o, list) else [o]
+        if outs is None:
+            outs = [[] for _ in o]
+        for k, t in enumerate(o):
+            outs[k].append(t)
+        gens.append(g)
+    pe = [torch.cat(ts, 0).detach().float().cpu().numpy() for ts in outs]
+    return pe, torch.cat(gens, 0).detach().float().cpu().numpy()
+
+
+def waveform_percentiles(generated, percentiles=(90, 75, 25, 5)):
+    """Percentile curves of plot_waveform_est, bbhMahoGANy.py:913-921 (host NumPy, one pass instead of a Python
+    loop over time samples): generated (n, n_pix[, 1]) -> {p: (n_pix,)}."""
+    g = np.asarray(generated)
+    g = g.reshape(g.shape[0], g.shape[1])
+    vals = np.percentile(g, list(percentiles), axis=0)
+    return {p: vals[i] for i, p in enumerate(percentiles)}

@@ -148,3 +148,27 @@ def test_two_model_version_parity():
     errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
     assert all(np.array_equal(a, b) for a, b in zip(dw, D.get_weights()))
     pc.compare_weights(G, og, w0[:len(G.get_weights())])
+
+
+def test_posterior_sampling_chain_on_device():
+    """bbhMahoGANy.py:1311-1343: generator.predict -> signal_pe.predict, chained on the device, equals the two
+    host-level predict calls; the percentile curves equal the reference's per-sample np.percentile loop."""
+    from gennet_b200 import nn, bbh
+    nn.clear_session()
+    nn.set_seed(5)
+    bbh.n_pix = 128
+    g = bbh.generator_model()
+    pe = bbh.signal_pe_model()
+    z = np.random.RandomState(0).uniform(-1, 1, (24, 100)).astype(np.float32)
+    samples, gen = bbh.posterior_samples(g, pe, n=24, batch=10, z=z)
+    gen_ref = g.predict(z)
+    ref = pe.predict(gen_ref.reshape(24, 128, 1))
+    assert np.array_equal(gen, gen_ref)
+    for a, b in zip(samples, ref):
+        assert a.shape == (24, 1) and np.array_equal(a, b)
+    s2, _ = bbh.posterior_samples(g, pe, n=50, seed=3, batch=16)          # Philox latents: batch-size invariant
+    s3, _ = bbh.posterior_samples(g, pe, n=50, seed=3, batch=50)
+    assert np.allclose(s2[0], s3[0], rtol=0, atol=1e-6) and np.allclose(s2[1], s3[1], rtol=0, atol=1e-6)
+    pc_ = bbh.waveform_percentiles(gen)
+    for p in (90, 75, 25, 5):
+        assert np.allclose(pc_[p], [np.percentile(gen[:, n, 0], p) for n in range(128)])
