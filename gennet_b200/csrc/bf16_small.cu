@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
                                                                   const __nv_bfloat16* __restrict__ dy,
                                                                   float* __restrict__ dw, float* __restrict__ db, int B,
                                                                   int L, int Lout, int Cout, int k, int s, int p,
-                                                                  long long rows_per_block) {
+                                                                  long long rows_per_block, int ld, int co0) {
+    // Cout = width of the channel slice handled by this launch (<= 128), ld = channels per dy row, co0 = first channel
     const int groups = Cout / 8;
     const int g = threadIdx.x % groups;
     const int ry = threadIdx.x / groups, nry = blockDim.x / groups;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
     if (ry < nry) {
         for (long long row = r0 + ry; row < r1; row += nry) {
             const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
-            uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * Cout) + g);
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * ld + co0) + g);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
             float gv[8];
 #pragma unroll
@@ -125,8 +126,67 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
         float t = 0.f;
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) t += sm[w8][i][co];
-        if (i < KMAX * CIN) atomicAdd(&dw[(size_t)i * Cout + co], t);
-        else if (db != nullptr) atomicAdd(&db[co], t);
+        if (i < KMAX * CIN) atomicAdd(&dw[(size_t)i * ld + co0 + co], t);
+        else if (db != nullptr) atomicAdd(&db[co0 + co], t);
+    }
+}
+
+// ---- first-layer data gradient: dx f32 (B,L,CIN) from dy bf16 (B,Lout,Cout) and w f32 (k,CIN,Cout) ----------------
+// Needed when the gradient flows on through a Cin <= 2 convolution (generator step through the frozen discriminator,
+// bbhMahoGANy.py:1296).  One warp per dy row: the row (Cout bf16) is read once with 128-bit loads, dotted with the
+// k*CIN weight rows held in shared memory, reduced by shuffles and scattered with k*CIN atomics into dx (zeroed by
+// the caller): HBM traffic = dy once.
+template <int CIN, int KMAX>
+__global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                  const float* __restrict__ w, float* __restrict__ dx,
+                                                                  int B, int L, int Lout, int Cout, int k, int s, int p) {
+    extern __shared__ float sw[];     // k*CIN*Cout
+    const int nw = k * CIN * Cout;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)B * Lout;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0; row < rows; row += nwarps) {
+        const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
+        float acc[KMAX * CIN];
+#pragma unroll
+        for (int i = 0; i < KMAX * CIN; ++i) acc[i] = 0.f;
+        for (int c8 = lane; c8 < Cout / 8; c8 += 32) {
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * Cout) + c8);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+            float gv[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 v = __bfloat1622float2(h[e]);
+                gv[2 * e] = v.x;
+                gv[2 * e + 1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < KMAX * CIN; ++i) {
+                if (i < k * CIN) {
+                    const float* wr = &sw[(size_t)i * Cout + c8 * 8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i] = fmaf(gv[j], wr[j], acc[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KMAX * CIN; ++i) {
+            float v = acc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[i] = v;
+        }
+        if (lane < k * CIN) {
+            const int t = lane / CIN, c = lane - t * CIN;
+            const int pos = l * s + t - p;
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < KMAX * CIN; ++i) v = (i == lane) ? acc[i] : v;
+            if (pos >= 0 && pos < L) atomicAdd(&dx[((size_t)b * L + pos) * CIN + c], v);
+        }
     }
 }
 
@@ -337,8 +397,8 @@ extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, flo
                                              int Lout, int Cout, int k, int stride, int pad_left, void* stream) {
     GN_REQUIRE(x && dy && dw, "null pointer");
     GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 5 && stride > 0 && pad_left >= 0, "bad geometry (k <= 5)");
-    GN_REQUIRE((Cin == 1 || Cin == 2) && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128),
-               "needs Cin in {1,2} and Cout in {8,16,32,64,128}");
+    GN_REQUIRE((Cin == 1 || Cin == 2) && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 2048)),
+               "needs Cin in {1,2} and Cout in {8,16,32,64} or a multiple of 128");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin * Cout, st);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);
@@ -348,13 +408,41 @@ extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, flo
     long long per = (rows + blocks - 1) / blocks;
     if (per < 64) per = 64;
     blocks = (rows + per - 1) / per;
-    if (Cin == 1)
-        conv_smallcin_wgrad_kernel<1, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
-                                                                         Cout, k, stride, pad_left, per);
-    else
-        conv_smallcin_wgrad_kernel<2, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L, Lout,
-                                                                         Cout, k, stride, pad_left, per);
+    // wide layers (the first discriminator convolution has 2*256 packed outputs) go slice by slice of 128 channels
+    const int slice = Cout < 128 ? Cout : 128;
+    for (int co0 = 0; co0 < Cout; co0 += slice) {
+        if (Cin == 1)
+            conv_smallcin_wgrad_kernel<1, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L,
+                                                                             Lout, slice, k, stride, pad_left, per, Cout,
+                                                                             co0);
+        else
+            conv_smallcin_wgrad_kernel<2, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L,
+                                                                             Lout, slice, k, stride, pad_left, per, Cout,
+                                                                             co0);
+    }
     return cuda_status("conv_smallcin_wgrad_kernel");
+}
+
+extern "C" int gn_conv1d_smallcin_dgrad_bf16(const void* dy, const float* w, float* dx, int B, int L, int Cin, int Lout,
+                                             int Cout, int k, int stride, int pad_left, void* stream) {
+    GN_REQUIRE(dy && w && dx, "null pointer");
+    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 5 && stride > 0 && pad_left >= 0, "bad geometry (k <= 5)");
+    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout % 8 == 0, "needs Cin in {1,2} and Cout % 8 == 0");
+    const size_t smem = sizeof(float) * (size_t)k * Cin * Cout;
+    GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * L * Cin, st);
+    if (B == 0) return GN_OK;
+    const long long rows = (long long)B * Lout;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    if (Cin == 1)
+        conv_smallcin_dgrad_kernel<1, 5><<<(unsigned)blocks, 256, smem, st>>>((const __nv_bfloat16*)dy, w, dx, B, L, Lout,
+                                                                            Cout, k, stride, pad_left);
+    else
+        conv_smallcin_dgrad_kernel<2, 5><<<(unsigned)blocks, 256, smem, st>>>((const __nv_bfloat16*)dy, w, dx, B, L, Lout,
+                                                                            Cout, k, stride, pad_left);
+    return cuda_status("conv_smallcin_dgrad_kernel");
 }
 
 extern "C" int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N,

@@ -427,10 +427,9 @@ class Conv1D(Layer):
                 call('gn_conv1d_smallcin_wgrad_bf16', ptr(x), ptr(dy, BF16), ptr(self.params[0].grad),
                      ptr(self.params[1].grad), B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad, stream())
             if need_dx:
-                dyf = _as_f32(dy)
                 dx = _empty(x.shape)
-                call('gn_conv1d_dgrad_f32', ptr(dyf), ptr(self.params[0].data), ptr(dx), B, L, cin, self.Lout,
-                     self.filters, self.k, self.s, self.pad, 1, stream())
+                call('gn_conv1d_smallcin_dgrad_bf16', ptr(dy, BF16), ptr(self.params[0].data), ptr(dx), B, L, cin,
+                     self.Lout, self.filters, self.k, self.s, self.pad, stream())
         else:
             dy = _as_f32(dy.contiguous())
             if tr:
@@ -458,6 +457,8 @@ class Conv2D(Layer):
         self.kh, self.kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
         self.sh, self.sw = (strides, strides) if isinstance(strides, int) else tuple(strides)
         self.padding = padding
+        self.post_act = None     # (code, param) of a following activation layer folded into the epilogue
+        self._wcache = None
 
     def build(self, in_shape):
         H, W, cin = in_shape
@@ -480,35 +481,106 @@ class Conv2D(Layer):
              self.kw, cin, self.filters, self.pw, stream())
         return w1, b1
 
+    def _act(self):
+        return self.post_act if self.post_act is not None else (_lib.ACT_NONE, 0.0)
+
+    def _path(self):
+        """'tc': the packed (L, 2*Cin) -> (Lout, 2*Cout) convolution on the tcgen05 kernels (bf16 mode, channel counts
+        that tile); 'smallcin': first discriminator layer (2*Cin = 2) on the streaming kernels; else float32 SIMT."""
+        H, W, cin = self.input_shape
+        c1, c2 = 2 * cin, 2 * self.filters
+        if _STATE['dtype'] != 'bfloat16' or self.kh > 8 or self.sh > 2:
+            return 'f32'
+        if c1 % 64 == 0 and c2 % 64 == 0 and (c1 % 128 == 0 or (c1 == 64 and c2 % 128 == 0)):
+            return 'tc'
+        if c1 == 2 and c2 % 128 == 0 and c2 <= 1024 and self.kh <= 5:
+            return 'smallcin'
+        return 'f32'
+
+    def _packed_bf16(self):
+        """(w1 f32, b1 f32, wk bf16, wt bf16) of the packed convolution, rebuilt when any weight changed."""
+        if self._wcache is None or self._wcache[0] != _STATE['wver']:
+            H, W, cin = self.input_shape
+            w1, b1 = self._pack()
+            wk = _empty_bf16(tuple(w1.shape))
+            wt = _empty_bf16((self.kh, 2 * self.filters, 2 * cin))
+            call('gn_conv_w_to_bf16', ptr(w1), ptr(wk, BF16), ptr(wt, BF16), self.kh, 2 * cin, 2 * self.filters, stream())
+            self._wcache = (_STATE['wver'], w1, b1, wk, wt)
+        return self._wcache[1:]
+
     def forward(self, x, ctx):
-        x = _as_f32(x)
         B = x.shape[0]
         H, W, cin = self.input_shape
-        w1, b1 = self._pack()
-        y = _empty((B, self.Lout, 2, self.filters))
-        call('gn_conv1d_fwd_f32', ptr(x), ptr(w1), ptr(b1), ptr(y), B, H, 2 * cin, self.Lout, 2 * self.filters,
-             self.kh, self.sh, self.pad, 1, _lib.ACT_NONE, 0.0, stream())
-        self._x, self._w1 = x, w1
+        c1, c2 = 2 * cin, 2 * self.filters
+        code, par = self._act()
+        self._mode = self._path()
+        if self._mode == 'tc':
+            x = _as_bf16(x).contiguous()
+            w1, b1, wk, wt = self._packed_bf16()
+            y = _empty_bf16((B, self.Lout, 2, self.filters))
+            call('gn_conv1d_fwd_bf16', ptr(x, BF16), ptr(wt, BF16), ptr(b1), ptr(y, BF16), B, H, c1, self.Lout, c2,
+                 self.kh, self.sh, self.pad, code, par, stream())
+        elif self._mode == 'smallcin':
+            x = _as_f32(x).contiguous()
+            w1, b1 = self._pack()
+            y = _empty_bf16((B, self.Lout, 2, self.filters))
+            call('gn_conv1d_smallcin_fwd_bf16', ptr(x), ptr(w1), ptr(b1), ptr(y, BF16), B, H, c1, self.Lout, c2, self.kh,
+                 self.sh, self.pad, code, par, stream())
+        else:
+            x = _as_f32(x).contiguous()
+            w1, b1 = self._pack()
+            y = _empty((B, self.Lout, 2, self.filters))
+            call('gn_conv1d_fwd_f32', ptr(x), ptr(w1), ptr(b1), ptr(y), B, H, c1, self.Lout, c2, self.kh, self.sh,
+                 self.pad, 1, code, par, stream())
+        self._x, self._y, self._w1 = x, y, w1
         return y
 
     def backward(self, dy, ctx, need_dx=True):
-        dy = _as_f32(dy)
         x, w1 = self._x, self._w1
         B = x.shape[0]
         H, W, cin = self.input_shape
-        if id(self) in ctx.trainable_ids:
+        c1, c2 = 2 * cin, 2 * self.filters
+        code, par = self._act()
+        if code != _lib.ACT_NONE and not getattr(dy, '_gn_preact', False):
+            dy = _act_bwd(dy.contiguous(), self._y, code, par)
+        tr = id(self) in ctx.trainable_ids
+        dw1 = db1 = None
+        if tr:
             dw1 = _empty(w1.shape)
-            db1 = _empty((2 * self.filters,))
-            call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(dw1), ptr(db1), B, H, 2 * cin, self.Lout,
-                 2 * self.filters, self.kh, self.sh, self.pad, 1, stream())
+            db1 = _empty((c2,))
+        dx = None
+        if self._mode == 'tc':
+            dy = _as_bf16(dy.contiguous())
+            if tr:
+                call('gn_conv1d_wgrad_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(dw1), ptr(db1), B, H, c1, self.Lout, c2,
+                     self.kh, self.sh, self.pad, stream())
+            if need_dx:
+                wk = self._packed_bf16()[2]
+                dx = _empty_bf16(x.shape)
+                call('gn_conv1d_dgrad_bf16', ptr(dy, BF16), ptr(wk, BF16), None, ptr(dx, BF16), None, B, H, c1, self.Lout,
+                     c2, self.kh, self.sh, self.pad, _lib.ACT_NONE, 0.0, stream())
+        elif self._mode == 'smallcin':
+            dy = _as_bf16(dy.contiguous())
+            if tr:
+                call('gn_conv1d_smallcin_wgrad_bf16', ptr(x), ptr(dy, BF16), ptr(dw1), ptr(db1), B, H, c1, self.Lout, c2,
+                     self.kh, self.sh, self.pad, stream())
+            if need_dx:
+                dx = _empty(x.shape)
+                call('gn_conv1d_smallcin_dgrad_bf16', ptr(dy, BF16), ptr(w1), ptr(dx), B, H, c1, self.Lout, c2, self.kh,
+                     self.sh, self.pad, stream())
+        else:
+            dy = _as_f32(dy.contiguous())
+            if tr:
+                call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(dw1), ptr(db1), B, H, c1, self.Lout, c2, self.kh,
+                     self.sh, self.pad, 1, stream())
+            if need_dx:
+                dx = _empty(x.shape)
+                call('gn_conv1d_dgrad_f32', ptr(dy), ptr(w1), ptr(dx), B, H, c1, self.Lout, c2, self.kh, self.sh,
+                     self.pad, 1, stream())
+        if tr:
             call('gn_conv2d_w2_unpack_f32', ptr(dw1), ptr(db1), ptr(self.params[0].grad), ptr(self.params[1].grad),
                  self.kh, self.kw, cin, self.filters, self.pw, stream())
-        dx = None
-        if need_dx:
-            dx = _empty(x.shape)
-            call('gn_conv1d_dgrad_f32', ptr(dy), ptr(w1), ptr(dx), B, H, 2 * cin, self.Lout, 2 * self.filters,
-                 self.kh, self.sh, self.pad, 1, stream())
-        self._x = self._w1 = None
+        self._x = self._y = self._w1 = None
         return dx
 
 
@@ -1046,7 +1118,8 @@ class Model(Layer):
                     u[0].layer.fused_up = 2
         # Conv1D -> (Activation | LeakyReLU | ReLU) with a single user: the activation runs in the conv epilogue
         for n in self._order:
-            if type(n.layer) is Conv1D and n.layer.activation is None and n not in self._out_nodes:
+            if type(n.layer) in (Conv1D, Conv2D) and getattr(n.layer, 'activation', None) is None \
+                    and n not in self._out_nodes:
                 u = users.get(id(n), [])
                 if len(u) == 1 and isinstance(u[0].layer, _ActLayer) and u[0].layer.code != _lib.ACT_NONE:
                     n.layer.post_act = (u[0].layer.code, u[0].layer.param)

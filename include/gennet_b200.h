@@ -152,7 +152,8 @@ int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, in
 
 /* Bandwidth-bound companions of the bf16 path.
  *   smallcin fwd  : first convolution of a network, Cin in {1,2}: x f32 (B,L,Cin) -> y bf16 (B,Lout,Cout), bias+act fused
- *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 5, Cout in {8,..,128})
+ *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 5, Cout in {8,16,32,64}
+ *                   or a multiple of 128)
  *   dense_small_* : Dense with N <= 4 outputs over bf16 features (K % 8 == 0): fwd y f32 (M,N); dgrad dx bf16 (M,K)
  *                   = act'(x_in) * dy w^T (x_in = the layer's input or NULL), dx_colsum f32 (colsum_channels)
  *                   OVERWRITTEN or NULL: sum of dx over rows and over features k with equal k % colsum_channels
@@ -164,6 +165,10 @@ int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const float* bia
                                 void* stream);
 int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
                                   int Cout, int k, int stride, int pad_left, void* stream);
+/* data gradient of a Cin in {1,2} convolution: dx f32 (B,L,Cin) OVERWRITTEN from dy bf16 (B,Lout,Cout) and w f32
+ * (k,Cin,Cout), k <= 5 (generator step through the frozen discriminator's first layer, bbhMahoGANy.py:1296) */
+int gn_conv1d_smallcin_dgrad_bf16(const void* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int Cout,
+                                  int k, int stride, int pad_left, void* stream);
 int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N, int act,
                             float act_param, void* stream);
 int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, float* dx_colsum,

@@ -95,7 +95,7 @@ def test_tc_conv_fwd_dgrad_wgrad(case):
 
 
 @pytest.mark.parametrize('case', [(3, 200, 1, 64, 5, 2, 'same'), (2, 256, 1, 64, 5, 1, 'same'), (2, 100, 2, 128, 5, 2, 'same'),
-                                  (2, 77, 1, 32, 3, 1, 'valid')])
+                                  (2, 77, 1, 32, 3, 1, 'valid'), (3, 128, 2, 512, 5, 2, 'same')])
 def test_first_layer_kernels(case):
     from gennet_b200 import _lib as L_
     B, L, Cin, Cout, k, s, padding = case
@@ -127,6 +127,17 @@ def test_first_layer_kernels(case):
             k, s, pad, st)
     assert_close(dw.cpu().numpy(), wr.grad.numpy(), 'smallcin wgrad', 1e-4)
     assert_close(db.cpu().numpy(), br.grad.numpy(), 'smallcin bias grad', 1e-4)
+    # data gradient through the small-Cin convolution (generator step through the frozen discriminator)
+    xg = x.cpu().double().requires_grad_(True)
+    xpg = xg.permute(0, 2, 1)
+    if padding == 'same':
+        xpg = F.pad(xpg, (pl, pr))
+    yg = F.conv1d(xpg, wr.detach().permute(2, 1, 0), br.detach(), stride=s).permute(0, 2, 1)
+    (yg * dy.float().cpu().double()).sum().backward()
+    dx = torch.full((B, L, Cin), float('nan'), device='cuda')
+    L_.call('gn_conv1d_smallcin_dgrad_bf16', L_.ptr(dy, torch.bfloat16), L_.ptr(w), L_.ptr(dx), B, L, Cin, Lout, Cout, k, s,
+            pad, st)
+    assert_close(dx.cpu().numpy(), xg.grad.numpy(), 'smallcin dgrad', 1e-5)
 
 
 @pytest.mark.parametrize('M,K,N', [(5, 64000, 1), (3, 4096, 2), (9, 1000 * 8, 4)])
