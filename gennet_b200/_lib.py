@@ -43,6 +43,11 @@ _SIGS = {
     'gn_conv1d_smallcin_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_smallcin_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_dgrad_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_cout1_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_cout1_dgrad_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_cout1_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_upsample1d_fwd_bf16': [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    'gn_upsample1d_bwd_bf16': [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_dense_small_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_dense_small_dgrad_bf16': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_dense_small_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],

@@ -369,9 +369,271 @@ __global__ void __launch_bounds__(256) act_bwd_bf16_kernel(const __nv_bfloat16* 
         dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * act_bwd_from_y(__bfloat162float(y[i]), act, ap));
 }
 
+// ---- UpSampling1D on bf16 activations (generator, bbhMahoGANy.py:248,258): y[b, j, :] = x[b, j / size, :] and its
+// adjoint dx[b, l, :] = sum_r dy[b, l*size + r, :]; 8 channels (16 bytes) per thread
+__global__ void __launch_bounds__(256) upsample_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            long long rows_out, int L, int C8, int size) {
+    const long long total = rows_out * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        const long long r = i / C8;                 // output row = b * (L*size) + j
+        const long long b = r / ((long long)L * size);
+        const int j = (int)(r - b * (long long)L * size);
+        reinterpret_cast<uint4*>(y)[i] = __ldg(reinterpret_cast<const uint4*>(x) + (b * L + j / size) * C8 + c);
+    }
+}
+__global__ void __launch_bounds__(256) upsample_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                __nv_bfloat16* __restrict__ dx, long long rows_in, int C8,
+                                                                int size) {
+    const long long total = rows_in * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        const long long r = i / C8;                 // input row = b * L + l ; its copies are rows r*size .. r*size+size-1
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int q = 0; q < size; ++q) {
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy) + (r * size + q) * C8 + c);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 v = __bfloat1622float2(h[e]);
+                acc[2 * e] += v.x;
+                acc[2 * e + 1] += v.y;
+            }
+        }
+        __nv_bfloat162 o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+        reinterpret_cast<uint4*>(dx)[i] = *reinterpret_cast<uint4*>(o);
+    }
+}
+
+// ---- last convolution of the generator: Cout = 1, stride 1 (bbhMahoGANy.py:291).  With one output channel the layer
+// is five dot products per input row: tap t of row pos contributes d_t = <x[b,pos,:], w[t,:]> to y[b, pos - t + p].
+// fwd: one warp per input row, 128-bit loads, shuffle reduction, k atomics into y (zeroed by the caller; the centre
+// tap carries the bias).  dgrad: dx[b,pos,:] = sum_t dy[b,pos-t+p] w[t,:] streamed out row by row.  wgrad:
+// dw[t,:] = sum_rows x[row,:] dy[row shifted by t]; thread = 8 channels, a slice of the rows, atomics across slices.
+template <int KMAX>
+__global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y, int B,
+                                                             int L, int Lout, int Cin, int k, int p) {
+    extern __shared__ float sw[];     // k*Cin
+    for (int i = threadIdx.x; i < k * Cin; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)B * L;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float bv = bias ? bias[0] : 0.f;
+    for (long long row = warp0; row < rows; row += nwarps) {
+        const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+        float acc[KMAX];
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) acc[t] = 0.f;
+        for (int c8 = lane; c8 < Cin / 8; c8 += 32) {
+            uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * Cin) + c8);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+            float xv[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 v = __bfloat1622float2(h[e]);
+                xv[2 * e] = v.x;
+                xv[2 * e + 1] = v.y;
+            }
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) {
+                if (t < k) {
+                    const float* wr = &sw[t * Cin + c8 * 8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[t] = fmaf(xv[j], wr[j], acc[t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+            float v = acc[t];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[t] = v;
+        }
+        if (lane < k) {
+            float v = 0.f;
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) v = (t == lane) ? acc[t] : v;
+            const int l = pos - lane + p;
+            if (l >= 0 && l < Lout) atomicAdd(&y[(size_t)b * Lout + l], v + (lane == p ? bv : 0.f));
+        }
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) conv_cout1_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ dx, int B, int L, int Lout,
+                                                               int Cin, int k, int p) {
+    const int C8 = Cin / 8;
+    const long long total = (long long)B * L * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        const long long row = i / C8;
+        const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+            if (t < k) {
+                const int l = pos - t + p;
+                if (l >= 0 && l < Lout) {
+                    const float g = __ldg(&dy[(size_t)b * Lout + l]);
+                    const float4* wp = reinterpret_cast<const float4*>(w + (size_t)t * Cin + c * 8);
+                    const float4 w0 = __ldg(&wp[0]), w1 = __ldg(&wp[1]);
+                    o[0] = fmaf(g, w0.x, o[0]); o[1] = fmaf(g, w0.y, o[1]); o[2] = fmaf(g, w0.z, o[2]); o[3] = fmaf(g, w0.w, o[3]);
+                    o[4] = fmaf(g, w1.x, o[4]); o[5] = fmaf(g, w1.y, o[5]); o[6] = fmaf(g, w1.z, o[6]); o[7] = fmaf(g, w1.w, o[7]);
+                }
+            }
+        }
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+        reinterpret_cast<uint4*>(dx)[i] = *reinterpret_cast<uint4*>(h);
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) conv_cout1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dw, int B, int L, int Lout, int Cin, int k,
+                                                               int p, long long rows_per_split) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;   // chunk of 8 channels
+    if (c >= Cin / 8) return;
+    const long long rows = (long long)B * L;
+    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
+    float acc[KMAX][8];
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+#pragma unroll 2
+    for (long long row = r0; row < r1; ++row) {
+        const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+        uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * Cin) + c);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        float xv[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 v = __bfloat1622float2(h[e]);
+            xv[2 * e] = v.x;
+            xv[2 * e + 1] = v.y;
+        }
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+            if (t < k) {
+                const int l = pos - t + p;
+                const float g = (l >= 0 && l < Lout) ? __ldg(&dy[(size_t)b * Lout + l]) : 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(xv[e], g, acc[t][e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t)
+        if (t < k)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&dw[(size_t)t * Cin + c * 8 + e], acc[t][e]);
+}
+
+__global__ void __launch_bounds__(1024) sum_all_kernel(const float* __restrict__ x, long long n, float* out) {
+    __shared__ float sm[32];
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    float t = block_sum(s, sm);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
 }  // namespace gn
 
 using namespace gn;
+
+extern "C" int gn_upsample1d_fwd_bf16(const void* x, void* y, int B, int L, int C, int size, void* stream) {
+    GN_REQUIRE(x && y && B >= 0 && L > 0 && C > 0 && C % 8 == 0 && size >= 1, "null pointer or bad size (C % 8 == 0)");
+    if (B == 0) return GN_OK;
+    const long long rows = (long long)B * L * size, total = rows * (C / 8);
+    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    upsample_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, rows, L, C / 8, size);
+    return cuda_status("upsample_bf16_kernel");
+}
+
+extern "C" int gn_upsample1d_bwd_bf16(const void* dy, void* dx, int B, int L, int C, int size, void* stream) {
+    GN_REQUIRE(dy && dx && B >= 0 && L > 0 && C > 0 && C % 8 == 0 && size >= 1, "null pointer or bad size (C % 8 == 0)");
+    if (B == 0) return GN_OK;
+    const long long rows = (long long)B * L, total = rows * (C / 8);
+    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    upsample_bwd_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, rows, C / 8, size);
+    return cuda_status("upsample_bwd_bf16_kernel");
+}
+
+static int check_cout1(int B, int L, int Cin, int Lout, int k, int p) {
+    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && Cin > 0 && Cin % 8 == 0 && k > 0 && k <= 5 && p >= 0 && p < k,
+               "needs Cin % 8 == 0, k <= 5, stride 1");
+    GN_REQUIRE(Lout <= L + k - 1, "Lout too large for L");
+    return GN_OK;
+}
+
+extern "C" int gn_conv1d_cout1_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int B, int L, int Cin,
+                                        int Lout, int k, int pad_left, void* stream) {
+    GN_REQUIRE(x && w && y, "null pointer");
+    int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
+    if (rc != GN_OK) return rc;
+    const size_t smem = sizeof(float) * (size_t)k * Cin;
+    GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(y, 0, sizeof(float) * (size_t)B * Lout, st);
+    if (B == 0) return GN_OK;
+    const long long rows = (long long)B * L;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    conv_cout1_fwd_kernel<5><<<(unsigned)blocks, 256, smem, st>>>((const __nv_bfloat16*)x, w, bias, y, B, L, Lout, Cin, k,
+                                                                pad_left);
+    return cuda_status("conv_cout1_fwd_kernel");
+}
+
+extern "C" int gn_conv1d_cout1_dgrad_bf16(const float* dy, const float* w, void* dx, int B, int L, int Cin, int Lout, int k,
+                                          int pad_left, void* stream) {
+    GN_REQUIRE(dy && w && dx, "null pointer");
+    int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
+    if (rc != GN_OK) return rc;
+    if (B == 0) return GN_OK;
+    const long long total = (long long)B * L * (Cin / 8);
+    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    conv_cout1_dgrad_kernel<5><<<grid, 256, 0, as_stream(stream)>>>(dy, w, (__nv_bfloat16*)dx, B, L, Lout, Cin, k, pad_left);
+    return cuda_status("conv_cout1_dgrad_kernel");
+}
+
+extern "C" int gn_conv1d_cout1_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int B, int L, int Cin,
+                                          int Lout, int k, int pad_left, void* stream) {
+    GN_REQUIRE(x && dy && dw, "null pointer");
+    int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
+    if (rc != GN_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin, st);
+    if (B > 0) {
+        const long long rows = (long long)B * L;
+        const int bx = (Cin / 8 + 255) / 256;
+        long long splits = (4LL * num_sms() * 8 + bx - 1) / bx;      // blocks are only Cin/8 threads wide
+        if (Cin / 8 < 256) splits = splits * 256 / (Cin / 8);
+        if (splits > rows) splits = rows;
+        if (splits > 65535) splits = 65535;
+        if (splits < 1) splits = 1;
+        long long per = (rows + splits - 1) / splits;
+        splits = (rows + per - 1) / per;
+        const int threads = Cin / 8 < 256 ? ((Cin / 8 + 31) / 32) * 32 : 256;
+        dim3 grid((Cin / 8 + threads - 1) / threads, (unsigned)splits);
+        conv_cout1_wgrad_kernel<5><<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, dy, dw, B, L, Lout, Cin, k, pad_left, per);
+    }
+    if (db != nullptr) sum_all_kernel<<<1, 1024, 0, st>>>(dy, (long long)B * Lout, db);
+    return cuda_status("conv_cout1_wgrad_kernel");
+}
+
 
 extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const float* bias, void* y, int B, int L,
                                            int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,

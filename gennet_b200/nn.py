@@ -353,12 +353,16 @@ class Conv1D(Layer):
     def _path(self):
         L, cin = self.input_shape
         co = self.filters
-        if _STATE['dtype'] != 'bfloat16' or self.fused_up != 1 or self.k > 8 or self.s > 2:
+        if _STATE['dtype'] != 'bfloat16' or self.k > 8 or self.s > 2:
             return 'f32'
         if cin % 64 == 0 and co % 64 == 0 and (cin % 128 == 0 or (cin == 64 and co % 128 == 0)):
-            return 'tc'
-        if cin <= 2 and co in (8, 16, 32, 64, 128) and self.k <= 5:
+            return 'tc'          # a fused UpSampling1D(2) is materialised in bf16 first (cheap next to the GEMM)
+        if self.fused_up != 1:
+            return 'f32'
+        if cin <= 2 and (co in (8, 16, 32, 64) or (co % 128 == 0 and co <= 1024)) and self.k <= 5:
             return 'smallcin'
+        if co == 1 and self.s == 1 and self.k <= 5 and cin % 8 == 0 and self._act()[0] == _lib.ACT_NONE:
+            return 'cout1'
         return 'f32'
 
     def _bf16_weights(self):
@@ -378,10 +382,20 @@ class Conv1D(Layer):
         self._mode = self._path()
         if self._mode == 'tc':
             x = _as_bf16(x)
+            if self.fused_up != 1:
+                xu = _empty_bf16((B, L, cin))
+                call('gn_upsample1d_fwd_bf16', ptr(x.contiguous(), BF16), ptr(xu, BF16), B, L // self.fused_up, cin,
+                     self.fused_up, stream())
+                x = xu
             wk, wt = self._bf16_weights()
             y = _empty_bf16((B, self.Lout, self.filters))
             call('gn_conv1d_fwd_bf16', ptr(x, BF16), ptr(wt, BF16), ptr(self.params[1].data), ptr(y, BF16), B, L, cin,
                  self.Lout, self.filters, self.k, self.s, self.pad, code, par, stream())
+        elif self._mode == 'cout1':
+            x = _as_bf16(x).contiguous()
+            y = _empty((B, self.Lout, 1))
+            call('gn_conv1d_cout1_fwd_bf16', ptr(x, BF16), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B,
+                 L, cin, self.Lout, self.k, self.pad, stream())
         elif self._mode == 'smallcin':
             x = _as_f32(x)
             y = _empty_bf16((B, self.Lout, self.filters))
@@ -419,8 +433,22 @@ class Conv1D(Layer):
                 sink, _ = _bias_sink(self, ctx, cin)
                 call('gn_conv1d_dgrad_bf16', ptr(dy, BF16), ptr(wk, BF16), ptr(x, BF16), ptr(dx, BF16), sink, B, L, cin,
                      self.Lout, self.filters, self.k, self.s, self.pad, icode, ipar, stream())
+                if self.fused_up != 1:
+                    dxp = _empty_bf16((B, L // self.fused_up, cin))
+                    call('gn_upsample1d_bwd_bf16', ptr(dx, BF16), ptr(dxp, BF16), B, L // self.fused_up, cin,
+                         self.fused_up, stream())
+                    dx = dxp
                 dx._gn_preact = self.in_act is not None
                 dx._gn_db_done = sink is not None
+        elif self._mode == 'cout1':
+            dy = _as_f32(dy).contiguous()
+            if tr:
+                call('gn_conv1d_cout1_wgrad_bf16', ptr(x, BF16), ptr(dy), ptr(self.params[0].grad),
+                     ptr(self.params[1].grad), B, L, cin, self.Lout, self.k, self.pad, stream())
+            if need_dx:
+                dx = _empty_bf16(x.shape)
+                call('gn_conv1d_cout1_dgrad_bf16', ptr(dy), ptr(self.params[0].data), ptr(dx, BF16), B, L, cin, self.Lout,
+                     self.k, self.pad, stream())
         elif self._mode == 'smallcin':
             dy = _as_bf16(dy.contiguous())
             if tr:

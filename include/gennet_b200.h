@@ -169,6 +169,18 @@ int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, flo
  * (k,Cin,Cout), k <= 5 (generator step through the frozen discriminator's first layer, bbhMahoGANy.py:1296) */
 int gn_conv1d_smallcin_dgrad_bf16(const void* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int Cout,
                                   int k, int stride, int pad_left, void* stream);
+/* last convolution of the generator (Cout = 1, stride 1, k <= 5; bbhMahoGANy.py:291): x bf16 (B,L,Cin) -> y f32 (B,Lout)
+ * OVERWRITTEN (bias added, no activation); dgrad dy f32 (B,Lout) -> dx bf16 (B,L,Cin); wgrad dw f32 (k,Cin), db f32 (1)
+ * OVERWRITTEN.  One pass over the big operand each. */
+int gn_conv1d_cout1_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int B, int L, int Cin, int Lout,
+                             int k, int pad_left, void* stream);
+int gn_conv1d_cout1_dgrad_bf16(const float* dy, const float* w, void* dx, int B, int L, int Cin, int Lout, int k,
+                               int pad_left, void* stream);
+int gn_conv1d_cout1_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout, int k,
+                               int pad_left, void* stream);
+/* UpSampling1D on bf16 activations (C % 8 == 0): y (B, L*size, C) from x (B, L, C); bwd sums the `size` copies */
+int gn_upsample1d_fwd_bf16(const void* x, void* y, int B, int L, int C, int size, void* stream);
+int gn_upsample1d_bwd_bf16(const void* dy, void* dx, int B, int L, int C, int size, void* stream);
 int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N, int act,
                             float act_param, void* stream);
 int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, float* dx_colsum,

@@ -170,3 +170,55 @@ def test_dense_small_bf16(M, K, N):
     L_.call('gn_dense_small_wgrad_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(dy), L_.ptr(dw), L_.ptr(db), M, K, N, st)
     assert_close(dw.cpu().numpy(), (xr.t() @ dy.cpu().double()).numpy(), 'dense small wgrad', 1e-5)
     assert_close(db.cpu().numpy(), dy.cpu().double().sum(0).numpy(), 'dense small bias grad', 1e-6)
+
+
+@pytest.mark.parametrize('case', [(3, 300, 1024, 5, 'same'), (2, 97, 64, 5, 'valid'), (2, 64, 256, 3, 'same')])
+def test_cout1_conv_kernels(case):
+    """Last generator convolution (Cout = 1, stride 1): fwd / dgrad / wgrad vs torch float64 on bf16-rounded inputs."""
+    from gennet_b200 import _lib as L_
+    B, L, Cin, k, padding = case
+    rs = np.random.RandomState(abs(hash(case)) % 2 ** 31)
+    x = bf(rs.normal(size=(B, L, Cin)))
+    w = torch.as_tensor((rs.normal(size=(k, Cin, 1)) / math.sqrt(k * Cin)).astype(np.float32)).cuda()
+    bias = torch.as_tensor(rs.normal(size=1).astype(np.float32)).cuda()
+    xr = x.float().cpu().double().requires_grad_(True)
+    wr = w.cpu().double().requires_grad_(True)
+    br = bias.cpu().double().requires_grad_(True)
+    xp = xr.permute(0, 2, 1)
+    pad = 0
+    if padding == 'same':
+        pl, pr = ko.same_pad(L, k, 1)
+        xp = F.pad(xp, (pl, pr))
+        pad = pl
+    yr = F.conv1d(xp, wr.permute(2, 1, 0), br).permute(0, 2, 1)
+    Lout = yr.shape[1]
+    st = L_.stream()
+    y = torch.full((B, Lout, 1), float('nan'), device='cuda')
+    L_.call('gn_conv1d_cout1_fwd_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(w), L_.ptr(bias), L_.ptr(y), B, L, Cin, Lout, k, pad, st)
+    assert_close(y.cpu().numpy(), yr.detach().numpy(), 'cout1 fwd', 1e-5)
+    dy = torch.as_tensor(rs.normal(size=(B, Lout, 1)).astype(np.float32)).cuda()
+    (yr * dy.cpu().double()).sum().backward()
+    dx = torch.full((B, L, Cin), float('nan'), dtype=torch.bfloat16, device='cuda')
+    L_.call('gn_conv1d_cout1_dgrad_bf16', L_.ptr(dy), L_.ptr(w), L_.ptr(dx, torch.bfloat16), B, L, Cin, Lout, k, pad, st)
+    assert_close(dx.float().cpu().numpy(), xr.grad.numpy(), 'cout1 dgrad', 2 ** -8)
+    dw = torch.full((k, Cin, 1), float('nan'), device='cuda')
+    db = torch.full((1,), float('nan'), device='cuda')
+    L_.call('gn_conv1d_cout1_wgrad_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(dy), L_.ptr(dw), L_.ptr(db), B, L, Cin, Lout, k, pad, st)
+    assert_close(dw.cpu().numpy(), wr.grad.numpy(), 'cout1 wgrad', 1e-5)
+    assert_close(db.cpu().numpy(), br.grad.numpy(), 'cout1 bias grad', 1e-5)
+
+
+def test_upsample_bf16_kernels():
+    from gennet_b200 import _lib as L_
+    rs = np.random.RandomState(0)
+    B, L, C = 3, 37, 64
+    x = bf(rs.normal(size=(B, L, C)))
+    y = torch.empty(B, 2 * L, C, dtype=torch.bfloat16, device='cuda')
+    st = L_.stream()
+    L_.call('gn_upsample1d_fwd_bf16', L_.ptr(x, torch.bfloat16), L_.ptr(y, torch.bfloat16), B, L, C, 2, st)
+    assert torch.equal(y, x.repeat_interleave(2, dim=1))
+    dy = bf(rs.normal(size=(B, 2 * L, C)))
+    dx = torch.empty(B, L, C, dtype=torch.bfloat16, device='cuda')
+    L_.call('gn_upsample1d_bwd_bf16', L_.ptr(dy, torch.bfloat16), L_.ptr(dx, torch.bfloat16), B, L, C, 2, st)
+    ref = dy.float().reshape(B, L, 2, C).sum(2)
+    assert_close(dx.float().cpu().numpy(), ref.cpu().numpy(), 'upsample bwd', 2 ** -8)

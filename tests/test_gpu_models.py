@@ -115,6 +115,44 @@ def test_pe_step_bf16_within_stated_tolerance():
         nn.set_compute_dtype('float32')
 
 
+def test_gan_steps_bf16_within_stated_tolerance():
+    """Throughput mode on the GAN of bbhMahoGANy.py (BASELINE config 3): generator convolutions (UpSampling folded,
+    Cout = 1 tail) and the discriminator's packed Conv2D layers on the tensor-core / streaming bf16 kernels.
+    Stated tolerance vs the float64 oracle (same as the PE test): outputs 2e-2 of scale, losses 3e-2 (+1e-4), gradients
+    1e-1 relative L2 / 3e-1 of max.  Dropout masks are fed; BatchNorm runs in float32 between the bf16 convolutions."""
+    from gennet_b200 import nn
+    try:
+        nn.set_compute_dtype('bfloat16')
+        (g, d, dg), (og, od, ocomp), z, sX, sy = pc.gan_case(256, 8)
+        a, b = g.predict(z), og.predict(z)
+        assert np.abs(a - b).max() <= 2e-2 * np.abs(b).max()
+        a, b = d.predict(sX), od.predict(sX)
+        assert np.abs(a - b).max() <= 2e-2 * max(np.abs(b).max(), 1e-6)
+
+        def step(prod, orc, x, y, seed):
+            noise = pc.draw_noise(orc, x, seed)
+            rp = prod.train_on_batch(x, y, _noise=pc.map_noise(noise, orc, prod))
+            ro = orc.train_on_batch(x, y, noise=dict(noise))
+            assert np.allclose(rp[0], ro[0], rtol=3e-2, atol=1e-4), (rp, ro)
+            gp = prod.get_gradients()
+            gmax = max(np.abs(q).max() for q in orc.last_grads)
+            assert len(gp) == len(orc.last_grads)
+            for i, (p_, q) in enumerate(zip(gp, orc.last_grads)):
+                # biases in front of BatchNorm have structurally zero gradients: compare those against 1e-2 of the
+                # largest gradient of the step instead of their own rounding noise
+                el2 = np.linalg.norm((p_ - q).ravel()) / max(np.linalg.norm(q.ravel()), 1e-2 * gmax * np.sqrt(q.size))
+                emax = np.abs(p_ - q).max() / max(np.abs(q).max(), 1e-2 * gmax)
+                assert np.isfinite(p_).all() and el2 <= 1e-1 and emax <= 3e-1, (i, q.shape, el2, emax)
+        step(d, od, sX, sy, 0)
+        pc.resync([(d, od)])
+        step(dg, ocomp, z, [1] * 8, 1)
+        convs = [l for l in g.all_layers() if isinstance(l, nn.Conv1D)]
+        assert [c._path() for c in convs] == ['tc', 'tc', 'tc', 'tc', 'tc', 'cout1']
+        assert [l._path() for l in d.all_layers() if isinstance(l, nn.Conv2D)] == ['smallcin', 'tc']
+    finally:
+        nn.set_compute_dtype('float32')
+
+
 @pytest.mark.gpu
 def test_keras_hdf5_roundtrip_on_device(tmp_path):
     """save -> load_model on the GPU path: identical predictions, optimizer state carried over (bbhMahoGANy.py:1173,1135)."""
