@@ -62,6 +62,10 @@ _SIGS = {
     'gn_bn_apply_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_i, c_p],
     'gn_bn_bwd_sums_f32': [c_p, c_p, c_p, c_ll, c_i, c_p, c_p],
     'gn_bn_bwd_apply_f32': [c_p, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_ll, c_i, c_p],
+    'gn_bn_stats_bf16': [c_p, c_ll, c_i, c_p, c_p],
+    'gn_chain_fwd_bf16': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p],
+    'gn_chain_bwd_sums_bf16': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p, c_p],
+    'gn_chain_bwd_bf16': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_p, c_p, c_ll, c_i, c_p],
     'gn_act_fwd_f32': [c_p, c_p, c_ll, c_i, c_f, c_p],
     'gn_act_bwd_f32': [c_p, c_p, c_p, c_ll, c_i, c_f, c_p],
     'gn_noise_fwd_f32': [c_p, c_p, c_p, c_ll, c_i, c_f, c_p],

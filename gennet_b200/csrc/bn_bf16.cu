@@ -1,0 +1,332 @@
+// BatchNormalization -> activation -> dropout chains on bf16 activations (throughput mode of the generator,
+// bbhMahoGANy.py:235-289: every hidden layer is Conv1D/Dense -> BatchNormalization(momentum) -> tanh -> Dropout).
+// In float32 mode each of those layers is its own exact kernel; here the chain is three streaming passes:
+//   forward :  per-channel sum / sum of squares of x (one pass)  ->  y = drop(act(gamma * xhat + beta))  (one pass)
+//   backward:  g = dy * drop' * act'(a) recomputed from x;  per-channel sum g, sum g*xhat (one pass)  ->
+//              dx = gamma * invstd * (g - sum_g/n - xhat * sum_gxhat/n), dgamma, dbeta (one pass)
+// Nothing but x, y and dx touches HBM: the activation output a and the dropout mask are recomputed (the mask from
+// the Philox counter of gn_noise_draw_f32, so fused and unfused runs draw identical masks), all arithmetic is fp32,
+// statistics accumulate in double.  Thread = 8 consecutive channels (one 128-bit access).
+#include "gn_common.cuh"
+#include "philox.cuh"
+
+#include <cuda_bf16.h>
+
+namespace gn {
+
+struct ChainArgs {
+    const float* mean;        // (C) batch or moving mean; null = no normalisation (pure activation / noise)
+    const float* scale;       // (C) 1/sqrt(var+eps), or the variance when use_var
+    const float* gamma;       // (C)
+    const float* beta;        // (C)
+    int use_var;
+    float eps;
+    int act;
+    float act_param;
+    int noise;                // -1 none, else GN_NOISE_*
+    float rate;
+    const float* r;           // fed noise tensor (rows*C) or null = Philox(seed, offset)
+    unsigned long long seed, offset;
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 pk = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h[e]);
+        v[2 * e] = f.x;
+        v[2 * e + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+}
+
+// multiplicative noise factors of the 8 elements starting at flat index i0 (i0 % 8 == 0); GaussianNoise (additive) is
+// not a factor and is not handled by the chain
+__device__ __forceinline__ void noise_factors(const ChainArgs& a, long long i0, float (&f)[8]) {
+    if (a.noise < 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 1.f;
+        return;
+    }
+    float rv[8];
+    if (a.r != nullptr) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.r + i0));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.r + i0) + 1);
+        rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+    } else {
+        // same stream as gn_noise_draw_f32 (rng_fill_kernel, stream id 3): block (offset + i) / 4, 4 values per block
+        const unsigned long long blk = (a.offset + (unsigned long long)i0) >> 2;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint4 u = philox_flat(a.seed, blk + q, 3u);
+            if (a.noise == GN_NOISE_DROPOUT) {
+                rv[4 * q + 0] = u01(u.x) >= a.rate ? 1.f : 0.f;
+                rv[4 * q + 1] = u01(u.y) >= a.rate ? 1.f : 0.f;
+                rv[4 * q + 2] = u01(u.z) >= a.rate ? 1.f : 0.f;
+                rv[4 * q + 3] = u01(u.w) >= a.rate ? 1.f : 0.f;
+            } else {
+                const float2 g0 = box_muller(u.x, u.y), g1 = box_muller(u.z, u.w);
+                rv[4 * q + 0] = g0.x; rv[4 * q + 1] = g0.y; rv[4 * q + 2] = g1.x; rv[4 * q + 3] = g1.y;
+            }
+        }
+    }
+    if (a.noise == GN_NOISE_DROPOUT) {
+        const float k = 1.f / (1.f - a.rate);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = rv[e] * k;
+    } else {
+        const float sd = sqrtf(a.rate / (1.f - a.rate));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(rv[e], sd, 1.f);
+    }
+}
+
+// per-channel affine of the normalisation for the 8 channels starting at c0:  h = x * sc + sh, xhat = (x - mu) * is
+__device__ __forceinline__ void channel_affine(const ChainArgs& a, int c0, float (&mu)[8], float (&is)[8], float (&sc)[8],
+                                               float (&sh)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (a.mean != nullptr) {
+            mu[e] = __ldg(&a.mean[c0 + e]);
+            const float s = __ldg(&a.scale[c0 + e]);
+            is[e] = a.use_var ? rsqrtf(s + a.eps) : s;
+            const float g = a.gamma ? __ldg(&a.gamma[c0 + e]) : 1.f;
+            const float b = a.beta ? __ldg(&a.beta[c0 + e]) : 0.f;
+            sc[e] = g * is[e];
+            sh[e] = b - mu[e] * sc[e];
+        } else {
+            mu[e] = 0.f; is[e] = 1.f; sc[e] = 1.f; sh[e] = 0.f;
+        }
+    }
+}
+
+// ---- statistics: sums (2C) double += (sum x, sum x^2)  [caller zeroes] -------------------------------------------------
+// block = (channel groups) x (row lanes); the lanes of a block are folded in shared memory before the double atomics
+template <bool BWD, int KIND>
+__global__ void __launch_bounds__(256) chain_sums_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                         ChainArgs a, long long rows, int C, int gpb, long long rows_per_block,
+                                                         double* __restrict__ sums) {
+    __shared__ float sm[2][256][9];
+    const int g = threadIdx.x % gpb, rl = threadIdx.x / gpb, nrl = blockDim.x / gpb;
+    const int cg = blockIdx.x * gpb + g;                 // channel group (8 channels)
+    const bool live = cg < C / 8 && rl < nrl;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float s0[8], s1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+    if (live) {
+        float mu[8], is[8], sc[8], sh[8];
+        if (BWD) channel_affine(a, cg * 8, mu, is, sc, sh);
+        for (long long r = r0 + rl; r < r1; r += nrl) {
+            const long long i0 = r * C + (long long)cg * 8;
+            float xv[8];
+            load8(x + i0, xv);
+            if (!BWD) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    s0[e] += xv[e];
+                    s1[e] = fmaf(xv[e], xv[e], s1[e]);
+                }
+            } else {
+                float gv[8], nf[8];
+                load8(dy + i0, gv);
+                noise_factors(a, i0, nf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float av = act_fwd_t<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
+                    const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
+                    s0[e] += gg;
+                    s1[e] = fmaf(gg, (xv[e] - mu[e]) * is[e], s1[e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sm[0][threadIdx.x][e] = s0[e];
+        sm[1][threadIdx.x][e] = s1[e];
+    }
+    __syncthreads();
+    // thread (which, g, e) folds the row lanes: 2 * gpb * 8 results per block
+    for (int t = threadIdx.x; t < 2 * gpb * 8; t += blockDim.x) {
+        const int which = t / (gpb * 8), rem = t - which * gpb * 8, gg = rem / 8, e = rem - gg * 8;
+        const int cgo = blockIdx.x * gpb + gg;
+        if (cgo >= C / 8) continue;
+        double acc = 0.0;
+        for (int l = 0; l < nrl; ++l) acc += (double)sm[which][l * gpb + gg][e];
+        atomicAdd(&sums[(size_t)which * C + cgo * 8 + e], acc);
+    }
+}
+
+// ---- forward apply: y = noise(act(bn(x))) --------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) chain_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                        ChainArgs a, long long rows, int C) {
+    const int C8 = C / 8;
+    const long long total = rows * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long long i0 = i * 8;
+        float mu[8], is[8], sc[8], sh[8], xv[8], nf[8], o[8];
+        channel_affine(a, cg * 8, mu, is, sc, sh);
+        load8(x + i0, xv);
+        noise_factors(a, i0, nf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = act_fwd_t<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param) * nf[e];
+        store8(y + i0, o);
+    }
+}
+
+// ---- backward apply: dx = sc * (g - sum_g/n - xhat * sum_gxhat/n);  without normalisation dx = g ---------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) chain_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                        __nv_bfloat16* __restrict__ dx, ChainArgs a, const double* __restrict__ sums,
+                                                        double n_total, long long rows, int C) {
+    const int C8 = C / 8;
+    const long long total = rows * C8;
+    const float inv_n = (float)(1.0 / n_total);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long long i0 = i * 8;
+        float mu[8], is[8], sc[8], sh[8], xv[8], gv[8], nf[8], o[8];
+        channel_affine(a, cg * 8, mu, is, sc, sh);
+        load8(x + i0, xv);
+        load8(dy + i0, gv);
+        noise_factors(a, i0, nf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float av = act_fwd_t<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
+            const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
+            if (a.mean != nullptr) {
+                const float m0 = (float)sums[cg * 8 + e] * inv_n, m1 = (float)sums[C + cg * 8 + e] * inv_n;
+                o[e] = sc[e] * (gg - m0 - (xv[e] - mu[e]) * is[e] * m1);
+            } else {
+                o[e] = gg;
+            }
+        }
+        store8(dx + i0, o);
+    }
+}
+
+__global__ void __launch_bounds__(256) chain_param_grads_kernel(const double* __restrict__ sums, float* dgamma, float* dbeta,
+                                                                int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (dbeta) dbeta[c] = (float)sums[c];
+    if (dgamma) dgamma[c] = (float)sums[C + c];
+}
+
+static void sums_geometry(long long rows, int C, int* gpb, dim3* grid, long long* rpb) {
+    const int groups = C / 8;
+    int g = groups < 256 ? groups : 256;
+    *gpb = g;
+    const int bx = (groups + g - 1) / g;
+    const int nrl = 256 / g;
+    long long splits = (4LL * num_sms() + bx - 1) / bx;
+    long long maxs = (rows + nrl - 1) / nrl;
+    if (splits > maxs) splits = maxs;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+    long long per = (rows + splits - 1) / splits;
+    splits = (rows + per - 1) / per;
+    *rpb = per;
+    *grid = dim3((unsigned)bx, (unsigned)splits);
+}
+
+#define GN_CHAIN_DISPATCH(KERNEL_CALL)                                   \
+    switch (a.act) {                                                     \
+        case GN_ACT_RELU: { constexpr int K_ = GN_ACT_RELU; KERNEL_CALL; break; }         \
+        case GN_ACT_TANH: { constexpr int K_ = GN_ACT_TANH; KERNEL_CALL; break; }         \
+        case GN_ACT_SIGMOID: { constexpr int K_ = GN_ACT_SIGMOID; KERNEL_CALL; break; }   \
+        case GN_ACT_LEAKY: { constexpr int K_ = GN_ACT_LEAKY; KERNEL_CALL; break; }       \
+        case GN_ACT_RELU_MAX: { constexpr int K_ = GN_ACT_RELU_MAX; KERNEL_CALL; break; } \
+        default: { constexpr int K_ = GN_ACT_NONE; KERNEL_CALL; break; }                  \
+    }
+
+static int make_chain(ChainArgs* a, const float* mean, const float* scale, const float* gamma, const float* beta, int use_var,
+                      float eps, int act, float act_param, int noise, float rate, const float* r, uint64_t seed,
+                      uint64_t offset, int C) {
+    GN_REQUIRE(C > 0 && C % 8 == 0, "C must be a positive multiple of 8");
+    GN_REQUIRE(mean == nullptr || scale != nullptr, "mean given without scale");
+    GN_REQUIRE(noise == -1 || noise == GN_NOISE_DROPOUT || noise == GN_NOISE_GDROPOUT, "noise must be -1, dropout or gaussian dropout");
+    GN_REQUIRE(noise < 0 || (rate >= 0.f && rate < 1.f), "rate must be in [0, 1)");
+    GN_REQUIRE(offset % 4 == 0, "offset must be a multiple of 4");
+    a->mean = mean; a->scale = scale; a->gamma = gamma; a->beta = beta; a->use_var = use_var; a->eps = eps;
+    a->act = act; a->act_param = act_param; a->noise = noise; a->rate = rate; a->r = r; a->seed = seed; a->offset = offset;
+    return GN_OK;
+}
+
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" int gn_bn_stats_bf16(const void* x, long long rows, int C, double* sums, void* stream) {
+    GN_REQUIRE(x && sums && rows >= 0 && C > 0 && C % 8 == 0, "null pointer or bad size (C % 8 == 0)");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st);
+    if (rows == 0) return GN_OK;
+    int gpb; dim3 grid; long long rpb;
+    sums_geometry(rows, C, &gpb, &grid, &rpb);
+    ChainArgs a{};
+    chain_sums_kernel<false, GN_ACT_NONE><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, a, rows, C, gpb, rpb, sums);
+    return cuda_status("chain_sums_kernel");
+}
+
+extern "C" int gn_chain_fwd_bf16(const void* x, void* y, const float* mean, const float* scale, const float* gamma,
+                                 const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
+                                 const float* r, uint64_t seed, uint64_t offset, long long rows, int C, void* stream) {
+    GN_REQUIRE(x && y && rows >= 0, "null pointer or rows < 0");
+    ChainArgs a{};
+    int rc = make_chain(&a, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, C);
+    if (rc != GN_OK) return rc;
+    if (rows == 0) return GN_OK;
+    const long long total = rows * (C / 8);
+    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    cudaStream_t st = as_stream(stream);
+    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, a, rows, C)));
+    return cuda_status("chain_fwd_kernel");
+}
+
+extern "C" int gn_chain_bwd_sums_bf16(const void* x, const void* dy, const float* mean, const float* invstd, const float* gamma,
+                                      const float* beta, int act, float act_param, int noise, float rate, const float* r,
+                                      uint64_t seed, uint64_t offset, long long rows, int C, double* sums, void* stream) {
+    GN_REQUIRE(x && dy && mean && invstd && sums && rows >= 0, "null pointer or rows < 0");
+    ChainArgs a{};
+    int rc = make_chain(&a, mean, invstd, gamma, beta, 0, 0.f, act, act_param, noise, rate, r, seed, offset, C);
+    if (rc != GN_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st);
+    if (rows == 0) return GN_OK;
+    int gpb; dim3 grid; long long rpb;
+    sums_geometry(rows, C, &gpb, &grid, &rpb);
+    GN_CHAIN_DISPATCH((chain_sums_kernel<true, K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, a, rows,
+                                                                       C, gpb, rpb, sums)));
+    return cuda_status("chain_sums_kernel(bwd)");
+}
+
+extern "C" int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, const double* sums, double n_total, int act,
+                                 float act_param, int noise, float rate, const float* r, uint64_t seed, uint64_t offset,
+                                 float* dgamma, float* dbeta, long long rows, int C, void* stream) {
+    GN_REQUIRE(x && dy && dx && rows >= 0, "null pointer or rows < 0");
+    GN_REQUIRE(mean == nullptr || (invstd && sums && n_total > 0), "normalisation needs invstd, sums and n_total");
+    ChainArgs a{};
+    int rc = make_chain(&a, mean, invstd, gamma, beta, 0, 0.f, act, act_param, noise, rate, r, seed, offset, C);
+    if (rc != GN_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    if (rows > 0) {
+        const long long total = rows * (C / 8);
+        unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+        GN_CHAIN_DISPATCH((chain_bwd_kernel<K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                                    (__nv_bfloat16*)dx, a, sums, n_total, rows, C)));
+    }
+    if (mean != nullptr && (dgamma || dbeta))
+        chain_param_grads_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, dgamma, dbeta, C);
+    return cuda_status("chain_bwd_kernel");
+}

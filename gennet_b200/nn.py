@@ -697,7 +697,90 @@ class BatchNormalization(Layer):
                        Param(n + '/moving_variance:0', np.ones(c, np.float32), trainable=False)]
         return in_shape
 
+    chain = (None, None)      # (activation layer, dropout layer) directly following, set by Model._fuse
+
+    def _chain_codes(self, ctx):
+        act, noise = self.chain
+        code, par = (act.code, act.param) if act is not None else (_lib.ACT_NONE, 0.0)
+        kind, rate = (noise.kind, noise.rate) if (noise is not None and ctx.training) else (-1, 0.0)
+        return code, par, kind, rate
+
+    def _forward_bf16(self, x, ctx):
+        """bf16 throughput mode: statistics in one pass, then y = drop(act(bn(x))) in one pass (gn_chain_*_bf16); the
+        activation and dropout layers of the chain become pass-throughs for this call."""
+        C = x.shape[-1]
+        rows = x.numel() // C
+        g, b, mm, mv = [p.data for p in self.params]
+        act, noise = self.chain
+        for l in (act, noise):
+            if l is not None:
+                l._chain_skip = True
+        code, par, kind, rate = self._chain_codes(ctx)
+        y = _empty_bf16(x.shape)
+        if not ctx.training:
+            call('gn_chain_fwd_bf16', ptr(x, BF16), ptr(y, BF16), ptr(mm), ptr(mv), ptr(g), ptr(b), 1, self.epsilon, code,
+                 par, -1, 0.0, None, 0, 0, rows, C, stream())
+            return y
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        stats = _empty((2 * C,))
+        n_total = float(rows * ctx.world)
+        call('gn_bn_stats_bf16', ptr(x, BF16), rows, C, ptr(sums, torch.float64), stream())
+        if ctx.world > 1:
+            ctx.dp.all_reduce(sums)
+        # centred second moment from the raw one (double): sum (x-mean)^2 = sum x^2 - (sum x)^2 / n
+        ssq = (sums[C:] - sums[:C] * sums[:C] / n_total).clamp_(min=0.0).contiguous()
+        call('gn_bn_finalize_f32', ptr(sums, torch.float64), None, n_total, C, self.epsilon, self.momentum,
+             ptr(stats), None, None, 0, stream())
+        call('gn_bn_finalize_f32', None, ptr(ssq, torch.float64), n_total, C, self.epsilon, self.momentum,
+             ptr(stats), ptr(mm), ptr(mv), 1, stream())
+        r, seed, off = None, 0, 0
+        if kind >= 0:
+            fed = ctx.noise.get(noise.name)
+            if fed is not None:
+                r = torch.as_tensor(np.ascontiguousarray(fed, dtype=np.float32)).to(x.device).reshape(x.shape).contiguous()
+            else:
+                n = x.numel()
+                off = _STATE['noise_counter'] + ((ctx.dp.rank << 48) if ctx.dp is not None else 0)
+                _STATE['noise_counter'] += (n + 3) // 4 * 4
+                seed = _STATE['seed']
+        call('gn_chain_fwd_bf16', ptr(x, BF16), ptr(y, BF16), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), 0,
+             self.epsilon, code, par, kind, rate, ptr(r) if r is not None else None, seed, off, rows, C, stream())
+        self._x, self._stats, self._n = x, stats, n_total
+        self._chain_state = (code, par, kind, rate, r, seed, off)
+        return y
+
+    def _backward_bf16(self, dy, ctx):
+        x, stats = self._x, self._stats
+        C = x.shape[-1]
+        rows = x.numel() // C
+        code, par, kind, rate, r, seed, off = self._chain_state
+        dy = _as_bf16(dy.contiguous()).reshape(x.shape)
+        g, b = self.params[0].data, self.params[1].data
+        rp = ptr(r) if r is not None else None
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        call('gn_chain_bwd_sums_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), code,
+             par, kind, rate, rp, seed, off, rows, C, ptr(sums, torch.float64), stream())
+        if ctx.world > 1:
+            ctx.dp.all_reduce(sums)
+        dx = _empty_bf16(x.shape)
+        tr = id(self) in ctx.trainable_ids
+        call('gn_chain_bwd_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(dx, BF16), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b),
+             ptr(sums, torch.float64), self._n, code, par, kind, rate, rp, seed, off,
+             ptr(self.params[0].grad) if tr else None, ptr(self.params[1].grad) if tr else None, rows, C, stream())
+        if tr and ctx.world > 1:
+            self.params[0].grad.mul_(1.0 / ctx.world)
+            self.params[1].grad.mul_(1.0 / ctx.world)
+        self._x = self._stats = self._chain_state = None
+        return dx
+
     def forward(self, x, ctx):
+        for l in self.chain:
+            if l is not None:
+                l._chain_skip = False
+        self._fused_call = x.dtype == BF16 and x.shape[-1] % 8 == 0 and \
+            not any(isinstance(l, GaussianNoise) for l in self.chain if l is not None)
+        if self._fused_call:
+            return self._forward_bf16(x.contiguous(), ctx)
         x = _as_f32(x)
         C = x.shape[-1]
         rows = x.numel() // C
@@ -726,6 +809,8 @@ class BatchNormalization(Layer):
         return y
 
     def backward(self, dy, ctx, need_dx=True):
+        if getattr(self, '_fused_call', False):
+            return self._backward_bf16(dy, ctx)
         dy = _as_f32(dy)
         x, stats = self._x, self._stats
         C = x.shape[-1]
@@ -752,8 +837,10 @@ class _ActLayer(Layer):
     code, param = _lib.ACT_NONE, 0.0
     fused = False        # True when the preceding Conv1D applies this activation in its epilogue
 
+    _chain_skip = False   # True for the current call when the preceding BatchNormalization ran the bf16 chain
+
     def forward(self, x, ctx):
-        if self.code == _lib.ACT_NONE or self.fused:
+        if self.code == _lib.ACT_NONE or self.fused or self._chain_skip:
             return x
         x = _as_f32(x)
         y = _empty(x.shape)
@@ -762,7 +849,7 @@ class _ActLayer(Layer):
         return y
 
     def backward(self, dy, ctx, need_dx=True):
-        if self.code == _lib.ACT_NONE or self.fused or not need_dx:
+        if self.code == _lib.ACT_NONE or self.fused or self._chain_skip or not need_dx:
             return dy
         dx = _act_bwd(dy, self._y, self.code, self.param)
         self._y = None
@@ -806,10 +893,32 @@ class _NoiseLayer(Layer):
         super().__init__(**kw)
         self.rate = float(rate)
 
+    _chain_skip = False   # True for the current call when the preceding BatchNormalization ran the bf16 chain
+
     def forward(self, x, ctx):
-        if not ctx.training:
+        self._bf16_state = None
+        if not ctx.training or self._chain_skip:
             self._r = None
             return x
+        if x.dtype == BF16 and x.shape[-1] % 8 == 0 and self.kind != _lib.NOISE_GNOISE:
+            # bf16 throughput mode: y = x * factor with the mask recomputed from the Philox counter in backward
+            x = x.contiguous()
+            C = x.shape[-1]
+            rows = x.numel() // C
+            fed = ctx.noise.get(self.name)
+            r, seed, off = None, 0, 0
+            if fed is not None:
+                r = torch.as_tensor(np.ascontiguousarray(fed, dtype=np.float32)).to(x.device).reshape(x.shape).contiguous()
+            else:
+                off = _STATE['noise_counter'] + ((ctx.dp.rank << 48) if ctx.dp is not None else 0)
+                _STATE['noise_counter'] += (x.numel() + 3) // 4 * 4
+                seed = _STATE['seed']
+            y = _empty_bf16(x.shape)
+            call('gn_chain_fwd_bf16', ptr(x, BF16), ptr(y, BF16), None, None, None, None, 0, 0.0, _lib.ACT_NONE, 0.0,
+                 self.kind, self.rate, ptr(r) if r is not None else None, seed, off, rows, C, stream())
+            self._bf16_state = (r, seed, off)
+            self._r = None
+            return y
         x = _as_f32(x)
         fed = ctx.noise.get(self.name)
         if fed is not None:
@@ -827,6 +936,17 @@ class _NoiseLayer(Layer):
         return y
 
     def backward(self, dy, ctx, need_dx=True):
+        if getattr(self, '_bf16_state', None) is not None and need_dx:
+            r, seed, off = self._bf16_state
+            dy = _as_bf16(dy.contiguous())
+            C = dy.shape[-1]
+            rows = dy.numel() // C
+            dx = _empty_bf16(dy.shape)
+            call('gn_chain_bwd_bf16', ptr(dy, BF16), ptr(dy, BF16), ptr(dx, BF16), None, None, None, None, None, 1.0,
+                 _lib.ACT_NONE, 0.0, self.kind, self.rate, ptr(r) if r is not None else None, seed, off, None, None,
+                 rows, C, stream())
+            self._bf16_state = None
+            return dx
         if self._r is None or not need_dx:
             return dy
         dy = _as_f32(dy)
@@ -1152,6 +1272,19 @@ class Model(Layer):
                 if len(u) == 1 and isinstance(u[0].layer, _ActLayer) and u[0].layer.code != _lib.ACT_NONE:
                     n.layer.post_act = (u[0].layer.code, u[0].layer.param)
                     u[0].layer.fused = True
+        # BatchNormalization -> [activation] -> [dropout]: candidates for the bf16 chain kernels (decided per call by the
+        # dtype of the tensor reaching the BatchNormalization; float32 tensors keep the exact per-layer kernels)
+        for n in self._order:
+            if type(n.layer) is BatchNormalization:
+                act = noise = None
+                cur = n
+                u = users.get(id(cur), [])
+                if len(u) == 1 and isinstance(u[0].layer, _ActLayer) and not u[0].layer.fused and cur not in self._out_nodes:
+                    act, cur = u[0].layer, u[0]
+                    u = users.get(id(cur), [])
+                if len(u) == 1 and isinstance(u[0].layer, (Dropout, GaussianDropout)) and cur not in self._out_nodes:
+                    noise = u[0].layer
+                n.layer.chain = (act, noise)
         # consumer of a fused conv+activation (through views / the now-identity activation layer): it may apply
         # the activation derivative in its own data-gradient epilogue, using its input as the mask source
         for n in self._order:

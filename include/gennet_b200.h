@@ -221,6 +221,29 @@ int gn_bn_bwd_apply_f32(const float* x, const float* dy, const float* stats, con
                         double n_total, float* dx, float* dgamma, float* dbeta, long long rows, int C,
                         void* stream);
 
+/* bf16 throughput mode of BatchNormalization -> activation -> dropout chains (generator hidden layers,
+ * bbhMahoGANy.py:235-289) as streaming passes over bf16 activations, fp32 arithmetic, double statistics; C % 8 == 0.
+ *   gn_bn_stats_bf16      : sums (2C) double OVERWRITTEN = (sum x, sum x^2) per channel (one pass; data-parallel callers
+ *                           all-reduce it, then gn_bn_finalize_f32 with sum_sq - sum^2/n gives mean / invstd / moving stats)
+ *   gn_chain_fwd_bf16     : y = noise(act(gamma * (x - mean) * invstd + beta)); scale = invstd, or the moving variance
+ *                           when use_var (inference); mean == NULL skips the normalisation (plain activation / dropout);
+ *                           noise = -1 | GN_NOISE_DROPOUT | GN_NOISE_GDROPOUT with the mask from r (f32, fed) or, when r is
+ *                           NULL, from the Philox stream of gn_noise_draw_f32(seed, offset) -- never materialised
+ *   gn_chain_bwd_sums_bf16: sums (2C) double OVERWRITTEN = (sum g, sum g*xhat), g = dy * noise' * act'(a), a recomputed
+ *   gn_chain_bwd_bf16     : dx = gamma*invstd*(g - sum_g/n - xhat*sum_gxhat/n), dgamma = sum_gxhat, dbeta = sum_g
+ *                           (mean == NULL: dx = g) */
+int gn_bn_stats_bf16(const void* x, long long rows, int C, double* sums, void* stream);
+int gn_chain_fwd_bf16(const void* x, void* y, const float* mean, const float* scale, const float* gamma, const float* beta,
+                      int use_var, float eps, int act, float act_param, int noise, float rate, const float* r,
+                      uint64_t seed, uint64_t offset, long long rows, int C, void* stream);
+int gn_chain_bwd_sums_bf16(const void* x, const void* dy, const float* mean, const float* invstd, const float* gamma,
+                           const float* beta, int act, float act_param, int noise, float rate, const float* r,
+                           uint64_t seed, uint64_t offset, long long rows, int C, double* sums, void* stream);
+int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, const double* sums, double n_total, int act, float act_param, int noise,
+                      float rate, const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta,
+                      long long rows, int C, void* stream);
+
 /* elementwise */
 int gn_act_fwd_f32(const float* x, float* y, long long n, int act, float param, void* stream);
 int gn_act_bwd_f32(const float* dy, const float* y, float* dx, long long n, int act, float param, void* stream);

@@ -288,3 +288,74 @@ def test_philox_streams():
     r = philox([5, 0, 0, 1], [42, 0])
     exp = [((x >> 8) + 0.5) / 16777216.0 * 2.0 - 1.0 for x in r]
     assert np.allclose(u[20:24].cpu().numpy(), np.array(exp, dtype=np.float32), atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rows,C,act,noise', [(300, 64, 2, 0), (77, 912, 1, 1), (1000, 8, 4, -1), (64, 1024, 0, 0)])
+def test_bf16_bn_act_dropout_chain(rows, C, act, noise):
+    """gn_bn_stats_bf16 / gn_chain_{fwd,bwd_sums,bwd}_bf16 vs torch float64 autograd of drop(act(bn(x))) on the same
+    bf16-rounded x, dy and a fed mask; and the Philox-mask variant is self-consistent between forward and backward."""
+    from gennet_b200 import _lib as L_
+    rs = np.random.RandomState(rows + C)
+    bfl = torch.bfloat16
+    x = torch.as_tensor(rs.normal(0.3, 1.5, size=(rows, C)).astype(np.float32)).cuda().to(bfl)
+    dy = torch.as_tensor(rs.normal(size=(rows, C)).astype(np.float32)).cuda().to(bfl)
+    gamma = torch.as_tensor(rs.uniform(0.5, 1.5, C).astype(np.float32)).cuda()
+    beta = torch.as_tensor(rs.normal(size=C).astype(np.float32)).cuda()
+    eps, rate = 1e-3, 0.2
+    st = L_.stream()
+    sums = torch.empty(2 * C, dtype=torch.float64, device='cuda')
+    L_.call('gn_bn_stats_bf16', L_.ptr(x, bfl), rows, C, L_.ptr(sums, torch.float64), st)
+    xd = x.double()
+    assert torch.allclose(sums[:C], xd.sum(0), rtol=1e-6, atol=1e-6) and torch.allclose(sums[C:], (xd * xd).sum(0), rtol=1e-6)
+    mean = xd.mean(0)
+    var = xd.var(0, unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + eps)
+    if noise == 0:
+        r = torch.as_tensor((rs.uniform(size=(rows, C)) >= rate).astype(np.float32)).cuda()
+        fac = r.double() / (1 - rate)
+    elif noise == 1:
+        r = torch.as_tensor(rs.normal(size=(rows, C)).astype(np.float32)).cuda()
+        fac = 1 + r.double() * np.sqrt(rate / (1 - rate))
+    else:
+        r, fac = None, torch.ones(rows, C, dtype=torch.float64, device='cuda')
+    xg = xd.clone().requires_grad_(True)
+    gg = gamma.double().clone().requires_grad_(True)
+    bg = beta.double().clone().requires_grad_(True)
+    mu_b = xg.mean(0)
+    h = gg * (xg - mu_b) / torch.sqrt(xg.var(0, unbiased=False) + eps) + bg
+    a = {0: h, 1: torch.relu(h), 2: torch.tanh(h), 4: torch.where(h >= 0, h, 0.2 * h)}[act]
+    yref = a * fac
+    (yref * dy.double()).sum().backward()
+    y = torch.empty_like(x)
+    meanf, invf = mean.float().contiguous(), invstd.float().contiguous()
+    rp = L_.ptr(r) if r is not None else None
+    L_.call('gn_chain_fwd_bf16', L_.ptr(x, bfl), L_.ptr(y, bfl), L_.ptr(meanf), L_.ptr(invf), L_.ptr(gamma), L_.ptr(beta), 0, eps,
+            act, 0.2, noise, rate, rp, 0, 0, rows, C, st)
+    assert_close(y.float().cpu().numpy(), yref.detach().cpu().numpy(), 'chain fwd', 2 ** -7)
+    L_.call('gn_chain_bwd_sums_bf16', L_.ptr(x, bfl), L_.ptr(dy, bfl), L_.ptr(meanf), L_.ptr(invf), L_.ptr(gamma), L_.ptr(beta), act,
+            0.2, noise, rate, rp, 0, 0, rows, C, L_.ptr(sums, torch.float64), st)
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(C, device='cuda')
+    dbeta = torch.empty(C, device='cuda')
+    L_.call('gn_chain_bwd_bf16', L_.ptr(x, bfl), L_.ptr(dy, bfl), L_.ptr(dx, bfl), L_.ptr(meanf), L_.ptr(invf), L_.ptr(gamma),
+            L_.ptr(beta), L_.ptr(sums, torch.float64), float(rows), act, 0.2, noise, rate, rp, 0, 0, L_.ptr(dgamma), L_.ptr(dbeta),
+            rows, C, st)
+    assert_close(dbeta.cpu().numpy(), bg.grad.cpu().numpy(), 'chain dbeta', 1e-4)
+    assert_close(dgamma.cpu().numpy(), gg.grad.cpu().numpy(), 'chain dgamma', 1e-4)
+    assert_close(dx.float().cpu().numpy(), xg.grad.cpu().numpy(), 'chain dx', 2 ** -7)
+    if noise >= 0:
+        # Philox masks: identical to gn_noise_draw_f32 at the same (seed, offset), in forward and in backward
+        rr = torch.empty(rows, C, device='cuda')
+        L_.call('gn_noise_draw_f32', L_.ptr(rr), rows * C, noise, rate, 77, 1024, st)
+        y1, y2 = torch.empty_like(x), torch.empty_like(x)
+        L_.call('gn_chain_fwd_bf16', L_.ptr(x, bfl), L_.ptr(y1, bfl), None, None, None, None, 0, 0.0, 0, 0.0, noise, rate, None, 77,
+                1024, rows, C, st)
+        L_.call('gn_chain_fwd_bf16', L_.ptr(x, bfl), L_.ptr(y2, bfl), None, None, None, None, 0, 0.0, 0, 0.0, noise, rate, L_.ptr(rr),
+                0, 0, rows, C, st)
+        assert torch.equal(y1, y2)
+        L_.call('gn_chain_bwd_bf16', L_.ptr(x, bfl), L_.ptr(dy, bfl), L_.ptr(y1, bfl), None, None, None, None, None, 1.0, 0, 0.0,
+                noise, rate, None, 77, 1024, None, None, rows, C, st)
+        L_.call('gn_chain_bwd_bf16', L_.ptr(x, bfl), L_.ptr(dy, bfl), L_.ptr(y2, bfl), None, None, None, None, None, 1.0, 0, 0.0,
+                noise, rate, L_.ptr(rr), 0, 0, None, None, rows, C, st)
+        assert torch.equal(y1, y2)
