@@ -38,9 +38,11 @@ __global__ void __launch_bounds__(256) conv_smallcin_fwd_kernel(const float* __r
 #pragma unroll
             for (int c = 0; c < CIN; ++c) {
                 const float xv = __ldg(&x[((size_t)b * L + pos) * CIN + c]);
-                const float* wr = &sw[(t * CIN + c) * Cout + g * 8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+                const float4* wr = reinterpret_cast<const float4*>(&sw[(t * CIN + c) * Cout + g * 8]);
+                const float4 w0 = wr[0], w1 = wr[1];
+                acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]);
+                acc[3] = fmaf(xv, w0.w, acc[3]); acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+                acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
             }
         }
         __nv_bfloat162 h[4];
@@ -166,9 +168,12 @@ __global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const __nv_bfl
 #pragma unroll
             for (int i = 0; i < KMAX * CIN; ++i) {
                 if (i < k * CIN) {
-                    const float* wr = &sw[(size_t)i * Cout + c8 * 8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i] = fmaf(gv[j], wr[j], acc[i]);
+                    const float4* wr = reinterpret_cast<const float4*>(&sw[(size_t)i * Cout + c8 * 8]);
+                    const float4 w0 = wr[0], w1 = wr[1];
+                    acc[i] = fmaf(gv[0], w0.x, acc[i]); acc[i] = fmaf(gv[1], w0.y, acc[i]);
+                    acc[i] = fmaf(gv[2], w0.z, acc[i]); acc[i] = fmaf(gv[3], w0.w, acc[i]);
+                    acc[i] = fmaf(gv[4], w1.x, acc[i]); acc[i] = fmaf(gv[5], w1.y, acc[i]);
+                    acc[i] = fmaf(gv[6], w1.z, acc[i]); acc[i] = fmaf(gv[7], w1.w, acc[i]);
                 }
             }
         }
@@ -444,9 +449,12 @@ __global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const __nv_bfloat16
 #pragma unroll
             for (int t = 0; t < KMAX; ++t) {
                 if (t < k) {
-                    const float* wr = &sw[t * Cin + c8 * 8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[t] = fmaf(xv[j], wr[j], acc[t]);
+                    const float4* wr = reinterpret_cast<const float4*>(&sw[t * Cin + c8 * 8]);
+                    const float4 w0 = wr[0], w1 = wr[1];
+                    acc[t] = fmaf(xv[0], w0.x, acc[t]); acc[t] = fmaf(xv[1], w0.y, acc[t]);
+                    acc[t] = fmaf(xv[2], w0.z, acc[t]); acc[t] = fmaf(xv[3], w0.w, acc[t]);
+                    acc[t] = fmaf(xv[4], w1.x, acc[t]); acc[t] = fmaf(xv[5], w1.y, acc[t]);
+                    acc[t] = fmaf(xv[6], w1.z, acc[t]); acc[t] = fmaf(xv[7], w1.w, acc[t]);
                 }
             }
         }
@@ -513,7 +521,7 @@ __global__ void __launch_bounds__(256) conv_cout1_wgrad_kernel(const __nv_bfloat
     for (int t = 0; t < KMAX; ++t)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (long long row = r0; row < r1; ++row) {
         const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
         uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * Cin) + c);
@@ -619,7 +627,9 @@ extern "C" int gn_conv1d_cout1_wgrad_bf16(const void* x, const float* dy, float*
     if (B > 0) {
         const long long rows = (long long)B * L;
         const int bx = (Cin / 8 + 255) / 256;
-        long long splits = (4LL * num_sms() * 8 + bx - 1) / bx;      // blocks are only Cin/8 threads wide
+        // few, long slices: every slice ends in k*8 atomics per thread onto the same k*Cin addresses, and same-address
+        // atomics serialise in L2
+        long long splits = (2LL * num_sms() + bx - 1) / bx;
         if (Cin / 8 < 256) splits = splits * 256 / (Cin / 8);
         if (splits > rows) splits = rows;
         if (splits > 65535) splits = 65535;

@@ -165,16 +165,23 @@ __global__ void __launch_bounds__(256) chain_sums_kernel(const __nv_bfloat16* __
 }
 
 // ---- forward apply: y = noise(act(bn(x))) --------------------------------------------------------------------------
+// A thread keeps ONE channel group for its whole life (its per-channel affine is computed once) and walks the rows
+// with a stride of `lanes` = (threads of the grid) / (C/8); consecutive threads hold consecutive channel groups, so
+// every access of a warp is a contiguous 512-byte run of a row.
 template <int KIND>
 __global__ void __launch_bounds__(256) chain_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                        ChainArgs a, long long rows, int C) {
+                                                        ChainArgs a, long long rows, int C, long long lanes) {
     const int C8 = C / 8;
-    const long long total = rows * C8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % C8);
-        const long long i0 = i * 8;
-        float mu[8], is[8], sc[8], sh[8], xv[8], nf[8], o[8];
-        channel_affine(a, cg * 8, mu, is, sc, sh);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = (int)(tid % C8);
+    const long long lane = tid / C8;
+    if (lane >= lanes) return;
+    float mu[8], is[8], sc[8], sh[8];
+    channel_affine(a, cg * 8, mu, is, sc, sh);
+#pragma unroll 2
+    for (long long r = lane; r < rows; r += lanes) {
+        const long long i0 = r * C + (long long)cg * 8;
+        float xv[8], nf[8], o[8];
         load8(x + i0, xv);
         noise_factors(a, i0, nf);
 #pragma unroll
@@ -187,15 +194,24 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const __nv_bfloat16* __r
 template <int KIND>
 __global__ void __launch_bounds__(256) chain_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                         __nv_bfloat16* __restrict__ dx, ChainArgs a, const double* __restrict__ sums,
-                                                        double n_total, long long rows, int C) {
+                                                        double n_total, long long rows, int C, long long lanes) {
     const int C8 = C / 8;
-    const long long total = rows * C8;
-    const float inv_n = (float)(1.0 / n_total);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % C8);
-        const long long i0 = i * 8;
-        float mu[8], is[8], sc[8], sh[8], xv[8], gv[8], nf[8], o[8];
-        channel_affine(a, cg * 8, mu, is, sc, sh);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = (int)(tid % C8);
+    const long long lane = tid / C8;
+    if (lane >= lanes) return;
+    float mu[8], is[8], sc[8], sh[8], m0[8], m1[8];
+    channel_affine(a, cg * 8, mu, is, sc, sh);
+    const bool bn = a.mean != nullptr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        m0[e] = bn ? (float)(sums[cg * 8 + e] / n_total) : 0.f;
+        m1[e] = bn ? (float)(sums[C + cg * 8 + e] / n_total) : 0.f;
+    }
+#pragma unroll 2
+    for (long long r = lane; r < rows; r += lanes) {
+        const long long i0 = r * C + (long long)cg * 8;
+        float xv[8], gv[8], nf[8], o[8];
         load8(x + i0, xv);
         load8(dy + i0, gv);
         noise_factors(a, i0, nf);
@@ -203,12 +219,7 @@ __global__ void __launch_bounds__(256) chain_bwd_kernel(const __nv_bfloat16* __r
         for (int e = 0; e < 8; ++e) {
             const float av = act_fwd_t<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
             const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
-            if (a.mean != nullptr) {
-                const float m0 = (float)sums[cg * 8 + e] * inv_n, m1 = (float)sums[C + cg * 8 + e] * inv_n;
-                o[e] = sc[e] * (gg - m0 - (xv[e] - mu[e]) * is[e] * m1);
-            } else {
-                o[e] = gg;
-            }
+            o[e] = bn ? sc[e] * (gg - m0[e] - (xv[e] - mu[e]) * is[e] * m1[e]) : gg;
         }
         store8(dx + i0, o);
     }
@@ -249,6 +260,17 @@ static void sums_geometry(long long rows, int C, int* gpb, dim3* grid, long long
         default: { constexpr int K_ = GN_ACT_NONE; KERNEL_CALL; break; }                  \
     }
 
+// grid of the apply kernels: `lanes` row lanes x C/8 channel groups, about 16 CTAs of 256 threads per SM
+static void apply_geometry(long long rows, int C, unsigned* grid, long long* lanes) {
+    const long long C8 = C / 8;
+    long long want = 16LL * num_sms() * 256;
+    long long l = want / C8;
+    if (l < 1) l = 1;
+    if (l > rows) l = rows;
+    *lanes = l;
+    *grid = (unsigned)((l * C8 + 255) / 256);
+}
+
 static int make_chain(ChainArgs* a, const float* mean, const float* scale, const float* gamma, const float* beta, int use_var,
                       float eps, int act, float act_param, int noise, float rate, const float* r, uint64_t seed,
                       uint64_t offset, int C) {
@@ -286,10 +308,10 @@ extern "C" int gn_chain_fwd_bf16(const void* x, void* y, const float* mean, cons
     int rc = make_chain(&a, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, C);
     if (rc != GN_OK) return rc;
     if (rows == 0) return GN_OK;
-    const long long total = rows * (C / 8);
-    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+    unsigned grid; long long lanes;
+    apply_geometry(rows, C, &grid, &lanes);
     cudaStream_t st = as_stream(stream);
-    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, a, rows, C)));
+    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, a, rows, C, lanes)));
     return cuda_status("chain_fwd_kernel");
 }
 
@@ -321,10 +343,10 @@ extern "C" int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const 
     if (rc != GN_OK) return rc;
     cudaStream_t st = as_stream(stream);
     if (rows > 0) {
-        const long long total = rows * (C / 8);
-        unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+        unsigned grid; long long lanes;
+        apply_geometry(rows, C, &grid, &lanes);
         GN_CHAIN_DISPATCH((chain_bwd_kernel<K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
-                                                                    (__nv_bfloat16*)dx, a, sums, n_total, rows, C)));
+                                                                    (__nv_bfloat16*)dx, a, sums, n_total, rows, C, lanes)));
     }
     if (mean != nullptr && (dgamma || dbeta))
         chain_param_grads_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, dgamma, dbeta, C);

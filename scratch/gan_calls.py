@@ -30,5 +30,5 @@ bbh.gan_train_step(G, D, DG, ns, real, z1, rn, z2)
 torch.cuda.synchronize()
 for name, ints, a, b in rec:
     t = a.elapsed_time(b)
-    if t > 0.25:
+    if t > 0.15:
         print('%-30s %8.3f ms  %s' % (name, t, ints))
