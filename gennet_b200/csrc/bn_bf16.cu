@@ -46,6 +46,23 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
 }
 
+// Activation in the bf16 chain: the result is rounded to 8 mantissa bits, so tanh / sigmoid use the SFU approximations
+// (tanh.approx.f32: ~2^-11 relative error) instead of the multi-instruction libm forms.
+template <int KIND>
+__device__ __forceinline__ float chain_act(float h, float p) {
+    if (KIND == GN_ACT_TANH) {
+        float y;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(h));
+        return y;
+    }
+    if (KIND == GN_ACT_SIGMOID) {
+        float y;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(0.5f * h));
+        return fmaf(0.5f, y, 0.5f);
+    }
+    return act_fwd_t<KIND>(h, p);
+}
+
 // multiplicative noise factors of the 8 elements starting at flat index i0 (i0 % 8 == 0); GaussianNoise (additive) is
 // not a factor and is not handled by the chain
 __device__ __forceinline__ void noise_factors(const ChainArgs& a, long long i0, float (&f)[8]) {
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(256) chain_sums_kernel(const __nv_bfloat16* __
                 noise_factors(a, i0, nf);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float av = act_fwd_t<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
+                    const float av = chain_act<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
                     const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
                     s0[e] += gg;
                     s1[e] = fmaf(gg, (xv[e] - mu[e]) * is[e], s1[e]);
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const __nv_bfloat16* __r
         load8(x + i0, xv);
         noise_factors(a, i0, nf);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = act_fwd_t<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param) * nf[e];
+        for (int e = 0; e < 8; ++e) o[e] = chain_act<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param) * nf[e];
         store8(y + i0, o);
     }
 }
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(256) chain_bwd_kernel(const __nv_bfloat16* __r
         noise_factors(a, i0, nf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float av = act_fwd_t<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
+            const float av = chain_act<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
             const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
             o[e] = bn ? sc[e] * (gg - m0[e] - (xv[e] - mu[e]) * is[e] * m1[e]) : gg;
         }
