@@ -272,6 +272,7 @@ def run_ours(args):
            'gpu_launches': launches, 'clocks': clocks}
 
     prof = profile_pass(one_step, args, B, L, N)      # every rank: the steps contain collectives
+    prof['roofline_whiten'] = whiten_roofline(synth_obj, dev)
     if rank == 0:
         out.update(prof)
         if world == 1:
@@ -324,6 +325,40 @@ def profile_pass(one_step, args, B, L, N):
                            'peak_source': which, 'avg_launch_ms': syn_ms, 'algorithmic_bytes_per_launch': syn_bytes},
         'kernel_time_ms_per_step': {k: v[0] / n for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:8]},
     }
+
+
+def whiten_roofline(synth_obj, dev, batch=8192, iters=10):
+    """BASELINE's second metric, "whitening HBM GB/s": gn_whiten_td_f32 alone (window -> rfft -> weights -> irfft) on
+    `batch` resident series of N = 8192 samples, timed with CUDA events; algorithmic bytes 8*N per series (read + write
+    the series once; window / weights / twiddles are batch-shared).  536 MB per launch >> 126 MB L2."""
+    import torch
+    hbm, _, _, which = peaks()
+    N = synth_obj.N
+    x = torch.randn(batch, N, device=dev) * 1e-21
+    for _ in range(3):
+        synth_obj.whiten_td(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        synth_obj.whiten_td(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = batch * 8 * N
+    gbs = nbytes / (ms / 1e3) / 1e9
+    traffic = None
+    try:
+        import glob
+        files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_whiten_traffic.json')))
+        with open(files[-1]) as f:
+            traffic = json.load(f)['dram_bytes_per_launch']      # ncu --set full capture of the same launch shape
+    except Exception:
+        pass
+    return {'bound': 'hbm', 'kernel': 'synth_kernel<12,0> (gn_whiten_td_f32: Tukey window, rfft, whitening weights, irfft)',
+            'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm, 'traffic': traffic, 'peak_source': which,
+            'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': nbytes, 'batch': batch,
+            'note': 'on-chip bound: ~420k FP32 lane-ops and ~4800 L1/shared wavefronts per 64 KiB series (DESIGN.md section 6)'}
 
 
 def cpu_reference_step_fn(sample_batch):
