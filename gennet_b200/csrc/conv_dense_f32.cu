@@ -55,6 +55,14 @@ struct BiasActStore {
         y[(size_t)m * ld + n] = act_fwd(v, act, ap);
     }
 };
+__global__ void __launch_bounds__(256) bias_act_inplace_kernel(float* __restrict__ y, const float* __restrict__ bias,
+                                                               long long n, int N, int act, float ap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = y[i];
+    if (bias) v += __ldg(&bias[i % N]);
+    y[i] = act_fwd(v, act, ap);
+}
 struct PlainStore {
     float* __restrict__ y;
     int ld;
@@ -306,8 +314,20 @@ extern "C" int gn_dense_fwd_f32(const float* x, const float* w, const float* bia
     RowMajorA fa{x, K};
     RowMajorB fb{w, N};
     BiasActStore epi{y, bias, N, act, act_param};
-    if (N <= 4) return launch_gemv_rows(fa, fb, epi, M, K, N, as_stream(stream));
-    return launch_gemm_simt<true, false>(fa, fb, epi, M, N, K, 1, as_stream(stream));
+    cudaStream_t st = as_stream(stream);
+    if (N <= 4) return launch_gemv_rows(fa, fb, epi, M, K, N, st);
+    // few output tiles over a long contraction (e.g. Flatten(204700) -> Dense(25), train_on_wvf_version/nn.py:90):
+    // split K across CTAs with atomic accumulation, then bias + activation in place
+    const int splits = pick_splits(M, N, K);
+    if (splits > 1) {
+        cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
+        int rc = launch_gemm_simt<true, false>(fa, fb, AtomicStore{y, N}, M, N, K, splits, st);
+        if (rc != GN_OK) return rc;
+        const long long tot = (long long)M * N;
+        bias_act_inplace_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(y, bias, tot, N, act, act_param);
+        return cuda_status("bias_act_inplace_kernel");
+    }
+    return launch_gemm_simt<true, false>(fa, fb, epi, M, N, K, 1, st);
 }
 
 extern "C" int gn_dense_dgrad_f32(const float* dy, const float* w, float* dx, int M, int K, int N, void* stream) {
