@@ -12,6 +12,7 @@
 #include "gn_common.cuh"
 #include "philox.cuh"
 
+#include <cstdlib>
 #include <math.h>
 #include <vector>
 
@@ -21,6 +22,7 @@ struct gn_fft_plan {
     float2* tw;   // device, exp(-2*pi*i*j/N), j in [0,N)   (real-FFT packing twiddles)
     float2* ptw;  // device, per-pass Stockham twiddles laid out [pass][r-1][k] = exp(-2*pi*i*r*k/(p*R)), k < p,
                   // so that the lanes of a warp (consecutive k) read consecutive 8-byte entries
+    float2* tw64; // device, N == 8192 only: [k1][t] = exp(-2*pi*i*k1*t/4096), k1, t < 64 (64 x 64 decomposition)
 };
 
 namespace gn {
@@ -192,6 +194,31 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ ptw, const I
     }
 }
 
+// 64-point DFT in registers as 4 x 16 (Cooley-Tukey): n = 16*n1 + n2, k = k1 + 4*k2.  v[16*k1 + n2] holds the radix-4
+// outputs after step 1, is rotated by W_64^(n2*k1) and transformed by Dft<16> per k1; bin k ends in v[out_reg(k)].
+__device__ constexpr float kCos64[64] = {1.000000000e+00f, 9.951847267e-01f, 9.807852804e-01f, 9.569403357e-01f, 9.238795325e-01f, 8.819212643e-01f, 8.314696123e-01f, 7.730104534e-01f, 7.071067812e-01f, 6.343932842e-01f, 5.555702330e-01f, 4.713967368e-01f, 3.826834324e-01f, 2.902846773e-01f, 1.950903220e-01f, 9.801714033e-02f, 6.123233996e-17f, -9.801714033e-02f, -1.950903220e-01f, -2.902846773e-01f, -3.826834324e-01f, -4.713967368e-01f, -5.555702330e-01f, -6.343932842e-01f, -7.071067812e-01f, -7.730104534e-01f, -8.314696123e-01f, -8.819212643e-01f, -9.238795325e-01f, -9.569403357e-01f, -9.807852804e-01f, -9.951847267e-01f, -1.000000000e+00f, -9.951847267e-01f, -9.807852804e-01f, -9.569403357e-01f, -9.238795325e-01f, -8.819212643e-01f, -8.314696123e-01f, -7.730104534e-01f, -7.071067812e-01f, -6.343932842e-01f, -5.555702330e-01f, -4.713967368e-01f, -3.826834324e-01f, -2.902846773e-01f, -1.950903220e-01f, -9.801714033e-02f, -1.836970199e-16f, 9.801714033e-02f, 1.950903220e-01f, 2.902846773e-01f, 3.826834324e-01f, 4.713967368e-01f, 5.555702330e-01f, 6.343932842e-01f, 7.071067812e-01f, 7.730104534e-01f, 8.314696123e-01f, 8.819212643e-01f, 9.238795325e-01f, 9.569403357e-01f, 9.807852804e-01f, 9.951847267e-01f};
+__device__ constexpr float kSin64[64] = {0.000000000e+00f, 9.801714033e-02f, 1.950903220e-01f, 2.902846773e-01f, 3.826834324e-01f, 4.713967368e-01f, 5.555702330e-01f, 6.343932842e-01f, 7.071067812e-01f, 7.730104534e-01f, 8.314696123e-01f, 8.819212643e-01f, 9.238795325e-01f, 9.569403357e-01f, 9.807852804e-01f, 9.951847267e-01f, 1.000000000e+00f, 9.951847267e-01f, 9.807852804e-01f, 9.569403357e-01f, 9.238795325e-01f, 8.819212643e-01f, 8.314696123e-01f, 7.730104534e-01f, 7.071067812e-01f, 6.343932842e-01f, 5.555702330e-01f, 4.713967368e-01f, 3.826834324e-01f, 2.902846773e-01f, 1.950903220e-01f, 9.801714033e-02f, 1.224646799e-16f, -9.801714033e-02f, -1.950903220e-01f, -2.902846773e-01f, -3.826834324e-01f, -4.713967368e-01f, -5.555702330e-01f, -6.343932842e-01f, -7.071067812e-01f, -7.730104534e-01f, -8.314696123e-01f, -8.819212643e-01f, -9.238795325e-01f, -9.569403357e-01f, -9.807852804e-01f, -9.951847267e-01f, -1.000000000e+00f, -9.951847267e-01f, -9.807852804e-01f, -9.569403357e-01f, -9.238795325e-01f, -8.819212643e-01f, -8.314696123e-01f, -7.730104534e-01f, -7.071067812e-01f, -6.343932842e-01f, -5.555702330e-01f, -4.713967368e-01f, -3.826834324e-01f, -2.902846773e-01f, -1.950903220e-01f, -9.801714033e-02f};
+template <int DIR>
+struct Dft<64, DIR> {
+    static __device__ __forceinline__ void run(float2* v) {
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) fft4<DIR>(v[n2], v[16 + n2], v[32 + n2], v[48 + n2]);
+#pragma unroll
+        for (int k1 = 1; k1 < 4; ++k1) {
+#pragma unroll
+            for (int n2 = 1; n2 < 16; ++n2) {
+                const int m = (n2 * k1) & 63;            // W_64^m = cos - i sin (forward), conjugate for the inverse
+                v[16 * k1 + n2] = cmul(v[16 * k1 + n2], make_float2(kCos64[m], DIR < 0 ? -kSin64[m] : kSin64[m]));
+            }
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) Dft<16, DIR>::run(v + 16 * k1);
+    }
+    static __device__ __forceinline__ constexpr int out_reg(int k) {
+        return 16 * (k & 3) + Dft<16, DIR>::out_reg(k >> 2);
+    }
+};
+
 // remainder radix so that M = REM * 16^a
 template <int LOG2M>
 struct Plan {
@@ -323,10 +350,121 @@ struct SynthArgs {
     float* y;
     const float2* tw;
     const float2* ptw;
+    const float2* tw64;
     int batch, n_templates, crop_lo, crop_len, roll, drop_dc;
     float noise_scale, out_scale;
     unsigned long long seed, sample_offset;
 };
+
+// ---- gn_whiten_td_f32 for N = 8192 (M = 4096 = 64 x 64): two register-resident radix-64 passes per transform --------
+// 64 threads own one series.  Element n = 64*n1 + n2 of the packed complex series, bin k = k1 + 64*k2:
+//   pass A (thread = n2): DFT-64 over n1, times W_4096^(n2*k1), to shared memory S[k1][n2]
+//   pass B (thread = k1): DFT-64 over n2, bin k1 + 64*k2
+// Rows of S are 65 complex apart, so the column writes of pass A and the row reads of pass B are both conflict free.
+// Four shared-memory round trips per series (A->B, B->pointwise, pointwise->A', A'->B') instead of six with radix 16,
+// and one twiddled pass per transform instead of two.  EXPERIMENTAL (GN_WHITEN_RADIX=64): parity-green, shared-memory
+// wavefronts drop by 35 %, but 168 registers leave 12 warps per SM and the kernel becomes latency bound on its
+// global loads (window, twiddles, input): 1.86 TB/s against 2.53 TB/s for the radix-16 kernel (round-1 ncu capture
+// profiles/r01_ncu_whiten64_experiment.summary.txt).  Kept off by default.
+constexpr int W64_LD = 65;
+template <int DIR, class LOAD>
+__device__ __forceinline__ void pass_a64(float2* S, const float2* __restrict__ tw64, LOAD load) {
+    const int t = threadIdx.x;
+    float2 v[64];
+#pragma unroll
+    for (int n1 = 0; n1 < 64; ++n1) v[n1] = load(64 * n1 + t);
+    Dft<64, DIR>::run(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 64; ++k1) {
+        float2 y = v[Dft<64, DIR>::out_reg(k1)];
+        if (k1 > 0) {
+            const float2 w = __ldg(&tw64[k1 * 64 + t]);
+            y = DIR > 0 ? cmulc(y, w) : cmul(y, w);
+        }
+        S[k1 * W64_LD + t] = y;
+    }
+}
+template <int DIR, class STORE>
+__device__ __forceinline__ void pass_b64(const float2* S, STORE store) {
+    const int t = threadIdx.x;
+    float2 v[64];
+#pragma unroll
+    for (int n2 = 0; n2 < 64; ++n2) v[n2] = S[t * W64_LD + n2];
+    __syncthreads();          // every row has been read: the stores below may reuse the buffer
+    Dft<64, DIR>::run(v);
+#pragma unroll
+    for (int k2 = 0; k2 < 64; ++k2) store(t + 64 * k2, v[Dft<64, DIR>::out_reg(k2)]);
+}
+
+__global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
+    constexpr int M = 4096, N = 8192;
+    __shared__ float2 S[64 * W64_LD];
+    const float2* __restrict__ tw = a.tw;
+    const float2* __restrict__ tw64 = a.tw64;
+    const float2* __restrict__ win2 = reinterpret_cast<const float2*>(a.window);
+    const float* __restrict__ wts = a.weights;
+    auto sidx = [](int k) { return (k >> 6) * W64_LD + (k & 63); };
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        const float2* __restrict__ src2 = reinterpret_cast<const float2*>(a.x + (size_t)b * N);
+        {   // pull the series this CTA handles next into L2
+            const int bn = b + gridDim.x;
+            if (bn < a.batch) {
+                const char* nx = reinterpret_cast<const char*>(a.x + (size_t)bn * N);
+                for (int ln = threadIdx.x; ln < N * 4 / 128; ln += blockDim.x)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)ln * 128));
+            }
+        }
+        // forward: window, packed real -> complex, 64 x 64 FFT, result in natural order S[k/64][k%64]
+        pass_a64<-1>(S, tw64, [&](int n) {
+            const float2 xv = __ldg(&src2[n]), wv = __ldg(&win2[n]);
+            return make_float2(xv.x * wv.x, xv.y * wv.y);
+        });
+        __syncthreads();
+        pass_b64<-1>(S, [&](int k, float2 val) { S[sidx(k)] = val; });
+        __syncthreads();
+        // real-FFT split, whitening weights, inverse packing (same algebra as whiten_pointwise)
+        for (int j = 0; j <= 32; ++j) {
+            const int k = threadIdx.x + 64 * j;
+            if (k > M / 2) break;
+            if (k == 0) {
+                const float2 z = S[0];
+                const float y0 = __ldg(&wts[0]) * (z.x + z.y);
+                const float yM = __ldg(&wts[M]) * (z.x - z.y);
+                S[0] = make_float2(0.5f * (y0 + yM), 0.5f * (y0 - yM));
+                continue;
+            }
+            const int mk = M - k;
+            const float2 zk = S[sidx(k)], zm = S[sidx(mk)];
+            const float2 A2 = make_float2(zk.x + zm.x, zk.y - zm.y);
+            const float2 O2 = make_float2(zk.y + zm.y, zm.x - zk.x);
+            const float2 t = __ldg(&tw[k]);
+            const float wk = __ldg(&wts[k]), wm = __ldg(&wts[mk]);
+            const float s = 0.25f * (wk + wm), d = 0.25f * (wk - wm);
+            const float2 tO = cmul(t, O2), ctA = cmulc(A2, t);
+            const float2 E = make_float2(fmaf(s, A2.x, d * tO.x), fmaf(s, A2.y, d * tO.y));
+            const float2 Op = make_float2(fmaf(s, O2.x, d * ctA.x), fmaf(s, O2.y, d * ctA.y));
+            S[sidx(k)] = make_float2(E.x - Op.y, E.y + Op.x);
+            S[sidx(mk)] = make_float2(E.x + Op.y, -E.y + Op.x);
+        }
+        __syncthreads();
+        // inverse: pass A reads and writes only column t of S, so it runs in place
+        pass_a64<+1>(S, tw64, [&](int n) { return S[sidx(n)]; });
+        __syncthreads();
+        float* __restrict__ yb = a.y + (size_t)b * a.crop_len;
+        const float oscale = a.out_scale;
+        const int crop_lo = a.crop_lo, crop_len = a.crop_len;
+        pass_b64<+1>(S, [&](int j, float2 val) {
+            const int n0 = 2 * j - crop_lo;
+            if (((crop_lo | crop_len) & 1) == 0) {
+                if (n0 >= 0 && n0 < crop_len) *reinterpret_cast<float2*>(yb + n0) = make_float2(val.x * oscale, val.y * oscale);
+            } else {
+                if (n0 >= 0 && n0 < crop_len) yb[n0] = val.x * oscale;
+                if (n0 + 1 >= 0 && n0 + 1 < crop_len) yb[n0 + 1] = val.y * oscale;
+            }
+        });
+        __syncthreads();          // pass B has read its rows (sync inside) and nobody touches S until the next pass A
+    }
+}
 
 template <int LOG2M, int MODE>
 __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth_kernel(SynthArgs a) {
@@ -449,11 +587,28 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
     }
 }
 
+static int whiten_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GN_WHITEN_RADIX");
+        v = e ? atoi(e) : 16;      // 64 selects the experimental two-pass kernel below (measured slower)
+    }
+    return v;
+}
+
 template <int MODE>
 static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
     a.tw = plan->tw;
     a.ptw = plan->ptw;
+    a.tw64 = plan->tw64;
     const int M = plan->N / 2;
+    if (MODE == MODE_WHITEN && plan->log2M == 12 && plan->tw64 != nullptr && whiten_variant() == 64) {
+        int grid = a.batch;
+        const int cap = num_sms() * 6 * 4;
+        if (grid > cap) grid = cap;
+        whiten64_kernel<<<grid, 64, 0, st>>>(a);
+        return cuda_status("whiten64_kernel");
+    }
     const size_t smem = (size_t)(M + (M >> 4) + 1) * sizeof(float2);
     const int threads = M / 16;
     // persistent CTAs: a multiple of the SM count, at most the batch
@@ -628,6 +783,23 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
             return GN_ERR_CUDA;
         }
     }
+    p->tw64 = nullptr;
+    if (N == 8192) {
+        std::vector<float2> t(64 * 64);
+        for (int k1 = 0; k1 < 64; ++k1)
+            for (int tt = 0; tt < 64; ++tt) {
+                double ang = -2.0 * 3.14159265358979323846264338327950288 * (double)(k1 * tt) / 4096.0;
+                t[k1 * 64 + tt] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        if (cudaMalloc(&p->tw64, sizeof(float2) * t.size()) != cudaSuccess ||
+            cudaMemcpy(p->tw64, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(p->tw);
+            cudaFree(p->ptw);
+            delete p;
+            cuda_status("gn_fft_plan_create(tw64)");
+            return GN_ERR_CUDA;
+        }
+    }
     *out = p;
     return GN_OK;
 }
@@ -636,6 +808,7 @@ extern "C" int gn_fft_plan_destroy(gn_fft_plan* p) {
     if (p == nullptr) return GN_OK;
     cudaFree(p->tw);
     cudaFree(p->ptw);
+    if (p->tw64) cudaFree(p->tw64);
     delete p;
     return GN_OK;
 }

@@ -243,3 +243,30 @@ def test_waveform_ingest_matches_oracle(Nx):
     # no offsets: plain resample / max
     got0 = wvf.ingest_waveforms(x[:2]).cpu().numpy()
     assert rel_err(got0, np.stack([so.ingest_waveform(x[i], 0) for i in range(2)])) < 2e-5
+
+
+@pytest.mark.gpu
+def test_whiten_radix64_variant_matches_oracle():
+    """The experimental 64 x 64 two-pass whitening kernel (GN_WHITEN_RADIX=64) against the float64 oracle; run in a
+    subprocess because the variant is latched from the environment on first use."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys; sys.path.insert(0, %r)\n"
+        "from gennet_b200 import synth\n"
+        "from oracle import synth_oracle as so\n"
+        "fs, T = 2048, 4\n"
+        "psd = so.analytic_psd(fs, T)\n"
+        "s = synth.Synthesizer(fs, T, psd)\n"
+        "rs = np.random.RandomState(1)\n"
+        "x = (rs.normal(size=(5, fs * T)) * 1e-21)\n"
+        "for crop in (False, True):\n"
+        "    got = s.whiten_td(torch.as_tensor(x.astype(np.float32)).cuda(), crop=crop).cpu().numpy()\n"
+        "    ref = np.stack([so.whiten_data(x[i].astype(np.float32).astype(np.float64), T, fs, psd, 'td') for i in range(5)])\n"
+        "    if crop: ref = np.stack([so.crop_central(r, fs, T) for r in ref])\n"
+        "    err = np.abs(got - ref).max() / np.abs(ref).max()\n"
+        "    assert got.shape == ref.shape and err < 1e-6, (crop, err)\n"
+        "print('ok')\n") % os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+    env = dict(os.environ, GN_WHITEN_RADIX='64')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
