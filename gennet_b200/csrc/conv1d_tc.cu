@@ -41,6 +41,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// One lane of a fully converged warp.  The producer and MMA warps walk their schedules with all 32 lanes and issue
+// TMA / tcgen05 instructions from the elected lane: the operands then stay in uniform registers, whereas issuing from a
+// divergent `if (lane == 0)` region makes the compiler wrap every UTCHMMA / UTMALDG in a per-value re-convergence loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
@@ -172,34 +186,62 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 struct TileCoord {
     int b, par, m0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(int tile, int n_nt, int m_tiles, int npar, int BN) {
-    TileCoord c;
-    int nt = tile % n_nt;
-    int r = tile / n_nt;
-    int mt = r % m_tiles;
-    int r2 = r / m_tiles;
-    c.par = r2 % npar;
-    c.b = r2 / npar;
-    c.m0 = mt * TC_BM;
-    c.n0 = nt * BN;
-    return c;
-}
+
+// Walks tile = first, first + step, ... over the mixed-radix index (nt fastest, then mt, parity, sample) WITHOUT
+// divisions: the step is decomposed into digits once and added with carries.  With tens of tiles per CTA and as little
+// as a few hundred cycles of MMA work per tile on the small layers, a dozen integer divisions per tile in each of the
+// single-thread warp roles (producer, MMA issuer, I/O, column sums) was what bounded the tile rate.
+template <int BN>
+struct TileWalker {
+    int nt, mt, par, b;            // current digits
+    int d_nt, d_mt, d_par, d_b;    // digits of the step
+    int n_nt, m_tiles, npar, B;
+    __device__ __forceinline__ void init(int first, int step, int n_nt_, int m_tiles_, int npar_, int B_) {
+        n_nt = n_nt_; m_tiles = m_tiles_; npar = npar_; B = B_;
+        nt = first % n_nt; int r = first / n_nt;
+        mt = r % m_tiles; r /= m_tiles;
+        par = r % npar; b = r / npar;
+        d_nt = step % n_nt; r = step / n_nt;
+        d_mt = r % m_tiles; r /= m_tiles;
+        d_par = r % npar; d_b = r / npar;
+    }
+    __device__ __forceinline__ bool valid() const { return b < B; }
+    __device__ __forceinline__ void next() {
+        nt += d_nt;
+        int c = nt >= n_nt;
+        nt -= c ? n_nt : 0;
+        mt += d_mt + c;
+        c = mt >= m_tiles;
+        mt -= c ? m_tiles : 0;
+        par += d_par + c;
+        c = par >= npar;
+        par -= c ? npar : 0;
+        b += d_b + c;
+    }
+    __device__ __forceinline__ TileCoord coord() const {
+        TileCoord t;
+        t.b = b; t.par = par; t.m0 = mt * TC_BM; t.n0 = nt * BN;
+        return t;
+    }
+};
 
 // walks the (tile, slab) sequence of one CTA
 template <int BN>
 struct SlabIter {
-    int tile, sl, total, step, n_nt, m_tiles, npar;
+    TileWalker<BN> w;
+    int sl;
     TileCoord c;
-    __device__ __forceinline__ void init(int first, int total_, int step_, int n_nt_, int m_tiles_, int npar_) {
-        tile = first; sl = 0; total = total_; step = step_; n_nt = n_nt_; m_tiles = m_tiles_; npar = npar_;
-        if (tile < total) c = decode_tile(tile, n_nt, m_tiles, npar, BN);
+    __device__ __forceinline__ void init(int first, int step, int n_nt, int m_tiles, int npar, int B) {
+        w.init(first, step, n_nt, m_tiles, npar, B);
+        sl = 0;
+        c = w.coord();
     }
-    __device__ __forceinline__ bool valid() const { return tile < total; }
+    __device__ __forceinline__ bool valid() const { return w.valid(); }
     __device__ __forceinline__ void next() {
         if (++sl == BN / TC_SLAB_COLS) {
             sl = 0;
-            tile += step;
-            if (tile < total) c = decode_tile(tile, n_nt, m_tiles, npar, BN);
+            w.next();
+            c = w.coord();
         }
     }
 };
@@ -228,6 +270,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int nkb = kdim / TC_BK;
     const int n_nt = ((a.mode == 0) ? a.Cout : a.Cin) / BN;
     const int total_tiles = a.B * npar * a.m_tiles * n_nt;
+    const int sshift = (a.s == 2) ? 1 : 0;             // the stride is 1 or 2 (check_tc_geom)
+    (void)total_tiles;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
@@ -254,64 +298,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int g = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
-                int tap_first = 0, tap_step = 1, ntaps = a.k;
-                if (a.mode == 1) {
-                    tap_first = (c.par + a.p) % a.s;
-                    tap_step = a.s;
-                    ntaps = (a.k - tap_first + a.s - 1) / a.s;
-                }
-                for (int ti = 0; ti < ntaps; ++ti) {
-                    const int tap = tap_first + ti * tap_step;
-                    // first row coordinate (global, pre-stride) along the length axis of A
-                    const int rowc = (a.mode == 0) ? (c.m0 * a.s + tap - a.p) : (c.m0 + (c.par + a.p - tap) / a.s);
-                    for (int kb = 0; kb < nkb; ++kb, ++g) {
-                        const int st = g % STAGES, ph = (g / STAGES) & 1;
-                        mbar_wait(&empty[st], ph ^ 1);
+        // TMA producer: the whole warp walks the schedule (all values warp-uniform), one elected lane issues
+        uint32_t st = 0, ph = 0;
+        TileWalker<BN> tw;
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next()) {
+            const TileCoord c = tw.coord();
+            int tap_first = 0, tap_step = 1, ntaps = a.k;
+            if (a.mode == 1) {
+                tap_first = (c.par + a.p) & (a.s - 1);
+                tap_step = a.s;
+                ntaps = (a.k - tap_first + a.s - 1) >> sshift;
+            }
+            for (int ti = 0; ti < ntaps; ++ti) {
+                const int tap = tap_first + ti * tap_step;
+                // first row coordinate (global, pre-stride) along the length axis of A; in the data gradient
+                // par + p - tap is a multiple of the stride by construction, so the arithmetic shift is exact
+                const int rowc = (a.mode == 0) ? (c.m0 * a.s + tap - a.p) : (c.m0 + ((c.par + a.p - tap) >> sshift));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    if (elect_one()) {
                         uint8_t* sA = tiles + st * S::STAGE_BYTES;
                         uint8_t* sB = sA + S::A_BYTES;
                         mbar_expect_tx(&full[st], S::STAGE_BYTES);
                         tma_load_3d(sA, &mapA, &full[st], kb * TC_BK, rowc, c.b);
                         tma_load_3d(sB, &mapB, &full[st], kb * TC_BK, c.n0, tap);
                     }
+                    __syncwarp();
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
-            int g = 0, ti_local = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti_local) {
-                const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
-                int ntaps = a.k;
-                if (a.mode == 1) {
-                    const int tap_first = (c.par + a.p) % a.s;
-                    ntaps = (a.k - tap_first + a.s - 1) / a.s;
-                }
-                const int niter = ntaps * nkb;
-                const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
+        // MMA issuer: same structure; the elected lane issues the four K=16 instructions of a stage and the commits
+        constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+        // descriptor words: lo = (addr >> 4) | LBO(16 B) << 16, hi = SBO(1024 B) | version 1 | SWIZZLE_128B; only the
+        // address field changes, by (stage bytes >> 4) per stage and 2 per K=16 step (all below 2^14, no carry)
+        constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t lo_a0 = ((base >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t lo_b0 = (((base + S::A_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+        uint32_t st = 0, ph = 0;
+        int ti_local = 0;
+        TileWalker<BN> tw;
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next(), ++ti_local) {
+            int ntaps = a.k;
+            if (a.mode == 1) {
+                const int tap_first = (tw.par + a.p) & (a.s - 1);
+                ntaps = (a.k - tap_first + a.s - 1) >> sshift;
+            }
+            const int niter = ntaps * nkb;
+            const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(&full[st], ph);
                 tc_fence_after();
-                const uint32_t tacc = tmem + (uint32_t)(acc * BN);
-                for (int it = 0; it < niter; ++it, ++g) {
-                    const int st = g % STAGES, ph = (g / STAGES) & 1;
-                    mbar_wait(&full[st], ph);
-                    tc_fence_after();
-                    const uint32_t sA = base + st * S::STAGE_BYTES;
-                    const uint32_t sB = sA + S::A_BYTES;
+                if (elect_one()) {
+                    const uint32_t la = lo_a0 + st * (uint32_t)(S::STAGE_BYTES >> 4);
+                    const uint32_t lb = lo_b0 + st * (uint32_t)(S::STAGE_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
-                        uint64_t da = make_desc(sA + k * 32, 16, 1024);
-                        uint64_t db = make_desc(sB + k * 32, 16, 1024);
+                        const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(la + 2u * k);
+                        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(lb + 2u * k);
                         tc_mma_bf16(tacc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[st]);      // frees the smem stage once the MMAs have read it
                 }
-                tc_commit(&tmem_full[acc]);     // accumulator complete
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
             }
+            if (elect_one()) tc_commit(&tmem_full[acc]);     // accumulator complete
+            __syncwarp();
         }
     } else if (warp == 6) {
         // I/O thread: owns every bulk store (bulk groups are per thread) and, for dgrad, the mask loads.
@@ -319,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // memory once at most one group is pending, which frees buffer (s-1) % 4 == (s+3) % 4 for slab s+3.
         if (lane == 0) {
             SlabIter<BN> ld, st;
-            ld.init(blockIdx.x, total_tiles, gridDim.x, n_nt, a.m_tiles, npar);
+            ld.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B);
             st = ld;
             auto prepare = [&](int s_idx) {
                 mbar_arrive(&slab_ready[s_idx & (TC_RING - 1)]);
@@ -347,11 +404,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // lane = (row parity, channel pair): 64 conflict-free 4-byte loads per slab, rows past the end excluded.
         if (a.colsum != nullptr) {
             SlabIter<BN> it;
-            it.init(blockIdx.x, total_tiles, gridDim.x, n_nt, a.m_tiles, npar);
+            it.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B);
             const int pr = lane & 15, half = lane >> 4;
             for (int s = 0; it.valid(); ++s, it.next()) {
                 const int b = s & (TC_RING - 1);
-                const int rows_class = (a.L - it.c.par + npar - 1) / npar;       // rows of this parity class
+                const int rows_class = (a.L - it.c.par + npar - 1) >> ((npar == 2) ? 1 : 0);   // rows of this parity class
                 const int nrows = min(TC_BM, rows_class - it.c.m0);
                 mbar_wait(&slab_done[b], (s / TC_RING) & 1);
                 const uint8_t* slab = ring + b * TC_SLAB_BYTES;
@@ -402,16 +459,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 m[i] = (p != nullptr) ? __ldg(reinterpret_cast<const uint4*>(p + sl * 64) + i) : make_uint4(0, 0, 0, 0);
         };
         int ti_local = 0, s = 0;
-        if (AUX && (int)blockIdx.x < total_tiles) mask_prefetch_l2(mask_row(decode_tile(blockIdx.x, n_nt, a.m_tiles, npar, BN)));
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti_local) {
-            const TileCoord c = decode_tile(tile, n_nt, a.m_tiles, npar, BN);
+        TileWalker<BN> tw, tw_next;
+        tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B);
+        tw_next = tw;
+        tw_next.next();
+        if (AUX && tw.valid()) mask_prefetch_l2(mask_row(tw.coord()));
+        for (; tw.valid(); tw.next(), tw_next.next(), ++ti_local) {
+            const TileCoord c = tw.coord();
             const uint8_t* mrow = mask_row(c);
             uint4 mk[4];
             if (AUX) {
                 mask_load(mk, mrow, 0);
                 // pull the next tile's mask rows into L2 while this tile is being processed
-                if (tile + (int)gridDim.x < total_tiles)
-                    mask_prefetch_l2(mask_row(decode_tile(tile + gridDim.x, n_nt, a.m_tiles, npar, BN)));
+                if (tw_next.valid()) mask_prefetch_l2(mask_row(tw_next.coord()));
             }
             const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_ph);
