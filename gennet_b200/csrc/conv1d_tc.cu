@@ -630,14 +630,14 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int g = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const WgUnit w = decode_wg_unit<BN>(u, a);
-                int bb = w.it0 / a.lblocks, lb = w.it0 - bb * a.lblocks;
-                for (int i = 0; i < w.niter; ++i, ++g) {
-                    const int st = g % STAGES, ph = (g / STAGES) & 1;
-                    mbar_wait(&empty[st], ph ^ 1);
+        // producer: the whole warp walks the schedule, one elected lane issues (operands stay in uniform registers)
+        uint32_t st = 0, ph = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const WgUnit w = decode_wg_unit<BN>(u, a);
+            int bb = w.it0 / a.lblocks, lb = w.it0 - bb * a.lblocks;
+            for (int i = 0; i < w.niter; ++i) {
+                mbar_wait(&empty[st], ph ^ 1);
+                if (elect_one()) {
                     const int l0 = lb * 64;
                     uint8_t* sA = tiles + st * STAGE_BYTES;
                     uint8_t* sB = sA + A_BYTES;
@@ -657,38 +657,46 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
                         for (int h = 0; h < BN / 64; ++h)
                             tma_load_3d(sB + h * 8192, &mapX, &full[st], w.n0 + h * 64, xrow, bb);
                     }
-                    if (++lb == a.lblocks) { lb = 0; ++bb; }
                 }
+                __syncwarp();
+                if (++lb == a.lblocks) { lb = 0; ++bb; }
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TC_BM, BN, 1, 1);     // both operands MN-major
-            int g = 0, ul = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
-                const WgUnit w = decode_wg_unit<BN>(u, a);
-                const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        constexpr uint32_t idesc = make_idesc(TC_BM, BN, 1, 1);     // both operands MN-major
+        // MN-major SW128 descriptors: 64-element MN blocks LBO = 8192 B apart, 8-row K groups SBO = 1024 B apart, 16 K
+        // rows per instruction = 2048 B; only the 14-bit address field changes between instructions
+        constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t lo_a0 = ((base >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);
+        const uint32_t lo_b0 = (((base + A_BYTES) >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);
+        uint32_t st = 0, ph = 0;
+        int ul = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+            const WgUnit w = decode_wg_unit<BN>(u, a);
+            const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+            for (int i = 0; i < w.niter; ++i) {
+                mbar_wait(&full[st], ph);
                 tc_fence_after();
-                const uint32_t tacc = tmem + (uint32_t)(acc * BN);
-                for (int i = 0; i < w.niter; ++i, ++g) {
-                    const int st = g % STAGES, ph = (g / STAGES) & 1;
-                    mbar_wait(&full[st], ph);
-                    tc_fence_after();
-                    const uint32_t sA = base + st * STAGE_BYTES;
-                    const uint32_t sB = sA + A_BYTES;
+                if (elect_one()) {
+                    const uint32_t la = lo_a0 + st * (uint32_t)(STAGE_BYTES >> 4);
+                    const uint32_t lb = lo_b0 + st * (uint32_t)(STAGE_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < 64 / 16; ++k) {
-                        // MN-major SW128: 64-element MN blocks LBO = 8192 B apart, 8-row K groups SBO = 1024 B apart;
-                        // 16 K rows per instruction = 2048 B
-                        uint64_t da = make_desc(sA + k * 2048, 8192, 1024);
-                        uint64_t db = make_desc(sB + k * 2048, 8192, 1024);
+                        const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(la + (2048u >> 4) * k);
+                        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(lb + (2048u >> 4) * k);
                         tc_mma_bf16(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[st]);
                 }
-                tc_commit(&tmem_full[acc]);
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
             }
+            if (elect_one()) tc_commit(&tmem_full[acc]);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
