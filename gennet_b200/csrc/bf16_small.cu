@@ -26,9 +26,9 @@ __global__ void __launch_bounds__(256) conv_smallcin_fwd_kernel(const float* __r
     const long long total = (long long)B * Lout * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i % groups);
-        const long long row = i / groups;
-        const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
+        int g, l;
+        const long long row = fast_div(i, groups, g);
+        const int b = (int)fast_div(row, Lout, l);
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = sw[nw + g * 8 + j];
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     if (ry < nry) {
         for (long long row = r0 + ry; row < r1; row += nry) {
-            const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
+            int l;
+            const int b = (int)fast_div(row, Lout, l);
             uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * ld + co0) + g);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
             float gv[8];
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const __nv_bfl
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long row = warp0; row < rows; row += nwarps) {
-        const int b = (int)(row / Lout), l = (int)(row - (long long)b * Lout);
+        int l;
+        const int b = (int)fast_div(row, Lout, l);
         float acc[KMAX * CIN];
 #pragma unroll
         for (int i = 0; i < KMAX * CIN; ++i) acc[i] = 0.f;
@@ -380,10 +382,9 @@ __global__ void __launch_bounds__(256) upsample_bf16_kernel(const __nv_bfloat16*
                                                             long long rows_out, int L, int C8, int size) {
     const long long total = rows_out * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C8);
-        const long long r = i / C8;                 // output row = b * (L*size) + j
-        const long long b = r / ((long long)L * size);
-        const int j = (int)(r - b * (long long)L * size);
+        int c, j;
+        const long long r = fast_div(i, C8, c);     // output row = b * (L*size) + j
+        const long long b = fast_div(r, L * size, j);
         reinterpret_cast<uint4*>(y)[i] = __ldg(reinterpret_cast<const uint4*>(x) + (b * L + j / size) * C8 + c);
     }
 }
@@ -392,8 +393,8 @@ __global__ void __launch_bounds__(256) upsample_bwd_bf16_kernel(const __nv_bfloa
                                                                 int size) {
     const long long total = rows_in * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C8);
-        const long long r = i / C8;                 // input row = b * L + l ; its copies are rows r*size .. r*size+size-1
+        int c;
+        const long long r = fast_div(i, C8, c);     // input row = b * L + l ; its copies are rows r*size .. r*size+size-1
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -432,7 +433,8 @@ __global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const __nv_bfloat16
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const float bv = bias ? bias[0] : 0.f;
     for (long long row = warp0; row < rows; row += nwarps) {
-        const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+        int pos;
+        const int b = (int)fast_div(row, L, pos);
         float acc[KMAX];
 #pragma unroll
         for (int t = 0; t < KMAX; ++t) acc[t] = 0.f;
@@ -482,9 +484,9 @@ __global__ void __launch_bounds__(256) conv_cout1_dgrad_kernel(const float* __re
     const int C8 = Cin / 8;
     const long long total = (long long)B * L * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C8);
-        const long long row = i / C8;
-        const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+        int c, pos;
+        const long long row = fast_div(i, C8, c);
+        const int b = (int)fast_div(row, L, pos);
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = 0.f;
@@ -523,7 +525,8 @@ __global__ void __launch_bounds__(256) conv_cout1_wgrad_kernel(const __nv_bfloat
         for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
 #pragma unroll 4
     for (long long row = r0; row < r1; ++row) {
-        const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+        int pos;
+        const int b = (int)fast_div(row, L, pos);
         uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * Cin) + c);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
         float xv[8];

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ beta, float* __restrict__ y,
                                                        long long n, int C, float eps, int use_var) {
     GN_EW_LOOP(i, n) {
-        int c = (int)(i % C);
+        int c;
+        (void)fast_div(i, C, c);
         float is = use_var ? 1.0f / sqrtf(inv[c] + eps) : inv[c];
         y[i] = (x[i] - mean[c]) * is * gamma[c] + beta[c];
     }
@@ -116,7 +117,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const double* __restrict__ sums, double n_total,
                                                            float* __restrict__ dx, long long n, int C) {
     GN_EW_LOOP(i, n) {
-        int c = (int)(i % C);
+        int c;
+        (void)fast_div(i, C, c);
         float mu = stats[c], is = stats[C + c];
         float xh = (x[i] - mu) * is;
         float sdy = (float)(sums[c] / n_total), sdx = (float)(sums[C + c] / n_total);
@@ -200,8 +202,8 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(float* __restrict__ out, 
 __global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int L,
                                                            int C, int size, long long n_out) {
     GN_EW_LOOP(i, n_out) {
-        int c = (int)(i % C);
-        long long r = i / C;
+        int c;
+        long long r = fast_div(i, C, c);
         int lo = (int)(r % ((long long)L * size));
         long long b = r / ((long long)L * size);
         y[i] = x[(b * L + lo / size) * C + c];
@@ -210,8 +212,8 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
                                                            int L, int C, int size, long long n_in) {
     GN_EW_LOOP(i, n_in) {
-        int c = (int)(i % C);
-        long long r = i / C;
+        int c;
+        long long r = fast_div(i, C, c);
         int l = (int)(r % L);
         long long b = r / L;
         float s = 0.f;
@@ -222,8 +224,8 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int L,
                                                           int C, int pool, int Lo, long long n_out) {
     GN_EW_LOOP(i, n_out) {
-        int c = (int)(i % C);
-        long long r = i / C;
+        int c;
+        long long r = fast_div(i, C, c);
         int lo = (int)(r % Lo);
         long long b = r / Lo;
         float m = x[(b * L + (long long)lo * pool) * C + c];
@@ -235,8 +237,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
                                                           const float* __restrict__ dy, float* __restrict__ dx,
                                                           int L, int C, int pool, int Lo, long long n_in) {
     GN_EW_LOOP(i, n_in) {
-        int c = (int)(i % C);
-        long long r = i / C;
+        int c;
+        long long r = fast_div(i, C, c);
         int l = (int)(r % L);
         long long b = r / L;
         int lo = l / pool;

@@ -74,6 +74,20 @@ __device__ __forceinline__ T block_sum(T v, T* smem32) {
     return r;
 }
 
+// x / d and x % d for a non-negative 64-bit x: the 32-bit unsigned division (a handful of instructions) whenever the
+// operands fit, which they do for every tensor that fits a GPU; the generic 64-bit division is a ~100-instruction
+// subroutine and used to dominate the index math of the streaming kernels.
+__device__ __forceinline__ long long fast_div(long long x, int d, int& rem) {
+    if (((unsigned long long)x >> 32) == 0ull) {
+        const unsigned q = (unsigned)x / (unsigned)d;
+        rem = (int)((unsigned)x - q * (unsigned)d);
+        return (long long)q;
+    }
+    const long long q = x / d;
+    rem = (int)(x - q * d);
+    return q;
+}
+
 // activation codes shared by fused epilogues and the elementwise kernels.  The *_t forms take the code at
 // compile time; act_dispatch() turns a run-time code into one uniform branch OUTSIDE the element loops (a
 // per-element `switch` compiles to an indirect branch per element, which serialises a fused epilogue).
