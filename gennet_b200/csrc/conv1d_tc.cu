@@ -140,7 +140,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 constexpr int TC_BM = 128;          // rows of an output tile (UMMA M)
 constexpr int TC_BK = 64;           // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 256;     // warps: 0 TMA producer, 1 MMA, 2-5 epilogue, 6 I/O (bulk stores), 7 column sums
+constexpr int TC_THREADS = 416;     // warps: 0 TMA producer, 1 MMA, 2-5 and 6-9 epilogue (two sets that take alternate
+                                    // slabs: a lone warp per TMEM lane quarter needs ~900 cycles per slab, which bounds
+                                    // every layer whose tile has little MMA work), 10 I/O (bulk stores), 11-12 column sums (alternate slabs)
+constexpr int TC_EPI_SETS = 2;
 constexpr int TC_WG_THREADS = 192;  // wgrad kernel: warps 0 TMA producer, 1 MMA, 2-5 epilogue
 
 struct TcArgs {
@@ -282,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);      // one arrival per epilogue warp
+            mbar_init(&tmem_empty[i], 4 * TC_EPI_SETS);      // one arrival per epilogue warp
         }
         for (int i = 0; i < TC_RING; ++i) {
             mbar_init(&slab_ready[i], 1);
@@ -370,7 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (elect_one()) tc_commit(&tmem_full[acc]);     // accumulator complete
             __syncwarp();
         }
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         // I/O thread: owns every bulk store (bulk groups are per thread) and, for dgrad, the mask loads.
         // Slab step s uses ring buffer s % 4.  After committing store s, store s-1 has been read out of shared
         // memory once at most one group is pending, which frees buffer (s-1) % 4 == (s+3) % 4 for slab s+3.
@@ -398,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             tma_store_wait_read<0>();
         }
-    } else if (warp == 7) {
+    } else if (warp >= 11) {
         // column sums of the finished bf16 slabs (dgrad only): the per-channel sum of dX over (b, l) is the bias
         // gradient of the layer that produced this conv's input, so that layer needs no separate pass over dX.
         // lane = (row parity, channel pair): 64 conflict-free 4-byte loads per slab, rows past the end excluded.
@@ -406,7 +409,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             SlabIter<BN> it;
             it.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B);
             const int pr = lane & 15, half = lane >> 4;
+            const int cset = warp - 11;                        // this warp takes slabs with s % 2 == cset
             for (int s = 0; it.valid(); ++s, it.next()) {
+                if ((s & 1) != cset) continue;
                 const int b = s & (TC_RING - 1);
                 const int rows_class = (a.L - it.c.par + npar - 1) >> ((npar == 2) ? 1 : 0);   // rows of this parity class
                 const int nrows = min(TC_BM, rows_class - it.c.m0);
@@ -437,6 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // TMEM -> registers -> bias / activation / mask -> bf16 -> swizzled slab -> (I/O thread) TMA store;
         // rows past the end of the sample are clipped by the tensor map.
         const int q = warp & 3;
+        const int eset = (warp - 2) >> 2;                       // epilogue set: slabs eset, eset + 2, ... of every tile
         const int row = q * 32 + lane;
         const uint32_t sw = (uint32_t)(row >> 1) & 3u;          // SWIZZLE_64B: 16-byte chunk index XOR address bits 7-8
         constexpr int NS = BN / TC_SLAB_COLS;
@@ -458,7 +464,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int i = 0; i < 4; ++i)
                 m[i] = (p != nullptr) ? __ldg(reinterpret_cast<const uint4*>(p + sl * 64) + i) : make_uint4(0, 0, 0, 0);
         };
-        int ti_local = 0, s = 0;
+        int ti_local = 0;
         TileWalker<BN> tw, tw_next;
         tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B);
         tw_next = tw;
@@ -469,7 +475,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint8_t* mrow = mask_row(c);
             uint4 mk[4];
             if (AUX) {
-                mask_load(mk, mrow, 0);
+                mask_load(mk, mrow, eset);
                 // pull the next tile's mask rows into L2 while this tile is being processed
                 if (tw_next.valid()) mask_prefetch_l2(mask_row(tw_next.coord()));
             }
@@ -478,12 +484,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_after();
             const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int sl = 0; sl < NS; ++sl, ++s) {
+            for (int sl = eset; sl < NS; sl += TC_EPI_SETS) {
+                const int s = ti_local * NS + sl;          // position of this slab in the CTA's slab sequence
                 uint4 mk_next[4];
-                if (AUX && sl + 1 < NS) mask_load(mk_next, mrow, sl + 1);
+                if (AUX && sl + TC_EPI_SETS < NS) mask_load(mk_next, mrow, sl + TC_EPI_SETS);
                 uint32_t v[32];
                 tmem_ld32(tacc + (uint32_t)(sl * TC_SLAB_COLS), v);
-                if (sl == NS - 1) {
+                if (sl + TC_EPI_SETS >= NS) {
                     // all of this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
