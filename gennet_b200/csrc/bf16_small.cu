@@ -53,6 +53,56 @@ __global__ void __launch_bounds__(256) conv_smallcin_fwd_kernel(const float* __r
     }
 }
 
+// Register-resident variant for k <= 5: a thread keeps the k*CIN*8 weights and 8 biases of its channel group in
+// registers and walks a run of consecutive output rows of one sample, so a row costs its k*CIN input loads, the FMAs,
+// the (compile-time) activation and one 128-bit store -- no shared-memory weight reads and no per-row index division.
+template <int CIN, int KMAX, int KIND>
+__global__ void __launch_bounds__(256) conv_smallcin_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                    const float* __restrict__ bias,
+                                                                    __nv_bfloat16* __restrict__ y, int B, int L, int Lout,
+                                                                    int Cout, int k, int s, int p, float ap, int gpb, int run,
+                                                                    int runs_per_sample, long long n_runs) {
+    const int g = blockIdx.y * gpb + threadIdx.x % gpb;          // channel group (8 channels)
+    const int lane_r = threadIdx.x / gpb, lanes = blockDim.x / gpb;
+    if (g >= Cout / 8 || lane_r >= lanes) return;
+    float wr[KMAX * CIN][8], bv[8];
+#pragma unroll
+    for (int i = 0; i < KMAX * CIN; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wr[i][j] = (i < k * CIN) ? __ldg(&w[(size_t)i * Cout + g * 8 + j]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = bias ? __ldg(&bias[g * 8 + j]) : 0.f;
+    for (long long r = (long long)blockIdx.x * lanes + lane_r; r < n_runs; r += (long long)gridDim.x * lanes) {
+        int ri;
+        const int b = (int)fast_div(r, runs_per_sample, ri);
+        const int l0 = ri * run, l1 = min(Lout, l0 + run);
+        const float* __restrict__ xb = x + (size_t)b * L * CIN;
+        __nv_bfloat16* __restrict__ yb = y + ((size_t)b * Lout) * Cout + g * 8;
+        for (int l = l0; l < l1; ++l) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = bv[j];
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) {
+                const int pos = l * s + t - p;
+                if (t < k && pos >= 0 && pos < L) {
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) {
+                        const float xv = __ldg(&xb[(size_t)pos * CIN + c]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[t * CIN + c][j], acc[j]);
+                    }
+                }
+            }
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                h[j] = __floats2bfloat162_rn(act_fwd_t<KIND>(acc[2 * j], ap), act_fwd_t<KIND>(acc[2 * j + 1], ap));
+            *reinterpret_cast<uint4*>(yb + (size_t)l * Cout) = *reinterpret_cast<uint4*>(h);
+        }
+    }
+}
+
 // ---- first-layer weight gradient: dw f32 (k,CIN,Cout), db f32 (Cout) from x f32 and dy bf16 (pre-activation grad) ----
 // thread = 8 consecutive output channels (one 128-bit dy load per row) x one row lane; k*CIN*8 (+8 bias) partial sums
 template <int CIN, int KMAX>
@@ -76,9 +126,14 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
     const long long rows = (long long)B * Lout;
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     if (ry < nry) {
-        for (long long row = r0 + ry; row < r1; row += nry) {
-            int l;
-            const int b = (int)fast_div(row, Lout, l);
+        // every row lane walks its own contiguous run of the block's rows: (sample, position) advance incrementally
+        const long long per_lane = (r1 - r0 + nry - 1) / nry;
+        const long long q0 = r0 + (long long)ry * per_lane, q1 = min(r1, q0 + per_lane);
+        int l = 0;
+        int b = (q0 < q1) ? (int)fast_div(q0, Lout, l) : 0;
+#pragma unroll 4
+        for (long long row = q0; row < q1; ++row, ++l) {
+            if (l == Lout) { l = 0; ++b; }
             uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * ld + co0) + g);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
             float gv[8];
@@ -657,6 +712,35 @@ extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const
     if (B == 0) return GN_OK;
     const size_t smem = sizeof(float) * ((size_t)k * Cin * Cout + Cout);
     GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
+    if (k <= 5) {
+        // register-resident path: 256 threads = gpb channel groups x row lanes; a run of 32 rows per thread visit
+        const int groups = Cout / 8;
+        const int gpb = groups < 32 ? groups : 32;
+        const int run = 32;
+        const int rps = (Lout + run - 1) / run;
+        const long long n_runs = (long long)B * rps;
+        const int lanes = 256 / gpb;
+        long long bx = (n_runs + lanes - 1) / lanes;
+        const long long cap = 8LL * num_sms();
+        if (bx > cap) bx = cap;
+        dim3 grid((unsigned)bx, (unsigned)((groups + gpb - 1) / gpb));
+        cudaStream_t st = as_stream(stream);
+        __nv_bfloat16* yy = (__nv_bfloat16*)y;
+#define GN_SCF(CI, KIND) conv_smallcin_fwd_reg_kernel<CI, 5, KIND><<<grid, 256, 0, st>>>(x, w, bias, yy, B, L, Lout, Cout, k, stride, pad_left, act_param, gpb, run, rps, n_runs)
+#define GN_SCF_ACT(CI)                                              \
+        switch (act) {                                              \
+            case GN_ACT_RELU: GN_SCF(CI, GN_ACT_RELU); break;       \
+            case GN_ACT_TANH: GN_SCF(CI, GN_ACT_TANH); break;       \
+            case GN_ACT_SIGMOID: GN_SCF(CI, GN_ACT_SIGMOID); break; \
+            case GN_ACT_LEAKY: GN_SCF(CI, GN_ACT_LEAKY); break;     \
+            case GN_ACT_RELU_MAX: GN_SCF(CI, GN_ACT_RELU_MAX); break; \
+            default: GN_SCF(CI, GN_ACT_NONE); break;                \
+        }
+        if (Cin == 1) { GN_SCF_ACT(1) } else { GN_SCF_ACT(2) }
+#undef GN_SCF_ACT
+#undef GN_SCF
+        return cuda_status("conv_smallcin_fwd_reg_kernel");
+    }
     long long total = (long long)B * Lout * (Cout / 8);
     unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
     if (Cin == 1)
@@ -679,7 +763,7 @@ extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, flo
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);
     if (B == 0) return GN_OK;
     const long long rows = (long long)B * Lout;
-    long long blocks = 4LL * num_sms();
+    long long blocks = 2LL * num_sms();      // few blocks: each ends in k*Cin*Cout same-address atomics, which serialise in L2
     long long per = (rows + blocks - 1) / blocks;
     if (per < 64) per = 64;
     blocks = (rows + per - 1) / per;
