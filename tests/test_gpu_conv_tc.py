@@ -27,6 +27,10 @@ CASES = [
     (2, 253, 256, 512, 5, 2, 'valid'),    # odd length, stride 2
     (2, 64, 512, 64, 5, 1, 'same'),       # BN = 64 path, many K blocks
     (1, 1018, 512, 1024, 5, 2, 'valid'),  # q tower conv5 geometry
+    # many tiles per persistent CTA: the division-free tile walker carries through every digit (n-tile, m-tile,
+    # parity class, sample) and both TMEM buffers / the slab ring wrap many times
+    (300, 600, 64, 128, 5, 1, 'valid'),   # 1500 forward tiles, BN = 128 / 64
+    (96, 515, 256, 512, 5, 2, 'same'),    # 576 tiles: two n-tiles forward, two parity classes in the data gradient
 ]
 
 
