@@ -14,6 +14,7 @@
 
 #include <cstdlib>
 #include <math.h>
+#include <mutex>
 #include <vector>
 
 struct gn_fft_plan {
@@ -23,6 +24,17 @@ struct gn_fft_plan {
     float2* ptw;  // device, per-pass Stockham twiddles laid out [pass][r-1][k] = exp(-2*pi*i*r*k/(p*R)), k < p,
                   // so that the lanes of a warp (consecutive k) read consecutive 8-byte entries
     float2* tw64; // device, N == 8192 only: [k1][t] = exp(-2*pi*i*k1*t/4096), k1, t < 64 (64 x 64 decomposition)
+    // Whitening coefficient tables (alpha_k, beta_k), M entries each, rebuilt by a prologue kernel on every call from
+    // the caller's weights.  A slot is keyed by the weights pointer: calls with the same pointer write the same values
+    // (the caller may not change the weights while a call that reads them is in flight), so they can share the slot on
+    // any number of streams; a slot handed to another pointer first waits for the event that covers its earlier users.
+    static constexpr int NSLOT = 4;
+    float2* coef[NSLOT];
+    const void* coef_key[NSLOT];
+    cudaEvent_t coef_done[NSLOT];
+    bool coef_used[NSLOT];
+    int coef_next;
+    std::mutex mu;
 };
 
 namespace gn {
@@ -115,6 +127,17 @@ struct Dft<16, DIR> {
     static __device__ __forceinline__ constexpr int out_reg(int r) { return 4 * (r & 3) + (r >> 2); }
 };
 
+// Table load (twiddles, whitening coefficients) that stays where it is written.  The tables are read-only, so a
+// __ldg / ld.global.nc of them is free to move: loop-invariant code motion lifts the per-thread loads (identical for
+// every series) out of the persistent loop, and ptxas hoists them over the preceding __syncthreads into the previous
+// pass -- in both cases the values no longer fit in the 64-register budget and are spilled to local memory, which
+// costs more L1 wavefronts than the L1-resident loads themselves.  A coherent ld.global is ordered by the barrier.
+__device__ __forceinline__ float2 ld_table(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.ca.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
 // shared-memory index with one pad slot per 16 complex values (kills the stride-R store conflicts)
 __device__ __forceinline__ int PADI(int i) { return i + (i >> 4); }
 
@@ -126,15 +149,29 @@ __device__ __forceinline__ int padi_off(int base_idx, int r) {
     return PADI(base_idx + r * STRIDE);
 }
 
+// Pass adapters.  get<T>(i, r, j) fetches logical element i + r*T of the pass input, put<P>(base, r, v, j) writes logical
+// element base + r*P of the pass output.  j is the compile-time slot of that element in the thread's own 16 points
+// whenever the element is tid + j*(M/16) (first-pass inputs, last-pass outputs): register adapters index with it.
 struct SmemIn {
     const float2* buf;
     template <int T>
-    __device__ __forceinline__ float2 get(int i, int r) const { return buf[padi_off<T>(i, r)]; }
+    __device__ __forceinline__ float2 get(int i, int r, int) const { return buf[padi_off<T>(i, r)]; }
 };
 struct SmemOut {
     float2* buf;
     template <int P>
-    __device__ __forceinline__ void put(int base, int r, float2 v) const { buf[padi_off<P>(base, r)] = v; }
+    __device__ __forceinline__ void put(int base, int r, float2 v, int) const { buf[padi_off<P>(base, r)] = v; }
+};
+// the thread's 16 points z[j] = element tid + j*(M/16), kept in registers between two transforms
+struct RegIn {
+    const float2* z;
+    template <int T>
+    __device__ __forceinline__ float2 get(int, int, int j) const { return z[j]; }
+};
+struct RegOut {
+    float2* z;
+    template <int P>
+    __device__ __forceinline__ void put(int, int, float2 v, int j) const { z[j] = v; }
 };
 
 // adapters for pass inputs/outputs expressed on the logical index
@@ -142,13 +179,13 @@ template <class F>
 struct IdxIn {
     F f;
     template <int T>
-    __device__ __forceinline__ float2 get(int i, int r) const { return f(i + r * T); }
+    __device__ __forceinline__ float2 get(int i, int r, int j) const { return f(i + r * T, j); }
 };
 template <class F>
 struct IdxOut {
     F f;
     template <int P>
-    __device__ __forceinline__ void put(int base, int r, float2 v) const { f(base + r * P, v); }
+    __device__ __forceinline__ void put(int base, int r, float2 v, int) const { f(base + r * P, v); }
 };
 template <class F>
 __device__ __forceinline__ IdxIn<F> make_in(F f) { return IdxIn<F>{f}; }
@@ -156,10 +193,10 @@ template <class F>
 __device__ __forceinline__ IdxOut<F> make_out(F f) { return IdxOut<F>{f}; }
 
 // One Stockham pass of radix R with sub-transform length P over the M-point array; each thread owns 16/R
-// butterflies (16 points).  IN::get<T>(i, r) fetches logical element i + r*T of the pass input, OUT::put<P>(base, r, v)
-// writes logical element base + r*P of the pass output.  A __syncthreads separates loads from stores so that the
-// pass may run in place.  ptw = this pass's twiddle table [r-1][k].
-template <int R, int P, int DIR, int LOG2M, class IN, class OUT>
+// butterflies (16 points).  A __syncthreads separates loads from stores so that the pass may run in place.
+// ptw = this pass's twiddle table [r-1][k].  TWP = 1 (radix 16 only): six table rows (r = 1,2,3,4,8,12) are loaded and
+// the other nine twiddles are formed as w^(4a) * w^b -- 2.5x fewer L1 wavefronts for 36 more FP32 operations.
+template <int R, int P, int DIR, int LOG2M, int TWP, class IN, class OUT>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ ptw, const IN& in, const OUT& out,
                                          bool sync_before_store) {
     constexpr int M = 1 << LOG2M;
@@ -172,13 +209,28 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ ptw, const I
     for (int it = 0; it < IT; ++it) {
         const int i = tid + it * NT;
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[it][r] = in.template get<T>(i, r);
+        for (int r = 0; r < R; ++r) v[it][r] = in.template get<T>(i, r, it + r * IT);
         if (P > 1) {
             const int k = i & (P - 1);
+            if constexpr (TWP == 1 && R == 16) {
+                float2 wl[4], wh[4];
 #pragma unroll
-            for (int r = 1; r < R; ++r) {
-                const float2 w = __ldg(&ptw[(r - 1) * P + k]);
-                v[it][r] = DIR > 0 ? cmulc(v[it][r], w) : cmul(v[it][r], w);
+                for (int b = 1; b < 4; ++b) {
+                    wl[b] = ld_table(&ptw[(b - 1) * P + k]);
+                    wh[b] = ld_table(&ptw[(4 * b - 1) * P + k]);
+                }
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    const int a = r >> 2, b = r & 3;
+                    const float2 w = a == 0 ? wl[b] : (b == 0 ? wh[a] : cmul(wh[a], wl[b]));
+                    v[it][r] = DIR > 0 ? cmulc(v[it][r], w) : cmul(v[it][r], w);
+                }
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    const float2 w = ld_table(&ptw[(r - 1) * P + k]);
+                    v[it][r] = DIR > 0 ? cmulc(v[it][r], w) : cmul(v[it][r], w);
+                }
             }
         }
         Dft<R, DIR>::run(v[it]);
@@ -190,7 +242,7 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ ptw, const I
         const int k = i & (P - 1);
         const int base = (i - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) out.template put<P>(base, r, v[it][Dft<R, DIR>::out_reg(r)]);
+        for (int r = 0; r < R; ++r) out.template put<P>(base, r, v[it][Dft<R, DIR>::out_reg(r)], r + it * R);
     }
 }
 
@@ -236,7 +288,7 @@ struct Plan {
     static constexpr int table_size() { return table_offset(N16); }
 };
 
-template <int DIR, int LOG2M, int J, class IN, class OUTL>
+template <int DIR, int LOG2M, int TWP, int J, class IN, class OUTL>
 __device__ __forceinline__ void fft16_passes(float2* buf, const float2* __restrict__ ptw, const IN& first_in,
                                              bool first_is_custom, bool first_from_smem, const OUTL& last_out,
                                              bool last_custom) {
@@ -249,31 +301,33 @@ __device__ __forceinline__ void fft16_passes(float2* buf, const float2* __restri
         SmemIn sin{buf};
         SmemOut sout{buf};
         if (J == 0 && first_is_custom) {
-            if (last && last_custom) fft_pass<16, P, DIR, LOG2M>(tab, first_in, last_out, first_from_smem);
-            else fft_pass<16, P, DIR, LOG2M>(tab, first_in, sout, first_from_smem);
+            if (last && last_custom) fft_pass<16, P, DIR, LOG2M, TWP>(tab, first_in, last_out, first_from_smem);
+            else fft_pass<16, P, DIR, LOG2M, TWP>(tab, first_in, sout, first_from_smem);
         } else {
-            if (last && last_custom) fft_pass<16, P, DIR, LOG2M>(tab, sin, last_out, false);
-            else fft_pass<16, P, DIR, LOG2M>(tab, sin, sout, true);
+            if (last && last_custom) fft_pass<16, P, DIR, LOG2M, TWP>(tab, sin, last_out, false);
+            else fft_pass<16, P, DIR, LOG2M, TWP>(tab, sin, sout, true);
         }
         if (!(last && last_custom)) __syncthreads();
-        fft16_passes<DIR, LOG2M, J + 1>(buf, ptw, first_in, first_is_custom, first_from_smem, last_out, last_custom);
+        fft16_passes<DIR, LOG2M, TWP, J + 1>(buf, ptw, first_in, first_is_custom, first_from_smem, last_out,
+                                             last_custom);
     }
 }
 
-// Full M-point complex FFT.  first_in reads the logical input of the first pass; the result ends in smem `buf`
-// (padded natural order) unless last_out is used for the final pass (last_custom).
-template <int DIR, int LOG2M, class IN, class OUTL>
+// Full M-point complex FFT.  first_in reads the logical input of the first pass (first_from_smem: it reads `buf`, so
+// the pass synchronises before it stores); the result ends in smem `buf` (padded natural order) unless last_out is
+// used for the final pass (last_custom).
+template <int DIR, int LOG2M, int TWP = 0, class IN, class OUTL>
 __device__ __forceinline__ void fft_full(float2* buf, const float2* __restrict__ ptw, const IN& first_in,
                                          bool first_from_smem, const OUTL& last_out, bool last_custom) {
     constexpr int REM = Plan<LOG2M>::REM;
     if constexpr (REM > 1) {
         // a REM pass is never the last one (N16 >= 1 for every supported size); it has P = 1: no twiddles
         SmemOut sout{buf};
-        fft_pass<REM, 1, DIR, LOG2M>(ptw, first_in, sout, first_from_smem);
+        fft_pass<REM, 1, DIR, LOG2M, TWP>(ptw, first_in, sout, first_from_smem);
         __syncthreads();
-        fft16_passes<DIR, LOG2M, 0>(buf, ptw, first_in, false, false, last_out, last_custom);
+        fft16_passes<DIR, LOG2M, TWP, 0>(buf, ptw, first_in, false, false, last_out, last_custom);
     } else {
-        fft16_passes<DIR, LOG2M, 0>(buf, ptw, first_in, true, first_from_smem, last_out, last_custom);
+        fft16_passes<DIR, LOG2M, TWP, 0>(buf, ptw, first_in, true, first_from_smem, last_out, last_custom);
     }
 }
 
@@ -351,6 +405,7 @@ struct SynthArgs {
     const float2* tw;
     const float2* ptw;
     const float2* tw64;
+    const float2* coef;      // (M) whitening coefficients (alpha_k, beta_k) of whiten_coef_kernel (VAR >= 1)
     int batch, n_templates, crop_lo, crop_len, roll, drop_dc;
     float noise_scale, out_scale;
     unsigned long long seed, sample_offset;
@@ -466,14 +521,48 @@ __global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
     }
 }
 
-template <int LOG2M, int MODE>
+// The rfft split, the whitening weights and the irfft packing collapse to two real coefficients per bin: with
+// Z = FFT_M(x[2n] + i x[2n+1]) and t_k = exp(-2 pi i k / N) = c_k + i s_k,
+//     Z'[k] = alpha_k Z[k] + beta_k * i conj(Z[(M-k) mod M]),   alpha_k = (w_k + w_{M-k})/2 + (w_k - w_{M-k})/2 * s_k,
+//                                                                beta_k  = (w_k - w_{M-k})/2 * c_k,
+// and IFFT_M(Z') = y[2n] + i y[2n+1] with y = irfft(rfft(x) * w) (k = 0 included: its partner is itself and w_M the
+// Nyquist weight).  Same arithmetic as gw_template_maker.py:277-283 (rfft, multiply, irfft).
+__global__ void whiten_coef_kernel(const float* __restrict__ wts, float2* __restrict__ ab, int M) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const double wk = (double)wts[k], wm = (double)wts[M - k];
+    double sn, cs;
+    sincospi((double)k / (double)M, &sn, &cs);      // angle 2 pi k / N
+    ab[k] = make_float2((float)(0.5 * (wk + wm) - 0.5 * (wk - wm) * sn), (float)(0.5 * (wk - wm) * cs));
+}
+
+// VAR 0: transforms meet in shared memory (forward result -> whiten_pointwise -> inverse).
+// VAR 1: a thread keeps its 16 points (bins tid + j*M/16: what the last forward pass leaves it and what the first inverse
+//        pass asks of it) in registers across the whitening step; only the partner bins M-k cross through shared memory
+//        (one conflict-free write + read instead of four padded sweeps), the pointwise step is two FMAs per component
+//        from the (alpha, beta) table, window loads are skipped where the window is exactly 1, and in SYNTH mode the
+//        coloured noise goes from its inverse transform to the forward transform in registers as well.
+// VAR 2: VAR 1 with product twiddles (fft_pass TWP = 1).
+template <int LOG2M, int MODE, int VAR>
 __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth_kernel(SynthArgs a) {
     constexpr int M = 1 << LOG2M;
     constexpr int N = 2 * M;
     constexpr int Nf = M + 1;
+    constexpr int NT = M / 16;
+    constexpr int TWP = VAR == 2 ? 1 : 0;
     extern __shared__ float2 buf[];  // PADI(M) complex
     const float2* __restrict__ tw = a.tw;
     const float2* __restrict__ ptw = a.ptw;
+    // bit j set: the window is exactly 1 on both samples of the thread's j-th point (flat part of the Tukey window)
+    unsigned wflat = 0;
+    if (VAR >= 1 && MODE != MODE_IRFFT) {
+        const float2* __restrict__ win2 = reinterpret_cast<const float2*>(a.window);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float2 w = __ldg(&win2[threadIdx.x + j * NT]);
+            if (w.x == 1.f && w.y == 1.f) wflat |= 1u << j;
+        }
+    }
 
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         // output of the final inverse pass: packed (y[2j], y[2j+1]) at logical index j
@@ -514,10 +603,12 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
             };
             irfft_pre<LOG2M>(buf, tw, spec, a.drop_dc != 0);
             __syncthreads();
-            fft_full<+1, LOG2M>(buf, ptw, SmemIn{buf}, true, make_out(out_store), true);
+            fft_full<+1, LOG2M, TWP>(buf, ptw, SmemIn{buf}, true, make_out(out_store), true);
             __syncthreads();
             continue;
         }
+
+        float2 z[16];      // VAR >= 1: the thread's points tid + j*NT between transforms
 
         if (MODE == MODE_SYNTH) {
             // coloured noise: Y[k] = amp[k]*(re[k] + i*im[k]), DC dropped (gen_noise :187-190)
@@ -540,7 +631,8 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
                 irfft_pre<LOG2M>(buf, tw, spec, true);
             }
             __syncthreads();
-            fft_full<+1, LOG2M>(buf, ptw, SmemIn{buf}, true, SmemOut{buf}, false);
+            if (VAR >= 1) fft_full<+1, LOG2M, TWP>(buf, ptw, SmemIn{buf}, true, RegOut{z}, true);
+            else fft_full<+1, LOG2M, TWP>(buf, ptw, SmemIn{buf}, true, SmemOut{buf}, false);
             // fft_full ends with a __syncthreads when the last pass goes to smem
         }
 
@@ -564,10 +656,10 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
             const float2* __restrict__ win2 = reinterpret_cast<const float2*>(a.window);
             const float2* __restrict__ src2 = reinterpret_cast<const float2*>(src);
             const float nscale = a.noise_scale;
-            auto first_load = [&](int idx) {
+            auto first_load = [&](int idx, int j) {
                 float2 v = make_float2(0.f, 0.f);
                 if (MODE == MODE_SYNTH) {
-                    float2 n = buf[PADI(idx)];
+                    float2 n = VAR >= 1 ? z[j] : buf[PADI(idx)];
                     v = make_float2(n.x * nscale, n.y * nscale);
                 }
                 if (src2 != nullptr) {
@@ -575,14 +667,35 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
                     v.x += s.x;
                     v.y += s.y;
                 }
+                if (VAR >= 1 && ((wflat >> j) & 1u)) return v;
                 float2 w = __ldg(&win2[idx]);
                 return make_float2(v.x * w.x, v.y * w.y);
             };
-            fft_full<-1, LOG2M>(buf, ptw, make_in(first_load), MODE == MODE_SYNTH, SmemOut{buf}, false);
+            // MODE_SYNTH: the first pass must not store into buf before every thread has read the noise transform's
+            // last-pass input (VAR >= 1) / its own noise points (VAR 0)
+            if (VAR >= 1) fft_full<-1, LOG2M, TWP>(buf, ptw, make_in(first_load), MODE == MODE_SYNTH, RegOut{z}, true);
+            else fft_full<-1, LOG2M, TWP>(buf, ptw, make_in(first_load), MODE == MODE_SYNTH, SmemOut{buf}, false);
         }
-        whiten_pointwise<LOG2M>(buf, tw, a.weights);
-        __syncthreads();
-        fft_full<+1, LOG2M>(buf, ptw, SmemIn{buf}, true, make_out(out_store), true);
+        if (VAR >= 1) {
+            __syncthreads();      // the last forward pass has been read by every thread
+#pragma unroll
+            for (int j = 0; j < 16; ++j) buf[j * NT + threadIdx.x] = z[j];
+            __syncthreads();
+            const float2* __restrict__ ab = a.coef;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = threadIdx.x + j * NT;
+                const float2 zm = buf[(M - k) & (M - 1)];      // a warp reads 32 consecutive slots, descending
+                const float2 c = ld_table(&ab[k]);
+                z[j] = make_float2(fmaf(c.x, z[j].x, c.y * zm.y), fmaf(c.x, z[j].y, c.y * zm.x));
+            }
+            // the first inverse pass synchronises before it stores: the partner reads above are complete by then
+            fft_full<+1, LOG2M, TWP>(buf, ptw, RegIn{z}, true, make_out(out_store), true);
+        } else {
+            whiten_pointwise<LOG2M>(buf, tw, a.weights);
+            __syncthreads();
+            fft_full<+1, LOG2M, TWP>(buf, ptw, SmemIn{buf}, true, make_out(out_store), true);
+        }
         __syncthreads();
     }
 }
@@ -596,19 +709,20 @@ static int whiten_variant() {
     return v;
 }
 
-template <int MODE>
-static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
-    a.tw = plan->tw;
-    a.ptw = plan->ptw;
-    a.tw64 = plan->tw64;
-    const int M = plan->N / 2;
-    if (MODE == MODE_WHITEN && plan->log2M == 12 && plan->tw64 != nullptr && whiten_variant() == 64) {
-        int grid = a.batch;
-        const int cap = num_sms() * 6 * 4;
-        if (grid > cap) grid = cap;
-        whiten64_kernel<<<grid, 64, 0, st>>>(a);
-        return cuda_status("whiten64_kernel");
+// GN_SYNTH_VAR selects the kernel organisation (see synth_kernel); every variant is parity-tested.
+static int synth_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GN_SYNTH_VAR");
+        v = e ? atoi(e) : 2;
+        if (v < 0 || v > 2) v = 2;
     }
+    return v;
+}
+
+template <int MODE, int VAR>
+static int launch_synth_var(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
+    const int M = plan->N / 2;
     const size_t smem = (size_t)(M + (M >> 4) + 1) * sizeof(float2);
     const int threads = M / 16;
     // persistent CTAs: a multiple of the SM count, at most the batch
@@ -618,26 +732,77 @@ static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
         const int cap = num_sms() * per_sm * 4;      // a few series per CTA slot keeps the tail short
         if (grid > cap) grid = cap;
     }
+    int slot = -1;
+    gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);      // the coefficient slots are the plan's own scratch
+    if (VAR >= 1 && MODE != MODE_IRFFT) {
+        std::lock_guard<std::mutex> lock(pl->mu);
+        for (int i = 0; i < gn_fft_plan::NSLOT; ++i)
+            if (pl->coef_used[i] && pl->coef_key[i] == (const void*)a.weights) slot = i;
+        if (slot < 0) {
+            slot = pl->coef_next;
+            pl->coef_next = (pl->coef_next + 1) % gn_fft_plan::NSLOT;
+            if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);
+            pl->coef_key[slot] = (const void*)a.weights;
+            pl->coef_used[slot] = false;
+        }
+        whiten_coef_kernel<<<(M + 255) / 256, 256, 0, st>>>(a.weights, pl->coef[slot], M);
+        a.coef = pl->coef[slot];
+    }
+    // after the main kernel: the slot's event must cover this use and every earlier one
+    auto release = [&]() {
+        if (slot < 0) return;
+        std::lock_guard<std::mutex> lock(pl->mu);
+        if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);      // orders later work only
+        cudaEventRecord(pl->coef_done[slot], st);
+        pl->coef_used[slot] = true;
+    };
 #define GN_SYNTH_CASE(L2)                                                                                   \
     case L2: {                                                                                              \
-        auto kfn = synth_kernel<L2, MODE>;                                                                  \
+        auto kfn = synth_kernel<L2, MODE, VAR>;                                                             \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         kfn<<<grid, threads, smem, st>>>(a);                                                                \
         break;                                                                                              \
     }
     switch (plan->log2M) {
+#ifndef GN_QUICK      // -DGN_QUICK: N = 8192 only, for fast compile-and-inspect iterations (never shipped)
         GN_SYNTH_CASE(8)
         GN_SYNTH_CASE(9)
         GN_SYNTH_CASE(10)
         GN_SYNTH_CASE(11)
-        GN_SYNTH_CASE(12)
         GN_SYNTH_CASE(13)
         GN_SYNTH_CASE(14)
+#endif
+        GN_SYNTH_CASE(12)
         default:
+            release();
             return fail(GN_ERR_UNSUPPORTED, "synth: unsupported FFT length N=%s%lld", "", plan->N);
     }
 #undef GN_SYNTH_CASE
+    release();
     return cuda_status("synth_kernel");
+}
+
+template <int MODE>
+static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
+    a.tw = plan->tw;
+    a.ptw = plan->ptw;
+    a.tw64 = plan->tw64;
+    if (MODE == MODE_WHITEN && plan->log2M == 12 && plan->tw64 != nullptr && whiten_variant() == 64) {
+        int grid = a.batch;
+        const int cap = num_sms() * 6 * 4;
+        if (grid > cap) grid = cap;
+        whiten64_kernel<<<grid, 64, 0, st>>>(a);
+        return cuda_status("whiten64_kernel");
+    }
+    if constexpr (MODE == MODE_IRFFT) {
+        return launch_synth_var<MODE, 0>(plan, a, st);      // no whitening step: one organisation
+    } else {
+        switch (synth_variant()) {
+            case 0: return launch_synth_var<MODE, 0>(plan, a, st);
+            case 1: return launch_synth_var<MODE, 1>(plan, a, st);
+            default: return launch_synth_var<MODE, 2>(plan, a, st);
+        }
+    }
 }
 
 __global__ void mean_std_kernel(const float* __restrict__ x, long long n, float* out) {
@@ -783,6 +948,27 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
             return GN_ERR_CUDA;
         }
     }
+    for (int i = 0; i < gn_fft_plan::NSLOT; ++i) {
+        p->coef[i] = nullptr;
+        p->coef_key[i] = nullptr;
+        p->coef_used[i] = false;
+        p->coef_done[i] = nullptr;
+    }
+    p->coef_next = 0;
+    for (int i = 0; i < gn_fft_plan::NSLOT; ++i) {
+        if (cudaMalloc(&p->coef[i], sizeof(float2) * (size_t)(N / 2)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->coef_done[i], cudaEventDisableTiming) != cudaSuccess) {
+            for (int q = 0; q <= i; ++q) {
+                if (p->coef[q]) cudaFree(p->coef[q]);
+                if (p->coef_done[q]) cudaEventDestroy(p->coef_done[q]);
+            }
+            cudaFree(p->tw);
+            cudaFree(p->ptw);
+            delete p;
+            cuda_status("gn_fft_plan_create(coefficient slots)");
+            return GN_ERR_CUDA;
+        }
+    }
     p->tw64 = nullptr;
     if (N == 8192) {
         std::vector<float2> t(64 * 64);
@@ -793,6 +979,10 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
             }
         if (cudaMalloc(&p->tw64, sizeof(float2) * t.size()) != cudaSuccess ||
             cudaMemcpy(p->tw64, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            for (int i = 0; i < gn_fft_plan::NSLOT; ++i) {
+                cudaFree(p->coef[i]);
+                cudaEventDestroy(p->coef_done[i]);
+            }
             cudaFree(p->tw);
             cudaFree(p->ptw);
             delete p;
@@ -809,6 +999,10 @@ extern "C" int gn_fft_plan_destroy(gn_fft_plan* p) {
     cudaFree(p->tw);
     cudaFree(p->ptw);
     if (p->tw64) cudaFree(p->tw64);
+    for (int i = 0; i < gn_fft_plan::NSLOT; ++i) {
+        cudaFree(p->coef[i]);
+        cudaEventDestroy(p->coef_done[i]);
+    }
     delete p;
     return GN_OK;
 }
