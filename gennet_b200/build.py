@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
         o = os.path.join(CSRC, src[:-3] + '.o')
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ['-c', s, '-o', o]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get('GN_EXTRA_NVCC', '').split() + ['-c', s, '-o', o]
             if verbose:
                 print(' '.join(cmd))
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

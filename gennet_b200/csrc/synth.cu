@@ -132,6 +132,12 @@ struct Dft<16, DIR> {
 // every series) out of the persistent loop, and ptxas hoists them over the preceding __syncthreads into the previous
 // pass -- in both cases the values no longer fit in the 64-register budget and are spilled to local memory, which
 // costs more L1 wavefronts than the L1-resident loads themselves.  A coherent ld.global is ordered by the barrier.
+// Streaming load of a series element that is read exactly once: no L1 allocation (the tables keep the L1).
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float2 ld_table(const float2* p) {
     float2 v;
     asm volatile("ld.global.ca.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
@@ -156,6 +162,8 @@ struct SmemIn {
     const float2* buf;
     template <int T>
     __device__ __forceinline__ float2 get(int i, int r, int) const { return buf[padi_off<T>(i, r)]; }
+    template <int T>
+    __device__ __forceinline__ float2 fix(float2 v, int, int, int) const { return v; }
 };
 struct SmemOut {
     float2* buf;
@@ -167,6 +175,8 @@ struct RegIn {
     const float2* z;
     template <int T>
     __device__ __forceinline__ float2 get(int, int, int j) const { return z[j]; }
+    template <int T>
+    __device__ __forceinline__ float2 fix(float2 v, int, int, int) const { return v; }
 };
 struct RegOut {
     float2* z;
@@ -180,12 +190,27 @@ struct IdxIn {
     F f;
     template <int T>
     __device__ __forceinline__ float2 get(int i, int r, int j) const { return f(i + r * T, j); }
+    template <int T>
+    __device__ __forceinline__ float2 fix(float2 v, int, int, int) const { return v; }
 };
+// two-phase input: f issues the global load of every point of the pass first, g finishes the values (window, noise)
+// in a second sweep, so that all loads of a thread are in flight together
+template <class F, class G>
+struct IdxIn2 {
+    F f;
+    G g;
+    template <int T>
+    __device__ __forceinline__ float2 get(int i, int r, int j) const { return f(i + r * T, j); }
+    template <int T>
+    __device__ __forceinline__ float2 fix(float2 v, int i, int r, int j) const { return g(v, i + r * T, j); }
+};
+template <class F, class G>
+__device__ __forceinline__ IdxIn2<F, G> make_in2(F f, G g) { return IdxIn2<F, G>{f, g}; }
 template <class F>
 struct IdxOut {
     F f;
     template <int P>
-    __device__ __forceinline__ void put(int base, int r, float2 v, int) const { f(base + r * P, v); }
+    __device__ __forceinline__ void put(int base, int r, float2 v, int j) const { f(base + r * P, v, j); }
 };
 template <class F>
 __device__ __forceinline__ IdxIn<F> make_in(F f) { return IdxIn<F>{f}; }
@@ -210,6 +235,8 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ ptw, const I
         const int i = tid + it * NT;
 #pragma unroll
         for (int r = 0; r < R; ++r) v[it][r] = in.template get<T>(i, r, it + r * IT);
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[it][r] = in.template fix<T>(v[it][r], i, r, it + r * IT);
         if (P > 1) {
             const int k = i & (P - 1);
             if constexpr (TWP == 1 && R == 16) {
@@ -394,6 +421,7 @@ __device__ __forceinline__ void irfft_pre(float2* buf, const float2* __restrict_
 #define GN_SYNTH_MINB(L2) (((1 << (L2)) / 16) >= 512 ? 1 : (65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * GN_SYNTH_REGS) > 8 ? 8 : 65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * GN_SYNTH_REGS)))
 constexpr int MODE_WHITEN = 0, MODE_IRFFT = 1, MODE_SYNTH = 2;
 
+
 struct SynthArgs {
     const float* x;          // WHITEN: (batch,N) input; IRFFT: (batch,Nf) complex; SYNTH: normals (batch,2,Nf) or null
     const float* amp;        // SYNTH: (Nf)
@@ -414,51 +442,55 @@ struct SynthArgs {
 // ---- gn_whiten_td_f32 for N = 8192 (M = 4096 = 64 x 64): two register-resident radix-64 passes per transform --------
 // 64 threads own one series.  Element n = 64*n1 + n2 of the packed complex series, bin k = k1 + 64*k2:
 //   pass A (thread = n2): DFT-64 over n1, times W_4096^(n2*k1), to shared memory S[k1][n2]
-//   pass B (thread = k1): DFT-64 over n2, bin k1 + 64*k2
-// Rows of S are 65 complex apart, so the column writes of pass A and the row reads of pass B are both conflict free.
-// Four shared-memory round trips per series (A->B, B->pointwise, pointwise->A', A'->B') instead of six with radix 16,
-// and one twiddled pass per transform instead of two.  EXPERIMENTAL (GN_WHITEN_RADIX=64): parity-green, shared-memory
-// wavefronts drop by 35 %, but 168 registers leave 12 warps per SM and the kernel becomes latency bound on its
-// global loads (window, twiddles, input): 1.86 TB/s against 2.53 TB/s for the radix-16 kernel (round-1 ncu capture
-// profiles/r01_ncu_whiten64_experiment.summary.txt).  Kept off by default.
+//   pass B (thread = k1): DFT-64 over n2 -> bins k1 + 64*k2 in the thread's registers
+// which is also what pass A of the inverse transform asks of thread k1, so the whitening step happens in registers:
+// only the partner bins (M-k) cross through shared memory (unpadded [k2][k1] layout, conflict-free both ways) and the
+// step itself is Z'[k] = alpha_k Z[k] + beta_k i conj(Z[M-k]) from the prologue's coefficient table.
+// Rows of S are 65 complex apart, so the column writes of pass A and the row reads of pass B are conflict free.
+// Six shared-memory sweeps per series against ten for the radix-16 organisation, one twiddled pass per transform; the
+// 63 pass twiddles of a thread are formed from 14 table entries (W^(t*b), W^(8*t*a)) because at 6 CTAs per SM the L1
+// keeps under 30 KB.  Selected with GN_WHITEN_RADIX=64.
 constexpr int W64_LD = 65;
-template <int DIR, class LOAD>
-__device__ __forceinline__ void pass_a64(float2* S, const float2* __restrict__ tw64, LOAD load) {
+template <int DIR>
+__device__ __forceinline__ void twiddle_store64(float2* S, const float2* __restrict__ tw64, float2* v) {
     const int t = threadIdx.x;
-    float2 v[64];
+    float2 lo[8];
 #pragma unroll
-    for (int n1 = 0; n1 < 64; ++n1) v[n1] = load(64 * n1 + t);
-    Dft<64, DIR>::run(v);
+    for (int b = 1; b < 8; ++b) lo[b] = ld_table(&tw64[b * 64 + t]);
 #pragma unroll
-    for (int k1 = 0; k1 < 64; ++k1) {
-        float2 y = v[Dft<64, DIR>::out_reg(k1)];
-        if (k1 > 0) {
-            const float2 w = __ldg(&tw64[k1 * 64 + t]);
-            y = DIR > 0 ? cmulc(y, w) : cmul(y, w);
+    for (int a8 = 0; a8 < 8; ++a8) {
+        float2 hi = make_float2(1.f, 0.f);
+        if (a8 > 0) hi = ld_table(&tw64[a8 * 8 * 64 + t]);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k1 = 8 * a8 + b;
+            float2 y = v[Dft<64, DIR>::out_reg(k1)];
+            if (k1 > 0) {
+                const float2 w = a8 == 0 ? lo[b] : (b == 0 ? hi : cmul(hi, lo[b]));
+                y = DIR > 0 ? cmulc(y, w) : cmul(y, w);
+            }
+            S[k1 * W64_LD + t] = y;
         }
-        S[k1 * W64_LD + t] = y;
     }
-}
-template <int DIR, class STORE>
-__device__ __forceinline__ void pass_b64(const float2* S, STORE store) {
-    const int t = threadIdx.x;
-    float2 v[64];
-#pragma unroll
-    for (int n2 = 0; n2 < 64; ++n2) v[n2] = S[t * W64_LD + n2];
-    __syncthreads();          // every row has been read: the stores below may reuse the buffer
-    Dft<64, DIR>::run(v);
-#pragma unroll
-    for (int k2 = 0; k2 < 64; ++k2) store(t + 64 * k2, v[Dft<64, DIR>::out_reg(k2)]);
 }
 
 __global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
     constexpr int M = 4096, N = 8192;
     __shared__ float2 S[64 * W64_LD];
-    const float2* __restrict__ tw = a.tw;
     const float2* __restrict__ tw64 = a.tw64;
     const float2* __restrict__ win2 = reinterpret_cast<const float2*>(a.window);
-    const float* __restrict__ wts = a.weights;
-    auto sidx = [](int k) { return (k >> 6) * W64_LD + (k & 63); };
+    const float2* __restrict__ ab = a.coef;
+    const int t = threadIdx.x;
+    // bit n1 set: the window is exactly 1 on both samples of element 64*n1 + t
+    unsigned flat_lo = 0, flat_hi = 0;
+#pragma unroll
+    for (int n1 = 0; n1 < 64; ++n1) {
+        const float2 w = __ldg(&win2[64 * n1 + t]);
+        if (w.x == 1.f && w.y == 1.f) {
+            if (n1 < 32) flat_lo |= 1u << n1;
+            else flat_hi |= 1u << (n1 - 32);
+        }
+    }
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         const float2* __restrict__ src2 = reinterpret_cast<const float2*>(a.x + (size_t)b * N);
         {   // pull the series this CTA handles next into L2
@@ -469,55 +501,56 @@ __global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)ln * 128));
             }
         }
-        // forward: window, packed real -> complex, 64 x 64 FFT, result in natural order S[k/64][k%64]
-        pass_a64<-1>(S, tw64, [&](int n) {
-            const float2 xv = __ldg(&src2[n]), wv = __ldg(&win2[n]);
-            return make_float2(xv.x * wv.x, xv.y * wv.y);
-        });
-        __syncthreads();
-        pass_b64<-1>(S, [&](int k, float2 val) { S[sidx(k)] = val; });
-        __syncthreads();
-        // real-FFT split, whitening weights, inverse packing (same algebra as whiten_pointwise)
-        for (int j = 0; j <= 32; ++j) {
-            const int k = threadIdx.x + 64 * j;
-            if (k > M / 2) break;
-            if (k == 0) {
-                const float2 z = S[0];
-                const float y0 = __ldg(&wts[0]) * (z.x + z.y);
-                const float yM = __ldg(&wts[M]) * (z.x - z.y);
-                S[0] = make_float2(0.5f * (y0 + yM), 0.5f * (y0 - yM));
-                continue;
+        float2 v[64];
+        // forward pass A: window, packed real -> complex
+#pragma unroll
+        for (int n1 = 0; n1 < 64; ++n1) v[n1] = ld_stream(&src2[64 * n1 + t]);
+#pragma unroll
+        for (int n1 = 0; n1 < 64; ++n1) {
+            const bool flat = n1 < 32 ? ((flat_lo >> n1) & 1u) : ((flat_hi >> (n1 - 32)) & 1u);
+            if (!flat) {
+                const float2 w = ld_table(&win2[64 * n1 + t]);
+                v[n1] = make_float2(v[n1].x * w.x, v[n1].y * w.y);
             }
-            const int mk = M - k;
-            const float2 zk = S[sidx(k)], zm = S[sidx(mk)];
-            const float2 A2 = make_float2(zk.x + zm.x, zk.y - zm.y);
-            const float2 O2 = make_float2(zk.y + zm.y, zm.x - zk.x);
-            const float2 t = __ldg(&tw[k]);
-            const float wk = __ldg(&wts[k]), wm = __ldg(&wts[mk]);
-            const float s = 0.25f * (wk + wm), d = 0.25f * (wk - wm);
-            const float2 tO = cmul(t, O2), ctA = cmulc(A2, t);
-            const float2 E = make_float2(fmaf(s, A2.x, d * tO.x), fmaf(s, A2.y, d * tO.y));
-            const float2 Op = make_float2(fmaf(s, O2.x, d * ctA.x), fmaf(s, O2.y, d * ctA.y));
-            S[sidx(k)] = make_float2(E.x - Op.y, E.y + Op.x);
-            S[sidx(mk)] = make_float2(E.x + Op.y, -E.y + Op.x);
         }
+        Dft<64, -1>::run(v);
+        twiddle_store64<-1>(S, tw64, v);
         __syncthreads();
-        // inverse: pass A reads and writes only column t of S, so it runs in place
-        pass_a64<+1>(S, tw64, [&](int n) { return S[sidx(n)]; });
+        // forward pass B
+#pragma unroll
+        for (int n2 = 0; n2 < 64; ++n2) v[n2] = S[t * W64_LD + n2];
+        __syncthreads();          // every row has been read: the exchange below reuses the buffer
+        Dft<64, -1>::run(v);
+        // whitening step: bin k = t + 64*k2 sits in v[out_reg(k2)]; partners through the unpadded exchange layout
+#pragma unroll
+        for (int k2 = 0; k2 < 64; ++k2) S[64 * k2 + t] = v[Dft<64, -1>::out_reg(k2)];
         __syncthreads();
+        float2 u[64];
+#pragma unroll
+        for (int k2 = 0; k2 < 64; ++k2) {
+            const int k = t + 64 * k2;
+            const float2 zm = S[(M - k) & (M - 1)];
+            const float2 c = ld_table(&ab[k]);
+            const float2 z = v[Dft<64, -1>::out_reg(k2)];
+            u[k2] = make_float2(fmaf(c.x, z.x, c.y * zm.y), fmaf(c.x, z.y, c.y * zm.x));
+        }
+        __syncthreads();          // partner reads complete before the inverse pass A overwrites S
+        // inverse pass A: thread t owns elements 64*n1 + t = the bins it just whitened
+        Dft<64, +1>::run(u);
+        twiddle_store64<+1>(S, tw64, u);
+        __syncthreads();
+#pragma unroll
+        for (int n2 = 0; n2 < 64; ++n2) v[n2] = S[t * W64_LD + n2];
+        __syncthreads();          // rows read: the next series' pass A may store
+        Dft<64, +1>::run(v);
         float* __restrict__ yb = a.y + (size_t)b * a.crop_len;
-        const float oscale = a.out_scale;
-        const int crop_lo = a.crop_lo, crop_len = a.crop_len;
-        pass_b64<+1>(S, [&](int j, float2 val) {
-            const int n0 = 2 * j - crop_lo;
-            if (((crop_lo | crop_len) & 1) == 0) {
-                if (n0 >= 0 && n0 < crop_len) *reinterpret_cast<float2*>(yb + n0) = make_float2(val.x * oscale, val.y * oscale);
-            } else {
-                if (n0 >= 0 && n0 < crop_len) yb[n0] = val.x * oscale;
-                if (n0 + 1 >= 0 && n0 + 1 < crop_len) yb[n0 + 1] = val.y * oscale;
-            }
-        });
-        __syncthreads();          // pass B has read its rows (sync inside) and nobody touches S until the next pass A
+        // the output scale is already in the coefficients; the host sends odd crop windows to the radix-16 kernel
+        const int nb = 2 * t - a.crop_lo;
+        float* __restrict__ yt = yb + nb;
+        const unsigned clen = (unsigned)a.crop_len;
+#pragma unroll
+        for (int k2 = 0; k2 < 64; ++k2)
+            if ((unsigned)(nb + 128 * k2) < clen) *reinterpret_cast<float2*>(yt + 128 * k2) = v[Dft<64, +1>::out_reg(k2)];
     }
 }
 
@@ -527,13 +560,15 @@ __global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
 //                                                                beta_k  = (w_k - w_{M-k})/2 * c_k,
 // and IFFT_M(Z') = y[2n] + i y[2n+1] with y = irfft(rfft(x) * w) (k = 0 included: its partner is itself and w_M the
 // Nyquist weight).  Same arithmetic as gw_template_maker.py:277-283 (rfft, multiply, irfft).
-__global__ void whiten_coef_kernel(const float* __restrict__ wts, float2* __restrict__ ab, int M) {
+// `scale` (the caller's output scale and the 1/M of the unnormalised inverse) is folded into both coefficients.
+__global__ void whiten_coef_kernel(const float* __restrict__ wts, float2* __restrict__ ab, int M, float scale) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= M) return;
     const double wk = (double)wts[k], wm = (double)wts[M - k];
     double sn, cs;
     sincospi((double)k / (double)M, &sn, &cs);      // angle 2 pi k / N
-    ab[k] = make_float2((float)(0.5 * (wk + wm) - 0.5 * (wk - wm) * sn), (float)(0.5 * (wk - wm) * cs));
+    const double sc = (double)scale;
+    ab[k] = make_float2((float)(sc * (0.5 * (wk + wm) - 0.5 * (wk - wm) * sn)), (float)(sc * 0.5 * (wk - wm) * cs));
 }
 
 // VAR 0: transforms meet in shared memory (forward result -> whiten_pointwise -> inverse).
@@ -541,18 +576,29 @@ __global__ void whiten_coef_kernel(const float* __restrict__ wts, float2* __rest
 //        pass asks of it) in registers across the whitening step; only the partner bins M-k cross through shared memory
 //        (one conflict-free write + read instead of four padded sweeps), the pointwise step is two FMAs per component
 //        from the (alpha, beta) table, window loads are skipped where the window is exactly 1, and in SYNTH mode the
-//        coloured noise goes from its inverse transform to the forward transform in registers as well.
-// VAR 2: VAR 1 with product twiddles (fft_pass TWP = 1).
+//        coloured noise goes from its inverse transform to the forward transform in registers as well; six-row product
+//        twiddles (fft_pass TWP = 1).
 template <int LOG2M, int MODE, int VAR>
 __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth_kernel(SynthArgs a) {
     constexpr int M = 1 << LOG2M;
     constexpr int N = 2 * M;
     constexpr int Nf = M + 1;
     constexpr int NT = M / 16;
-    constexpr int TWP = VAR == 2 ? 1 : 0;
+    constexpr int TWP = VAR >= 1 ? 1 : 0;
     extern __shared__ float2 buf[];  // PADI(M) complex
     const float2* __restrict__ tw = a.tw;
     const float2* __restrict__ ptw = a.ptw;
+    // VAR >= 1, even crop window: bit j set when the thread's j-th output pair lies inside the crop; the pair then goes to
+    // ycrop[2*j*NT] of the series (one test and one store with an immediate offset per pair)
+    unsigned omask = 0;
+    constexpr bool fast_out = VAR >= 1 && MODE != MODE_IRFFT;      // the host sends odd crop windows to VAR 0
+    if (fast_out) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n0 = 2 * ((int)threadIdx.x + j * NT) - a.crop_lo;
+            if (n0 >= 0 && n0 < a.crop_len) omask |= 1u << j;
+        }
+    }
     // bit j set: the window is exactly 1 on both samples of the thread's j-th point (flat part of the Tukey window)
     unsigned wflat = 0;
     if (VAR >= 1 && MODE != MODE_IRFFT) {
@@ -567,8 +613,13 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         // output of the final inverse pass: packed (y[2j], y[2j+1]) at logical index j
         float* __restrict__ yb = a.y + (size_t)b * (MODE == MODE_IRFFT ? N : a.crop_len);
-        const float oscale = a.out_scale;
-        auto out_store = [&](int j, float2 val) {
+        const float oscale = (VAR >= 1 && MODE != MODE_IRFFT) ? 1.f : a.out_scale;      // VAR >= 1: in the coefficients
+        float* __restrict__ ycrop = yb + (2 * (int)threadIdx.x - a.crop_lo);          // dereferenced under omask only
+        auto out_store = [&](int j, float2 val, int slot) {
+            if (fast_out) {
+                if ((omask >> slot) & 1u) *reinterpret_cast<float2*>(ycrop + 2 * slot * NT) = val;
+                return;
+            }
             if (MODE == MODE_IRFFT) {
                 int n0 = (2 * j + a.roll) & (N - 1);
                 if ((a.roll & 1) == 0) {
@@ -667,13 +718,28 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
                     v.x += s.x;
                     v.y += s.y;
                 }
-                if (VAR >= 1 && ((wflat >> j) & 1u)) return v;
                 float2 w = __ldg(&win2[idx]);
+                return make_float2(v.x * w.x, v.y * w.y);
+            };
+            // VAR >= 1: the same in two phases -- every global load of the pass first, then noise, window
+            // (SYNTH: the noise already fills the registers, so the template loads stay with the second phase)
+            auto load_src = [&](int idx, int j) {
+                if (MODE == MODE_WHITEN) return ld_stream(&src2[idx]);
+                return make_float2(z[j].x * nscale, z[j].y * nscale);
+            };
+            auto finish = [&](float2 v, int idx, int j) {
+                if (MODE == MODE_SYNTH && src2 != nullptr) {
+                    const float2 s = __ldg(&src2[idx]);
+                    v.x += s.x;
+                    v.y += s.y;
+                }
+                if ((wflat >> j) & 1u) return v;
+                const float2 w = ld_table(&win2[idx]);
                 return make_float2(v.x * w.x, v.y * w.y);
             };
             // MODE_SYNTH: the first pass must not store into buf before every thread has read the noise transform's
             // last-pass input (VAR >= 1) / its own noise points (VAR 0)
-            if (VAR >= 1) fft_full<-1, LOG2M, TWP>(buf, ptw, make_in(first_load), MODE == MODE_SYNTH, RegOut{z}, true);
+            if (VAR >= 1) fft_full<-1, LOG2M, TWP>(buf, ptw, make_in2(load_src, finish), MODE == MODE_SYNTH, RegOut{z}, true);
             else fft_full<-1, LOG2M, TWP>(buf, ptw, make_in(first_load), MODE == MODE_SYNTH, SmemOut{buf}, false);
         }
         if (VAR >= 1) {
@@ -709,13 +775,33 @@ static int whiten_variant() {
     return v;
 }
 
+// Coefficient slot for this call's weights (see gn_fft_plan): the prologue kernel may be launched on `st` afterwards.
+static int coef_acquire(gn_fft_plan* pl, const float* weights, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(pl->mu);
+    for (int i = 0; i < gn_fft_plan::NSLOT; ++i)
+        if (pl->coef_key[i] == (const void*)weights) return i;
+    const int slot = pl->coef_next;
+    pl->coef_next = (pl->coef_next + 1) % gn_fft_plan::NSLOT;
+    if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);
+    pl->coef_key[slot] = (const void*)weights;
+    pl->coef_used[slot] = false;
+    return slot;
+}
+// After the main kernel: the slot's event must cover this use and every earlier one.
+static void coef_release(gn_fft_plan* pl, int slot, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(pl->mu);
+    if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);      // orders later work on st only
+    cudaEventRecord(pl->coef_done[slot], st);
+    pl->coef_used[slot] = true;
+}
+
 // GN_SYNTH_VAR selects the kernel organisation (see synth_kernel); every variant is parity-tested.
 static int synth_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GN_SYNTH_VAR");
-        v = e ? atoi(e) : 2;
-        if (v < 0 || v > 2) v = 2;
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 1) v = 1;
     }
     return v;
 }
@@ -735,30 +821,16 @@ static int launch_synth_var(const gn_fft_plan* plan, SynthArgs a, cudaStream_t s
     int slot = -1;
     gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);      // the coefficient slots are the plan's own scratch
     if (VAR >= 1 && MODE != MODE_IRFFT) {
-        std::lock_guard<std::mutex> lock(pl->mu);
-        for (int i = 0; i < gn_fft_plan::NSLOT; ++i)
-            if (pl->coef_used[i] && pl->coef_key[i] == (const void*)a.weights) slot = i;
-        if (slot < 0) {
-            slot = pl->coef_next;
-            pl->coef_next = (pl->coef_next + 1) % gn_fft_plan::NSLOT;
-            if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);
-            pl->coef_key[slot] = (const void*)a.weights;
-            pl->coef_used[slot] = false;
-        }
-        whiten_coef_kernel<<<(M + 255) / 256, 256, 0, st>>>(a.weights, pl->coef[slot], M);
+        slot = coef_acquire(pl, a.weights, st);
+        whiten_coef_kernel<<<(M + 255) / 256, 256, 0, st>>>(a.weights, pl->coef[slot], M, a.out_scale);
         a.coef = pl->coef[slot];
     }
-    // after the main kernel: the slot's event must cover this use and every earlier one
     auto release = [&]() {
-        if (slot < 0) return;
-        std::lock_guard<std::mutex> lock(pl->mu);
-        if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);      // orders later work only
-        cudaEventRecord(pl->coef_done[slot], st);
-        pl->coef_used[slot] = true;
+        if (slot >= 0) coef_release(pl, slot, st);
     };
 #define GN_SYNTH_CASE(L2)                                                                                   \
     case L2: {                                                                                              \
-        auto kfn = synth_kernel<L2, MODE, VAR>;                                                             \
+        auto kfn = synth_kernel<L2, MODE, VAR>;                                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         kfn<<<grid, threads, smem, st>>>(a);                                                                \
         break;                                                                                              \
@@ -787,21 +859,26 @@ static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
     a.tw = plan->tw;
     a.ptw = plan->ptw;
     a.tw64 = plan->tw64;
-    if (MODE == MODE_WHITEN && plan->log2M == 12 && plan->tw64 != nullptr && whiten_variant() == 64) {
+    if (MODE == MODE_WHITEN && plan->log2M == 12 && plan->tw64 != nullptr && whiten_variant() == 64 &&
+        ((a.crop_lo | a.crop_len) & 1) == 0) {
         int grid = a.batch;
         const int cap = num_sms() * 6 * 4;
         if (grid > cap) grid = cap;
+        gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);
+        const int slot = coef_acquire(pl, a.weights, st);
+        whiten_coef_kernel<<<(plan->N / 2 + 255) / 256, 256, 0, st>>>(a.weights, pl->coef[slot], plan->N / 2, a.out_scale);
+        a.coef = pl->coef[slot];
         whiten64_kernel<<<grid, 64, 0, st>>>(a);
+        coef_release(pl, slot, st);
         return cuda_status("whiten64_kernel");
     }
     if constexpr (MODE == MODE_IRFFT) {
         return launch_synth_var<MODE, 0>(plan, a, st);      // no whitening step: one organisation
     } else {
-        switch (synth_variant()) {
-            case 0: return launch_synth_var<MODE, 0>(plan, a, st);
-            case 1: return launch_synth_var<MODE, 1>(plan, a, st);
-            default: return launch_synth_var<MODE, 2>(plan, a, st);
-        }
+        // VAR >= 1 stores whole sample pairs: crop windows with an odd start or length take the VAR 0 organisation
+        const int var = ((a.crop_lo | a.crop_len) & 1) ? 0 : synth_variant();
+        if (var == 0) return launch_synth_var<MODE, 0>(plan, a, st);
+        return launch_synth_var<MODE, 1>(plan, a, st);
     }
 }
 

@@ -38,7 +38,9 @@ print('VAR=%%s err=%%.2e | whiten full %%.1f us %%.0f GB/s | crop %%.1f us %%.0f
     os.environ.get('GN_SYNTH_VAR'), err, t1 * 1e3, B * 8 * N / t1 / 1e6, t2 * 1e3, B * (4 * N + 4 * fs) / t2 / 1e6,
     t3 * 1e3, B * (4 * N + 4 * fs) / t3 / 1e6, t4 * 1e3))
 ''' % ROOT
-for v in (sys.argv[1:] or ['0', '1', '2']):
-    env = dict(os.environ, GN_SYNTH_VAR=v)
+# arguments: comma-separated KEY=VALUE settings per run, e.g.  GN_SYNTH_VAR=2,GN_SYNTH_WAVES=1  GN_WHITEN_RADIX=64
+for spec in (sys.argv[1:] or ['GN_SYNTH_VAR=0', 'GN_SYNTH_VAR=1', 'GN_SYNTH_VAR=2']):
+    env = dict(os.environ)
+    env.update(kv.split('=') for kv in spec.split(','))
     r = subprocess.run([sys.executable, '-c', CHILD], env=env, capture_output=True, text=True)
-    print(r.stdout.strip() or r.stderr[-2000:], flush=True)
+    print(spec, '|', r.stdout.strip() or r.stderr[-2000:], flush=True)

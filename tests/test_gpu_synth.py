@@ -246,27 +246,65 @@ def test_waveform_ingest_matches_oracle(Nx):
 
 
 @pytest.mark.gpu
-def test_whiten_radix64_variant_matches_oracle():
-    """The experimental 64 x 64 two-pass whitening kernel (GN_WHITEN_RADIX=64) against the float64 oracle; run in a
-    subprocess because the variant is latched from the environment on first use."""
+@pytest.mark.parametrize('env', [{'GN_WHITEN_RADIX': '64'}, {'GN_SYNTH_VAR': '0'}, {'GN_SYNTH_VAR': '1'}])
+def test_whiten_kernel_organisations_match_oracle(env):
+    """Every organisation of the whitening / synthesis kernels against the float64 oracle: the 64 x 64 two-pass kernel
+    (GN_WHITEN_RADIX=64), the shared-memory organisation (GN_SYNTH_VAR=0, also the fallback for odd crop windows) and the
+    register organisation (GN_SYNTH_VAR=1, the default).  Run in a subprocess because the selection is latched from the
+    environment on first use."""
     import subprocess
     import sys
     code = (
         "import numpy as np, torch, sys; sys.path.insert(0, %r)\n"
         "from gennet_b200 import synth\n"
         "from oracle import synth_oracle as so\n"
-        "fs, T = 2048, 4\n"
-        "psd = so.analytic_psd(fs, T)\n"
-        "s = synth.Synthesizer(fs, T, psd)\n"
-        "rs = np.random.RandomState(1)\n"
-        "x = (rs.normal(size=(5, fs * T)) * 1e-21)\n"
-        "for crop in (False, True):\n"
-        "    got = s.whiten_td(torch.as_tensor(x.astype(np.float32)).cuda(), crop=crop).cpu().numpy()\n"
-        "    ref = np.stack([so.whiten_data(x[i].astype(np.float32).astype(np.float64), T, fs, psd, 'td') for i in range(5)])\n"
-        "    if crop: ref = np.stack([so.crop_central(r, fs, T) for r in ref])\n"
-        "    err = np.abs(got - ref).max() / np.abs(ref).max()\n"
-        "    assert got.shape == ref.shape and err < 1e-6, (crop, err)\n"
+        "for fs in (2048, 512):\n"
+        "    T = 4\n"
+        "    psd = so.analytic_psd(fs, T)\n"
+        "    s = synth.Synthesizer(fs, T, psd)\n"
+        "    rs = np.random.RandomState(1)\n"
+        "    x = (rs.normal(size=(5, fs * T)) * 1e-21)\n"
+        "    for crop in (False, True):\n"
+        "        got = s.whiten_td(torch.as_tensor(x.astype(np.float32)).cuda(), crop=crop, scale=2.5).cpu().numpy()\n"
+        "        ref = 2.5 * np.stack([so.whiten_data(x[i].astype(np.float32).astype(np.float64), T, fs, psd, 'td') for i in range(5)])\n"
+        "        if crop: ref = np.stack([so.crop_central(r, fs, T) for r in ref])\n"
+        "        err = np.abs(got - ref).max() / np.abs(ref).max()\n"
+        "        assert got.shape == ref.shape and err < 1e-6, (fs, crop, err)\n"
+        "    Nf = fs * T // 2 + 1\n"
+        "    normals = rs.normal(size=(3, 2, Nf)).astype(np.float32)\n"
+        "    templ = (rs.normal(size=(4, fs * T)) * 1e-21).astype(np.float32)\n"
+        "    tidx = np.array([2, 0, 3], dtype=np.int32)\n"
+        "    out = s.synth(3, templates=torch.as_tensor(templ).cuda(), tidx=torch.as_tensor(tidx).cuda(), normals=torch.as_tensor(normals).cuda()).cpu().numpy()\n"
+        "    for b in range(3):\n"
+        "        n = so.gen_noise(fs, T, psd, normals=normals[b].astype(np.float64))\n"
+        "        ref = so.crop_central(so.whiten_data(n + templ[tidx[b]].astype(np.float64), T, fs, psd, 'td'), fs, T)\n"
+        "        err = np.abs(out[b] - ref).max() / np.abs(ref).max()\n"
+        "        assert err < 2e-6, (fs, b, err)\n"
         "print('ok')\n") % os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-    env = dict(os.environ, GN_WHITEN_RADIX='64')
-    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, **env), capture_output=True, text=True,
+                         timeout=300)
     assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_whiten_odd_crop_windows_and_two_weight_vectors(gs):
+    """Crop windows with an odd start or length (served by the shared-memory organisation) and two weight vectors
+    alternating on one plan (the plan's coefficient slots are keyed by the weights pointer) through the C ABI."""
+    import torch
+    from gennet_b200._lib import call, ptr, stream
+    fs, T = 512, 4
+    N = fs * T
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    rs = np.random.RandomState(7)
+    x = (rs.normal(size=(3, N)) * 1e-21).astype(np.float32)
+    xd = torch.as_tensor(x).cuda()
+    ref = np.stack([so.whiten_data(r.astype(np.float64), T, fs, psd) for r in x])
+    w2 = (s.weights * torch.linspace(0.5, 2.0, s.weights.numel(), device='cuda')).contiguous()
+    win, wts2 = s.window.double().cpu().numpy(), w2.double().cpu().numpy()
+    ref2 = np.fft.irfft(np.fft.rfft(x.astype(np.float64) * win, axis=1) * wts2, N, axis=1)
+    for lo, ln in [(0, N), (1, N - 1), (3, 700), (2, 701), (N // 2 - 1, 2), (N - 1, 1)]:
+        for wts, r in ((s.weights, ref), (w2, ref2), (s.weights, ref)):
+            y = torch.full((3, ln), 7.0, device='cuda')
+            call('gn_whiten_td_f32', s._plan, ptr(xd), ptr(s.window), ptr(wts), ptr(y), 3, lo, ln, 1.0, stream())
+            assert np.abs(y.cpu().numpy() - r[:, lo:lo + ln]).max() / np.abs(r).max() < TOL, (lo, ln)
