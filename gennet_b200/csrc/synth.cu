@@ -420,6 +420,9 @@ __device__ __forceinline__ void irfft_pre(float2* buf, const float2* __restrict_
 #endif
 #define GN_SYNTH_MINB(L2) (((1 << (L2)) / 16) >= 512 ? 1 : (65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * GN_SYNTH_REGS) > 8 ? 8 : 65536 / ((((1 << (L2)) / 16) < 32 ? 32 : ((1 << (L2)) / 16)) * GN_SYNTH_REGS)))
 constexpr int MODE_WHITEN = 0, MODE_IRFFT = 1, MODE_SYNTH = 2;
+#ifndef GN_COEF_PREFETCH
+#define GN_COEF_PREFETCH 6
+#endif
 
 
 struct SynthArgs {
@@ -433,7 +436,7 @@ struct SynthArgs {
     const float2* tw;
     const float2* ptw;
     const float2* tw64;
-    const float2* coef;      // (M) whitening coefficients (alpha_k, beta_k) of whiten_coef_kernel (VAR >= 1)
+    const float2* coef;      // (M + 1) whitening coefficients (alpha_k, beta_k) and flat window range of whiten_coef_kernel
     int batch, n_templates, crop_lo, crop_len, roll, drop_dc;
     float noise_scale, out_scale;
     unsigned long long seed, sample_offset;
@@ -481,16 +484,10 @@ __global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
     const float2* __restrict__ win2 = reinterpret_cast<const float2*>(a.window);
     const float2* __restrict__ ab = a.coef;
     const int t = threadIdx.x;
-    // bit n1 set: the window is exactly 1 on both samples of element 64*n1 + t
-    unsigned flat_lo = 0, flat_hi = 0;
-#pragma unroll
-    for (int n1 = 0; n1 < 64; ++n1) {
-        const float2 w = __ldg(&win2[64 * n1 + t]);
-        if (w.x == 1.f && w.y == 1.f) {
-            if (n1 < 32) flat_lo |= 1u << n1;
-            else flat_hi |= 1u << (n1 - 32);
-        }
-    }
+    // the window is exactly 1 on element 64*n1 + t when (unsigned)(wf0 + 64*n1) < wflen (flat range from the prologue)
+    const int2 fr = *reinterpret_cast<const int2*>(a.coef + M);
+    const int wf0 = t - fr.x;
+    const unsigned wflen = (unsigned)(fr.y - fr.x);
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         const float2* __restrict__ src2 = reinterpret_cast<const float2*>(a.x + (size_t)b * N);
         {   // pull the series this CTA handles next into L2
@@ -507,8 +504,7 @@ __global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
         for (int n1 = 0; n1 < 64; ++n1) v[n1] = ld_stream(&src2[64 * n1 + t]);
 #pragma unroll
         for (int n1 = 0; n1 < 64; ++n1) {
-            const bool flat = n1 < 32 ? ((flat_lo >> n1) & 1u) : ((flat_hi >> (n1 - 32)) & 1u);
-            if (!flat) {
+            if (!((unsigned)(wf0 + 64 * n1) < wflen)) {
                 const float2 w = ld_table(&win2[64 * n1 + t]);
                 v[n1] = make_float2(v[n1].x * w.x, v[n1].y * w.y);
             }
@@ -561,14 +557,36 @@ __global__ void __launch_bounds__(64, 6) whiten64_kernel(SynthArgs a) {
 // and IFFT_M(Z') = y[2n] + i y[2n+1] with y = irfft(rfft(x) * w) (k = 0 included: its partner is itself and w_M the
 // Nyquist weight).  Same arithmetic as gw_template_maker.py:277-283 (rfft, multiply, irfft).
 // `scale` (the caller's output scale and the 1/M of the unnormalised inverse) is folded into both coefficients.
-__global__ void whiten_coef_kernel(const float* __restrict__ wts, float2* __restrict__ ab, int M, float scale) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= M) return;
-    const double wk = (double)wts[k], wm = (double)wts[M - k];
-    double sn, cs;
-    sincospi((double)k / (double)M, &sn, &cs);      // angle 2 pi k / N
+// The same launch finds the flat part of the window: ab[M] holds (as two ints) the range [lo, hi) of packed elements
+// n (samples 2n, 2n+1) on which the window is exactly 1 -- the main kernels skip the window load and multiply there.
+// A window whose unit elements are not one contiguous run gets the empty range (every element is then multiplied).
+__global__ void __launch_bounds__(1024) whiten_coef_kernel(const float* __restrict__ wts, const float* __restrict__ window,
+                                                           float2* __restrict__ ab, int M, float scale) {
     const double sc = (double)scale;
-    ab[k] = make_float2((float)(sc * (0.5 * (wk + wm) - 0.5 * (wk - wm) * sn)), (float)(sc * 0.5 * (wk - wm) * cs));
+    int lo = M, hi = 0, cnt = 0;
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        const double wk = (double)wts[k], wm = (double)wts[M - k];
+        double sn, cs;
+        sincospi((double)k / (double)M, &sn, &cs);      // angle 2 pi k / N
+        ab[k] = make_float2((float)(sc * (0.5 * (wk + wm) - 0.5 * (wk - wm) * sn)), (float)(sc * 0.5 * (wk - wm) * cs));
+        if (window[2 * k] == 1.f && window[2 * k + 1] == 1.f) {
+            lo = min(lo, k);
+            hi = max(hi, k + 1);
+            ++cnt;
+        }
+    }
+    __shared__ int s_lo, s_hi, s_cnt;
+    if (threadIdx.x == 0) { s_lo = M; s_hi = 0; s_cnt = 0; }
+    __syncthreads();
+    atomicMin(&s_lo, lo);
+    atomicMax(&s_hi, hi);
+    atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int2 r = make_int2(0, 0);
+        if (s_cnt > 0 && s_hi - s_lo == s_cnt) r = make_int2(s_lo, s_hi);
+        *reinterpret_cast<int2*>(ab + M) = r;
+    }
 }
 
 // VAR 0: transforms meet in shared memory (forward result -> whiten_pointwise -> inverse).
@@ -588,36 +606,27 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
     extern __shared__ float2 buf[];  // PADI(M) complex
     const float2* __restrict__ tw = a.tw;
     const float2* __restrict__ ptw = a.ptw;
-    // VAR >= 1, even crop window: bit j set when the thread's j-th output pair lies inside the crop; the pair then goes to
-    // ycrop[2*j*NT] of the series (one test and one store with an immediate offset per pair)
-    unsigned omask = 0;
     constexpr bool fast_out = VAR >= 1 && MODE != MODE_IRFFT;      // the host sends odd crop windows to VAR 0
-    if (fast_out) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n0 = 2 * ((int)threadIdx.x + j * NT) - a.crop_lo;
-            if (n0 >= 0 && n0 < a.crop_len) omask |= 1u << j;
-        }
-    }
-    // bit j set: the window is exactly 1 on both samples of the thread's j-th point (flat part of the Tukey window)
-    unsigned wflat = 0;
+    // VAR >= 1: the thread's j-th point is packed element tid + j*NT.  The window is exactly 1 on it when
+    // (unsigned)(wf0 + j*NT) < wflen (flat range from the prologue), and its output pair lies inside the (even) crop
+    // window when (unsigned)(nb + 2*j*NT) < crop_len: one add and one compare each, no per-thread mask to keep.
+    int wf0 = 0;
+    unsigned wflen = 0;
     if (VAR >= 1 && MODE != MODE_IRFFT) {
-        const float2* __restrict__ win2 = reinterpret_cast<const float2*>(a.window);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float2 w = __ldg(&win2[threadIdx.x + j * NT]);
-            if (w.x == 1.f && w.y == 1.f) wflat |= 1u << j;
-        }
+        const int2 fr = *reinterpret_cast<const int2*>(a.coef + M);
+        wf0 = (int)threadIdx.x - fr.x;
+        wflen = (unsigned)(fr.y - fr.x);
     }
-
+    const int nb = 2 * (int)threadIdx.x - a.crop_lo;
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         // output of the final inverse pass: packed (y[2j], y[2j+1]) at logical index j
         float* __restrict__ yb = a.y + (size_t)b * (MODE == MODE_IRFFT ? N : a.crop_len);
         const float oscale = (VAR >= 1 && MODE != MODE_IRFFT) ? 1.f : a.out_scale;      // VAR >= 1: in the coefficients
-        float* __restrict__ ycrop = yb + (2 * (int)threadIdx.x - a.crop_lo);          // dereferenced under omask only
+        float* __restrict__ ycrop = yb + nb;          // dereferenced inside the crop window only
         auto out_store = [&](int j, float2 val, int slot) {
             if (fast_out) {
-                if ((omask >> slot) & 1u) *reinterpret_cast<float2*>(ycrop + 2 * slot * NT) = val;
+                if ((unsigned)(nb + 2 * slot * NT) < (unsigned)a.crop_len)
+                    *reinterpret_cast<float2*>(ycrop + 2 * slot * NT) = val;
                 return;
             }
             if (MODE == MODE_IRFFT) {
@@ -733,7 +742,7 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
                     v.x += s.x;
                     v.y += s.y;
                 }
-                if ((wflat >> j) & 1u) return v;
+                if ((unsigned)(wf0 + j * NT) < wflen) return v;
                 const float2 w = ld_table(&win2[idx]);
                 return make_float2(v.x * w.x, v.y * w.y);
             };
@@ -746,13 +755,18 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16, GN_SYNTH_MINB(LOG2M)) synth
             __syncthreads();      // the last forward pass has been read by every thread
 #pragma unroll
             for (int j = 0; j < 16; ++j) buf[j * NT + threadIdx.x] = z[j];
-            __syncthreads();
             const float2* __restrict__ ab = a.coef;
+            // the first coefficients do not depend on the exchange: their loads fly while the CTA meets at the barrier
+            constexpr int NPRE = GN_COEF_PREFETCH;
+            float2 cpre[NPRE > 0 ? NPRE : 1];
+#pragma unroll
+            for (int j = 0; j < NPRE; ++j) cpre[j] = ld_table(&ab[threadIdx.x + j * NT]);
+            __syncthreads();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int k = threadIdx.x + j * NT;
                 const float2 zm = buf[(M - k) & (M - 1)];      // a warp reads 32 consecutive slots, descending
-                const float2 c = ld_table(&ab[k]);
+                const float2 c = j < NPRE ? cpre[j < NPRE ? j : 0] : ld_table(&ab[k]);
                 z[j] = make_float2(fmaf(c.x, z[j].x, c.y * zm.y), fmaf(c.x, z[j].y, c.y * zm.x));
             }
             // the first inverse pass synchronises before it stores: the partner reads above are complete by then
@@ -822,7 +836,7 @@ static int launch_synth_var(const gn_fft_plan* plan, SynthArgs a, cudaStream_t s
     gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);      // the coefficient slots are the plan's own scratch
     if (VAR >= 1 && MODE != MODE_IRFFT) {
         slot = coef_acquire(pl, a.weights, st);
-        whiten_coef_kernel<<<(M + 255) / 256, 256, 0, st>>>(a.weights, pl->coef[slot], M, a.out_scale);
+        whiten_coef_kernel<<<1, 1024, 0, st>>>(a.weights, a.window, pl->coef[slot], M, a.out_scale);
         a.coef = pl->coef[slot];
     }
     auto release = [&]() {
@@ -866,7 +880,7 @@ static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
         if (grid > cap) grid = cap;
         gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);
         const int slot = coef_acquire(pl, a.weights, st);
-        whiten_coef_kernel<<<(plan->N / 2 + 255) / 256, 256, 0, st>>>(a.weights, pl->coef[slot], plan->N / 2, a.out_scale);
+        whiten_coef_kernel<<<1, 1024, 0, st>>>(a.weights, a.window, pl->coef[slot], plan->N / 2, a.out_scale);
         a.coef = pl->coef[slot];
         whiten64_kernel<<<grid, 64, 0, st>>>(a);
         coef_release(pl, slot, st);
@@ -1033,7 +1047,7 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
     }
     p->coef_next = 0;
     for (int i = 0; i < gn_fft_plan::NSLOT; ++i) {
-        if (cudaMalloc(&p->coef[i], sizeof(float2) * (size_t)(N / 2)) != cudaSuccess ||
+        if (cudaMalloc(&p->coef[i], sizeof(float2) * (size_t)(N / 2 + 1)) != cudaSuccess ||      // + the flat range
             cudaEventCreateWithFlags(&p->coef_done[i], cudaEventDisableTiming) != cudaSuccess) {
             for (int q = 0; q <= i; ++q) {
                 if (p->coef[q]) cudaFree(p->coef[q]);
