@@ -199,6 +199,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # BASELINE's second metric, timed alone before the training loop starts (and again after it, see below)
+    whiten_alone = whiten_roofline(synth_obj, dev, sample_clocks=local if rank == 0 else None)
     for it in range(args.warmup):
         one_step(it)
     barrier()
@@ -296,7 +298,9 @@ def run_ours(args):
            'gpu_launches': launches, 'clocks': clocks}
 
     prof = profile_pass(one_step, args, B, L, N)      # every rank: the steps contain collectives
-    prof['roofline_whiten'] = whiten_roofline(synth_obj, dev)
+    after = whiten_roofline(synth_obj, dev, sample_clocks=local if rank == 0 else None)
+    whiten_alone['after_training_loop'] = {k: after[k] for k in ('achieved', 'frac', 'avg_launch_ms', 'clocks')}
+    prof['roofline_whiten'] = whiten_alone
     if rank == 0:
         out.update(prof)
         if world == 1:
@@ -351,7 +355,7 @@ def profile_pass(one_step, args, B, L, N):
     }
 
 
-def whiten_roofline(synth_obj, dev, batch=8192, iters=10):
+def whiten_roofline(synth_obj, dev, batch=8192, iters=20, sample_clocks=None):
     """BASELINE's second metric, "whitening HBM GB/s": gn_whiten_td_f32 alone (window -> rfft -> weights -> irfft) on
     `batch` resident series of N = 8192 samples, timed with CUDA events; algorithmic bytes 8*N per series (read + write
     the series once; window / weights / twiddles are batch-shared).  536 MB per launch >> 126 MB L2."""
@@ -362,12 +366,16 @@ def whiten_roofline(synth_obj, dev, batch=8192, iters=10):
     for _ in range(3):
         synth_obj.whiten_td(x)
     torch.cuda.synchronize()
+    sampler = ClockSampler(sample_clocks, period_s=0.001) if sample_clocks is not None else None
+    if sampler is not None:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
         synth_obj.whiten_td(x)
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
     ms = e0.elapsed_time(e1) / iters
     nbytes = batch * 8 * N
     gbs = nbytes / (ms / 1e3) / 1e9
@@ -379,10 +387,12 @@ def whiten_roofline(synth_obj, dev, batch=8192, iters=10):
             traffic = json.load(f)['dram_bytes_per_launch']      # ncu --set full capture of the same launch shape
     except Exception:
         pass
-    return {'bound': 'hbm', 'kernel': 'synth_kernel<12,0> (gn_whiten_td_f32: Tukey window, rfft, whitening weights, irfft)',
+    return {'bound': 'hbm', 'kernel': 'synth_kernel<12,0,1> (gn_whiten_td_f32: Tukey window, rfft, whitening weights, irfft; '
+                                      'the timed call includes its ~3 us coefficient prologue whiten_coef_kernel)',
             'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm, 'traffic': traffic, 'peak_source': which,
-            'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': nbytes, 'batch': batch,
-            'note': 'on-chip bound: ~420k FP32 lane-ops and ~4800 L1/shared wavefronts per 64 KiB series (DESIGN.md section 6)'}
+            'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': nbytes, 'batch': batch, 'iters': iters,
+            'clocks': clocks,
+            'note': 'on-chip bound: ~400k FP32 lane-ops and ~4000 L1/shared wavefronts per 64 KiB series (DESIGN.md section 6)'}
 
 
 def cpu_reference_step_fn(sample_batch):

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgennet_b200.so')
+# GENNET_B200_LIB: developer override (kernel experiments built to another file); the product is the in-tree library
+LIB_PATH = os.environ.get('GENNET_B200_LIB') or os.path.join(_HERE, 'libgennet_b200.so')
 
 c_f = ctypes.c_float
 c_d = ctypes.c_double
