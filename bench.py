@@ -299,7 +299,7 @@ def run_ours(args):
 
     prof = profile_pass(one_step, args, B, L, N)      # every rank: the steps contain collectives
     after = whiten_roofline(synth_obj, dev, sample_clocks=local if rank == 0 else None)
-    whiten_alone['after_training_loop'] = {k: after[k] for k in ('achieved', 'frac', 'avg_launch_ms', 'clocks')}
+    whiten_alone['after_training_loop'] = {k: after[k] for k in ('achieved', 'frac', 'avg_launch_ms', 'clocks', 'batch')}
     prof['roofline_whiten'] = whiten_alone
     if rank == 0:
         out.update(prof)
@@ -355,43 +355,55 @@ def profile_pass(one_step, args, B, L, N):
     }
 
 
-def whiten_roofline(synth_obj, dev, batch=8192, iters=20, sample_clocks=None):
+WHITEN_BATCHES = (8192, 32768)      # series per launch; the last one is the headline (2.1 GB in + out per launch)
+
+
+def whiten_roofline(synth_obj, dev, batches=WHITEN_BATCHES, iters=20, sample_clocks=None):
     """BASELINE's second metric, "whitening HBM GB/s": gn_whiten_td_f32 alone (window -> rfft -> weights -> irfft) on
     `batch` resident series of N = 8192 samples, timed with CUDA events; algorithmic bytes 8*N per series (read + write
-    the series once; window / weights / twiddles are batch-shared).  536 MB per launch >> 126 MB L2."""
+    the series once; window / weights / twiddles are batch-shared).  >= 537 MB per launch >> 126 MB L2.  A launch has
+    ~26 us of fixed cost (coefficient prologue, first wave with cold caches and aligned phases, tail of the persistent
+    grid: scratch/whiten_batch.py), so the figure is reported for two batch sizes."""
     import torch
     hbm, _, _, which = peaks()
     N = synth_obj.N
-    x = torch.randn(batch, N, device=dev) * 1e-21
-    for _ in range(3):
-        synth_obj.whiten_td(x)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(sample_clocks, period_s=0.001) if sample_clocks is not None else None
-    if sampler is not None:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        synth_obj.whiten_td(x)
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler is not None else None
-    ms = e0.elapsed_time(e1) / iters
+    by_batch, clocks, ms = {}, None, None
+    for batch in batches:
+        x = torch.randn(batch, N, device=dev) * 1e-21
+        for _ in range(3):
+            synth_obj.whiten_td(x)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(sample_clocks, period_s=0.001) if sample_clocks is not None else None
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            synth_obj.whiten_td(x)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler is not None else None
+        ms = e0.elapsed_time(e1) / iters
+        gbs = batch * 8 * N / (ms / 1e3) / 1e9
+        by_batch[str(batch)] = {'achieved': gbs, 'frac': gbs / hbm, 'avg_launch_ms': ms, 'clocks': clocks}
+        del x
+    batch = batches[-1]
     nbytes = batch * 8 * N
-    gbs = nbytes / (ms / 1e3) / 1e9
+    gbs = by_batch[str(batch)]['achieved']
     traffic = None
     try:
         import glob
         files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_whiten_traffic.json')))
         with open(files[-1]) as f:
-            traffic = json.load(f)['dram_bytes_per_launch']      # ncu --set full capture of the same launch shape
+            t = json.load(f)                  # ncu --set full capture of one launch; scaled per series if the batch differs
+        traffic = t['dram_bytes_per_launch'] * (float(batch) / t.get('batch', 8192))
     except Exception:
         pass
     return {'bound': 'hbm', 'kernel': 'synth_kernel<12,0,1> (gn_whiten_td_f32: Tukey window, rfft, whitening weights, irfft; '
                                       'the timed call includes its ~3 us coefficient prologue whiten_coef_kernel)',
             'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm, 'traffic': traffic, 'peak_source': which,
             'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': nbytes, 'batch': batch, 'iters': iters,
-            'clocks': clocks,
+            'clocks': clocks, 'by_batch': by_batch,
             'note': 'on-chip bound: ~400k FP32 lane-ops and ~4000 L1/shared wavefronts per 64 KiB series (DESIGN.md section 6)'}
 
 
