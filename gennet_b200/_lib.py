@@ -80,6 +80,8 @@ _SIGS = {
     'gn_maxpool1d_bwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_axpy_f32': [c_p, c_p, c_f, c_ll, c_p],
     'gn_gather_rows_f32': [c_p, c_p, c_p, c_i, c_ll, c_p],
+    'gn_kde2d_pdf_f32': [c_p, c_i, c_p, c_i, c_d, c_d, c_d, c_d, c_p, c_p],
+    'gn_overlap_sums_f32': [c_p, c_p, c_ll, c_p, c_p],
     'gn_maxnorm_roll_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
     'gn_flip_transpose_f32': [c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_stack_residual_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],

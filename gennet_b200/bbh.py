@@ -205,3 +205,64 @@ def waveform_percentiles(generated, percentiles=(90, 75, 25, 5)):
     g = g.reshape(g.shape[0], g.shape[1])
     vals = np.percentile(g, list(percentiles), axis=0)
     return {p: vals[i] for i, p in enumerate(percentiles)}
+
+
+class gaussian_kde2d:
+    """``scipy.stats.gaussian_kde(dataset)`` for the two-dimensional (chirp mass, mass ratio) sample sets of
+    make_contour_plot, bbhMahoGANy.py:787-791, evaluated on the device.  ``dataset`` (2, n) as the reference passes it.
+    Bandwidth: Scott's rule ``n**(-1/6)`` on the unbiased data covariance, exactly scipy's default; the small 2x2
+    algebra is done in float64 on the host, the n x m sum of Gaussians by ``gn_kde2d_pdf_f32``."""
+
+    def __init__(self, dataset):
+        d = np.atleast_2d(np.asarray(dataset, dtype=np.float64))
+        if d.shape[0] != 2 or d.shape[1] < 2:
+            raise ValueError('gaussian_kde2d expects a (2, n) dataset with n > 1')
+        self.dataset = d
+        self.d, self.n = d.shape
+        self.factor = float(self.n) ** (-1.0 / (self.d + 4))
+        self._data_covariance = np.atleast_2d(np.cov(d, rowvar=1, bias=False))
+        self.covariance = self._data_covariance * self.factor ** 2
+        self.inv_cov = np.linalg.inv(self._data_covariance) / self.factor ** 2
+        self._norm_factor = np.sqrt(np.linalg.det(2 * np.pi * self.covariance)) * self.n
+        self._mean = d.mean(axis=1)
+        self._dev = nn._to_device(np.ascontiguousarray((d - self._mean[:, None]).T.astype(np.float32)))
+
+    def pdf_device(self, positions):
+        """positions (2, m) -> CUDA float32 tensor (m)."""
+        p = np.atleast_2d(np.asarray(positions, dtype=np.float64))
+        if p.shape[0] != 2:
+            raise ValueError('positions must be (2, m)')
+        pos = nn._to_device(np.ascontiguousarray((p - self._mean[:, None]).T.astype(np.float32)))
+        out = torch.empty((p.shape[1],), dtype=torch.float32, device=pos.device)
+        call('gn_kde2d_pdf_f32', ptr(self._dev), int(self.n), ptr(pos), int(p.shape[1]), float(self.inv_cov[0, 0]),
+             float(self.inv_cov[0, 1]), float(self.inv_cov[1, 1]), float(1.0 / self._norm_factor), ptr(out), stream())
+        return out
+
+    def pdf(self, positions):
+        return self.pdf_device(positions).cpu().numpy().astype(np.float64)
+
+    evaluate = pdf
+    __call__ = pdf
+
+
+def overlap_beta(pred_samp, lalinf_samp, kernel_cnn=None, kernel_lalinf=None, n_grid=100):
+    """The overlap statistic of overlap_tests, bbhMahoGANy.py:853-870: both kernel density estimates on the
+    ``n_grid x n_grid`` ``np.mgrid`` spanning the pooled samples, beta = sum(p q) / sqrt(sum(p^2) sum(q^2)).
+    ``pred_samp``: what ``signal_pe.predict`` returns ([mc (n,1), q (n,1)], or (n,2) for the combined model);
+    ``lalinf_samp``: [mc (m,), q (m,)].  The reference's K-S and Anderson-Darling scores stay with SciPy."""
+    if isinstance(pred_samp, (list, tuple)):
+        px, py = np.asarray(pred_samp[0], np.float64).reshape(-1), np.asarray(pred_samp[1], np.float64).reshape(-1)
+    else:
+        ps = np.asarray(pred_samp, np.float64)
+        px, py = ps[:, 0].reshape(-1), ps[:, 1].reshape(-1)
+    lx, ly = np.asarray(lalinf_samp[0], np.float64).reshape(-1), np.asarray(lalinf_samp[1], np.float64).reshape(-1)
+    comb_mc, comb_q = np.concatenate((px, lx)), np.concatenate((py, ly))
+    X, Y = np.mgrid[np.min(comb_mc):np.max(comb_mc):complex(0, n_grid), np.min(comb_q):np.max(comb_q):complex(0, n_grid)]
+    positions = np.vstack([X.ravel(), Y.ravel()])
+    kernel_cnn = kernel_cnn or gaussian_kde2d(np.array([px, py]))
+    kernel_lalinf = kernel_lalinf or gaussian_kde2d(np.array([lx, ly]))
+    a, b = kernel_cnn.pdf_device(positions), kernel_lalinf.pdf_device(positions)
+    sums = torch.empty((3,), dtype=torch.float64, device=a.device)
+    call('gn_overlap_sums_f32', ptr(a), ptr(b), int(a.numel()), ptr(sums, torch.float64), stream())
+    s = sums.cpu().numpy()
+    return float(s[0] / np.sqrt(s[1] * s[2]))

@@ -264,6 +264,16 @@ int gn_maxpool1d_bwd_f32(const float* x, const float* y, const float* dy, float*
                          void* stream);
 /* a += b (gradient accumulation where two branches share an input, bbhMahoGANy.py:362,382) */
 int gn_axpy_f32(float* a, const float* b, float alpha, long long n, void* stream);
+/* Evaluation stage of the GAN loop (bbhMahoGANy.py:1311-1343 -> make_contour_plot :787-791, overlap_tests :853-870).
+ * gn_kde2d_pdf_f32: scipy.stats.gaussian_kde(dataset).pdf(positions) for a two-dimensional dataset:
+ *   pdf[j] = inv_norm * sum_i exp(-1/2 (x_i - p_j)^T A (x_i - p_j)),  A = [[a11,a12],[a12,a22]] = inverse of the
+ *   bandwidth-scaled data covariance (Scott factor n^(-1/6)), inv_norm = 1 / (n sqrt(det(2 pi covariance))).
+ * data_xy (n,2) f32 and pos_xy (m,2) f32 interleaved (x,y) pairs (the host centres both on the data mean);
+ * pdf (m) f32.
+ * gn_overlap_sums_f32: out3 = {sum a b, sum a^2, sum b^2} (double), beta = out3[0] / sqrt(out3[1] out3[2]) (:868-870). */
+int gn_kde2d_pdf_f32(const float* data_xy, int n, const float* pos_xy, int m, double a11, double a12, double a22,
+                     double inv_norm, float* pdf, void* stream);
+int gn_overlap_sums_f32(const float* a, const float* b, long long n, double* out3, void* stream);
 /* gather rows: out[i,:] = src[idx[i],:]  (template batch assembly, bbhMahoGANy.py:1156-1158,1244) */
 int gn_gather_rows_f32(const float* src, const int* idx, float* out, int n, long long row_len, void* stream);
 
