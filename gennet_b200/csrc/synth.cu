@@ -25,12 +25,15 @@ struct gn_fft_plan {
                   // so that the lanes of a warp (consecutive k) read consecutive 8-byte entries
     float2* tw64; // device, N == 8192 only: [k1][t] = exp(-2*pi*i*k1*t/4096), k1, t < 64 (64 x 64 decomposition)
     // Whitening coefficient tables (alpha_k, beta_k), M entries each, rebuilt by a prologue kernel on every call from
-    // the caller's weights.  A slot is keyed by the weights pointer: calls with the same pointer write the same values
-    // (the caller may not change the weights while a call that reads them is in flight), so they can share the slot on
-    // any number of streams; a slot handed to another pointer first waits for the event that covers its earlier users.
+    // the caller's weights, window and output scale.  A slot is keyed by (weights pointer, window pointer, scale): calls
+    // with the same key write the same values (the caller may not change weights or window while a call that reads them
+    // is in flight), so they can share the slot on any number of streams; a slot handed to another key first waits for
+    // the event that covers its earlier users.
     static constexpr int NSLOT = 4;
     float2* coef[NSLOT];
     const void* coef_key[NSLOT];
+    const void* coef_win[NSLOT];
+    float coef_scale[NSLOT];
     cudaEvent_t coef_done[NSLOT];
     bool coef_used[NSLOT];
     int coef_next;
@@ -790,14 +793,18 @@ static int whiten_variant() {
 }
 
 // Coefficient slot for this call's weights (see gn_fft_plan): the prologue kernel may be launched on `st` afterwards.
-static int coef_acquire(gn_fft_plan* pl, const float* weights, cudaStream_t st) {
+static int coef_acquire(gn_fft_plan* pl, const float* weights, const float* window, float scale, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(pl->mu);
     for (int i = 0; i < gn_fft_plan::NSLOT; ++i)
-        if (pl->coef_key[i] == (const void*)weights) return i;
+        if (pl->coef_key[i] == (const void*)weights && pl->coef_win[i] == (const void*)window &&
+            pl->coef_scale[i] == scale)
+            return i;
     const int slot = pl->coef_next;
     pl->coef_next = (pl->coef_next + 1) % gn_fft_plan::NSLOT;
     if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);
     pl->coef_key[slot] = (const void*)weights;
+    pl->coef_win[slot] = (const void*)window;
+    pl->coef_scale[slot] = scale;
     pl->coef_used[slot] = false;
     return slot;
 }
@@ -835,7 +842,7 @@ static int launch_synth_var(const gn_fft_plan* plan, SynthArgs a, cudaStream_t s
     int slot = -1;
     gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);      // the coefficient slots are the plan's own scratch
     if (VAR >= 1 && MODE != MODE_IRFFT) {
-        slot = coef_acquire(pl, a.weights, st);
+        slot = coef_acquire(pl, a.weights, a.window, a.out_scale, st);
         whiten_coef_kernel<<<1, 1024, 0, st>>>(a.weights, a.window, pl->coef[slot], M, a.out_scale);
         a.coef = pl->coef[slot];
     }
@@ -879,7 +886,7 @@ static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
         const int cap = num_sms() * 6 * 4;
         if (grid > cap) grid = cap;
         gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);
-        const int slot = coef_acquire(pl, a.weights, st);
+        const int slot = coef_acquire(pl, a.weights, a.window, a.out_scale, st);
         whiten_coef_kernel<<<1, 1024, 0, st>>>(a.weights, a.window, pl->coef[slot], plan->N / 2, a.out_scale);
         a.coef = pl->coef[slot];
         whiten64_kernel<<<grid, 64, 0, st>>>(a);
@@ -1042,6 +1049,8 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
     for (int i = 0; i < gn_fft_plan::NSLOT; ++i) {
         p->coef[i] = nullptr;
         p->coef_key[i] = nullptr;
+        p->coef_win[i] = nullptr;
+        p->coef_scale[i] = 0.f;
         p->coef_used[i] = false;
         p->coef_done[i] = nullptr;
     }

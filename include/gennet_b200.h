@@ -67,7 +67,7 @@ int gn_fft_plan_destroy(gn_fft_plan* plan);
  *   y[b, j] = scale * irfft( rfft(window * x[b]) * weights )[crop_lo + j],  j < crop_len
  * x (batch,N) f32; window (N) f32 = tukey(N,1/8); weights (N/2+1) f32 = sqrt(2/(S*fs)), 0 where S<=0, [0]=0.
  * Each call first rebuilds, on `stream`, a per-bin coefficient table from `weights`, `window` and `scale` in scratch
- * owned by the plan (slots keyed by the weights pointer, guarded by events): a plan may be used from several streams
+ * owned by the plan (slots keyed by the weights and window pointers and the scale, guarded by events): a plan may be used from several streams
  * and host threads; as with any asynchronous call, weights/window must not be overwritten while a call that reads
  * them is still in flight.  The same holds for gn_synth_f32. */
 int gn_whiten_td_f32(const gn_fft_plan* plan, const float* x, const float* window, const float* weights,

@@ -308,3 +308,38 @@ def test_whiten_odd_crop_windows_and_two_weight_vectors(gs):
             y = torch.full((3, ln), 7.0, device='cuda')
             call('gn_whiten_td_f32', s._plan, ptr(xd), ptr(s.window), ptr(wts), ptr(y), 3, lo, ln, 1.0, stream())
             assert np.abs(y.cpu().numpy() - r[:, lo:lo + ln]).max() / np.abs(r).max() < TOL, (lo, ln)
+
+
+@pytest.mark.gpu
+def test_whiten_concurrent_streams_share_one_plan(gs):
+    """Two streams interleave calls on one plan with different weights and output scales (more distinct keys than the
+    plan has coefficient slots, so slots are recycled under the event guard); every result must be its own."""
+    import torch
+    from gennet_b200._lib import call, ptr
+    fs, T = 2048, 4
+    N = fs * T
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    rs = np.random.RandomState(11)
+    x = (rs.normal(size=(64, N)) * 1e-21).astype(np.float32)
+    xd = torch.as_tensor(x).cuda()
+    win = s.window.double().cpu().numpy()
+    variants = []
+    for i in range(6):
+        w = (s.weights * (1.0 + 0.25 * i)).contiguous()
+        variants.append((w, 1.0 + i, np.fft.irfft(np.fft.rfft(x.astype(np.float64) * win, axis=1) *
+                                                  w.double().cpu().numpy(), N, axis=1) * (1.0 + i)))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):
+        for i, (w, scale, ref) in enumerate(variants):
+            st = streams[(i + rep) % 2]
+            y = torch.empty((64, N), device='cuda')
+            with torch.cuda.stream(st):
+                call('gn_whiten_td_f32', s._plan, ptr(xd), ptr(s.window), ptr(w), ptr(y), 64, 0, N, float(scale),
+                     st.cuda_stream)
+            outs.append((y, ref))
+    torch.cuda.synchronize()
+    for y, ref in outs:
+        assert rel_err(y.cpu().numpy(), ref) < TOL
