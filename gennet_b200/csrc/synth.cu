@@ -792,9 +792,10 @@ static int whiten_variant() {
     return v;
 }
 
-// Coefficient slot for this call's weights (see gn_fft_plan): the prologue kernel may be launched on `st` afterwards.
+// Coefficient slot for this call's key (see gn_fft_plan): the prologue kernel may be launched on `st` afterwards.
+// The caller holds pl->mu from here until coef_release has returned, so that no other host thread can recycle the slot
+// between this call's prologue and the event that covers its main kernel.
 static int coef_acquire(gn_fft_plan* pl, const float* weights, const float* window, float scale, cudaStream_t st) {
-    std::lock_guard<std::mutex> lock(pl->mu);
     for (int i = 0; i < gn_fft_plan::NSLOT; ++i)
         if (pl->coef_key[i] == (const void*)weights && pl->coef_win[i] == (const void*)window &&
             pl->coef_scale[i] == scale)
@@ -810,7 +811,6 @@ static int coef_acquire(gn_fft_plan* pl, const float* weights, const float* wind
 }
 // After the main kernel: the slot's event must cover this use and every earlier one.
 static void coef_release(gn_fft_plan* pl, int slot, cudaStream_t st) {
-    std::lock_guard<std::mutex> lock(pl->mu);
     if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);      // orders later work on st only
     cudaEventRecord(pl->coef_done[slot], st);
     pl->coef_used[slot] = true;
@@ -841,7 +841,9 @@ static int launch_synth_var(const gn_fft_plan* plan, SynthArgs a, cudaStream_t s
     }
     int slot = -1;
     gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);      // the coefficient slots are the plan's own scratch
+    std::unique_lock<std::mutex> lock(pl->mu, std::defer_lock);
     if (VAR >= 1 && MODE != MODE_IRFFT) {
+        lock.lock();
         slot = coef_acquire(pl, a.weights, a.window, a.out_scale, st);
         whiten_coef_kernel<<<1, 1024, 0, st>>>(a.weights, a.window, pl->coef[slot], M, a.out_scale);
         a.coef = pl->coef[slot];
@@ -886,6 +888,7 @@ static int launch_synth(const gn_fft_plan* plan, SynthArgs a, cudaStream_t st) {
         const int cap = num_sms() * 6 * 4;
         if (grid > cap) grid = cap;
         gn_fft_plan* pl = const_cast<gn_fft_plan*>(plan);
+        std::lock_guard<std::mutex> lock(pl->mu);
         const int slot = coef_acquire(pl, a.weights, a.window, a.out_scale, st);
         whiten_coef_kernel<<<1, 1024, 0, st>>>(a.weights, a.window, pl->coef[slot], plan->N / 2, a.out_scale);
         a.coef = pl->coef[slot];

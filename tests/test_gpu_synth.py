@@ -343,3 +343,51 @@ def test_whiten_concurrent_streams_share_one_plan(gs):
     torch.cuda.synchronize()
     for y, ref in outs:
         assert rel_err(y.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.gpu
+def test_whiten_host_threads_share_one_plan(gs):
+    """Two host threads (ctypes releases the GIL), each on its own stream and with its own weights and scales, hammer one
+    plan: the slot bookkeeping is serialised by the plan's mutex from prologue to event record."""
+    import threading
+    import torch
+    from gennet_b200._lib import call, ptr
+    fs, T = 512, 4
+    N = fs * T
+    psd = so.analytic_psd(fs, T)
+    s = gs.Synthesizer(fs, T, psd)
+    rs = np.random.RandomState(12)
+    x = (rs.normal(size=(16, N)) * 1e-21).astype(np.float32)
+    xd = torch.as_tensor(x).cuda()
+    win = s.window.double().cpu().numpy()
+    base = np.fft.rfft(x.astype(np.float64) * win, axis=1)
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            ws = [(s.weights * (1.0 + 0.5 * tid + 0.1 * j)).contiguous() for j in range(5)]
+            torch.cuda.synchronize()
+            outs = []
+            for it in range(40):
+                j = it % 5
+                y = torch.empty((16, N), device='cuda')
+                with torch.cuda.stream(st):
+                    call('gn_whiten_td_f32', s._plan, ptr(xd), ptr(s.window), ptr(ws[j]), ptr(y), 16, 0, N,
+                         float(1 + j), st.cuda_stream)
+                outs.append((y, j))
+            st.synchronize()
+            results[tid] = [(y.cpu().numpy(), ws[j].double().cpu().numpy(), 1.0 + j) for y, j in outs]
+        except Exception as e:      # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for tid in (0, 1):
+        for y, w, scale in results[tid]:
+            assert rel_err(y, np.fft.irfft(base * w, N, axis=1) * scale) < TOL
