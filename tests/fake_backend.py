@@ -215,6 +215,18 @@ class Fake:
     def gn_gather_rows_f32(self, src, idx, out, n, row_len, st):
         out.reshape(n, row_len).copy_(src.reshape(-1, row_len)[idx.long()])
 
+    def gn_kde2d_pdf_f32(self, data, n, pos, m, a11, a12, a22, inv_norm, pdf, st):
+        d = data.reshape(n, 2).double()
+        q = pos.reshape(m, 2).double()
+        dx = d[:, 0][None, :] - q[:, 0][:, None]
+        dy = d[:, 1][None, :] - q[:, 1][:, None]
+        e = 0.5 * (a11 * dx * dx + 2.0 * a12 * dx * dy + a22 * dy * dy)
+        pdf.copy_((torch.exp(-e).sum(1) * inv_norm).float())
+
+    def gn_overlap_sums_f32(self, a, b, n, out3, st):
+        x, y = a.reshape(-1).double(), b.reshape(-1).double()
+        out3.copy_(torch.stack([(x * y).sum(), (x * x).sum(), (y * y).sum()]))
+
     def gn_flip_transpose_f32(self, src, out, k, A, Bn, st):
         out.reshape(k, A, Bn).copy_(src.reshape(k, Bn, A).flip(0).permute(0, 2, 1))
 

@@ -136,3 +136,17 @@ def test_two_model_version_wiring(fake):
     errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
     assert all(np.array_equal(a, b) for a, b in zip(dw, D.get_weights()))
     pc.compare_weights(G, og, w0[:len(G.get_weights())])
+
+
+def test_overlap_beta_host_algebra_matches_scipy_golden(fake):
+    """bbh.gaussian_kde2d / overlap_beta: Scott factor, covariance, normalisation, centring and the comparison grid are
+    host code; with the two device entry points answered by the CPU stand-in the score must equal SciPy's."""
+    import os
+    from gennet_b200 import bbh
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'kde_overlap.npz'))
+    k = bbh.gaussian_kde2d(g['pred'])
+    assert abs(k.factor - 1500 ** (-1.0 / 6)) < 1e-15
+    p = k.pdf(g['positions'])
+    assert np.abs(p - g['cnn_pdf']).max() < 2e-6 * g['cnn_pdf'].max()          # positions pass through float32
+    beta = bbh.overlap_beta([g['pred'][0][:, None], g['pred'][1][:, None]], [g['lal'][0], g['lal'][1]])
+    assert abs(beta - float(g['beta'])) < 1e-6
