@@ -131,32 +131,45 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
         const long long q0 = r0 + (long long)ry * per_lane, q1 = min(r1, q0 + per_lane);
         int l = 0;
         int b = (q0 < q1) ? (int)fast_div(q0, Lout, l) : 0;
-#pragma unroll 4
-        for (long long row = q0; row < q1; ++row, ++l) {
-            if (l == Lout) { l = 0; ++b; }
-            uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * ld + co0) + g);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-            float gv[8];
+        // rows in batches of U: all U 128-bit dy loads of a thread are issued before the first is used (the kernel is
+        // latency bound otherwise: two 256-thread blocks per SM at ~100 registers keep too few bytes in flight)
+        constexpr int U = CIN == 1 ? 8 : 2;      // CIN = 2 already sits at the 128-register limit of two blocks per SM
+        const uint4* __restrict__ dyg = reinterpret_cast<const uint4*>(dy + co0) + g;
+        const size_t ldv = (size_t)ld / 8;      // dy row pitch in uint4 (ld % 8 == 0)
+        for (long long row = q0; row < q1; row += U) {
+            uint4 pkv[U];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 v = __bfloat1622float2(h[e]);
-                gv[2 * e] = v.x;
-                gv[2 * e + 1] = v.y;
-            }
+            for (int u = 0; u < U; ++u)
+                pkv[u] = (row + u < q1) ? __ldg(dyg + (size_t)(row + u) * ldv) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) accb[j] += gv[j];
+            for (int u = 0; u < U; ++u) {
+                if (row + u < q1) {
+                    if (l == Lout) { l = 0; ++b; }
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pkv[u]);
+                    float gv[8];
 #pragma unroll
-            for (int t = 0; t < KMAX; ++t) {
-                if (t < k) {
-                    const int pos = l * s + t - p;
-                    if (pos >= 0 && pos < L) {
+                    for (int e = 0; e < 4; ++e) {
+                        float2 v = __bfloat1622float2(h[e]);
+                        gv[2 * e] = v.x;
+                        gv[2 * e + 1] = v.y;
+                    }
 #pragma unroll
-                        for (int c = 0; c < CIN; ++c) {
-                            const float xv = __ldg(&x[((size_t)b * L + pos) * CIN + c]);
+                    for (int j = 0; j < 8; ++j) accb[j] += gv[j];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[t * CIN + c][j] = fmaf(xv, gv[j], acc[t * CIN + c][j]);
+                    for (int t = 0; t < KMAX; ++t) {
+                        if (t < k) {
+                            const int pos = l * s + t - p;
+                            if (pos >= 0 && pos < L) {
+#pragma unroll
+                                for (int c = 0; c < CIN; ++c) {
+                                    const float xv = __ldg(&x[((size_t)b * L + pos) * CIN + c]);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) acc[t * CIN + c][j] = fmaf(xv, gv[j], acc[t * CIN + c][j]);
+                                }
+                            }
                         }
                     }
+                    ++l;
                 }
             }
         }

@@ -751,17 +751,29 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
 // ------------------------------------------------------------------------------------------------ helpers
 // weights: f32 (k,Cin,Cout) -> bf16 same layout (dgrad B operand: K = co contiguous) and bf16 transposed
 // (k,Cout,Cin) (forward B operand: K = ci contiguous)
+// One 32 x 32 (ci, co) tile of one tap per block, transposed through shared memory: both outputs are written with
+// consecutive lanes on consecutive addresses (the direct form scattered 2-byte stores Cin elements apart).
 __global__ void __launch_bounds__(256) conv_w_cast_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wk,
                                                           __nv_bfloat16* __restrict__ wt, int k, int Cin, int Cout) {
-    const long long n = (long long)k * Cin * Cout;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        int co = (int)(i % Cout);
-        long long r = i / Cout;
-        int ci = (int)(r % Cin);
-        int t = (int)(r / Cin);
-        __nv_bfloat16 h = __float2bfloat16_rn(w[i]);
-        wk[i] = h;
-        wt[((size_t)t * Cout + co) * Cin + ci] = h;
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int t = blockIdx.z;
+    const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        if (ci < Cin && co < Cout) {
+            const size_t i = ((size_t)t * Cin + ci) * Cout + co;
+            const __nv_bfloat16 h = __float2bfloat16_rn(w[i]);
+            wk[i] = h;
+            tile[r][tx] = h;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        if (ci < Cin && co < Cout) wt[((size_t)t * Cout + co) * Cin + ci] = tile[tx][r];
     }
 }
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
@@ -924,8 +936,8 @@ using namespace gn;
 
 extern "C" int gn_conv_w_to_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, void* stream) {
     GN_REQUIRE(w && wk && wt && k > 0 && Cin > 0 && Cout > 0, "null pointer or bad size");
-    long long n = (long long)k * Cin * Cout;
-    unsigned grid = (unsigned)((n + 255) / 256 < 8LL * num_sms() ? (n + 255) / 256 : 8LL * num_sms());
+    GN_REQUIRE(k <= 65535 && (Cin + 31) / 32 <= 65535, "weight tensor too large for the cast grid");
+    dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32), (unsigned)k);
     conv_w_cast_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
     return cuda_status("conv_w_cast_kernel");
 }
