@@ -149,7 +149,6 @@ class Ctx:
         dp = _STATE['dp']
         self.world = dp.world if dp is not None else 1
         self.dp = dp
-        self.grad_sync = None      # _GradSync of the model whose train_on_batch owns this context (data parallel only)
 
 
 # ----------------------------------------------------------------------------- symbolic graph
@@ -1370,10 +1369,7 @@ class Model(Layer):
         for o, g in zip(self._out_nodes, dys):
             grads[id(o)] = g
         first_users = self._nodes_needing_dx(ctx, need_dx)
-        sync = ctx.grad_sync if (ctx.grad_sync is not None and ctx.grad_sync.owner is self) else None
-        for step, n in enumerate(reversed(self._order)):
-            if sync is not None and step > 0:
-                sync.passed(step - 1)      # everything up to the previous node has been enqueued
+        for n in reversed(self._order):
             g = grads.pop(id(n), None)
             if g is None:
                 continue
@@ -1464,13 +1460,12 @@ class Model(Layer):
                 ctx.dp.all_reduce(d)
             dys.append(d)
             invs += [inv_rows, inv_rows]
+        self.backward(dys if self._multi_out else dys[0], ctx, need_dx=False)
         segs = c['segments']
         if ctx.world > 1:
-            ctx.grad_sync = _GradSync(self, c, ctx.dp)
-        self.backward(dys if self._multi_out else dys[0], ctx, need_dx=False)
-        if ctx.world > 1:
-            ctx.grad_sync.finish(res)
-            ctx.grad_sync = None
+            for _, p, g in segs:
+                ctx.dp.all_reduce(g)
+            ctx.dp.all_reduce(res)
         self.optimizer.apply(segs, 1.0)
         if len(set(invs)) == 1:
             res = res * invs[0]
@@ -1581,76 +1576,6 @@ def _home_params(params):
         p.data = view
         p.grad = grad[o:o + p.numel()].view(p.shape)
         p.arena, p.offset = arena, o
-
-
-class _GradSync:
-    """Data-parallel gradient exchange overlapped with the backward pass.
-
-    The trainable gradients of a compiled model live in flat arena segments.  They are cut into buckets of consecutive
-    parameters (>= ``BUCKET`` floats); a bucket is final once the last graph node owning one of its parameters has run
-    its backward (a bias gradient produced by the consumer's data-gradient epilogue is written before that, the consumer
-    comes earlier in the reversed order).  ``passed(i)`` is called by the owning model's backward loop after node i of
-    the reversed order has been enqueued and starts the asynchronous all-reduce of every bucket that became final, so
-    the exchange of the deep layers runs under the backward kernels of the shallow ones; ``finish`` starts what is left
-    (plus the loss / metric sums) and makes the compute stream wait for all of it before the optimizer."""
-    BUCKET = 1 << 20
-
-    def __init__(self, model, compiled, dp):
-        self.owner, self.dp, self.handles = model, dp, []
-        plan = compiled.get('sync_plan')
-        if plan is None:
-            plan = compiled['sync_plan'] = self._plan(model, compiled)
-        self.plan = plan                       # [(ready_step, grad_slice)] sorted by ready_step
-        self.next = 0
-
-    @classmethod
-    def _plan(cls, model, compiled):
-        order = list(reversed(model._order))
-        last = {}                              # id(param) -> last step (reversed order) of a node owning it
-        for step, n in enumerate(order):
-            for l in n.layer.all_layers():
-                for p in l.params:
-                    last[id(p)] = step
-        train_layers = [l for l in model.all_layers() if id(l) in compiled['trainable_ids']]
-        tparams, seen = [], set()
-        for l in train_layers:
-            for p in l.params:
-                if p.trainable and id(p) not in seen:
-                    seen.add(id(p))
-                    tparams.append(p)
-        covered = sum((p.numel() + 3) // 4 * 4 for p in tparams)
-        if covered != sum(g.numel() for _, _, g in compiled['segments']):
-            # parameters shared in a way the bucket walk does not understand: exchange whole segments after backward
-            return [(len(order), g) for _, _, g in compiled['segments']]
-        tparams.sort(key=lambda p: (id(p.arena), p.offset))
-        plan, cur = [], None                   # cur = [arena, lo, hi, ready]
-        for p in tparams:
-            end = p.offset + (p.numel() + 3) // 4 * 4
-            ready = last.get(id(p), len(order) - 1)
-            if cur is not None and cur[0] is p.arena and cur[2] == p.offset and cur[2] - cur[1] < cls.BUCKET:
-                cur[2], cur[3] = end, max(cur[3], ready)
-            else:
-                if cur is not None:
-                    plan.append(cur)
-                cur = [p.arena, p.offset, end, ready]
-        if cur is not None:
-            plan.append(cur)
-        plan.sort(key=lambda b: b[3])
-        return [(ready, a['grad'][lo:hi]) for a, lo, hi, ready in plan]
-
-    def passed(self, step):
-        while self.next < len(self.plan) and self.plan[self.next][0] <= step:
-            self.handles.append(self.dp.all_reduce(self.plan[self.next][1], async_op=True))
-            self.next += 1
-
-    def finish(self, extra=None):
-        self.passed(1 << 30)
-        if extra is not None:
-            self.handles.append(self.dp.all_reduce(extra, async_op=True))
-        for h in self.handles:
-            if h is not None:
-                h.wait()
-        self.handles = []
 
 
 def _segments(params):

@@ -19,10 +19,7 @@ class DataParallel:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def all_reduce(self, t, async_op=False):
-        """Sum over ranks in place.  async_op: returns the work handle (the caller waits on it before using ``t``)."""
-        if async_op:
-            return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+    def all_reduce(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 

@@ -150,37 +150,3 @@ def test_overlap_beta_host_algebra_matches_scipy_golden(fake):
     assert np.abs(p - g['cnn_pdf']).max() < 2e-6 * g['cnn_pdf'].max()          # positions pass through float32
     beta = bbh.overlap_beta([g['pred'][0][:, None], g['pred'][1][:, None]], [g['lal'][0], g['lal'][1]])
     assert abs(beta - float(g['beta'])) < 1e-6
-
-
-def test_gradient_sync_plan_covers_the_arena_and_orders_buckets(fake):
-    """_GradSync (overlapped data-parallel gradient exchange): the buckets partition the trainable gradient arena, a
-    bucket never becomes ready before the last node that owns one of its parameters, and the deep tower's buckets are
-    ready while the shallow tower still has backward work to do."""
-    from gennet_b200 import bbh, nn
-    nn.set_seed(1)
-    bbh.n_pix = 512
-    pe = bbh.signal_pe_model()
-    pe.compile(loss='mean_squared_error', optimizer=nn.Adam(lr=9e-5, beta_1=0.5), metrics=['accuracy'])
-    old = nn._GradSync.BUCKET
-    nn._GradSync.BUCKET = 1 << 16
-    try:
-        plan = nn._GradSync._plan(pe, pe._compiled)
-    finally:
-        nn._GradSync.BUCKET = old
-    segs = pe._compiled['segments']
-    assert sum(g.numel() for _, g in plan) == sum(g.numel() for _, _, g in segs)
-    lo = sorted((g.data_ptr(), g.numel()) for _, g in plan)
-    for (p0, n0), (p1, _) in zip(lo, lo[1:]):
-        assert p0 + 4 * n0 == p1                        # contiguous, no overlap
-    order = list(reversed(pe._order))
-    last = {}
-    for step, n in enumerate(order):
-        for l in n.layer.all_layers():
-            for p in l.params:
-                last[id(p)] = step
-    for ready, g in plan:
-        a0, a1 = g.data_ptr(), g.data_ptr() + 4 * g.numel()
-        owners = [last[id(p)] for l in pe.all_layers() for p in l.params
-                  if p.grad is not None and a0 <= p.grad.data_ptr() < a1]
-        assert owners and ready == max(owners)
-    assert len(plan) >= 3 and plan[0][0] < len(order) // 2 and [r for r, _ in plan] == sorted(r for r, _ in plan)
