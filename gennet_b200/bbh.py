@@ -266,3 +266,21 @@ def overlap_beta(pred_samp, lalinf_samp, kernel_cnn=None, kernel_lalinf=None, n_
     call('gn_overlap_sums_f32', ptr(a), ptr(b), int(a.numel()), ptr(sums, torch.float64), stream())
     s = sums.cpu().numpy()
     return float(s[0] / np.sqrt(s[1] * s[2]))
+
+
+def overlap_tests(pred_samp, lalinf_samp, true_vals=None, kernel_cnn=None, kernel_lalinf=None):
+    """bbhMahoGANy.py:811-871, same arguments and return value ``(ks_score, ad_score, beta_score)``.  The two-sample
+    K-S and Anderson-Darling scores are the reference's own SciPy calls on a few thousand host samples (:836-850); the
+    overlap score runs on the device (``overlap_beta``).  ``pred_samp`` is what ``signal_pe.predict`` returned:
+    [mc (n,1), q (n,1)], or (n,2) with ``comb_pe_model``; kernels default to the KDEs of the two sample sets."""
+    from scipy.stats import anderson_ksamp, ks_2samp
+    if isinstance(pred_samp, (list, tuple)):
+        px, py = np.asarray(pred_samp[0]).reshape(-1), np.asarray(pred_samp[1]).reshape(-1)
+    else:
+        ps = np.asarray(pred_samp)
+        px, py = ps[:, 0].reshape(-1), ps[:, 1].reshape(-1)
+    lx, ly = np.asarray(lalinf_samp[0][:]).reshape(-1), np.asarray(lalinf_samp[1][:]).reshape(-1)
+    ks_score = np.array([ks_2samp(px, lx), ks_2samp(py, ly)])
+    ad_score = [anderson_ksamp([px, lx]), anderson_ksamp([py, ly])]
+    beta_score = overlap_beta([px, py], [lx, ly], kernel_cnn=kernel_cnn, kernel_lalinf=kernel_lalinf)
+    return ks_score, ad_score, beta_score

@@ -150,3 +150,20 @@ def test_overlap_beta_host_algebra_matches_scipy_golden(fake):
     assert np.abs(p - g['cnn_pdf']).max() < 2e-6 * g['cnn_pdf'].max()          # positions pass through float32
     beta = bbh.overlap_beta([g['pred'][0][:, None], g['pred'][1][:, None]], [g['lal'][0], g['lal'][1]])
     assert abs(beta - float(g['beta'])) < 1e-6
+
+
+def test_overlap_tests_mirrors_the_reference_triplet(fake):
+    """bbh.overlap_tests (bbhMahoGANy.py:811-871): K-S and Anderson-Darling are SciPy's, beta is the device path."""
+    import os
+    import warnings
+    from scipy.stats import anderson_ksamp, ks_2samp
+    from gennet_b200 import bbh
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'kde_overlap.npz'))
+    pred, lal = g['pred'], g['lal']
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ks, ad, beta = bbh.overlap_tests([pred[0][:, None], pred[1][:, None]], [lal[0], lal[1]], true_vals=[30.0, 0.8])
+        ref_ad = anderson_ksamp([pred[1], lal[1]])
+    assert ks.shape == (2, 2) and np.allclose(ks[0], ks_2samp(pred[0], lal[0]))
+    assert len(ad) == 2 and ad[1].statistic == ref_ad.statistic
+    assert abs(beta - float(g['beta'])) < 1e-6
