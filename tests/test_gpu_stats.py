@@ -70,3 +70,13 @@ def test_kde_argument_validation(bbh):
     d = torch.zeros(8, device='cuda')
     with pytest.raises(_lib.GennetError):
         _lib.call('gn_kde2d_pdf_f32', _lib.ptr(d), 4, _lib.ptr(d), 4, 1.0, 2.0, 1.0, 1.0, _lib.ptr(d), _lib.stream())
+
+
+def test_overlap_tests_triplet(bbh):
+    """bbh.overlap_tests, the drop-in for bbhMahoGANy.py:811-871: SciPy K-S / Anderson-Darling + device beta."""
+    import warnings
+    g = np.load(GOLD)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ks, ad, beta = bbh.overlap_tests([g['pred'][0][:, None], g['pred'][1][:, None]], [g['lal'][0], g['lal'][1]], [30, 0.8])
+    assert ks.shape == (2, 2) and len(ad) == 2 and abs(beta - float(g['beta'])) < 1e-5
