@@ -362,8 +362,8 @@ def whiten_roofline(synth_obj, dev, batches=WHITEN_BATCHES, iters=20, sample_clo
     """BASELINE's second metric, "whitening HBM GB/s": gn_whiten_td_f32 alone (window -> rfft -> weights -> irfft) on
     `batch` resident series of N = 8192 samples, timed with CUDA events; algorithmic bytes 8*N per series (read + write
     the series once; window / weights / twiddles are batch-shared).  >= 537 MB per launch >> 126 MB L2.  A launch has
-    ~26 us of fixed cost (coefficient prologue, first wave with cold caches and aligned phases, tail of the persistent
-    grid: scratch/whiten_batch.py), so the figure is reported for two batch sizes."""
+    ~20 us of fixed cost (coefficient prologue, first wave with cold caches and aligned phases, tail of the
+    grid: scratch/whiten_batch.py, scratch/whiten_waves.py), so the figure is reported for two batch sizes."""
     import torch
     hbm, _, _, which = peaks()
     N = synth_obj.N
