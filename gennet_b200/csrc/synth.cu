@@ -832,7 +832,7 @@ static int launch_synth_var(const gn_fft_plan* plan, SynthArgs a, cudaStream_t s
     const int M = plan->N / 2;
     const size_t smem = (size_t)(M + (M >> 4) + 1) * sizeof(float2);
     const int threads = M / 16;
-    // persistent CTAs: a multiple of the SM count, at most the batch
+    // one CTA per series; beyond GN_WAVES waves of resident CTAs the CTAs stride over the batch
     int grid = a.batch;
     {
         const int per_sm = threads >= 512 ? 1 : (threads >= 256 ? 65536 / (256 * GN_SYNTH_REGS) : 6);
@@ -840,7 +840,7 @@ static int launch_synth_var(const gn_fft_plan* plan, SynthArgs a, cudaStream_t s
 #define GN_WAVES 64     // CTAs per resident slot: the per-CTA prologue is a few instructions, so one series per CTA (up to
                          // 64 waves) lets the hardware scheduler balance the tail: 599 -> 575 us on 32768 series against 4 waves
 #endif
-        const int cap = num_sms() * per_sm * GN_WAVES;      // a few series per CTA slot keeps the tail short
+        const int cap = num_sms() * per_sm * GN_WAVES;
         if (grid > cap) grid = cap;
     }
     int slot = -1;
