@@ -1,4 +1,4 @@
-"""Timings and float64 error of the synthesis kernel organisations (GN_SYNTH_VAR = 0, 1, 2) on one GPU.
+"""Timings and float64 error of the synthesis kernel organisations (GN_SYNTH_VAR = 0, 1; GN_WHITEN_RADIX = 64) on one GPU.
 Each variant runs in its own process (the selection is read once per process)."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -39,7 +39,7 @@ print('VAR=%%s err=%%.2e | whiten full %%.1f us %%.0f GB/s | crop %%.1f us %%.0f
     t3 * 1e3, B * (4 * N + 4 * fs) / t3 / 1e6, t4 * 1e3))
 ''' % ROOT
 # arguments: comma-separated KEY=VALUE settings per run, e.g.  GN_SYNTH_VAR=2,GN_SYNTH_WAVES=1  GN_WHITEN_RADIX=64
-for spec in (sys.argv[1:] or ['GN_SYNTH_VAR=0', 'GN_SYNTH_VAR=1', 'GN_SYNTH_VAR=2']):
+for spec in (sys.argv[1:] or ['GN_SYNTH_VAR=0', 'GN_SYNTH_VAR=1', 'GN_WHITEN_RADIX=64']):
     env = dict(os.environ)
     env.update(kv.split('=') for kv in spec.split(','))
     r = subprocess.run([sys.executable, '-c', CHILD], env=env, capture_output=True, text=True)
