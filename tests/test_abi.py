@@ -35,6 +35,10 @@ def test_version_and_error_channel():
     assert rc == -1 and b'power of two' in lib.gn_last_error()
     rc = lib.gn_dense_fwd_f32(None, None, None, None, 1, 1, 1, 0, 0.0, None)
     assert rc == -1 and b'null pointer' in lib.gn_last_error()
+    rc = lib.gn_kde2d_pdf_f32(None, 4, None, 4, 1.0, 0.0, 1.0, 1.0, None, None)
+    assert rc == -1 and b'null pointer' in lib.gn_last_error()
+    rc = lib.gn_overlap_sums_f32(None, None, 10, None, None)
+    assert rc == -1 and b'null pointer' in lib.gn_last_error()
 
 
 def test_no_cpu_fallback_without_device():
