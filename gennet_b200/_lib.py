@@ -41,6 +41,11 @@ _SIGS = {
     'gn_conv1d_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_dgrad_bf16': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_split_f32_bf16': [c_p, c_p, c_ll, c_i, c_p],
+    'gn_conv_w_split_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_fwd_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    'gn_conv1d_dgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    'gn_conv1d_wgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_smallcin_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_dgrad_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

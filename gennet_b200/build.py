@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgennet_b200.so')
-SOURCES = ['api.cu', 'synth.cu', 'conv_dense_f32.cu', 'elementwise.cu', 'conv1d_tc.cu', 'bf16_small.cu', 'bn_bf16.cu', 'stats.cu']
+SOURCES = ['api.cu', 'synth.cu', 'conv_dense_f32.cu', 'elementwise.cu', 'conv1d_tc.cu', 'conv1d_tc3.cu', 'bf16_small.cu', 'bn_bf16.cu', 'stats.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         if not os.path.exists(s):
-            continue
+            raise RuntimeError('CUDA source %s is listed in SOURCES but missing' % s)
         o = os.path.join(CSRC, src[:-3] + '.o')
         objs.append(o)
         if force or _stale(o, [s] + headers):

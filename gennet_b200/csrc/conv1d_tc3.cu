@@ -1,0 +1,827 @@
+// Conv1D as implicit GEMM on the 5th-generation tensor cores (tcgen05) AT FLOAT32 ACCURACY: split-bf16 operands.
+//
+//   The reference trains in float32 (cuDNN / Eigen fp32 convolutions behind the Conv1D layers of
+//   bbhMahoGANy.py:250-292,362-395).  A float32 value x is carried as NC bf16 "planes"
+//        x = x0 + x1 + x2,   x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1)       (NC = 3: 24 mantissa bits)
+//   and a product a*b is accumulated in fp32 tensor memory as the sum of the plane products a_i*b_j with i + j < NC
+//   (NC = 3: six tcgen05.mma per K step, dropped terms <= 2^-23 |a||b|; NC = 2: three, <= 2^-15).  Products of bf16
+//   values are exact in fp32, so the result differs from an fp32 FMA chain only by accumulation order.
+//
+//   Layout: every operand tensor is stored as (NC, B, L, C) bf16 (plane-major).  One 4-D TMA load per operand and
+//   pipeline stage brings the (128 | BN) rows x 32 channels x NC planes box of one tap (SWIZZLE_64B; K = 32 per stage
+//   so that NC planes of both operands fit three to six stages).  Zero padding, sample boundaries, ragged tails and the
+//   stride-2 sampling come from TMA out-of-bounds fill / traversal stride exactly as in conv1d_tc.cu.
+//   Warp roles (320 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer, warps 2-9 two epilogue sets
+//   (tcgen05.ld -> bias / activation | activation-derivative mask -> fp32 rows stored straight from registers: a
+//   thread owns 32 consecutive channels of one output row = one full 128-byte line -> optional re-split into the
+//   planes the next convolution consumes -> optional per-channel column sums).  With six MMAs per K step the tensor
+//   pipe is the bound on every layer, so the epilogue needs no shared-memory staging.
+//
+//   forward : Y[b,l,co]  = act( sum_{t,ci} X[b, l*s+t-p, ci] * W[t,ci,co] + bias[co] )      A=X   (K-major)  B=Wt[t][co][ci]
+//   dgrad   : dX[b,j,ci] = act'(Xin[b,j,ci]) * sum_{t,co} dY[b,(j+p-t)/s,co] * W[t,ci,co]    A=dY  (K-major)  B=W [t][ci][co]
+//   wgrad   : dW[t,ci,co] = sum_{b,l} X[b,l*s+t-p,ci] * dY[b,l,co]                           A=X^T, B=dY (both MN-major)
+#include "tc_common.cuh"
+
+namespace gn {
+
+int launch_colsum(const float* x, long long rows, int C, float* out, cudaStream_t st);      // conv_dense_f32.cu
+
+constexpr int T3_BK = 32;            // bf16 elements per 64-byte swizzle row = K per pipeline stage
+constexpr int T3_THREADS = 320;      // warps: 0 TMA producer, 1 MMA issuer, 2-5 and 6-9 epilogue (alternate 32-column slabs)
+constexpr int T3_EPI_SETS = 2;
+constexpr int T3_WG_THREADS = 192;   // wgrad: warps 0 producer, 1 MMA, 2-5 epilogue
+constexpr int T3_SMEM_BUDGET = 232448 - 1024 /*align slack*/ - 256 /*barriers*/;
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// float32 -> NC bf16 planes (round to nearest each step; the residuals are exact in fp32)
+template <int NC>
+__device__ __forceinline__ void split3(float x, __nv_bfloat16 (&p)[3]) {
+    p[0] = __float2bfloat16_rn(x);
+    if (NC > 1) {
+        const float r1 = x - __bfloat162float(p[0]);
+        p[1] = __float2bfloat16_rn(r1);
+        if (NC > 2) p[2] = __float2bfloat16_rn(r1 - __bfloat162float(p[1]));
+    }
+}
+
+struct Tc3Args {
+    int B, L, Lout, Cin, Cout, k, s, p;   // convolution geometry (L = input length, Lout = output length)
+    int mode;                              // 0 fwd, 1 dgrad
+    int act;                               // fwd: output activation; dgrad: derivative mask taken from `aux`
+    float act_param;
+    const float* bias;                     // fwd, may be null
+    const float* aux;                      // dgrad: the conv's own input X in fp32 (output of the previous activation) or null
+    float* out;                            // fp32 result: fwd Y (B,Lout,Cout); dgrad dX (B,L,Cin); may be null
+    __nv_bfloat16* planes;                 // optional: the same result re-split as (NC,B,rows,C) bf16 planes
+    long long plane_stride;                // elements between planes of `planes`
+    float* colsum;                         // optional: per-channel sum of the result over (b, row), atomically accumulated
+    int m_tiles;                           // tiles of 128 rows per (sample, parity)
+};
+
+template <int BN, int NC>
+struct T3Smem {
+    static constexpr int A_PLANE = TC_BM * 64;       // 128 rows x 64 B
+    static constexpr int B_PLANE = BN * 64;
+    static constexpr int STAGE_BYTES = NC * (A_PLANE + B_PLANE);
+    static constexpr int STAGES_MAX = T3_SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+// plane pairs (i, j), i + j < NC, smallest products first
+template <int NC> struct PlanePairs;
+template <> struct PlanePairs<1> { static constexpr int N = 1; __host__ __device__ static constexpr int a(int) { return 0; } __host__ __device__ static constexpr int b(int) { return 0; } };
+template <> struct PlanePairs<2> {
+    static constexpr int N = 3;
+    __host__ __device__ static constexpr int a(int q) { return q == 0 ? 1 : 0; }
+    __host__ __device__ static constexpr int b(int q) { return q == 1 ? 1 : 0; }
+};
+template <> struct PlanePairs<3> {
+    static constexpr int N = 6;      // (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
+    __host__ __device__ static constexpr int a(int q) { return q == 0 ? 2 : ((q == 1 || q == 3) ? 1 : 0); }
+    __host__ __device__ static constexpr int b(int q) { return q == 2 ? 2 : ((q == 1 || q == 4) ? 1 : 0); }
+};
+
+// ------------------------------------------------------------------------------------------------ fwd / dgrad
+// Persistent: grid = min(#tiles, #SMs), tile = blockIdx.x + i*gridDim.x with the n-tile fastest.  Pipelines:
+//   shared-memory ring (full/empty mbarriers)      TMA producer -> MMA issuer
+//   TMEM accumulator ring (2 x BN fp32 columns)    MMA issuer   -> epilogue warps
+template <int BN, int NC, bool AUX>
+__global__ void __launch_bounds__(T3_THREADS)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Tc3Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = T3Smem<BN, NC>;
+    constexpr int STAGES = S::STAGES;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npar = (a.mode == 1) ? a.s : 1;
+    const int kdim = (a.mode == 0) ? a.Cin : a.Cout;   // contraction channels
+    const int nkb = kdim / T3_BK;
+    const int cols = (a.mode == 0) ? a.Cout : a.Cin;   // channels of the result
+    const int n_nt = cols / BN;
+    const int sshift = (a.s == 2) ? 1 : 0;             // the stride is 1 or 2 (checked on the host)
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4 * T3_EPI_SETS);      // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // TMA producer: the whole warp walks the schedule (all values warp-uniform), one elected lane issues
+        uint32_t st = 0, ph = 0;
+        TileWalker<BN> tw;
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next()) {
+            const TileCoord c = tw.coord();
+            int tap_first = 0, tap_step = 1, ntaps = a.k;
+            if (a.mode == 1) {
+                tap_first = (c.par + a.p) & (a.s - 1);
+                tap_step = a.s;
+                ntaps = (a.k - tap_first + a.s - 1) >> sshift;
+            }
+            for (int ti = 0; ti < ntaps; ++ti) {
+                const int tap = tap_first + ti * tap_step;
+                // first row coordinate (global, pre-stride) along the length axis of A; in the data gradient
+                // par + p - tap is a multiple of the stride by construction, so the arithmetic shift is exact
+                const int rowc = (a.mode == 0) ? (c.m0 * a.s + tap - a.p) : (c.m0 + ((c.par + a.p - tap) >> sshift));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    if (elect_one()) {
+                        uint8_t* sA = tiles + st * S::STAGE_BYTES;
+                        uint8_t* sB = sA + NC * S::A_PLANE;
+                        mbar_expect_tx(&full[st], S::STAGE_BYTES);
+                        tma_load_4d(sA, &mapA, &full[st], kb * T3_BK, rowc, c.b, 0);
+                        tma_load_4d(sB, &mapB, &full[st], kb * T3_BK, c.n0, tap, 0);
+                    }
+                    __syncwarp();
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // MMA issuer: per stage two K = 16 steps x the plane pairs, all into the same fp32 accumulator
+        constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+        // K-major SWIZZLE_64B descriptor: hi = SBO (8 rows x 64 B = 512 B) | version 1 | layout type 4; lo = addr >> 4 | LBO
+        constexpr uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+        using PP = PlanePairs<NC>;
+        uint32_t st = 0, ph = 0;
+        int ti_local = 0;
+        TileWalker<BN> tw;
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next(), ++ti_local) {
+            int ntaps = a.k;
+            if (a.mode == 1) {
+                const int tap_first = (tw.par + a.p) & (a.s - 1);
+                ntaps = (a.k - tap_first + a.s - 1) >> sshift;
+            }
+            const int niter = ntaps * nkb;
+            const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = ((base + st * (uint32_t)S::STAGE_BYTES) >> 4);
+                    const uint32_t sb = sa + (uint32_t)((NC * S::A_PLANE) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < T3_BK / 16; ++ks) {
+#pragma unroll
+                        for (int q = 0; q < PP::N; ++q) {
+                            const uint32_t la = ((sa + (uint32_t)((PP::a(q) * S::A_PLANE) >> 4) + 2u * ks) & 0x3FFFu) | (1u << 16);
+                            const uint32_t lb = ((sb + (uint32_t)((PP::b(q) * S::B_PLANE) >> 4) + 2u * ks) & 0x3FFFu) | (1u << 16);
+                            const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)la;
+                            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)lb;
+                            tc_mma_bf16(tacc, da, db, idesc, (it > 0 || ks > 0 || q > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&empty[st]);      // frees the smem stage once the MMAs have read it
+                }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
+            }
+            if (elect_one()) tc_commit(&tmem_full[acc]);     // accumulator complete
+            __syncwarp();
+        }
+    } else {
+        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (rows of the tile); set (w-2)/4 takes slabs set, set+2, ...
+        const int q = warp & 3;
+        const int eset = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        constexpr int NS = BN / 32;
+        const int rows_out = (a.mode == 0) ? a.Lout : a.L;
+        int ti_local = 0;
+        TileWalker<BN> tw;
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next(), ++ti_local) {
+            const TileCoord c = tw.coord();
+            // output row of this thread: forward l = m0 + row; data gradient j = (m0 + row) * stride + parity
+            const int j = (c.m0 + row) * npar + c.par;
+            const bool valid = j < rows_out;
+            const size_t roff = ((size_t)c.b * rows_out + (valid ? j : 0)) * cols + c.n0;
+            const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int sl = eset; sl < NS; sl += T3_EPI_SETS) {
+                float mk[32];
+                if (AUX) {
+                    const float4* mp = reinterpret_cast<const float4*>(a.aux + roff + sl * 32);
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 m = valid ? __ldg(&mp[g4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        mk[4 * g4 + 0] = m.x; mk[4 * g4 + 1] = m.y; mk[4 * g4 + 2] = m.z; mk[4 * g4 + 3] = m.w;
+                    }
+                }
+                uint32_t v[32];
+                tmem_ld32(tacc + (uint32_t)(sl * 32), v);
+                if (sl + T3_EPI_SETS >= NS) {
+                    // all of this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (a.mode == 0) {
+                    if (a.bias != nullptr) {
+                        const float4* bp = reinterpret_cast<const float4*>(a.bias + c.n0 + sl * 32);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            float4 bv = __ldg(&bp[g4]);
+                            f[4 * g4 + 0] += bv.x; f[4 * g4 + 1] += bv.y; f[4 * g4 + 2] += bv.z; f[4 * g4 + 3] += bv.w;
+                        }
+                    }
+                    act_dispatch(a.act, [&](auto tag) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = act_fwd_t<decltype(tag)::kind>(f[i], a.act_param);
+                    });
+                } else if (AUX) {
+                    act_dispatch(a.act, [&](auto tag) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] *= act_bwd_t<decltype(tag)::kind>(mk[i], a.act_param);
+                    });
+                }
+                if (valid) {
+                    if (a.out != nullptr) {
+                        float4* op = reinterpret_cast<float4*>(a.out + roff + sl * 32);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) op[g4] = make_float4(f[4 * g4], f[4 * g4 + 1], f[4 * g4 + 2], f[4 * g4 + 3]);
+                    }
+                    if (a.planes != nullptr) {
+                        uint32_t pk[3][16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            __nv_bfloat16 p0[3], p1[3];
+                            split3<NC>(f[2 * i], p0);
+                            split3<NC>(f[2 * i + 1], p1);
+#pragma unroll
+                            for (int pl = 0; pl < NC; ++pl) {
+                                __nv_bfloat162 h;
+                                h.x = p0[pl];
+                                h.y = p1[pl];
+                                pk[pl][i] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                        }
+#pragma unroll
+                        for (int pl = 0; pl < NC; ++pl) {
+                            uint4* pp = reinterpret_cast<uint4*>(a.planes + (size_t)pl * a.plane_stride + roff + sl * 32);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) pp[g] = make_uint4(pk[pl][4 * g], pk[pl][4 * g + 1], pk[pl][4 * g + 2], pk[pl][4 * g + 3]);
+                        }
+                    }
+                }
+                if (a.colsum != nullptr) {
+                    // per-channel sums over the 32 rows of this warp: lane i keeps channel i
+                    float mine = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float s = warp_sum(valid ? f[i] : 0.f);
+                        if (lane == i) mine = s;
+                    }
+                    atomicAdd(a.colsum + c.n0 + sl * 32 + lane, mine);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// dW[t, ci, co] (fp32, atomically accumulated; caller zeroes) = sum over (b, l) of X[b, l*s+t-p, ci] * dY[b, l, co]
+// Persistent split-K as conv_tc_wgrad_kernel: work unit = (K chunk, tap, 128 x BN block of (ci, co)), output tile
+// fastest.  K = 32 positions per stage; both operands MN-major SWIZZLE_128B: a 64-channel block of one plane is
+// 32 rows x 128 B = 4 KB, the NC planes of a block arrive with one 4-D TMA load (plane stride 4 KB), blocks are
+// NC * 4 KB apart (= LBO).  The K extent of one accumulator is capped on the host (T3_WG_MAX_ITERS) so that the
+// accumulation error of the fp32 tensor-memory adder stays far below the 1e-4 gradient tolerance.
+struct Tc3WgradArgs {
+    int B, L, Lout, Cin, Cout, k, s, p;
+    int lblocks;        // ceil(Lout / 32)
+    int iters_total;    // B * lblocks
+    int iters_per_chunk;
+    int n_chunks;
+    int n_tiles_n;      // number of N tiles
+    int out_tiles;      // k * m_tiles * n_tiles_n
+    float* dw;          // (k, Cin, Cout) fp32
+};
+
+struct Wg3Unit {
+    int tap, m0, n0, it0, niter;
+};
+template <int BN>
+__device__ __forceinline__ Wg3Unit decode_wg3_unit(int u, const Tc3WgradArgs& a) {
+    Wg3Unit w;
+    const int kc = u / a.out_tiles, t = u - kc * a.out_tiles;
+    w.tap = t % a.k;
+    const int r = t / a.k;
+    const int mt = r / a.n_tiles_n, nt = r - mt * a.n_tiles_n;
+    w.m0 = mt * TC_BM;
+    w.n0 = nt * BN;
+    w.it0 = kc * a.iters_per_chunk;
+    w.niter = min(a.iters_total - w.it0, a.iters_per_chunk);
+    return w;
+}
+
+template <int BN, int NC>
+struct T3WgSmem {
+    static constexpr int BLK = 32 * 128;                       // one 64-channel block of one plane: 32 positions x 128 B
+    static constexpr int A_BYTES = 2 * NC * BLK;               // 128 channels
+    static constexpr int B_BYTES = (BN / 64) * NC * BLK;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES_MAX = T3_SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, int NC, bool SWAP>
+__global__ void __launch_bounds__(T3_WG_THREADS)
+conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                      Tc3WgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = T3WgSmem<BN, NC>;
+    constexpr int STAGES = S::STAGES;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_units = a.out_tiles * a.n_chunks;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapDY);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        uint32_t st = 0, ph = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const Wg3Unit w = decode_wg3_unit<BN>(u, a);
+            int bb = w.it0 / a.lblocks, lb = w.it0 - bb * a.lblocks;
+            for (int i = 0; i < w.niter; ++i) {
+                mbar_wait(&empty[st], ph ^ 1);
+                if (elect_one()) {
+                    const int l0 = lb * 32;
+                    uint8_t* sA = tiles + st * S::STAGE_BYTES;
+                    uint8_t* sB = sA + S::A_BYTES;
+                    mbar_expect_tx(&full[st], S::STAGE_BYTES);
+                    const int xrow = l0 * a.s + w.tap - a.p;     // X position of output position l0 for this tap
+                    if (!SWAP) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) tma_load_4d(sA + h * NC * S::BLK, &mapX, &full[st], w.m0 + h * 64, xrow, bb, 0);
+#pragma unroll
+                        for (int h = 0; h < BN / 64; ++h) tma_load_4d(sB + h * NC * S::BLK, &mapDY, &full[st], w.n0 + h * 64, l0, bb, 0);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) tma_load_4d(sA + h * NC * S::BLK, &mapDY, &full[st], w.m0 + h * 64, l0, bb, 0);
+#pragma unroll
+                        for (int h = 0; h < BN / 64; ++h) tma_load_4d(sB + h * NC * S::BLK, &mapX, &full[st], w.n0 + h * 64, xrow, bb, 0);
+                    }
+                }
+                __syncwarp();
+                if (++lb == a.lblocks) { lb = 0; ++bb; }
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(TC_BM, BN, 1, 1);     // both operands MN-major
+        // MN-major SWIZZLE_128B: 64-element MN blocks LBO = NC * 4 KB apart, 8-row K groups SBO = 1024 B apart,
+        // 16 K rows per instruction = 2048 B
+        constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t lbo = (uint32_t)((NC * S::BLK) >> 4) << 16;
+        using PP = PlanePairs<NC>;
+        uint32_t st = 0, ph = 0;
+        int ul = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+            const Wg3Unit w = decode_wg3_unit<BN>(u, a);
+            const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+            for (int i = 0; i < w.niter; ++i) {
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = ((base + st * (uint32_t)S::STAGE_BYTES) >> 4);
+                    const uint32_t sb = sa + (uint32_t)(S::A_BYTES >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                        for (int q = 0; q < PP::N; ++q) {
+                            const uint32_t la = ((sa + (uint32_t)((PP::a(q) * S::BLK) >> 4) + (2048u >> 4) * ks) & 0x3FFFu) | lbo;
+                            const uint32_t lb = ((sb + (uint32_t)((PP::b(q) * S::BLK) >> 4) + (2048u >> 4) * ks) & 0x3FFFu) | lbo;
+                            const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)la;
+                            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)lb;
+                            tc_mma_bf16(tacc, da, db, idesc, (i > 0 || ks > 0 || q > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&empty[st]);
+                }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
+            }
+            if (elect_one()) tc_commit(&tmem_full[acc]);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int ul = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+            const Wg3Unit w = decode_wg3_unit<BN>(u, a);
+            const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tacc + (uint32_t)c0, v);
+                if (c0 + 32 >= BN) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!SWAP) {
+                    // thread = input channel, 32 consecutive output channels: eight 16-byte vector reductions
+                    float* dst = a.dw + ((size_t)w.tap * a.Cin + (w.m0 + row)) * a.Cout + w.n0 + c0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        red_add_v4_f32(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                       __uint_as_float(v[i + 3]));
+                } else {
+                    // thread = output channel (consecutive across the warp), columns = input channels
+                    float* dst = a.dw + ((size_t)w.tap * a.Cin + (w.n0 + c0)) * a.Cout + w.m0 + row;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * a.Cout, __uint_as_float(v[i]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+// float32 tensor -> NC bf16 planes (plane p at planes + p * n).  Eight elements per thread and step.
+template <int NC>
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes,
+                                                        long long n) {
+    const long long n8 = n >> 3;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += step) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+        const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        uint32_t pk[3][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 p0[3], p1[3];
+            split3<NC>(f[2 * e], p0);
+            split3<NC>(f[2 * e + 1], p1);
+#pragma unroll
+            for (int pl = 0; pl < NC; ++pl) {
+                __nv_bfloat162 h;
+                h.x = p0[pl];
+                h.y = p1[pl];
+                pk[pl][e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+#pragma unroll
+        for (int pl = 0; pl < NC; ++pl)
+            reinterpret_cast<uint4*>(planes + (size_t)pl * n)[i] = make_uint4(pk[pl][0], pk[pl][1], pk[pl][2], pk[pl][3]);
+    }
+    // tail (n % 8 elements)
+    const long long t0 = n8 << 3;
+    for (long long i = t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        __nv_bfloat16 p[3];
+        split3<NC>(x[i], p);
+#pragma unroll
+        for (int pl = 0; pl < NC; ++pl) planes[(size_t)pl * n + i] = p[pl];
+    }
+}
+
+// weights: f32 (k,Cin,Cout) -> planes of the same layout (dgrad B operand) and planes of the transposed layout
+// (k,Cout,Cin) (forward B operand); one 32 x 32 (ci, co) tile of one tap per block, transposed through shared memory
+template <int NC>
+__global__ void __launch_bounds__(256) conv_w_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wk,
+                                                           __nv_bfloat16* __restrict__ wt, int k, int Cin, int Cout) {
+    __shared__ __nv_bfloat16 tile[NC][32][33];
+    const int t = blockIdx.z;
+    const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const size_t plane = (size_t)k * Cin * Cout;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        if (ci < Cin && co < Cout) {
+            const size_t i = ((size_t)t * Cin + ci) * Cout + co;
+            __nv_bfloat16 p[3];
+            split3<NC>(w[i], p);
+#pragma unroll
+            for (int pl = 0; pl < NC; ++pl) {
+                wk[pl * plane + i] = p[pl];
+                tile[pl][r][tx] = p[pl];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        if (ci < Cin && co < Cout) {
+#pragma unroll
+            for (int pl = 0; pl < NC; ++pl) wt[pl * plane + ((size_t)t * Cout + co) * Cin + ci] = tile[pl][tx][r];
+        }
+    }
+}
+
+// 4-D bf16 tensor map over a plane-major tensor (NC, d2, d1, d0): dims (d0 contiguous, d1, d2, NC); box
+// (b0, b1 rows, 1, NC); traversal stride es1 along d1 (box extent b1*es1 in global coordinates -> b1 rows in smem)
+static int make_map4(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, int nc, uint64_t st1,
+                     uint64_t st2, uint64_t st3, uint32_t b0, uint32_t b1, uint32_t es1, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = tc_encode_fn();
+    if (fn == nullptr) return fail(GN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s", "");
+    cuuint64_t dims[4] = {d0, d1, d2, (cuuint64_t)nc};
+    cuuint64_t strides[3] = {st1 * 2, st2 * 2, st3 * 2};
+    cuuint32_t box[4] = {b0, b1 * es1, 1, (cuuint32_t)nc};
+    cuuint32_t estr[4] = {1, es1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GN_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed (%s code %lld)", "", (long long)r);
+    return GN_OK;
+}
+
+template <int BN, int NC, bool AUX>
+static int launch_conv_tc3(const CUtensorMap& mA, const CUtensorMap& mB, const Tc3Args& a, long long total_tiles,
+                           cudaStream_t st) {
+    auto kfn = conv_tc3_kernel<BN, NC, AUX>;
+    constexpr int smem = T3Smem<BN, NC>::TOTAL;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
+    static_assert(T3Smem<BN, NC>::STAGES >= 3, "pipeline too shallow");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const int grid = (int)(total_tiles < (long long)num_sms() ? total_tiles : (long long)num_sms());
+    kfn<<<grid, T3_THREADS, smem, st>>>(mA, mB, a);
+    return cuda_status("conv_tc3_kernel");
+}
+
+template <int NC>
+static int dispatch_conv_tc3(int BN, bool aux, const CUtensorMap& mA, const CUtensorMap& mB, const Tc3Args& a,
+                             long long tiles, cudaStream_t st) {
+    if (!aux) {
+        if (BN == 256) return launch_conv_tc3<256, NC, false>(mA, mB, a, tiles, st);
+        if (BN == 128) return launch_conv_tc3<128, NC, false>(mA, mB, a, tiles, st);
+        return launch_conv_tc3<64, NC, false>(mA, mB, a, tiles, st);
+    }
+    if (BN == 256) return launch_conv_tc3<256, NC, true>(mA, mB, a, tiles, st);
+    if (BN == 128) return launch_conv_tc3<128, NC, true>(mA, mB, a, tiles, st);
+    return launch_conv_tc3<64, NC, true>(mA, mB, a, tiles, st);
+}
+static int pick_bn3(int C) { return (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : 64); }
+
+template <int BN, int NC, bool SWAP>
+static int launch_wgrad_tc3(const CUtensorMap& mX, const CUtensorMap& mDY, const Tc3WgradArgs& a, int grid,
+                            cudaStream_t st) {
+    auto kfn = conv_tc3_wgrad_kernel<BN, NC, SWAP>;
+    constexpr int smem = T3WgSmem<BN, NC>::TOTAL;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
+    static_assert(T3WgSmem<BN, NC>::STAGES >= 3, "pipeline too shallow");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    kfn<<<grid, T3_WG_THREADS, smem, st>>>(mX, mDY, a);
+    return cuda_status("conv_tc3_wgrad_kernel");
+}
+
+template <int NC>
+static int dispatch_wgrad_tc3(int BN, bool swap, const CUtensorMap& mX, const CUtensorMap& mDY, const Tc3WgradArgs& a,
+                              int grid, cudaStream_t st) {
+    if (swap) return launch_wgrad_tc3<64, NC, true>(mX, mDY, a, grid, st);
+    if (BN == 256) return launch_wgrad_tc3<256, NC, false>(mX, mDY, a, grid, st);
+    if (BN == 128) return launch_wgrad_tc3<128, NC, false>(mX, mDY, a, grid, st);
+    return launch_wgrad_tc3<64, NC, false>(mX, mDY, a, grid, st);
+}
+
+// K chunks of the persistent split-K wgrad: minimise waves * (iterations per chunk + fixed cost per unit), with the
+// iterations of one accumulator capped at T3_WG_MAX_ITERS (K = 32 positions each)
+constexpr int T3_WG_MAX_ITERS = 512;
+static int pick_wgrad3_chunks(int out_tiles, int iters_total, int grid) {
+    const int ovh = 8;
+    int lo = (iters_total + T3_WG_MAX_ITERS - 1) / T3_WG_MAX_ITERS, hi = (iters_total + 31) / 32;
+    if (lo < 1) lo = 1;
+    if (hi < lo) hi = lo;
+    if (hi > 8192) hi = 8192;
+    long long best_cost = -1;
+    int best = lo;
+    for (int nk = lo; nk <= hi; ++nk) {
+        const int ipc = (iters_total + nk - 1) / nk;
+        const int nk_eff = (iters_total + ipc - 1) / ipc;
+        const long long units = (long long)out_tiles * nk_eff;
+        const long long waves = (units + grid - 1) / grid;
+        const long long cost = waves * (ipc + ovh);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nk_eff; }
+    }
+    return best;
+}
+
+static int check_tc3_geom(int B, int L, int Cin, int Lout, int Cout, int k, int s, int p, int nc) {
+    GN_REQUIRE(B > 0 && L > 0 && Lout > 0 && k > 0 && k <= 16 && (s == 1 || s == 2) && p >= 0 && p < k, "bad geometry");
+    GN_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tensor-core path needs Cin and Cout to be multiples of 64");
+    GN_REQUIRE(B <= 65535, "batch too large for one launch");
+    GN_REQUIRE(nc >= 1 && nc <= 3, "number of bf16 planes must be 1, 2 or 3");
+    return GN_OK;
+}
+
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" int gn_split_f32_bf16(const float* x, void* planes, long long n, int nc, void* stream) {
+    GN_REQUIRE(x && planes && n >= 0 && nc >= 1 && nc <= 3, "null pointer, n < 0 or planes not in 1..3");
+    GN_REQUIRE(n % 8 == 0 || nc == 1, "element count must be a multiple of 8 (16-byte aligned planes)");
+    if (n == 0) return GN_OK;
+    const long long want = (n / 8 + 255) / 256;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want < 16LL * num_sms() ? want : 16LL * num_sms()));
+    cudaStream_t st = as_stream(stream);
+    if (nc == 3) split_f32_kernel<3><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, n);
+    else if (nc == 2) split_f32_kernel<2><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, n);
+    else split_f32_kernel<1><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, n);
+    return cuda_status("split_f32_kernel");
+}
+
+extern "C" int gn_conv_w_split_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, int nc, void* stream) {
+    GN_REQUIRE(w && wk && wt && k > 0 && Cin > 0 && Cout > 0 && nc >= 1 && nc <= 3, "null pointer or bad size");
+    GN_REQUIRE(k <= 65535 && (Cin + 31) / 32 <= 65535, "weight tensor too large for the split grid");
+    dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32), (unsigned)k);
+    cudaStream_t st = as_stream(stream);
+    if (nc == 3) conv_w_split_kernel<3><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
+    else if (nc == 2) conv_w_split_kernel<2><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
+    else conv_w_split_kernel<1><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
+    return cuda_status("conv_w_split_kernel");
+}
+
+extern "C" int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L,
+                                    int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
+                                    float act_param, int nc, void* stream) {
+    GN_REQUIRE(xs && wts && (y || ys), "null pointer");
+    int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
+    if (rc != GN_OK) return rc;
+    CUtensorMap mA, mB;
+    const int BN = pick_bn3(Cout);
+    // A: X planes viewed as (Cin, L, B, NC); 128 output rows per tile, traversal stride = conv stride
+    rc = make_map4(&mA, xs, Cin, L, B, nc, Cin, (uint64_t)L * Cin, (uint64_t)B * L * Cin, T3_BK, TC_BM, stride,
+                   CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != GN_OK) return rc;
+    // B: Wt planes (NC, k, Cout, Cin) viewed as (Cin, Cout, k, NC)
+    rc = make_map4(&mB, wts, Cin, Cout, k, nc, Cin, (uint64_t)Cout * Cin, (uint64_t)k * Cout * Cin, T3_BK, BN, 1,
+                   CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != GN_OK) return rc;
+    Tc3Args a{};
+    a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
+    a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = y;
+    a.planes = (__nv_bfloat16*)ys; a.plane_stride = (long long)B * Lout * Cout;
+    a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
+    const long long tiles = (long long)B * a.m_tiles * (Cout / BN);
+    cudaStream_t st = as_stream(stream);
+    if (nc == 3) return dispatch_conv_tc3<3>(BN, false, mA, mB, a, tiles, st);
+    if (nc == 2) return dispatch_conv_tc3<2>(BN, false, mA, mB, a, tiles, st);
+    return dispatch_conv_tc3<1>(BN, false, mA, mB, a, tiles, st);
+}
+
+extern "C" int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, float* dx, void* dxs,
+                                      float* dx_colsum, int B, int L, int Cin, int Lout, int Cout, int k, int stride,
+                                      int pad_left, int in_act, float in_act_param, int nc, void* stream) {
+    GN_REQUIRE(dys && wks && (dx || dxs), "null pointer");
+    int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
+    if (rc != GN_OK) return rc;
+    CUtensorMap mA, mB;
+    const int BN = pick_bn3(Cin);
+    // A: dY planes viewed as (Cout, Lout, B, NC), 128 rows, unit traversal stride (parity classes handle the conv stride)
+    rc = make_map4(&mA, dys, Cout, Lout, B, nc, Cout, (uint64_t)Lout * Cout, (uint64_t)B * Lout * Cout, T3_BK, TC_BM, 1,
+                   CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != GN_OK) return rc;
+    // B: W planes (NC, k, Cin, Cout) viewed as (Cout, Cin, k, NC)
+    rc = make_map4(&mB, wks, Cout, Cin, k, nc, Cout, (uint64_t)Cin * Cout, (uint64_t)k * Cin * Cout, T3_BK, BN, 1,
+                   CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != GN_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    Tc3Args a{};
+    a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
+    a.mode = 1; a.act = in_act; a.act_param = in_act_param; a.aux = x_in; a.out = dx;
+    a.planes = (__nv_bfloat16*)dxs; a.plane_stride = (long long)B * L * Cin;
+    a.colsum = dx_colsum;
+    if (dx_colsum != nullptr) cudaMemsetAsync(dx_colsum, 0, sizeof(float) * (size_t)Cin, st);
+    const int rows = (L + stride - 1) / stride;      // rows of the largest parity class
+    a.m_tiles = (rows + TC_BM - 1) / TC_BM;
+    const bool aux = (x_in != nullptr && in_act != GN_ACT_NONE);
+    const long long tiles = (long long)B * stride * a.m_tiles * (Cin / BN);
+    if (nc == 3) return dispatch_conv_tc3<3>(BN, aux, mA, mB, a, tiles, st);
+    if (nc == 2) return dispatch_conv_tc3<2>(BN, aux, mA, mB, a, tiles, st);
+    return dispatch_conv_tc3<1>(BN, aux, mA, mB, a, tiles, st);
+}
+
+extern "C" int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L,
+                                      int Cin, int Lout, int Cout, int k, int stride, int pad_left, int nc, void* stream) {
+    GN_REQUIRE(xs && dys && dw, "null pointer");
+    GN_REQUIRE(db == nullptr || dy != nullptr, "the bias gradient needs the float32 dy");
+    int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
+    if (rc != GN_OK) return rc;
+    GN_REQUIRE(Cin % 128 == 0 || (Cin == 64 && Cout % 128 == 0), "wgrad needs Cin % 128 == 0, or Cin == 64 with Cout % 128 == 0");
+    cudaStream_t st = as_stream(stream);
+    CUtensorMap mX, mDY;
+    // X planes (Cin, L, B, NC): 64 channels x 32 positions (traversal stride = conv stride); dY planes (Cout, Lout, B, NC)
+    rc = make_map4(&mX, xs, Cin, L, B, nc, Cin, (uint64_t)L * Cin, (uint64_t)B * L * Cin, 64, 32, stride,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != GN_OK) return rc;
+    rc = make_map4(&mDY, dys, Cout, Lout, B, nc, Cout, (uint64_t)Lout * Cout, (uint64_t)B * Lout * Cout, 64, 32, 1,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != GN_OK) return rc;
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin * Cout, st);
+    Tc3WgradArgs a{};
+    a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
+    a.lblocks = (Lout + 31) / 32;
+    a.iters_total = B * a.lblocks;
+    a.dw = dw;
+    const bool swap = (Cin == 64);
+    int m_tiles, BN;
+    if (!swap) { m_tiles = Cin / 128; BN = pick_bn3(Cout); a.n_tiles_n = Cout / BN; }
+    else { m_tiles = Cout / 128; BN = 64; a.n_tiles_n = 1; }
+    a.out_tiles = k * m_tiles * a.n_tiles_n;
+    const int nsm = num_sms();
+    int nk = pick_wgrad3_chunks(a.out_tiles, a.iters_total, nsm);
+    a.iters_per_chunk = (a.iters_total + nk - 1) / nk;
+    a.n_chunks = (a.iters_total + a.iters_per_chunk - 1) / a.iters_per_chunk;
+    const long long units = (long long)a.out_tiles * a.n_chunks;
+    const int grid = (int)(units < nsm ? units : nsm);
+    if (nc == 3) rc = dispatch_wgrad_tc3<3>(BN, swap, mX, mDY, a, grid, st);
+    else if (nc == 2) rc = dispatch_wgrad_tc3<2>(BN, swap, mX, mDY, a, grid, st);
+    else rc = dispatch_wgrad_tc3<1>(BN, swap, mX, mDY, a, grid, st);
+    if (rc != GN_OK) return rc;
+    if (db != nullptr) return launch_colsum(dy, (long long)B * Lout, Cout, db, st);
+    return GN_OK;
+}

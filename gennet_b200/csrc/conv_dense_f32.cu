@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
     }
 }
 
-static int launch_colsum(const float* x, long long rows, int C, float* out, cudaStream_t st) {
+int launch_colsum(const float* x, long long rows, int C, float* out, cudaStream_t st) {
     cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, st);
     if (rows <= 0 || C <= 0) return GN_OK;
     int cb = (C + 31) / 32;

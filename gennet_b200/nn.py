@@ -37,10 +37,20 @@ def set_seed(seed):
 
 
 def set_compute_dtype(name):
-    """'float32': exact-parity SIMT path (default).  'bfloat16': activations and conv operands in bf16 with
-    fp32 accumulation on the tcgen05 tensor cores, fp32 master weights / gradients / optimizer."""
-    assert name in ('float32', 'bfloat16')
+    """'float32': every GEMM on the float32 SIMT kernels (default).
+    'bf16x3': float32 activations / weights / gradients as in 'float32', but every Conv1D whose channel counts tile
+    runs on the tcgen05 tensor cores with its operands split into three bf16 planes (six plane products per K step
+    accumulated in fp32 tensor memory: float32-class accuracy, the mode the parity tests and the benchmark headline
+    use).  'bf16x2': two planes, three products (~2^-16 relative).
+    'bfloat16': activations and conv operands in bf16 with fp32 accumulation on the tcgen05 tensor cores, fp32
+    master weights / gradients / optimizer (throughput mode, stated tolerance in tests/test_gpu_models.py)."""
+    assert name in ('float32', 'bfloat16', 'bf16x3', 'bf16x2')
     _STATE['dtype'] = name
+
+
+def _split_planes():
+    """Number of bf16 planes of the split tensor-core mode (0 = not in that mode)."""
+    return {'bf16x3': 3, 'bf16x2': 2}.get(_STATE['dtype'], 0)
 
 
 def compute_dtype():
@@ -82,7 +92,8 @@ def _bias_sink(layer, ctx, features):
     data-gradient kernel can produce it as the per-channel sum of its output (fused activation mask, the
     producer is trainable and ran on the tensor-core path); else (None, 0)."""
     src = layer.bias_src
-    if src is None or layer.in_act is None or id(src) not in ctx.trainable_ids or getattr(src, '_mode', None) != 'tc':
+    if src is None or layer.in_act is None or id(src) not in ctx.trainable_ids or \
+            getattr(src, '_mode', None) not in ('tc', 'tc3'):
         return None, 0
     C = src.filters
     if C % 8 != 0 or features % C != 0:
@@ -96,6 +107,13 @@ def _as_bf16(x):
     y = _empty_bf16(x.shape)
     call('gn_cast_f32_to_bf16', ptr(x.contiguous()), ptr(y, BF16), x.numel(), stream())
     return y
+
+
+def _split(x, nc):
+    """float32 tensor -> (nc,) + shape bf16 planes with x = sum of the planes to float32 accuracy."""
+    planes = _empty_bf16((nc,) + tuple(x.shape))
+    call('gn_split_f32_bf16', ptr(x), ptr(planes, BF16), x.numel(), nc, stream())
+    return planes
 
 
 def _act_bwd(dy, y, code, param):
@@ -332,7 +350,9 @@ class Conv1D(Layer):
         self.post_act = None     # (code, param) of a following activation layer folded into the epilogue
         self.in_act = None       # (code, param) of the fused activation that produced our input
         self.bias_src = None     # the Conv1D that produced our input when in_act is fused (set by _fuse)
+        self.plane_consumer = None   # the Conv1D that alone consumes our (activated) output (set by _fuse)
         self._wcache = None
+        self._wsplit = None
 
     def build(self, in_shape):
         L, cin = in_shape
@@ -353,9 +373,12 @@ class Conv1D(Layer):
     def _path(self):
         L, cin = self.input_shape
         co = self.filters
+        tiles = cin % 64 == 0 and co % 64 == 0 and (cin % 128 == 0 or (cin == 64 and co % 128 == 0))
+        if _split_planes():
+            return 'tc3' if (tiles and self.k <= 8 and self.s <= 2) else 'f32'
         if _STATE['dtype'] != 'bfloat16' or self.k > 8 or self.s > 2:
             return 'f32'
-        if cin % 64 == 0 and co % 64 == 0 and (cin % 128 == 0 or (cin == 64 and co % 128 == 0)):
+        if tiles:
             return 'tc'          # a fused UpSampling1D(2) is materialised in bf16 first (cheap next to the GEMM)
         if self.fused_up != 1:
             return 'f32'
@@ -375,12 +398,94 @@ class Conv1D(Layer):
             self._wcache = (_STATE['wver'], wk, wt)
         return self._wcache[1], self._wcache[2]
 
+    def _split_weights(self, nc):
+        """(wk planes (nc,k,Cin,Cout), wt planes (nc,k,Cout,Cin)) of the split tensor-core mode, per weight version."""
+        if self._wsplit is None or self._wsplit[0] != (_STATE['wver'], nc):
+            L, cin = self.input_shape
+            wk = _empty_bf16((nc, self.k, cin, self.filters))
+            wt = _empty_bf16((nc, self.k, self.filters, cin))
+            call('gn_conv_w_split_bf16', ptr(self.params[0].data), ptr(wk, BF16), ptr(wt, BF16), self.k, cin,
+                 self.filters, nc, stream())
+            self._wsplit = ((_STATE['wver'], nc), wk, wt)
+        return self._wsplit[1], self._wsplit[2]
+
+    def _forward_tc3(self, x, ctx):
+        """Split tensor-core mode: x float32 (with the planes the producer's epilogue already wrote, if any) ->
+        y float32, plus y's planes when the only consumer is another split-mode convolution."""
+        nc = _split_planes()
+        B = x.shape[0]
+        L, cin = self.input_shape
+        code, par = self._act()
+        xs = getattr(x, '_gn_planes', None)
+        x = _as_f32(x).contiguous()
+        if xs is None or xs.shape[0] != nc or self.fused_up != 1:
+            xs = _split(x, nc)
+        if self.fused_up != 1:
+            Lp = L // self.fused_up
+            xu = _empty_bf16((nc, B, L, cin))
+            call('gn_upsample1d_fwd_bf16', ptr(xs, BF16), ptr(xu, BF16), nc * B, Lp, cin, self.fused_up, stream())
+            xs = xu
+        wk, wt = self._split_weights(nc)
+        y = _empty((B, self.Lout, self.filters))
+        cons = self.plane_consumer
+        ys = None
+        if cons is not None and cons.fused_up == 1 and cons._path() == 'tc3':
+            ys = _empty_bf16((nc, B, self.Lout, self.filters))
+        call('gn_conv1d_fwd_bf16x3', ptr(xs, BF16), ptr(wt, BF16), ptr(self.params[1].data), ptr(y),
+             ptr(ys, BF16) if ys is not None else None, B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad,
+             code, par, nc, stream())
+        if ys is not None:
+            y._gn_planes = ys
+        self._xs = xs
+        return x, y
+
+    def _backward_tc3(self, dy, ctx, need_dx, db_done):
+        nc = _split_planes()
+        x, xs = self._x, self._xs
+        B = x.shape[0]
+        L, cin = self.input_shape
+        tr = id(self) in ctx.trainable_ids
+        dys = getattr(dy, '_gn_planes', None)
+        dy = _as_f32(dy).contiguous()
+        if dys is None or dys.shape[0] != nc:
+            dys = _split(dy, nc)
+        if tr:
+            db = None if db_done else ptr(self.params[1].grad)
+            call('gn_conv1d_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), ptr(self.params[0].grad), db, B, L,
+                 cin, self.Lout, self.filters, self.k, self.s, self.pad, nc, stream())
+        dx = None
+        if need_dx:
+            wk, wt = self._split_weights(nc)
+            dx = _empty((B, L, cin))
+            icode, ipar = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
+            sink, _ = _bias_sink(self, ctx, cin)
+            # the producer takes the planes of dx as they are when the activation mask was applied here
+            emit = self.fused_up == 1 and self.in_act is not None and getattr(self.bias_src, '_mode', None) == 'tc3'
+            dxs = _empty_bf16((nc, B, L, cin)) if emit else None
+            xin = x if (self.in_act is not None and self.fused_up == 1) else None
+            call('gn_conv1d_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), ptr(xin) if xin is not None else None, ptr(dx),
+                 ptr(dxs, BF16) if dxs is not None else None, sink if xin is not None else None, B, L, cin, self.Lout,
+                 self.filters, self.k, self.s, self.pad, icode if xin is not None else _lib.ACT_NONE, ipar, nc, stream())
+            if self.fused_up != 1:
+                dxp = _empty((B, L // self.fused_up, cin))
+                call('gn_upsample1d_bwd_f32', ptr(dx), ptr(dxp), B, L // self.fused_up, cin, self.fused_up, stream())
+                dx = dxp
+            else:
+                dx._gn_preact = xin is not None
+                dx._gn_db_done = xin is not None and sink is not None
+                if dxs is not None:
+                    dx._gn_planes = dxs
+        self._x = self._y = self._xs = None
+        return dx
+
     def forward(self, x, ctx):
         B = x.shape[0]
         L, cin = self.input_shape
         code, par = self._act()
         self._mode = self._path()
-        if self._mode == 'tc':
+        if self._mode == 'tc3':
+            x, y = self._forward_tc3(x, ctx)
+        elif self._mode == 'tc':
             x = _as_bf16(x)
             if self.fused_up != 1:
                 xu = _empty_bf16((B, L, cin))
@@ -419,6 +524,8 @@ class Conv1D(Layer):
             dy = _act_bwd(dy.contiguous(), self._y, code, par)
         tr = id(self) in ctx.trainable_ids
         dx = None
+        if self._mode == 'tc3':
+            return self._backward_tc3(dy, ctx, need_dx, db_done)
         if self._mode == 'tc':
             dy = _as_bf16(dy.contiguous())
             if tr:
@@ -487,6 +594,7 @@ class Conv2D(Layer):
         self.padding = padding
         self.post_act = None     # (code, param) of a following activation layer folded into the epilogue
         self._wcache = None
+        self._wsplit = None
 
     def build(self, in_shape):
         H, W, cin = in_shape
@@ -517,9 +625,12 @@ class Conv2D(Layer):
         that tile); 'smallcin': first discriminator layer (2*Cin = 2) on the streaming kernels; else float32 SIMT."""
         H, W, cin = self.input_shape
         c1, c2 = 2 * cin, 2 * self.filters
+        tiles = c1 % 64 == 0 and c2 % 64 == 0 and (c1 % 128 == 0 or (c1 == 64 and c2 % 128 == 0))
+        if _split_planes():
+            return 'tc3' if (tiles and self.kh <= 8 and self.sh <= 2) else 'f32'
         if _STATE['dtype'] != 'bfloat16' or self.kh > 8 or self.sh > 2:
             return 'f32'
-        if c1 % 64 == 0 and c2 % 64 == 0 and (c1 % 128 == 0 or (c1 == 64 and c2 % 128 == 0)):
+        if tiles:
             return 'tc'
         if c1 == 2 and c2 % 128 == 0 and c2 <= 1024 and self.kh <= 5:
             return 'smallcin'
@@ -536,13 +647,33 @@ class Conv2D(Layer):
             self._wcache = (_STATE['wver'], w1, b1, wk, wt)
         return self._wcache[1:]
 
+    def _packed_split(self, nc):
+        """(w1 f32, b1 f32, wk planes, wt planes) of the packed convolution in the split tensor-core mode."""
+        if self._wsplit is None or self._wsplit[0] != (_STATE['wver'], nc):
+            H, W, cin = self.input_shape
+            w1, b1 = self._pack()
+            wk = _empty_bf16((nc,) + tuple(w1.shape))
+            wt = _empty_bf16((nc, self.kh, 2 * self.filters, 2 * cin))
+            call('gn_conv_w_split_bf16', ptr(w1), ptr(wk, BF16), ptr(wt, BF16), self.kh, 2 * cin, 2 * self.filters, nc,
+                 stream())
+            self._wsplit = ((_STATE['wver'], nc), w1, b1, wk, wt)
+        return self._wsplit[1:]
+
     def forward(self, x, ctx):
         B = x.shape[0]
         H, W, cin = self.input_shape
         c1, c2 = 2 * cin, 2 * self.filters
         code, par = self._act()
         self._mode = self._path()
-        if self._mode == 'tc':
+        if self._mode == 'tc3':
+            nc = _split_planes()
+            x = _as_f32(x).contiguous()
+            w1, b1, wk, wt = self._packed_split(nc)
+            self._xs = _split(x, nc)
+            y = _empty((B, self.Lout, 2, self.filters))
+            call('gn_conv1d_fwd_bf16x3', ptr(self._xs, BF16), ptr(wt, BF16), ptr(b1), ptr(y), None, B, H, c1, self.Lout, c2,
+                 self.kh, self.sh, self.pad, code, par, nc, stream())
+        elif self._mode == 'tc':
             x = _as_bf16(x).contiguous()
             w1, b1, wk, wt = self._packed_bf16()
             y = _empty_bf16((B, self.Lout, 2, self.filters))
@@ -577,7 +708,20 @@ class Conv2D(Layer):
             dw1 = _empty(w1.shape)
             db1 = _empty((c2,))
         dx = None
-        if self._mode == 'tc':
+        if self._mode == 'tc3':
+            nc = _split_planes()
+            dy = _as_f32(dy).contiguous()
+            dys = _split(dy, nc)
+            if tr:
+                call('gn_conv1d_wgrad_bf16x3', ptr(self._xs, BF16), ptr(dys, BF16), ptr(dy), ptr(dw1), ptr(db1), B, H, c1,
+                     self.Lout, c2, self.kh, self.sh, self.pad, nc, stream())
+            if need_dx:
+                wk = self._packed_split(nc)[2]
+                dx = _empty(x.shape)
+                call('gn_conv1d_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), None, ptr(dx), None, None, B, H, c1,
+                     self.Lout, c2, self.kh, self.sh, self.pad, _lib.ACT_NONE, 0.0, nc, stream())
+            self._xs = None
+        elif self._mode == 'tc':
             dy = _as_bf16(dy.contiguous())
             if tr:
                 call('gn_conv1d_wgrad_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(dw1), ptr(db1), B, H, c1, self.Lout, c2,
@@ -1241,16 +1385,50 @@ class Model(Layer):
             visit(o)
         assert id(self._in_node) in seen, 'outputs do not depend on the input'
         self._order = [n for n in order if n is not self._in_node and not isinstance(n.layer, InputLayer)]
-        self.layers = []
-        for n in self._order:
-            if n.layer not in self.layers:
-                self.layers.append(n.layer)
+        self.layers = self._keras_layer_order()
         if self.name is None:
             self.name = _uid(self.prefix)
         self.input_shape = ins[0].shape
         self.output_shape = [o.shape for o in outs] if self._multi_out else outs[0].shape
         self.built = True
         self._fuse()
+
+    def _keras_layer_order(self):
+        """``model.layers`` as Keras 2.2.4 orders it (keras/engine/network.py ``_map_graph_network``): by depth from
+        the outputs, deepest first, ties broken by the pre-order index of the traversal that starts at the first
+        output.  ``layer_names`` of a saved file, ``get_weights`` / ``set_weights`` and the optimizer state follow
+        this order, so a two-branch model (bbhMahoGANy.py:357-404, saved at :1173, reloaded at :1135) interleaves its
+        branches exactly as a Keras-written ``signal_pe.h5`` does.  A functional model lists its InputLayer first; a
+        Sequential model does not list it (``Sequential.layers`` of 2.2.4)."""
+        layer_index, finished, post = {}, set(), []
+
+        def build_map(n):
+            if id(n) in finished:
+                return
+            if id(n.layer) not in layer_index:
+                layer_index[id(n.layer)] = len(layer_index)
+            for i in n.inputs:
+                build_map(i)
+            finished.add(id(n))
+            post.append(n)
+        for o in self._out_nodes:
+            build_map(o)
+        node_depth, layer_depth, by_id = {}, {}, {}
+        for n in reversed(post):
+            d = max(node_depth.get(id(n), 0), layer_depth.get(id(n.layer), 0))
+            node_depth[id(n)] = layer_depth[id(n.layer)] = d
+            by_id[id(n.layer)] = n.layer
+            for i in n.inputs:
+                node_depth[id(i)] = max(d + 1, node_depth.get(id(i), 0))
+        top = max(layer_depth.values())
+        for lid, l in by_id.items():
+            if isinstance(l, InputLayer):
+                layer_depth[lid] = top
+        ordered = sorted(by_id, key=lambda lid: (-layer_depth[lid], layer_index[lid]))
+        layers = [by_id[lid] for lid in ordered]
+        if isinstance(self, Sequential):
+            layers = [l for l in layers if not isinstance(l, InputLayer)]
+        return layers
 
     def _fuse(self):
         """UpSampling1D(2) feeding exactly one Conv1D is folded into the convolution's loader."""
@@ -1291,14 +1469,18 @@ class Model(Layer):
             if type(n.layer) in (Conv1D, Dense):
                 src = n.inputs[0]
                 ok = True
+                reshaped = False
                 while ok and src is not self._in_node and (
                         (isinstance(src.layer, _ActLayer) and src.layer.fused) or isinstance(src.layer, Reshape)):
                     ok = len(users.get(id(src), [])) == 1 and src not in self._out_nodes
+                    reshaped = reshaped or isinstance(src.layer, Reshape)
                     src = src.inputs[0]
                 if ok and src is not self._in_node and type(src.layer) is Conv1D and src.layer.post_act is not None \
                         and len(users.get(id(src), [])) == 1:
                     n.layer.in_act = src.layer.post_act
                     n.layer.bias_src = src.layer     # its bias gradient = column sums of our data gradient
+                    if type(n.layer) is Conv1D and not reshaped:
+                        src.layer.plane_consumer = n.layer
 
     # a model can be used as a layer
     def __call__(self, x):

@@ -154,6 +154,30 @@ int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void*
 int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
                          int Cout, int k, int stride, int pad_left, void* stream);
 
+/* ---- tensor-core Conv1D at FLOAT32 accuracy: split-bf16 operands ("bf16x3") -------------------------------
+ * The reference's Conv1D layers compute in float32 (bbhMahoGANy.py:250-292,362-395 through cuDNN/Eigen).  Here a
+ * float32 tensor t is carried as nc bf16 planes, t = t0 + t1 (+ t2) with t0 = bf16(t), t1 = bf16(t - t0), ...,
+ * stored plane-major as (nc, B, L, C), and a product is accumulated in fp32 tensor memory as the sum of the plane
+ * products t_i * w_j with i + j < nc (nc = 3: six tcgen05.mma per K step, float32-class accuracy; nc = 2: three,
+ * ~2^-16; nc = 1 is plain bf16).  Same geometry limits as gn_conv1d_*_bf16.
+ *   gn_split_f32_bf16    : x f32 (n) -> planes bf16 (nc, n);  n % 8 == 0
+ *   gn_conv_w_split_bf16 : w f32 (k,Cin,Cout) -> wk planes (nc,k,Cin,Cout) [dgrad operand], wt planes (nc,k,Cout,Cin) [fwd]
+ *   fwd   : y f32 (B,Lout,Cout) and / or ys planes (nc,B,Lout,Cout) = act(conv(x, w) + bias); either may be NULL
+ *   dgrad : dx f32 (B,L,Cin) and / or dxs planes = act'(x_in) * conv_transpose(dy, w); x_in f32 = this conv's input
+ *           or NULL; dx_colsum f32 (Cin) OVERWRITTEN or NULL (bias gradient of the convolution that produced x_in)
+ *   wgrad : dw f32 (k,Cin,Cout) OVERWRITTEN from the x and dy planes; db f32 (Cout) OVERWRITTEN from the float32 dy
+ *           (NULL: skipped) */
+int gn_split_f32_bf16(const float* x, void* planes, long long n, int nc, void* stream);
+int gn_conv_w_split_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, int nc, void* stream);
+int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L, int Cin,
+                         int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param, int nc,
+                         void* stream);
+int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, float* dx, void* dxs, float* dx_colsum,
+                           int B, int L, int Cin, int Lout, int Cout, int k, int stride, int pad_left, int in_act,
+                           float in_act_param, int nc, void* stream);
+int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L, int Cin,
+                           int Lout, int Cout, int k, int stride, int pad_left, int nc, void* stream);
+
 /* Bandwidth-bound companions of the bf16 path.
  *   smallcin fwd  : first convolution of a network, Cin in {1,2}: x f32 (B,L,Cin) -> y bf16 (B,Lout,Cout), bias+act fused
  *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 5, Cout in {8,16,32,64}

@@ -480,7 +480,11 @@ class BranchModel(Sequential):
     def __init__(self, branches):
         Layer.__init__(self)
         self.branches = branches
-        self.layers = [l for b in branches for l in b]
+        # Keras 2.2.4 `model.layers` (keras/engine/network.py _map_graph_network): by depth from the outputs, deepest
+        # first; ties go to the layer met first by the traversal that starts at the first output, i.e. to the
+        # earlier branch.  get_weights / set_weights / the gradient list follow this order.
+        keyed = [(-(len(b) - 1 - i), bi, l) for bi, b in enumerate(branches) for i, l in enumerate(b)]
+        self.layers = [l for _, _, l in sorted(keyed, key=lambda t: (t[0], t[1]))]
         self.in_shape = self.out_shape = None
 
     def build(self, in_shape, gen=None, dtype=torch.float64):

@@ -210,3 +210,60 @@ def test_posterior_sampling_chain_on_device():
     pc_ = bbh.waveform_percentiles(gen)
     for p in (90, 75, 25, 5):
         assert np.allclose(pc_[p], [np.percentile(gen[:, n, 0], p) for n in range(128)])
+
+
+# ---- split-bf16 tensor-core mode ('bf16x3'): the SAME rtol 1e-4 as the float32 SIMT path ------------------------
+@pytest.fixture
+def bf16x3():
+    from gennet_b200 import nn
+    nn.set_compute_dtype('bf16x3')
+    try:
+        yield nn
+    finally:
+        nn.set_compute_dtype('float32')
+
+
+@pytest.mark.parametrize('n_pix,B', [(256, 8), (2048, 8)])
+def test_pe_step_parity_bf16x3(bf16x3, n_pix, B):
+    """CNN point estimator on the tcgen05 tensor cores with three-plane split operands: predict, losses, every
+    one-step gradient within rtol 1e-4 of the float64 oracle, updated weights -- at the BASELINE n_pix too."""
+    nn = bf16x3
+    prod, orc, x, y = pc.pe_case(n_pix, B)
+    convs = [l for l in prod.all_layers() if isinstance(l, nn.Conv1D)]
+    assert [c._path() for c in convs] == ['f32', 'tc3', 'tc3', 'tc3', 'f32', 'tc3', 'tc3', 'tc3', 'tc3']
+    errs, w0 = pc.compare_step(prod, orc, x, y)
+    pc.compare_weights(prod, orc, w0)
+    print('bf16x3 PE n_pix %d: max gradient error %.2e' % (n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))
+    if n_pix == 256:
+        pc.resync([(prod, orc)])
+        errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)
+        pc.compare_weights(prod, orc, w0)
+
+
+@pytest.mark.parametrize('n_pix,B', [(128, 8), (2048, 8)])
+def test_gan_steps_parity_bf16x3(bf16x3, n_pix, B):
+    nn = bf16x3
+    (g, d, dg), (og, od, ocomp), z, sX, sy = pc.gan_case(n_pix, B)
+    convs = [l for l in g.all_layers() if isinstance(l, nn.Conv1D)]
+    assert [c._path() for c in convs] == ['tc3', 'tc3', 'tc3', 'tc3', 'tc3', 'f32']
+    pc.assert_close(g.predict(z), og.predict(z), 'generator.predict')
+    errs, w0 = pc.compare_step(d, od, sX, sy)
+    pc.compare_weights(d, od, w0)
+    pc.resync([(d, od)])
+    dw = [w.copy() for w in d.get_weights()]
+    errs, w0 = pc.compare_step(dg, ocomp, z, [1] * B, check_predict=False)
+    assert all(np.array_equal(a, b) for a, b in zip(dw, d.get_weights()))
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+    print('bf16x3 GAN n_pix %d: max gradient error %.2e' % (n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))
+
+
+def test_burst_iteration_parity_bf16x3(bf16x3):
+    (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny = pc.burst_case(512, 8)
+    errs, w0 = pc.compare_step(d, od, sX, sy)
+    pc.compare_weights(d, od, w0)
+    pc.resync([(d, od)])
+    errs, w0 = pc.compare_step(sub_g, osub, z, ny, check_predict=False)
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+    pc.resync([(g, og)])
+    errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 8, check_predict=False)
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])

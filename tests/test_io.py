@@ -97,6 +97,16 @@ def test_golden_digest_is_self_consistent():
     assert d['datasets']['optimizer_weights/Adam_1/iterations:0'][1] == 'int64'
 
 
+def gold_names(fname):
+    return json.load(open(GOLDEN))[fname]['layer_names']
+
+
+PE_LAYER_NAMES = ['input_1', 'conv1d_5', 'activation_6', 'conv1d_1', 'conv1d_6', 'activation_1', 'activation_7', 'conv1d_2',
+                  'conv1d_7', 'activation_2', 'activation_8', 'conv1d_3', 'conv1d_8', 'activation_3', 'activation_9',
+                  'conv1d_4', 'conv1d_9', 'activation_4', 'activation_10', 'flatten_1', 'flatten_2', 'dense_1', 'dense_2',
+                  'activation_5', 're_lu_1']
+
+
 def test_save_and_load_weights_roundtrip(fake, tmp_path):
     from gennet_b200 import nn, hdf5
     from tests import parity_cases as pc
@@ -106,8 +116,12 @@ def test_save_and_load_weights_roundtrip(fake, tmp_path):
     f = hdf5.File(p)
     names = [n.decode() for n in f.attrs['layer_names']]
     assert names == [l.name for l in prod.layers]
+    # Keras 2.2.4 orders a functional model's layers by depth from the outputs (network.py _map_graph_network), ties to
+    # the branch of the first output: the two towers of signal_pe_model (bbhMahoGANy.py:357-404) interleave, and
+    # the deeper q tower's first convolution comes before the mc tower's although it was created later
+    assert names == PE_LAYER_NAMES
     assert f.attrs['backend'] == 'tensorflow' and f.attrs['keras_version'] == '2.2.4'
-    conv = [l for l in prod.layers if isinstance(l, nn.Conv1D)][1]
+    conv = [l for l in prod.layers if isinstance(l, nn.Conv1D) and l.params[0].shape == (5, 64, 128)][0]
     assert [n.decode() for n in f[conv.name].attrs['weight_names']] == [conv.name + '/kernel:0', conv.name + '/bias:0']
     k = f[conv.name][conv.name + '/kernel:0'][...]
     assert k.shape == (5, 64, 128) and k.dtype == np.float32                                  # Keras (k, Cin, Cout)
@@ -274,7 +288,9 @@ def test_load_reference_keras_models(fake, fname):
         gio._restore_optimizer(m, f['optimizer_weights'])
         mom = np.asarray(f['optimizer_weights/training/Adam/Variable:0'][...])       # first moment of the conv kernel
         vel = np.asarray(f['optimizer_weights/training/Adam/Variable_6:0'][...])     # its second moment (6 weights)
-        got_m, got_v = gio._param_slots(m, m.optimizer, m.layers[1].params[0])
+        assert [l.name for l in m.layers] == [n for n in gold_names(fname)]       # the file's own layer_names, InputLayer first
+        conv = [l for l in m.layers if type(l).__name__ == 'Conv1D'][0]
+        got_m, got_v = gio._param_slots(m, m.optimizer, conv.params[0])
         assert np.array_equal(got_m, mom) and np.array_equal(got_v, vel) and m.optimizer.iterations == 2532
     orc.set_weights([w.astype(np.float64) for w in m.get_weights()])
     got, ref = m.predict(x), orc.predict(x)
