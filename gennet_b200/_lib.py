@@ -64,7 +64,7 @@ _SIGS = {
     'gn_dense_dgrad_f32': [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_dense_wgrad_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_bn_stats_f32': [c_p, c_ll, c_i, c_p, c_p, c_p],
-    'gn_bn_finalize_f32': [c_p, c_p, c_d, c_i, c_f, c_f, c_p, c_p, c_p, c_i, c_p],
+    'gn_bn_finalize_f32': [c_p, c_p, c_d, c_i, c_f, c_f, c_p, c_p, c_p, c_i, c_p, c_d, c_p],
     'gn_bn_apply_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_i, c_p],
     'gn_bn_bwd_sums_f32': [c_p, c_p, c_p, c_ll, c_i, c_p, c_p],
     'gn_bn_bwd_apply_f32': [c_p, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_ll, c_i, c_p],
@@ -91,6 +91,7 @@ _SIGS = {
     'gn_flip_transpose_f32': [c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_stack_residual_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
     'gn_stack_residual_bwd_f32': [c_p, c_p, c_i, c_i, c_p],
+    'gn_stack_pair_f32': [c_p, c_p, c_p, c_ll, c_p],
     'gn_residual_moments_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
     'gn_residual_moments_bwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_d, c_p],
     'gn_loss_fwd_bwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_i, c_p],
@@ -142,7 +143,7 @@ def require_device():
 
 # launch accounting: every C-ABI call below launches at least one kernel of this library
 COUNTS = {'calls': 0}
-PROFILE = None      # set to a list to record (name, tag, start_event, end_event) per call
+PROFILE = None      # set to a list to record (name, tag, start_event, end_event, args) per call
 
 
 def call(name, *args, tag=None):
@@ -154,7 +155,7 @@ def call(name, *args, tag=None):
         e0.record()
         rc = getattr(load(), name)(*args)
         e1.record()
-        PROFILE.append((name, tag, e0, e1))
+        PROFILE.append((name, tag, e0, e1, args))
     else:
         rc = getattr(load(), name)(*args)
     if rc != 0:

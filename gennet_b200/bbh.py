@@ -150,23 +150,36 @@ def pe_train_step(signal_pe, templates, pars, idx, noise, sigma):
     return signal_pe.train_on_batch(batch.reshape(B, L, 1), [p[:, 0].contiguous(), p[:, 1].contiguous()])
 
 
+_LABELS = {}
+
+
+def _gan_labels(B, dev):
+    """sy = [1]*B + [0]*B (:1289) and the generator step's [1]*B (:1296), resident on the device per batch size."""
+    key = (B, str(dev))
+    if key not in _LABELS:
+        sy = torch.cat([torch.ones(B, device=dev), torch.zeros(B, device=dev)])
+        _LABELS[key] = (sy, torch.ones(B, device=dev))
+    return _LABELS[key]
+
+
 def gan_train_step(generator, signal_discriminator, signal_discriminator_on_generator, noise_signal_dev,
-                   real, z1, real_noise, z2, _noise_d=None, _noise_g=None):
+                   real, z1, real_noise, z2, _noise_d=None, _noise_g=None, _return_device=False):
     """One iteration of the GAN loop, bbhMahoGANy.py:1241-1299, on device-resident inputs:
     real (B, n_pix) templates, z1/z2 (B,100) U(-1,1) latents, real_noise (B, n_pix) N(0,1).
-    Returns (sd_loss, sg_loss) as the reference's [loss, acc] lists."""
+    Returns (sd_loss, sg_loss) as the reference's [loss, acc] lists (device tensors with ``_return_device``: no
+    host synchronisation inside the iteration)."""
     B, L = real.shape
     dev = real.device
     fake = generator.forward(z1, nn.Ctx(False))                              # generator.predict (:1248)
     sX = torch.empty((2 * B, L, 2, 1), dtype=torch.float32, device=dev)
     # real images: stack(template, N(0,1)) (:1276-1284); fake: stack(G(z), noise_signal - G(z)) (:1268-1272)
-    sX[:B, :, 0, 0] = real
-    sX[:B, :, 1, 0] = real_noise
+    call('gn_stack_pair_f32', ptr(real.contiguous()), ptr(real_noise.contiguous()), ptr(sX[:B]), B * L, stream())
     call('gn_stack_residual_fwd_f32', ptr(fake.reshape(B, L).contiguous()), ptr(noise_signal_dev), ptr(sX[B:]), B, L,
          stream())
-    sy = torch.cat([torch.ones(B, device=dev), torch.zeros(B, device=dev)])
-    sd_loss = signal_discriminator.train_on_batch(sX, sy, _noise=_noise_d)           # :1292
-    sg_loss = signal_discriminator_on_generator.train_on_batch(z2, torch.ones(B, device=dev), _noise=_noise_g)  # :1296
+    sy, ones = _gan_labels(B, dev)
+    sd_loss = signal_discriminator.train_on_batch(sX, sy, _noise=_noise_d, _return_device=_return_device)      # :1292
+    sg_loss = signal_discriminator_on_generator.train_on_batch(z2, ones, _noise=_noise_g,
+                                                               _return_device=_return_device)                  # :1296
     return sd_loss, sg_loss
 
 

@@ -5,7 +5,11 @@
 //        x = x0 + x1 + x2,   x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1)       (NC = 3: 24 mantissa bits)
 //   and a product a*b is accumulated in fp32 tensor memory as the sum of the plane products a_i*b_j with i + j < NC
 //   (NC = 3: six tcgen05.mma per K step, dropped terms <= 2^-23 |a||b|; NC = 2: three, <= 2^-15).  Products of bf16
-//   values are exact in fp32, so the result differs from an fp32 FMA chain only by accumulation order.
+//   values are exact in fp32, so the result differs from an fp32 FMA chain only by how the sums are rounded.
+//   The tensor-memory accumulator TRUNCATES on every tcgen05.mma (measured: results biased towards zero by about
+//   0.3 ulp per accumulation), so with NC > 1 a tile keeps TWO accumulators: MAIN takes only the x0*w0 products
+//   (K/16 accumulations), CORR the 2^-8-times-smaller cross products (whose truncation is then negligible); the
+//   epilogue adds them in float32.  Double-buffered that is 4 x BN tensor-memory columns, hence BN <= 128.
 //
 //   Layout: every operand tensor is stored as (NC, B, L, C) bf16 (plane-major).  One 4-D TMA load per operand and
 //   pipeline stage brings the (128 | BN) rows x 32 channels x NC planes box of one tap (SWIZZLE_64B; K = 32 per stage
@@ -128,7 +132,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    constexpr int ACC_COLS = (NC > 1 ? 2 : 1) * BN;      // MAIN [+ CORR] accumulator of one tile
+    // two accumulator buffers (the epilogue of tile i overlaps the MMAs of tile i+1) when they fit the 512 columns;
+    // MAIN + CORR at BN = 256 is single-buffered: chosen on the host only for tiles with >= 80 K steps, where the
+    // exposed epilogue (~7 %) costs less than the second read of the activation tile that BN = 128 needs
+    constexpr int BUFS = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static_assert(BUFS * ACC_COLS <= 512, "tensor memory holds 512 columns");
+    if (warp == 1) tmem_alloc<BUFS * ACC_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,10 +191,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 ntaps = (a.k - tap_first + a.s - 1) >> sshift;
             }
             const int niter = ntaps * nkb;
-            const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
+            const int acc = (BUFS == 2) ? (ti_local & 1) : 0, acc_ph = ((BUFS == 2) ? (ti_local >> 1) : ti_local) & 1;
             mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+            const uint32_t tacc = tmem + (uint32_t)(acc * ACC_COLS);
             for (int it = 0; it < niter; ++it) {
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
@@ -199,7 +209,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             const uint32_t lb = ((sb + (uint32_t)((PP::b(q) * S::B_PLANE) >> 4) + 2u * ks) & 0x3FFFu) | (1u << 16);
                             const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)la;
                             const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)lb;
-                            tc_mma_bf16(tacc, da, db, idesc, (it > 0 || ks > 0 || q > 0) ? 1u : 0u);
+                            if (q == PP::N - 1) tc_mma_bf16(tacc, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);      // MAIN
+                            else tc_mma_bf16(tacc + BN, da, db, idesc, (it > 0 || ks > 0 || q > 0) ? 1u : 0u);       // CORR
                         }
                     }
                     tc_commit(&empty[st]);      // frees the smem stage once the MMAs have read it
@@ -225,10 +236,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int j = (c.m0 + row) * npar + c.par;
             const bool valid = j < rows_out;
             const size_t roff = ((size_t)c.b * rows_out + (valid ? j : 0)) * cols + c.n0;
-            const int acc = ti_local & 1, acc_ph = (ti_local >> 1) & 1;
+            const int acc = (BUFS == 2) ? (ti_local & 1) : 0, acc_ph = ((BUFS == 2) ? (ti_local >> 1) : ti_local) & 1;
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
-            const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t tacc = tmem + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int sl = eset; sl < NS; sl += T3_EPI_SETS) {
                 float mk[32];
@@ -240,17 +251,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         mk[4 * g4 + 0] = m.x; mk[4 * g4 + 1] = m.y; mk[4 * g4 + 2] = m.z; mk[4 * g4 + 3] = m.w;
                     }
                 }
-                uint32_t v[32];
-                tmem_ld32(tacc + (uint32_t)(sl * 32), v);
+                float f[32];
+                {
+                    uint32_t v[32];
+                    tmem_ld32(tacc + (uint32_t)(sl * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (NC > 1) {
+                        tmem_ld32(tacc + (uint32_t)(BN + sl * 32), v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
+                    }
+                }
                 if (sl + T3_EPI_SETS >= NS) {
                     // all of this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                 if (a.mode == 0) {
                     if (a.bias != nullptr) {
                         const float4* bp = reinterpret_cast<const float4*>(a.bias + c.n0 + sl * 32);
@@ -300,14 +318,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                 }
                 if (a.colsum != nullptr) {
-                    // per-channel sums over the 32 rows of this warp: lane i keeps channel i
-                    float mine = 0.f;
+                    // per-channel sums over the 32 rows of this warp by a transposing butterfly (31 shuffles): after
+                    // the step with offset o a lane holds partial sums of the o channels whose bit o matches its own,
+                    // at the end lane l holds the full sum of channel l
+                    if (!valid) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = warp_sum(valid ? f[i] : 0.f);
-                        if (lane == i) mine = s;
+                        for (int i = 0; i < 32; ++i) f[i] = 0.f;
                     }
-                    atomicAdd(a.colsum + c.n0 + sl * 32 + lane, mine);
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float send = up ? f[i] : f[i + o];
+                            const float keep = up ? f[i + o] : f[i];
+                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    atomicAdd(a.colsum + c.n0 + sl * 32 + lane, f[0]);
                 }
             }
         }
@@ -316,7 +344,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<2 * BN>(tmem);
+        tmem_dealloc<BUFS * ACC_COLS>(tmem);
     }
 }
 
@@ -401,7 +429,9 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    constexpr int ACC_COLS = (NC > 1 ? 2 : 1) * BN;      // MAIN [+ CORR] accumulator of one unit
+    static_assert(2 * ACC_COLS <= 512, "tensor memory holds 512 columns");
+    if (warp == 1) tmem_alloc<2 * ACC_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -451,7 +481,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
             mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
             tc_fence_after();
-            const uint32_t tacc = tmem + (uint32_t)(acc * BN);
+            const uint32_t tacc = tmem + (uint32_t)(acc * ACC_COLS);
             for (int i = 0; i < w.niter; ++i) {
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
@@ -466,7 +496,8 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             const uint32_t lb = ((sb + (uint32_t)((PP::b(q) * S::BLK) >> 4) + (2048u >> 4) * ks) & 0x3FFFu) | lbo;
                             const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)la;
                             const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)lb;
-                            tc_mma_bf16(tacc, da, db, idesc, (i > 0 || ks > 0 || q > 0) ? 1u : 0u);
+                            if (q == PP::N - 1) tc_mma_bf16(tacc, da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);        // MAIN
+                            else tc_mma_bf16(tacc + BN, da, db, idesc, (i > 0 || ks > 0 || q > 0) ? 1u : 0u);         // CORR
                         }
                     }
                     tc_commit(&empty[st]);
@@ -486,11 +517,17 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
-            const uint32_t tacc = tmem + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t tacc = tmem + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tacc + (uint32_t)c0, v);
+                if (NC > 1) {
+                    uint32_t vc[32];
+                    tmem_ld32(tacc + (uint32_t)(BN + c0), vc);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vc[i]));
+                }
                 if (c0 + 32 >= BN) {
                     tc_fence_before();
                     __syncwarp();
@@ -516,7 +553,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<2 * BN>(tmem);
+        tmem_dealloc<2 * ACC_COLS>(tmem);
     }
 }
 
@@ -640,7 +677,12 @@ static int dispatch_conv_tc3(int BN, bool aux, const CUtensorMap& mA, const CUte
     if (BN == 128) return launch_conv_tc3<128, NC, true>(mA, mB, a, tiles, st);
     return launch_conv_tc3<64, NC, true>(mA, mB, a, tiles, st);
 }
-static int pick_bn3(int C) { return (C % 256 == 0) ? 256 : ((C % 128 == 0) ? 128 : 64); }
+// widest N tile.  nc > 1: MAIN + CORR accumulators double-buffered need 4 x BN tensor-memory columns, so BN = 256 runs
+// single-buffered and is taken only when a tile has enough K steps (ksteps = taps * K / 16) to hide its epilogue
+static int pick_bn3(int C, int nc, int ksteps) {
+    if (C % 256 == 0 && (nc == 1 || ksteps >= 80)) return 256;
+    return (C % 128 == 0) ? 128 : 64;
+}
 
 template <int BN, int NC, bool SWAP>
 static int launch_wgrad_tc3(const CUtensorMap& mX, const CUtensorMap& mDY, const Tc3WgradArgs& a, int grid,
@@ -662,14 +704,16 @@ template <int NC>
 static int dispatch_wgrad_tc3(int BN, bool swap, const CUtensorMap& mX, const CUtensorMap& mDY, const Tc3WgradArgs& a,
                               int grid, cudaStream_t st) {
     if (swap) return launch_wgrad_tc3<64, NC, true>(mX, mDY, a, grid, st);
-    if (BN == 256) return launch_wgrad_tc3<256, NC, false>(mX, mDY, a, grid, st);
+    if constexpr (NC == 1) {
+        if (BN == 256) return launch_wgrad_tc3<256, NC, false>(mX, mDY, a, grid, st);
+    }
     if (BN == 128) return launch_wgrad_tc3<128, NC, false>(mX, mDY, a, grid, st);
     return launch_wgrad_tc3<64, NC, false>(mX, mDY, a, grid, st);
 }
 
 // K chunks of the persistent split-K wgrad: minimise waves * (iterations per chunk + fixed cost per unit), with the
 // iterations of one accumulator capped at T3_WG_MAX_ITERS (K = 32 positions each)
-constexpr int T3_WG_MAX_ITERS = 512;
+constexpr int T3_WG_MAX_ITERS = 64;      // 2048 positions = 128 truncating accumulations of the MAIN products
 static int pick_wgrad3_chunks(int out_tiles, int iters_total, int grid) {
     const int ovh = 8;
     int lo = (iters_total + T3_WG_MAX_ITERS - 1) / T3_WG_MAX_ITERS, hi = (iters_total + 31) / 32;
@@ -732,7 +776,7 @@ extern "C" int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
     if (rc != GN_OK) return rc;
     CUtensorMap mA, mB;
-    const int BN = pick_bn3(Cout);
+    const int BN = pick_bn3(Cout, nc, k * Cin / 16);
     // A: X planes viewed as (Cin, L, B, NC); 128 output rows per tile, traversal stride = conv stride
     rc = make_map4(&mA, xs, Cin, L, B, nc, Cin, (uint64_t)L * Cin, (uint64_t)B * L * Cin, T3_BK, TC_BM, stride,
                    CU_TENSOR_MAP_SWIZZLE_64B);
@@ -760,7 +804,7 @@ extern "C" int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const fl
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
     if (rc != GN_OK) return rc;
     CUtensorMap mA, mB;
-    const int BN = pick_bn3(Cin);
+    const int BN = pick_bn3(Cin, nc, 0);      // mask, column sums and re-split make this epilogue too long to expose
     // A: dY planes viewed as (Cout, Lout, B, NC), 128 rows, unit traversal stride (parity classes handle the conv stride)
     rc = make_map4(&mA, dys, Cout, Lout, B, nc, Cout, (uint64_t)Lout * Cout, (uint64_t)B * Lout * Cout, T3_BK, TC_BM, 1,
                    CU_TENSOR_MAP_SWIZZLE_64B);
@@ -809,7 +853,7 @@ extern "C" int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const flo
     a.dw = dw;
     const bool swap = (Cin == 64);
     int m_tiles, BN;
-    if (!swap) { m_tiles = Cin / 128; BN = pick_bn3(Cout); a.n_tiles_n = Cout / BN; }
+    if (!swap) { m_tiles = Cin / 128; BN = pick_bn3(Cout, nc, 0); a.n_tiles_n = Cout / BN; }
     else { m_tiles = Cout / 128; BN = 64; a.n_tiles_n = 1; }
     a.out_tiles = k * m_tiles * a.n_tiles_n;
     const int nsm = num_sms();

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sum_x, const double* __restrict__ sum_sq, double n,
                                    int C, float eps, float momentum, float* __restrict__ stats,
-                                   float* __restrict__ moving_mean, float* __restrict__ moving_var, int phase) {
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var, int phase,
+                                   float* __restrict__ biased, double debias) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     if (phase == 0) {
@@ -63,10 +64,22 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum_x, const doubl
     stats[C + c] = (float)(1.0 / sqrt(var + (double)eps));
     if (moving_mean != nullptr) {
         double m = (double)momentum;
-        moving_mean[c] = (float)((double)moving_mean[c] * m + (double)stats[c] * (1.0 - m));
         // Keras 2.2.4 feeds the moving variance the "sample variance" var*n/(n-(1+eps))
         double sv = var * (n / (n - (1.0 + (double)eps)));
-        moving_var[c] = (float)((double)moving_var[c] * m + sv * (1.0 - m));
+        if (biased != nullptr) {
+            // K.moving_average_update of Keras 2.2.4 on TF 1.12 = assign_moving_average(zero_debias=True): the
+            // exponential average runs on a zero-initialised shadow accumulator and the moving statistic is
+            // OVERWRITTEN with accumulator / (1 - momentum^step)
+            const float bm = (float)((double)biased[c] * m + (double)stats[c] * (1.0 - m));
+            const float bv = (float)((double)biased[C + c] * m + sv * (1.0 - m));
+            biased[c] = bm;
+            biased[C + c] = bv;
+            moving_mean[c] = (float)((double)bm * debias);
+            moving_var[c] = (float)((double)bv * debias);
+        } else {
+            moving_mean[c] = (float)((double)moving_mean[c] * m + (double)stats[c] * (1.0 - m));
+            moving_var[c] = (float)((double)moving_var[c] * m + sv * (1.0 - m));
+        }
     }
 }
 
@@ -273,6 +286,10 @@ __global__ void __launch_bounds__(256) stack_residual_fwd_kernel(const float* __
         reinterpret_cast<float2*>(y)[i] = make_float2(v, cst[i % L] - v);
     }
 }
+__global__ void __launch_bounds__(256) stack_pair_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                         float* __restrict__ y, long long n) {
+    GN_EW_LOOP(i, n) { reinterpret_cast<float2*>(y)[i] = make_float2(a[i], b[i]); }
+}
 __global__ void __launch_bounds__(256) stack_residual_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
                                                                  long long n) {
     GN_EW_LOOP(i, n) {
@@ -398,12 +415,12 @@ extern "C" int gn_bn_stats_f32(const float* x, long long rows, int C, double* su
 
 extern "C" int gn_bn_finalize_f32(const double* sum_x, const double* sum_sq, double n_total, int C, float eps,
                                   float momentum, float* stats, float* moving_mean, float* moving_var, int phase,
-                                  void* stream) {
+                                  float* biased, double debias, void* stream) {
     GN_REQUIRE(stats && C > 0 && n_total > 0, "null pointer or bad size");
     GN_REQUIRE(phase == 0 ? sum_x != nullptr : sum_sq != nullptr, "missing sums for this phase");
     GN_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "moving_mean/var must both be given or both NULL");
     bn_finalize_kernel<<<(C + 255) / 256, 256, 0, as_stream(stream)>>>(sum_x, sum_sq, n_total, C, eps, momentum, stats,
-                                                                       moving_mean, moving_var, phase);
+                                                                       moving_mean, moving_var, phase, biased, debias);
     return cuda_status("bn_finalize_kernel");
 }
 
@@ -580,6 +597,12 @@ extern "C" int gn_stack_residual_fwd_f32(const float* x, const float* cst, float
     if (n == 0) return GN_OK;
     stack_residual_fwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, cst, y, L, n);
     return cuda_status("stack_residual_fwd_kernel");
+}
+extern "C" int gn_stack_pair_f32(const float* a, const float* b, float* y, long long n, void* stream) {
+    GN_REQUIRE(a && b && y && n >= 0, "null pointer or n < 0");
+    if (n == 0) return GN_OK;
+    stack_pair_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(a, b, y, n);
+    return cuda_status("stack_pair_kernel");
 }
 extern "C" int gn_stack_residual_bwd_f32(const float* dy, float* dx, int B, int L, void* stream) {
     GN_REQUIRE(dy && dx && B >= 0 && L > 0, "null pointer or bad size");

@@ -29,11 +29,12 @@ struct gn_fft_plan {
     // with the same key write the same values (the caller may not change weights or window while a call that reads them
     // is in flight), so they can share the slot on any number of streams; a slot handed to another key first waits for
     // the event that covers its earlier users.
-    static constexpr int NSLOT = 4;
+    static constexpr int NSLOT = 8;
     float2* coef[NSLOT];
     const void* coef_key[NSLOT];
     const void* coef_win[NSLOT];
     float coef_scale[NSLOT];
+    cudaStream_t coef_stream[NSLOT];     // a slot is only ever re-used AS IS by the stream that filled it
     cudaEvent_t coef_done[NSLOT];
     bool coef_used[NSLOT];
     int coef_next;
@@ -798,14 +799,15 @@ static int whiten_variant() {
 static int coef_acquire(gn_fft_plan* pl, const float* weights, const float* window, float scale, cudaStream_t st) {
     for (int i = 0; i < gn_fft_plan::NSLOT; ++i)
         if (pl->coef_key[i] == (const void*)weights && pl->coef_win[i] == (const void*)window &&
-            pl->coef_scale[i] == scale)
-            return i;
+            pl->coef_scale[i] == scale && pl->coef_stream[i] == st && pl->coef_used[i])
+            return i;      // same stream: the prologue that rewrites the slot is ordered after every earlier use of it
     const int slot = pl->coef_next;
     pl->coef_next = (pl->coef_next + 1) % gn_fft_plan::NSLOT;
     if (pl->coef_used[slot]) cudaStreamWaitEvent(st, pl->coef_done[slot], 0);
     pl->coef_key[slot] = (const void*)weights;
     pl->coef_win[slot] = (const void*)window;
     pl->coef_scale[slot] = scale;
+    pl->coef_stream[slot] = st;
     pl->coef_used[slot] = false;
     return slot;
 }
@@ -1058,6 +1060,7 @@ extern "C" int gn_fft_plan_create(int N, gn_fft_plan** out) {
         p->coef_key[i] = nullptr;
         p->coef_win[i] = nullptr;
         p->coef_scale[i] = 0.f;
+        p->coef_stream[i] = nullptr;
         p->coef_used[i] = false;
         p->coef_done[i] = nullptr;
     }

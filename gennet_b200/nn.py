@@ -22,7 +22,7 @@ from ._lib import call, ptr, stream
 # ----------------------------------------------------------------------------- session state
 _NAME_COUNTS = {}
 _STATE = {'seed': 1234, 'noise_counter': 0, 'init_rng': np.random.RandomState(1234), 'dp': None,
-          'dtype': 'float32', 'wver': 0}
+          'dtype': 'float32', 'wver': 0, 'bn_zero_debias': True}
 
 
 def clear_session():
@@ -51,6 +51,12 @@ def set_compute_dtype(name):
 def _split_planes():
     """Number of bf16 planes of the split tensor-core mode (0 = not in that mode)."""
     return {'bf16x3': 3, 'bf16x2': 2}.get(_STATE['dtype'], 0)
+
+
+def set_bn_zero_debias(flag):
+    """True (default): BatchNormalization moving statistics follow Keras 2.2.4 on TensorFlow 1.12
+    (assign_moving_average(zero_debias=True)); False: plain exponential moving average (tf.keras behaviour)."""
+    _STATE['bn_zero_debias'] = bool(flag)
 
 
 def compute_dtype():
@@ -843,6 +849,29 @@ class BatchNormalization(Layer):
 
     chain = (None, None)      # (activation layer, dropout layer) directly following, set by Model._fuse
 
+    def _finalize(self, ssq, n_total, C, stats, ctx):
+        """1/sqrt(var + eps) of the batch and the moving-statistics update of a training-mode call.  Keras 2.2.4 on
+        TF 1.12 updates them through assign_moving_average(zero_debias=True) (K.moving_average_update): a
+        zero-initialised shadow accumulator per statistic and moving = accumulator / (1 - momentum^step); the shadow
+        state is not a layer weight (it is not saved, as in Keras).  set_bn_zero_debias(False) selects the plain
+        exponential average.  A layer frozen when the running model was compiled does not update (Keras skips the
+        updates of non-trainable layers)."""
+        mm, mv = self.params[2].data, self.params[3].data
+        if id(self) not in ctx.trainable_ids:
+            call('gn_bn_finalize_f32', None, ptr(ssq, torch.float64), n_total, C, self.epsilon, self.momentum, ptr(stats),
+                 None, None, 1, None, 1.0, stream())
+            return
+        biased, debias = None, 1.0
+        if _STATE['bn_zero_debias']:
+            if getattr(self, '_biased', None) is None:
+                self._biased = torch.zeros(2 * C, dtype=torch.float32, device=mm.device)
+                self._local_step = 0
+            self._local_step += 1
+            biased = self._biased
+            debias = 1.0 / (1.0 - self.momentum ** self._local_step)
+        call('gn_bn_finalize_f32', None, ptr(ssq, torch.float64), n_total, C, self.epsilon, self.momentum, ptr(stats),
+             ptr(mm), ptr(mv), 1, ptr(biased) if biased is not None else None, debias, stream())
+
     def _chain_codes(self, ctx):
         act, noise = self.chain
         code, par = (act.code, act.param) if act is not None else (_lib.ACT_NONE, 0.0)
@@ -874,9 +903,8 @@ class BatchNormalization(Layer):
         # centred second moment from the raw one (double): sum (x-mean)^2 = sum x^2 - (sum x)^2 / n
         ssq = (sums[C:] - sums[:C] * sums[:C] / n_total).clamp_(min=0.0).contiguous()
         call('gn_bn_finalize_f32', ptr(sums, torch.float64), None, n_total, C, self.epsilon, self.momentum,
-             ptr(stats), None, None, 0, stream())
-        call('gn_bn_finalize_f32', None, ptr(ssq, torch.float64), n_total, C, self.epsilon, self.momentum,
-             ptr(stats), ptr(mm), ptr(mv), 1, stream())
+             ptr(stats), None, None, 0, None, 1.0, stream())
+        self._finalize(ssq, n_total, C, stats, ctx)
         r, seed, off = None, 0, 0
         if kind >= 0:
             fed = ctx.noise.get(noise.name)
@@ -941,12 +969,11 @@ class BatchNormalization(Layer):
         if ctx.world > 1:
             ctx.dp.all_reduce(sums)
         call('gn_bn_finalize_f32', ptr(sums, torch.float64), None, n_total, C, self.epsilon, self.momentum,
-             ptr(stats), None, None, 0, stream())
+             ptr(stats), None, None, 0, None, 1.0, stream())
         call('gn_bn_stats_f32', ptr(x), rows, C, ptr(sums, torch.float64), ptr(stats), stream())
         if ctx.world > 1:
             ctx.dp.all_reduce(sums)
-        call('gn_bn_finalize_f32', None, ptr(sums[C:], torch.float64), n_total, C, self.epsilon, self.momentum,
-             ptr(stats), ptr(mm), ptr(mv), 1, stream())
+        self._finalize(sums[C:], n_total, C, stats, ctx)
         call('gn_bn_apply_f32', ptr(x), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), ptr(y), rows, C,
              self.epsilon, 0, stream())
         self._x, self._stats, self._n = x, stats, n_total
@@ -1789,13 +1816,23 @@ def _to_device(x):
         return t.to(torch.float32).contiguous()
     a = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
     key = a.shape
-    buf = _PINNED.get(key)
-    if buf is None:
+    slot = _PINNED.get(key)
+    if slot is None:
         if len(_PINNED) > 64:
             _PINNED.clear()
-        buf = torch.empty(a.shape, dtype=torch.float32).pin_memory()
-        _PINNED[key] = buf
-    # the previous async copy out of this staging buffer must have completed
-    torch.cuda.current_stream().synchronize()
+        # two pinned staging buffers per shape, each guarded by the event of the last copy out of it: the host never
+        # waits for the compute stream, only (rarely) for the H2D copy issued two calls ago from the same buffer
+        slot = {'bufs': [torch.empty(a.shape, dtype=torch.float32).pin_memory() for _ in range(2)],
+                'events': [None, None], 'next': 0}
+        _PINNED[key] = slot
+    i = slot['next']
+    slot['next'] = 1 - i
+    if slot['events'][i] is not None:
+        slot['events'][i].synchronize()
+    buf = slot['bufs'][i]
     buf.copy_(torch.from_numpy(a))
-    return buf.to(device(), non_blocking=True)
+    t = buf.to(device(), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    slot['events'][i] = ev
+    return t

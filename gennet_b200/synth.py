@@ -156,6 +156,10 @@ class Synthesizer:
 
     # -- whiten_data(..., 'td') ---------------------------------------------------------------
     def whiten_td(self, x, crop=False, scale=1.0):
+        """whiten_data(..., 'td') (:243-286) of a batch; x: CUDA tensor, or a host array (copied through pinned staging)."""
+        if isinstance(x, np.ndarray) and x.dtype == np.float32:
+            from . import nn
+            x = nn._to_device(x)
         x = _dev(x).reshape(-1, self.N)
         lo, ln = (self.crop_lo, self.crop_len) if crop else (0, self.N)
         y = torch.empty((x.shape[0], ln), dtype=torch.float32, device=x.device)

@@ -237,8 +237,14 @@ int gn_dense_wgrad_f32(const float* x, const float* dy, float* dw, float* db, in
  *   step 0: gn_bn_sums(x) -> sums (2C) = (sum x, sum x^2 about `shift`)  ... see gn_bn_* below. */
 int gn_bn_stats_f32(const float* x, long long rows, int C, double* sums /* (2C): sum(x), sum((x-shift)^2) */,
                     const float* shift /* (C) or NULL */, void* stream);
+/* phase 0: stats[0:C] = sum_x / n.  phase 1: stats[C:2C] = 1/sqrt(sum_sq/n + eps) and, when moving_mean / moving_var
+ * are given, their update.  biased == NULL: plain exponential average moving = moving*m + batch*(1-m).
+ * biased != NULL (f32 (2C), zero-initialised by the caller, one per layer): the zero-debiased average Keras 2.2.4
+ * gets from TF 1.12 (K.moving_average_update -> assign_moving_average(zero_debias=True)):
+ * biased = biased*m + batch*(1-m); moving = biased * debias with debias = 1/(1 - m^step), step counted by the caller. */
 int gn_bn_finalize_f32(const double* sum_x, const double* sum_sq, double n_total, int C, float eps, float momentum,
-                       float* stats, float* moving_mean, float* moving_var, int phase, void* stream);
+                       float* stats, float* moving_mean, float* moving_var, int phase, float* biased, double debias,
+                       void* stream);
 int gn_bn_apply_f32(const float* x, const float* mean, const float* invstd_or_var, const float* gamma,
                     const float* beta, float* y, long long rows, int C, float eps, int use_var, void* stream);
 /* backward sums: sums (2C) double = (sum dy, sum dy*xhat) with xhat=(x-mean)*invstd */
@@ -316,6 +322,8 @@ int gn_maxnorm_roll_f32(const float* x, const int* offsets, float* y, int B, int
 /* MyLayer, bbhMahoGANy.py:164-188: y (B,L,2) = stack([x, const - x], axis=2); bwd dx = dy[...,0]-dy[...,1] */
 int gn_stack_residual_fwd_f32(const float* x, const float* cst, float* y, int B, int L, void* stream);
 int gn_stack_residual_bwd_f32(const float* dy, float* dx, int B, int L, void* stream);
+/* real images of the GAN loop, bbhMahoGANy.py:1276-1284: y (n,2) = concatenate((signal, noise), axis=2) */
+int gn_stack_pair_f32(const float* a, const float* b, float* y, long long n, void* stream);
 /* MyLayer, tests/burstMahoGANy.py:100-125: out (2) = [mean(c-x), mean((c-x)^2)] over the whole batch;
  * sums (2) double workspace = un-normalised sums (for data-parallel all-reduce) */
 int gn_residual_moments_fwd_f32(const float* x, const float* cst, double* sums, int B, int L, void* stream);

@@ -148,6 +148,9 @@ class Conv2DTranspose(Layer):
         return apply_activation(y.permute(0, 2, 3, 1), self.activation, _kink(noise, self))
 
 
+ZERO_DEBIAS = True      # Keras 2.2.4 + TF 1.12 moving averages (see BatchNormalization.forward); False = plain EMA
+
+
 class BatchNormalization(Layer):
     """[A5] eps 1e-3, axis -1, batch mean + biased var in training, moving stats in
     inference; moving_var is fed the n/(n-(1+eps)) 'sample variance'."""
@@ -156,6 +159,8 @@ class BatchNormalization(Layer):
     def __init__(self, momentum=0.99, epsilon=1e-3):
         super().__init__()
         self.momentum, self.epsilon = momentum, epsilon
+        self.biased = None          # shadow accumulators of the zero-debiased moving average (not layer weights)
+        self.local_step = 0
 
     def build(self, in_shape, gen, dtype):
         c = in_shape[-1]
@@ -172,14 +177,32 @@ class BatchNormalization(Layer):
             n = x.numel() / x.shape[-1]
             with torch.no_grad():
                 m = self.momentum
-                self.state[0] = self.state[0] * m + mean.detach() * (1 - m)
-                self.state[1] = self.state[1] * m + var.detach() * (n / (n - (1.0 + self.epsilon))) * (1 - m)
+                sv = var.detach() * (n / (n - (1.0 + self.epsilon)))
+                upd = noise.get('__updates__') if isinstance(noise, dict) else None
+                if upd is not None and id(self) not in upd:
+                    pass            # Keras: a layer that was non-trainable for this compiled model contributes no updates
+                elif ZERO_DEBIAS:
+                    # K.moving_average_update (keras/backend/tensorflow_backend.py, 2.2.4) ->
+                    # tf.python.training.moving_averages.assign_moving_average(x, value, momentum, zero_debias=True)
+                    # (TF 1.12 _zero_debias): biased -= (biased - value)*(1-m); local_step += 1;
+                    # x -= x - biased / (1 - m**local_step), i.e. x is overwritten with the debiased average
+                    if self.biased is None:
+                        self.biased = [torch.zeros_like(self.state[0]), torch.zeros_like(self.state[1])]
+                        self.local_step = 0
+                    self.biased[0] = self.biased[0] * m + mean.detach() * (1 - m)
+                    self.biased[1] = self.biased[1] * m + sv * (1 - m)
+                    self.local_step += 1
+                    self.state[0] = self.biased[0] / (1 - m ** self.local_step)
+                    self.state[1] = self.biased[1] / (1 - m ** self.local_step)
+                else:
+                    self.state[0] = self.state[0] * m + mean.detach() * (1 - m)
+                    self.state[1] = self.state[1] * m + sv * (1 - m)
         else:
             mean, var = self.state
         return (x - mean) / torch.sqrt(var + self.epsilon) * g + b
 
 
-KINK_TOL = 2e-6
+KINK_TOL = 1e-5      # of the tensor's scale: the forward tolerance of a float32-class implementation
 
 
 def _fed_mask(x, own, ykink, cond):
@@ -370,7 +393,22 @@ class MaxPooling1D(Layer):
         return (in_shape[0] // self.p, in_shape[1])
 
     def forward(self, x, training, noise):
-        return F.max_pool1d(x.permute(0, 2, 1), self.p).permute(0, 2, 1)
+        ykink = _kink(noise, self)
+        if ykink is None:
+            return F.max_pool1d(x.permute(0, 2, 1), self.p).permute(0, 2, 1)
+        # Like a ReLU kink, a near-tie inside a pooling window is a discontinuity of the gradient: the window element
+        # the implementation under test selected (identified by its pooled OUTPUT, fed in) is differentiated here too --
+        # but only where it is within KINK_TOL (of the tensor's scale) of the true maximum; anything else raises.
+        B, L, C = x.shape
+        n = L // self.p
+        win = x[:, :n * self.p].reshape(B, n, self.p, C)
+        fed_y = torch.as_tensor(np.asarray(ykink)).to(x.dtype).reshape(B, n, 1, C)
+        idx = (win.detach() - fed_y).abs().argmin(dim=2, keepdim=True)
+        chosen = torch.gather(win, 2, idx).squeeze(2)
+        gap = float((win.detach().max(dim=2).values - chosen.detach()).max())
+        lim = KINK_TOL * max(float(x.detach().abs().max()), 1e-30)
+        assert gap <= lim, 'pooling selection disagrees with the oracle away from a tie (gap %g > %g)' % (gap, lim)
+        return chosen
 
 
 class StackResidual(Layer):
@@ -628,6 +666,7 @@ def _compile(model, loss, optimizer):
     model.optimizer = optimizer
     # trainable set is frozen at compile time [A11]
     model.collected = [w for l in model.all_layers() if l.trainable for w in l.weights]
+    model.update_ids = set(id(l) for l in model.all_layers() if l.trainable)
 
 
 def _labels(y, like):
@@ -638,7 +677,8 @@ def _labels(y, like):
 
 
 def _train_on_batch(model, x, y, noise=None):
-    noise = {} if noise is None else noise
+    noise = dict({} if noise is None else noise)
+    noise['__updates__'] = model.update_ids
     out = model.forward(_t(x, model), True, noise)
     outs = out if isinstance(out, list) else [out]
     ys = y if isinstance(out, list) else [y]

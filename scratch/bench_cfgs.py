@@ -17,7 +17,7 @@ def breakdown(f):
     f(); torch.cuda.synchronize()
     prof, _lib.PROFILE = _lib.PROFILE, None
     tot = {}
-    for name, tag, a, b in prof:
+    for name, tag, a, b, _args in prof:
         d = tot.setdefault(name, [0.0, 0]); d[0] += a.elapsed_time(b); d[1] += 1
     return ', '.join('%s x%d %.2f' % (k.replace('gn_', ''), v[1], v[0]) for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:6])
 for mode in ('float32', 'bfloat16'):

@@ -32,7 +32,7 @@ bbh.gan_train_step(G, D, DG, ns, real, z1, rn, z2)
 torch.cuda.synchronize()
 prof, _lib.PROFILE = _lib.PROFILE, None
 tot = {}
-for name, tag, a, b in prof:
+for name, tag, a, b, _args in prof:
     d = tot.setdefault(name, [0.0, 0]); d[0] += a.elapsed_time(b); d[1] += 1
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:25]:
     print('  %-34s n=%3d %8.3f ms' % (k, v[1], v[0]))

@@ -19,7 +19,7 @@ e0.record(); pe.train_on_batch(x, y, _return_device=True); e1.record()
 torch.cuda.synchronize()
 prof, _lib.PROFILE = _lib.PROFILE, None
 tot = 0
-for name, tag, a, b in prof:
+for name, tag, a, b, _args in prof:
     t = a.elapsed_time(b); tot += t
     print('%-34s %8.3f ms  %s' % (name, t, tag or ''))
 print('sum of launches %.3f ms; step wall (events) %.3f ms; %d launches' % (tot, e0.elapsed_time(e1), len(prof)))

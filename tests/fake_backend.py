@@ -144,13 +144,18 @@ class Fake:
         sh = shift[:C].double() if shift is not None else 0.0
         sums[C:] = ((xv - sh) ** 2).sum(0)
 
-    def gn_bn_finalize_f32(self, sum_x, sum_sq, n, C, eps, mom, stats, mm, mv, phase, st):
+    def gn_bn_finalize_f32(self, sum_x, sum_sq, n, C, eps, mom, stats, mm, mv, phase, biased, debias, st):
         if phase == 0:
             stats[:C] = (sum_x[:C] / n).float()
             return
         var = sum_sq[:C] / n
         stats[C:2 * C] = (1.0 / torch.sqrt(var + eps)).float()
-        if mm is not None:
+        if mm is not None and biased is not None:
+            biased[:C] = (biased[:C].double() * mom + stats[:C].double() * (1 - mom)).float()
+            biased[C:2 * C] = (biased[C:2 * C].double() * mom + var * (n / (n - (1.0 + eps))) * (1 - mom)).float()
+            mm.copy_((biased[:C].double() * debias).float())
+            mv.copy_((biased[C:2 * C].double() * debias).float())
+        elif mm is not None:
             mm.copy_((mm.double() * mom + stats[:C].double() * (1 - mom)).float())
             mv.copy_((mv.double() * mom + var * (n / (n - (1.0 + eps))) * (1 - mom)).float())
 

@@ -1,5 +1,5 @@
 """The bench line committed from the last GPU run of the round carries every key of the measurement contract (this is
-a schema check of profiles/r*_bench_bf16_final.json, not a performance assertion), and bench.py parses its flags."""
+a schema check of the newest profiles/r*_bench_final.json, not a performance assertion), and bench.py parses its flags."""
 import glob
 import json
 import os
@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _line():
-    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_bench_bf16_final.json')))
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_bench_final.json'))) or \
+        sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_bench_bf16_final.json')))
     assert files, 'no committed bench line'
     return json.loads(open(files[-1]).read().strip().splitlines()[-1])
 
@@ -41,6 +42,6 @@ def test_bench_cli_flags():
     import importlib.util
     spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
     src = open(os.path.join(ROOT, 'bench.py')).read()
-    for flag in ('--gpus', '--steps', '--warmup', '--impl'):
+    for flag in ('--gpus', '--steps', '--warmup', '--impl', '--config', '--mode', '--check'):
         assert flag in src
     assert spec is not None

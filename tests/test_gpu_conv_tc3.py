@@ -1,7 +1,9 @@
 """GPU parity of the split-bf16 tcgen05 Conv1D kernels (conv1d_tc3.cu) against float64 math on the SAME float32
 inputs.  With three planes the kernel is a float32-class convolution (six bf16 plane products per K step, exact in
-the fp32 accumulator): tolerance 2e-6 of the tensor scale at test size and 2e-5 at BASELINE size (K up to 5 * 1024
-forward, 512 * 2040 positions in the weight gradient), far inside north_star's rtol 1e-4.  Two planes: 1e-4."""
+the fp32 accumulator; the accumulator itself truncates, ~0.3 ulp per tcgen05.mma, which is why the kernel keeps the
+large x0*w0 products in their own accumulator): tolerance 6e-6 of the tensor scale at test size and 1e-5 at BASELINE
+size (K up to 5 * 512 forward, 64 * 507 positions in the weight gradient), far inside north_star's rtol 1e-4.
+Two planes: 1e-4."""
 import math
 
 import numpy as np
@@ -26,7 +28,7 @@ CASES = [
     (300, 600, 64, 128, 5, 1, 'valid'),   # many tiles per persistent CTA
     (96, 515, 256, 512, 5, 2, 'same'),    # two n-tiles forward, two parity classes in the data gradient
 ]
-TOL = {3: 2e-6, 2: 1e-4, 1: 2 ** -7}
+TOL = {3: 6e-6, 2: 1e-4, 1: 2 ** -7}
 
 
 def dev(a):
@@ -126,7 +128,7 @@ def test_tc3_conv_fwd_dgrad_wgrad(case, nc):
 def test_tc3_accuracy_at_baseline_size(capsys):
     """Largest layer of the CNN point estimator at BASELINE batch (conv 512 -> 1024, k 5, stride 2, 64 of the 512
     samples): forward K = 2560, weight gradient over 64 * 507 positions per accumulator chunk.  Reports the observed
-    errors (the evidence for the accumulation behaviour of the fp32 tensor-memory adder) and bounds them at 2e-5."""
+    errors (the evidence for the accumulation behaviour of the fp32 tensor-memory adder) and bounds them at 1e-5."""
     from gennet_b200 import _lib as L_
     B, L, Cin, Cout, k, s, nc = 64, 1018, 512, 1024, 5, 2, 3
     rs = np.random.RandomState(5)
@@ -167,4 +169,4 @@ def test_tc3_accuracy_at_baseline_size(capsys):
          'fwd_simt_f32': err(y32, yr.detach()), 'wgrad_simt_f32': err(dw32, wr.grad)}
     with capsys.disabled():
         print('\n[tc3 accuracy, conv 512->1024 k5 s2, B=64] ' + ' '.join('%s=%.2e' % kv for kv in e.items()))
-    assert e['fwd'] <= 2e-5 and e['dgrad'] <= 2e-5 and e['wgrad'] <= 2e-5, e
+    assert e['fwd'] <= 1e-5 and e['dgrad'] <= 1e-5 and e['wgrad'] <= 1e-5, e

@@ -110,7 +110,7 @@ def test_pe_step_bf16_within_stated_tolerance():
             assert np.isfinite(a).all() and el2 <= 1e-1 and emax <= 3e-1, (i, b.shape, el2, emax)
         # the tensor-core kernels were really used
         convs = [l for l in prod.all_layers() if isinstance(l, nn.Conv1D)]
-        assert [c._path() for c in convs] == ['smallcin', 'tc', 'tc', 'tc', 'smallcin', 'tc', 'tc', 'tc', 'tc']
+        assert sorted(c._path() for c in convs) == ['smallcin'] * 2 + ['tc'] * 7
     finally:
         nn.set_compute_dtype('float32')
 
@@ -230,7 +230,7 @@ def test_pe_step_parity_bf16x3(bf16x3, n_pix, B):
     nn = bf16x3
     prod, orc, x, y = pc.pe_case(n_pix, B)
     convs = [l for l in prod.all_layers() if isinstance(l, nn.Conv1D)]
-    assert [c._path() for c in convs] == ['f32', 'tc3', 'tc3', 'tc3', 'f32', 'tc3', 'tc3', 'tc3', 'tc3']
+    assert sorted(c._path() for c in convs) == ['f32'] * 2 + ['tc3'] * 7
     errs, w0 = pc.compare_step(prod, orc, x, y)
     pc.compare_weights(prod, orc, w0)
     print('bf16x3 PE n_pix %d: max gradient error %.2e' % (n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))

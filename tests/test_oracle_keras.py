@@ -37,10 +37,27 @@ def test_bn_train_and_moving_update():
     assert torch.allclose(y.reshape(-1, 3).mean(0), torch.zeros(3, dtype=torch.float64), atol=1e-12)
     n = 20.0
     var_b = flat.var(0, unbiased=False)
-    assert torch.allclose(bn.state[0], 0.1 * flat.mean(0))
-    assert torch.allclose(bn.state[1], 0.9 + 0.1 * var_b * n / (n - 1.001))
+    # Keras 2.2.4 on TF 1.12: zero-debiased moving average -- after the first update the moving statistics ARE the
+    # batch statistics (the initial 0 / 1 are discarded), after the second the debiased mix of the two batches
+    assert torch.allclose(bn.state[0], flat.mean(0))
+    assert torch.allclose(bn.state[1], var_b * n / (n - 1.001))
+    x2 = torch.randn(5, 4, 3, dtype=torch.float64) + 1.0
+    bn.forward(x2, True, {})
+    f2 = x2.reshape(-1, 3)
+    want = (0.9 * 0.1 * flat.mean(0) + 0.1 * f2.mean(0)) / (1 - 0.9 ** 2)
+    assert torch.allclose(bn.state[0], want)
     y2 = bn.forward(x, False, {})
     assert torch.allclose(y2, (x - bn.state[0]) / torch.sqrt(bn.state[1] + 1e-3))
+    # plain exponential average (tf.keras / zero_debias=False)
+    try:
+        ko.ZERO_DEBIAS = False
+        bn = ko.BatchNormalization(momentum=0.9)
+        bn.build((4, 3), None, torch.float64)
+        bn.forward(x, True, {})
+        assert torch.allclose(bn.state[0], 0.1 * flat.mean(0))
+        assert torch.allclose(bn.state[1], 0.9 + 0.1 * var_b * n / (n - 1.001))
+    finally:
+        ko.ZERO_DEBIAS = True
 
 
 def test_adam_first_step_closed_form():
