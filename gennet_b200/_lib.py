@@ -52,6 +52,15 @@ _SIGS = {
     'gn_conv1d_cout1_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_cout1_dgrad_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_cout1_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_smallcin_fwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_conv1d_smallcin_wgrad_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_smallcin_dgrad_f32': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_cout1_fwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_cout1_dgrad_f32': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_conv1d_cout1_wgrad_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_dense_small_fwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_dense_small_dgrad_f32': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_dense_small_wgrad_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_upsample1d_fwd_bf16': [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_upsample1d_bwd_bf16': [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_dense_small_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
@@ -72,6 +81,10 @@ _SIGS = {
     'gn_chain_fwd_bf16': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p],
     'gn_chain_bwd_sums_bf16': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p, c_p],
     'gn_chain_bwd_bf16': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_p, c_p, c_ll, c_i, c_p],
+    'gn_bn_sums_f32': [c_p, c_ll, c_i, c_p, c_p],
+    'gn_chain_fwd_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p],
+    'gn_chain_bwd_sums_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p, c_p],
+    'gn_chain_bwd_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_p, c_p, c_ll, c_i, c_p],
     'gn_act_fwd_f32': [c_p, c_p, c_ll, c_i, c_f, c_p],
     'gn_act_bwd_f32': [c_p, c_p, c_p, c_ll, c_i, c_f, c_p],
     'gn_noise_fwd_f32': [c_p, c_p, c_p, c_ll, c_i, c_f, c_p],

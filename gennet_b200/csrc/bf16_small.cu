@@ -1,4 +1,4 @@
-// Bandwidth-bound companions of the tensor-core path (bf16 activations): the first convolution of every
+// Bandwidth-bound companions of the tensor-core path: the first convolution of every
 // network (Cin = 1 or 2: K = 5..10, no GEMM worth the name) and the Dense heads with <= 4 outputs over the
 // flattened feature map (a GEMV over up to 519 168 features).  HBM-bound streaming kernels: 128-bit accesses,
 // warp-shuffle reductions, one pass over the big operand.
@@ -10,12 +10,60 @@
 
 namespace gn {
 
+// The big operand of every kernel here (the activation / gradient tensor that is streamed once) is bf16 in the bf16
+// throughput mode and float32 in the split-operand ("bf16x3") mode, whose activations stay float32: the kernels are
+// templates over that element type and touch it eight elements at a time (one 128-bit access for bf16, two for float).
+template <typename T> struct Act8;
+template <> struct Act8<__nv_bfloat16> {
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[2 * e] = f.x;
+            v[2 * e + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) { unpack(ldraw(p), v); }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+    }
+    static __device__ __forceinline__ float round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }   // as stored
+    static __device__ __forceinline__ float get(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+};
+template <> struct Act8<float> {
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw ldraw(const float* p) {
+        Raw r;
+        r.a = __ldg(reinterpret_cast<const float4*>(p));
+        r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        return r;
+    }
+    static __device__ __forceinline__ Raw zero() { Raw r; r.a = r.b = make_float4(0.f, 0.f, 0.f, 0.f); return r; }
+    static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+        v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+    }
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) { unpack(ldraw(p), v); }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    static __device__ __forceinline__ float round(float x) { return x; }
+    static __device__ __forceinline__ float get(const float* p) { return *p; }
+};
+
 // ---- first-layer convolution: x f32 (B,L,CIN), w f32 (k,CIN,Cout) -> y bf16 (B,Lout,Cout), fused bias + act ----
 // thread = (row, 8 consecutive output channels); weights (<= 16*2*256 floats) live in shared memory
-template <int CIN>
+template <int CIN, typename T>
 __global__ void __launch_bounds__(256) conv_smallcin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias,
-                                                                __nv_bfloat16* __restrict__ y, int B, int L, int Lout,
+                                                                T* __restrict__ y, int B, int L, int Lout,
                                                                 int Cout, int k, int s, int p, int act, float ap) {
     extern __shared__ float sw[];     // k*CIN*Cout weights then Cout bias
     const int nw = k * CIN * Cout;
@@ -45,21 +93,19 @@ __global__ void __launch_bounds__(256) conv_smallcin_fwd_kernel(const float* __r
                 acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
             }
         }
-        __nv_bfloat162 h[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            h[j] = __floats2bfloat162_rn(act_fwd(acc[2 * j], act, ap), act_fwd(acc[2 * j + 1], act, ap));
-        *reinterpret_cast<uint4*>(y + (size_t)row * Cout + g * 8) = *reinterpret_cast<uint4*>(h);
+        for (int j = 0; j < 8; ++j) acc[j] = act_fwd(acc[j], act, ap);
+        Act8<T>::store(y + (size_t)row * Cout + g * 8, acc);
     }
 }
 
 // Register-resident variant for k <= 5: a thread keeps the k*CIN*8 weights and 8 biases of its channel group in
 // registers and walks a run of consecutive output rows of one sample, so a row costs its k*CIN input loads, the FMAs,
 // the (compile-time) activation and one 128-bit store -- no shared-memory weight reads and no per-row index division.
-template <int CIN, int KMAX, int KIND>
+template <int CIN, int KMAX, int KIND, typename T>
 __global__ void __launch_bounds__(256) conv_smallcin_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                     const float* __restrict__ bias,
-                                                                    __nv_bfloat16* __restrict__ y, int B, int L, int Lout,
+                                                                    T* __restrict__ y, int B, int L, int Lout,
                                                                     int Cout, int k, int s, int p, float ap, int gpb, int run,
                                                                     int runs_per_sample, long long n_runs) {
     const int g = blockIdx.y * gpb + threadIdx.x % gpb;          // channel group (8 channels)
@@ -77,7 +123,7 @@ __global__ void __launch_bounds__(256) conv_smallcin_fwd_reg_kernel(const float*
         const int b = (int)fast_div(r, runs_per_sample, ri);
         const int l0 = ri * run, l1 = min(Lout, l0 + run);
         const float* __restrict__ xb = x + (size_t)b * L * CIN;
-        __nv_bfloat16* __restrict__ yb = y + ((size_t)b * Lout) * Cout + g * 8;
+        T* __restrict__ yb = y + ((size_t)b * Lout) * Cout + g * 8;
         for (int l = l0; l < l1; ++l) {
             float acc[8];
 #pragma unroll
@@ -94,20 +140,18 @@ __global__ void __launch_bounds__(256) conv_smallcin_fwd_reg_kernel(const float*
                     }
                 }
             }
-            __nv_bfloat162 h[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                h[j] = __floats2bfloat162_rn(act_fwd_t<KIND>(acc[2 * j], ap), act_fwd_t<KIND>(acc[2 * j + 1], ap));
-            *reinterpret_cast<uint4*>(yb + (size_t)l * Cout) = *reinterpret_cast<uint4*>(h);
+            for (int j = 0; j < 8; ++j) acc[j] = act_fwd_t<KIND>(acc[j], ap);
+            Act8<T>::store(yb + (size_t)l * Cout, acc);
         }
     }
 }
 
 // ---- first-layer weight gradient: dw f32 (k,CIN,Cout), db f32 (Cout) from x f32 and dy bf16 (pre-activation grad) ----
 // thread = 8 consecutive output channels (one 128-bit dy load per row) x one row lane; k*CIN*8 (+8 bias) partial sums
-template <int CIN, int KMAX>
+template <int CIN, int KMAX, typename T>
 __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* __restrict__ x,
-                                                                  const __nv_bfloat16* __restrict__ dy,
+                                                                  const T* __restrict__ dy,
                                                                   float* __restrict__ dw, float* __restrict__ db, int B,
                                                                   int L, int Lout, int Cout, int k, int s, int p,
                                                                   long long rows_per_block, int ld, int co0) {
@@ -133,26 +177,20 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
         int b = (q0 < q1) ? (int)fast_div(q0, Lout, l) : 0;
         // rows in batches of U: all U 128-bit dy loads of a thread are issued before the first is used (the kernel is
         // latency bound otherwise: two 256-thread blocks per SM at ~100 registers keep too few bytes in flight)
-        constexpr int U = CIN == 1 ? 8 : 2;      // CIN = 2 already sits at the 128-register limit of two blocks per SM
-        const uint4* __restrict__ dyg = reinterpret_cast<const uint4*>(dy + co0) + g;
-        const size_t ldv = (size_t)ld / 8;      // dy row pitch in uint4 (ld % 8 == 0)
+        // CIN = 2 already sits at the 128-register limit of two blocks per SM; float rows take twice the registers
+        constexpr int U = (CIN == 1 ? 8 : 2) / (sizeof(T) == 4 ? 2 : 1);
+        const T* __restrict__ dyg = dy + co0 + g * 8;
         for (long long row = q0; row < q1; row += U) {
-            uint4 pkv[U];
+            typename Act8<T>::Raw pkv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                pkv[u] = (row + u < q1) ? __ldg(dyg + (size_t)(row + u) * ldv) : make_uint4(0u, 0u, 0u, 0u);
+                pkv[u] = (row + u < q1) ? Act8<T>::ldraw(dyg + (size_t)(row + u) * ld) : Act8<T>::zero();
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (row + u < q1) {
                     if (l == Lout) { l = 0; ++b; }
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pkv[u]);
                     float gv[8];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float2 v = __bfloat1622float2(h[e]);
-                        gv[2 * e] = v.x;
-                        gv[2 * e + 1] = v.y;
-                    }
+                    Act8<T>::unpack(pkv[u], gv);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) accb[j] += gv[j];
 #pragma unroll
@@ -207,8 +245,8 @@ __global__ void __launch_bounds__(256) conv_smallcin_wgrad_kernel(const float* _
 // bbhMahoGANy.py:1296).  One warp per dy row: the row (Cout bf16) is read once with 128-bit loads, dotted with the
 // k*CIN weight rows held in shared memory, reduced by shuffles and scattered with k*CIN atomics into dx (zeroed by
 // the caller): HBM traffic = dy once.
-template <int CIN, int KMAX>
-__global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const __nv_bfloat16* __restrict__ dy,
+template <int CIN, int KMAX, typename T>
+__global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const T* __restrict__ dy,
                                                                   const float* __restrict__ w, float* __restrict__ dx,
                                                                   int B, int L, int Lout, int Cout, int k, int s, int p) {
     extern __shared__ float sw[];     // k*CIN*Cout
@@ -226,15 +264,8 @@ __global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const __nv_bfl
 #pragma unroll
         for (int i = 0; i < KMAX * CIN; ++i) acc[i] = 0.f;
         for (int c8 = lane; c8 < Cout / 8; c8 += 32) {
-            uint4 pk = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * Cout) + c8);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
             float gv[8];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 v = __bfloat1622float2(h[e]);
-                gv[2 * e] = v.x;
-                gv[2 * e + 1] = v.y;
-            }
+            Act8<T>::load(dy + (size_t)row * Cout + c8 * 8, gv);
 #pragma unroll
             for (int i = 0; i < KMAX * CIN; ++i) {
                 if (i < k * CIN) {
@@ -267,21 +298,21 @@ __global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const __nv_bfl
 
 // ---- Dense with N <= 4 outputs over bf16 features -------------------------------------------------------------
 // fwd: y[m, j] = act(sum_k x[m,k] w[k,j] + b[j]) : one CTA per row m, 128-bit loads, block reduction
-template <int NS>
-__global__ void __launch_bounds__(512) dense_small_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x,
+template <int NS, typename T>
+__global__ void __launch_bounds__(512) dense_small_fwd_bf16_kernel(const T* __restrict__ x,
                                                                    const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ y,
                                                                    int K, int act, float ap) {
     __shared__ float sm[32];
     const int m = blockIdx.x;
-    const __nv_bfloat16* xr = x + (size_t)m * K;
+    const T* xr = x + (size_t)m * K;
     float acc[NS];
 #pragma unroll
     for (int j = 0; j < NS; ++j) acc[j] = 0.f;
     const int K8 = K / 8;
     for (int i = threadIdx.x; i < K8; i += blockDim.x) {
-        uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr) + i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        float xv[8];
+        Act8<T>::load(xr + (size_t)i * 8, xv);
         // the 8*NS weights of this chunk are contiguous: NS*2 128-bit loads
         float wv[8 * NS];
         const float4* wp = reinterpret_cast<const float4*>(w + (size_t)i * 8 * NS);
@@ -291,17 +322,13 @@ __global__ void __launch_bounds__(512) dense_small_fwd_bf16_kernel(const __nv_bf
             wv[4 * q4] = t4.x; wv[4 * q4 + 1] = t4.y; wv[4 * q4 + 2] = t4.z; wv[4 * q4 + 3] = t4.w;
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float2 v = __bfloat1622float2(h[e]);
+        for (int e = 0; e < 8; ++e) {
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                acc[j] = fmaf(v.x, wv[(2 * e) * NS + j], acc[j]);
-                acc[j] = fmaf(v.y, wv[(2 * e + 1) * NS + j], acc[j]);
-            }
+            for (int j = 0; j < NS; ++j) acc[j] = fmaf(xv[e], wv[e * NS + j], acc[j]);
         }
     }
     for (int kk = K8 * 8 + threadIdx.x; kk < K; kk += blockDim.x) {
-        float v = __bfloat162float(xr[kk]);
+        float v = Act8<T>::get(xr + kk);
 #pragma unroll
         for (int j = 0; j < NS; ++j) acc[j] = fmaf(v, __ldg(&w[(size_t)kk * NS + j]), acc[j]);
     }
@@ -316,11 +343,11 @@ __global__ void __launch_bounds__(512) dense_small_fwd_bf16_kernel(const __nv_bf
 // thread = 8 consecutive features (its 8*NS weights stay in registers) x a slice of the rows; optionally the
 // per-channel sum of dx (feature k belongs to channel k % C: the flattened (L, C) output of a convolution), which
 // is the bias gradient of that convolution, accumulated with one atomic per thread and channel.
-template <int NS, int KIND>
+template <int NS, int KIND, typename T>
 __global__ void __launch_bounds__(256) dense_small_dgrad_bf16_kernel(const float* __restrict__ dy,
                                                                      const float* __restrict__ w,
-                                                                     const __nv_bfloat16* __restrict__ xin,
-                                                                     __nv_bfloat16* __restrict__ dx, int M, int K,
+                                                                     const T* __restrict__ xin,
+                                                                     T* __restrict__ dx, int M, int K,
                                                                      int m_per_split, float ap,
                                                                      float* __restrict__ colsum, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;   // chunk of 8 features
@@ -350,24 +377,14 @@ __global__ void __launch_bounds__(256) dense_small_dgrad_bf16_kernel(const float
             o[e] = sacc;
         }
         if (KIND != GN_ACT_NONE) {
-            uint4 pk = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)m * K) + c);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+            float xv[8];
+            Act8<T>::load(xin + (size_t)m * K + (size_t)c * 8, xv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 v = __bfloat1622float2(h[e]);
-                o[2 * e] *= act_bwd_t<KIND>(v.x, ap);
-                o[2 * e + 1] *= act_bwd_t<KIND>(v.y, ap);
-            }
+            for (int e = 0; e < 8; ++e) o[e] *= act_bwd_t<KIND>(xv[e], ap);
         }
-        __nv_bfloat162 h2[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            h2[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-            float2 r = __bfloat1622float2(h2[e]);      // the sum is over the values as stored
-            cs[2 * e] += r.x;
-            cs[2 * e + 1] += r.y;
-        }
-        *(reinterpret_cast<uint4*>(dx + (size_t)m * K) + c) = *reinterpret_cast<uint4*>(h2);
+        for (int e = 0; e < 8; ++e) cs[e] += Act8<T>::round(o[e]);      // the sum is over the values as stored
+        Act8<T>::store(dx + (size_t)m * K + (size_t)c * 8, o);
     }
     if (colsum != nullptr) {
         // same-address atomics serialise in L2 (~tens of ns each), so fold inside the block first: the block's
@@ -393,8 +410,8 @@ __global__ void __launch_bounds__(256) dense_small_dgrad_bf16_kernel(const float
 }
 
 // wgrad: dw[k,j] = sum_m x[m,k] dy[m,j] : thread = 8 consecutive k, loop over a slice of m, atomics across slices
-template <int NS>
-__global__ void __launch_bounds__(256) dense_small_wgrad_bf16_kernel(const __nv_bfloat16* __restrict__ x,
+template <int NS, typename T>
+__global__ void __launch_bounds__(256) dense_small_wgrad_bf16_kernel(const T* __restrict__ x,
                                                                      const float* __restrict__ dy,
                                                                      float* __restrict__ dw, int M, int K,
                                                                      int m_per_split) {
@@ -407,19 +424,15 @@ __global__ void __launch_bounds__(256) dense_small_wgrad_bf16_kernel(const __nv_
 #pragma unroll
         for (int j = 0; j < NS; ++j) acc[e][j] = 0.f;
     for (int m = mb; m < me; ++m) {
-        uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)m * K) + c);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        float xv[8];
+        Act8<T>::load(x + (size_t)m * K + (size_t)c * 8, xv);
         float g[NS];
 #pragma unroll
         for (int j = 0; j < NS; ++j) g[j] = __ldg(&dy[(size_t)m * NS + j]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float2 v = __bfloat1622float2(h[e]);
+        for (int e = 0; e < 8; ++e) {
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                acc[2 * e][j] = fmaf(v.x, g[j], acc[2 * e][j]);
-                acc[2 * e + 1][j] = fmaf(v.y, g[j], acc[2 * e + 1][j]);
-            }
+            for (int j = 0; j < NS; ++j) acc[e][j] = fmaf(xv[e], g[j], acc[e][j]);
         }
     }
 #pragma unroll
@@ -485,69 +498,74 @@ __global__ void __launch_bounds__(256) upsample_bwd_bf16_kernel(const __nv_bfloa
 
 // ---- last convolution of the generator: Cout = 1, stride 1 (bbhMahoGANy.py:291).  With one output channel the layer
 // is five dot products per input row: tap t of row pos contributes d_t = <x[b,pos,:], w[t,:]> to y[b, pos - t + p].
-// fwd: one warp per input row, 128-bit loads, shuffle reduction, k atomics into y (zeroed by the caller; the centre
-// tap carries the bias).  dgrad: dx[b,pos,:] = sum_t dy[b,pos-t+p] w[t,:] streamed out row by row.  wgrad:
+// fwd: one warp per input row of a 32-row output tile, 128-bit loads, shuffle reduction, tap products combined through
+// shared memory in a fixed order (bit-reproducible).  dgrad: dx[b,pos,:] = sum_t dy[b,pos-t+p] w[t,:] streamed out row by row.  wgrad:
 // dw[t,:] = sum_rows x[row,:] dy[row shifted by t]; thread = 8 channels, a slice of the rows, atomics across slices.
-template <int KMAX>
-__global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+constexpr int COUT1_ROWS = 32;      // output rows per block of the Cout = 1 forward
+template <int KMAX, typename T>
+__global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y, int B,
-                                                             int L, int Lout, int Cin, int k, int p) {
-    extern __shared__ float sw[];     // k*Cin
+                                                             int L, int Lout, int Cin, int k, int p, int tiles_per_sample) {
+    // One block = COUT1_ROWS consecutive output rows of one sample.  Every input row the tile touches (the tile plus a
+    // k-1 row halo) is read once by one warp, which leaves its k tap products in shared memory; the outputs are then
+    // summed from shared memory in a fixed order: no atomics, bit-reproducible, x is read (1 + (k-1)/32) times.
+    extern __shared__ float sw[];     // k*Cin weights, then (COUT1_ROWS + KMAX - 1) * KMAX partial products
+    float* part = sw + k * Cin;
     for (int i = threadIdx.x; i < k * Cin; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long rows = (long long)B * L;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float bv = bias ? bias[0] : 0.f;
-    for (long long row = warp0; row < rows; row += nwarps) {
-        int pos;
-        const int b = (int)fast_div(row, L, pos);
-        float acc[KMAX];
+    for (long long tile = blockIdx.x; tile < (long long)B * tiles_per_sample; tile += gridDim.x) {
+        const int b = (int)(tile / tiles_per_sample);
+        const int l0 = (int)(tile - (long long)b * tiles_per_sample) * COUT1_ROWS;
+        const int nin = COUT1_ROWS + k - 1;                       // input rows l0 - p ... l0 - p + nin - 1
+        for (int ri = warp; ri < nin; ri += 8) {
+            const int pos = l0 - p + ri;
+            float acc[KMAX];
 #pragma unroll
-        for (int t = 0; t < KMAX; ++t) acc[t] = 0.f;
-        for (int c8 = lane; c8 < Cin / 8; c8 += 32) {
-            uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * Cin) + c8);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-            float xv[8];
+            for (int t = 0; t < KMAX; ++t) acc[t] = 0.f;
+            if (pos >= 0 && pos < L) {
+                const T* xr = x + ((size_t)b * L + pos) * Cin;
+                for (int c8 = lane; c8 < Cin / 8; c8 += 32) {
+                    float xv[8];
+                    Act8<T>::load(xr + c8 * 8, xv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 v = __bfloat1622float2(h[e]);
-                xv[2 * e] = v.x;
-                xv[2 * e + 1] = v.y;
+                    for (int t = 0; t < KMAX; ++t) {
+                        if (t < k) {
+                            const float4* wr = reinterpret_cast<const float4*>(&sw[t * Cin + c8 * 8]);
+                            const float4 w0 = wr[0], w1 = wr[1];
+                            acc[t] = fmaf(xv[0], w0.x, acc[t]); acc[t] = fmaf(xv[1], w0.y, acc[t]);
+                            acc[t] = fmaf(xv[2], w0.z, acc[t]); acc[t] = fmaf(xv[3], w0.w, acc[t]);
+                            acc[t] = fmaf(xv[4], w1.x, acc[t]); acc[t] = fmaf(xv[5], w1.y, acc[t]);
+                            acc[t] = fmaf(xv[6], w1.z, acc[t]); acc[t] = fmaf(xv[7], w1.w, acc[t]);
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int t = 0; t < KMAX; ++t) {
-                if (t < k) {
-                    const float4* wr = reinterpret_cast<const float4*>(&sw[t * Cin + c8 * 8]);
-                    const float4 w0 = wr[0], w1 = wr[1];
-                    acc[t] = fmaf(xv[0], w0.x, acc[t]); acc[t] = fmaf(xv[1], w0.y, acc[t]);
-                    acc[t] = fmaf(xv[2], w0.z, acc[t]); acc[t] = fmaf(xv[3], w0.w, acc[t]);
-                    acc[t] = fmaf(xv[4], w1.x, acc[t]); acc[t] = fmaf(xv[5], w1.y, acc[t]);
-                    acc[t] = fmaf(xv[6], w1.z, acc[t]); acc[t] = fmaf(xv[7], w1.w, acc[t]);
-                }
+                float v = acc[t];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) part[ri * KMAX + t] = v;
             }
         }
-#pragma unroll
-        for (int t = 0; t < KMAX; ++t) {
-            float v = acc[t];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc[t] = v;
+        __syncthreads();
+        if (threadIdx.x < COUT1_ROWS) {
+            const int l = l0 + threadIdx.x;
+            if (l < Lout) {
+                float v = bv;             // y[l] = bias + sum_t <x[l + t - p], w[t]>; input row l + t - p is tile row i + t
+                for (int t = 0; t < k; ++t) v += part[(threadIdx.x + t) * KMAX + t];
+                y[(size_t)b * Lout + l] = v;
+            }
         }
-        if (lane < k) {
-            float v = 0.f;
-#pragma unroll
-            for (int t = 0; t < KMAX; ++t) v = (t == lane) ? acc[t] : v;
-            const int l = pos - lane + p;
-            if (l >= 0 && l < Lout) atomicAdd(&y[(size_t)b * Lout + l], v + (lane == p ? bv : 0.f));
-        }
+        __syncthreads();
     }
 }
 
-template <int KMAX>
+template <int KMAX, typename T>
 __global__ void __launch_bounds__(256) conv_cout1_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                               __nv_bfloat16* __restrict__ dx, int B, int L, int Lout,
+                                                               T* __restrict__ dx, int B, int L, int Lout,
                                                                int Cin, int k, int p) {
     const int C8 = Cin / 8;
     const long long total = (long long)B * L * C8;
@@ -571,15 +589,12 @@ __global__ void __launch_bounds__(256) conv_cout1_dgrad_kernel(const float* __re
                 }
             }
         }
-        __nv_bfloat162 h[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-        reinterpret_cast<uint4*>(dx)[i] = *reinterpret_cast<uint4*>(h);
+        Act8<T>::store(dx + (size_t)i * 8, o);
     }
 }
 
-template <int KMAX>
-__global__ void __launch_bounds__(256) conv_cout1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy,
+template <int KMAX, typename T>
+__global__ void __launch_bounds__(256) conv_cout1_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dw, int B, int L, int Lout, int Cin, int k,
                                                                int p, long long rows_per_split) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;   // chunk of 8 channels
@@ -595,15 +610,8 @@ __global__ void __launch_bounds__(256) conv_cout1_wgrad_kernel(const __nv_bfloat
     for (long long row = r0; row < r1; ++row) {
         int pos;
         const int b = (int)fast_div(row, L, pos);
-        uint4 pk = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * Cin) + c);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
         float xv[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float2 v = __bfloat1622float2(h[e]);
-            xv[2 * e] = v.x;
-            xv[2 * e + 1] = v.y;
-        }
+        Act8<T>::load(x + (size_t)row * Cin + (size_t)c * 8, xv);
 #pragma unroll
         for (int t = 0; t < KMAX; ++t) {
             if (t < k) {
@@ -658,38 +666,39 @@ static int check_cout1(int B, int L, int Cin, int Lout, int k, int p) {
     return GN_OK;
 }
 
-extern "C" int gn_conv1d_cout1_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int B, int L, int Cin,
-                                        int Lout, int k, int pad_left, void* stream) {
+template <typename T>
+static int cout1_fwd(const T* x, const float* w, const float* bias, float* y, int B, int L, int Cin, int Lout, int k,
+                     int pad_left, void* stream) {
     GN_REQUIRE(x && w && y, "null pointer");
     int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
     if (rc != GN_OK) return rc;
-    const size_t smem = sizeof(float) * (size_t)k * Cin;
+    const size_t smem = sizeof(float) * ((size_t)k * Cin + (size_t)(COUT1_ROWS + 4) * 5);
     GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(y, 0, sizeof(float) * (size_t)B * Lout, st);
     if (B == 0) return GN_OK;
-    const long long rows = (long long)B * L;
-    long long blocks = (rows + 7) / 8;
-    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    conv_cout1_fwd_kernel<5><<<(unsigned)blocks, 256, smem, st>>>((const __nv_bfloat16*)x, w, bias, y, B, L, Lout, Cin, k,
-                                                                pad_left);
+    const int tps = (Lout + COUT1_ROWS - 1) / COUT1_ROWS;
+    long long blocks = (long long)B * tps;
+    if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+    conv_cout1_fwd_kernel<5, T><<<(unsigned)blocks, 256, smem, st>>>(x, w, bias, y, B, L, Lout, Cin, k, pad_left, tps);
     return cuda_status("conv_cout1_fwd_kernel");
 }
 
-extern "C" int gn_conv1d_cout1_dgrad_bf16(const float* dy, const float* w, void* dx, int B, int L, int Cin, int Lout, int k,
-                                          int pad_left, void* stream) {
+template <typename T>
+static int cout1_dgrad(const float* dy, const float* w, T* dx, int B, int L, int Cin, int Lout, int k, int pad_left,
+                       void* stream) {
     GN_REQUIRE(dy && w && dx, "null pointer");
     int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
     if (rc != GN_OK) return rc;
     if (B == 0) return GN_OK;
     const long long total = (long long)B * L * (Cin / 8);
     unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
-    conv_cout1_dgrad_kernel<5><<<grid, 256, 0, as_stream(stream)>>>(dy, w, (__nv_bfloat16*)dx, B, L, Lout, Cin, k, pad_left);
+    conv_cout1_dgrad_kernel<5, T><<<grid, 256, 0, as_stream(stream)>>>(dy, w, dx, B, L, Lout, Cin, k, pad_left);
     return cuda_status("conv_cout1_dgrad_kernel");
 }
 
-extern "C" int gn_conv1d_cout1_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int B, int L, int Cin,
-                                          int Lout, int k, int pad_left, void* stream) {
+template <typename T>
+static int cout1_wgrad(const T* x, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout, int k,
+                       int pad_left, void* stream) {
     GN_REQUIRE(x && dy && dw, "null pointer");
     int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
     if (rc != GN_OK) return rc;
@@ -709,17 +718,16 @@ extern "C" int gn_conv1d_cout1_wgrad_bf16(const void* x, const float* dy, float*
         splits = (rows + per - 1) / per;
         const int threads = Cin / 8 < 256 ? ((Cin / 8 + 31) / 32) * 32 : 256;
         dim3 grid((Cin / 8 + threads - 1) / threads, (unsigned)splits);
-        conv_cout1_wgrad_kernel<5><<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, dy, dw, B, L, Lout, Cin, k, pad_left, per);
+        conv_cout1_wgrad_kernel<5, T><<<grid, threads, 0, st>>>(x, dy, dw, B, L, Lout, Cin, k, pad_left, per);
     }
     if (db != nullptr) sum_all_kernel<<<1, 1024, 0, st>>>(dy, (long long)B * Lout, db);
     return cuda_status("conv_cout1_wgrad_kernel");
 }
 
-
-extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const float* bias, void* y, int B, int L,
-                                           int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
-                                           float act_param, void* stream) {
-    GN_REQUIRE(x && w && y, "null pointer");
+template <typename T>
+static int smallcin_fwd(const float* x, const float* w, const float* bias, T* yy, int B, int L, int Cin, int Lout, int Cout,
+                        int k, int stride, int pad_left, int act, float act_param, void* stream) {
+    GN_REQUIRE(x && w && yy, "null pointer");
     GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 16 && stride > 0 && pad_left >= 0, "bad geometry");
     GN_REQUIRE((Cin == 1 || Cin == 2) && Cout % 8 == 0 && Cout <= 1024, "needs Cin in {1,2} and Cout % 8 == 0");
     if (B == 0) return GN_OK;
@@ -738,8 +746,7 @@ extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const
         if (bx > cap) bx = cap;
         dim3 grid((unsigned)bx, (unsigned)((groups + gpb - 1) / gpb));
         cudaStream_t st = as_stream(stream);
-        __nv_bfloat16* yy = (__nv_bfloat16*)y;
-#define GN_SCF(CI, KIND) conv_smallcin_fwd_reg_kernel<CI, 5, KIND><<<grid, 256, 0, st>>>(x, w, bias, yy, B, L, Lout, Cout, k, stride, pad_left, act_param, gpb, run, rps, n_runs)
+#define GN_SCF(CI, KIND) conv_smallcin_fwd_reg_kernel<CI, 5, KIND, T><<<grid, 256, 0, st>>>(x, w, bias, yy, B, L, Lout, Cout, k, stride, pad_left, act_param, gpb, run, rps, n_runs)
 #define GN_SCF_ACT(CI)                                              \
         switch (act) {                                              \
             case GN_ACT_RELU: GN_SCF(CI, GN_ACT_RELU); break;       \
@@ -757,16 +764,17 @@ extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const
     long long total = (long long)B * Lout * (Cout / 8);
     unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
     if (Cin == 1)
-        conv_smallcin_fwd_kernel<1><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, L, Lout, Cout,
-                                                                           k, stride, pad_left, act, act_param);
+        conv_smallcin_fwd_kernel<1, T><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, yy, B, L, Lout, Cout, k, stride,
+                                                                              pad_left, act, act_param);
     else
-        conv_smallcin_fwd_kernel<2><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, L, Lout, Cout,
-                                                                           k, stride, pad_left, act, act_param);
+        conv_smallcin_fwd_kernel<2, T><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, yy, B, L, Lout, Cout, k, stride,
+                                                                              pad_left, act, act_param);
     return cuda_status("conv_smallcin_fwd_kernel");
 }
 
-extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, float* db, int B, int L, int Cin,
-                                             int Lout, int Cout, int k, int stride, int pad_left, void* stream) {
+template <typename T>
+static int smallcin_wgrad(const float* x, const T* dy, float* dw, float* db, int B, int L, int Cin, int Lout, int Cout,
+                          int k, int stride, int pad_left, void* stream) {
     GN_REQUIRE(x && dy && dw, "null pointer");
     GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 5 && stride > 0 && pad_left >= 0, "bad geometry (k <= 5)");
     GN_REQUIRE((Cin == 1 || Cin == 2) && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 2048)),
@@ -784,19 +792,18 @@ extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, flo
     const int slice = Cout < 128 ? Cout : 128;
     for (int co0 = 0; co0 < Cout; co0 += slice) {
         if (Cin == 1)
-            conv_smallcin_wgrad_kernel<1, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L,
-                                                                             Lout, slice, k, stride, pad_left, per, Cout,
-                                                                             co0);
+            conv_smallcin_wgrad_kernel<1, 5, T><<<(unsigned)blocks, 256, 0, st>>>(x, dy, dw, db, B, L, Lout, slice, k, stride,
+                                                                                pad_left, per, Cout, co0);
         else
-            conv_smallcin_wgrad_kernel<2, 5><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, dw, db, B, L,
-                                                                             Lout, slice, k, stride, pad_left, per, Cout,
-                                                                             co0);
+            conv_smallcin_wgrad_kernel<2, 5, T><<<(unsigned)blocks, 256, 0, st>>>(x, dy, dw, db, B, L, Lout, slice, k, stride,
+                                                                                pad_left, per, Cout, co0);
     }
     return cuda_status("conv_smallcin_wgrad_kernel");
 }
 
-extern "C" int gn_conv1d_smallcin_dgrad_bf16(const void* dy, const float* w, float* dx, int B, int L, int Cin, int Lout,
-                                             int Cout, int k, int stride, int pad_left, void* stream) {
+template <typename T>
+static int smallcin_dgrad(const T* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int Cout, int k,
+                          int stride, int pad_left, void* stream) {
     GN_REQUIRE(dy && w && dx, "null pointer");
     GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 5 && stride > 0 && pad_left >= 0, "bad geometry (k <= 5)");
     GN_REQUIRE((Cin == 1 || Cin == 2) && Cout % 8 == 0, "needs Cin in {1,2} and Cout % 8 == 0");
@@ -809,35 +816,33 @@ extern "C" int gn_conv1d_smallcin_dgrad_bf16(const void* dy, const float* w, flo
     long long blocks = (rows + 7) / 8;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
     if (Cin == 1)
-        conv_smallcin_dgrad_kernel<1, 5><<<(unsigned)blocks, 256, smem, st>>>((const __nv_bfloat16*)dy, w, dx, B, L, Lout,
-                                                                            Cout, k, stride, pad_left);
+        conv_smallcin_dgrad_kernel<1, 5, T><<<(unsigned)blocks, 256, smem, st>>>(dy, w, dx, B, L, Lout, Cout, k, stride, pad_left);
     else
-        conv_smallcin_dgrad_kernel<2, 5><<<(unsigned)blocks, 256, smem, st>>>((const __nv_bfloat16*)dy, w, dx, B, L, Lout,
-                                                                            Cout, k, stride, pad_left);
+        conv_smallcin_dgrad_kernel<2, 5, T><<<(unsigned)blocks, 256, smem, st>>>(dy, w, dx, B, L, Lout, Cout, k, stride, pad_left);
     return cuda_status("conv_smallcin_dgrad_kernel");
 }
 
-extern "C" int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N,
-                                       int act, float act_param, void* stream) {
-    GN_REQUIRE(x && w && y, "null pointer");
+template <typename T>
+static int dense_small_fwd(const T* xb, const float* w, const float* bias, float* y, int M, int K, int N, int act,
+                           float act_param, void* stream) {
+    GN_REQUIRE(xb && w && y, "null pointer");
     GN_REQUIRE(M >= 0 && K > 0 && N >= 1 && N <= 4 && K % 8 == 0, "needs 1 <= N <= 4 and K % 8 == 0");
     if (M == 0) return GN_OK;
     cudaStream_t st = as_stream(stream);
-    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
     switch (N) {
-        case 1: dense_small_fwd_bf16_kernel<1><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
-        case 2: dense_small_fwd_bf16_kernel<2><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
-        case 3: dense_small_fwd_bf16_kernel<3><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
-        default: dense_small_fwd_bf16_kernel<4><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+        case 1: dense_small_fwd_bf16_kernel<1, T><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+        case 2: dense_small_fwd_bf16_kernel<2, T><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+        case 3: dense_small_fwd_bf16_kernel<3, T><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
+        default: dense_small_fwd_bf16_kernel<4, T><<<M, 512, 0, st>>>(xb, w, bias, y, K, act, act_param); break;
     }
-    return cuda_status("dense_small_fwd_bf16_kernel");
+    return cuda_status("dense_small_fwd_kernel");
 }
 
-template <int NS>
-static void launch_dense_small_dgrad(dim3 grid, cudaStream_t st, const float* dy, const float* w, const __nv_bfloat16* xi,
-                                     __nv_bfloat16* d, int M, int K, int per, int in_act, float ap, float* colsum, int C) {
+template <int NS, typename T>
+static void launch_dense_small_dgrad(dim3 grid, cudaStream_t st, const float* dy, const float* w, const T* xi, T* d, int M,
+                                     int K, int per, int in_act, float ap, float* colsum, int C) {
     if (xi == nullptr) in_act = GN_ACT_NONE;
-#define GN_DSD(KIND) dense_small_dgrad_bf16_kernel<NS, KIND><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, per, ap, colsum, C)
+#define GN_DSD(KIND) dense_small_dgrad_bf16_kernel<NS, KIND, T><<<grid, 256, 0, st>>>(dy, w, xi, d, M, K, per, ap, colsum, C)
     switch (in_act) {
         case GN_ACT_RELU: GN_DSD(GN_ACT_RELU); break;
         case GN_ACT_TANH: GN_DSD(GN_ACT_TANH); break;
@@ -849,10 +854,10 @@ static void launch_dense_small_dgrad(dim3 grid, cudaStream_t st, const float* dy
 #undef GN_DSD
 }
 
-extern "C" int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, float* dx_colsum,
-                                         int colsum_channels, int M, int K, int N, int in_act, float in_act_param,
-                                         void* stream) {
-    GN_REQUIRE(dy && w && dx, "null pointer");
+template <typename T>
+static int dense_small_dgrad(const float* dy, const float* w, const T* xi, T* d, float* dx_colsum, int colsum_channels,
+                             int M, int K, int N, int in_act, float in_act_param, void* stream) {
+    GN_REQUIRE(dy && w && d, "null pointer");
     GN_REQUIRE(M >= 0 && K > 0 && N >= 1 && N <= 4 && K % 8 == 0, "needs 1 <= N <= 4 and K % 8 == 0");
     GN_REQUIRE(dx_colsum == nullptr || (colsum_channels > 0 && colsum_channels % 8 == 0 && K % colsum_channels == 0),
                "column sums need channels % 8 == 0 and K % channels == 0");
@@ -868,20 +873,18 @@ extern "C" int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const 
     int per = (M + splits - 1) / splits;
     splits = (M + per - 1) / per;
     dim3 grid(bx, splits);
-    const __nv_bfloat16* xi = (const __nv_bfloat16*)x_in;
-    __nv_bfloat16* d = (__nv_bfloat16*)dx;
     switch (N) {
-        case 1: launch_dense_small_dgrad<1>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
-        case 2: launch_dense_small_dgrad<2>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
-        case 3: launch_dense_small_dgrad<3>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
-        default: launch_dense_small_dgrad<4>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
+        case 1: launch_dense_small_dgrad<1, T>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
+        case 2: launch_dense_small_dgrad<2, T>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
+        case 3: launch_dense_small_dgrad<3, T>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
+        default: launch_dense_small_dgrad<4, T>(grid, st, dy, w, xi, d, M, K, per, in_act, in_act_param, dx_colsum, colsum_channels); break;
     }
-    return cuda_status("dense_small_dgrad_bf16_kernel");
+    return cuda_status("dense_small_dgrad_kernel");
 }
 
-extern "C" int gn_dense_small_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int M, int K, int N,
-                                         void* stream) {
-    GN_REQUIRE(x && dy && dw, "null pointer");
+template <typename T>
+static int dense_small_wgrad(const T* xb, const float* dy, float* dw, float* db, int M, int K, int N, void* stream) {
+    GN_REQUIRE(xb && dy && dw, "null pointer");
     GN_REQUIRE(M >= 0 && K > 0 && N >= 1 && N <= 4 && K % 8 == 0, "needs 1 <= N <= 4 and K % 8 == 0");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)K * N, st);
@@ -895,16 +898,98 @@ extern "C" int gn_dense_small_wgrad_bf16(const void* x, const float* dy, float* 
         int per = (M + splits - 1) / splits;
         splits = (M + per - 1) / per;
         dim3 grid(bx, splits);
-        const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
         switch (N) {
-            case 1: dense_small_wgrad_bf16_kernel<1><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
-            case 2: dense_small_wgrad_bf16_kernel<2><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
-            case 3: dense_small_wgrad_bf16_kernel<3><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
-            default: dense_small_wgrad_bf16_kernel<4><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+            case 1: dense_small_wgrad_bf16_kernel<1, T><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+            case 2: dense_small_wgrad_bf16_kernel<2, T><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+            case 3: dense_small_wgrad_bf16_kernel<3, T><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
+            default: dense_small_wgrad_bf16_kernel<4, T><<<grid, 256, 0, st>>>(xb, dy, dw, M, K, per); break;
         }
     }
     if (db != nullptr) dense_small_bias_grad_kernel<<<1, 32, 0, st>>>(dy, db, M, N);
-    return cuda_status("dense_small_wgrad_bf16_kernel");
+    return cuda_status("dense_small_wgrad_kernel");
+}
+
+typedef __nv_bfloat16 bf16_t;
+
+// bf16 activations (throughput mode)
+extern "C" int gn_conv1d_cout1_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int B, int L, int Cin,
+                                        int Lout, int k, int pad_left, void* stream) {
+    return cout1_fwd<bf16_t>((const bf16_t*)x, w, bias, y, B, L, Cin, Lout, k, pad_left, stream);
+}
+extern "C" int gn_conv1d_cout1_dgrad_bf16(const float* dy, const float* w, void* dx, int B, int L, int Cin, int Lout, int k,
+                                          int pad_left, void* stream) {
+    return cout1_dgrad<bf16_t>(dy, w, (bf16_t*)dx, B, L, Cin, Lout, k, pad_left, stream);
+}
+extern "C" int gn_conv1d_cout1_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int B, int L, int Cin,
+                                          int Lout, int k, int pad_left, void* stream) {
+    return cout1_wgrad<bf16_t>((const bf16_t*)x, dy, dw, db, B, L, Cin, Lout, k, pad_left, stream);
+}
+extern "C" int gn_conv1d_smallcin_fwd_bf16(const float* x, const float* w, const float* bias, void* y, int B, int L,
+                                           int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
+                                           float act_param, void* stream) {
+    return smallcin_fwd<bf16_t>(x, w, bias, (bf16_t*)y, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param, stream);
+}
+extern "C" int gn_conv1d_smallcin_wgrad_bf16(const float* x, const void* dy, float* dw, float* db, int B, int L, int Cin,
+                                             int Lout, int Cout, int k, int stride, int pad_left, void* stream) {
+    return smallcin_wgrad<bf16_t>(x, (const bf16_t*)dy, dw, db, B, L, Cin, Lout, Cout, k, stride, pad_left, stream);
+}
+extern "C" int gn_conv1d_smallcin_dgrad_bf16(const void* dy, const float* w, float* dx, int B, int L, int Cin, int Lout,
+                                             int Cout, int k, int stride, int pad_left, void* stream) {
+    return smallcin_dgrad<bf16_t>((const bf16_t*)dy, w, dx, B, L, Cin, Lout, Cout, k, stride, pad_left, stream);
+}
+extern "C" int gn_dense_small_fwd_bf16(const void* x, const float* w, const float* bias, float* y, int M, int K, int N,
+                                       int act, float act_param, void* stream) {
+    return dense_small_fwd<bf16_t>((const bf16_t*)x, w, bias, y, M, K, N, act, act_param, stream);
+}
+extern "C" int gn_dense_small_dgrad_bf16(const float* dy, const float* w, const void* x_in, void* dx, float* dx_colsum,
+                                         int colsum_channels, int M, int K, int N, int in_act, float in_act_param,
+                                         void* stream) {
+    return dense_small_dgrad<bf16_t>(dy, w, (const bf16_t*)x_in, (bf16_t*)dx, dx_colsum, colsum_channels, M, K, N, in_act,
+                                     in_act_param, stream);
+}
+extern "C" int gn_dense_small_wgrad_bf16(const void* x, const float* dy, float* dw, float* db, int M, int K, int N,
+                                         void* stream) {
+    return dense_small_wgrad<bf16_t>((const bf16_t*)x, dy, dw, db, M, K, N, stream);
+}
+
+// float32 activations (float32 and split-operand modes): same kernels, same arguments
+extern "C" int gn_conv1d_cout1_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int L, int Cin,
+                                       int Lout, int k, int pad_left, void* stream) {
+    return cout1_fwd<float>(x, w, bias, y, B, L, Cin, Lout, k, pad_left, stream);
+}
+extern "C" int gn_conv1d_cout1_dgrad_f32(const float* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int k,
+                                         int pad_left, void* stream) {
+    return cout1_dgrad<float>(dy, w, dx, B, L, Cin, Lout, k, pad_left, stream);
+}
+extern "C" int gn_conv1d_cout1_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int L, int Cin,
+                                         int Lout, int k, int pad_left, void* stream) {
+    return cout1_wgrad<float>(x, dy, dw, db, B, L, Cin, Lout, k, pad_left, stream);
+}
+extern "C" int gn_conv1d_smallcin_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int L,
+                                          int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
+                                          float act_param, void* stream) {
+    return smallcin_fwd<float>(x, w, bias, y, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param, stream);
+}
+extern "C" int gn_conv1d_smallcin_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int L, int Cin,
+                                            int Lout, int Cout, int k, int stride, int pad_left, void* stream) {
+    return smallcin_wgrad<float>(x, dy, dw, db, B, L, Cin, Lout, Cout, k, stride, pad_left, stream);
+}
+extern "C" int gn_conv1d_smallcin_dgrad_f32(const float* dy, const float* w, float* dx, int B, int L, int Cin, int Lout,
+                                            int Cout, int k, int stride, int pad_left, void* stream) {
+    return smallcin_dgrad<float>(dy, w, dx, B, L, Cin, Lout, Cout, k, stride, pad_left, stream);
+}
+extern "C" int gn_dense_small_fwd_f32(const float* x, const float* w, const float* bias, float* y, int M, int K, int N,
+                                      int act, float act_param, void* stream) {
+    return dense_small_fwd<float>(x, w, bias, y, M, K, N, act, act_param, stream);
+}
+extern "C" int gn_dense_small_dgrad_f32(const float* dy, const float* w, const float* x_in, float* dx, float* dx_colsum,
+                                        int colsum_channels, int M, int K, int N, int in_act, float in_act_param,
+                                        void* stream) {
+    return dense_small_dgrad<float>(dy, w, x_in, dx, dx_colsum, colsum_channels, M, K, N, in_act, in_act_param, stream);
+}
+extern "C" int gn_dense_small_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int M, int K, int N,
+                                        void* stream) {
+    return dense_small_wgrad<float>(x, dy, dw, db, M, K, N, stream);
 }
 
 extern "C" int gn_act_bwd_bf16(const void* dy, const void* y, void* dx, long long n, int act, float param, void* stream) {

@@ -1,6 +1,7 @@
-// BatchNormalization -> activation -> dropout chains on bf16 activations (throughput mode of the generator,
-// bbhMahoGANy.py:235-289: every hidden layer is Conv1D/Dense -> BatchNormalization(momentum) -> tanh -> Dropout).
-// In float32 mode each of those layers is its own exact kernel; here the chain is three streaming passes:
+// BatchNormalization -> activation -> dropout chains (generator, bbhMahoGANy.py:235-289: every hidden layer is
+// Conv1D/Dense -> BatchNormalization(momentum) -> tanh -> Dropout) as three streaming passes, for bf16 activations
+// (throughput mode) and for float32 activations (float32 / split-operand modes: libm-accurate activations, statistics
+// accumulated in double from the first element on):
 //   forward :  per-channel sum / sum of squares of x (one pass)  ->  y = drop(act(gamma * xhat + beta))  (one pass)
 //   backward:  g = dy * drop' * act'(a) recomputed from x;  per-channel sum g, sum g*xhat (one pass)  ->
 //              dx = gamma * invstd * (g - sum_g/n - xhat * sum_gxhat/n), dgamma, dbeta (one pass)
@@ -11,6 +12,8 @@
 #include "philox.cuh"
 
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 namespace gn {
 
@@ -45,11 +48,20 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
     for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
     *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
 }
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
 
 // Activation in the bf16 chain: the result is rounded to 8 mantissa bits, so tanh / sigmoid use the SFU approximations
 // (tanh.approx.f32: ~2^-11 relative error) instead of the multi-instruction libm forms.
-template <int KIND>
+template <int KIND, bool EXACT>
 __device__ __forceinline__ float chain_act(float h, float p) {
+    if (EXACT) return act_fwd_t<KIND>(h, p);          // float32 activations: the same libm forms as the per-layer kernels
     if (KIND == GN_ACT_TANH) {
         float y;
         asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(h));
@@ -125,18 +137,20 @@ __device__ __forceinline__ void channel_affine(const ChainArgs& a, int c0, float
 
 // ---- statistics: sums (2C) double += (sum x, sum x^2)  [caller zeroes] -------------------------------------------------
 // block = (channel groups) x (row lanes); the lanes of a block are folded in shared memory before the double atomics
-template <bool BWD, int KIND>
-__global__ void __launch_bounds__(256) chain_sums_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+template <bool BWD, int KIND, typename T>
+__global__ void __launch_bounds__(256) chain_sums_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                          ChainArgs a, long long rows, int C, int gpb, long long rows_per_block,
                                                          double* __restrict__ sums) {
-    __shared__ float sm[2][256][9];
+    constexpr bool EXACT = sizeof(T) == 4;
+    typedef typename std::conditional<EXACT, double, float>::type Acc;      // per-thread partial sums
+    __shared__ Acc sm[2][256][9];
     const int g = threadIdx.x % gpb, rl = threadIdx.x / gpb, nrl = blockDim.x / gpb;
     const int cg = blockIdx.x * gpb + g;                 // channel group (8 channels)
     const bool live = cg < C / 8 && rl < nrl;
     const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-    float s0[8], s1[8];
+    Acc s0[8], s1[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+    for (int e = 0; e < 8; ++e) s0[e] = s1[e] = (Acc)0;
     if (live) {
         float mu[8], is[8], sc[8], sh[8];
         if (BWD) channel_affine(a, cg * 8, mu, is, sc, sh);
@@ -147,8 +161,8 @@ __global__ void __launch_bounds__(256) chain_sums_kernel(const __nv_bfloat16* __
             if (!BWD) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    s0[e] += xv[e];
-                    s1[e] = fmaf(xv[e], xv[e], s1[e]);
+                    s0[e] += (Acc)xv[e];
+                    s1[e] += (Acc)xv[e] * (Acc)xv[e];
                 }
             } else {
                 float gv[8], nf[8];
@@ -156,10 +170,10 @@ __global__ void __launch_bounds__(256) chain_sums_kernel(const __nv_bfloat16* __
                 noise_factors(a, i0, nf);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float av = chain_act<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
+                    const float av = chain_act<KIND, EXACT>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
                     const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
-                    s0[e] += gg;
-                    s1[e] = fmaf(gg, (xv[e] - mu[e]) * is[e], s1[e]);
+                    s0[e] += (Acc)gg;
+                    s1[e] += (Acc)gg * (Acc)((xv[e] - mu[e]) * is[e]);
                 }
             }
         }
@@ -185,9 +199,10 @@ __global__ void __launch_bounds__(256) chain_sums_kernel(const __nv_bfloat16* __
 // A thread keeps ONE channel group for its whole life (its per-channel affine is computed once) and walks the rows
 // with a stride of `lanes` = (threads of the grid) / (C/8); consecutive threads hold consecutive channel groups, so
 // every access of a warp is a contiguous 512-byte run of a row.
-template <int KIND>
-__global__ void __launch_bounds__(256) chain_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+template <int KIND, typename T>
+__global__ void __launch_bounds__(256) chain_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                         ChainArgs a, long long rows, int C, long long lanes) {
+    constexpr bool EXACT = sizeof(T) == 4;
     const int C8 = C / 8;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = (int)(tid % C8);
@@ -202,16 +217,17 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const __nv_bfloat16* __r
         load8(x + i0, xv);
         noise_factors(a, i0, nf);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = chain_act<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param) * nf[e];
+        for (int e = 0; e < 8; ++e) o[e] = chain_act<KIND, EXACT>(fmaf(xv[e], sc[e], sh[e]), a.act_param) * nf[e];
         store8(y + i0, o);
     }
 }
 
 // ---- backward apply: dx = sc * (g - sum_g/n - xhat * sum_gxhat/n);  without normalisation dx = g ---------------------
-template <int KIND>
-__global__ void __launch_bounds__(256) chain_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                        __nv_bfloat16* __restrict__ dx, ChainArgs a, const double* __restrict__ sums,
+template <int KIND, typename T>
+__global__ void __launch_bounds__(256) chain_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                        T* __restrict__ dx, ChainArgs a, const double* __restrict__ sums,
                                                         double n_total, long long rows, int C, long long lanes) {
+    constexpr bool EXACT = sizeof(T) == 4;
     const int C8 = C / 8;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = (int)(tid % C8);
@@ -234,7 +250,7 @@ __global__ void __launch_bounds__(256) chain_bwd_kernel(const __nv_bfloat16* __r
         noise_factors(a, i0, nf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float av = chain_act<KIND>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
+            const float av = chain_act<KIND, EXACT>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
             const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
             o[e] = bn ? sc[e] * (gg - m0[e] - (xv[e] - mu[e]) * is[e] * m1[e]) : gg;
         }
@@ -305,7 +321,8 @@ static int make_chain(ChainArgs* a, const float* mean, const float* scale, const
 
 using namespace gn;
 
-extern "C" int gn_bn_stats_bf16(const void* x, long long rows, int C, double* sums, void* stream) {
+template <typename T>
+static int bn_stats_t(const T* x, long long rows, int C, double* sums, void* stream) {
     GN_REQUIRE(x && sums && rows >= 0 && C > 0 && C % 8 == 0, "null pointer or bad size (C % 8 == 0)");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st);
@@ -313,13 +330,14 @@ extern "C" int gn_bn_stats_bf16(const void* x, long long rows, int C, double* su
     int gpb; dim3 grid; long long rpb;
     sums_geometry(rows, C, &gpb, &grid, &rpb);
     ChainArgs a{};
-    chain_sums_kernel<false, GN_ACT_NONE><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, a, rows, C, gpb, rpb, sums);
+    chain_sums_kernel<false, GN_ACT_NONE, T><<<grid, 256, 0, st>>>(x, nullptr, a, rows, C, gpb, rpb, sums);
     return cuda_status("chain_sums_kernel");
 }
 
-extern "C" int gn_chain_fwd_bf16(const void* x, void* y, const float* mean, const float* scale, const float* gamma,
-                                 const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
-                                 const float* r, uint64_t seed, uint64_t offset, long long rows, int C, void* stream) {
+template <typename T>
+static int chain_fwd_t(const T* x, T* y, const float* mean, const float* scale, const float* gamma, const float* beta,
+                       int use_var, float eps, int act, float act_param, int noise, float rate, const float* r, uint64_t seed,
+                       uint64_t offset, long long rows, int C, void* stream) {
     GN_REQUIRE(x && y && rows >= 0, "null pointer or rows < 0");
     ChainArgs a{};
     int rc = make_chain(&a, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, C);
@@ -328,13 +346,14 @@ extern "C" int gn_chain_fwd_bf16(const void* x, void* y, const float* mean, cons
     unsigned grid; long long lanes;
     apply_geometry(rows, C, &grid, &lanes);
     cudaStream_t st = as_stream(stream);
-    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, a, rows, C, lanes)));
+    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, y, a, rows, C, lanes)));
     return cuda_status("chain_fwd_kernel");
 }
 
-extern "C" int gn_chain_bwd_sums_bf16(const void* x, const void* dy, const float* mean, const float* invstd, const float* gamma,
-                                      const float* beta, int act, float act_param, int noise, float rate, const float* r,
-                                      uint64_t seed, uint64_t offset, long long rows, int C, double* sums, void* stream) {
+template <typename T>
+static int chain_bwd_sums_t(const T* x, const T* dy, const float* mean, const float* invstd, const float* gamma,
+                            const float* beta, int act, float act_param, int noise, float rate, const float* r, uint64_t seed,
+                            uint64_t offset, long long rows, int C, double* sums, void* stream) {
     GN_REQUIRE(x && dy && mean && invstd && sums && rows >= 0, "null pointer or rows < 0");
     ChainArgs a{};
     int rc = make_chain(&a, mean, invstd, gamma, beta, 0, 0.f, act, act_param, noise, rate, r, seed, offset, C);
@@ -344,15 +363,15 @@ extern "C" int gn_chain_bwd_sums_bf16(const void* x, const void* dy, const float
     if (rows == 0) return GN_OK;
     int gpb; dim3 grid; long long rpb;
     sums_geometry(rows, C, &gpb, &grid, &rpb);
-    GN_CHAIN_DISPATCH((chain_sums_kernel<true, K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, a, rows,
-                                                                       C, gpb, rpb, sums)));
+    GN_CHAIN_DISPATCH((chain_sums_kernel<true, K_, T><<<grid, 256, 0, st>>>(x, dy, a, rows, C, gpb, rpb, sums)));
     return cuda_status("chain_sums_kernel(bwd)");
 }
 
-extern "C" int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const float* mean, const float* invstd,
-                                 const float* gamma, const float* beta, const double* sums, double n_total, int act,
-                                 float act_param, int noise, float rate, const float* r, uint64_t seed, uint64_t offset,
-                                 float* dgamma, float* dbeta, long long rows, int C, void* stream) {
+template <typename T>
+static int chain_bwd_t(const T* x, const T* dy, T* dx, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, const double* sums, double n_total, int act, float act_param, int noise, float rate,
+                       const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta, long long rows, int C,
+                       void* stream) {
     GN_REQUIRE(x && dy && dx && rows >= 0, "null pointer or rows < 0");
     GN_REQUIRE(mean == nullptr || (invstd && sums && n_total > 0), "normalisation needs invstd, sums and n_total");
     ChainArgs a{};
@@ -362,10 +381,59 @@ extern "C" int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const 
     if (rows > 0) {
         unsigned grid; long long lanes;
         apply_geometry(rows, C, &grid, &lanes);
-        GN_CHAIN_DISPATCH((chain_bwd_kernel<K_><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
-                                                                    (__nv_bfloat16*)dx, a, sums, n_total, rows, C, lanes)));
+        GN_CHAIN_DISPATCH((chain_bwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, dy, dx, a, sums, n_total, rows, C, lanes)));
     }
     if (mean != nullptr && (dgamma || dbeta))
         chain_param_grads_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, dgamma, dbeta, C);
     return cuda_status("chain_bwd_kernel");
+}
+
+typedef __nv_bfloat16 bf16_t;
+
+extern "C" int gn_bn_stats_bf16(const void* x, long long rows, int C, double* sums, void* stream) {
+    return bn_stats_t<bf16_t>((const bf16_t*)x, rows, C, sums, stream);
+}
+extern "C" int gn_chain_fwd_bf16(const void* x, void* y, const float* mean, const float* scale, const float* gamma,
+                                 const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
+                                 const float* r, uint64_t seed, uint64_t offset, long long rows, int C, void* stream) {
+    return chain_fwd_t<bf16_t>((const bf16_t*)x, (bf16_t*)y, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate,
+                               r, seed, offset, rows, C, stream);
+}
+extern "C" int gn_chain_bwd_sums_bf16(const void* x, const void* dy, const float* mean, const float* invstd, const float* gamma,
+                                      const float* beta, int act, float act_param, int noise, float rate, const float* r,
+                                      uint64_t seed, uint64_t offset, long long rows, int C, double* sums, void* stream) {
+    return chain_bwd_sums_t<bf16_t>((const bf16_t*)x, (const bf16_t*)dy, mean, invstd, gamma, beta, act, act_param, noise, rate, r,
+                                    seed, offset, rows, C, sums, stream);
+}
+extern "C" int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, const double* sums, double n_total, int act,
+                                 float act_param, int noise, float rate, const float* r, uint64_t seed, uint64_t offset,
+                                 float* dgamma, float* dbeta, long long rows, int C, void* stream) {
+    return chain_bwd_t<bf16_t>((const bf16_t*)x, (const bf16_t*)dy, (bf16_t*)dx, mean, invstd, gamma, beta, sums, n_total, act,
+                               act_param, noise, rate, r, seed, offset, dgamma, dbeta, rows, C, stream);
+}
+
+// float32 activations: same arguments, every activation tensor is float*
+extern "C" int gn_bn_sums_f32(const float* x, long long rows, int C, double* sums, void* stream) {
+    return bn_stats_t<float>(x, rows, C, sums, stream);
+}
+extern "C" int gn_chain_fwd_f32(const float* x, float* y, const float* mean, const float* scale, const float* gamma,
+                                const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
+                                const float* r, uint64_t seed, uint64_t offset, long long rows, int C, void* stream) {
+    return chain_fwd_t<float>(x, y, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, rows, C,
+                              stream);
+}
+extern "C" int gn_chain_bwd_sums_f32(const float* x, const float* dy, const float* mean, const float* invstd,
+                                     const float* gamma, const float* beta, int act, float act_param, int noise, float rate,
+                                     const float* r, uint64_t seed, uint64_t offset, long long rows, int C, double* sums,
+                                     void* stream) {
+    return chain_bwd_sums_t<float>(x, dy, mean, invstd, gamma, beta, act, act_param, noise, rate, r, seed, offset, rows, C, sums,
+                                   stream);
+}
+extern "C" int gn_chain_bwd_f32(const float* x, const float* dy, float* dx, const float* mean, const float* invstd,
+                                const float* gamma, const float* beta, const double* sums, double n_total, int act,
+                                float act_param, int noise, float rate, const float* r, uint64_t seed, uint64_t offset,
+                                float* dgamma, float* dbeta, long long rows, int C, void* stream) {
+    return chain_bwd_t<float>(x, dy, dx, mean, invstd, gamma, beta, sums, n_total, act, act_param, noise, rate, r, seed, offset,
+                              dgamma, dbeta, rows, C, stream);
 }

@@ -22,7 +22,7 @@ from ._lib import call, ptr, stream
 # ----------------------------------------------------------------------------- session state
 _NAME_COUNTS = {}
 _STATE = {'seed': 1234, 'noise_counter': 0, 'init_rng': np.random.RandomState(1234), 'dp': None,
-          'dtype': 'float32', 'wver': 0, 'bn_zero_debias': True}
+          'dtype': 'float32', 'wver': 0, 'bn_zero_debias': True, 'f32_chain': True}
 
 
 def clear_session():
@@ -292,9 +292,15 @@ class Dense(Layer):
     def forward(self, x, ctx):
         B, K = x.shape
         y = _empty((B, self.units))
+        # <= 4 outputs over a long feature vector: the streaming GEMV kernels (bf16 or float32 features)
         self._bf16 = x.dtype == BF16 and self.units <= 4 and K % 8 == 0
+        self._small32 = x.dtype == torch.float32 and self.units <= 4 and K % 8 == 0 and K >= 1024
         if self._bf16:
             call('gn_dense_small_fwd_bf16', ptr(x, BF16), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B,
+                 K, self.units, _ACTS[self.activation], 0.0, stream())
+        elif self._small32:
+            x = x.contiguous()
+            call('gn_dense_small_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B,
                  K, self.units, _ACTS[self.activation], 0.0, stream())
         else:
             x = _as_f32(x)
@@ -311,15 +317,16 @@ class Dense(Layer):
             dy = _act_bwd(dy, self._y, _ACTS[self.activation], 0.0)
         tr = id(self) in ctx.trainable_ids
         dx = None
-        if self._bf16:
+        if self._bf16 or self._small32:
+            sfx, dt = ('_bf16', BF16) if self._bf16 else ('_f32', torch.float32)
             if tr:
-                call('gn_dense_small_wgrad_bf16', ptr(x, BF16), ptr(dy), ptr(self.params[0].grad),
+                call('gn_dense_small_wgrad' + sfx, ptr(x, dt), ptr(dy), ptr(self.params[0].grad),
                      ptr(self.params[1].grad), B, K, self.units, stream())
             if need_dx:
-                dx = _empty_bf16((B, K))
+                dx = _empty_bf16((B, K)) if self._bf16 else _empty((B, K))
                 code, par = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
                 sink, C = _bias_sink(self, ctx, K)
-                call('gn_dense_small_dgrad_bf16', ptr(dy), ptr(self.params[0].data), ptr(x, BF16), ptr(dx, BF16), sink, C, B, K,
+                call('gn_dense_small_dgrad' + sfx, ptr(dy), ptr(self.params[0].data), ptr(x, dt), ptr(dx, dt), sink, C, B, K,
                      self.units, code, par, stream())
                 dx._gn_preact = self.in_act is not None
                 dx._gn_db_done = sink is not None
@@ -380,9 +387,15 @@ class Conv1D(Layer):
         L, cin = self.input_shape
         co = self.filters
         tiles = cin % 64 == 0 and co % 64 == 0 and (cin % 128 == 0 or (cin == 64 and co % 128 == 0))
-        if _split_planes():
-            return 'tc3' if (tiles and self.k <= 8 and self.s <= 2) else 'f32'
-        if _STATE['dtype'] != 'bfloat16' or self.k > 8 or self.s > 2:
+        # bandwidth-bound edge layers (first convolution Cin <= 2, last convolution Cout = 1): streaming kernels
+        edge_in = self.fused_up == 1 and cin <= 2 and (co in (8, 16, 32, 64) or (co % 128 == 0 and co <= 1024)) and self.k <= 5
+        edge_out = self.fused_up == 1 and co == 1 and self.s == 1 and self.k <= 5 and cin % 8 == 0 and \
+            self._act()[0] == _lib.ACT_NONE
+        if _STATE['dtype'] != 'bfloat16':
+            if _split_planes() and tiles and self.k <= 8 and self.s <= 2:
+                return 'tc3'
+            return 'smallcin32' if edge_in else ('cout1_32' if edge_out else 'f32')
+        if self.k > 8 or self.s > 2:
             return 'f32'
         if tiles:
             return 'tc'          # a fused UpSampling1D(2) is materialised in bf16 first (cheap next to the GEMM)
@@ -507,6 +520,16 @@ class Conv1D(Layer):
             y = _empty((B, self.Lout, 1))
             call('gn_conv1d_cout1_fwd_bf16', ptr(x, BF16), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B,
                  L, cin, self.Lout, self.k, self.pad, stream())
+        elif self._mode == 'cout1_32':
+            x = _as_f32(x).contiguous()
+            y = _empty((B, self.Lout, 1))
+            call('gn_conv1d_cout1_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y), B,
+                 L, cin, self.Lout, self.k, self.pad, stream())
+        elif self._mode == 'smallcin32':
+            x = _as_f32(x).contiguous()
+            y = _empty((B, self.Lout, self.filters))
+            call('gn_conv1d_smallcin_fwd_f32', ptr(x), ptr(self.params[0].data), ptr(self.params[1].data), ptr(y),
+                 B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad, code, par, stream())
         elif self._mode == 'smallcin':
             x = _as_f32(x)
             y = _empty_bf16((B, self.Lout, self.filters))
@@ -553,15 +576,25 @@ class Conv1D(Layer):
                     dx = dxp
                 dx._gn_preact = self.in_act is not None
                 dx._gn_db_done = sink is not None
-        elif self._mode == 'cout1':
+        elif self._mode in ('cout1', 'cout1_32'):
+            sfx, dt = ('_bf16', BF16) if self._mode == 'cout1' else ('_f32', torch.float32)
             dy = _as_f32(dy).contiguous()
             if tr:
-                call('gn_conv1d_cout1_wgrad_bf16', ptr(x, BF16), ptr(dy), ptr(self.params[0].grad),
+                call('gn_conv1d_cout1_wgrad' + sfx, ptr(x, dt), ptr(dy), ptr(self.params[0].grad),
                      ptr(self.params[1].grad), B, L, cin, self.Lout, self.k, self.pad, stream())
             if need_dx:
-                dx = _empty_bf16(x.shape)
-                call('gn_conv1d_cout1_dgrad_bf16', ptr(dy), ptr(self.params[0].data), ptr(dx, BF16), B, L, cin, self.Lout,
+                dx = _empty_bf16(x.shape) if self._mode == 'cout1' else _empty(x.shape)
+                call('gn_conv1d_cout1_dgrad' + sfx, ptr(dy), ptr(self.params[0].data), ptr(dx, dt), B, L, cin, self.Lout,
                      self.k, self.pad, stream())
+        elif self._mode == 'smallcin32':
+            dy = _as_f32(dy.contiguous())
+            if tr:
+                call('gn_conv1d_smallcin_wgrad_f32', ptr(x), ptr(dy), ptr(self.params[0].grad),
+                     ptr(self.params[1].grad), B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad, stream())
+            if need_dx:
+                dx = _empty(x.shape)
+                call('gn_conv1d_smallcin_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, L, cin,
+                     self.Lout, self.filters, self.k, self.s, self.pad, stream())
         elif self._mode == 'smallcin':
             dy = _as_bf16(dy.contiguous())
             if tr:
@@ -632,9 +665,12 @@ class Conv2D(Layer):
         H, W, cin = self.input_shape
         c1, c2 = 2 * cin, 2 * self.filters
         tiles = c1 % 64 == 0 and c2 % 64 == 0 and (c1 % 128 == 0 or (c1 == 64 and c2 % 128 == 0))
-        if _split_planes():
-            return 'tc3' if (tiles and self.kh <= 8 and self.sh <= 2) else 'f32'
-        if _STATE['dtype'] != 'bfloat16' or self.kh > 8 or self.sh > 2:
+        edge_in = c1 == 2 and c2 % 128 == 0 and c2 <= 1024 and self.kh <= 5
+        if _STATE['dtype'] != 'bfloat16':
+            if _split_planes() and tiles and self.kh <= 8 and self.sh <= 2:
+                return 'tc3'
+            return 'smallcin32' if edge_in else 'f32'
+        if self.kh > 8 or self.sh > 2:
             return 'f32'
         if tiles:
             return 'tc'
@@ -685,12 +721,17 @@ class Conv2D(Layer):
             y = _empty_bf16((B, self.Lout, 2, self.filters))
             call('gn_conv1d_fwd_bf16', ptr(x, BF16), ptr(wt, BF16), ptr(b1), ptr(y, BF16), B, H, c1, self.Lout, c2,
                  self.kh, self.sh, self.pad, code, par, stream())
-        elif self._mode == 'smallcin':
+        elif self._mode in ('smallcin', 'smallcin32'):
             x = _as_f32(x).contiguous()
             w1, b1 = self._pack()
-            y = _empty_bf16((B, self.Lout, 2, self.filters))
-            call('gn_conv1d_smallcin_fwd_bf16', ptr(x), ptr(w1), ptr(b1), ptr(y, BF16), B, H, c1, self.Lout, c2, self.kh,
-                 self.sh, self.pad, code, par, stream())
+            if self._mode == 'smallcin':
+                y = _empty_bf16((B, self.Lout, 2, self.filters))
+                call('gn_conv1d_smallcin_fwd_bf16', ptr(x), ptr(w1), ptr(b1), ptr(y, BF16), B, H, c1, self.Lout, c2, self.kh,
+                     self.sh, self.pad, code, par, stream())
+            else:
+                y = _empty((B, self.Lout, 2, self.filters))
+                call('gn_conv1d_smallcin_fwd_f32', ptr(x), ptr(w1), ptr(b1), ptr(y), B, H, c1, self.Lout, c2, self.kh,
+                     self.sh, self.pad, code, par, stream())
         else:
             x = _as_f32(x).contiguous()
             w1, b1 = self._pack()
@@ -737,14 +778,15 @@ class Conv2D(Layer):
                 dx = _empty_bf16(x.shape)
                 call('gn_conv1d_dgrad_bf16', ptr(dy, BF16), ptr(wk, BF16), None, ptr(dx, BF16), None, B, H, c1, self.Lout,
                      c2, self.kh, self.sh, self.pad, _lib.ACT_NONE, 0.0, stream())
-        elif self._mode == 'smallcin':
-            dy = _as_bf16(dy.contiguous())
+        elif self._mode in ('smallcin', 'smallcin32'):
+            sfx, dt = ('_bf16', BF16) if self._mode == 'smallcin' else ('_f32', torch.float32)
+            dy = _as_bf16(dy.contiguous()) if self._mode == 'smallcin' else _as_f32(dy.contiguous())
             if tr:
-                call('gn_conv1d_smallcin_wgrad_bf16', ptr(x), ptr(dy, BF16), ptr(dw1), ptr(db1), B, H, c1, self.Lout, c2,
+                call('gn_conv1d_smallcin_wgrad' + sfx, ptr(x), ptr(dy, dt), ptr(dw1), ptr(db1), B, H, c1, self.Lout, c2,
                      self.kh, self.sh, self.pad, stream())
             if need_dx:
                 dx = _empty(x.shape)
-                call('gn_conv1d_smallcin_dgrad_bf16', ptr(dy, BF16), ptr(w1), ptr(dx), B, H, c1, self.Lout, c2, self.kh,
+                call('gn_conv1d_smallcin_dgrad' + sfx, ptr(dy, dt), ptr(w1), ptr(dx), B, H, c1, self.Lout, c2, self.kh,
                      self.sh, self.pad, stream())
         else:
             dy = _as_f32(dy.contiguous())
@@ -878,26 +920,28 @@ class BatchNormalization(Layer):
         kind, rate = (noise.kind, noise.rate) if (noise is not None and ctx.training) else (-1, 0.0)
         return code, par, kind, rate
 
-    def _forward_bf16(self, x, ctx):
-        """bf16 throughput mode: statistics in one pass, then y = drop(act(bn(x))) in one pass (gn_chain_*_bf16); the
-        activation and dropout layers of the chain become pass-throughs for this call."""
+    def _forward_chain(self, x, ctx):
+        """Chain kernels (bf16 or float32 activations): statistics in one pass, then y = drop(act(bn(x))) in one pass
+        (gn_chain_*); the activation and dropout layers of the chain become pass-throughs for this call."""
         C = x.shape[-1]
         rows = x.numel() // C
+        dt = x.dtype
+        sfx = '_bf16' if dt == BF16 else '_f32'
         g, b, mm, mv = [p.data for p in self.params]
         act, noise = self.chain
         for l in (act, noise):
             if l is not None:
                 l._chain_skip = True
         code, par, kind, rate = self._chain_codes(ctx)
-        y = _empty_bf16(x.shape)
+        y = torch.empty(x.shape, dtype=dt, device=x.device)
         if not ctx.training:
-            call('gn_chain_fwd_bf16', ptr(x, BF16), ptr(y, BF16), ptr(mm), ptr(mv), ptr(g), ptr(b), 1, self.epsilon, code,
+            call('gn_chain_fwd' + sfx, ptr(x, dt), ptr(y, dt), ptr(mm), ptr(mv), ptr(g), ptr(b), 1, self.epsilon, code,
                  par, -1, 0.0, None, 0, 0, rows, C, stream())
             return y
         sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
         stats = _empty((2 * C,))
         n_total = float(rows * ctx.world)
-        call('gn_bn_stats_bf16', ptr(x, BF16), rows, C, ptr(sums, torch.float64), stream())
+        call('gn_bn_stats_bf16' if dt == BF16 else 'gn_bn_sums_f32', ptr(x, dt), rows, C, ptr(sums, torch.float64), stream())
         if ctx.world > 1:
             ctx.dp.all_reduce(sums)
         # centred second moment from the raw one (double): sum (x-mean)^2 = sum x^2 - (sum x)^2 / n
@@ -915,28 +959,30 @@ class BatchNormalization(Layer):
                 off = _STATE['noise_counter'] + ((ctx.dp.rank << 48) if ctx.dp is not None else 0)
                 _STATE['noise_counter'] += (n + 3) // 4 * 4
                 seed = _STATE['seed']
-        call('gn_chain_fwd_bf16', ptr(x, BF16), ptr(y, BF16), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), 0,
+        call('gn_chain_fwd' + sfx, ptr(x, dt), ptr(y, dt), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), 0,
              self.epsilon, code, par, kind, rate, ptr(r) if r is not None else None, seed, off, rows, C, stream())
         self._x, self._stats, self._n = x, stats, n_total
         self._chain_state = (code, par, kind, rate, r, seed, off)
         return y
 
-    def _backward_bf16(self, dy, ctx):
+    def _backward_chain(self, dy, ctx):
         x, stats = self._x, self._stats
         C = x.shape[-1]
         rows = x.numel() // C
+        dt = x.dtype
+        sfx = '_bf16' if dt == BF16 else '_f32'
         code, par, kind, rate, r, seed, off = self._chain_state
-        dy = _as_bf16(dy.contiguous()).reshape(x.shape)
+        dy = (_as_bf16(dy.contiguous()) if dt == BF16 else _as_f32(dy).contiguous()).reshape(x.shape)
         g, b = self.params[0].data, self.params[1].data
         rp = ptr(r) if r is not None else None
         sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
-        call('gn_chain_bwd_sums_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), code,
+        call('gn_chain_bwd_sums' + sfx, ptr(x, dt), ptr(dy, dt), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), code,
              par, kind, rate, rp, seed, off, rows, C, ptr(sums, torch.float64), stream())
         if ctx.world > 1:
             ctx.dp.all_reduce(sums)
-        dx = _empty_bf16(x.shape)
+        dx = torch.empty(x.shape, dtype=dt, device=x.device)
         tr = id(self) in ctx.trainable_ids
-        call('gn_chain_bwd_bf16', ptr(x, BF16), ptr(dy, BF16), ptr(dx, BF16), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b),
+        call('gn_chain_bwd' + sfx, ptr(x, dt), ptr(dy, dt), ptr(dx, dt), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b),
              ptr(sums, torch.float64), self._n, code, par, kind, rate, rp, seed, off,
              ptr(self.params[0].grad) if tr else None, ptr(self.params[1].grad) if tr else None, rows, C, stream())
         if tr and ctx.world > 1:
@@ -949,10 +995,10 @@ class BatchNormalization(Layer):
         for l in self.chain:
             if l is not None:
                 l._chain_skip = False
-        self._fused_call = x.dtype == BF16 and x.shape[-1] % 8 == 0 and \
+        self._fused_call = x.shape[-1] % 8 == 0 and (x.dtype == BF16 or _STATE['f32_chain']) and \
             not any(isinstance(l, GaussianNoise) for l in self.chain if l is not None)
         if self._fused_call:
-            return self._forward_bf16(x.contiguous(), ctx)
+            return self._forward_chain(x.contiguous(), ctx)
         x = _as_f32(x)
         C = x.shape[-1]
         rows = x.numel() // C
@@ -981,7 +1027,7 @@ class BatchNormalization(Layer):
 
     def backward(self, dy, ctx, need_dx=True):
         if getattr(self, '_fused_call', False):
-            return self._backward_bf16(dy, ctx)
+            return self._backward_chain(dy, ctx)
         dy = _as_f32(dy)
         x, stats = self._x, self._stats
         C = x.shape[-1]
@@ -1071,9 +1117,11 @@ class _NoiseLayer(Layer):
         if not ctx.training or self._chain_skip:
             self._r = None
             return x
-        if x.dtype == BF16 and x.shape[-1] % 8 == 0 and self.kind != _lib.NOISE_GNOISE:
-            # bf16 throughput mode: y = x * factor with the mask recomputed from the Philox counter in backward
+        if (x.dtype == BF16 or _STATE['f32_chain']) and x.shape[-1] % 8 == 0 and self.kind != _lib.NOISE_GNOISE:
+            # chain kernel: y = x * factor with the mask recomputed from the Philox counter in backward (never stored)
             x = x.contiguous()
+            dt = x.dtype
+            sfx = '_bf16' if dt == BF16 else '_f32'
             C = x.shape[-1]
             rows = x.numel() // C
             fed = ctx.noise.get(self.name)
@@ -1084,10 +1132,10 @@ class _NoiseLayer(Layer):
                 off = _STATE['noise_counter'] + ((ctx.dp.rank << 48) if ctx.dp is not None else 0)
                 _STATE['noise_counter'] += (x.numel() + 3) // 4 * 4
                 seed = _STATE['seed']
-            y = _empty_bf16(x.shape)
-            call('gn_chain_fwd_bf16', ptr(x, BF16), ptr(y, BF16), None, None, None, None, 0, 0.0, _lib.ACT_NONE, 0.0,
+            y = torch.empty(x.shape, dtype=dt, device=x.device)
+            call('gn_chain_fwd' + sfx, ptr(x, dt), ptr(y, dt), None, None, None, None, 0, 0.0, _lib.ACT_NONE, 0.0,
                  self.kind, self.rate, ptr(r) if r is not None else None, seed, off, rows, C, stream())
-            self._bf16_state = (r, seed, off)
+            self._bf16_state = (r, seed, off, dt)
             self._r = None
             return y
         x = _as_f32(x)
@@ -1108,12 +1156,13 @@ class _NoiseLayer(Layer):
 
     def backward(self, dy, ctx, need_dx=True):
         if getattr(self, '_bf16_state', None) is not None and need_dx:
-            r, seed, off = self._bf16_state
-            dy = _as_bf16(dy.contiguous())
+            r, seed, off, dt = self._bf16_state
+            sfx = '_bf16' if dt == BF16 else '_f32'
+            dy = _as_bf16(dy.contiguous()) if dt == BF16 else _as_f32(dy).contiguous()
             C = dy.shape[-1]
             rows = dy.numel() // C
-            dx = _empty_bf16(dy.shape)
-            call('gn_chain_bwd_bf16', ptr(dy, BF16), ptr(dy, BF16), ptr(dx, BF16), None, None, None, None, None, 1.0,
+            dx = torch.empty(dy.shape, dtype=dt, device=dy.device)
+            call('gn_chain_bwd' + sfx, ptr(dy, dt), ptr(dy, dt), ptr(dx, dt), None, None, None, None, None, 1.0,
                  _lib.ACT_NONE, 0.0, self.kind, self.rate, ptr(r) if r is not None else None, seed, off, None, None,
                  rows, C, stream())
             self._bf16_state = None

@@ -154,6 +154,27 @@ int gn_conv1d_dgrad_bf16(const void* dy, const void* wk, const void* x_in, void*
 int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
                          int Cout, int k, int stride, int pad_left, void* stream);
 
+/* The same bandwidth-bound kernels with FLOAT32 activations (float32 and split-operand modes, whose activations are
+ * float32): identical arguments and semantics, every `void*` activation / gradient tensor above is `float*` here. */
+int gn_conv1d_smallcin_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int L, int Cin,
+                               int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param,
+                               void* stream);
+int gn_conv1d_smallcin_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
+                                 int Cout, int k, int stride, int pad_left, void* stream);
+int gn_conv1d_smallcin_dgrad_f32(const float* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int Cout,
+                                 int k, int stride, int pad_left, void* stream);
+int gn_conv1d_cout1_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int L, int Cin, int Lout,
+                            int k, int pad_left, void* stream);
+int gn_conv1d_cout1_dgrad_f32(const float* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int k,
+                              int pad_left, void* stream);
+int gn_conv1d_cout1_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
+                              int k, int pad_left, void* stream);
+int gn_dense_small_fwd_f32(const float* x, const float* w, const float* bias, float* y, int M, int K, int N, int act,
+                           float act_param, void* stream);
+int gn_dense_small_dgrad_f32(const float* dy, const float* w, const float* x_in, float* dx, float* dx_colsum,
+                             int colsum_channels, int M, int K, int N, int in_act, float in_act_param, void* stream);
+int gn_dense_small_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int M, int K, int N, void* stream);
+
 /* ---- tensor-core Conv1D at FLOAT32 accuracy: split-bf16 operands ("bf16x3") -------------------------------
  * The reference's Conv1D layers compute in float32 (bbhMahoGANy.py:250-292,362-395 through cuDNN/Eigen).  Here a
  * float32 tensor t is carried as nc bf16 planes, t = t0 + t1 (+ t2) with t0 = bf16(t), t1 = bf16(t - t0), ...,
@@ -277,6 +298,20 @@ int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const float* mean
                       const float* beta, const double* sums, double n_total, int act, float act_param, int noise,
                       float rate, const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta,
                       long long rows, int C, void* stream);
+
+/* The same chains over FLOAT32 activations (float32 / split-operand modes): libm-accurate activations, per-thread
+ * statistics in double; gn_bn_sums_f32 is the one-pass (sum x, sum x^2) form of gn_bn_stats_bf16. */
+int gn_bn_sums_f32(const float* x, long long rows, int C, double* sums, void* stream);
+int gn_chain_fwd_f32(const float* x, float* y, const float* mean, const float* scale, const float* gamma, const float* beta,
+                     int use_var, float eps, int act, float act_param, int noise, float rate, const float* r,
+                     uint64_t seed, uint64_t offset, long long rows, int C, void* stream);
+int gn_chain_bwd_sums_f32(const float* x, const float* dy, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, int act, float act_param, int noise, float rate, const float* r,
+                          uint64_t seed, uint64_t offset, long long rows, int C, double* sums, void* stream);
+int gn_chain_bwd_f32(const float* x, const float* dy, float* dx, const float* mean, const float* invstd, const float* gamma,
+                     const float* beta, const double* sums, double n_total, int act, float act_param, int noise,
+                     float rate, const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta,
+                     long long rows, int C, void* stream);
 
 /* elementwise */
 int gn_act_fwd_f32(const float* x, float* y, long long n, int act, float param, void* stream);

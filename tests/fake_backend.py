@@ -100,6 +100,95 @@ class Fake:
         if db is not None:
             db.copy_(dy.reshape(-1, Cout).sum(0))
 
+    # bandwidth-bound edge layers with float32 activations: same maths as the generic kernels
+    def gn_conv1d_smallcin_fwd_f32(self, x, w, b, y, B, L, Cin, Lout, Cout, k, s, p, act, ap, st):
+        self.gn_conv1d_fwd_f32(x, w, b, y, B, L, Cin, Lout, Cout, k, s, p, 1, act, ap, st)
+
+    def gn_conv1d_smallcin_wgrad_f32(self, x, dy, dw, db, B, L, Cin, Lout, Cout, k, s, p, st):
+        self.gn_conv1d_wgrad_f32(x, dy, dw, db, B, L, Cin, Lout, Cout, k, s, p, 1, st)
+
+    def gn_conv1d_smallcin_dgrad_f32(self, dy, w, dx, B, L, Cin, Lout, Cout, k, s, p, st):
+        self.gn_conv1d_dgrad_f32(dy, w, dx, B, L, Cin, Lout, Cout, k, s, p, 1, st)
+
+    def gn_conv1d_cout1_fwd_f32(self, x, w, b, y, B, L, Cin, Lout, k, p, st):
+        self.gn_conv1d_fwd_f32(x, w, b, y, B, L, Cin, Lout, 1, k, 1, p, 1, 0, 0.0, st)
+
+    def gn_conv1d_cout1_dgrad_f32(self, dy, w, dx, B, L, Cin, Lout, k, p, st):
+        self.gn_conv1d_dgrad_f32(dy, w, dx, B, L, Cin, Lout, 1, k, 1, p, 1, st)
+
+    def gn_conv1d_cout1_wgrad_f32(self, x, dy, dw, db, B, L, Cin, Lout, k, p, st):
+        self.gn_conv1d_wgrad_f32(x, dy, dw, db, B, L, Cin, Lout, 1, k, 1, p, 1, st)
+
+    def gn_dense_small_fwd_f32(self, x, w, b, y, M, K, N, act, ap, st):
+        self.gn_dense_fwd_f32(x, w, b, y, M, K, N, act, ap, st)
+
+    def gn_dense_small_wgrad_f32(self, x, dy, dw, db, M, K, N, st):
+        self.gn_dense_wgrad_f32(x, dy, dw, db, M, K, N, st)
+
+    def gn_dense_small_dgrad_f32(self, dy, w, xin, dx, colsum, C, M, K, N, in_act, ap, st):
+        g = dy.reshape(M, N) @ w.reshape(K, N).t()
+        if xin is not None and in_act != 0:
+            g = g * _act_bwd(xin.reshape(M, K), in_act, ap)
+        dx.reshape(M, K).copy_(g)
+        if colsum is not None:
+            colsum[:C] = g.reshape(M, K // C, C).sum((0, 1))
+
+    # BatchNormalization -> activation -> dropout chains over float32 activations (gn_chain_*_f32)
+    def _chain_noise(self, kind, rate, r, seed, off, shape):
+        if kind < 0:
+            return torch.ones(shape)
+        if r is None:      # stand-in for the device Philox stream: any draw that is identical in forward and backward
+            g = torch.Generator().manual_seed((int(seed) * 1000003 + int(off)) % (2 ** 63))
+            r = torch.rand(shape, generator=g) if kind == 0 else torch.randn(shape, generator=g)
+            if kind == 0:
+                r = (r >= rate).float()
+        r = r.reshape(shape)
+        if kind == 0:
+            return r / (1.0 - rate)
+        return 1.0 + r * math.sqrt(rate / (1.0 - rate))
+
+    def gn_bn_sums_f32(self, x, rows, C, sums, st):
+        xv = x.reshape(rows, C).double()
+        sums[:C] = xv.sum(0)
+        sums[C:] = (xv * xv).sum(0)
+
+    def _chain_pre(self, x, mean, scale, gamma, beta, use_var, eps, rows, C):
+        xv = x.reshape(rows, C)
+        if mean is None:
+            return xv, None, None
+        inv = 1.0 / torch.sqrt(scale[:C] + eps) if use_var else scale[:C]
+        g = gamma[:C] if gamma is not None else torch.ones(C)
+        b = beta[:C] if beta is not None else torch.zeros(C)
+        xhat = (xv - mean[:C]) * inv
+        return xhat * g + b, xhat, g * inv
+
+    def gn_chain_fwd_f32(self, x, y, mean, scale, gamma, beta, use_var, eps, act, ap, noise, rate, r, seed, off, rows, C, st):
+        h, _, _ = self._chain_pre(x, mean, scale, gamma, beta, use_var, eps, rows, C)
+        y.reshape(rows, C).copy_(_act(h, act, ap) * self._chain_noise(noise, rate, r, seed, off, (rows, C)))
+
+    def _chain_g(self, x, dy, mean, invstd, gamma, beta, act, ap, noise, rate, r, seed, off, rows, C):
+        h, xhat, sc = self._chain_pre(x, mean, invstd, gamma, beta, 0, 0.0, rows, C)
+        g = dy.reshape(rows, C) * self._chain_noise(noise, rate, r, seed, off, (rows, C)) * _act_bwd(_act(h, act, ap), act, ap)
+        return g, xhat, sc
+
+    def gn_chain_bwd_sums_f32(self, x, dy, mean, invstd, gamma, beta, act, ap, noise, rate, r, seed, off, rows, C, sums, st):
+        g, xhat, _ = self._chain_g(x, dy, mean, invstd, gamma, beta, act, ap, noise, rate, r, seed, off, rows, C)
+        sums[:C] = g.double().sum(0)
+        sums[C:] = (g.double() * xhat.double()).sum(0)
+
+    def gn_chain_bwd_f32(self, x, dy, dx, mean, invstd, gamma, beta, sums, n, act, ap, noise, rate, r, seed, off, dgamma, dbeta,
+                         rows, C, st):
+        g, xhat, sc = self._chain_g(x, dy, mean, invstd, gamma, beta, act, ap, noise, rate, r, seed, off, rows, C)
+        if mean is None:
+            dx.reshape(rows, C).copy_(g)
+            return
+        m0, m1 = (sums[:C] / n).float(), (sums[C:2 * C] / n).float()
+        dx.reshape(rows, C).copy_(sc * (g - m0 - xhat * m1))
+        if dbeta is not None:
+            dbeta.copy_(sums[:C].float())
+        if dgamma is not None:
+            dgamma.copy_(sums[C:2 * C].float())
+
     def gn_conv2d_w2_pack_f32(self, w2, b, w1, b1, kh, kw, Cin, Cout, pw, st):
         w2 = w2.reshape(kh, kw, Cin, Cout)
         o = torch.zeros(kh, 2, Cin, 2, Cout)

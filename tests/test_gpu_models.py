@@ -230,7 +230,7 @@ def test_pe_step_parity_bf16x3(bf16x3, n_pix, B):
     nn = bf16x3
     prod, orc, x, y = pc.pe_case(n_pix, B)
     convs = [l for l in prod.all_layers() if isinstance(l, nn.Conv1D)]
-    assert sorted(c._path() for c in convs) == ['f32'] * 2 + ['tc3'] * 7
+    assert sorted(c._path() for c in convs) == ['smallcin32'] * 2 + ['tc3'] * 7
     errs, w0 = pc.compare_step(prod, orc, x, y)
     pc.compare_weights(prod, orc, w0)
     print('bf16x3 PE n_pix %d: max gradient error %.2e' % (n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))
@@ -245,7 +245,8 @@ def test_gan_steps_parity_bf16x3(bf16x3, n_pix, B):
     nn = bf16x3
     (g, d, dg), (og, od, ocomp), z, sX, sy = pc.gan_case(n_pix, B)
     convs = [l for l in g.all_layers() if isinstance(l, nn.Conv1D)]
-    assert [c._path() for c in convs] == ['tc3', 'tc3', 'tc3', 'tc3', 'tc3', 'f32']
+    assert [c._path() for c in convs] == ['tc3', 'tc3', 'tc3', 'tc3', 'tc3', 'cout1_32']
+    assert [l._path() for l in d.all_layers() if isinstance(l, nn.Conv2D)] == ['smallcin32', 'tc3']
     pc.assert_close(g.predict(z), og.predict(z), 'generator.predict')
     errs, w0 = pc.compare_step(d, od, sX, sy)
     pc.compare_weights(d, od, w0)
