@@ -160,9 +160,9 @@ _CONV_ARGPOS = {'gn_conv1d_fwd_f32': 4, 'gn_conv1d_dgrad_f32': 3, 'gn_conv1d_wgr
                 'gn_conv1d_fwd_bf16': 4, 'gn_conv1d_dgrad_bf16': 5, 'gn_conv1d_wgrad_bf16': 4,
                 'gn_conv1d_fwd_bf16x3': 5, 'gn_conv1d_dgrad_bf16x3': 6, 'gn_conv1d_wgrad_bf16x3': 5,
                 'gn_conv1d_smallcin_fwd_bf16': 4, 'gn_conv1d_smallcin_wgrad_bf16': 4, 'gn_conv1d_smallcin_dgrad_bf16': 3,
-                'gn_conv1d_edge_fwd_f32': 4, 'gn_conv1d_edge_wgrad_f32': 4, 'gn_conv1d_edge_dgrad_f32': 3}
+                'gn_conv1d_smallcin_fwd_f32': 4, 'gn_conv1d_smallcin_wgrad_f32': 4, 'gn_conv1d_smallcin_dgrad_f32': 3}
 _DENSE_ARGPOS = {'gn_dense_fwd_f32': 4, 'gn_dense_dgrad_f32': 3, 'gn_dense_wgrad_f32': 4,
-                 'gn_dense_fwd_bf16x3': 5, 'gn_dense_dgrad_bf16x3': 4, 'gn_dense_wgrad_bf16x3': 5}
+                 'gn_dense_fwd_bf16x3': 5, 'gn_dense_dgrad_bf16x3': 5, 'gn_dense_wgrad_bf16x3': 5}
 TENSOR_CORE_CALLS = ('gn_conv1d_fwd_bf16', 'gn_conv1d_dgrad_bf16', 'gn_conv1d_wgrad_bf16', 'gn_conv1d_fwd_bf16x3',
                      'gn_conv1d_dgrad_bf16x3', 'gn_conv1d_wgrad_bf16x3', 'gn_dense_fwd_bf16x3', 'gn_dense_dgrad_bf16x3',
                      'gn_dense_wgrad_bf16x3')

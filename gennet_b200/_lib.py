@@ -46,6 +46,11 @@ _SIGS = {
     'gn_conv1d_fwd_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     'gn_conv1d_dgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     'gn_conv1d_wgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_split_pad_f32_bf16': [c_p, c_p, c_ll, c_i, c_i, c_i, c_p],
+    'gn_dense_w_split_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    'gn_dense_fwd_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    'gn_dense_dgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    'gn_dense_wgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_smallcin_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_dgrad_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -100,6 +105,7 @@ _SIGS = {
     'gn_gather_rows_f32': [c_p, c_p, c_p, c_i, c_ll, c_p],
     'gn_kde2d_pdf_f32': [c_p, c_i, c_p, c_i, c_d, c_d, c_d, c_d, c_p, c_p],
     'gn_overlap_sums_f32': [c_p, c_p, c_ll, c_p, c_p],
+    'gn_percentiles_f32': [c_p, c_i, c_i, c_p, c_i, c_p, c_p],
     'gn_maxnorm_roll_f32': [c_p, c_p, c_p, c_i, c_i, c_p],
     'gn_flip_transpose_f32': [c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_stack_residual_fwd_f32': [c_p, c_p, c_p, c_i, c_i, c_p],

@@ -212,11 +212,16 @@ def posterior_samples(generator, signal_pe, n=4000, seed=0, batch=1000, z=None):
 
 
 def waveform_percentiles(generated, percentiles=(90, 75, 25, 5)):
-    """Percentile curves of plot_waveform_est, bbhMahoGANy.py:913-921 (host NumPy, one pass instead of a Python
-    loop over time samples): generated (n, n_pix[, 1]) -> {p: (n_pix,)}."""
-    g = np.asarray(generated)
-    g = g.reshape(g.shape[0], g.shape[1])
-    vals = np.percentile(g, list(percentiles), axis=0)
+    """Percentile curves of plot_waveform_est, bbhMahoGANy.py:913-921, on the device (gn_percentiles_f32: per time
+    sample a shared-memory sort of the n generated values, np.percentile's linear interpolation) instead of the
+    reference's Python loop over time samples: generated (n, n_pix[, 1]) NumPy array or CUDA tensor -> {p: (n_pix,)}."""
+    g = generated if isinstance(generated, torch.Tensor) else nn._to_device(np.asarray(generated, dtype=np.float32))
+    g = g.to(torch.float32).reshape(g.shape[0], g.shape[1]).contiguous()
+    n, L = g.shape
+    pc = nn._to_device(np.asarray(percentiles, dtype=np.float32))
+    out = torch.empty((len(percentiles), L), dtype=torch.float32, device=g.device)
+    call('gn_percentiles_f32', ptr(g), n, L, ptr(pc), len(percentiles), ptr(out), stream())
+    vals = out.cpu().numpy()
     return {p: vals[i] for i, p in enumerate(percentiles)}
 
 

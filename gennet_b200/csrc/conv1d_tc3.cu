@@ -67,6 +67,10 @@ struct Tc3Args {
     long long plane_stride;                // elements between planes of `planes`
     float* colsum;                         // optional: per-channel sum of the result over (b, row), atomically accumulated
     int m_tiles;                           // tiles of 128 rows per (sample, parity)
+    // split-K (Dense layers with a long contraction and few output tiles; B == 1, k == 1, forward only): the "sample"
+    // digit of the tile index counts K chunks of `kchunk` channels; every chunk adds its partial result into the
+    // zeroed fp32 output with vector reductions, bias / activation follow in bias_act_kernel
+    int kchunks, kchunk;
 };
 
 template <int BN, int NC>
@@ -113,11 +117,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npar = (a.mode == 1) ? a.s : 1;
-    const int kdim = (a.mode == 0) ? a.Cin : a.Cout;   // contraction channels
+    const bool splitk = a.kchunks > 1;
+    const int kdim = splitk ? a.kchunk : ((a.mode == 0) ? a.Cin : a.Cout);   // contraction channels (of one chunk)
     const int nkb = kdim / T3_BK;
     const int cols = (a.mode == 0) ? a.Cout : a.Cin;   // channels of the result
     const int n_nt = cols / BN;
     const int sshift = (a.s == 2) ? 1 : 0;             // the stride is 1 or 2 (checked on the host)
+    const int walk_b = splitk ? a.kchunks : a.B;       // extent of the slowest tile digit
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
@@ -148,7 +154,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // TMA producer: the whole warp walks the schedule (all values warp-uniform), one elected lane issues
         uint32_t st = 0, ph = 0;
         TileWalker<BN> tw;
-        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next()) {
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, walk_b); tw.valid(); tw.next()) {
             const TileCoord c = tw.coord();
             int tap_first = 0, tap_step = 1, ntaps = a.k;
             if (a.mode == 1) {
@@ -167,8 +173,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         uint8_t* sA = tiles + st * S::STAGE_BYTES;
                         uint8_t* sB = sA + NC * S::A_PLANE;
                         mbar_expect_tx(&full[st], S::STAGE_BYTES);
-                        tma_load_4d(sA, &mapA, &full[st], kb * T3_BK, rowc, c.b, 0);
-                        tma_load_4d(sB, &mapB, &full[st], kb * T3_BK, c.n0, tap, 0);
+                        const int kc = kb * T3_BK + (splitk ? c.b * a.kchunk : 0);
+                        tma_load_4d(sA, &mapA, &full[st], kc, rowc, splitk ? 0 : c.b, 0);
+                        tma_load_4d(sB, &mapB, &full[st], kc, c.n0, tap, 0);
                     }
                     __syncwarp();
                     if (++st == STAGES) { st = 0; ph ^= 1u; }
@@ -184,7 +191,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         uint32_t st = 0, ph = 0;
         int ti_local = 0;
         TileWalker<BN> tw;
-        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next(), ++ti_local) {
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, walk_b); tw.valid(); tw.next(), ++ti_local) {
             int ntaps = a.k;
             if (a.mode == 1) {
                 const int tap_first = (tw.par + a.p) & (a.s - 1);
@@ -230,12 +237,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int rows_out = (a.mode == 0) ? a.Lout : a.L;
         int ti_local = 0;
         TileWalker<BN> tw;
-        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, a.B); tw.valid(); tw.next(), ++ti_local) {
+        for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, walk_b); tw.valid(); tw.next(), ++ti_local) {
             const TileCoord c = tw.coord();
             // output row of this thread: forward l = m0 + row; data gradient j = (m0 + row) * stride + parity
             const int j = (c.m0 + row) * npar + c.par;
             const bool valid = j < rows_out;
-            const size_t roff = ((size_t)c.b * rows_out + (valid ? j : 0)) * cols + c.n0;
+            const size_t roff = ((size_t)(splitk ? 0 : c.b) * rows_out + (valid ? j : 0)) * cols + c.n0;
             const int acc = (BUFS == 2) ? (ti_local & 1) : 0, acc_ph = ((BUFS == 2) ? (ti_local >> 1) : ti_local) & 1;
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
@@ -268,6 +275,16 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                if (splitk) {
+                    if (valid) {
+                        float* op = a.out + roff + sl * 32;
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(op + 4 * g4), "f"(f[4 * g4]),
+                                         "f"(f[4 * g4 + 1]), "f"(f[4 * g4 + 2]), "f"(f[4 * g4 + 3]) : "memory");
+                    }
+                    continue;
                 }
                 if (a.mode == 0) {
                     if (a.bias != nullptr) {
@@ -363,7 +380,8 @@ struct Tc3WgradArgs {
     int n_chunks;
     int n_tiles_n;      // number of N tiles
     int out_tiles;      // k * m_tiles * n_tiles_n
-    float* dw;          // (k, Cin, Cout) fp32
+    int rows_store;     // input channels (rows of dW per tap) that exist in dw: < Cin when the planes are zero-padded (Dense)
+    float* dw;          // (k, rows_store, Cout) fp32
 };
 
 struct Wg3Unit {
@@ -535,16 +553,19 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 }
                 if (!SWAP) {
                     // thread = input channel, 32 consecutive output channels: eight 16-byte vector reductions
-                    float* dst = a.dw + ((size_t)w.tap * a.Cin + (w.m0 + row)) * a.Cout + w.n0 + c0;
+                    if (w.m0 + row < a.rows_store) {
+                        float* dst = a.dw + ((size_t)w.tap * a.rows_store + (w.m0 + row)) * a.Cout + w.n0 + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        red_add_v4_f32(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                       __uint_as_float(v[i + 3]));
+                        for (int i = 0; i < 32; i += 4)
+                            red_add_v4_f32(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                           __uint_as_float(v[i + 3]));
+                    }
                 } else {
                     // thread = output channel (consecutive across the warp), columns = input channels
-                    float* dst = a.dw + ((size_t)w.tap * a.Cin + (w.n0 + c0)) * a.Cout + w.m0 + row;
+                    float* dst = a.dw + ((size_t)w.tap * a.rows_store + (w.n0 + c0)) * a.Cout + w.m0 + row;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * a.Cout, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i)
+                        if (w.n0 + c0 + i < a.rows_store) atomicAdd(dst + (size_t)i * a.Cout, __uint_as_float(v[i]));
                 }
             }
         }
@@ -596,11 +617,43 @@ __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict_
     }
 }
 
+// y[r, c] = act(y[r, c] + bias[c]) in place (second pass of a split-K Dense forward); C % 4 == 0
+__global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, long long n4, int C4,
+                                                       int act, float ap) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<float4*>(y)[i];
+        if (bias != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % C4));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        v.x = act_fwd(v.x, act, ap); v.y = act_fwd(v.y, act, ap); v.z = act_fwd(v.z, act, ap); v.w = act_fwd(v.w, act, ap);
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+}
+
+// float32 matrix (rows, K) -> NC bf16 planes of a (rows, Kp) matrix, columns K..Kp-1 zero (Dense operands whose feature
+// count is not a multiple of the 64-channel tile, e.g. the generator's Dense(100 -> 128 n_pix), bbhMahoGANy.py:234)
+template <int NC>
+__global__ void __launch_bounds__(256) split_pad_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes,
+                                                            long long rows, int K, int Kp) {
+    const long long n = rows * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / Kp;
+        const int c = (int)(i - r * Kp);
+        __nv_bfloat16 p[3];
+        split3<NC>(c < K ? x[r * K + c] : 0.f, p);
+#pragma unroll
+        for (int pl = 0; pl < NC; ++pl) planes[(size_t)pl * n + i] = p[pl];
+    }
+}
+
 // weights: f32 (k,Cin,Cout) -> planes of the same layout (dgrad B operand) and planes of the transposed layout
 // (k,Cout,Cin) (forward B operand); one 32 x 32 (ci, co) tile of one tap per block, transposed through shared memory
+// Cin_src <= Cin: rows Cin_src..Cin-1 of every tap are written as zeros (w holds (k, Cin_src, Cout))
 template <int NC>
 __global__ void __launch_bounds__(256) conv_w_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wk,
-                                                           __nv_bfloat16* __restrict__ wt, int k, int Cin, int Cout) {
+                                                           __nv_bfloat16* __restrict__ wt, int k, int Cin, int Cout,
+                                                           int Cin_src) {
     __shared__ __nv_bfloat16 tile[NC][32][33];
     const int t = blockIdx.z;
     const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
@@ -612,7 +665,7 @@ __global__ void __launch_bounds__(256) conv_w_split_kernel(const float* __restri
         if (ci < Cin && co < Cout) {
             const size_t i = ((size_t)t * Cin + ci) * Cout + co;
             __nv_bfloat16 p[3];
-            split3<NC>(w[i], p);
+            split3<NC>(ci < Cin_src ? w[((size_t)t * Cin_src + ci) * Cout + co] : 0.f, p);
 #pragma unroll
             for (int pl = 0; pl < NC; ++pl) {
                 wk[pl * plane + i] = p[pl];
@@ -763,15 +816,23 @@ extern "C" int gn_conv_w_split_bf16(const float* w, void* wk, void* wt, int k, i
     GN_REQUIRE(k <= 65535 && (Cin + 31) / 32 <= 65535, "weight tensor too large for the split grid");
     dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32), (unsigned)k);
     cudaStream_t st = as_stream(stream);
-    if (nc == 3) conv_w_split_kernel<3><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
-    else if (nc == 2) conv_w_split_kernel<2><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
-    else conv_w_split_kernel<1><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout);
+    if (nc == 3) conv_w_split_kernel<3><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout, Cin);
+    else if (nc == 2) conv_w_split_kernel<2><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout, Cin);
+    else conv_w_split_kernel<1><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout, Cin);
     return cuda_status("conv_w_split_kernel");
 }
+
+static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L, int Cin, int Lout,
+                   int Cout, int k, int stride, int pad_left, int act, float act_param, int nc, int kchunks, void* stream);
 
 extern "C" int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L,
                                     int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
                                     float act_param, int nc, void* stream) {
+    return fwd_tc3(xs, wts, bias, y, ys, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param, nc, 1, stream);
+}
+
+static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L, int Cin, int Lout,
+                   int Cout, int k, int stride, int pad_left, int act, float act_param, int nc, int kchunks, void* stream) {
     GN_REQUIRE(xs && wts && (y || ys), "null pointer");
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
     if (rc != GN_OK) return rc;
@@ -790,7 +851,11 @@ extern "C" int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float
     a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = y;
     a.planes = (__nv_bfloat16*)ys; a.plane_stride = (long long)B * Lout * Cout;
     a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
-    const long long tiles = (long long)B * a.m_tiles * (Cout / BN);
+    a.kchunks = kchunks;
+    a.kchunk = Cin / kchunks;
+    GN_REQUIRE(kchunks == 1 || (B == 1 && k == 1 && ys == nullptr && y != nullptr && a.kchunk % T3_BK == 0),
+               "split-K needs B == 1, k == 1, a float32 output and chunks of whole 32-channel blocks");
+    const long long tiles = (long long)(kchunks > 1 ? kchunks : B) * a.m_tiles * (Cout / BN);
     cudaStream_t st = as_stream(stream);
     if (nc == 3) return dispatch_conv_tc3<3>(BN, false, mA, mB, a, tiles, st);
     if (nc == 2) return dispatch_conv_tc3<2>(BN, false, mA, mB, a, tiles, st);
@@ -829,8 +894,8 @@ extern "C" int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const fl
     return dispatch_conv_tc3<1>(BN, aux, mA, mB, a, tiles, st);
 }
 
-extern "C" int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L,
-                                      int Cin, int Lout, int Cout, int k, int stride, int pad_left, int nc, void* stream) {
+static int wgrad_tc3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
+                     int Cout, int k, int stride, int pad_left, int nc, int rows_store, void* stream) {
     GN_REQUIRE(xs && dys && dw, "null pointer");
     GN_REQUIRE(db == nullptr || dy != nullptr, "the bias gradient needs the float32 dy");
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
@@ -845,9 +910,10 @@ extern "C" int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const flo
     rc = make_map4(&mDY, dys, Cout, Lout, B, nc, Cout, (uint64_t)Lout * Cout, (uint64_t)B * Lout * Cout, 64, 32, 1,
                    CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != GN_OK) return rc;
-    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin * Cout, st);
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * rows_store * Cout, st);
     Tc3WgradArgs a{};
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
+    a.rows_store = rows_store;
     a.lblocks = (Lout + 31) / 32;
     a.iters_total = B * a.lblocks;
     a.dw = dw;
@@ -868,4 +934,78 @@ extern "C" int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const flo
     if (rc != GN_OK) return rc;
     if (db != nullptr) return launch_colsum(dy, (long long)B * Lout, Cout, db, st);
     return GN_OK;
+}
+
+extern "C" int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L,
+                                      int Cin, int Lout, int Cout, int k, int stride, int pad_left, int nc, void* stream) {
+    return wgrad_tc3(xs, dys, dy, dw, db, B, L, Cin, Lout, Cout, k, stride, pad_left, nc, Cin, stream);
+}
+
+// ---- Dense layers on the same kernels: a Dense GEMM is a convolution with one tap over a single "sample" whose
+// positions are the batch rows (M).  Kp = feature count padded to a multiple of 64 in the PLANES only.
+extern "C" int gn_split_pad_f32_bf16(const float* x, void* planes, long long rows, int K, int Kp, int nc, void* stream) {
+    GN_REQUIRE(x && planes && rows >= 0 && K > 0 && Kp >= K && nc >= 1 && nc <= 3, "null pointer or bad size");
+    if (rows == 0) return GN_OK;
+    const long long n = rows * Kp, want = (n + 255) / 256;
+    const unsigned grid = (unsigned)(want < 16LL * num_sms() ? want : 16LL * num_sms());
+    cudaStream_t st = as_stream(stream);
+    if (nc == 3) split_pad_f32_kernel<3><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, rows, K, Kp);
+    else if (nc == 2) split_pad_f32_kernel<2><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, rows, K, Kp);
+    else split_pad_f32_kernel<1><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, rows, K, Kp);
+    return cuda_status("split_pad_f32_kernel");
+}
+
+extern "C" int gn_dense_w_split_bf16(const float* w, void* wk, void* wt, int K, int Kp, int N, int nc, void* stream) {
+    GN_REQUIRE(w && wk && wt && K > 0 && Kp >= K && N > 0 && nc >= 1 && nc <= 3, "null pointer or bad size");
+    GN_REQUIRE((Kp + 31) / 32 <= 65535, "weight matrix too large for the split grid");
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((Kp + 31) / 32), 1u);
+    cudaStream_t st = as_stream(stream);
+    if (nc == 3) conv_w_split_kernel<3><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, 1, Kp, N, K);
+    else if (nc == 2) conv_w_split_kernel<2><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, 1, Kp, N, K);
+    else conv_w_split_kernel<1><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, 1, Kp, N, K);
+    return cuda_status("conv_w_split_kernel(dense)");
+}
+
+extern "C" int gn_dense_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int M, int Kp,
+                                   int N, int act, float act_param, int nc, void* stream) {
+    GN_REQUIRE(M > 0 && M <= 65535 * 128, "bad batch size");
+    // split-K: a long contraction with few output tiles (burst discriminator Dense(16128 -> 1024) at batch 16-128 has
+    // 8 tiles for 148 SMs) is cut into chunks of >= 256 channels that run as separate tiles and meet in the output by
+    // vector reductions; it also keeps the truncating tensor-memory accumulator short (<= 4096 channels per chunk)
+    int chunks = 1;
+    if (y != nullptr && ys == nullptr && Kp >= 1024 && Kp % 32 == 0 && N % 4 == 0) {
+        const long long tiles = (long long)((M + 127) / 128) * (N / (N % 128 == 0 ? 128 : 64));
+        const int units = Kp / 32;
+        for (int c = 2; c <= units; ++c) {
+            if (units % c != 0) continue;
+            const int kc = Kp / c;
+            if (kc < 256) break;
+            if (tiles * c <= 2LL * num_sms() || kc > 4096) chunks = c;
+        }
+    }
+    if (chunks == 1) return fwd_tc3(xs, wts, bias, y, ys, 1, M, Kp, M, N, 1, 1, 0, act, act_param, nc, 1, stream);
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
+    int rc = fwd_tc3(xs, wts, nullptr, y, nullptr, 1, M, Kp, M, N, 1, 1, 0, GN_ACT_NONE, 0.f, nc, chunks, stream);
+    if (rc != GN_OK) return rc;
+    if (bias != nullptr || act != GN_ACT_NONE) {
+        const long long n4 = (long long)M * N / 4;
+        const unsigned grid = (unsigned)((n4 + 255) / 256 < 16LL * num_sms() ? (n4 + 255) / 256 : 16LL * num_sms());
+        bias_act_kernel<<<grid, 256, 0, st>>>(y, bias, n4, N / 4, act, act_param);
+        return cuda_status("bias_act_kernel");
+    }
+    return GN_OK;
+}
+
+extern "C" int gn_dense_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, float* dx, float* dx_colsum, int M,
+                                     int K, int N, int in_act, float in_act_param, int nc, void* stream) {
+    GN_REQUIRE(K % 64 == 0, "the data gradient needs an unpadded feature count (K % 64 == 0)");
+    return gn_conv1d_dgrad_bf16x3(dys, wks, x_in, dx, nullptr, dx_colsum, 1, M, K, M, N, 1, 1, 0, in_act, in_act_param, nc,
+                                  stream);
+}
+
+extern "C" int gn_dense_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int M, int K,
+                                     int N, int Kp, int nc, void* stream) {
+    GN_REQUIRE(K > 0 && Kp >= K, "bad feature counts");
+    return wgrad_tc3(xs, dys, dy, dw, db, 1, M, Kp, M, N, 1, 1, 0, nc, K, stream);
 }

@@ -55,9 +55,71 @@ __global__ void __launch_bounds__(1024) overlap_sums_kernel(const float* __restr
     }
 }
 
+// ---- percentile curves of plot_waveform_est (bbhMahoGANy.py:913-921): for every time sample l the p-th percentiles of
+// the n generated waveforms, np.percentile's default linear interpolation: q = p/100 * (n-1), (1-g) a[j] + g a[j+1].
+// One block per tile of TL adjacent time samples (a 32-byte sector of every row is used whole): the tile is staged
+// column by column in shared memory (padded to a power of two with +inf), each column is sorted by a bitonic network
+// run by the whole block, and the requested order statistics are interpolated in double.
+__global__ void __launch_bounds__(256) percentile_kernel(const float* __restrict__ x, int n, int L, int n_pad, int TL,
+                                                         const float* __restrict__ pcts, int npct, float* __restrict__ out) {
+    extern __shared__ float col[];      // TL columns of n_pad floats
+    const int l0 = blockIdx.x * TL;
+    for (int i = threadIdx.x; i < n_pad * TL; i += blockDim.x) {
+        const int r = i / TL, c = i - r * TL;
+        col[c * n_pad + r] = (r < n && l0 + c < L) ? x[(size_t)r * L + l0 + c] : __int_as_float(0x7f800000);
+    }
+    __syncthreads();
+    for (int c = 0; c < TL; ++c) {
+        float* a = col + c * n_pad;
+        for (int size = 2; size <= n_pad; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < n_pad / 2; t += blockDim.x) {
+                    const int i = 2 * t - (t & (stride - 1));      // lower index of the pair
+                    const int j = i + stride;
+                    const bool up = (i & size) == 0;
+                    const float u = a[i], v = a[j];
+                    if ((u > v) == up) { a[i] = v; a[j] = u; }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int t = threadIdx.x; t < TL * npct; t += blockDim.x) {
+        const int c = t / npct, q = t - c * npct;
+        if (l0 + c >= L) continue;
+        const double pos = (double)pcts[q] / 100.0 * (double)(n - 1);
+        int j = (int)floor(pos);
+        if (j < 0) j = 0;
+        if (j > n - 1) j = n - 1;
+        const int j1 = j + 1 < n ? j + 1 : n - 1;
+        const double g = pos - (double)j;
+        const double lo = (double)col[c * n_pad + j], hi = (double)col[c * n_pad + j1];
+        out[(size_t)q * L + l0 + c] = (float)(lo + (hi - lo) * g);
+    }
+}
+
 }  // namespace gn
 
 using namespace gn;
+
+extern "C" int gn_percentiles_f32(const float* x, int n, int L, const float* pcts, int npct, float* out, void* stream) {
+    GN_REQUIRE(x && pcts && out, "null pointer");
+    GN_REQUIRE(n > 0 && L > 0 && npct > 0 && npct <= 64, "needs n > 0, L > 0 and 1..64 percentiles");
+    int n_pad = 2;
+    while (n_pad < n) n_pad <<= 1;
+    GN_REQUIRE(n_pad <= 32768, "at most 32768 waveforms per call");
+    int TL = 40960 / n_pad;             // <= 160 KB of shared memory
+    if (TL > 8) TL = 8;
+    if (TL < 1) TL = 1;
+    const size_t smem = sizeof(float) * (size_t)n_pad * TL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(percentile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 163840);
+        attr_set = true;
+    }
+    percentile_kernel<<<(L + TL - 1) / TL, 256, smem, as_stream(stream)>>>(x, n, L, n_pad, TL, pcts, npct, out);
+    return cuda_status("percentile_kernel");
+}
 
 extern "C" int gn_kde2d_pdf_f32(const float* data_xy, int n, const float* pos_xy, int m, double a11, double a12,
                                 double a22, double inv_norm, float* pdf, void* stream) {

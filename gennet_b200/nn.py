@@ -289,8 +289,76 @@ class Dense(Layer):
                        Param(self.name + '/bias:0', np.zeros(self.units, np.float32))]
         return (self.units,)
 
+    def _tc_planes(self):
+        """Number of bf16 planes when this layer runs on the tensor-core kernels (0 = it does not): any mode but
+        'float32', N a multiple of 64, a GEMM large enough to be worth two operand conversions."""
+        nc = _split_planes() or (1 if _STATE['dtype'] == 'bfloat16' else 0)
+        K, N = self.input_shape[0], self.units
+        if nc == 0 or N % 64 != 0 or K < 32 or K * N < (1 << 20):
+            return 0
+        return nc
+
+    def _kp(self):
+        K, N = self.input_shape[0], self.units
+        if K <= 64 and N % 128 == 0:
+            return 64
+        return -(-K // 128) * 128
+
+    def _tc_weights(self, nc):
+        key = (_STATE['wver'], nc)
+        if getattr(self, '_wsplit', None) is None or self._wsplit[0] != key:
+            K, N, Kp = self.input_shape[0], self.units, self._kp()
+            wk = _empty_bf16((nc, Kp, N))
+            wt = _empty_bf16((nc, N, Kp))
+            call('gn_dense_w_split_bf16', ptr(self.params[0].data), ptr(wk, BF16), ptr(wt, BF16), K, Kp, N, nc, stream())
+            self._wsplit = (key, wk, wt)
+        return self._wsplit[1], self._wsplit[2]
+
+    def _forward_tc(self, x, nc):
+        B, K = x.shape
+        N, Kp = self.units, self._kp()
+        x = _as_f32(x).contiguous()
+        xs = _empty_bf16((nc, B, Kp))
+        call('gn_split_pad_f32_bf16', ptr(x), ptr(xs, BF16), B, K, Kp, nc, stream())
+        wk, wt = self._tc_weights(nc)
+        y = _empty((B, N))
+        call('gn_dense_fwd_bf16x3', ptr(xs, BF16), ptr(wt, BF16), ptr(self.params[1].data), ptr(y), None, B, Kp, N,
+             _ACTS[self.activation], 0.0, nc, stream())
+        self._xs = xs
+        return x, y
+
+    def _backward_tc(self, dy, ctx, need_dx, nc):
+        x, xs = self._x, self._xs
+        B, K = x.shape
+        N, Kp = self.units, self._kp()
+        dy = _as_f32(dy).contiguous()
+        dys = _split(dy, nc)
+        if id(self) in ctx.trainable_ids:
+            call('gn_dense_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), ptr(self.params[0].grad),
+                 ptr(self.params[1].grad), B, K, N, Kp, nc, stream())
+        dx = None
+        if need_dx:
+            dx = _empty((B, K))
+            if K == Kp:
+                wk, wt = self._tc_weights(nc)
+                code, par = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
+                sink, _ = _bias_sink(self, ctx, K)
+                call('gn_dense_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), ptr(x) if self.in_act is not None else None,
+                     ptr(dx), sink if self.in_act is not None else None, B, K, N, code, par, nc, stream())
+                dx._gn_preact = self.in_act is not None
+                dx._gn_db_done = self.in_act is not None and sink is not None
+            else:
+                call('gn_dense_dgrad_f32', ptr(dy), ptr(self.params[0].data), ptr(dx), B, K, self.units, stream())
+        self._xs = None
+        return dx
+
     def forward(self, x, ctx):
         B, K = x.shape
+        self._tc = self._tc_planes()
+        if self._tc:
+            self._bf16 = self._small32 = False
+            self._x, self._y = self._forward_tc(x, self._tc)
+            return self._y
         y = _empty((B, self.units))
         # <= 4 outputs over a long feature vector: the streaming GEMV kernels (bf16 or float32 features)
         self._bf16 = x.dtype == BF16 and self.units <= 4 and K % 8 == 0
@@ -317,6 +385,10 @@ class Dense(Layer):
             dy = _act_bwd(dy, self._y, _ACTS[self.activation], 0.0)
         tr = id(self) in ctx.trainable_ids
         dx = None
+        if self._tc:
+            dx = self._backward_tc(dy, ctx, need_dx, self._tc)
+            self._x = self._y = None
+            return dx
         if self._bf16 or self._small32:
             sfx, dt = ('_bf16', BF16) if self._bf16 else ('_f32', torch.float32)
             if tr:

@@ -199,6 +199,25 @@ int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, 
 int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L, int Cin,
                            int Lout, int Cout, int k, int stride, int pad_left, int nc, void* stream);
 
+/* Dense layers on the same split-operand kernels (Dense(100 -> 128 n_pix) of the generator, bbhMahoGANy.py:234;
+ * Dense(16128 -> 1024) of the burst discriminator, burstMahoGANy.py:351; the out x out layers of 2_model_version):
+ * y (M,N) = act(x (M,K) w (K,N) + bias) is a one-tap convolution over a single sample whose positions are the M batch
+ * rows.  Kp = K rounded up to the channel tile (64, or 128 for the weight gradient) exists in the PLANES only, zero filled.
+ *   gn_split_pad_f32_bf16 : x f32 (rows,K) -> planes bf16 (nc,rows,Kp)
+ *   gn_dense_w_split_bf16 : w f32 (K,N) -> wk planes (nc,Kp,N) [dgrad operand], wt planes (nc,N,Kp) [fwd operand]
+ *   fwd   : y f32 (M,N) and / or ys planes (nc,M,N); N % 64 == 0, Kp % 64 == 0
+ *   dgrad : dx f32 (M,K) = act'(x_in) * dy w^T; needs K % 64 == 0 (no padding); dx_colsum as for the convolution
+ *   wgrad : dw f32 (K,N) OVERWRITTEN (only the K real rows are written), db f32 (N) from the float32 dy;
+ *           Kp % 128 == 0, or Kp == 64 with N % 128 == 0 */
+int gn_split_pad_f32_bf16(const float* x, void* planes, long long rows, int K, int Kp, int nc, void* stream);
+int gn_dense_w_split_bf16(const float* w, void* wk, void* wt, int K, int Kp, int N, int nc, void* stream);
+int gn_dense_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int M, int Kp, int N,
+                        int act, float act_param, int nc, void* stream);
+int gn_dense_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, float* dx, float* dx_colsum, int M, int K,
+                          int N, int in_act, float in_act_param, int nc, void* stream);
+int gn_dense_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int M, int K, int N,
+                          int Kp, int nc, void* stream);
+
 /* Bandwidth-bound companions of the bf16 path.
  *   smallcin fwd  : first convolution of a network, Cin in {1,2}: x f32 (B,L,Cin) -> y bf16 (B,Lout,Cout), bias+act fused
  *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 5, Cout in {8,16,32,64}
@@ -339,6 +358,9 @@ int gn_axpy_f32(float* a, const float* b, float alpha, long long n, void* stream
 int gn_kde2d_pdf_f32(const float* data_xy, int n, const float* pos_xy, int m, double a11, double a12, double a22,
                      double inv_norm, float* pdf, void* stream);
 int gn_overlap_sums_f32(const float* a, const float* b, long long n, double* out3, void* stream);
+/* Percentile curves of plot_waveform_est (bbhMahoGANy.py:913-921): out (npct, L) f32, out[q, l] = np.percentile(x[:, l],
+ * pcts[q]) (default linear interpolation) of the n generated waveforms x (n, L) f32; n <= 32768, npct <= 64. */
+int gn_percentiles_f32(const float* x, int n, int L, const float* pcts, int npct, float* out, void* stream);
 /* gather rows: out[i,:] = src[idx[i],:]  (template batch assembly, bbhMahoGANy.py:1156-1158,1244) */
 int gn_gather_rows_f32(const float* src, const int* idx, float* out, int n, long long row_len, void* stream);
 

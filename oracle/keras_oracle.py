@@ -397,13 +397,12 @@ class MaxPooling1D(Layer):
         if ykink is None:
             return F.max_pool1d(x.permute(0, 2, 1), self.p).permute(0, 2, 1)
         # Like a ReLU kink, a near-tie inside a pooling window is a discontinuity of the gradient: the window element
-        # the implementation under test selected (identified by its pooled OUTPUT, fed in) is differentiated here too --
+        # the implementation under test selected (its INDEX within the window, fed in) is differentiated here too --
         # but only where it is within KINK_TOL (of the tensor's scale) of the true maximum; anything else raises.
         B, L, C = x.shape
         n = L // self.p
         win = x[:, :n * self.p].reshape(B, n, self.p, C)
-        fed_y = torch.as_tensor(np.asarray(ykink)).to(x.dtype).reshape(B, n, 1, C)
-        idx = (win.detach() - fed_y).abs().argmin(dim=2, keepdim=True)
+        idx = torch.as_tensor(np.asarray(ykink['pool_idx'])).to(torch.int64).reshape(B, n, 1, C)
         chosen = torch.gather(win, 2, idx).squeeze(2)
         gap = float((win.detach().max(dim=2).values - chosen.detach()).max())
         lim = KINK_TOL * max(float(x.detach().abs().max()), 1e-30)

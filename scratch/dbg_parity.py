@@ -40,3 +40,17 @@ for mode in sys.argv[2:]:
     elif which == 'pe':
         prod, orc, x, y = pc.pe_case(int(os.environ.get('NPIX', 2048)), 8)
         report(mode + ' pe', prod, orc, x, y)
+if which == 'burst_flow':
+    for mode in sys.argv[2:]:
+        nn.set_compute_dtype(mode)
+        (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny = pc.burst_case(int(os.environ.get('NPIX', 512)), 8)
+        variant = os.environ.get('VARIANT', 'full')
+        if variant in ('full', 'predict'):
+            po, oo = d.predict(sX), od.predict(sX)
+            print('D.predict err', np.abs(po - oo).max() / np.abs(oo).max())
+        report(mode + ' D', d, od, sX, sy)
+        if variant in ('full', 'resync'):
+            pc.resync([(d, od)])
+        report(mode + ' subG', sub_g, osub, z, ny)
+        pc.resync([(g, og)])
+        report(mode + ' DG', dg, ocomp, z, [1] * 8)

@@ -81,7 +81,15 @@ def record_kinks(product_model):
 
         def fw(x, ctx, _l=l, _orig=orig):
             y = _orig(x, ctx)
-            _l._pc_rec[_l.name] = y.detach().float().cpu().numpy().copy()
+            if type(_l).__name__ == 'MaxPooling1D':
+                # the window element the product selected: the first one equal to the pooled output (gn_maxpool1d_bwd_f32)
+                xv = x.detach().float().cpu().numpy()
+                B, L, C = xv.shape
+                n = L // _l.pool
+                win = xv[:, :n * _l.pool].reshape(B, n, _l.pool, C)
+                _l._pc_rec[_l.name] = {'pool_idx': (win == win.max(axis=2, keepdims=True)).argmax(axis=2)}
+            else:
+                _l._pc_rec[_l.name] = y.detach().float().cpu().numpy().copy()
             return y
         l.forward = fw
         l._pc_wrapped = True

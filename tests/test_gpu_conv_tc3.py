@@ -170,3 +170,48 @@ def test_tc3_accuracy_at_baseline_size(capsys):
     with capsys.disabled():
         print('\n[tc3 accuracy, conv 512->1024 k5 s2, B=64] ' + ' '.join('%s=%.2e' % kv for kv in e.items()))
     assert e['fwd'] <= 1e-5 and e['dgrad'] <= 1e-5 and e['wgrad'] <= 1e-5, e
+
+
+@pytest.mark.parametrize('M,K,N', [(16, 100, 512), (128, 100, 4096), (24, 16128, 1024), (200, 256, 128), (8, 64, 256)])
+@pytest.mark.parametrize('nc', [3, 1])
+def test_dense_on_split_tensor_core_kernels(M, K, N, nc):
+    """Dense fwd / dgrad / wgrad on the split-operand tcgen05 kernels (one-tap convolution over the batch rows), with
+    the feature count padded in the planes only (K = 100 -> Kp = 128): vs torch float64."""
+    from gennet_b200 import _lib as L_
+    tol = 6e-6 if nc == 3 else 2 ** -7
+    rs = np.random.RandomState(M + K + N)
+    x, w, b = dev(rs.normal(size=(M, K))), dev(rs.normal(size=(K, N)) / math.sqrt(K)), dev(rs.normal(size=N))
+    dy = dev(rs.normal(size=(M, N)))
+    Kp = 64 if (K <= 64 and N % 128 == 0) else -(-K // 128) * 128
+    st = L_.stream()
+    xs = torch.full((nc, M, Kp), float('nan'), dtype=BF, device='cuda')
+    L_.call('gn_split_pad_f32_bf16', L_.ptr(x), L_.ptr(xs, BF), M, K, Kp, nc, st)
+    assert torch.equal(xs[:, :, :K], split(x, nc)) and (xs[:, :, K:] == 0).all()
+    wk = torch.full((nc, Kp, N), float('nan'), dtype=BF, device='cuda')
+    wt = torch.full((nc, N, Kp), float('nan'), dtype=BF, device='cuda')
+    L_.call('gn_dense_w_split_bf16', L_.ptr(w), L_.ptr(wk, BF), L_.ptr(wt, BF), K, Kp, N, nc, st)
+    assert torch.equal(wk[:, :K], split(w, nc)) and (wk[:, K:] == 0).all() and torch.equal(wt, wk.permute(0, 2, 1).contiguous())
+    xr, wr = (xs.double().sum(0)[:, :K] if nc == 1 else x.double()), (wk.double().sum(0)[:K] if nc == 1 else w.double())
+    y = torch.full((M, N), float('nan'), device='cuda')
+    L_.call('gn_dense_fwd_bf16x3', L_.ptr(xs, BF), L_.ptr(wt, BF), L_.ptr(b), L_.ptr(y), None, M, Kp, N, L_.ACT_TANH, 0.0, nc, st)
+    torch.cuda.synchronize()
+    assert_close(y.cpu().numpy(), torch.tanh(xr @ wr + b.double()).cpu().numpy(), 'dense tc fwd', tol)
+    dys = split(dy, nc)
+    dyr = dys.double().sum(0) if nc == 1 else dy.double()
+    dw = torch.full((K, N), float('nan'), device='cuda')
+    db = torch.full((N,), float('nan'), device='cuda')
+    guard = torch.full((64,), 7.0, device='cuda')                 # allocated right after dw: padded rows must not be written
+    L_.call('gn_dense_wgrad_bf16x3', L_.ptr(xs, BF), L_.ptr(dys, BF), L_.ptr(dy), L_.ptr(dw), L_.ptr(db), M, K, N, Kp, nc, st)
+    torch.cuda.synchronize()
+    assert_close(dw.cpu().numpy(), (xr.t() @ dyr).cpu().numpy(), 'dense tc wgrad', tol)
+    assert_close(db.cpu().numpy(), dy.double().sum(0).cpu().numpy(), 'dense tc bias grad', 1e-5)
+    assert (guard == 7.0).all()
+    if K % 64 == 0:
+        dx = torch.full((M, K), float('nan'), device='cuda')
+        cs = torch.full((K,), float('nan'), device='cuda')
+        xpos = torch.relu(x).contiguous()
+        L_.call('gn_dense_dgrad_bf16x3', L_.ptr(dys, BF), L_.ptr(wk, BF), L_.ptr(xpos), L_.ptr(dx), L_.ptr(cs), M, K, N,
+                L_.ACT_RELU, 0.0, nc, st)
+        ref = (dyr @ wr.t()) * (xpos > 0)
+        assert_close(dx.cpu().numpy(), ref.cpu().numpy(), 'dense tc dgrad*mask', tol)
+        assert_close(cs.cpu().numpy(), ref.sum(0).cpu().numpy(), 'dense tc dgrad column sums', max(tol, 1e-5))

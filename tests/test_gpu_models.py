@@ -118,8 +118,9 @@ def test_pe_step_bf16_within_stated_tolerance():
 def test_gan_steps_bf16_within_stated_tolerance():
     """Throughput mode on the GAN of bbhMahoGANy.py (BASELINE config 3): generator convolutions (UpSampling folded,
     Cout = 1 tail) and the discriminator's packed Conv2D layers on the tensor-core / streaming bf16 kernels.
-    Stated tolerance vs the float64 oracle (same as the PE test): outputs 2e-2 of scale, losses 3e-2 (+1e-4), gradients
-    1e-1 relative L2 / 3e-1 of max.  Dropout masks are fed; BatchNorm runs in float32 between the bf16 convolutions."""
+    Stated tolerance vs the float64 oracle: outputs 2e-2 of scale, losses 3e-2 (+1e-4), gradients 1.5e-1 relative L2 /
+    3e-1 of max (the generator's Dense(100 -> 128 n_pix) also runs with bf16 operands on the tensor cores).  Dropout
+    masks are fed; BatchNorm runs in float32 between the bf16 convolutions."""
     from gennet_b200 import nn
     try:
         nn.set_compute_dtype('bfloat16')
@@ -142,7 +143,7 @@ def test_gan_steps_bf16_within_stated_tolerance():
                 # largest gradient of the step instead of their own rounding noise
                 el2 = np.linalg.norm((p_ - q).ravel()) / max(np.linalg.norm(q.ravel()), 1e-2 * gmax * np.sqrt(q.size))
                 emax = np.abs(p_ - q).max() / max(np.abs(q).max(), 1e-2 * gmax)
-                assert np.isfinite(p_).all() and el2 <= 1e-1 and emax <= 3e-1, (i, q.shape, el2, emax)
+                assert np.isfinite(p_).all() and el2 <= 1.5e-1 and emax <= 3e-1, (i, q.shape, el2, emax)
         step(d, od, sX, sy, 0)
         pc.resync([(d, od)])
         step(dg, ocomp, z, [1] * 8, 1)
@@ -209,7 +210,7 @@ def test_posterior_sampling_chain_on_device():
     assert np.allclose(s2[0], s3[0], rtol=0, atol=1e-6) and np.allclose(s2[1], s3[1], rtol=0, atol=1e-6)
     pc_ = bbh.waveform_percentiles(gen)
     for p in (90, 75, 25, 5):
-        assert np.allclose(pc_[p], [np.percentile(gen[:, n, 0], p) for n in range(128)])
+        assert np.allclose(pc_[p], [np.percentile(gen[:, n, 0], p) for n in range(128)], rtol=1e-5, atol=1e-7)
 
 
 # ---- split-bf16 tensor-core mode ('bf16x3'): the SAME rtol 1e-4 as the float32 SIMT path ------------------------
@@ -268,3 +269,81 @@ def test_burst_iteration_parity_bf16x3(bf16x3):
     pc.resync([(g, og)])
     errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 8, check_predict=False)
     pc.compare_weights(g, og, w0[:len(g.get_weights())])
+
+
+def test_posterior_samples_and_percentiles_vs_oracle():
+    """bbhMahoGANy.py:1311-1343 / :913-921 against the float64 oracle carrying the same weights: generator.predict ->
+    signal_pe.predict chained on the device equals og.predict -> ope.predict (rtol 1e-4), and the device percentile
+    curves equal np.percentile of the oracle's generated waveforms."""
+    from gennet_b200 import nn, bbh
+    from oracle import keras_oracle as ko
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(5)
+    bbh.n_pix = 256
+    g, pe = bbh.generator_model(), bbh.signal_pe_model()
+    og = ko.build(ko.bbh_generator_model(256), seed=11)
+    ope = ko.build(ko.bbh_signal_pe_model(256), seed=12)
+    ope.branches[0][-2].weights[1].data += 0.5          # keep the ReLU heads active
+    ope.branches[1][-2].weights[1].data += 0.5
+    pc.sync_weights(g, og)
+    pc.sync_weights(pe, ope)
+    z = np.random.RandomState(3).uniform(-1, 1, (37, 100)).astype(np.float32)
+    samples, gen = bbh.posterior_samples(g, pe, n=37, batch=16, z=z)
+    gen_ref = og.predict(z)
+    pc.assert_close(gen, gen_ref, 'generated waveforms')
+    ref = ope.predict(gen_ref)
+    for k, (a, b) in enumerate(zip(samples, ref)):
+        pc.assert_close(a, b, 'posterior sample %d' % k)
+    curves = bbh.waveform_percentiles(gen, percentiles=(90, 75, 50, 25, 5, 0, 100))
+    gr = gen_ref.reshape(37, 256)
+    for p, c in curves.items():
+        want = np.array([np.percentile(gr[:, n], p) for n in range(256)])      # the reference's loop (:918-921)
+        pc.assert_close(c, want, 'percentile %g' % p)
+
+
+@pytest.mark.parametrize('n,L', [(1000, 64), (4000, 130), (37, 9), (2, 5), (4097, 16)])
+def test_percentile_kernel_matches_numpy(n, L):
+    from gennet_b200 import bbh
+    rs = np.random.RandomState(n + L)
+    x = rs.normal(size=(n, L)).astype(np.float32)
+    x[:, 0] = 1.0                                           # ties
+    got = bbh.waveform_percentiles(x, percentiles=(90, 75, 25, 5, 33.3))
+    for p, c in got.items():
+        want = np.percentile(x.astype(np.float64), p, axis=0)
+        assert np.abs(c - want).max() <= 1e-6 * max(np.abs(want).max(), 1.0), (p, np.abs(c - want).max())
+
+
+def test_pe_train_step_batch_assembly_vs_oracle():
+    """bbhMahoGANy.py:1153-1166 on the device (bbh.pe_train_step: gn_gather_rows_f32 + gn_add_scaled_f32 + train step)
+    against the reference's host assembly `x = templates[idx]; x[:B/8] += sigma * n; y = pars[idx]` fed to the float64
+    oracle: the assembled batch and labels are identical, the losses and gradients agree within rtol 1e-4."""
+    from gennet_b200 import bbh
+    prod, orc, _, _ = pc.pe_case(256, 16)
+    rs = np.random.RandomState(7)
+    templates = rs.normal(size=(50, 256)).astype(np.float32)
+    pars = rs.uniform(0.3, 1.0, (50, 2)).astype(np.float32)
+    idx = rs.randint(0, 50, 16).astype(np.int32)
+    noise = rs.normal(size=(2, 256)).astype(np.float32)
+    sigma = 2.5
+    want_x = templates[idx].copy()
+    want_x[:2] += np.float32(sigma) * noise
+    want_y = pars[idx]
+    seen = {}
+    orig = prod.train_on_batch
+
+    def spy(x, y, **kw):
+        seen['x'] = x.detach().cpu().numpy().copy()
+        seen['y'] = [t.detach().cpu().numpy().copy() for t in y]
+        return orig(x, y, **kw)
+    prod.train_on_batch = spy
+    dev = lambda a, dt=torch.float32: torch.as_tensor(a).cuda().to(dt)
+    rec = pc.record_kinks(prod)
+    rp = bbh.pe_train_step(prod, dev(templates), dev(pars), dev(idx, torch.int32), dev(noise), sigma)
+    assert np.abs(seen['x'].reshape(16, 256) - want_x).max() <= 2.4e-7 * np.abs(want_x).max()      # one fma vs mul + add
+    assert np.array_equal(seen['y'][0], want_y[:, 0]) and np.array_equal(seen['y'][1], want_y[:, 1])
+    ro = orc.train_on_batch(seen['x'].reshape(16, 256, 1), [want_y[:, 0], want_y[:, 1]],
+                            noise={'__kinks__': pc.map_kinks(rec, orc, prod)})
+    pc.assert_close(rp, ro, 'pe_train_step losses', 2e-4)
+    for i, (a, b) in enumerate(zip(prod.get_gradients(), orc.last_grads)):
+        pc.assert_close(a, b, 'pe_train_step gradient %d' % i, 1e-4, floor=1e-3 * max(np.abs(q).max() for q in orc.last_grads))
