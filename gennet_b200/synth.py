@@ -287,10 +287,21 @@ def gen_bbh(fs, T_obs, psds, dets=['H1'], beta=[0.75, 0.95], par=None, gw_tmp=Fa
 def sim_data(fs, T_obs, psds, dets=['H1'], Nnoise=25, size=1000, mdist='astro', beta=[0.75, 0.95], waveform=None,
              antenna=None, gw_tmp=True, rng=np.random, chunk=256):
     """gw_template_maker.py:632-740 (one detector, do_time_grid off as shipped).  Template synthesis is
-    batched on the GPU in chunks; returns ([ts (size,1,fs), yval], list[bbhparams])."""
+    batched on the GPU in chunks; returns ([ts (size,1,fs), yval], list[bbhparams]).
+
+    ``Nnoise > 0`` (:684-692, "not typically used"): every template is followed by ``Nnoise`` noise realisations and the
+    counter advances by one per realisation, so ``ceil(size / Nnoise)`` templates are drawn and ``ceil(size / Nnoise) *
+    Nnoise`` rows come back, each the FULL-length whitened series (``N = T_obs * fs`` samples: this branch does not
+    crop).  With the module default ``gw_tmp = True`` the reference then fails at :737, concatenating the ``(1, 1, fs)``
+    GW150914-like template onto ``(rows, 1, N)`` rows; that combination raises here as well."""
     assert waveform is not None, 'LALSuite is not available: pass waveform(par, fs, T_obs) -> (hp_fd, hc_fd)'
     s = _synth_for(fs, T_obs, psds)
     n = size - 1 if gw_tmp else size
+    if Nnoise > 0:
+        if gw_tmp:
+            raise ValueError('sim_data(Nnoise > 0, gw_tmp=True): the reference concatenates a (1,1,fs) template onto '
+                             'full-length noisy rows and fails (gw_template_maker.py:737); use gw_tmp=False')
+        n = -(-n // Nnoise)          # templates drawn before the row counter reaches `size`
     pars = [gen_par(fs, T_obs, mdist=mdist, beta=beta, gw_tmp=False, rng=rng) for _ in range(n)]
     ts = []
     for c0 in range(0, n, chunk):
@@ -304,14 +315,17 @@ def sim_data(fs, T_obs, psds, dets=['H1'], Nnoise=25, size=1000, mdist='astro', 
         Fc = np.array([a[1] for a in ant], np.float32)
         if Nnoise > 0:
             full, _ = s.bbh_from_fd(hp, hc, idx, Fp, Fc, crop=False)
+            per_t = []
             for j in range(Nnoise):
                 nrm = rng.normal(0, 1, (len(ps), 2, s.Nf)).astype(np.float32)
-                ts.append(s.synth(len(ps), templates=full, normals=_dev(nrm)).cpu().numpy())
+                noisy = s.gen_noise(_dev(nrm)) + full                           # ts_noise + ts_new (:687-688)
+                per_t.append(s.whiten_td(noisy, crop=False).cpu().numpy())
+            ts.append(np.stack(per_t, axis=1).reshape(len(ps) * Nnoise, -1))    # template-major, as the reference appends
         else:
             out, _ = s.bbh_from_fd(hp, hc, idx, Fp, Fc, crop=True)
             ts.append(out.cpu().numpy())
     if Nnoise > 0:
-        pars = [p for c0 in range(0, n, chunk) for _ in range(Nnoise) for p in pars[c0:c0 + chunk]]
+        pars = [p for p in pars for _ in range(Nnoise)]
     ts = np.concatenate(ts).astype(np.float64)[:, None, :] if ts else np.zeros((0, 1, fs))
     yval = np.ones(len(ts), dtype=int)
     order = rng.permutation(len(ts))

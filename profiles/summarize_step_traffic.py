@@ -27,10 +27,11 @@ def main():
                     'tensor_pipe_active_pct': val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')})
     tot = sum(p['dram_read_bytes'] + p['dram_write_bytes'] for p in per)
     tt = sum(p['time_s'] for p in per)
-    res = {'source': 'ncu --set full --clock-control none -k regex:conv_tc -s 63 -c 21 python bench.py --steps 2 --warmup 3 (%s)'
-                     % rep.split('/')[-1],
-           'what': 'the tcgen05 Conv1D launches (fwd, dgrad, wgrad of the 7 tensor-core layers) of one signal_pe training '
-                   'step, batch 512, n_pix 2048',
+    what = sys.argv[3] if len(sys.argv) > 3 else ('the tcgen05 Conv1D launches (fwd, dgrad, wgrad of the 7 tensor-core layers) of '
+                                                  'one signal_pe training step, batch 512, n_pix 2048')
+    src = sys.argv[4] if len(sys.argv) > 4 else 'ncu --set full --clock-control none -k regex:conv_tc -s 63 -c 21 python bench.py --steps 2 --warmup 3'
+    res = {'source': '%s (%s)' % (src, rep.split('/')[-1]),
+           'what': what,
            'launches': len(per), 'dram_bytes_per_step': tot, 'dram_bytes_per_launch': tot / max(len(per), 1),
            'time_weighted_tensor_pipe_active_pct': sum(p['time_s'] * p['tensor_pipe_active_pct'] for p in per) / tt,
            'per_launch': per}

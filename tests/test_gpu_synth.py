@@ -225,6 +225,38 @@ def test_template_bank_generator_end_to_end(tmp_path):
 
 
 @pytest.mark.gpu
+def test_sim_data_noise_realisations_branch():
+    """sim_data(Nnoise > 0), gw_template_maker.py:684-692: ceil(size / Nnoise) templates x Nnoise realisations, rows are
+    the FULL-length whitened (coloured noise + already-whitened template) series, template-major before the final
+    permutation; every row equals the oracle's gen_noise -> + template -> whiten_data on the same draws.  With
+    gw_tmp=True the reference fails at :737 (shape mismatch), and so does this."""
+    from gennet_b200 import synth
+    from oracle import synth_oracle as so
+    fs, T = 1024, 4
+    N = fs * T
+    psd = so.analytic_psd(fs, T)
+
+    def waveform(par, fs_, T_):
+        return so.newtonian_chirp_fd(par.m1, par.m2, fs_, T_)
+    kw = dict(dets=['H1'], Nnoise=2, size=5, mdist='hunt_constrain', beta=[0.45, 0.55], waveform=waveform)
+    with pytest.raises(ValueError):
+        synth.sim_data(fs, T, psd, gw_tmp=True, rng=np.random.RandomState(3), **kw)
+    (ts, yval), pars = synth.sim_data(fs, T, psd, gw_tmp=False, rng=np.random.RandomState(3), **kw)
+    assert ts.shape == (6, 1, N) and yval.shape == (6,) and len(pars) == 6            # ceil(5 / 2) * 2 rows, not cropped
+    # replay the RNG: parameters, then the normals of realisation 0 and 1 for all templates, then the permutation
+    rs = np.random.RandomState(3)
+    p3 = [synth.gen_par(fs, T, mdist='hunt_constrain', beta=[0.45, 0.55], gw_tmp=False, rng=rs) for _ in range(3)]
+    nrm = [rs.normal(0, 1, (3, 2, N // 2 + 1)).astype(np.float32) for _ in range(2)]
+    order = rs.permutation(6)
+    for row, src in enumerate(order):
+        t, j = divmod(int(src), 2)
+        assert (pars[row].m1, pars[row].m2, pars[row].idx) == (p3[t].m1, p3[t].m2, p3[t].idx)
+        templ, _ = so.gen_bbh_from_fd(*so.newtonian_chirp_fd(p3[t].m1, p3[t].m2, fs, T), fs, T, psd, p3[t].idx, 1.0, 0.0)
+        noisy = so.gen_noise(fs, T, psd, normals=nrm[j][t].astype(np.float64)) + templ
+        assert rel_err(ts[row, 0], so.whiten_data(noisy, T, fs, psd, 'td')) < 5e-6
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('Nx', [4096, 16000, 3001])
 def test_waveform_ingest_matches_oracle(Nx):
     """GPU resample (dense operator) + max-normalise + roll vs the float64 restatement of load_txtwfs.py:47-50."""
