@@ -101,6 +101,10 @@ _SIGS = {
     'gn_upsample1d_bwd_f32': [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_maxpool1d_fwd_f32': [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_maxpool1d_bwd_f32': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    'gn_gap_fwd_f32': [c_p, c_p, c_i, c_i, c_i, c_p],
+    'gn_gap_bwd_f32': [c_p, c_p, c_i, c_i, c_i, c_p],
+    'gn_transpose_f32': [c_p, c_p, c_i, c_i, c_i, c_p],
+    'gn_reg_terms_f32': [c_p, c_p, c_ll, c_f, c_f, c_p, c_p],
     'gn_axpy_f32': [c_p, c_p, c_f, c_ll, c_p],
     'gn_gather_rows_f32': [c_p, c_p, c_p, c_i, c_ll, c_p],
     'gn_kde2d_pdf_f32': [c_p, c_i, c_p, c_i, c_d, c_d, c_d, c_d, c_p, c_p],
@@ -119,7 +123,7 @@ _SIGS = {
 }
 
 # constants mirrored from the header
-ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_LEAKY, ACT_RELU_MAX = range(6)
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_LEAKY, ACT_RELU_MAX, ACT_ELU = range(7)
 NOISE_DROPOUT, NOISE_GDROPOUT, NOISE_GNOISE = range(3)
 LOSS_BCE, LOSS_MSE, LOSS_CHISQ = range(3)
 

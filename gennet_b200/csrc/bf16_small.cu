@@ -754,6 +754,7 @@ static int smallcin_fwd(const float* x, const float* w, const float* bias, T* yy
             case GN_ACT_SIGMOID: GN_SCF(CI, GN_ACT_SIGMOID); break; \
             case GN_ACT_LEAKY: GN_SCF(CI, GN_ACT_LEAKY); break;     \
             case GN_ACT_RELU_MAX: GN_SCF(CI, GN_ACT_RELU_MAX); break; \
+            case GN_ACT_ELU: GN_SCF(CI, GN_ACT_ELU); break;         \
             default: GN_SCF(CI, GN_ACT_NONE); break;                \
         }
         if (Cin == 1) { GN_SCF_ACT(1) } else { GN_SCF_ACT(2) }
@@ -849,6 +850,7 @@ static void launch_dense_small_dgrad(dim3 grid, cudaStream_t st, const float* dy
         case GN_ACT_SIGMOID: GN_DSD(GN_ACT_SIGMOID); break;
         case GN_ACT_LEAKY: GN_DSD(GN_ACT_LEAKY); break;
         case GN_ACT_RELU_MAX: GN_DSD(GN_ACT_RELU_MAX); break;
+        case GN_ACT_ELU: GN_DSD(GN_ACT_ELU); break;
         default: GN_DSD(GN_ACT_NONE); break;
     }
 #undef GN_DSD

@@ -290,6 +290,7 @@ static void sums_geometry(long long rows, int C, int* gpb, dim3* grid, long long
         case GN_ACT_SIGMOID: { constexpr int K_ = GN_ACT_SIGMOID; KERNEL_CALL; break; }   \
         case GN_ACT_LEAKY: { constexpr int K_ = GN_ACT_LEAKY; KERNEL_CALL; break; }       \
         case GN_ACT_RELU_MAX: { constexpr int K_ = GN_ACT_RELU_MAX; KERNEL_CALL; break; } \
+        case GN_ACT_ELU: { constexpr int K_ = GN_ACT_ELU; KERNEL_CALL; break; }           \
         default: { constexpr int K_ = GN_ACT_NONE; KERNEL_CALL; break; }                  \
     }
 

@@ -251,6 +251,9 @@ extern "C" int gn_conv1d_dgrad_f32(const float* dy, const float* w, float* dx, i
     ConvDgradA fa{dy, g};
     ConvDgradB fb{w, g};
     PlainStore epi{dx, Cin};
+    // a convolution that reads <= 4 channels (the first layer of a network when the gradient flows on through it, e.g. the
+    // generator step through the discriminator of 2_model_version): one warp per input position instead of a 128-wide tile
+    if (Cin <= 4) return launch_gemv_rows(fa, fb, epi, B * g.Lp, up * k * Cout, Cin, as_stream(stream));
     return launch_gemm_simt<true, true>(fa, fb, epi, B * g.Lp, Cin, up * k * Cout, 1, as_stream(stream));
 }
 

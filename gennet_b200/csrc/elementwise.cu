@@ -542,6 +542,89 @@ extern "C" int gn_maxpool1d_bwd_f32(const float* x, const float* y, const float*
     maxpool_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, y, dy, dx, L, C, pool, L / pool, n);
     return cuda_status("maxpool_bwd_kernel");
 }
+namespace gn {
+// ---- layers of the 2_model_version networks (no_weight_code/subtract_model.py:330-390, weight_version/subtract_model.py:215-222)
+// GlobalAveragePooling1D/2D: y[b,c] = mean_l x[b,l,c]; block = 32 channels x 8 row lanes of one sample
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int C) {
+    __shared__ float sm[8][33];
+    const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < C)
+        for (int l = ry; l < L; l += 8) s += x[((size_t)b * L + l) * C + c];
+    sm[ry][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+        y[(size_t)b * C + c] = t / (float)L;
+    }
+}
+__global__ void __launch_bounds__(256) gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int L, int C,
+                                                      long long n) {
+    const float inv = 1.f / (float)L;
+    GN_EW_LOOP(i, n) {
+        int c;
+        const long long r = fast_div(i, C, c);
+        dx[i] = dy[(r / L) * C + c] * inv;
+    }
+}
+// batched transpose y[b, c, r] = x[b, r, c] through 32 x 32 shared-memory tiles (BatchNormalization(axis=1): the
+// normalised axis is moved innermost, normalised by the channels-last kernels and moved back)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+    __shared__ float tile[32][33];
+    const size_t base = (size_t)blockIdx.z * R * C;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < R && c0 + tx < C) tile[i][tx] = x[base + (size_t)(r0 + i) * C + c0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < C && r0 + tx < R) y[base + (size_t)(c0 + i) * R + r0 + tx] = tile[tx][i];
+}
+// keras.regularizers.l1 / l2 on a tensor x: loss += l1 * sum |x| + l2 * sum x^2 (double, accumulated) and, when g is
+// given, g += l1 * sign(x) + 2 * l2 * x  (kernel_regularizer on the weight gradient, activity_regularizer on dL/dy)
+__global__ void __launch_bounds__(256) reg_terms_kernel(const float* __restrict__ x, float* __restrict__ g, long long n,
+                                                        float l1, float l2, double* __restrict__ loss) {
+    __shared__ double sm[32];
+    double acc = 0.0;
+    GN_EW_LOOP(i, n) {
+        const float v = x[i];
+        acc += (double)(l1 * fabsf(v)) + (double)l2 * (double)v * (double)v;
+        if (g != nullptr) g[i] += l1 * (v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f)) + 2.f * l2 * v;
+    }
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0 && loss != nullptr) atomicAdd(loss, acc);
+}
+}  // namespace gn
+
+extern "C" int gn_gap_fwd_f32(const float* x, float* y, int B, int L, int C, void* stream) {
+    GN_REQUIRE(x && y && B >= 0 && L > 0 && C > 0 && B <= 65535, "null pointer or bad size");
+    if (B == 0) return GN_OK;
+    gn::gap_fwd_kernel<<<dim3((C + 31) / 32, B), 256, 0, as_stream(stream)>>>(x, y, L, C);
+    return cuda_status("gap_fwd_kernel");
+}
+extern "C" int gn_gap_bwd_f32(const float* dy, float* dx, int B, int L, int C, void* stream) {
+    GN_REQUIRE(dy && dx && B >= 0 && L > 0 && C > 0, "null pointer or bad size");
+    const long long n = (long long)B * L * C;
+    if (n == 0) return GN_OK;
+    gn::gap_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(dy, dx, L, C, n);
+    return cuda_status("gap_bwd_kernel");
+}
+extern "C" int gn_transpose_f32(const float* x, float* y, int B, int R, int C, void* stream) {
+    GN_REQUIRE(x && y && B >= 0 && R > 0 && C > 0 && B <= 65535 && (R + 31) / 32 <= 65535, "null pointer or bad size");
+    if (B == 0) return GN_OK;
+    gn::transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32, B), 256, 0, as_stream(stream)>>>(x, y, R, C);
+    return cuda_status("transpose_kernel");
+}
+extern "C" int gn_reg_terms_f32(const float* x, float* g, long long n, float l1, float l2, double* loss, void* stream) {
+    GN_REQUIRE(x && n >= 0 && l1 >= 0.f && l2 >= 0.f, "null pointer, n < 0 or negative coefficient");
+    if (n == 0) return GN_OK;
+    gn::reg_terms_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, g, n, l1, l2, loss);
+    return cuda_status("reg_terms_kernel");
+}
 extern "C" int gn_axpy_f32(float* a, const float* b, float alpha, long long n, void* stream) {
     GN_REQUIRE(a && b && n >= 0, "null pointer or n < 0");
     if (n == 0) return GN_OK;

@@ -98,6 +98,7 @@ __device__ __forceinline__ float act_fwd_t(float x, float a) {
     if (KIND == GN_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
     if (KIND == GN_ACT_LEAKY) return x >= 0.f ? x : a * x;
     if (KIND == GN_ACT_RELU_MAX) return fminf(fmaxf(x, 0.f), a);
+    if (KIND == GN_ACT_ELU) return x > 0.f ? x : expm1f(x);
     return x;
 }
 // derivative expressed through the OUTPUT y (all supported activations allow it)
@@ -108,6 +109,7 @@ __device__ __forceinline__ float act_bwd_t(float y, float a) {
     if (KIND == GN_ACT_SIGMOID) return y * (1.f - y);
     if (KIND == GN_ACT_LEAKY) return y >= 0.f ? 1.f : a;
     if (KIND == GN_ACT_RELU_MAX) return (y > 0.f && y < a) ? 1.f : 0.f;
+    if (KIND == GN_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
     return 1.f;
 }
 template <int K>
@@ -121,6 +123,7 @@ __device__ __forceinline__ void act_dispatch(int kind, F&& f) {
     else if (kind == GN_ACT_SIGMOID) f(ActTag<GN_ACT_SIGMOID>());
     else if (kind == GN_ACT_LEAKY) f(ActTag<GN_ACT_LEAKY>());
     else if (kind == GN_ACT_RELU_MAX) f(ActTag<GN_ACT_RELU_MAX>());
+    else if (kind == GN_ACT_ELU) f(ActTag<GN_ACT_ELU>());
     else f(ActTag<GN_ACT_NONE>());
 }
 // run-time code, one element (compare chain, no jump table); prefer act_dispatch around a loop
@@ -130,6 +133,7 @@ __device__ __forceinline__ float act_fwd(float x, int kind, float a) {
     if (kind == GN_ACT_SIGMOID) return act_fwd_t<GN_ACT_SIGMOID>(x, a);
     if (kind == GN_ACT_LEAKY) return act_fwd_t<GN_ACT_LEAKY>(x, a);
     if (kind == GN_ACT_RELU_MAX) return act_fwd_t<GN_ACT_RELU_MAX>(x, a);
+    if (kind == GN_ACT_ELU) return act_fwd_t<GN_ACT_ELU>(x, a);
     return x;
 }
 __device__ __forceinline__ float act_bwd_from_y(float y, int kind, float a) {
@@ -138,6 +142,7 @@ __device__ __forceinline__ float act_bwd_from_y(float y, int kind, float a) {
     if (kind == GN_ACT_SIGMOID) return act_bwd_t<GN_ACT_SIGMOID>(y, a);
     if (kind == GN_ACT_LEAKY) return act_bwd_t<GN_ACT_LEAKY>(y, a);
     if (kind == GN_ACT_RELU_MAX) return act_bwd_t<GN_ACT_RELU_MAX>(y, a);
+    if (kind == GN_ACT_ELU) return act_bwd_t<GN_ACT_ELU>(y, a);
     return 1.f;
 }
 

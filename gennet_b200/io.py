@@ -169,9 +169,17 @@ def layer_config(layer):
         cfg.update(filters=layer.filters, kernel_size=[layer.kh, layer.kw], strides=[layer.sh, layer.sw],
                    padding=layer.padding, data_format='channels_last', activation=layer.activation or 'linear',
                    **_kernel_cfg(layer))
+        for key in ('kernel_regularizer', 'activity_regularizer'):
+            r = getattr(layer, key, None)
+            if r is not None:
+                cfg[key] = {'class_name': 'L1L2', 'config': r.get_config()}
         return 'Conv2DTranspose', cfg
+    if t in (nn.GlobalAveragePooling1D, nn.GlobalAveragePooling2D):
+        if t is nn.GlobalAveragePooling2D:
+            cfg.update(data_format='channels_last')
+        return t.__name__, cfg
     if t is nn.BatchNormalization:
-        cfg.update(axis=-1, momentum=layer.momentum, epsilon=layer.epsilon, center=True, scale=True,
+        cfg.update(axis=layer.axis, momentum=layer.momentum, epsilon=layer.epsilon, center=True, scale=True,
                    beta_initializer=_ZEROS, gamma_initializer=_ONES, moving_mean_initializer=_ZEROS,
                    moving_variance_initializer=_ONES, beta_regularizer=None, gamma_regularizer=None,
                    beta_constraint=None, gamma_constraint=None)
@@ -261,10 +269,20 @@ def _layer_from_config(class_name, cfg, custom_objects):
         return nn.Conv2D(cfg['filters'], tuple(cfg['kernel_size']), strides=tuple(cfg.get('strides', (1, 1))),
                          padding=cfg.get('padding', 'valid'), **kw)
     if class_name in ('Conv2DTranspose', 'Deconvolution2D'):
+        def reg(c):
+            return None if not c else nn.Regularizer(l1=c['config'].get('l1', 0.0), l2=c['config'].get('l2', 0.0))
         return nn.Conv2DTranspose(cfg['filters'], tuple(cfg['kernel_size']), strides=tuple(cfg.get('strides', (1, 1))),
-                                  padding=cfg.get('padding', 'valid'), activation=act(cfg.get('activation')), **kw)
+                                  padding=cfg.get('padding', 'valid'), activation=act(cfg.get('activation')),
+                                  kernel_regularizer=reg(cfg.get('kernel_regularizer')),
+                                  activity_regularizer=reg(cfg.get('activity_regularizer')), **kw)
+    if class_name == 'GlobalAveragePooling1D':
+        return nn.GlobalAveragePooling1D(**kw)
+    if class_name == 'GlobalAveragePooling2D':
+        return nn.GlobalAveragePooling2D(**kw)
     if class_name == 'BatchNormalization':
-        return nn.BatchNormalization(momentum=cfg.get('momentum', 0.99), epsilon=cfg.get('epsilon', 1e-3), **kw)
+        ax = cfg.get('axis', -1)
+        ax = ax[0] if isinstance(ax, (list, tuple)) else ax
+        return nn.BatchNormalization(momentum=cfg.get('momentum', 0.99), epsilon=cfg.get('epsilon', 1e-3), axis=ax, **kw)
     if class_name == 'Activation':
         return nn.Activation(cfg['activation'], **kw)
     if class_name == 'LeakyReLU':

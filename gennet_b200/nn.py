@@ -141,7 +141,7 @@ def _same_pad(L, k, s):
 
 
 _ACTS = {None: _lib.ACT_NONE, 'linear': _lib.ACT_NONE, 'relu': _lib.ACT_RELU, 'tanh': _lib.ACT_TANH,
-         'sigmoid': _lib.ACT_SIGMOID}
+         'sigmoid': _lib.ACT_SIGMOID, 'elu': _lib.ACT_ELU}
 
 
 class Param:
@@ -173,6 +173,41 @@ class Ctx:
         dp = _STATE['dp']
         self.world = dp.world if dp is not None else 1
         self.dp = dp
+        self.reg_loss = None            # device double: regularisation losses of this call (keras `model.losses`)
+
+    def add_reg(self, x, g, l1, l2, with_loss=True):
+        """keras.regularizers.l1/l2 terms of tensor x: loss accumulated into self.reg_loss, gradient added into g."""
+        if with_loss and self.reg_loss is None:
+            self.reg_loss = torch.zeros(1, dtype=torch.float64, device=x.device)
+        call('gn_reg_terms_f32', ptr(x), ptr(g) if g is not None else None, x.numel(), float(l1), float(l2),
+             ptr(self.reg_loss, torch.float64) if with_loss else None, stream())
+
+
+class Regularizer:
+    """keras.regularizers.L1L2 (weight_version/subtract_model.py:217): ``regularizers.l1(0.001)``, ``regularizers.l2(0.01)``."""
+
+    def __init__(self, l1=0.0, l2=0.0):
+        self.l1, self.l2 = float(l1), float(l2)
+
+    def get_config(self):
+        return {'l1': self.l1, 'l2': self.l2}
+
+
+class regularizers:
+    """Namespace mirroring ``from keras import regularizers``."""
+    L1L2 = Regularizer
+
+    @staticmethod
+    def l1(l=0.01):
+        return Regularizer(l1=l)
+
+    @staticmethod
+    def l2(l=0.01):
+        return Regularizer(l2=l)
+
+    @staticmethod
+    def l1_l2(l1=0.01, l2=0.01):
+        return Regularizer(l1=l1, l2=l2)
 
 
 # ----------------------------------------------------------------------------- symbolic graph
@@ -283,23 +318,25 @@ class Dense(Layer):
         self.bias_src = None         # the Conv1D that produced our input when in_act is fused (set by _fuse)
 
     def build(self, in_shape):
-        assert len(in_shape) == 1, 'Dense expects a flat input, got %s' % (in_shape,)
-        fin = in_shape[0]
+        # Keras Dense acts on the last axis; leading axes (no_weight_code/subtract_model.py:262: Dense on (1, noise_dim))
+        # are folded into the rows of the GEMM
+        fin = in_shape[-1]
+        self._lead = tuple(in_shape[:-1])
         self.params = [Param(self.name + '/kernel:0', _glorot((fin, self.units), fin, self.units)),
                        Param(self.name + '/bias:0', np.zeros(self.units, np.float32))]
-        return (self.units,)
+        return self._lead + (self.units,)
 
     def _tc_planes(self):
         """Number of bf16 planes when this layer runs on the tensor-core kernels (0 = it does not): any mode but
         'float32', N a multiple of 64, a GEMM large enough to be worth two operand conversions."""
         nc = _split_planes() or (1 if _STATE['dtype'] == 'bfloat16' else 0)
-        K, N = self.input_shape[0], self.units
+        K, N = self.input_shape[-1], self.units
         if nc == 0 or N % 64 != 0 or K < 32 or K * N < (1 << 20):
             return 0
         return nc
 
     def _kp(self):
-        K, N = self.input_shape[0], self.units
+        K, N = self.input_shape[-1], self.units
         if K <= 64 and N % 128 == 0:
             return 64
         return -(-K // 128) * 128
@@ -307,7 +344,7 @@ class Dense(Layer):
     def _tc_weights(self, nc):
         key = (_STATE['wver'], nc)
         if getattr(self, '_wsplit', None) is None or self._wsplit[0] != key:
-            K, N, Kp = self.input_shape[0], self.units, self._kp()
+            K, N, Kp = self.input_shape[-1], self.units, self._kp()
             wk = _empty_bf16((nc, Kp, N))
             wt = _empty_bf16((nc, N, Kp))
             call('gn_dense_w_split_bf16', ptr(self.params[0].data), ptr(wk, BF16), ptr(wt, BF16), K, Kp, N, nc, stream())
@@ -353,6 +390,17 @@ class Dense(Layer):
         return dx
 
     def forward(self, x, ctx):
+        if self._lead:
+            return self._forward2d(x.reshape(-1, x.shape[-1]), ctx).reshape((x.shape[0],) + self._lead + (self.units,))
+        return self._forward2d(x, ctx)
+
+    def backward(self, dy, ctx, need_dx=True):
+        if self._lead:
+            dx = self._backward2d(dy.reshape(-1, self.units), ctx, need_dx)
+            return None if dx is None else dx.reshape((dy.shape[0],) + self._lead + (dx.shape[-1],))
+        return self._backward2d(dy, ctx, need_dx)
+
+    def _forward2d(self, x, ctx):
         B, K = x.shape
         self._tc = self._tc_planes()
         if self._tc:
@@ -377,7 +425,7 @@ class Dense(Layer):
         self._x, self._y = x, y
         return y
 
-    def backward(self, dy, ctx, need_dx=True):
+    def _backward2d(self, dy, ctx, need_dx=True):
         x = self._x
         B, K = x.shape
         dy = _as_f32(dy)
@@ -883,16 +931,26 @@ class Conv2DTranspose(Layer):
     prefix = 'conv2d_transpose'
 
     def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', activation=None,
-                 kernel_initializer='glorot_uniform', **kw):
+                 kernel_initializer='glorot_uniform', dilation_rate=(1, 1), kernel_regularizer=None,
+                 activity_regularizer=None, **kw):
         super().__init__(**kw)
         self.filters = int(filters)
         self.kh, self.kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
         self.sh, self.sw = (strides, strides) if isinstance(strides, int) else tuple(strides)
         self.padding = padding
         self.activation = activation
+        self.dilation_rate = (dilation_rate, dilation_rate) if isinstance(dilation_rate, int) else tuple(dilation_rate)
+        self.kernel_regularizer, self.activity_regularizer = kernel_regularizer, activity_regularizer
 
     def build(self, in_shape):
         H, W, cin = in_shape
+        if self.dilation_rate != (1, 1):
+            # Keras 2.2.4, keras/backend/tensorflow_backend.py conv2d_transpose: a dilated transposed convolution goes to
+            # tf.nn.atrous_conv2d_transpose after `assert dilation_rate[0] == dilation_rate[1]`; the generator of
+            # 2_model_version/no_weight_code/subtract_model.py:278-297 asks for (1, 9), (1, 7), (1, 2), (1, 3) and fails there
+            assert self.dilation_rate[0] == self.dilation_rate[1], \
+                'Conv2DTranspose: dilation_rate %s is rejected by Keras 2.2.4 (rates must be equal)' % (self.dilation_rate,)
+            raise NotImplementedError('dilated Conv2DTranspose is not used by any network of the reference that builds')
         if not (self.kh == 1 and self.sh == 1 and self.sw == 1 and self.padding == 'valid'):
             raise NotImplementedError('Conv2DTranspose is implemented for the reference generator geometry only '
                                       '(kernel (1, kw), strides (1, 1), padding valid)')
@@ -919,6 +977,14 @@ class Conv2DTranspose(Layer):
         code = _ACTS[self.activation]
         call('gn_conv1d_fwd_f32', ptr(x), ptr(w1), ptr(self.params[1].data), ptr(y), B * H, W, cin, self.Wout,
              self.filters, self.kw, 1, self.kw - 1, 1, code, 0.0, stream())
+        if ctx.training:
+            # regularisation losses enter the reported loss (keras `model.losses`); a kernel penalty is the same on every
+            # rank of a data-parallel run, an activity penalty sums over the ranks' batches
+            if self.activity_regularizer is not None:
+                ctx.add_reg(y, None, self.activity_regularizer.l1, self.activity_regularizer.l2)
+            if self.kernel_regularizer is not None:
+                r = self.kernel_regularizer
+                ctx.add_reg(self.params[0].data, None, r.l1 / ctx.world, r.l2 / ctx.world)
         self._x, self._y, self._w = x, y, w1
         return y
 
@@ -928,6 +994,9 @@ class Conv2DTranspose(Layer):
         H, W, cin = self.input_shape
         dy = _as_f32(dy).contiguous()
         code = _ACTS[self.activation]
+        if self.activity_regularizer is not None:
+            dy = dy.clone()          # d(l1 sum|y| + l2 sum y^2)/dy joins the incoming gradient of the layer OUTPUT
+            ctx.add_reg(self._y, dy, self.activity_regularizer.l1, self.activity_regularizer.l2, with_loss=False)
         if code != _lib.ACT_NONE:
             dy = _act_bwd(dy, self._y, code, 0.0)
         if id(self) in ctx.trainable_ids:
@@ -935,6 +1004,9 @@ class Conv2DTranspose(Layer):
             call('gn_conv1d_wgrad_f32', ptr(x), ptr(dy), ptr(dw1), ptr(self.params[1].grad), B * H, W, cin, self.Wout,
                  self.filters, self.kw, 1, self.kw - 1, 1, stream())
             call('gn_flip_transpose_f32', ptr(dw1), ptr(self.params[0].grad), self.kw, self.filters, cin, stream())
+            if self.kernel_regularizer is not None:
+                r = self.kernel_regularizer
+                ctx.add_reg(self.params[0].data, self.params[0].grad, r.l1 / ctx.world, r.l2 / ctx.world, with_loss=False)
         dx = None
         if need_dx:
             dx = _empty(x.shape)
@@ -950,11 +1022,17 @@ class BatchNormalization(Layer):
 
     def __init__(self, momentum=0.99, epsilon=1e-3, axis=-1, **kw):
         super().__init__(**kw)
-        assert axis == -1
+        assert axis in (-1, 1), 'BatchNormalization: axis -1 (channels) or 1 (no_weight_code/subtract_model.py:264-357)'
         self.momentum, self.epsilon = float(momentum), float(epsilon)
+        self.axis = axis
+
+    def _mid(self):
+        """True when the normalised axis is axis 1 of an input with more axes behind it: it is then moved innermost
+        (gn_transpose_f32), normalised by the channels-last kernels and moved back."""
+        return self.axis == 1 and len(self.input_shape) > 1
 
     def build(self, in_shape):
-        c = in_shape[-1]
+        c = in_shape[0] if (self.axis == 1 and len(in_shape) > 1) else in_shape[-1]
         n = self.name
         self.params = [Param(n + '/gamma:0', np.ones(c, np.float32)), Param(n + '/beta:0', np.zeros(c, np.float32)),
                        Param(n + '/moving_mean:0', np.zeros(c, np.float32), trainable=False),
@@ -1064,6 +1142,32 @@ class BatchNormalization(Layer):
         return dx
 
     def forward(self, x, ctx):
+        if not self._mid():
+            return self._forward_last(x, ctx)
+        x = _as_f32(x).contiguous()
+        B, A = x.shape[0], x.shape[1]
+        inner = x.numel() // (B * A)
+        xt = _empty((B, inner, A))
+        call('gn_transpose_f32', ptr(x), ptr(xt), B, A, inner, stream())
+        yt = self._forward_last(xt, ctx).contiguous()
+        y = _empty(x.shape)
+        call('gn_transpose_f32', ptr(_as_f32(yt)), ptr(y), B, inner, A, stream())
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        if not self._mid():
+            return self._backward_last(dy, ctx, need_dx)
+        dy = _as_f32(dy).contiguous()
+        B, A = dy.shape[0], dy.shape[1]
+        inner = dy.numel() // (B * A)
+        dyt = _empty((B, inner, A))
+        call('gn_transpose_f32', ptr(dy), ptr(dyt), B, A, inner, stream())
+        dxt = _as_f32(self._backward_last(dyt, ctx, need_dx)).contiguous()
+        dx = _empty(dy.shape)
+        call('gn_transpose_f32', ptr(dxt), ptr(dx), B, inner, A, stream())
+        return dx
+
+    def _forward_last(self, x, ctx):
         for l in self.chain:
             if l is not None:
                 l._chain_skip = False
@@ -1097,7 +1201,7 @@ class BatchNormalization(Layer):
         self._x, self._stats, self._n = x, stats, n_total
         return y
 
-    def backward(self, dy, ctx, need_dx=True):
+    def _backward_last(self, dy, ctx, need_dx=True):
         if getattr(self, '_fused_call', False):
             return self._backward_chain(dy, ctx)
         dy = _as_f32(dy)
@@ -1359,6 +1463,34 @@ class MaxPooling1D(Layer):
         return dx
 
 
+class GlobalAveragePooling1D(Layer):
+    """Keras GlobalAveragePooling1D / 2D (channels_last): mean over every axis between batch and channels
+    (2_model_version/no_weight_code/subtract_model.py:330,371)."""
+    prefix = 'global_average_pooling1d'
+
+    def build(self, in_shape):
+        return (in_shape[-1],)
+
+    def forward(self, x, ctx):
+        x = _as_f32(x).contiguous()
+        B, C = x.shape[0], x.shape[-1]
+        self._L = x.numel() // (B * C)
+        y = _empty((B, C))
+        call('gn_gap_fwd_f32', ptr(x), ptr(y), B, self._L, C, stream())
+        self._shape = tuple(x.shape)
+        return y
+
+    def backward(self, dy, ctx, need_dx=True):
+        dy = _as_f32(dy).contiguous()
+        dx = _empty(self._shape)
+        call('gn_gap_bwd_f32', ptr(dy), ptr(dx), self._shape[0], self._L, self._shape[-1], stream())
+        return dx
+
+
+class GlobalAveragePooling2D(GlobalAveragePooling1D):
+    prefix = 'global_average_pooling2d'
+
+
 class StackResidual(Layer):
     """bbhMahoGANy.py:164-188 ``MyLayer``: stack([x, const - x], axis=2) -> (B, n_pix, 2, 1)."""
     prefix = 'my_layer'
@@ -1601,7 +1733,7 @@ class Model(Layer):
         # BatchNormalization -> [activation] -> [dropout]: candidates for the bf16 chain kernels (decided per call by the
         # dtype of the tensor reaching the BatchNormalization; float32 tensors keep the exact per-layer kernels)
         for n in self._order:
-            if type(n.layer) is BatchNormalization:
+            if type(n.layer) is BatchNormalization and n.layer.axis != 1:
                 act = noise = None
                 cur = n
                 u = users.get(id(cur), [])
@@ -1801,14 +1933,20 @@ class Model(Layer):
             res = res * invs[0]
         else:
             res = res * torch.tensor(invs, dtype=torch.float32, device=res.device)
+        reg = ctx.reg_loss              # keras: total loss = output losses + sum(model.losses)
+        if reg is not None and ctx.world > 1:
+            ctx.dp.all_reduce(reg)
         if _return_device:
+            if reg is not None:
+                res[0] += reg[0].to(torch.float32)
             return res
         r = res.detach().cpu().numpy().astype(np.float64)      # the D2H read of the step's loss / metric
+        regv = float(reg.item()) if reg is not None else 0.0
         losses = [float(r[2 * k]) for k in range(len(outs))]
         accs = [float(r[2 * k + 1]) for k in range(len(outs))]
         if len(outs) == 1:
-            return [losses[0], accs[0]] if self.metrics else losses[0]
-        return [float(sum(losses))] + losses + (accs if self.metrics else [])
+            return [losses[0] + regv, accs[0]] if self.metrics else losses[0] + regv
+        return [float(sum(losses)) + regv] + losses + (accs if self.metrics else [])
 
     def fit(self, x, y, batch_size=32, epochs=1, verbose=0, shuffle=True, **kw):
         x = np.asarray(x)

@@ -37,6 +37,7 @@ extern "C" {
 #define GN_ACT_SIGMOID 3
 #define GN_ACT_LEAKY 4    /* param = alpha */
 #define GN_ACT_RELU_MAX 5 /* param = max_value */
+#define GN_ACT_ELU 6      /* alpha = 1 (2_model_version/weight_version/subtract_model.py:215) */
 
 /* dropout-family codes (Keras Dropout / GaussianDropout / GaussianNoise) */
 #define GN_NOISE_DROPOUT 0   /* r = keep mask (0/1):  y = x*r/(1-rate)              */
@@ -346,6 +347,17 @@ int gn_upsample1d_bwd_f32(const float* dy, float* dx, int B, int L, int C, int s
 int gn_maxpool1d_fwd_f32(const float* x, float* y, int B, int L, int C, int pool, void* stream);
 int gn_maxpool1d_bwd_f32(const float* x, const float* y, const float* dy, float* dx, int B, int L, int C, int pool,
                          void* stream);
+/* Layers of the 2_model_version networks.
+ * gn_gap_{fwd,bwd}_f32: GlobalAveragePooling1D / 2D (no_weight_code/subtract_model.py:330,371): y (B,C) = mean over the
+ *   L positions of x (B,L,C); dx = dy / L broadcast.
+ * gn_transpose_f32: y (B,C,R) = x (B,R,C); BatchNormalization(axis=1) (no_weight_code/subtract_model.py:264-292,344-357)
+ *   moves the normalised axis innermost, runs the channels-last kernels and moves it back.
+ * gn_reg_terms_f32: keras.regularizers.l1 / l2 (weight_version/subtract_model.py:217): *loss (double, ACCUMULATED; may be
+ *   NULL) += l1 sum|x| + l2 sum x^2 and, when g != NULL, g += l1 sign(x) + 2 l2 x. */
+int gn_gap_fwd_f32(const float* x, float* y, int B, int L, int C, void* stream);
+int gn_gap_bwd_f32(const float* dy, float* dx, int B, int L, int C, void* stream);
+int gn_transpose_f32(const float* x, float* y, int B, int R, int C, void* stream);
+int gn_reg_terms_f32(const float* x, float* g, long long n, float l1, float l2, double* loss, void* stream);
 /* a += b (gradient accumulation where two branches share an input, bbhMahoGANy.py:362,382) */
 int gn_axpy_f32(float* a, const float* b, float alpha, long long n, void* stream);
 /* Evaluation stage of the GAN loop (bbhMahoGANy.py:1311-1343 -> make_contour_plot :787-791, overlap_tests :853-870).

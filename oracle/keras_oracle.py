@@ -131,10 +131,14 @@ class Conv2DTranspose(Layer):
     conv2d w.r.t. its input, i.e. torch's conv_transpose2d with weight (Cin, Cout, kh, kw)."""
     kind = 'conv2d_transpose'
 
-    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', activation=None):
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', activation=None, kernel_regularizer=None,
+                 activity_regularizer=None):
         super().__init__()
         assert padding == 'valid'
         self.filters, self.k, self.s, self.activation = filters, tuple(kernel_size), tuple(strides), activation
+        # (l1, l2) pairs: keras.regularizers.L1L2 -> K.sum(l1 * |x|) + K.sum(l2 * x^2), added to the model's total loss
+        # (keras/engine/base_layer.py __call__ / add_weight, Keras 2.2.4: no division by the batch size)
+        self.kernel_regularizer, self.activity_regularizer = kernel_regularizer, activity_regularizer
 
     def build(self, in_shape, gen, dtype):
         H, W, cin = in_shape
@@ -144,8 +148,14 @@ class Conv2DTranspose(Layer):
         return ((H - 1) * self.s[0] + kh, (W - 1) * self.s[1] + kw, self.filters)
 
     def forward(self, x, training, noise):        # x (B,H,W,C) NHWC
-        y = F.conv_transpose2d(x.permute(0, 3, 1, 2), self.weights[0].permute(3, 2, 0, 1), self.weights[1], stride=self.s)
-        return apply_activation(y.permute(0, 2, 3, 1), self.activation, _kink(noise, self))
+        y = F.conv_transpose2d(x.permute(0, 3, 1, 2).contiguous(), self.weights[0].permute(3, 2, 0, 1).contiguous(), self.weights[1],
+                               stride=self.s)
+        y = apply_activation(y.permute(0, 2, 3, 1), self.activation, _kink(noise, self))
+        if training and isinstance(noise, dict):
+            for reg, t in ((self.kernel_regularizer, self.weights[0]), (self.activity_regularizer, y)):
+                if reg is not None:
+                    noise.setdefault('__losses__', []).append(reg[0] * t.abs().sum() + reg[1] * (t * t).sum())
+        return y
 
 
 ZERO_DEBIAS = True      # Keras 2.2.4 + TF 1.12 moving averages (see BatchNormalization.forward); False = plain EMA
@@ -156,19 +166,29 @@ class BatchNormalization(Layer):
     inference; moving_var is fed the n/(n-(1+eps)) 'sample variance'."""
     kind = 'bn'
 
-    def __init__(self, momentum=0.99, epsilon=1e-3):
+    def __init__(self, momentum=0.99, epsilon=1e-3, axis=-1):
         super().__init__()
-        self.momentum, self.epsilon = momentum, epsilon
+        self.momentum, self.epsilon, self.axis = momentum, epsilon, axis
         self.biased = None          # shadow accumulators of the zero-debiased moving average (not layer weights)
         self.local_step = 0
 
     def build(self, in_shape, gen, dtype):
-        c = in_shape[-1]
+        c = in_shape[0] if (self.axis == 1 and len(in_shape) > 1) else in_shape[-1]
+        self.mid = self.axis == 1 and len(in_shape) > 1
         self.weights = [torch.ones(c, dtype=dtype, requires_grad=True), torch.zeros(c, dtype=dtype, requires_grad=True)]
         self.state = [torch.zeros(c, dtype=dtype), torch.ones(c, dtype=dtype)]
         return in_shape
 
     def forward(self, x, training, noise):
+        if getattr(self, 'mid', False):
+            # axis = 1 (no_weight_code/subtract_model.py:264-357): the statistics run over every other axis; move the
+            # normalised axis last, normalise, move it back
+            perm = [0] + list(range(2, x.dim())) + [1]
+            inv = [0, x.dim() - 1] + list(range(1, x.dim() - 1))
+            return self._forward_last(x.permute(perm), training, noise).permute(inv)
+        return self._forward_last(x, training, noise)
+
+    def _forward_last(self, x, training, noise):
         g, b = self.weights
         if training:
             axes = tuple(range(x.dim() - 1))
@@ -249,6 +269,8 @@ def apply_activation(x, act, ykink=None):
         return torch.tanh(x)
     if act == 'sigmoid':
         return torch.sigmoid(x)
+    if act == 'elu':            # keras.activations.elu, alpha = 1.0
+        return torch.where(x > 0, x, torch.expm1(x))
     raise ValueError(act)
 
 
@@ -410,6 +432,17 @@ class MaxPooling1D(Layer):
         return chosen
 
 
+class GlobalAveragePooling(Layer):
+    """Keras GlobalAveragePooling1D / 2D, channels_last: mean over every axis between batch and channels."""
+    kind = 'shape'
+
+    def build(self, in_shape, gen, dtype):
+        return (in_shape[-1],)
+
+    def forward(self, x, training, noise):
+        return x.mean(dim=tuple(range(1, x.dim() - 1)))
+
+
 class StackResidual(Layer):
     """bbhMahoGANy.py:164-188 MyLayer: stack([x, const-x], axis=2) -> (B,L,2,1)."""
     kind = 'mylayer'
@@ -555,7 +588,7 @@ _PREFIX = {Dense: 'dense', Conv1D: 'conv1d', Conv2D: 'conv2d', Conv2DTranspose: 
            Activation: 'activation', LeakyReLU: 'leaky_re_lu', ReLU: 're_lu', Dropout: 'dropout',
            GaussianDropout: 'gaussian_dropout', GaussianNoise: 'gaussian_noise', Reshape: 'reshape',
            Flatten: 'flatten', UpSampling1D: 'up_sampling1d', MaxPooling1D: 'max_pooling1d',
-           StackResidual: 'my_layer', ResidualMoments: 'my_layer'}
+           StackResidual: 'my_layer', ResidualMoments: 'my_layer', GlobalAveragePooling: 'global_average_pooling1d'}
 
 
 _NAME_COUNTS = {}
@@ -678,6 +711,7 @@ def _labels(y, like):
 def _train_on_batch(model, x, y, noise=None):
     noise = dict({} if noise is None else noise)
     noise['__updates__'] = model.update_ids
+    noise['__losses__'] = []          # regularisation terms of THIS forward pass
     out = model.forward(_t(x, model), True, noise)
     outs = out if isinstance(out, list) else [out]
     ys = y if isinstance(out, list) else [y]
@@ -686,7 +720,7 @@ def _train_on_batch(model, x, y, noise=None):
         yt = _labels(yy, o)
         losses.append(model.loss_fn(yt, o).mean())
         accs.append(accuracy(yt, o.detach(), model.loss_name))
-    total = sum(losses)
+    total = sum(losses) + sum(noise.get('__losses__', []))        # + keras `model.losses` (regularisers)
     grads = torch.autograd.grad(total, model.collected, allow_unused=True)
     grads = [torch.zeros_like(p) if g is None else g for p, g in zip(model.collected, grads)]
     model.last_grads = [g.detach().numpy().copy() for g in grads]
@@ -805,6 +839,40 @@ def two_model_get_discriminative(in_dim=50, n_channels=50, conv_sz=16, leak=0.2)
     """The discriminator stored in 2_model_version/weight_version/d_model.hdf5 (model_config attribute)."""
     m = Sequential([Reshape((-1, 1)), Conv1D(n_channels, conv_sz), LeakyReLU(leak), Flatten(), Dense(50, activation='tanh'),
                     Dense(2, activation='sigmoid')])
+    m.input_shape = (in_dim,)
+    return m
+
+
+def subtract_get_generative(noise_dim=10, out_dim=50):
+    """2_model_version/weight_version/subtract_model.py:199-251: the transposed-convolution generator with ELU
+    activations and, on its first Conv2DTranspose, activity_regularizer=l1(0.001) and kernel_regularizer=l2(0.01)."""
+    L = [Reshape((-1, 1, 1)), BatchNormalization(),
+         Conv2DTranspose(128, (1, 4), activation='elu', kernel_regularizer=(0.0, 0.01), activity_regularizer=(0.001, 0.0)),
+         BatchNormalization()]
+    for f, k in ((64, 8), (32, 16), (16, 32)):
+        L += [Conv2DTranspose(f, (1, k), activation='elu'), BatchNormalization()]
+    L += [Flatten(), BatchNormalization(), Dense(out_dim, activation='elu'), BatchNormalization(), Dense(out_dim)]
+    m = Sequential(L)
+    m.input_shape = (1, noise_dim)
+    return m
+
+
+def subtract_get_discriminative(in_dim=50, n_channels=50, drate=0.3):
+    """2_model_version/weight_version/subtract_model.py:253-291."""
+    m = Sequential([Reshape((-1, 1)), Conv1D(50, 16), LeakyReLU(0.2), Dropout(drate), Flatten(), Dense(n_channels),
+                    Dropout(drate), Dense(2, activation='sigmoid')])
+    m.input_shape = (in_dim,)
+    return m
+
+
+def nw_get_discriminative(in_dim=50, gauss_noise=1.6):
+    """2_model_version/no_weight_code/subtract_model.py:322-390: three Conv1D(.., 8, tanh) -> LeakyReLU(0.2) ->
+    GaussianNoise(1.6) -> BatchNormalization(axis=1) blocks, GlobalAveragePooling1D, Dense(2, sigmoid)."""
+    L = [Reshape((-1, 1))]
+    for f in (128, 256, 512):
+        L += [Conv1D(f, 8, activation='tanh'), LeakyReLU(0.2), GaussianNoise(gauss_noise), BatchNormalization(axis=1)]
+    L += [GlobalAveragePooling(), Dense(2, activation='sigmoid')]
+    m = Sequential(L)
     m.input_shape = (in_dim,)
     return m
 

@@ -23,6 +23,8 @@ def _act(x, kind, p):
         return torch.where(x >= 0, x, p * x)
     if kind == 5:
         return torch.clamp(x, 0.0, p)
+    if kind == 6:
+        return torch.where(x > 0, x, torch.expm1(x))
     return x
 
 
@@ -37,6 +39,8 @@ def _act_bwd(y, kind, p):
         return torch.where(y >= 0, torch.ones_like(y), torch.full_like(y, p))
     if kind == 5:
         return ((y > 0) & (y < p)).float()
+    if kind == 6:
+        return torch.where(y > 0, torch.ones_like(y), y + 1.0)
     return torch.ones_like(y)
 
 
@@ -188,6 +192,22 @@ class Fake:
             dbeta.copy_(sums[:C].float())
         if dgamma is not None:
             dgamma.copy_(sums[C:2 * C].float())
+
+    def gn_gap_fwd_f32(self, x, y, B, L, C, st):
+        y.reshape(B, C).copy_(x.reshape(B, L, C).mean(1))
+
+    def gn_gap_bwd_f32(self, dy, dx, B, L, C, st):
+        dx.reshape(B, L, C).copy_((dy.reshape(B, 1, C) / L).expand(B, L, C))
+
+    def gn_transpose_f32(self, x, y, B, R, C, st):
+        y.reshape(B, C, R).copy_(x.reshape(B, R, C).permute(0, 2, 1))
+
+    def gn_reg_terms_f32(self, x, g, n, l1, l2, loss, st):
+        xv = x.reshape(-1)[:n]
+        if loss is not None:
+            loss += (l1 * xv.abs().double().sum() + l2 * (xv.double() ** 2).sum())
+        if g is not None:
+            g.reshape(-1)[:n] += l1 * torch.sign(xv) + 2 * l2 * xv
 
     def gn_conv2d_w2_pack_f32(self, w2, b, w1, b1, kh, kw, Cin, Cout, pw, st):
         w2 = w2.reshape(kh, kw, Cin, Cout)

@@ -56,6 +56,7 @@ def draw_noise(oracle_model, x, seed):
         if hasattr(l, 'biased'):
             l.biased, l.local_step = biased, step
     noise.pop('__gen__')
+    noise.pop('__losses__', None)
     return noise
 
 
@@ -319,3 +320,55 @@ def two_model_case(B, seed=0, out_dim=50):
     yz = np.zeros((B, 2), np.float32)
     yz[:, 1] = 1
     return (G, D, GAN), (og, od, ogan), X, y, z, yz
+
+
+def subtract_case(B, seed=0, noise_dim=10, out_dim=50):
+    """2_model_version/weight_version/subtract_model.py (the subtract stage of BASELINE config 5): ELU transposed-conv
+    generator with the l1 activity / l2 kernel regularisers, Dropout discriminator, stacked GAN; inputs as the script
+    samples them (noise rows, residual rows x_t - G(z); latents)."""
+    from gennet_b200 import nn
+    from gennet_b200.two_model import subtract_model as sm
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(seed)
+    sm.hyperparams.noise_dim, sm.hyperparams.outdim = noise_dim, out_dim
+    G, _ = sm.get_generative(nn.Input(shape=(1, noise_dim)), out_dim=out_dim, lr=4e-3)
+    D, _ = sm.get_discriminative(nn.Input(shape=(out_dim,)), lr=4e-3)
+    GAN, _ = sm.make_gan(nn.Input((1, noise_dim)), G, D)
+    og = ko.build(ko.subtract_get_generative(noise_dim, out_dim), seed=seed + 1)
+    og.compile('binary_crossentropy', ko.Adam(4e-3, beta_1=0.5))
+    od = ko.build(ko.subtract_get_discriminative(out_dim), seed=seed + 2)
+    od.compile('binary_crossentropy', ko.Adam(4e-3, beta_1=0.5))
+    ogan = ko.Sequential([og, od])
+    ogan.build((1, noise_dim))
+    ko.set_trainable(od, False)
+    ogan.compile('binary_crossentropy', og.optimizer)
+    ko.set_trainable(od, True)
+    sync_weights(G, og)
+    sync_weights(D, od)
+    rs = np.random.RandomState(seed)
+    X = rs.normal(0, 5, size=(2 * B, out_dim)).astype(np.float32)
+    y = np.ones((2 * B, 2), np.float32)               # the script's labels: all ones (subtract_model.py:95-97)
+    z = rs.normal(0, 1, size=(B, 1, noise_dim)).astype(np.float32)
+    yz = np.ones((B, 2), np.float32)
+    return (G, D, GAN), (og, od, ogan), X, y, z, yz
+
+
+def nw_disc_case(B, seed=0, out_dim=50):
+    """2_model_version/no_weight_code/subtract_model.py:322-390: the MSE discriminator with GaussianNoise and
+    BatchNormalization(axis=1) blocks, global average pooling, Adam with decay, soft labels."""
+    from gennet_b200 import nn
+    from gennet_b200.two_model import subtract_model_nw as nw
+    nn.clear_session()
+    ko.clear_session()
+    nn.set_seed(seed)
+    D, _ = nw.get_discriminative(nn.Input(shape=(out_dim,)), lr=1e-3)
+    od = ko.build(ko.nw_get_discriminative(out_dim), seed=seed + 2)
+    od.compile('mean_squared_error', ko.Adam(1e-3, beta_1=0.5, decay=1e-4))
+    sync_weights(D, od)
+    rs = np.random.RandomState(seed)
+    X = rs.normal(0, 5, size=(B, out_dim)).astype(np.float32)
+    y = np.zeros((B, 2), np.float32)
+    y[:B // 2, 0], y[B // 2:, 1] = rs.uniform(0.7, 1), rs.uniform(0.7, 1)
+    y[:B // 2, 1], y[B // 2:, 0] = rs.uniform(0, 0.3), rs.uniform(0, 0.3)
+    return D, od, X, y

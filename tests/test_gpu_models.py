@@ -347,3 +347,63 @@ def test_pe_train_step_batch_assembly_vs_oracle():
     pc.assert_close(rp, ro, 'pe_train_step losses', 2e-4)
     for i, (a, b) in enumerate(zip(prod.get_gradients(), orc.last_grads)):
         pc.assert_close(a, b, 'pe_train_step gradient %d' % i, 1e-4, floor=1e-3 * max(np.abs(q).max() for q in orc.last_grads))
+
+
+@pytest.mark.parametrize('which', ['pe', 'gan'])
+def test_step_parity_bf16x2(which):
+    """Two-plane split operands (three plane products per K step, 16 mantissa bits per operand): the whole-step parity
+    suite at the same rtol 1e-4, at the BASELINE n_pix.  Reported by bench.py as an extra line, not the headline."""
+    from gennet_b200 import nn
+    nn.set_compute_dtype('bf16x2')
+    try:
+        if which == 'pe':
+            prod, orc, x, y = pc.pe_case(2048, 8)
+            errs, w0 = pc.compare_step(prod, orc, x, y)
+            pc.compare_weights(prod, orc, w0)
+        else:
+            (g, d, dg), (og, od, ocomp), z, sX, sy = pc.gan_case(2048, 8)
+            pc.assert_close(g.predict(z), og.predict(z), 'generator.predict')
+            errs, w0 = pc.compare_step(d, od, sX, sy)
+            pc.resync([(d, od)])
+            errs2, w0 = pc.compare_step(dg, ocomp, z, [1] * 8, check_predict=False)
+            errs.update({'g_' + k: v for k, v in errs2.items()})
+        print('bf16x2 %s n_pix 2048: max gradient error %.2e' % (which, max(v for k, v in errs.items() if 'grad' in k)))
+    finally:
+        nn.set_compute_dtype('float32')
+
+
+@pytest.mark.parametrize('mode', ['float32', 'bf16x3'])
+def test_subtract_stage_parity(mode):
+    """2_model_version/weight_version/subtract_model.py (config 5 subtract stage): ELU transposed-conv generator with the
+    l1 activity / l2 kernel regularisers, Dropout discriminator: predict, D step, G step through the frozen D."""
+    from gennet_b200 import nn
+    nn.set_compute_dtype(mode)
+    try:
+        (G, D, GAN), (og, od, ogan), X, y, z, yz = pc.subtract_case(16)
+        pc.assert_close(G.predict(z), og.predict(z), 'G.predict')
+        errs, w0 = pc.compare_step(D, od, X, y)
+        pc.compare_weights(D, od, w0)
+        pc.resync([(D, od)])
+        dw = [w.copy() for w in D.get_weights()]
+        errs, w0 = pc.compare_step(GAN, ogan, z, yz, check_predict=False)
+        assert all(np.array_equal(a, b) for a, b in zip(dw, D.get_weights()))
+        pc.compare_weights(G, og, w0[:len(G.get_weights())])
+    finally:
+        nn.set_compute_dtype('float32')
+
+
+@pytest.mark.parametrize('mode', ['float32', 'bf16x3'])
+def test_nw_discriminator_parity(mode):
+    """2_model_version/no_weight_code/subtract_model.py:322-390: Conv1D(tanh) -> LeakyReLU -> GaussianNoise(1.6) ->
+    BatchNormalization(axis=1) blocks, GlobalAveragePooling1D, MSE, Adam with decay."""
+    from gennet_b200 import nn
+    nn.set_compute_dtype(mode)
+    try:
+        D, od, X, y = pc.nw_disc_case(16)
+        if mode == 'bf16x3':
+            assert [l._path() for l in D.all_layers() if isinstance(l, nn.Conv1D)] == ['f32', 'tc3', 'tc3']
+        pc.assert_close(D.predict(X), od.predict(X), 'D.predict')
+        errs, w0 = pc.compare_step(D, od, X, y)
+        pc.compare_weights(D, od, w0)
+    finally:
+        nn.set_compute_dtype('float32')
