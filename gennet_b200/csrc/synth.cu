@@ -143,9 +143,15 @@ __device__ __forceinline__ float2 ld_stream(const float2* p) {
     return v;
 }
 __device__ __forceinline__ float2 ld_table(const float2* p) {
+#ifdef GN_TABLE_LDG
+    // experiment: movable read-only loads; with a register budget that holds the tables (GN_SYNTH_REGS >= 128) and
+    // persistent CTAs (GN_WAVES = 1) the compiler keeps the per-thread twiddles / coefficients in registers across series
+    return __ldg(p);
+#else
     float2 v;
     asm volatile("ld.global.ca.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
     return v;
+#endif
 }
 
 // shared-memory index with one pad slot per 16 complex values (kills the stride-R store conflicts)
