@@ -34,10 +34,11 @@ FS, T_OBS, N_TEMPLATES = 2048, 4, 1024
 PE_BATCH, GAN_BATCH = 512, 128
 UNIT = 'samples/s'
 METRICS = {'gan': 'train samples/sec (synth+whiten+G/D step)', 'pe': 'train samples/sec (synth+whiten+CNN-PE step)'}
-MODES = {'bf16x3': 'bf16x3', 'bf16x2': 'bf16x2', 'bf16': 'bfloat16', 'fp32': 'float32'}
-DTYPES = {'bf16x3': 'f32 (3-plane split-bf16 operands on tcgen05, fp32 accumulate)',
+MODES = {'f16x2': 'f16x2', 'bf16x3': 'bf16x3', 'bf16x2': 'bf16x2', 'bf16': 'bfloat16', 'fp32': 'float32'}
+DTYPES = {'f16x2': 'f32 (scaled fp16-pair operands on tcgen05, fp32 accumulate)',
+          'bf16x3': 'f32 (3-plane split-bf16 operands on tcgen05, fp32 accumulate)',
           'bf16x2': 'f32 (2-plane split-bf16 operands on tcgen05, fp32 accumulate)', 'bf16': 'bf16', 'fp32': 'f32'}
-PLANE_PRODUCTS = {'bf16x3': 6, 'bf16x2': 3, 'bf16': 1}
+PLANE_PRODUCTS = {'f16x2': 3, 'bf16x3': 6, 'bf16x2': 3, 'bf16': 1}
 
 
 def peaks():
@@ -159,13 +160,16 @@ def make_inputs(seed, device):
 _CONV_ARGPOS = {'gn_conv1d_fwd_f32': 4, 'gn_conv1d_dgrad_f32': 3, 'gn_conv1d_wgrad_f32': 4,
                 'gn_conv1d_fwd_bf16': 4, 'gn_conv1d_dgrad_bf16': 5, 'gn_conv1d_wgrad_bf16': 4,
                 'gn_conv1d_fwd_bf16x3': 5, 'gn_conv1d_dgrad_bf16x3': 6, 'gn_conv1d_wgrad_bf16x3': 5,
+                'gn_conv1d_fwd_f16x2': 7, 'gn_conv1d_dgrad_f16x2': 8, 'gn_conv1d_wgrad_f16x2': 7,
                 'gn_conv1d_smallcin_fwd_bf16': 4, 'gn_conv1d_smallcin_wgrad_bf16': 4, 'gn_conv1d_smallcin_dgrad_bf16': 3,
                 'gn_conv1d_smallcin_fwd_f32': 4, 'gn_conv1d_smallcin_wgrad_f32': 4, 'gn_conv1d_smallcin_dgrad_f32': 3}
 _DENSE_ARGPOS = {'gn_dense_fwd_f32': 4, 'gn_dense_dgrad_f32': 3, 'gn_dense_wgrad_f32': 4,
-                 'gn_dense_fwd_bf16x3': 5, 'gn_dense_dgrad_bf16x3': 5, 'gn_dense_wgrad_bf16x3': 5}
+                 'gn_dense_fwd_bf16x3': 5, 'gn_dense_dgrad_bf16x3': 5, 'gn_dense_wgrad_bf16x3': 5,
+                 'gn_dense_fwd_f16x2': 6, 'gn_dense_dgrad_f16x2': 7, 'gn_dense_wgrad_f16x2': 7}
 TENSOR_CORE_CALLS = ('gn_conv1d_fwd_bf16', 'gn_conv1d_dgrad_bf16', 'gn_conv1d_wgrad_bf16', 'gn_conv1d_fwd_bf16x3',
                      'gn_conv1d_dgrad_bf16x3', 'gn_conv1d_wgrad_bf16x3', 'gn_dense_fwd_bf16x3', 'gn_dense_dgrad_bf16x3',
-                     'gn_dense_wgrad_bf16x3')
+                     'gn_dense_wgrad_bf16x3', 'gn_conv1d_fwd_f16x2', 'gn_conv1d_dgrad_f16x2', 'gn_conv1d_wgrad_f16x2',
+                     'gn_dense_fwd_f16x2', 'gn_dense_dgrad_f16x2', 'gn_dense_wgrad_f16x2')
 
 
 def call_flops(name, args):
@@ -210,7 +214,8 @@ def tensor_roofline(tot, mode, step_ms_events):
     flops = sum(tot[k][2] for k in names)
     ach = flops / (ms / 1e3) / 1e12 if ms > 0 else 0.0
     prod = PLANE_PRODUCTS.get(mode, 1)
-    traffic, src = ncu_traffic('conv_tc3_step_traffic' if mode in ('bf16x3', 'bf16x2') else 'conv_tc_step_traffic')
+    traffic, src = ncu_traffic({'f16x2': 'conv_f16x2_step_traffic', 'bf16x3': 'conv_tc3_step_traffic', 'bf16x2': 'conv_tc3_step_traffic'}.get(
+        mode, 'conv_tc_step_traffic'))
     all_ms = sum(v[0] for v in tot.values())
     return {'bound': 'tensor', 'kernel': 'tcgen05 Conv1D/Dense implicit GEMM family (%s)' % ', '.join(sorted(names)),
             'achieved': ach, 'peak': tf_burst, 'unit': 'TFLOP/s', 'frac': ach / tf_burst,
@@ -218,7 +223,7 @@ def tensor_roofline(tot, mode, step_ms_events):
             'peak_source': which + ' (cuBLAS bf16; burst = kernel timed alone, sustained = inside a long step)',
             'plane_products_per_flop': prod, 'issued_tensor_tflops': ach * prod,
             'tensor_pipe_frac_burst': ach * prod / tf_burst, 'tensor_pipe_frac_sustained': ach * prod / tf_sust,
-            'note': ('achieved counts ALGORITHMIC float32 flops; every product is issued as %d bf16 tcgen05.mma '
+            'note': ('achieved counts ALGORITHMIC float32 flops; every product is issued as %d 16-bit tcgen05.mma '
                      '(split operands), so the tensor pipe executes achieved x %d' % (prod, prod)) if prod > 1 else
                     'bf16 operands: one tcgen05.mma per product',
             'traffic': traffic, 'traffic_source': src, 'avg_launch_ms': ms / max(launches, 1e-9),
@@ -563,7 +568,11 @@ def run_ours(args):
            'vs_baseline': None, 'dtype': DTYPES[args.mode], 'data': 'synthetic',
            'config': {'workload': head.describe(), 'name': args.config, 'batch_per_gpu': head.B,
                       'global_batch': head.B * world, 'n_pix': FS, 'fft_len': FS * T_OBS, 'parallelism': 'dp%d' % world,
-                      'precision': {'bf16x3': 'float32 activations / weights / gradients / Adam; Conv1D and Conv2D operands split into three '
+                      'precision': {'f16x2': 'float32 activations / weights / gradients / Adam; Conv1D, Conv2D and Dense operands as scaled '
+                                             'fp16 pairs (two fp16 planes of the tensor times a power of two from its max |x|: 22-23 bits '
+                                             'relative to the tensor scale), three tcgen05.mma per K step into two fp32 TMEM accumulators '
+                                             '(float32-class accuracy: tests/test_gpu_conv_f16x2.py, tests/test_gpu_models.py at rtol 1e-4)',
+                                    'bf16x3': 'float32 activations / weights / gradients / Adam; Conv1D and Conv2D operands split into three '
                                               'bf16 planes, six tcgen05.mma per K step into two fp32 TMEM accumulators (float32-class '
                                               'accuracy: tests/test_gpu_conv_tc3.py, tests/test_gpu_models.py at rtol 1e-4)',
                                     'bf16x2': 'as bf16x3 with two planes / three products (~2^-16 relative)',

@@ -51,6 +51,17 @@ _SIGS = {
     'gn_dense_fwd_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     'gn_dense_dgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     'gn_dense_wgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_amax_f32': [c_p, c_ll, c_p, c_p],
+    'gn_split_f32_f16x2': [c_p, c_p, c_p, c_i, c_ll, c_p],
+    'gn_conv_w_split_f16x2': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    'gn_conv1d_fwd_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_conv1d_dgrad_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_conv1d_wgrad_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    'gn_split_pad_f32_f16x2': [c_p, c_p, c_p, c_ll, c_i, c_i, c_p],
+    'gn_dense_w_split_f16x2': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    'gn_dense_fwd_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_dense_dgrad_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
+    'gn_dense_wgrad_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_fwd_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_smallcin_wgrad_bf16': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_conv1d_smallcin_dgrad_bf16': [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

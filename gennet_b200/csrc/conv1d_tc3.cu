@@ -25,6 +25,7 @@
 //   dgrad   : dX[b,j,ci] = act'(Xin[b,j,ci]) * sum_{t,co} dY[b,(j+p-t)/s,co] * W[t,ci,co]    A=dY  (K-major)  B=W [t][ci][co]
 //   wgrad   : dW[t,ci,co] = sum_{b,l} X[b,l*s+t-p,ci] * dY[b,l,co]                           A=X^T, B=dY (both MN-major)
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace gn {
 
@@ -55,6 +56,44 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16 (&p)[3]) {
     }
 }
 
+// ---- the scaled fp16 pair format ("f16x2"): a float32 tensor t with max |t| = amax is carried as two fp16 planes
+//        t = (T0 + 2^-11 T1) / s,   s = 2^f16s_exp(amax),   T0 = fp16(t s),   T1 = fp16((t s - T0) 2^11)
+//   s places amax in [2^14, 2^15), so T0 keeps 11 significant bits for every element down to 2^-28 amax and T1 the next
+//   11 (fp16 is a normal number from 2^-14 up): 22-23 bits of t relative to the TENSOR's scale.  A product needs three
+//   plane products, T0 W0 into MAIN and T0 W1 + T1 W0 into CORR (the dropped T1 W1 is <= 2^-22 |t||w|); the epilogue
+//   forms (MAIN + 2^-11 CORR) / (s_t s_w).
+constexpr float F16S_LO = 2048.f;             // 2^11: weight of the low plane
+__host__ __device__ __forceinline__ int f16s_exp(float amax) {
+#ifdef __CUDA_ARCH__
+    const uint32_t bits = __float_as_uint(amax);
+#else
+    uint32_t bits;
+    memcpy(&bits, &amax, 4);
+#endif
+    int e = (int)((bits >> 23) & 0xffu) - 127;      // floor(log2(amax)) of a normal number
+    if (e < -100) e = -100;                          // zero / tiny tensors: any scale will do, keep 2^se finite
+    return 14 - e;                                   // in [-113, 114]
+}
+__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
+__device__ __forceinline__ void split2h(float xs, uint16_t& h0, uint16_t& h1) {
+    const __half a = __float2half_rn(xs);
+    const __half b = __float2half_rn((xs - __half2float(a)) * F16S_LO);
+    h0 = __half_as_ushort(a);
+    h1 = __half_as_ushort(b);
+}
+// one element -> the 16-bit patterns of its planes in either format (F16S: `scale` = s, NC == 2)
+template <int NC, bool F16S>
+__device__ __forceinline__ void split_bits(float x, float scale, uint16_t (&p)[3]) {
+    if (F16S) {
+        split2h(x * scale, p[0], p[1]);
+    } else {
+        __nv_bfloat16 b[3];
+        split3<NC>(x, b);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) p[i] = __bfloat16_as_ushort(b[i]);
+    }
+}
+
 struct Tc3Args {
     int B, L, Lout, Cin, Cout, k, s, p;   // convolution geometry (L = input length, Lout = output length)
     int mode;                              // 0 fwd, 1 dgrad
@@ -71,7 +110,29 @@ struct Tc3Args {
     // digit of the tile index counts K chunks of `kchunk` channels; every chunk adds its partial result into the
     // zeroed fp32 output with vector reductions, bias / activation follow in bias_act_kernel
     int kchunks, kchunk;
+    // scaled fp16 pair operands (NC == 2): max |.| of the tensors behind A and B (device scalars), else null
+    const float* amax_a;
+    const float* amax_b;
+    float* amax_out;                       // optional: max |result| over the valid elements, atomically (bits as uint)
 };
+
+// operand formats: the instruction descriptor's A / B format fields (bits 7, 10) are 1 for bf16, 0 for fp16
+__device__ __forceinline__ uint32_t idesc_fmt(uint32_t idesc_bf16, bool f16) {
+    return f16 ? (idesc_bf16 & ~((1u << 7) | (1u << 10))) : idesc_bf16;
+}
+// factors of the epilogue: result = (MAIN + cs * CORR) * ia * ib
+struct OutScale {
+    float cs, ia, ib;
+};
+__device__ __forceinline__ OutScale out_scale(const float* amax_a, const float* amax_b) {
+    OutScale o{1.f, 1.f, 1.f};
+    if (amax_a != nullptr) {
+        o.cs = 1.f / F16S_LO;
+        o.ia = pow2i(-f16s_exp(__ldg(amax_a)));
+        o.ib = pow2i(-f16s_exp(__ldg(amax_b)));
+    }
+    return o;
+}
 
 template <int BN, int NC>
 struct T3Smem {
@@ -184,7 +245,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else if (warp == 1) {
         // MMA issuer: per stage two K = 16 steps x the plane pairs, all into the same fp32 accumulator
-        constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+        const uint32_t idesc = idesc_fmt(make_idesc(TC_BM, BN, 0, 0), a.amax_a != nullptr);
         // K-major SWIZZLE_64B descriptor: hi = SBO (8 rows x 64 B = 512 B) | version 1 | layout type 4; lo = addr >> 4 | LBO
         constexpr uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);
         using PP = PlanePairs<NC>;
@@ -235,6 +296,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int row = q * 32 + lane;
         constexpr int NS = BN / 32;
         const int rows_out = (a.mode == 0) ? a.Lout : a.L;
+        const OutScale os = out_scale(a.amax_a, a.amax_b);
+        float amax_run = 0.f;
         int ti_local = 0;
         TileWalker<BN> tw;
         for (tw.init(blockIdx.x, gridDim.x, n_nt, a.m_tiles, npar, walk_b); tw.valid(); tw.next(), ++ti_local) {
@@ -266,8 +329,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                     if (NC > 1) {
                         tmem_ld32(tacc + (uint32_t)(BN + sl * 32), v);
+                        // bf16 planes: cs = ia = ib = 1, i.e. MAIN + CORR rounded once as before
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
+                        for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), os.cs, f[i]) * os.ia * os.ib;
                     }
                 }
                 if (sl + T3_EPI_SETS >= NS) {
@@ -304,6 +368,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] *= act_bwd_t<decltype(tag)::kind>(mk[i], a.act_param);
                     });
+                }
+                if (a.amax_out != nullptr && valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) amax_run = fmaxf(amax_run, fabsf(f[i]));
                 }
                 if (valid) {
                     if (a.out != nullptr) {
@@ -356,6 +424,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
             }
         }
+        if (a.amax_out != nullptr) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) amax_run = fmaxf(amax_run, __shfl_xor_sync(0xffffffffu, amax_run, o));
+            if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(a.amax_out), __float_as_uint(amax_run));
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -382,6 +455,8 @@ struct Tc3WgradArgs {
     int out_tiles;      // k * m_tiles * n_tiles_n
     int rows_store;     // input channels (rows of dW per tap) that exist in dw: < Cin when the planes are zero-padded (Dense)
     float* dw;          // (k, rows_store, Cout) fp32
+    const float* amax_x;   // scaled fp16 pair operands (NC == 2): max |.| of x and dy (device scalars), else null
+    const float* amax_dy;
 };
 
 struct Wg3Unit {
@@ -486,7 +561,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(TC_BM, BN, 1, 1);     // both operands MN-major
+        const uint32_t idesc = idesc_fmt(make_idesc(TC_BM, BN, 1, 1), a.amax_x != nullptr);     // both operands MN-major
         // MN-major SWIZZLE_128B: 64-element MN blocks LBO = NC * 4 KB apart, 8-row K groups SBO = 1024 B apart,
         // 16 K rows per instruction = 2048 B
         constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -529,6 +604,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const OutScale os = out_scale(a.amax_x, a.amax_dy);
         int ul = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
             const Wg3Unit w = decode_wg3_unit<BN>(u, a);
@@ -544,7 +620,8 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     uint32_t vc[32];
                     tmem_ld32(tacc + (uint32_t)(BN + c0), vc);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vc[i]));
+                    for (int i = 0; i < 32; ++i)
+                        v[i] = __float_as_uint(fmaf(__uint_as_float(vc[i]), os.cs, __uint_as_float(v[i])) * os.ia * os.ib);
                 }
                 if (c0 + 32 >= BN) {
                     tc_fence_before();
@@ -579,10 +656,35 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
-// float32 tensor -> NC bf16 planes (plane p at planes + p * n).  Eight elements per thread and step.
-template <int NC>
-__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes,
-                                                        long long n) {
+// max |x| of a float32 tensor into a device scalar (zeroed by the caller): non-negative floats order like their bits
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+    const long long n4 = n >> 2;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+static int launch_amax(const float* x, long long n, float* amax, cudaStream_t st) {
+    cudaMemsetAsync(amax, 0, sizeof(float), st);
+    if (n == 0) return GN_OK;
+    const long long want = (n / 4 + 255) / 256;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want < 8LL * num_sms() ? want : 8LL * num_sms()));
+    amax_kernel<<<grid, 256, 0, st>>>(x, n, amax);
+    return cuda_status("amax_kernel");
+}
+
+// float32 tensor -> 16-bit planes (plane p at planes + p * n): NC bf16 planes, or the scaled fp16 pair (F16S, NC == 2,
+// `amax` = device scalar holding max |x|).  Eight elements per thread and step.
+template <int NC, bool F16S>
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ x, uint16_t* __restrict__ planes,
+                                                        long long n, const float* __restrict__ amax) {
+    const float scale = F16S ? pow2i(f16s_exp(__ldg(amax))) : 1.f;
     const long long n8 = n >> 3;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += step) {
@@ -592,16 +694,11 @@ __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict_
         uint32_t pk[3][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 p0[3], p1[3];
-            split3<NC>(f[2 * e], p0);
-            split3<NC>(f[2 * e + 1], p1);
+            uint16_t p0[3], p1[3];
+            split_bits<NC, F16S>(f[2 * e], scale, p0);
+            split_bits<NC, F16S>(f[2 * e + 1], scale, p1);
 #pragma unroll
-            for (int pl = 0; pl < NC; ++pl) {
-                __nv_bfloat162 h;
-                h.x = p0[pl];
-                h.y = p1[pl];
-                pk[pl][e] = *reinterpret_cast<uint32_t*>(&h);
-            }
+            for (int pl = 0; pl < NC; ++pl) pk[pl][e] = (uint32_t)p0[pl] | ((uint32_t)p1[pl] << 16);
         }
 #pragma unroll
         for (int pl = 0; pl < NC; ++pl)
@@ -610,8 +707,8 @@ __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict_
     // tail (n % 8 elements)
     const long long t0 = n8 << 3;
     for (long long i = t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        __nv_bfloat16 p[3];
-        split3<NC>(x[i], p);
+        uint16_t p[3];
+        split_bits<NC, F16S>(x[i], scale, p);
 #pragma unroll
         for (int pl = 0; pl < NC; ++pl) planes[(size_t)pl * n + i] = p[pl];
     }
@@ -631,17 +728,18 @@ __global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict__ y, co
     }
 }
 
-// float32 matrix (rows, K) -> NC bf16 planes of a (rows, Kp) matrix, columns K..Kp-1 zero (Dense operands whose feature
+// float32 matrix (rows, K) -> planes of a (rows, Kp) matrix, columns K..Kp-1 zero (Dense operands whose feature
 // count is not a multiple of the 64-channel tile, e.g. the generator's Dense(100 -> 128 n_pix), bbhMahoGANy.py:234)
-template <int NC>
-__global__ void __launch_bounds__(256) split_pad_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes,
-                                                            long long rows, int K, int Kp) {
+template <int NC, bool F16S>
+__global__ void __launch_bounds__(256) split_pad_f32_kernel(const float* __restrict__ x, uint16_t* __restrict__ planes,
+                                                            long long rows, int K, int Kp, const float* __restrict__ amax) {
+    const float scale = F16S ? pow2i(f16s_exp(__ldg(amax))) : 1.f;
     const long long n = rows * Kp;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / Kp;
         const int c = (int)(i - r * Kp);
-        __nv_bfloat16 p[3];
-        split3<NC>(c < K ? x[r * K + c] : 0.f, p);
+        uint16_t p[3];
+        split_bits<NC, F16S>(c < K ? x[r * K + c] : 0.f, scale, p);
 #pragma unroll
         for (int pl = 0; pl < NC; ++pl) planes[(size_t)pl * n + i] = p[pl];
     }
@@ -650,11 +748,12 @@ __global__ void __launch_bounds__(256) split_pad_f32_kernel(const float* __restr
 // weights: f32 (k,Cin,Cout) -> planes of the same layout (dgrad B operand) and planes of the transposed layout
 // (k,Cout,Cin) (forward B operand); one 32 x 32 (ci, co) tile of one tap per block, transposed through shared memory
 // Cin_src <= Cin: rows Cin_src..Cin-1 of every tap are written as zeros (w holds (k, Cin_src, Cout))
-template <int NC>
-__global__ void __launch_bounds__(256) conv_w_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wk,
-                                                           __nv_bfloat16* __restrict__ wt, int k, int Cin, int Cout,
-                                                           int Cin_src) {
-    __shared__ __nv_bfloat16 tile[NC][32][33];
+template <int NC, bool F16S>
+__global__ void __launch_bounds__(256) conv_w_split_kernel(const float* __restrict__ w, uint16_t* __restrict__ wk,
+                                                           uint16_t* __restrict__ wt, int k, int Cin, int Cout,
+                                                           int Cin_src, const float* __restrict__ amax) {
+    __shared__ uint16_t tile[NC][32][33];
+    const float scale = F16S ? pow2i(f16s_exp(__ldg(amax))) : 1.f;
     const int t = blockIdx.z;
     const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -664,8 +763,8 @@ __global__ void __launch_bounds__(256) conv_w_split_kernel(const float* __restri
         const int ci = ci0 + r, co = co0 + tx;
         if (ci < Cin && co < Cout) {
             const size_t i = ((size_t)t * Cin + ci) * Cout + co;
-            __nv_bfloat16 p[3];
-            split3<NC>(ci < Cin_src ? w[((size_t)t * Cin_src + ci) * Cout + co] : 0.f, p);
+            uint16_t p[3];
+            split_bits<NC, F16S>(ci < Cin_src ? w[((size_t)t * Cin_src + ci) * Cout + co] : 0.f, scale, p);
 #pragma unroll
             for (int pl = 0; pl < NC; ++pl) {
                 wk[pl * plane + i] = p[pl];
@@ -798,44 +897,86 @@ static int check_tc3_geom(int B, int L, int Cin, int Lout, int Cout, int k, int 
 
 using namespace gn;
 
-extern "C" int gn_split_f32_bf16(const float* x, void* planes, long long n, int nc, void* stream) {
+// ---- operand conversion.  amax == nullptr: nc bf16 planes; else the scaled fp16 pair (two planes) with the tensor's
+// max |x| in the device scalar `amax` (computed here unless have_amax: a producer already accumulated it)
+static int split_impl(const float* x, void* planes, long long n, int nc, float* amax, int have_amax, void* stream) {
     GN_REQUIRE(x && planes && n >= 0 && nc >= 1 && nc <= 3, "null pointer, n < 0 or planes not in 1..3");
     GN_REQUIRE(n % 8 == 0 || nc == 1, "element count must be a multiple of 8 (16-byte aligned planes)");
     if (n == 0) return GN_OK;
     const long long want = (n / 8 + 255) / 256;
     const unsigned grid = (unsigned)(want < 1 ? 1 : (want < 16LL * num_sms() ? want : 16LL * num_sms()));
     cudaStream_t st = as_stream(stream);
-    if (nc == 3) split_f32_kernel<3><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, n);
-    else if (nc == 2) split_f32_kernel<2><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, n);
-    else split_f32_kernel<1><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, n);
+    uint16_t* pl = (uint16_t*)planes;
+    if (amax != nullptr) {
+        if (!have_amax) {
+            int rc = launch_amax(x, n, amax, st);
+            if (rc != GN_OK) return rc;
+        }
+        split_f32_kernel<2, true><<<grid, 256, 0, st>>>(x, pl, n, amax);
+    } else if (nc == 3) split_f32_kernel<3, false><<<grid, 256, 0, st>>>(x, pl, n, nullptr);
+    else if (nc == 2) split_f32_kernel<2, false><<<grid, 256, 0, st>>>(x, pl, n, nullptr);
+    else split_f32_kernel<1, false><<<grid, 256, 0, st>>>(x, pl, n, nullptr);
     return cuda_status("split_f32_kernel");
 }
+extern "C" int gn_split_f32_bf16(const float* x, void* planes, long long n, int nc, void* stream) {
+    return split_impl(x, planes, n, nc, nullptr, 0, stream);
+}
+extern "C" int gn_split_f32_f16x2(const float* x, void* planes, float* amax, int have_amax, long long n, void* stream) {
+    GN_REQUIRE(amax, "null pointer");
+    return split_impl(x, planes, n, 2, amax, have_amax, stream);
+}
+extern "C" int gn_amax_f32(const float* x, long long n, float* amax, void* stream) {
+    GN_REQUIRE(x && amax && n >= 0, "null pointer or n < 0");
+    return launch_amax(x, n, amax, as_stream(stream));
+}
 
-extern "C" int gn_conv_w_split_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, int nc, void* stream) {
-    GN_REQUIRE(w && wk && wt && k > 0 && Cin > 0 && Cout > 0 && nc >= 1 && nc <= 3, "null pointer or bad size");
+static int w_split_impl(const float* w, void* wk, void* wt, int k, int Cin, int Cout, int Cin_src, int nc, float* amax,
+                        void* stream) {
+    GN_REQUIRE(w && wk && wt && k > 0 && Cin > 0 && Cout > 0 && Cin_src > 0 && Cin_src <= Cin && nc >= 1 && nc <= 3,
+               "null pointer or bad size");
     GN_REQUIRE(k <= 65535 && (Cin + 31) / 32 <= 65535, "weight tensor too large for the split grid");
     dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32), (unsigned)k);
     cudaStream_t st = as_stream(stream);
-    if (nc == 3) conv_w_split_kernel<3><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout, Cin);
-    else if (nc == 2) conv_w_split_kernel<2><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout, Cin);
-    else conv_w_split_kernel<1><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, k, Cin, Cout, Cin);
+    uint16_t *a = (uint16_t*)wk, *b = (uint16_t*)wt;
+    if (amax != nullptr) {
+        int rc = launch_amax(w, (long long)k * Cin_src * Cout, amax, st);
+        if (rc != GN_OK) return rc;
+        conv_w_split_kernel<2, true><<<grid, 256, 0, st>>>(w, a, b, k, Cin, Cout, Cin_src, amax);
+    } else if (nc == 3) conv_w_split_kernel<3, false><<<grid, 256, 0, st>>>(w, a, b, k, Cin, Cout, Cin_src, nullptr);
+    else if (nc == 2) conv_w_split_kernel<2, false><<<grid, 256, 0, st>>>(w, a, b, k, Cin, Cout, Cin_src, nullptr);
+    else conv_w_split_kernel<1, false><<<grid, 256, 0, st>>>(w, a, b, k, Cin, Cout, Cin_src, nullptr);
     return cuda_status("conv_w_split_kernel");
 }
-
-static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L, int Cin, int Lout,
-                   int Cout, int k, int stride, int pad_left, int act, float act_param, int nc, int kchunks, void* stream);
-
-extern "C" int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L,
-                                    int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
-                                    float act_param, int nc, void* stream) {
-    return fwd_tc3(xs, wts, bias, y, ys, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param, nc, 1, stream);
+extern "C" int gn_conv_w_split_bf16(const float* w, void* wk, void* wt, int k, int Cin, int Cout, int nc, void* stream) {
+    return w_split_impl(w, wk, wt, k, Cin, Cout, Cin, nc, nullptr, stream);
+}
+extern "C" int gn_conv_w_split_f16x2(const float* w, void* wk, void* wt, float* amax, int k, int Cin, int Cout,
+                                     void* stream) {
+    GN_REQUIRE(amax, "null pointer");
+    return w_split_impl(w, wk, wt, k, Cin, Cout, Cin, 2, amax, stream);
 }
 
-static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L, int Cin, int Lout,
-                   int Cout, int k, int stride, int pad_left, int act, float act_param, int nc, int kchunks, void* stream) {
+// operand format of a compute call: nc bf16 planes (amax pointers null) or scaled fp16 pairs
+struct Fmt3 {
+    int nc;
+    const float* amax_a;      // tensor behind the A operand (x or dy)
+    const float* amax_b;      // tensor behind the B operand (w; dy in the weight gradient)
+};
+static int check_fmt(const Fmt3& f) {
+    GN_REQUIRE((f.amax_a == nullptr) == (f.amax_b == nullptr), "both operands must be in the same plane format");
+    GN_REQUIRE(f.amax_a == nullptr || f.nc == 2, "scaled fp16 operands come as two planes");
+    return GN_OK;
+}
+
+static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, float* y_amax, int B, int L, int Cin,
+                   int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param, Fmt3 f, int kchunks,
+                   void* stream) {
     GN_REQUIRE(xs && wts && (y || ys), "null pointer");
+    const int nc = f.nc;
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
     if (rc != GN_OK) return rc;
+    if ((rc = check_fmt(f)) != GN_OK) return rc;
+    GN_REQUIRE(f.amax_a == nullptr || ys == nullptr, "the epilogue re-split exists for bf16 planes only");
     CUtensorMap mA, mB;
     const int BN = pick_bn3(Cout, nc, k * Cin / 16);
     // A: X planes viewed as (Cin, L, B, NC); 128 output rows per tile, traversal stride = conv stride
@@ -850,24 +991,43 @@ static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y,
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
     a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = y;
     a.planes = (__nv_bfloat16*)ys; a.plane_stride = (long long)B * Lout * Cout;
+    a.amax_a = f.amax_a; a.amax_b = f.amax_b; a.amax_out = y_amax;
     a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
     a.kchunks = kchunks;
     a.kchunk = Cin / kchunks;
-    GN_REQUIRE(kchunks == 1 || (B == 1 && k == 1 && ys == nullptr && y != nullptr && a.kchunk % T3_BK == 0),
+    GN_REQUIRE(kchunks == 1 || (B == 1 && k == 1 && ys == nullptr && y != nullptr && y_amax == nullptr && a.kchunk % T3_BK == 0),
                "split-K needs B == 1, k == 1, a float32 output and chunks of whole 32-channel blocks");
     const long long tiles = (long long)(kchunks > 1 ? kchunks : B) * a.m_tiles * (Cout / BN);
     cudaStream_t st = as_stream(stream);
+    if (y_amax != nullptr) cudaMemsetAsync(y_amax, 0, sizeof(float), st);
     if (nc == 3) return dispatch_conv_tc3<3>(BN, false, mA, mB, a, tiles, st);
     if (nc == 2) return dispatch_conv_tc3<2>(BN, false, mA, mB, a, tiles, st);
     return dispatch_conv_tc3<1>(BN, false, mA, mB, a, tiles, st);
 }
 
-extern "C" int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, float* dx, void* dxs,
-                                      float* dx_colsum, int B, int L, int Cin, int Lout, int Cout, int k, int stride,
-                                      int pad_left, int in_act, float in_act_param, int nc, void* stream) {
+extern "C" int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L,
+                                    int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
+                                    float act_param, int nc, void* stream) {
+    return fwd_tc3(xs, wts, bias, y, ys, nullptr, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param,
+                   Fmt3{nc, nullptr, nullptr}, 1, stream);
+}
+extern "C" int gn_conv1d_fwd_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax,
+                                   const float* bias, float* y, float* y_amax, int B, int L, int Cin, int Lout, int Cout,
+                                   int k, int stride, int pad_left, int act, float act_param, void* stream) {
+    GN_REQUIRE(x_amax && w_amax, "null pointer");
+    return fwd_tc3(xs, wts, bias, y, nullptr, y_amax, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param,
+                   Fmt3{2, x_amax, w_amax}, 1, stream);
+}
+
+static int dgrad_tc3(const void* dys, const void* wks, const float* x_in, float* dx, void* dxs, float* dx_colsum,
+                     float* dx_amax, int B, int L, int Cin, int Lout, int Cout, int k, int stride, int pad_left, int in_act,
+                     float in_act_param, Fmt3 f, void* stream) {
     GN_REQUIRE(dys && wks && (dx || dxs), "null pointer");
+    const int nc = f.nc;
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
     if (rc != GN_OK) return rc;
+    if ((rc = check_fmt(f)) != GN_OK) return rc;
+    GN_REQUIRE(f.amax_a == nullptr || dxs == nullptr, "the epilogue re-split exists for bf16 planes only");
     CUtensorMap mA, mB;
     const int BN = pick_bn3(Cin, nc, 0);      // mask, column sums and re-split make this epilogue too long to expose
     // A: dY planes viewed as (Cout, Lout, B, NC), 128 rows, unit traversal stride (parity classes handle the conv stride)
@@ -884,7 +1044,9 @@ extern "C" int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const fl
     a.mode = 1; a.act = in_act; a.act_param = in_act_param; a.aux = x_in; a.out = dx;
     a.planes = (__nv_bfloat16*)dxs; a.plane_stride = (long long)B * L * Cin;
     a.colsum = dx_colsum;
+    a.amax_a = f.amax_a; a.amax_b = f.amax_b; a.amax_out = dx_amax;
     if (dx_colsum != nullptr) cudaMemsetAsync(dx_colsum, 0, sizeof(float) * (size_t)Cin, st);
+    if (dx_amax != nullptr) cudaMemsetAsync(dx_amax, 0, sizeof(float), st);
     const int rows = (L + stride - 1) / stride;      // rows of the largest parity class
     a.m_tiles = (rows + TC_BM - 1) / TC_BM;
     const bool aux = (x_in != nullptr && in_act != GN_ACT_NONE);
@@ -894,12 +1056,29 @@ extern "C" int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const fl
     return dispatch_conv_tc3<1>(BN, aux, mA, mB, a, tiles, st);
 }
 
+extern "C" int gn_conv1d_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, float* dx, void* dxs,
+                                      float* dx_colsum, int B, int L, int Cin, int Lout, int Cout, int k, int stride,
+                                      int pad_left, int in_act, float in_act_param, int nc, void* stream) {
+    return dgrad_tc3(dys, wks, x_in, dx, dxs, dx_colsum, nullptr, B, L, Cin, Lout, Cout, k, stride, pad_left, in_act,
+                     in_act_param, Fmt3{nc, nullptr, nullptr}, stream);
+}
+extern "C" int gn_conv1d_dgrad_f16x2(const void* dys, const float* dy_amax, const void* wks, const float* w_amax,
+                                     const float* x_in, float* dx, float* dx_colsum, float* dx_amax, int B, int L, int Cin,
+                                     int Lout, int Cout, int k, int stride, int pad_left, int in_act, float in_act_param,
+                                     void* stream) {
+    GN_REQUIRE(dy_amax && w_amax, "null pointer");
+    return dgrad_tc3(dys, wks, x_in, dx, nullptr, dx_colsum, dx_amax, B, L, Cin, Lout, Cout, k, stride, pad_left, in_act,
+                     in_act_param, Fmt3{2, dy_amax, w_amax}, stream);
+}
+
 static int wgrad_tc3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout,
-                     int Cout, int k, int stride, int pad_left, int nc, int rows_store, void* stream) {
+                     int Cout, int k, int stride, int pad_left, Fmt3 f, int rows_store, void* stream) {
     GN_REQUIRE(xs && dys && dw, "null pointer");
     GN_REQUIRE(db == nullptr || dy != nullptr, "the bias gradient needs the float32 dy");
+    const int nc = f.nc;
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
     if (rc != GN_OK) return rc;
+    if ((rc = check_fmt(f)) != GN_OK) return rc;
     GN_REQUIRE(Cin % 128 == 0 || (Cin == 64 && Cout % 128 == 0), "wgrad needs Cin % 128 == 0, or Cin == 64 with Cout % 128 == 0");
     cudaStream_t st = as_stream(stream);
     CUtensorMap mX, mDY;
@@ -917,6 +1096,7 @@ static int wgrad_tc3(const void* xs, const void* dys, const float* dy, float* dw
     a.lblocks = (Lout + 31) / 32;
     a.iters_total = B * a.lblocks;
     a.dw = dw;
+    a.amax_x = f.amax_a; a.amax_dy = f.amax_b;
     const bool swap = (Cin == 64);
     int m_tiles, BN;
     if (!swap) { m_tiles = Cin / 128; BN = pick_bn3(Cout, nc, 0); a.n_tiles_n = Cout / BN; }
@@ -938,36 +1118,52 @@ static int wgrad_tc3(const void* xs, const void* dys, const float* dy, float* dw
 
 extern "C" int gn_conv1d_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int B, int L,
                                       int Cin, int Lout, int Cout, int k, int stride, int pad_left, int nc, void* stream) {
-    return wgrad_tc3(xs, dys, dy, dw, db, B, L, Cin, Lout, Cout, k, stride, pad_left, nc, Cin, stream);
+    return wgrad_tc3(xs, dys, dy, dw, db, B, L, Cin, Lout, Cout, k, stride, pad_left, Fmt3{nc, nullptr, nullptr}, Cin, stream);
+}
+extern "C" int gn_conv1d_wgrad_f16x2(const void* xs, const float* x_amax, const void* dys, const float* dy_amax,
+                                     const float* dy, float* dw, float* db, int B, int L, int Cin, int Lout, int Cout, int k,
+                                     int stride, int pad_left, void* stream) {
+    GN_REQUIRE(x_amax && dy_amax, "null pointer");
+    return wgrad_tc3(xs, dys, dy, dw, db, B, L, Cin, Lout, Cout, k, stride, pad_left, Fmt3{2, x_amax, dy_amax}, Cin, stream);
 }
 
 // ---- Dense layers on the same kernels: a Dense GEMM is a convolution with one tap over a single "sample" whose
 // positions are the batch rows (M).  Kp = feature count padded to a multiple of 64 in the PLANES only.
-extern "C" int gn_split_pad_f32_bf16(const float* x, void* planes, long long rows, int K, int Kp, int nc, void* stream) {
+static int split_pad_impl(const float* x, void* planes, long long rows, int K, int Kp, int nc, float* amax, void* stream) {
     GN_REQUIRE(x && planes && rows >= 0 && K > 0 && Kp >= K && nc >= 1 && nc <= 3, "null pointer or bad size");
     if (rows == 0) return GN_OK;
     const long long n = rows * Kp, want = (n + 255) / 256;
     const unsigned grid = (unsigned)(want < 16LL * num_sms() ? want : 16LL * num_sms());
     cudaStream_t st = as_stream(stream);
-    if (nc == 3) split_pad_f32_kernel<3><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, rows, K, Kp);
-    else if (nc == 2) split_pad_f32_kernel<2><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, rows, K, Kp);
-    else split_pad_f32_kernel<1><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes, rows, K, Kp);
+    uint16_t* pl = (uint16_t*)planes;
+    if (amax != nullptr) {
+        int rc = launch_amax(x, rows * K, amax, st);
+        if (rc != GN_OK) return rc;
+        split_pad_f32_kernel<2, true><<<grid, 256, 0, st>>>(x, pl, rows, K, Kp, amax);
+    } else if (nc == 3) split_pad_f32_kernel<3, false><<<grid, 256, 0, st>>>(x, pl, rows, K, Kp, nullptr);
+    else if (nc == 2) split_pad_f32_kernel<2, false><<<grid, 256, 0, st>>>(x, pl, rows, K, Kp, nullptr);
+    else split_pad_f32_kernel<1, false><<<grid, 256, 0, st>>>(x, pl, rows, K, Kp, nullptr);
     return cuda_status("split_pad_f32_kernel");
+}
+extern "C" int gn_split_pad_f32_bf16(const float* x, void* planes, long long rows, int K, int Kp, int nc, void* stream) {
+    return split_pad_impl(x, planes, rows, K, Kp, nc, nullptr, stream);
+}
+extern "C" int gn_split_pad_f32_f16x2(const float* x, void* planes, float* amax, long long rows, int K, int Kp, void* stream) {
+    GN_REQUIRE(amax, "null pointer");
+    return split_pad_impl(x, planes, rows, K, Kp, 2, amax, stream);
 }
 
 extern "C" int gn_dense_w_split_bf16(const float* w, void* wk, void* wt, int K, int Kp, int N, int nc, void* stream) {
-    GN_REQUIRE(w && wk && wt && K > 0 && Kp >= K && N > 0 && nc >= 1 && nc <= 3, "null pointer or bad size");
-    GN_REQUIRE((Kp + 31) / 32 <= 65535, "weight matrix too large for the split grid");
-    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((Kp + 31) / 32), 1u);
-    cudaStream_t st = as_stream(stream);
-    if (nc == 3) conv_w_split_kernel<3><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, 1, Kp, N, K);
-    else if (nc == 2) conv_w_split_kernel<2><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, 1, Kp, N, K);
-    else conv_w_split_kernel<1><<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wt, 1, Kp, N, K);
-    return cuda_status("conv_w_split_kernel(dense)");
+    GN_REQUIRE(K > 0 && Kp >= K, "bad feature counts");
+    return w_split_impl(w, wk, wt, 1, Kp, N, K, nc, nullptr, stream);
+}
+extern "C" int gn_dense_w_split_f16x2(const float* w, void* wk, void* wt, float* amax, int K, int Kp, int N, void* stream) {
+    GN_REQUIRE(amax && K > 0 && Kp >= K, "null pointer or bad feature counts");
+    return w_split_impl(w, wk, wt, 1, Kp, N, K, 2, amax, stream);
 }
 
-extern "C" int gn_dense_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int M, int Kp,
-                                   int N, int act, float act_param, int nc, void* stream) {
+static int dense_fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int M, int Kp, int N, int act,
+                         float act_param, Fmt3 f, void* stream) {
     GN_REQUIRE(M > 0 && M <= 65535 * 128, "bad batch size");
     // split-K: a long contraction with few output tiles (burst discriminator Dense(16128 -> 1024) at batch 16-128 has
     // 8 tiles for 148 SMs) is cut into chunks of >= 256 channels that run as separate tiles and meet in the output by
@@ -983,10 +1179,10 @@ extern "C" int gn_dense_fwd_bf16x3(const void* xs, const void* wts, const float*
             if (tiles * c <= 2LL * num_sms() || kc > 4096) chunks = c;
         }
     }
-    if (chunks == 1) return fwd_tc3(xs, wts, bias, y, ys, 1, M, Kp, M, N, 1, 1, 0, act, act_param, nc, 1, stream);
+    if (chunks == 1) return fwd_tc3(xs, wts, bias, y, ys, nullptr, 1, M, Kp, M, N, 1, 1, 0, act, act_param, f, 1, stream);
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
-    int rc = fwd_tc3(xs, wts, nullptr, y, nullptr, 1, M, Kp, M, N, 1, 1, 0, GN_ACT_NONE, 0.f, nc, chunks, stream);
+    int rc = fwd_tc3(xs, wts, nullptr, y, nullptr, nullptr, 1, M, Kp, M, N, 1, 1, 0, GN_ACT_NONE, 0.f, f, chunks, stream);
     if (rc != GN_OK) return rc;
     if (bias != nullptr || act != GN_ACT_NONE) {
         const long long n4 = (long long)M * N / 4;
@@ -996,16 +1192,38 @@ extern "C" int gn_dense_fwd_bf16x3(const void* xs, const void* wts, const float*
     }
     return GN_OK;
 }
+extern "C" int gn_dense_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int M, int Kp,
+                                   int N, int act, float act_param, int nc, void* stream) {
+    return dense_fwd_tc3(xs, wts, bias, y, ys, M, Kp, N, act, act_param, Fmt3{nc, nullptr, nullptr}, stream);
+}
+extern "C" int gn_dense_fwd_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax,
+                                  const float* bias, float* y, int M, int Kp, int N, int act, float act_param, void* stream) {
+    GN_REQUIRE(x_amax && w_amax, "null pointer");
+    return dense_fwd_tc3(xs, wts, bias, y, nullptr, M, Kp, N, act, act_param, Fmt3{2, x_amax, w_amax}, stream);
+}
 
 extern "C" int gn_dense_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, float* dx, float* dx_colsum, int M,
                                      int K, int N, int in_act, float in_act_param, int nc, void* stream) {
     GN_REQUIRE(K % 64 == 0, "the data gradient needs an unpadded feature count (K % 64 == 0)");
-    return gn_conv1d_dgrad_bf16x3(dys, wks, x_in, dx, nullptr, dx_colsum, 1, M, K, M, N, 1, 1, 0, in_act, in_act_param, nc,
-                                  stream);
+    return dgrad_tc3(dys, wks, x_in, dx, nullptr, dx_colsum, nullptr, 1, M, K, M, N, 1, 1, 0, in_act, in_act_param,
+                     Fmt3{nc, nullptr, nullptr}, stream);
+}
+extern "C" int gn_dense_dgrad_f16x2(const void* dys, const float* dy_amax, const void* wks, const float* w_amax,
+                                    const float* x_in, float* dx, float* dx_colsum, int M, int K, int N, int in_act,
+                                    float in_act_param, void* stream) {
+    GN_REQUIRE(dy_amax && w_amax, "null pointer");
+    GN_REQUIRE(K % 64 == 0, "the data gradient needs an unpadded feature count (K % 64 == 0)");
+    return dgrad_tc3(dys, wks, x_in, dx, nullptr, dx_colsum, nullptr, 1, M, K, M, N, 1, 1, 0, in_act, in_act_param,
+                     Fmt3{2, dy_amax, w_amax}, stream);
 }
 
 extern "C" int gn_dense_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int M, int K,
                                      int N, int Kp, int nc, void* stream) {
     GN_REQUIRE(K > 0 && Kp >= K, "bad feature counts");
-    return wgrad_tc3(xs, dys, dy, dw, db, 1, M, Kp, M, N, 1, 1, 0, nc, K, stream);
+    return wgrad_tc3(xs, dys, dy, dw, db, 1, M, Kp, M, N, 1, 1, 0, Fmt3{nc, nullptr, nullptr}, K, stream);
+}
+extern "C" int gn_dense_wgrad_f16x2(const void* xs, const float* x_amax, const void* dys, const float* dy_amax,
+                                    const float* dy, float* dw, float* db, int M, int K, int N, int Kp, void* stream) {
+    GN_REQUIRE(x_amax && dy_amax && K > 0 && Kp >= K, "null pointer or bad feature counts");
+    return wgrad_tc3(xs, dys, dy, dw, db, 1, M, Kp, M, N, 1, 1, 0, Fmt3{2, x_amax, dy_amax}, K, stream);
 }

@@ -42,15 +42,23 @@ def set_compute_dtype(name):
     runs on the tcgen05 tensor cores with its operands split into three bf16 planes (six plane products per K step
     accumulated in fp32 tensor memory: float32-class accuracy, the mode the parity tests and the benchmark headline
     use).  'bf16x2': two planes, three products (~2^-16 relative).
+    'f16x2': as 'bf16x3' with the operands as scaled fp16 pairs (two fp16 planes of the tensor times a power of two taken
+    from its largest element: 22-23 bits relative to the tensor's scale, three plane products per K step = half the
+    tensor-core work of 'bf16x3').
     'bfloat16': activations and conv operands in bf16 with fp32 accumulation on the tcgen05 tensor cores, fp32
     master weights / gradients / optimizer (throughput mode, stated tolerance in tests/test_gpu_models.py)."""
-    assert name in ('float32', 'bfloat16', 'bf16x3', 'bf16x2')
+    assert name in ('float32', 'bfloat16', 'bf16x3', 'bf16x2', 'f16x2')
     _STATE['dtype'] = name
 
 
 def _split_planes():
-    """Number of bf16 planes of the split tensor-core mode (0 = not in that mode)."""
-    return {'bf16x3': 3, 'bf16x2': 2}.get(_STATE['dtype'], 0)
+    """Number of 16-bit planes of the split tensor-core mode (0 = not in that mode)."""
+    return {'bf16x3': 3, 'bf16x2': 2, 'f16x2': 2}.get(_STATE['dtype'], 0)
+
+
+def _f16s():
+    """True when the planes are scaled fp16 pairs (tensor attribute _gn_amax = device scalar max |x|)."""
+    return _STATE['dtype'] == 'f16x2'
 
 
 def set_bn_zero_debias(flag):
@@ -115,11 +123,80 @@ def _as_bf16(x):
     return y
 
 
+F16 = torch.float16
+
+
+def _pdt():
+    """dtype of the operand planes in the current split mode."""
+    return F16 if _f16s() else BF16
+
+
+def _empty_planes(shape):
+    return torch.empty(shape, dtype=_pdt(), device=device())
+
+
 def _split(x, nc):
-    """float32 tensor -> (nc,) + shape bf16 planes with x = sum of the planes to float32 accuracy."""
-    planes = _empty_bf16((nc,) + tuple(x.shape))
-    call('gn_split_f32_bf16', ptr(x), ptr(planes, BF16), x.numel(), nc, stream())
+    """float32 tensor -> (nc,) + shape 16-bit planes: bf16 planes whose sum is x to float32 accuracy, or (mode 'f16x2')
+    the scaled fp16 pair with the device scalar max |x| attached as planes._gn_amax (taken from x._gn_amax when the kernel
+    that produced x already accumulated it)."""
+    planes = _empty_planes((nc,) + tuple(x.shape))
+    if _f16s():
+        amax = getattr(x, '_gn_amax', None)
+        have = amax is not None
+        if not have:
+            amax = _empty((1,))
+        call('gn_split_f32_f16x2', ptr(x), ptr(planes, F16), ptr(amax), 1 if have else 0, x.numel(), stream())
+        planes._gn_amax = amax
+    else:
+        call('gn_split_f32_bf16', ptr(x), ptr(planes, BF16), x.numel(), nc, stream())
     return planes
+
+
+def _w_split(w, k, cin, cout, nc):
+    """Conv weights f32 (k,cin,cout) -> (wk planes (nc,k,cin,cout), wt planes (nc,k,cout,cin))."""
+    wk = _empty_planes((nc, k, cin, cout))
+    wt = _empty_planes((nc, k, cout, cin))
+    if _f16s():
+        amax = _empty((1,))
+        call('gn_conv_w_split_f16x2', ptr(w), ptr(wk, F16), ptr(wt, F16), ptr(amax), k, cin, cout, stream())
+        wk._gn_amax = wt._gn_amax = amax
+    else:
+        call('gn_conv_w_split_bf16', ptr(w), ptr(wk, BF16), ptr(wt, BF16), k, cin, cout, nc, stream())
+    return wk, wt
+
+
+def _conv_fwd_split(xs, wt, bias, y, ys, want_amax, geom, code, par, nc):
+    """Forward convolution on the split-operand tensor-core kernels; geom = (B, L, Cin, Lout, Cout, k, stride, pad).
+    want_amax ('f16x2'): the epilogue also accumulates max |y| for the consumer's split."""
+    if _f16s():
+        am = _empty((1,)) if want_amax else None
+        call('gn_conv1d_fwd_f16x2', ptr(xs, F16), ptr(xs._gn_amax), ptr(wt, F16), ptr(wt._gn_amax), bias, ptr(y), ptr(am),
+             *geom, code, par, stream())
+        if am is not None:
+            y._gn_amax = am
+    else:
+        call('gn_conv1d_fwd_bf16x3', ptr(xs, BF16), ptr(wt, BF16), bias, ptr(y), ptr(ys, BF16) if ys is not None else None,
+             *geom, code, par, nc, stream())
+
+
+def _conv_dgrad_split(dys, wk, xin, dx, dxs, sink, want_amax, geom, code, par, nc):
+    if _f16s():
+        am = _empty((1,)) if want_amax else None
+        call('gn_conv1d_dgrad_f16x2', ptr(dys, F16), ptr(dys._gn_amax), ptr(wk, F16), ptr(wk._gn_amax), xin, ptr(dx), sink,
+             ptr(am), *geom, code, par, stream())
+        if am is not None:
+            dx._gn_amax = am
+    else:
+        call('gn_conv1d_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), xin, ptr(dx), ptr(dxs, BF16) if dxs is not None else None,
+             sink, *geom, code, par, nc, stream())
+
+
+def _conv_wgrad_split(xs, dys, dy, dw, db, geom, nc):
+    if _f16s():
+        call('gn_conv1d_wgrad_f16x2', ptr(xs, F16), ptr(xs._gn_amax), ptr(dys, F16), ptr(dys._gn_amax), ptr(dy), dw, db, *geom,
+             stream())
+    else:
+        call('gn_conv1d_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), dw, db, *geom, nc, stream())
 
 
 def _act_bwd(dy, y, code, param):
@@ -345,9 +422,15 @@ class Dense(Layer):
         key = (_STATE['wver'], nc)
         if getattr(self, '_wsplit', None) is None or self._wsplit[0] != key:
             K, N, Kp = self.input_shape[-1], self.units, self._kp()
-            wk = _empty_bf16((nc, Kp, N))
-            wt = _empty_bf16((nc, N, Kp))
-            call('gn_dense_w_split_bf16', ptr(self.params[0].data), ptr(wk, BF16), ptr(wt, BF16), K, Kp, N, nc, stream())
+            wk = _empty_planes((nc, Kp, N)) if nc > 1 else _empty_bf16((nc, Kp, N))
+            wt = _empty_planes((nc, N, Kp)) if nc > 1 else _empty_bf16((nc, N, Kp))
+            if nc > 1 and _f16s():
+                amax = _empty((1,))
+                call('gn_dense_w_split_f16x2', ptr(self.params[0].data), ptr(wk, F16), ptr(wt, F16), ptr(amax), K, Kp, N,
+                     stream())
+                wk._gn_amax = wt._gn_amax = amax
+            else:
+                call('gn_dense_w_split_bf16', ptr(self.params[0].data), ptr(wk, BF16), ptr(wt, BF16), K, Kp, N, nc, stream())
             self._wsplit = (key, wk, wt)
         return self._wsplit[1], self._wsplit[2]
 
@@ -355,12 +438,19 @@ class Dense(Layer):
         B, K = x.shape
         N, Kp = self.units, self._kp()
         x = _as_f32(x).contiguous()
-        xs = _empty_bf16((nc, B, Kp))
-        call('gn_split_pad_f32_bf16', ptr(x), ptr(xs, BF16), B, K, Kp, nc, stream())
         wk, wt = self._tc_weights(nc)
         y = _empty((B, N))
-        call('gn_dense_fwd_bf16x3', ptr(xs, BF16), ptr(wt, BF16), ptr(self.params[1].data), ptr(y), None, B, Kp, N,
-             _ACTS[self.activation], 0.0, nc, stream())
+        if nc > 1 and _f16s():
+            xs = _empty_planes((nc, B, Kp))
+            xs._gn_amax = _empty((1,))
+            call('gn_split_pad_f32_f16x2', ptr(x), ptr(xs, F16), ptr(xs._gn_amax), B, K, Kp, stream())
+            call('gn_dense_fwd_f16x2', ptr(xs, F16), ptr(xs._gn_amax), ptr(wt, F16), ptr(wt._gn_amax), ptr(self.params[1].data),
+                 ptr(y), B, Kp, N, _ACTS[self.activation], 0.0, stream())
+        else:
+            xs = _empty_bf16((nc, B, Kp))
+            call('gn_split_pad_f32_bf16', ptr(x), ptr(xs, BF16), B, K, Kp, nc, stream())
+            call('gn_dense_fwd_bf16x3', ptr(xs, BF16), ptr(wt, BF16), ptr(self.params[1].data), ptr(y), None, B, Kp, N,
+                 _ACTS[self.activation], 0.0, nc, stream())
         self._xs = xs
         return x, y
 
@@ -369,10 +459,15 @@ class Dense(Layer):
         B, K = x.shape
         N, Kp = self.units, self._kp()
         dy = _as_f32(dy).contiguous()
+        f16 = nc > 1 and _f16s()
         dys = _split(dy, nc)
         if id(self) in ctx.trainable_ids:
-            call('gn_dense_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), ptr(self.params[0].grad),
-                 ptr(self.params[1].grad), B, K, N, Kp, nc, stream())
+            if f16:
+                call('gn_dense_wgrad_f16x2', ptr(xs, F16), ptr(xs._gn_amax), ptr(dys, F16), ptr(dys._gn_amax), ptr(dy),
+                     ptr(self.params[0].grad), ptr(self.params[1].grad), B, K, N, Kp, stream())
+            else:
+                call('gn_dense_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), ptr(self.params[0].grad),
+                     ptr(self.params[1].grad), B, K, N, Kp, nc, stream())
         dx = None
         if need_dx:
             dx = _empty((B, K))
@@ -380,8 +475,13 @@ class Dense(Layer):
                 wk, wt = self._tc_weights(nc)
                 code, par = self.in_act if self.in_act is not None else (_lib.ACT_NONE, 0.0)
                 sink, _ = _bias_sink(self, ctx, K)
-                call('gn_dense_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), ptr(x) if self.in_act is not None else None,
-                     ptr(dx), sink if self.in_act is not None else None, B, K, N, code, par, nc, stream())
+                if f16:
+                    call('gn_dense_dgrad_f16x2', ptr(dys, F16), ptr(dys._gn_amax), ptr(wk, F16), ptr(wk._gn_amax),
+                         ptr(x) if self.in_act is not None else None, ptr(dx), sink if self.in_act is not None else None,
+                         B, K, N, code, par, stream())
+                else:
+                    call('gn_dense_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), ptr(x) if self.in_act is not None else None,
+                         ptr(dx), sink if self.in_act is not None else None, B, K, N, code, par, nc, stream())
                 dx._gn_preact = self.in_act is not None
                 dx._gn_db_done = self.in_act is not None and sink is not None
             else:
@@ -541,10 +641,7 @@ class Conv1D(Layer):
         """(wk planes (nc,k,Cin,Cout), wt planes (nc,k,Cout,Cin)) of the split tensor-core mode, per weight version."""
         if self._wsplit is None or self._wsplit[0] != (_STATE['wver'], nc):
             L, cin = self.input_shape
-            wk = _empty_bf16((nc, self.k, cin, self.filters))
-            wt = _empty_bf16((nc, self.k, self.filters, cin))
-            call('gn_conv_w_split_bf16', ptr(self.params[0].data), ptr(wk, BF16), ptr(wt, BF16), self.k, cin,
-                 self.filters, nc, stream())
+            wk, wt = _w_split(self.params[0].data, self.k, cin, self.filters, nc)
             self._wsplit = ((_STATE['wver'], nc), wk, wt)
         return self._wsplit[1], self._wsplit[2]
 
@@ -557,22 +654,25 @@ class Conv1D(Layer):
         code, par = self._act()
         xs = getattr(x, '_gn_planes', None)
         x = _as_f32(x).contiguous()
-        if xs is None or xs.shape[0] != nc or self.fused_up != 1:
+        if xs is None or xs.shape[0] != nc or xs.dtype != _pdt() or self.fused_up != 1:
             xs = _split(x, nc)
         if self.fused_up != 1:
             Lp = L // self.fused_up
-            xu = _empty_bf16((nc, B, L, cin))
-            call('gn_upsample1d_fwd_bf16', ptr(xs, BF16), ptr(xu, BF16), nc * B, Lp, cin, self.fused_up, stream())
+            xu = _empty_planes((nc, B, L, cin))
+            # a 16-bit copy: the planes of the repeated tensor are the repeated planes (and share the scale)
+            call('gn_upsample1d_fwd_bf16', ptr(xs, None), ptr(xu, None), nc * B, Lp, cin, self.fused_up, stream())
+            if _f16s():
+                xu._gn_amax = xs._gn_amax
             xs = xu
         wk, wt = self._split_weights(nc)
         y = _empty((B, self.Lout, self.filters))
         cons = self.plane_consumer
+        feeds_tc3 = cons is not None and cons.fused_up == 1 and cons._path() == 'tc3'
         ys = None
-        if cons is not None and cons.fused_up == 1 and cons._path() == 'tc3':
+        if feeds_tc3 and not _f16s():
             ys = _empty_bf16((nc, B, self.Lout, self.filters))
-        call('gn_conv1d_fwd_bf16x3', ptr(xs, BF16), ptr(wt, BF16), ptr(self.params[1].data), ptr(y),
-             ptr(ys, BF16) if ys is not None else None, B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad,
-             code, par, nc, stream())
+        _conv_fwd_split(xs, wt, ptr(self.params[1].data), y, ys, feeds_tc3,
+                        (B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad), code, par, nc)
         if ys is not None:
             y._gn_planes = ys
         self._xs = xs
@@ -586,12 +686,12 @@ class Conv1D(Layer):
         tr = id(self) in ctx.trainable_ids
         dys = getattr(dy, '_gn_planes', None)
         dy = _as_f32(dy).contiguous()
-        if dys is None or dys.shape[0] != nc:
+        if dys is None or dys.shape[0] != nc or dys.dtype != _pdt():
             dys = _split(dy, nc)
+        geom = (B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad)
         if tr:
             db = None if db_done else ptr(self.params[1].grad)
-            call('gn_conv1d_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), ptr(self.params[0].grad), db, B, L,
-                 cin, self.Lout, self.filters, self.k, self.s, self.pad, nc, stream())
+            _conv_wgrad_split(xs, dys, dy, ptr(self.params[0].grad), db, geom, nc)
         dx = None
         if need_dx:
             wk, wt = self._split_weights(nc)
@@ -600,11 +700,10 @@ class Conv1D(Layer):
             sink, _ = _bias_sink(self, ctx, cin)
             # the producer takes the planes of dx as they are when the activation mask was applied here
             emit = self.fused_up == 1 and self.in_act is not None and getattr(self.bias_src, '_mode', None) == 'tc3'
-            dxs = _empty_bf16((nc, B, L, cin)) if emit else None
+            dxs = _empty_bf16((nc, B, L, cin)) if (emit and not _f16s()) else None
             xin = x if (self.in_act is not None and self.fused_up == 1) else None
-            call('gn_conv1d_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), ptr(xin) if xin is not None else None, ptr(dx),
-                 ptr(dxs, BF16) if dxs is not None else None, sink if xin is not None else None, B, L, cin, self.Lout,
-                 self.filters, self.k, self.s, self.pad, icode if xin is not None else _lib.ACT_NONE, ipar, nc, stream())
+            _conv_dgrad_split(dys, wk, ptr(xin) if xin is not None else None, dx, dxs, sink if xin is not None else None,
+                              emit, geom, icode if xin is not None else _lib.ACT_NONE, ipar, nc)
             if self.fused_up != 1:
                 dxp = _empty((B, L // self.fused_up, cin))
                 call('gn_upsample1d_bwd_f32', ptr(dx), ptr(dxp), B, L // self.fused_up, cin, self.fused_up, stream())
@@ -814,10 +913,7 @@ class Conv2D(Layer):
         if self._wsplit is None or self._wsplit[0] != (_STATE['wver'], nc):
             H, W, cin = self.input_shape
             w1, b1 = self._pack()
-            wk = _empty_bf16((nc,) + tuple(w1.shape))
-            wt = _empty_bf16((nc, self.kh, 2 * self.filters, 2 * cin))
-            call('gn_conv_w_split_bf16', ptr(w1), ptr(wk, BF16), ptr(wt, BF16), self.kh, 2 * cin, 2 * self.filters, nc,
-                 stream())
+            wk, wt = _w_split(w1, self.kh, 2 * cin, 2 * self.filters, nc)
             self._wsplit = ((_STATE['wver'], nc), w1, b1, wk, wt)
         return self._wsplit[1:]
 
@@ -833,8 +929,8 @@ class Conv2D(Layer):
             w1, b1, wk, wt = self._packed_split(nc)
             self._xs = _split(x, nc)
             y = _empty((B, self.Lout, 2, self.filters))
-            call('gn_conv1d_fwd_bf16x3', ptr(self._xs, BF16), ptr(wt, BF16), ptr(b1), ptr(y), None, B, H, c1, self.Lout, c2,
-                 self.kh, self.sh, self.pad, code, par, nc, stream())
+            _conv_fwd_split(self._xs, wt, ptr(b1), y, None, False, (B, H, c1, self.Lout, c2, self.kh, self.sh, self.pad),
+                            code, par, nc)
         elif self._mode == 'tc':
             x = _as_bf16(x).contiguous()
             w1, b1, wk, wt = self._packed_bf16()
@@ -879,14 +975,13 @@ class Conv2D(Layer):
             nc = _split_planes()
             dy = _as_f32(dy).contiguous()
             dys = _split(dy, nc)
+            geom = (B, H, c1, self.Lout, c2, self.kh, self.sh, self.pad)
             if tr:
-                call('gn_conv1d_wgrad_bf16x3', ptr(self._xs, BF16), ptr(dys, BF16), ptr(dy), ptr(dw1), ptr(db1), B, H, c1,
-                     self.Lout, c2, self.kh, self.sh, self.pad, nc, stream())
+                _conv_wgrad_split(self._xs, dys, dy, ptr(dw1), ptr(db1), geom, nc)
             if need_dx:
                 wk = self._packed_split(nc)[2]
                 dx = _empty(x.shape)
-                call('gn_conv1d_dgrad_bf16x3', ptr(dys, BF16), ptr(wk, BF16), None, ptr(dx), None, None, B, H, c1,
-                     self.Lout, c2, self.kh, self.sh, self.pad, _lib.ACT_NONE, 0.0, nc, stream())
+                _conv_dgrad_split(dys, wk, None, dx, None, None, False, geom, _lib.ACT_NONE, 0.0, nc)
             self._xs = None
         elif self._mode == 'tc':
             dy = _as_bf16(dy.contiguous())

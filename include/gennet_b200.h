@@ -219,6 +219,38 @@ int gn_dense_dgrad_bf16x3(const void* dys, const void* wks, const float* x_in, f
 int gn_dense_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, float* dw, float* db, int M, int K, int N,
                           int Kp, int nc, void* stream);
 
+/* ---- the same split-operand kernels with SCALED FP16 PAIRS ("f16x2"): half the tensor-core work of bf16x3 -------
+ * A float32 tensor t with max |t| = amax is carried as two fp16 planes (2, ...) plus the device scalar amax:
+ *     t = (T0 + 2^-11 T1) / s,  s = 2^(14 - floor(log2 amax)),  T0 = fp16(t s),  T1 = fp16((t s - T0) 2^11)
+ * i.e. 22-23 significant bits relative to the TENSOR's largest element (elements below 2^-28 amax lose bits), and a
+ * product needs three plane products (T0 W0 | T0 W1 + T1 W0; the dropped term is <= 2^-22 |t||w|); the kernels undo
+ * both scales in the epilogue.  Results are float32; geometry, outputs and OVERWRITE rules as the _bf16x3 entry points.
+ *   gn_amax_f32            : amax[0] = max |x| (device scalar)
+ *   gn_split_f32_f16x2     : x f32 (n) -> planes fp16 (2, n), amax[0] = max |x| (have_amax != 0: amax[0] already holds
+ *                            it, e.g. from the y_amax / dx_amax output of the producing convolution)
+ *   gn_conv_w_split_f16x2, gn_split_pad_f32_f16x2, gn_dense_w_split_f16x2 : as their _bf16 counterparts, plus amax
+ *   fwd / dgrad            : y_amax / dx_amax (device scalar, OVERWRITTEN, may be NULL) = max |result| */
+int gn_amax_f32(const float* x, long long n, float* amax, void* stream);
+int gn_split_f32_f16x2(const float* x, void* planes, float* amax, int have_amax, long long n, void* stream);
+int gn_conv_w_split_f16x2(const float* w, void* wk, void* wt, float* amax, int k, int Cin, int Cout, void* stream);
+int gn_conv1d_fwd_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax, const float* bias,
+                        float* y, float* y_amax, int B, int L, int Cin, int Lout, int Cout, int k, int stride,
+                        int pad_left, int act, float act_param, void* stream);
+int gn_conv1d_dgrad_f16x2(const void* dys, const float* dy_amax, const void* wks, const float* w_amax, const float* x_in,
+                          float* dx, float* dx_colsum, float* dx_amax, int B, int L, int Cin, int Lout, int Cout, int k,
+                          int stride, int pad_left, int in_act, float in_act_param, void* stream);
+int gn_conv1d_wgrad_f16x2(const void* xs, const float* x_amax, const void* dys, const float* dy_amax, const float* dy,
+                          float* dw, float* db, int B, int L, int Cin, int Lout, int Cout, int k, int stride, int pad_left,
+                          void* stream);
+int gn_split_pad_f32_f16x2(const float* x, void* planes, float* amax, long long rows, int K, int Kp, void* stream);
+int gn_dense_w_split_f16x2(const float* w, void* wk, void* wt, float* amax, int K, int Kp, int N, void* stream);
+int gn_dense_fwd_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax, const float* bias, float* y,
+                       int M, int Kp, int N, int act, float act_param, void* stream);
+int gn_dense_dgrad_f16x2(const void* dys, const float* dy_amax, const void* wks, const float* w_amax, const float* x_in,
+                         float* dx, float* dx_colsum, int M, int K, int N, int in_act, float in_act_param, void* stream);
+int gn_dense_wgrad_f16x2(const void* xs, const float* x_amax, const void* dys, const float* dy_amax, const float* dy,
+                         float* dw, float* db, int M, int K, int N, int Kp, void* stream);
+
 /* Bandwidth-bound companions of the bf16 path.
  *   smallcin fwd  : first convolution of a network, Cin in {1,2}: x f32 (B,L,Cin) -> y bf16 (B,Lout,Cout), bias+act fused
  *   smallcin wgrad: dw f32 (k,Cin,Cout), db f32 (Cout) OVERWRITTEN from x f32 and dy bf16 (k <= 5, Cout in {8,16,32,64}

@@ -213,11 +213,12 @@ def test_posterior_sampling_chain_on_device():
         assert np.allclose(pc_[p], [np.percentile(gen[:, n, 0], p) for n in range(128)], rtol=1e-5, atol=1e-7)
 
 
-# ---- split-bf16 tensor-core mode ('bf16x3'): the SAME rtol 1e-4 as the float32 SIMT path ------------------------
-@pytest.fixture
-def bf16x3():
+# ---- split-operand tensor-core modes ('bf16x3': three bf16 planes; 'f16x2': scaled fp16 pairs): the SAME rtol 1e-4
+# as the float32 SIMT path
+@pytest.fixture(params=['bf16x3', 'f16x2'])
+def bf16x3(request):
     from gennet_b200 import nn
-    nn.set_compute_dtype('bf16x3')
+    nn.set_compute_dtype(request.param)
     try:
         yield nn
     finally:
@@ -234,7 +235,7 @@ def test_pe_step_parity_bf16x3(bf16x3, n_pix, B):
     assert sorted(c._path() for c in convs) == ['smallcin32'] * 2 + ['tc3'] * 7
     errs, w0 = pc.compare_step(prod, orc, x, y)
     pc.compare_weights(prod, orc, w0)
-    print('bf16x3 PE n_pix %d: max gradient error %.2e' % (n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))
+    print('%s PE n_pix %d: max gradient error %.2e' % (nn.compute_dtype(), n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))
     if n_pix == 256:
         pc.resync([(prod, orc)])
         errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)
@@ -256,7 +257,7 @@ def test_gan_steps_parity_bf16x3(bf16x3, n_pix, B):
     errs, w0 = pc.compare_step(dg, ocomp, z, [1] * B, check_predict=False)
     assert all(np.array_equal(a, b) for a, b in zip(dw, d.get_weights()))
     pc.compare_weights(g, og, w0[:len(g.get_weights())])
-    print('bf16x3 GAN n_pix %d: max gradient error %.2e' % (n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))
+    print('%s GAN n_pix %d: max gradient error %.2e' % (nn.compute_dtype(), n_pix, max(v for k, v in errs.items() if k.startswith('grad'))))
 
 
 def test_burst_iteration_parity_bf16x3(bf16x3):
@@ -372,7 +373,7 @@ def test_step_parity_bf16x2(which):
         nn.set_compute_dtype('float32')
 
 
-@pytest.mark.parametrize('mode', ['float32', 'bf16x3'])
+@pytest.mark.parametrize('mode', ['float32', 'bf16x3', 'f16x2'])
 def test_subtract_stage_parity(mode):
     """2_model_version/weight_version/subtract_model.py (config 5 subtract stage): ELU transposed-conv generator with the
     l1 activity / l2 kernel regularisers, Dropout discriminator: predict, D step, G step through the frozen D."""
@@ -392,7 +393,7 @@ def test_subtract_stage_parity(mode):
         nn.set_compute_dtype('float32')
 
 
-@pytest.mark.parametrize('mode', ['float32', 'bf16x3'])
+@pytest.mark.parametrize('mode', ['float32', 'bf16x3', 'f16x2'])
 def test_nw_discriminator_parity(mode):
     """2_model_version/no_weight_code/subtract_model.py:322-390: Conv1D(tanh) -> LeakyReLU -> GaussianNoise(1.6) ->
     BatchNormalization(axis=1) blocks, GlobalAveragePooling1D, MSE, Adam with decay."""
@@ -400,7 +401,7 @@ def test_nw_discriminator_parity(mode):
     nn.set_compute_dtype(mode)
     try:
         D, od, X, y = pc.nw_disc_case(16)
-        if mode == 'bf16x3':
+        if mode != 'float32':
             assert [l._path() for l in D.all_layers() if isinstance(l, nn.Conv1D)] == ['f32', 'tc3', 'tc3']
         pc.assert_close(D.predict(X), od.predict(X), 'D.predict')
         errs, w0 = pc.compare_step(D, od, X, y)
