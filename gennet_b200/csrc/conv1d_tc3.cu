@@ -31,7 +31,6 @@ namespace gn {
 
 int launch_colsum(const float* x, long long rows, int C, float* out, cudaStream_t st);      // conv_dense_f32.cu
 
-constexpr int T3_BK = 32;            // bf16 elements per 64-byte swizzle row = K per pipeline stage
 constexpr int T3_THREADS = 320;      // warps: 0 TMA producer, 1 MMA issuer, 2-5 and 6-9 epilogue (alternate 32-column slabs)
 constexpr int T3_EPI_SETS = 2;
 constexpr int T3_WG_THREADS = 192;   // wgrad: warps 0 producer, 1 MMA, 2-5 epilogue
@@ -134,10 +133,14 @@ __device__ __forceinline__ OutScale out_scale(const float* amax_a, const float* 
     return o;
 }
 
-template <int BN, int NC>
+// BK = contraction channels per pipeline stage: 32 (64-byte rows, SWIZZLE_64B) or 64 (128-byte rows, SWIZZLE_128B).
+// The TMA unit moves a box row by row, and 64-byte rows reach only ~40 B/clk per SM against >= 60 B/clk for 128-byte
+// rows (profiles/r02_conv_f16x2_step_traffic.json: the 128-wide tiles of the two-plane formats are operand-fetch bound),
+// so the two-plane formats use BK = 64 wherever three stages fit; three planes keep BK = 32 for pipeline depth.
+template <int BN, int NC, int BK = 32>
 struct T3Smem {
-    static constexpr int A_PLANE = TC_BM * 64;       // 128 rows x 64 B
-    static constexpr int B_PLANE = BN * 64;
+    static constexpr int A_PLANE = TC_BM * BK * 2;       // 128 rows x (64 | 128) B
+    static constexpr int B_PLANE = BN * BK * 2;
     static constexpr int STAGE_BYTES = NC * (A_PLANE + B_PLANE);
     static constexpr int STAGES_MAX = T3_SMEM_BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
@@ -162,11 +165,11 @@ template <> struct PlanePairs<3> {
 // Persistent: grid = min(#tiles, #SMs), tile = blockIdx.x + i*gridDim.x with the n-tile fastest.  Pipelines:
 //   shared-memory ring (full/empty mbarriers)      TMA producer -> MMA issuer
 //   TMEM accumulator ring (2 x BN fp32 columns)    MMA issuer   -> epilogue warps
-template <int BN, int NC, bool AUX>
+template <int BN, int NC, bool AUX, int BK>
 __global__ void __launch_bounds__(T3_THREADS)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Tc3Args a) {
     extern __shared__ uint8_t smem_raw[];
-    using S = T3Smem<BN, NC>;
+    using S = T3Smem<BN, NC, BK>;
     constexpr int STAGES = S::STAGES;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
@@ -180,7 +183,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int npar = (a.mode == 1) ? a.s : 1;
     const bool splitk = a.kchunks > 1;
     const int kdim = splitk ? a.kchunk : ((a.mode == 0) ? a.Cin : a.Cout);   // contraction channels (of one chunk)
-    const int nkb = kdim / T3_BK;
+    const int nkb = kdim / BK;
     const int cols = (a.mode == 0) ? a.Cout : a.Cin;   // channels of the result
     const int n_nt = cols / BN;
     const int sshift = (a.s == 2) ? 1 : 0;             // the stride is 1 or 2 (checked on the host)
@@ -234,7 +237,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         uint8_t* sA = tiles + st * S::STAGE_BYTES;
                         uint8_t* sB = sA + NC * S::A_PLANE;
                         mbar_expect_tx(&full[st], S::STAGE_BYTES);
-                        const int kc = kb * T3_BK + (splitk ? c.b * a.kchunk : 0);
+                        const int kc = kb * BK + (splitk ? c.b * a.kchunk : 0);
                         tma_load_4d(sA, &mapA, &full[st], kc, rowc, splitk ? 0 : c.b, 0);
                         tma_load_4d(sB, &mapB, &full[st], kc, c.n0, tap, 0);
                     }
@@ -246,8 +249,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 1) {
         // MMA issuer: per stage two K = 16 steps x the plane pairs, all into the same fp32 accumulator
         const uint32_t idesc = idesc_fmt(make_idesc(TC_BM, BN, 0, 0), a.amax_a != nullptr);
-        // K-major SWIZZLE_64B descriptor: hi = SBO (8 rows x 64 B = 512 B) | version 1 | layout type 4; lo = addr >> 4 | LBO
-        constexpr uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+        // K-major descriptor: hi = SBO (8 rows x 64 | 128 B) | version 1 | layout type (4 = SWIZZLE_64B, 2 = SWIZZLE_128B);
+        // lo = addr >> 4 | LBO; a K = 16 step advances the start address by 32 B inside the swizzle row
+        constexpr uint32_t desc_hi = (BK == 32) ? ((512u >> 4) | (1u << 14) | (4u << 29)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
         using PP = PlanePairs<NC>;
         uint32_t st = 0, ph = 0;
         int ti_local = 0;
@@ -270,7 +274,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const uint32_t sa = ((base + st * (uint32_t)S::STAGE_BYTES) >> 4);
                     const uint32_t sb = sa + (uint32_t)((NC * S::A_PLANE) >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < T3_BK / 16; ++ks) {
+                    for (int ks = 0; ks < BK / 16; ++ks) {
 #pragma unroll
                         for (int q = 0; q < PP::N; ++q) {
                             const uint32_t la = ((sa + (uint32_t)((PP::a(q) * S::A_PLANE) >> 4) + 2u * ks) & 0x3FFFu) | (1u << 16);
@@ -800,13 +804,13 @@ static int make_map4(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
     return GN_OK;
 }
 
-template <int BN, int NC, bool AUX>
+template <int BN, int NC, bool AUX, int BK>
 static int launch_conv_tc3(const CUtensorMap& mA, const CUtensorMap& mB, const Tc3Args& a, long long total_tiles,
                            cudaStream_t st) {
-    auto kfn = conv_tc3_kernel<BN, NC, AUX>;
-    constexpr int smem = T3Smem<BN, NC>::TOTAL;
+    auto kfn = conv_tc3_kernel<BN, NC, AUX, BK>;
+    constexpr int smem = T3Smem<BN, NC, BK>::TOTAL;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    static_assert(T3Smem<BN, NC>::STAGES >= 3, "pipeline too shallow");
+    static_assert(T3Smem<BN, NC, BK>::STAGES >= 3, "pipeline too shallow");
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -817,17 +821,26 @@ static int launch_conv_tc3(const CUtensorMap& mA, const CUtensorMap& mB, const T
     return cuda_status("conv_tc3_kernel");
 }
 
+// channels per stage: 64 for the two-plane formats on tiles up to 128 wide (three 64 KB stages), else 32
+static int pick_bk3(int BN, int nc) { return (nc == 2 && BN <= 128) ? 64 : 32; }
+
 template <int NC>
 static int dispatch_conv_tc3(int BN, bool aux, const CUtensorMap& mA, const CUtensorMap& mB, const Tc3Args& a,
                              long long tiles, cudaStream_t st) {
-    if (!aux) {
-        if (BN == 256) return launch_conv_tc3<256, NC, false>(mA, mB, a, tiles, st);
-        if (BN == 128) return launch_conv_tc3<128, NC, false>(mA, mB, a, tiles, st);
-        return launch_conv_tc3<64, NC, false>(mA, mB, a, tiles, st);
+    if constexpr (NC == 2) {
+        if (BN == 128) return aux ? launch_conv_tc3<128, NC, true, 64>(mA, mB, a, tiles, st)
+                                  : launch_conv_tc3<128, NC, false, 64>(mA, mB, a, tiles, st);
+        if (BN == 64) return aux ? launch_conv_tc3<64, NC, true, 64>(mA, mB, a, tiles, st)
+                                 : launch_conv_tc3<64, NC, false, 64>(mA, mB, a, tiles, st);
     }
-    if (BN == 256) return launch_conv_tc3<256, NC, true>(mA, mB, a, tiles, st);
-    if (BN == 128) return launch_conv_tc3<128, NC, true>(mA, mB, a, tiles, st);
-    return launch_conv_tc3<64, NC, true>(mA, mB, a, tiles, st);
+    if (!aux) {
+        if (BN == 256) return launch_conv_tc3<256, NC, false, 32>(mA, mB, a, tiles, st);
+        if (BN == 128) return launch_conv_tc3<128, NC, false, 32>(mA, mB, a, tiles, st);
+        return launch_conv_tc3<64, NC, false, 32>(mA, mB, a, tiles, st);
+    }
+    if (BN == 256) return launch_conv_tc3<256, NC, true, 32>(mA, mB, a, tiles, st);
+    if (BN == 128) return launch_conv_tc3<128, NC, true, 32>(mA, mB, a, tiles, st);
+    return launch_conv_tc3<64, NC, true, 32>(mA, mB, a, tiles, st);
 }
 // widest N tile.  nc > 1: MAIN + CORR accumulators double-buffered need 4 x BN tensor-memory columns, so BN = 256 runs
 // single-buffered and is taken only when a tile has enough K steps (ksteps = taps * K / 16) to hide its epilogue
@@ -980,12 +993,12 @@ static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y,
     CUtensorMap mA, mB;
     const int BN = pick_bn3(Cout, nc, k * Cin / 16);
     // A: X planes viewed as (Cin, L, B, NC); 128 output rows per tile, traversal stride = conv stride
-    rc = make_map4(&mA, xs, Cin, L, B, nc, Cin, (uint64_t)L * Cin, (uint64_t)B * L * Cin, T3_BK, TC_BM, stride,
-                   CU_TENSOR_MAP_SWIZZLE_64B);
+    const int BK = pick_bk3(BN, nc);
+    const CUtensorMapSwizzle swz = (BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    rc = make_map4(&mA, xs, Cin, L, B, nc, Cin, (uint64_t)L * Cin, (uint64_t)B * L * Cin, BK, TC_BM, stride, swz);
     if (rc != GN_OK) return rc;
     // B: Wt planes (NC, k, Cout, Cin) viewed as (Cin, Cout, k, NC)
-    rc = make_map4(&mB, wts, Cin, Cout, k, nc, Cin, (uint64_t)Cout * Cin, (uint64_t)k * Cout * Cin, T3_BK, BN, 1,
-                   CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_map4(&mB, wts, Cin, Cout, k, nc, Cin, (uint64_t)Cout * Cin, (uint64_t)k * Cout * Cin, BK, BN, 1, swz);
     if (rc != GN_OK) return rc;
     Tc3Args a{};
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
@@ -995,8 +1008,8 @@ static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y,
     a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
     a.kchunks = kchunks;
     a.kchunk = Cin / kchunks;
-    GN_REQUIRE(kchunks == 1 || (B == 1 && k == 1 && ys == nullptr && y != nullptr && y_amax == nullptr && a.kchunk % T3_BK == 0),
-               "split-K needs B == 1, k == 1, a float32 output and chunks of whole 32-channel blocks");
+    GN_REQUIRE(kchunks == 1 || (B == 1 && k == 1 && ys == nullptr && y != nullptr && y_amax == nullptr && a.kchunk % BK == 0),
+               "split-K needs B == 1, k == 1, a float32 output and chunks of whole channel blocks");
     const long long tiles = (long long)(kchunks > 1 ? kchunks : B) * a.m_tiles * (Cout / BN);
     cudaStream_t st = as_stream(stream);
     if (y_amax != nullptr) cudaMemsetAsync(y_amax, 0, sizeof(float), st);
@@ -1031,12 +1044,12 @@ static int dgrad_tc3(const void* dys, const void* wks, const float* x_in, float*
     CUtensorMap mA, mB;
     const int BN = pick_bn3(Cin, nc, 0);      // mask, column sums and re-split make this epilogue too long to expose
     // A: dY planes viewed as (Cout, Lout, B, NC), 128 rows, unit traversal stride (parity classes handle the conv stride)
-    rc = make_map4(&mA, dys, Cout, Lout, B, nc, Cout, (uint64_t)Lout * Cout, (uint64_t)B * Lout * Cout, T3_BK, TC_BM, 1,
-                   CU_TENSOR_MAP_SWIZZLE_64B);
+    const int BK = pick_bk3(BN, nc);
+    const CUtensorMapSwizzle swz = (BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    rc = make_map4(&mA, dys, Cout, Lout, B, nc, Cout, (uint64_t)Lout * Cout, (uint64_t)B * Lout * Cout, BK, TC_BM, 1, swz);
     if (rc != GN_OK) return rc;
     // B: W planes (NC, k, Cin, Cout) viewed as (Cout, Cin, k, NC)
-    rc = make_map4(&mB, wks, Cout, Cin, k, nc, Cout, (uint64_t)Cin * Cout, (uint64_t)k * Cin * Cout, T3_BK, BN, 1,
-                   CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_map4(&mB, wks, Cout, Cin, k, nc, Cout, (uint64_t)Cin * Cout, (uint64_t)k * Cin * Cout, BK, BN, 1, swz);
     if (rc != GN_OK) return rc;
     cudaStream_t st = as_stream(stream);
     Tc3Args a{};
@@ -1169,9 +1182,9 @@ static int dense_fwd_tc3(const void* xs, const void* wts, const float* bias, flo
     // 8 tiles for 148 SMs) is cut into chunks of >= 256 channels that run as separate tiles and meet in the output by
     // vector reductions; it also keeps the truncating tensor-memory accumulator short (<= 4096 channels per chunk)
     int chunks = 1;
-    if (y != nullptr && ys == nullptr && Kp >= 1024 && Kp % 32 == 0 && N % 4 == 0) {
+    if (y != nullptr && ys == nullptr && Kp >= 1024 && Kp % 64 == 0 && N % 4 == 0) {
         const long long tiles = (long long)((M + 127) / 128) * (N / (N % 128 == 0 ? 128 : 64));
-        const int units = Kp / 32;
+        const int units = Kp / 64;      // chunks of whole 64-channel blocks (the widest stage)
         for (int c = 2; c <= units; ++c) {
             if (units % c != 0) continue;
             const int kc = Kp / c;
