@@ -2,7 +2,7 @@
 """Benchmark of the GenNet hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--config gan|pe] [--mode bf16x3|bf16x2|bf16|fp32] [--check]
+                    [--config gan|pe] [--mode f16x2|bf16x3|bf16x2|bf16|fp32] [--check]
 
 Workloads (BASELINE.json `configs`, metric "train samples/sec (synth+whiten+G/D step)"):
   gan (default, configs[2]): bbhMahoGANy.py GAN waveform estimator, n_pix 2048, 128 samples per GPU (global batch 1024
@@ -13,9 +13,10 @@ Workloads (BASELINE.json `configs`, metric "train samples/sec (synth+whiten+G/D 
   pe  (configs[1]): CNN point estimator, n_pix 2048, batch 512 per GPU.  One step = Philox noise + injected chirp ->
       whiten -> crop (gn_synth_f32) fused with signal_pe.train_on_batch.  Always measured too and reported under
       `extra.pe` of the same JSON line.
-Modes: bf16x3 (default) = float32 tensors, Conv1D/Conv2D on the tcgen05 tensor cores with three-plane split-bf16
-operands (float32-class accuracy: the mode every rtol-1e-4 parity test runs in); bf16x2; bf16 (throughput mode,
-stated tolerance); fp32 (SIMT).
+Modes: f16x2 (default) = float32 tensors, Conv1D / Conv2D / Dense on the tcgen05 tensor cores with scaled fp16-pair
+operands (three MMAs per product, float32-class accuracy: every rtol-1e-4 whole-step parity test runs in this mode);
+bf16x3 = the same with three bf16 planes (six MMAs per product, element-wise 24-bit operands); bf16x2; bf16 (throughput
+mode, stated tolerance); fp32 (SIMT).
 """
 import argparse
 import json
@@ -492,7 +493,7 @@ def timed(fn, first, steps, barrier, world, dev):
     return float(t.item()), res
 
 
-def measure(w, steps, warmup, barrier, world, dev, rank, local, profile=True, mode='bf16x3'):
+def measure(w, steps, warmup, barrier, world, dev, rank, local, profile=True, mode='f16x2'):
     """value (device-resident), e2e (public API, host arrays), e2e_overlapped, launch count, clocks, roofline."""
     import torch
     from gennet_b200 import _lib
@@ -506,6 +507,16 @@ def measure(w, steps, warmup, barrier, world, dev, rank, local, profile=True, mo
     last = res.detach().cpu().numpy()
     assert np.isfinite(last).all(), 'training diverged'
     out = {'value': w.B * world * steps / (ms / 1e3), 'ms_per_step': ms / steps, 'gpu_launches': launches, 'clocks': clocks}
+    # host time to ENQUEUE one step (no synchronisation inside): when it is below the device time of the step the
+    # launches are hidden behind the running kernels and a CUDA graph has nothing to recover
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(3):
+        w.step(2 * 10 ** 6 + it)
+    host_ms = (time.perf_counter() - t0) / 3 * 1e3
+    torch.cuda.synchronize()
+    out['host_enqueue_ms_per_step'] = host_ms
+    out['launch_bound'] = bool(host_ms > ms / steps)
     n_e2e = max(3, steps // 2)
     for it in range(2):
         w.api_step(it)
@@ -583,7 +594,7 @@ def run_ours(args):
            'parity': {'synthesis': 'pinned (reference source executed, tests/golden/synth_ref.npz)',
                       'network': 'unpinned (Keras/TensorFlow absent; float64 restatement, rtol 1e-4 in this mode)'},
            'e2e': m['e2e'], 'e2e_overlapped': m['e2e_overlapped'], 'gpu_launches': m['gpu_launches'], 'clocks': m['clocks']}
-    for k in ('roofline', 'roofline_synth', 'kernel_time_ms_per_step'):
+    for k in ('roofline', 'roofline_synth', 'kernel_time_ms_per_step', 'host_enqueue_ms_per_step', 'launch_bound'):
         if k in m:
             out[k] = m[k]
     extra = {}
@@ -597,9 +608,12 @@ def run_ours(args):
         extra[other] = om
         del ow
         torch.cuda.empty_cache()
-        if world == 1 and args.mode == 'bf16x3':
+        if world == 1 and args.mode == 'f16x2':
             # the other tensor-core modes on the same two workloads, clearly labelled
-            for mname, key, note in (('bf16x2', 'bf16x2_mode', dict(same_precision=True, dtype=DTYPES['bf16x2'],
+            for mname, key, note in (('bf16x3', 'bf16x3_mode', dict(same_precision=True, dtype=DTYPES['bf16x3'],
+                                      tolerance='whole-step parity suite at rtol 1e-4 (tests/test_gpu_models.py); operands carry '
+                                                '24 mantissa bits element-wise, six MMAs per product')),
+                                     ('bf16x2', 'bf16x2_mode', dict(same_precision=True, dtype=DTYPES['bf16x2'],
                                       tolerance='whole-step parity suite at rtol 1e-4 (tests/test_gpu_models.py::test_step_parity_bf16x2); '
                                                 'operands carry 16 mantissa bits')),
                                      ('bf16', 'bf16_throughput_mode', dict(same_precision=False, dtype='bf16',
@@ -793,8 +807,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='gan', choices=['gan', 'pe'],
                     help='headline workload (the other one is measured too and reported under extra)')
-    ap.add_argument('--mode', default='bf16x3', choices=sorted(MODES),
-                    help='bf16x3: float32-accuracy split-operand tensor-core mode (default, the parity mode); '
+    ap.add_argument('--mode', default='f16x2', choices=sorted(MODES),
+                    help='f16x2: float32-accuracy split-operand tensor-core mode with scaled fp16 pairs (default, the parity '
+                         'mode); bf16x3: the same with three bf16 planes; '
                          'bf16: throughput mode; fp32: SIMT')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary workload and the bf16 comparison lines')
     ap.add_argument('--check', action='store_true', help='data-parallel equivalence check (use with torchrun, N >= 2)')

@@ -509,9 +509,21 @@ __global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const T* __restrict
     // One block = COUT1_ROWS consecutive output rows of one sample.  Every input row the tile touches (the tile plus a
     // k-1 row halo) is read once by one warp, which leaves its k tap products in shared memory; the outputs are then
     // summed from shared memory in a fixed order: no atomics, bit-reproducible, x is read (1 + (k-1)/32) times.
-    extern __shared__ float sw[];     // k*Cin weights, then (COUT1_ROWS + KMAX - 1) * KMAX partial products
-    float* part = sw + k * Cin;
-    for (int i = threadIdx.x; i < k * Cin; i += blockDim.x) sw[i] = w[i];
+    // Weights in shared memory as float4 [tap][iteration][half][lane]: lane l of iteration i owns channels
+    // 8 (l + 32 i) .. + 7, so a warp's 128-bit reads are contiguous (conflict-free); a warp works on two rows at a time
+    // so that every weight read feeds two rows.
+    extern __shared__ float4 sw4[];   // k * n_it * 2 * 32 float4 weights, then (COUT1_ROWS + KMAX - 1) * KMAX partial products
+    const int C8 = Cin / 8, n_it = (C8 + 31) / 32;
+    float* part = reinterpret_cast<float*>(sw4 + (size_t)k * n_it * 64);
+    {
+        float* swf = reinterpret_cast<float*>(sw4);
+        for (int i = threadIdx.x; i < k * n_it * 256; i += blockDim.x) {
+            const int j = i & 3, lane_ = (i >> 2) & 31, h = (i >> 7) & 1, ti = i >> 8;      // ti = t * n_it + it
+            const int t = ti / n_it, it = ti - t * n_it;
+            const int c = (lane_ + 32 * it) * 8 + h * 4 + j;
+            swf[i] = (c < Cin) ? w[(size_t)t * Cin + c] : 0.f;
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float bv = bias ? bias[0] : 0.f;
@@ -519,36 +531,45 @@ __global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const T* __restrict
         const int b = (int)(tile / tiles_per_sample);
         const int l0 = (int)(tile - (long long)b * tiles_per_sample) * COUT1_ROWS;
         const int nin = COUT1_ROWS + k - 1;                       // input rows l0 - p ... l0 - p + nin - 1
-        for (int ri = warp; ri < nin; ri += 8) {
-            const int pos = l0 - p + ri;
-            float acc[KMAX];
+        for (int ri = 2 * warp; ri < nin; ri += 16) {
+            float acc[2][KMAX];
 #pragma unroll
-            for (int t = 0; t < KMAX; ++t) acc[t] = 0.f;
-            if (pos >= 0 && pos < L) {
-                const T* xr = x + ((size_t)b * L + pos) * Cin;
-                for (int c8 = lane; c8 < Cin / 8; c8 += 32) {
-                    float xv[8];
-                    Act8<T>::load(xr + c8 * 8, xv);
+            for (int t = 0; t < KMAX; ++t) acc[0][t] = acc[1][t] = 0.f;
+            const int pos0 = l0 - p + ri;
+            const bool ok0 = pos0 >= 0 && pos0 < L, ok1 = ri + 1 < nin && pos0 + 1 >= 0 && pos0 + 1 < L;
+            const T* xr = x + ((size_t)b * L + pos0) * Cin;
+            for (int it = 0; it < n_it; ++it) {
+                const int c8 = lane + 32 * it;
+                float xv[2][8];
 #pragma unroll
-                    for (int t = 0; t < KMAX; ++t) {
-                        if (t < k) {
-                            const float4* wr = reinterpret_cast<const float4*>(&sw[t * Cin + c8 * 8]);
-                            const float4 w0 = wr[0], w1 = wr[1];
-                            acc[t] = fmaf(xv[0], w0.x, acc[t]); acc[t] = fmaf(xv[1], w0.y, acc[t]);
-                            acc[t] = fmaf(xv[2], w0.z, acc[t]); acc[t] = fmaf(xv[3], w0.w, acc[t]);
-                            acc[t] = fmaf(xv[4], w1.x, acc[t]); acc[t] = fmaf(xv[5], w1.y, acc[t]);
-                            acc[t] = fmaf(xv[6], w1.z, acc[t]); acc[t] = fmaf(xv[7], w1.w, acc[t]);
+                for (int e = 0; e < 8; ++e) xv[0][e] = xv[1][e] = 0.f;
+                if (c8 < C8) {
+                    if (ok0) Act8<T>::load(xr + c8 * 8, xv[0]);
+                    if (ok1) Act8<T>::load(xr + Cin + c8 * 8, xv[1]);
+                }
+#pragma unroll
+                for (int t = 0; t < KMAX; ++t) {
+                    if (t < k) {
+                        const float4 w0 = sw4[((t * n_it + it) * 2 + 0) * 32 + lane], w1 = sw4[((t * n_it + it) * 2 + 1) * 32 + lane];
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            acc[r][t] = fmaf(xv[r][0], w0.x, acc[r][t]); acc[r][t] = fmaf(xv[r][1], w0.y, acc[r][t]);
+                            acc[r][t] = fmaf(xv[r][2], w0.z, acc[r][t]); acc[r][t] = fmaf(xv[r][3], w0.w, acc[r][t]);
+                            acc[r][t] = fmaf(xv[r][4], w1.x, acc[r][t]); acc[r][t] = fmaf(xv[r][5], w1.y, acc[r][t]);
+                            acc[r][t] = fmaf(xv[r][6], w1.z, acc[r][t]); acc[r][t] = fmaf(xv[r][7], w1.w, acc[r][t]);
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int t = 0; t < KMAX; ++t) {
-                float v = acc[t];
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) part[ri * KMAX + t] = v;
-            }
+                for (int t = 0; t < KMAX; ++t) {
+                    float v = acc[r][t];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && ri + r < nin) part[(ri + r) * KMAX + t] = v;
+                }
         }
         __syncthreads();
         if (threadIdx.x < COUT1_ROWS) {
@@ -563,40 +584,138 @@ __global__ void __launch_bounds__(256) conv_cout1_fwd_kernel(const T* __restrict
     }
 }
 
+// A thread keeps ONE group of 8 channels (its k x 8 weights in registers) and walks a contiguous run of rows with a
+// sliding window of the k gradient values; consecutive threads hold consecutive channel groups, so a warp writes
+// contiguous runs of a row.
 template <int KMAX, typename T>
 __global__ void __launch_bounds__(256) conv_cout1_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                T* __restrict__ dx, int B, int L, int Lout,
-                                                               int Cin, int k, int p) {
+                                                               int Cin, int k, int p, long long lanes, long long run) {
     const int C8 = Cin / 8;
-    const long long total = (long long)B * L * C8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c, pos;
-        const long long row = fast_div(i, C8, c);
-        const int b = (int)fast_div(row, L, pos);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = (int)(tid % C8);
+    const long long lane = tid / C8;
+    if (lane >= lanes) return;
+    const long long rows = (long long)B * L;
+    const long long r0 = lane * run, r1 = min(rows, r0 + run);
+    if (r0 >= r1) return;
+    float wv[KMAX][8];
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) {
+        if (t < k) {
+            const float4* wp = reinterpret_cast<const float4*>(w + (size_t)t * Cin + cg * 8);
+            const float4 w0 = __ldg(&wp[0]), w1 = __ldg(&wp[1]);
+            wv[t][0] = w0.x; wv[t][1] = w0.y; wv[t][2] = w0.z; wv[t][3] = w0.w;
+            wv[t][4] = w1.x; wv[t][5] = w1.y; wv[t][6] = w1.z; wv[t][7] = w1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) wv[t][e] = 0.f;
+        }
+    }
+    int pos;
+    int b = (int)fast_div(r0, L, pos);
+    float g[KMAX];      // g[t] = dy[b, pos - t + p]
+    auto reload = [&]() {
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+            const int l = pos - t + p;
+            g[t] = (t < k && l >= 0 && l < Lout) ? __ldg(&dy[(size_t)b * Lout + l]) : 0.f;
+        }
+    };
+    reload();
+    for (long long row = r0; row < r1; ++row) {
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = 0.f;
 #pragma unroll
-        for (int t = 0; t < KMAX; ++t) {
-            if (t < k) {
-                const int l = pos - t + p;
-                if (l >= 0 && l < Lout) {
-                    const float g = __ldg(&dy[(size_t)b * Lout + l]);
-                    const float4* wp = reinterpret_cast<const float4*>(w + (size_t)t * Cin + c * 8);
-                    const float4 w0 = __ldg(&wp[0]), w1 = __ldg(&wp[1]);
-                    o[0] = fmaf(g, w0.x, o[0]); o[1] = fmaf(g, w0.y, o[1]); o[2] = fmaf(g, w0.z, o[2]); o[3] = fmaf(g, w0.w, o[3]);
-                    o[4] = fmaf(g, w1.x, o[4]); o[5] = fmaf(g, w1.y, o[5]); o[6] = fmaf(g, w1.z, o[6]); o[7] = fmaf(g, w1.w, o[7]);
-                }
-            }
+        for (int t = 0; t < KMAX; ++t)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(g[t], wv[t][e], o[e]);
+        Act8<T>::store(dx + ((size_t)row * C8 + cg) * 8, o);
+        if (++pos == L) {
+            pos = 0;
+            ++b;
+            if (row + 1 < r1) reload();
+        } else {
+#pragma unroll
+            for (int t = KMAX - 1; t > 0; --t) g[t] = g[t - 1];
+            const int l = pos + p;
+            g[0] = (l < Lout) ? __ldg(&dy[(size_t)b * Lout + l]) : 0.f;
         }
-        Act8<T>::store(dx + (size_t)i * 8, o);
     }
 }
 
+// dw[t, c] = sum over rows of x[row, c] dy[row shifted by t].  Block = 32 channel groups x 8 row lanes (a warp reads a
+// contiguous 1 KB run of one row); every warp walks a contiguous run of rows with the sliding gradient window, the eight
+// warps of a block meet in shared memory, one atomic per (tap, channel) and block.  Needs (Cin / 8) % 32 == 0.
 template <int KMAX, typename T>
 __global__ void __launch_bounds__(256) conv_cout1_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dw, int B, int L, int Lout, int Cin, int k,
-                                                               int p, long long rows_per_split) {
+                                                               int p, long long rows_per_block) {
+    __shared__ float red[8][KMAX * 8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cg = blockIdx.x * 32 + lane;
+    const long long rows = (long long)B * L;
+    const long long b0 = (long long)blockIdx.y * rows_per_block, b1 = min(rows, b0 + rows_per_block);
+    const long long per = (b1 - b0 + 7) / 8;
+    const long long r0 = b0 + warp * per, r1 = min(b1, r0 + per);
+    float acc[KMAX][8];
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+    if (r0 < r1) {
+        int pos;
+        int b = (int)fast_div(r0, L, pos);
+        float g[KMAX];
+        auto reload = [&]() {
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) {
+                const int l = pos - t + p;
+                g[t] = (t < k && l >= 0 && l < Lout) ? __ldg(&dy[(size_t)b * Lout + l]) : 0.f;
+            }
+        };
+        reload();
+#pragma unroll 4
+        for (long long row = r0; row < r1; ++row) {
+            float xv[8];
+            Act8<T>::load(x + ((size_t)row * (Cin / 8) + cg) * 8, xv);
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(xv[e], g[t], acc[t][e]);
+            if (++pos == L) {
+                pos = 0;
+                ++b;
+                if (row + 1 < r1) reload();
+            } else {
+#pragma unroll
+                for (int t = KMAX - 1; t > 0; --t) g[t] = g[t - 1];
+                const int l = pos + p;
+                g[0] = (l < Lout) ? __ldg(&dy[(size_t)b * Lout + l]) : 0.f;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[warp][t * 8 + e][lane] = acc[t][e];
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * 8 * 32; i += blockDim.x) {
+        const int l_ = i & 31, te = i >> 5;      // te = t * 8 + e
+        float v = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) v += red[wq][te][l_];
+        const int t = te >> 3, e = te & 7;
+        atomicAdd(&dw[(size_t)t * Cin + (blockIdx.x * 32 + l_) * 8 + e], v);
+    }
+}
+
+// general channel counts: thread = 8 channels, a slice of the rows, atomics across slices
+template <int KMAX, typename T>
+__global__ void __launch_bounds__(256) conv_cout1_wgrad_slices_kernel(const T* __restrict__ x, const float* __restrict__ dy,
+                                                                      float* __restrict__ dw, int B, int L, int Lout, int Cin,
+                                                                      int k, int p, long long rows_per_split) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;   // chunk of 8 channels
     if (c >= Cin / 8) return;
     const long long rows = (long long)B * L;
@@ -672,7 +791,8 @@ static int cout1_fwd(const T* x, const float* w, const float* bias, float* y, in
     GN_REQUIRE(x && w && y, "null pointer");
     int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
     if (rc != GN_OK) return rc;
-    const size_t smem = sizeof(float) * ((size_t)k * Cin + (size_t)(COUT1_ROWS + 4) * 5);
+    const int n_it = (Cin / 8 + 31) / 32;
+    const size_t smem = sizeof(float) * ((size_t)k * n_it * 256 + (size_t)(COUT1_ROWS + 4) * 5);
     GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
     cudaStream_t st = as_stream(stream);
     if (B == 0) return GN_OK;
@@ -690,9 +810,15 @@ static int cout1_dgrad(const float* dy, const float* w, T* dx, int B, int L, int
     int rc = check_cout1(B, L, Cin, Lout, k, pad_left);
     if (rc != GN_OK) return rc;
     if (B == 0) return GN_OK;
-    const long long total = (long long)B * L * (Cin / 8);
-    unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
-    conv_cout1_dgrad_kernel<5, T><<<grid, 256, 0, as_stream(stream)>>>(dy, w, dx, B, L, Lout, Cin, k, pad_left);
+    // about 16 CTAs of 256 threads per SM; every thread walks `run` consecutive rows of its channel group
+    const long long C8 = Cin / 8, rows = (long long)B * L;
+    long long lanes = 16LL * num_sms() * 256 / C8;
+    if (lanes < 1) lanes = 1;
+    if (lanes > rows) lanes = rows;
+    const long long run = (rows + lanes - 1) / lanes;
+    lanes = (rows + run - 1) / run;
+    const unsigned grid = (unsigned)((lanes * C8 + 255) / 256);
+    conv_cout1_dgrad_kernel<5, T><<<grid, 256, 0, as_stream(stream)>>>(dy, w, dx, B, L, Lout, Cin, k, pad_left, lanes, run);
     return cuda_status("conv_cout1_dgrad_kernel");
 }
 
@@ -704,7 +830,18 @@ static int cout1_wgrad(const T* x, const float* dy, float* dw, float* db, int B,
     if (rc != GN_OK) return rc;
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin, st);
-    if (B > 0) {
+    if (B > 0 && (Cin / 8) % 32 == 0) {
+        const long long rows = (long long)B * L;
+        const int bx = Cin / 256;
+        long long splits = (4LL * num_sms() + bx - 1) / bx;
+        if (splits > (rows + 63) / 64) splits = (rows + 63) / 64;      // at least 8 rows per warp
+        if (splits > 65535) splits = 65535;
+        if (splits < 1) splits = 1;
+        long long per = (rows + splits - 1) / splits;
+        splits = (rows + per - 1) / per;
+        dim3 grid((unsigned)bx, (unsigned)splits);
+        conv_cout1_wgrad_kernel<5, T><<<grid, 256, 0, st>>>(x, dy, dw, B, L, Lout, Cin, k, pad_left, per);
+    } else if (B > 0) {
         const long long rows = (long long)B * L;
         const int bx = (Cin / 8 + 255) / 256;
         // few, long slices: every slice ends in k*8 atomics per thread onto the same k*Cin addresses, and same-address
@@ -718,7 +855,7 @@ static int cout1_wgrad(const T* x, const float* dy, float* dw, float* db, int B,
         splits = (rows + per - 1) / per;
         const int threads = Cin / 8 < 256 ? ((Cin / 8 + 31) / 32) * 32 : 256;
         dim3 grid((Cin / 8 + threads - 1) / threads, (unsigned)splits);
-        conv_cout1_wgrad_kernel<5, T><<<grid, threads, 0, st>>>(x, dy, dw, B, L, Lout, Cin, k, pad_left, per);
+        conv_cout1_wgrad_slices_kernel<5, T><<<grid, threads, 0, st>>>(x, dy, dw, B, L, Lout, Cin, k, pad_left, per);
     }
     if (db != nullptr) sum_all_kernel<<<1, 1024, 0, st>>>(dy, (long long)B * Lout, db);
     return cuda_status("conv_cout1_wgrad_kernel");
