@@ -195,67 +195,88 @@ __global__ void __launch_bounds__(256) chain_sums_kernel(const T* __restrict__ x
     }
 }
 
+// optional side output of the apply kernels: max |result| into a device scalar (zeroed by the launcher), for the
+// consumer's operand split (gn_split_f32_f16x2 with have_amax); non-negative floats order like their bit patterns
+__device__ __forceinline__ void warp_amax(float* amax, float m) {
+    if (amax == nullptr) return;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+}
+
 // ---- forward apply: y = noise(act(bn(x))) --------------------------------------------------------------------------
 // A thread keeps ONE channel group for its whole life (its per-channel affine is computed once) and walks the rows
 // with a stride of `lanes` = (threads of the grid) / (C/8); consecutive threads hold consecutive channel groups, so
 // every access of a warp is a contiguous 512-byte run of a row.
 template <int KIND, typename T>
 __global__ void __launch_bounds__(256) chain_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
-                                                        ChainArgs a, long long rows, int C, long long lanes) {
+                                                        ChainArgs a, long long rows, int C, long long lanes,
+                                                        float* __restrict__ amax) {
     constexpr bool EXACT = sizeof(T) == 4;
     const int C8 = C / 8;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = (int)(tid % C8);
     const long long lane = tid / C8;
-    if (lane >= lanes) return;
-    float mu[8], is[8], sc[8], sh[8];
-    channel_affine(a, cg * 8, mu, is, sc, sh);
+    float m = 0.f;
+    if (lane < lanes) {
+        float mu[8], is[8], sc[8], sh[8];
+        channel_affine(a, cg * 8, mu, is, sc, sh);
 #pragma unroll 2
-    for (long long r = lane; r < rows; r += lanes) {
-        const long long i0 = r * C + (long long)cg * 8;
-        float xv[8], nf[8], o[8];
-        load8(x + i0, xv);
-        noise_factors(a, i0, nf);
+        for (long long r = lane; r < rows; r += lanes) {
+            const long long i0 = r * C + (long long)cg * 8;
+            float xv[8], nf[8], o[8];
+            load8(x + i0, xv);
+            noise_factors(a, i0, nf);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = chain_act<KIND, EXACT>(fmaf(xv[e], sc[e], sh[e]), a.act_param) * nf[e];
-        store8(y + i0, o);
+            for (int e = 0; e < 8; ++e) {
+                o[e] = chain_act<KIND, EXACT>(fmaf(xv[e], sc[e], sh[e]), a.act_param) * nf[e];
+                m = fmaxf(m, fabsf(o[e]));
+            }
+            store8(y + i0, o);
+        }
     }
+    warp_amax(amax, m);
 }
 
 // ---- backward apply: dx = sc * (g - sum_g/n - xhat * sum_gxhat/n);  without normalisation dx = g ---------------------
 template <int KIND, typename T>
 __global__ void __launch_bounds__(256) chain_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                         T* __restrict__ dx, ChainArgs a, const double* __restrict__ sums,
-                                                        double n_total, long long rows, int C, long long lanes) {
+                                                        double n_total, long long rows, int C, long long lanes,
+                                                        float* __restrict__ amax) {
     constexpr bool EXACT = sizeof(T) == 4;
     const int C8 = C / 8;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = (int)(tid % C8);
     const long long lane = tid / C8;
-    if (lane >= lanes) return;
-    float mu[8], is[8], sc[8], sh[8], m0[8], m1[8];
-    channel_affine(a, cg * 8, mu, is, sc, sh);
-    const bool bn = a.mean != nullptr;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        m0[e] = bn ? (float)(sums[cg * 8 + e] / n_total) : 0.f;
-        m1[e] = bn ? (float)(sums[C + cg * 8 + e] / n_total) : 0.f;
-    }
-#pragma unroll 2
-    for (long long r = lane; r < rows; r += lanes) {
-        const long long i0 = r * C + (long long)cg * 8;
-        float xv[8], gv[8], nf[8], o[8];
-        load8(x + i0, xv);
-        load8(dy + i0, gv);
-        noise_factors(a, i0, nf);
+    float m = 0.f;
+    if (lane < lanes) {
+        float mu[8], is[8], sc[8], sh[8], m0[8], m1[8];
+        channel_affine(a, cg * 8, mu, is, sc, sh);
+        const bool bn = a.mean != nullptr;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float av = chain_act<KIND, EXACT>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
-            const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
-            o[e] = bn ? sc[e] * (gg - m0[e] - (xv[e] - mu[e]) * is[e] * m1[e]) : gg;
+            m0[e] = bn ? (float)(sums[cg * 8 + e] / n_total) : 0.f;
+            m1[e] = bn ? (float)(sums[C + cg * 8 + e] / n_total) : 0.f;
         }
-        store8(dx + i0, o);
+#pragma unroll 2
+        for (long long r = lane; r < rows; r += lanes) {
+            const long long i0 = r * C + (long long)cg * 8;
+            float xv[8], gv[8], nf[8], o[8];
+            load8(x + i0, xv);
+            load8(dy + i0, gv);
+            noise_factors(a, i0, nf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float av = chain_act<KIND, EXACT>(fmaf(xv[e], sc[e], sh[e]), a.act_param);
+                const float gg = gv[e] * nf[e] * act_bwd_t<KIND>(av, a.act_param);
+                o[e] = bn ? sc[e] * (gg - m0[e] - (xv[e] - mu[e]) * is[e] * m1[e]) : gg;
+                m = fmaxf(m, fabsf(o[e]));
+            }
+            store8(dx + i0, o);
+        }
     }
+    warp_amax(amax, m);
 }
 
 __global__ void __launch_bounds__(256) chain_param_grads_kernel(const double* __restrict__ sums, float* dgamma, float* dbeta,
@@ -338,16 +359,17 @@ static int bn_stats_t(const T* x, long long rows, int C, double* sums, void* str
 template <typename T>
 static int chain_fwd_t(const T* x, T* y, const float* mean, const float* scale, const float* gamma, const float* beta,
                        int use_var, float eps, int act, float act_param, int noise, float rate, const float* r, uint64_t seed,
-                       uint64_t offset, long long rows, int C, void* stream) {
+                       uint64_t offset, long long rows, int C, float* amax, void* stream) {
     GN_REQUIRE(x && y && rows >= 0, "null pointer or rows < 0");
     ChainArgs a{};
     int rc = make_chain(&a, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, C);
     if (rc != GN_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    if (amax != nullptr) cudaMemsetAsync(amax, 0, sizeof(float), st);
     if (rows == 0) return GN_OK;
     unsigned grid; long long lanes;
     apply_geometry(rows, C, &grid, &lanes);
-    cudaStream_t st = as_stream(stream);
-    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, y, a, rows, C, lanes)));
+    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, y, a, rows, C, lanes, amax)));
     return cuda_status("chain_fwd_kernel");
 }
 
@@ -372,17 +394,18 @@ template <typename T>
 static int chain_bwd_t(const T* x, const T* dy, T* dx, const float* mean, const float* invstd, const float* gamma,
                        const float* beta, const double* sums, double n_total, int act, float act_param, int noise, float rate,
                        const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta, long long rows, int C,
-                       void* stream) {
+                       float* amax, void* stream) {
     GN_REQUIRE(x && dy && dx && rows >= 0, "null pointer or rows < 0");
     GN_REQUIRE(mean == nullptr || (invstd && sums && n_total > 0), "normalisation needs invstd, sums and n_total");
     ChainArgs a{};
     int rc = make_chain(&a, mean, invstd, gamma, beta, 0, 0.f, act, act_param, noise, rate, r, seed, offset, C);
     if (rc != GN_OK) return rc;
     cudaStream_t st = as_stream(stream);
+    if (amax != nullptr) cudaMemsetAsync(amax, 0, sizeof(float), st);
     if (rows > 0) {
         unsigned grid; long long lanes;
         apply_geometry(rows, C, &grid, &lanes);
-        GN_CHAIN_DISPATCH((chain_bwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, dy, dx, a, sums, n_total, rows, C, lanes)));
+        GN_CHAIN_DISPATCH((chain_bwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, dy, dx, a, sums, n_total, rows, C, lanes, amax)));
     }
     if (mean != nullptr && (dgamma || dbeta))
         chain_param_grads_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, dgamma, dbeta, C);
@@ -398,7 +421,7 @@ extern "C" int gn_chain_fwd_bf16(const void* x, void* y, const float* mean, cons
                                  const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
                                  const float* r, uint64_t seed, uint64_t offset, long long rows, int C, void* stream) {
     return chain_fwd_t<bf16_t>((const bf16_t*)x, (bf16_t*)y, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate,
-                               r, seed, offset, rows, C, stream);
+                               r, seed, offset, rows, C, nullptr, stream);
 }
 extern "C" int gn_chain_bwd_sums_bf16(const void* x, const void* dy, const float* mean, const float* invstd, const float* gamma,
                                       const float* beta, int act, float act_param, int noise, float rate, const float* r,
@@ -411,7 +434,7 @@ extern "C" int gn_chain_bwd_bf16(const void* x, const void* dy, void* dx, const 
                                  float act_param, int noise, float rate, const float* r, uint64_t seed, uint64_t offset,
                                  float* dgamma, float* dbeta, long long rows, int C, void* stream) {
     return chain_bwd_t<bf16_t>((const bf16_t*)x, (const bf16_t*)dy, (bf16_t*)dx, mean, invstd, gamma, beta, sums, n_total, act,
-                               act_param, noise, rate, r, seed, offset, dgamma, dbeta, rows, C, stream);
+                               act_param, noise, rate, r, seed, offset, dgamma, dbeta, rows, C, nullptr, stream);
 }
 
 // float32 activations: same arguments, every activation tensor is float*
@@ -422,7 +445,14 @@ extern "C" int gn_chain_fwd_f32(const float* x, float* y, const float* mean, con
                                 const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
                                 const float* r, uint64_t seed, uint64_t offset, long long rows, int C, void* stream) {
     return chain_fwd_t<float>(x, y, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, rows, C,
-                              stream);
+                              nullptr, stream);
+}
+extern "C" int gn_chain_fwd_amax_f32(const float* x, float* y, const float* mean, const float* scale, const float* gamma,
+                                     const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
+                                     const float* r, uint64_t seed, uint64_t offset, long long rows, int C, float* y_amax,
+                                     void* stream) {
+    return chain_fwd_t<float>(x, y, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, rows, C,
+                              y_amax, stream);
 }
 extern "C" int gn_chain_bwd_sums_f32(const float* x, const float* dy, const float* mean, const float* invstd,
                                      const float* gamma, const float* beta, int act, float act_param, int noise, float rate,
@@ -436,5 +466,12 @@ extern "C" int gn_chain_bwd_f32(const float* x, const float* dy, float* dx, cons
                                 float act_param, int noise, float rate, const float* r, uint64_t seed, uint64_t offset,
                                 float* dgamma, float* dbeta, long long rows, int C, void* stream) {
     return chain_bwd_t<float>(x, dy, dx, mean, invstd, gamma, beta, sums, n_total, act, act_param, noise, rate, r, seed, offset,
-                              dgamma, dbeta, rows, C, stream);
+                              dgamma, dbeta, rows, C, nullptr, stream);
+}
+extern "C" int gn_chain_bwd_amax_f32(const float* x, const float* dy, float* dx, const float* mean, const float* invstd,
+                                     const float* gamma, const float* beta, const double* sums, double n_total, int act,
+                                     float act_param, int noise, float rate, const float* r, uint64_t seed, uint64_t offset,
+                                     float* dgamma, float* dbeta, long long rows, int C, float* dx_amax, void* stream) {
+    return chain_bwd_t<float>(x, dy, dx, mean, invstd, gamma, beta, sums, n_total, act, act_param, noise, rate, r, seed, offset,
+                              dgamma, dbeta, rows, C, dx_amax, stream);
 }

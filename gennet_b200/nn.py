@@ -199,6 +199,28 @@ def _conv_wgrad_split(xs, dys, dy, dw, db, geom, nc):
         call('gn_conv1d_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), dw, db, *geom, nc, stream())
 
 
+def _chain_fwd(sfx, x, y, dt, mean, scale, gamma, beta, use_var, eps, code, par, kind, rate, r, seed, off, rows, C):
+    """gn_chain_fwd_*; in mode 'f16x2' the float32 form also accumulates max |y| (y._gn_amax) for the consumer's split."""
+    if dt == torch.float32 and _f16s():
+        y._gn_amax = _empty((1,))
+        call('gn_chain_fwd_amax_f32', ptr(x), ptr(y), mean, scale, gamma, beta, use_var, eps, code, par, kind, rate, r, seed,
+             off, rows, C, ptr(y._gn_amax), stream())
+    else:
+        call('gn_chain_fwd' + sfx, ptr(x, dt), ptr(y, dt), mean, scale, gamma, beta, use_var, eps, code, par, kind, rate, r,
+             seed, off, rows, C, stream())
+
+
+def _chain_bwd(sfx, x, dy, dx, dt, mean, invstd, gamma, beta, sums, n_total, code, par, kind, rate, r, seed, off, dgamma,
+               dbeta, rows, C):
+    if dt == torch.float32 and _f16s():
+        dx._gn_amax = _empty((1,))
+        call('gn_chain_bwd_amax_f32', ptr(x), ptr(dy), ptr(dx), mean, invstd, gamma, beta, sums, n_total, code, par, kind,
+             rate, r, seed, off, dgamma, dbeta, rows, C, ptr(dx._gn_amax), stream())
+    else:
+        call('gn_chain_bwd' + sfx, ptr(x, dt), ptr(dy, dt), ptr(dx, dt), mean, invstd, gamma, beta, sums, n_total, code, par,
+             kind, rate, r, seed, off, dgamma, dbeta, rows, C, stream())
+
+
 def _act_bwd(dy, y, code, param):
     """dy * act'(y) in the dtype the tensors are in."""
     if dy.dtype == BF16 and y.dtype == BF16:
@@ -1180,8 +1202,8 @@ class BatchNormalization(Layer):
         code, par, kind, rate = self._chain_codes(ctx)
         y = torch.empty(x.shape, dtype=dt, device=x.device)
         if not ctx.training:
-            call('gn_chain_fwd' + sfx, ptr(x, dt), ptr(y, dt), ptr(mm), ptr(mv), ptr(g), ptr(b), 1, self.epsilon, code,
-                 par, -1, 0.0, None, 0, 0, rows, C, stream())
+            _chain_fwd(sfx, x, y, dt, ptr(mm), ptr(mv), ptr(g), ptr(b), 1, self.epsilon, code, par, -1, 0.0, None, 0, 0,
+                       rows, C)
             return y
         sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
         stats = _empty((2 * C,))
@@ -1204,8 +1226,8 @@ class BatchNormalization(Layer):
                 off = _STATE['noise_counter'] + ((ctx.dp.rank << 48) if ctx.dp is not None else 0)
                 _STATE['noise_counter'] += (n + 3) // 4 * 4
                 seed = _STATE['seed']
-        call('gn_chain_fwd' + sfx, ptr(x, dt), ptr(y, dt), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), 0,
-             self.epsilon, code, par, kind, rate, ptr(r) if r is not None else None, seed, off, rows, C, stream())
+        _chain_fwd(sfx, x, y, dt, ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), 0, self.epsilon, code, par, kind, rate,
+                   ptr(r) if r is not None else None, seed, off, rows, C)
         self._x, self._stats, self._n = x, stats, n_total
         self._chain_state = (code, par, kind, rate, r, seed, off)
         return y
@@ -1227,9 +1249,9 @@ class BatchNormalization(Layer):
             ctx.dp.all_reduce(sums)
         dx = torch.empty(x.shape, dtype=dt, device=x.device)
         tr = id(self) in ctx.trainable_ids
-        call('gn_chain_bwd' + sfx, ptr(x, dt), ptr(dy, dt), ptr(dx, dt), ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b),
-             ptr(sums, torch.float64), self._n, code, par, kind, rate, rp, seed, off,
-             ptr(self.params[0].grad) if tr else None, ptr(self.params[1].grad) if tr else None, rows, C, stream())
+        _chain_bwd(sfx, x, dy, dx, dt, ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), ptr(sums, torch.float64), self._n,
+                   code, par, kind, rate, rp, seed, off, ptr(self.params[0].grad) if tr else None,
+                   ptr(self.params[1].grad) if tr else None, rows, C)
         if tr and ctx.world > 1:
             self.params[0].grad.mul_(1.0 / ctx.world)
             self.params[1].grad.mul_(1.0 / ctx.world)
@@ -1382,6 +1404,7 @@ class _NoiseLayer(Layer):
         self.rate = float(rate)
 
     _chain_skip = False   # True for the current call when the preceding BatchNormalization ran the bf16 chain
+    pre_act = None        # (code, param) of a ReLU / LeakyReLU fused into the convolution that feeds us (set by _fuse)
 
     def forward(self, x, ctx):
         self._bf16_state = None
@@ -1404,9 +1427,12 @@ class _NoiseLayer(Layer):
                 _STATE['noise_counter'] += (x.numel() + 3) // 4 * 4
                 seed = _STATE['seed']
             y = torch.empty(x.shape, dtype=dt, device=x.device)
-            call('gn_chain_fwd' + sfx, ptr(x, dt), ptr(y, dt), None, None, None, None, 0, 0.0, _lib.ACT_NONE, 0.0,
-                 self.kind, self.rate, ptr(r) if r is not None else None, seed, off, rows, C, stream())
+            _chain_fwd(sfx, x, y, dt, None, None, None, None, 0, 0.0, _lib.ACT_NONE, 0.0, self.kind, self.rate,
+                       ptr(r) if r is not None else None, seed, off, rows, C)
             self._bf16_state = (r, seed, off, dt)
+            # the sign activation fused into the producing convolution's epilogue gets its derivative in OUR backward
+            # pass (x is its output: same sign as the pre-activation), which saves the separate mask pass
+            self._xin = x if (self.pre_act is not None and dt == torch.float32) else None
             self._r = None
             return y
         x = _as_f32(x)
@@ -1433,10 +1459,13 @@ class _NoiseLayer(Layer):
             C = dy.shape[-1]
             rows = dy.numel() // C
             dx = torch.empty(dy.shape, dtype=dt, device=dy.device)
-            call('gn_chain_bwd' + sfx, ptr(dy, dt), ptr(dy, dt), ptr(dx, dt), None, None, None, None, None, 1.0,
-                 _lib.ACT_NONE, 0.0, self.kind, self.rate, ptr(r) if r is not None else None, seed, off, None, None,
-                 rows, C, stream())
-            self._bf16_state = None
+            xin = getattr(self, '_xin', None)
+            code, par = self.pre_act if xin is not None else (_lib.ACT_NONE, 0.0)
+            _chain_bwd(sfx, xin if xin is not None else dy, dy, dx, dt, None, None, None, None, None, 1.0, code, par,
+                       self.kind, self.rate, ptr(r) if r is not None else None, seed, off, None, None, rows, C)
+            if xin is not None:
+                dx._gn_preact = True
+            self._bf16_state = self._xin = None
             return dx
         if self._r is None or not need_dx:
             return dy
@@ -1825,6 +1854,14 @@ class Model(Layer):
                 if len(u) == 1 and isinstance(u[0].layer, _ActLayer) and u[0].layer.code != _lib.ACT_NONE:
                     n.layer.post_act = (u[0].layer.code, u[0].layer.param)
                     u[0].layer.fused = True
+        # Conv (ReLU | LeakyReLU in the epilogue) -> Dropout: the dropout's backward pass applies the activation mask too
+        for n in self._order:
+            if type(n.layer) in (Conv1D, Conv2D) and n.layer.post_act is not None and \
+                    n.layer.post_act[0] in (_lib.ACT_RELU, _lib.ACT_LEAKY):
+                a = users.get(id(n), [])[0]
+                u = users.get(id(a), [])
+                if len(u) == 1 and isinstance(u[0].layer, (Dropout, GaussianDropout)) and a not in self._out_nodes:
+                    u[0].layer.pre_act = n.layer.post_act
         # BatchNormalization -> [activation] -> [dropout]: candidates for the bf16 chain kernels (decided per call by the
         # dtype of the tensor reaching the BatchNormalization; float32 tensors keep the exact per-layer kernels)
         for n in self._order:
@@ -1941,6 +1978,7 @@ class Model(Layer):
                     acc = grads[id(src)] = _as_f32(acc)
                 call('gn_axpy_f32', ptr(acc.reshape(-1)), ptr(_as_f32(dx).reshape(-1).contiguous()), 1.0,
                      dx.numel(), stream())
+                acc._gn_amax = acc._gn_planes = None      # side products of the kernel that wrote acc are stale now
             else:
                 grads[id(src)] = dx
         return grads.get(id(self._in_node))

@@ -364,6 +364,15 @@ int gn_chain_bwd_f32(const float* x, const float* dy, float* dx, const float* me
                      const float* beta, const double* sums, double n_total, int act, float act_param, int noise,
                      float rate, const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta,
                      long long rows, int C, void* stream);
+/* the same two apply passes with a side output: y_amax / dx_amax (device scalar, OVERWRITTEN) = max |result|, the scale
+ * source of the consumer's gn_split_f32_f16x2(have_amax = 1) */
+int gn_chain_fwd_amax_f32(const float* x, float* y, const float* mean, const float* scale, const float* gamma, const float* beta,
+                          int use_var, float eps, int act, float act_param, int noise, float rate, const float* r,
+                          uint64_t seed, uint64_t offset, long long rows, int C, float* y_amax, void* stream);
+int gn_chain_bwd_amax_f32(const float* x, const float* dy, float* dx, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, const double* sums, double n_total, int act, float act_param,
+                          int noise, float rate, const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta,
+                          long long rows, int C, float* dx_amax, void* stream);
 
 /* elementwise */
 int gn_act_fwd_f32(const float* x, float* y, long long n, int act, float param, void* stream);
