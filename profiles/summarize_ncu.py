@@ -31,7 +31,10 @@ KEYS = ['gpu__time_duration.sum', 'sm__cycles_elapsed.avg.per_second', 'dram__by
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):      # raw page already exported on the GPU box (ncu -i rep --page raw --csv)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h, u = rows[0], rows[1]
     idx = {k: i for i, k in enumerate(h)}

@@ -11,7 +11,10 @@ import sys
 
 def main():
     rep, dst = sys.argv[1], sys.argv[2]
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):      # already exported on the GPU box: ncu -i rep --page raw --csv > file.csv
+        out = open(rep).read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h, u = rows[0], rows[1]
     idx = {k: i for i, k in enumerate(h)}
