@@ -80,7 +80,8 @@ def test_dense_small_f32(M, K, N):
     assert_close(db.cpu().numpy(), dy.cpu().double().sum(0).numpy(), 'dense small bias grad f32', 1e-6)
 
 
-@pytest.mark.parametrize('case', [(3, 300, 1024, 5, 'same'), (2, 97, 64, 5, 'valid'), (2, 64, 256, 3, 'same')])
+@pytest.mark.parametrize('case', [(3, 300, 1024, 5, 'same'), (2, 97, 64, 5, 'valid'), (2, 64, 256, 3, 'same'),
+                                  (40, 37, 256, 5, 'same'), (1500, 9, 512, 4, 'valid')])
 def test_cout1_conv_kernels_f32(case):
     from gennet_b200 import _lib as L_
     B, L, Cin, k, padding = case
@@ -113,7 +114,8 @@ def test_cout1_conv_kernels_f32(case):
     assert_close(db.cpu().numpy(), br.grad.numpy(), 'cout1 bias grad f32', 1e-5)
 
 
-@pytest.mark.parametrize('rows,C,act,noise', [(300, 64, 2, 0), (77, 912, 1, 1), (1000, 8, 4, -1), (64, 1024, 0, 0), (4096, 256, 2, 0)])
+@pytest.mark.parametrize('rows,C,act,noise', [(300, 64, 2, 0), (77, 912, 1, 1), (1000, 8, 4, -1), (64, 1024, 0, 0), (4096, 256, 2, 0),
+                                                (515, 128, 4, 0)])
 def test_f32_bn_act_dropout_chain(rows, C, act, noise):
     """gn_bn_sums_f32 / gn_chain_{fwd,bwd_sums,bwd}_f32 vs torch float64 autograd of drop(act(bn(x))) with a fed mask;
     the Philox-mask variant is self-consistent between forward and backward and equals gn_noise_draw_f32."""
@@ -161,6 +163,15 @@ def test_f32_bn_act_dropout_chain(rows, C, act, noise):
     assert_close(dbeta.cpu().numpy(), bg.grad.cpu().numpy(), 'chain dbeta f32', kink_tol)
     assert_close(dgamma.cpu().numpy(), gg.grad.cpu().numpy(), 'chain dgamma f32', kink_tol)
     assert_close(dx.cpu().numpy(), xg.grad.cpu().numpy(), 'chain dx f32', 1e-5)
+    # the forms with the max |result| side output (scale source of the f16x2 operand split): same results, exact maximum
+    y_a, dx_a = torch.full_like(x, float('nan')), torch.full_like(x, float('nan'))
+    am_y, am_dx = torch.full((1,), float('nan'), device='cuda'), torch.full((1,), float('nan'), device='cuda')
+    L_.call('gn_chain_fwd_amax_f32', L_.ptr(x), L_.ptr(y_a), L_.ptr(meanf), L_.ptr(invf), L_.ptr(gamma), L_.ptr(beta), 0, eps, act,
+            0.2, noise, rate, rp, 0, 0, rows, C, L_.ptr(am_y), st)
+    L_.call('gn_chain_bwd_amax_f32', L_.ptr(x), L_.ptr(dy), L_.ptr(dx_a), L_.ptr(meanf), L_.ptr(invf), L_.ptr(gamma), L_.ptr(beta),
+            L_.ptr(sums, f64), float(rows), act, 0.2, noise, rate, rp, 0, 0, None, None, rows, C, L_.ptr(am_dx), st)
+    assert torch.equal(y_a, y) and torch.equal(dx_a, dx)
+    assert am_y.item() == y.abs().max().item() and am_dx.item() == dx.abs().max().item()
     if noise >= 0:
         rr = torch.empty(rows, C, device='cuda')
         L_.call('gn_noise_draw_f32', L_.ptr(rr), rows * C, noise, rate, 77, 1024, st)
@@ -168,6 +179,15 @@ def test_f32_bn_act_dropout_chain(rows, C, act, noise):
         L_.call('gn_chain_fwd_f32', L_.ptr(x), L_.ptr(y1), None, None, None, None, 0, 0.0, 0, 0.0, noise, rate, None, 77, 1024, rows, C, st)
         L_.call('gn_chain_fwd_f32', L_.ptr(x), L_.ptr(y2), None, None, None, None, 0, 0.0, 0, 0.0, noise, rate, L_.ptr(rr), 0, 0, rows, C, st)
         assert torch.equal(y1, y2)
+        if act in (1, 4):
+            # dropout behind a convolution with a fused ReLU / LeakyReLU: the mask-only backward pass also applies the
+            # activation derivative, taken from the activation's OUTPUT (same sign as its input)
+            post = torch.relu(x) if act == 1 else torch.where(x >= 0, x, 0.2 * x)
+            L_.call('gn_chain_bwd_f32', L_.ptr(post.contiguous()), L_.ptr(dy), L_.ptr(y1), None, None, None, None, None, 1.0, act, 0.2,
+                    noise, rate, L_.ptr(rr), 0, 0, None, None, rows, C, st)
+            fr = (rr >= rate).double() / (1 - rate) if noise == 0 else 1 + rr.double() * np.sqrt(rate / (1 - rate))
+            dref = dy.double() * fr * torch.where(x > 0, torch.ones_like(fr), torch.full_like(fr, 0.0 if act == 1 else 0.2))
+            assert_close(y1.cpu().numpy(), dref.cpu().numpy(), 'dropout backward with the producer activation mask', 1e-6)
         L_.call('gn_chain_bwd_f32', L_.ptr(x), L_.ptr(dy), L_.ptr(y1), None, None, None, None, None, 1.0, 0, 0.0, noise, rate, None, 77,
                 1024, None, None, rows, C, st)
         L_.call('gn_chain_bwd_f32', L_.ptr(x), L_.ptr(dy), L_.ptr(y2), None, None, None, None, None, 1.0, 0, 0.0, noise, rate, L_.ptr(rr),
