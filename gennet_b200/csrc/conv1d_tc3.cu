@@ -1,25 +1,26 @@
-// Conv1D as implicit GEMM on the 5th-generation tensor cores (tcgen05) AT FLOAT32 ACCURACY: split-bf16 operands.
+// Conv1D as implicit GEMM on the 5th-generation tensor cores (tcgen05) AT FLOAT32 ACCURACY: split 16-bit operands.
 //
 //   The reference trains in float32 (cuDNN / Eigen fp32 convolutions behind the Conv1D layers of
-//   bbhMahoGANy.py:250-292,362-395).  A float32 value x is carried as NC bf16 "planes"
-//        x = x0 + x1 + x2,   x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1)       (NC = 3: 24 mantissa bits)
-//   and a product a*b is accumulated in fp32 tensor memory as the sum of the plane products a_i*b_j with i + j < NC
-//   (NC = 3: six tcgen05.mma per K step, dropped terms <= 2^-23 |a||b|; NC = 2: three, <= 2^-15).  Products of bf16
-//   values are exact in fp32, so the result differs from an fp32 FMA chain only by how the sums are rounded.
+//   bbhMahoGANy.py:250-292,362-395).  A float32 tensor is carried as NC 16-bit "planes" in one of two formats:
+//     bf16 planes        x = x0 + x1 + x2,  x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1)   (NC = 3: 24 mantissa bits)
+//       a product a*b = sum of the plane products a_i*b_j with i + j < NC (NC = 3: six tcgen05.mma per K step, dropped
+//       terms <= 2^-23 |a||b|; NC = 2: three, <= 2^-15)
+//     scaled fp16 pair   t = (T0 + 2^-11 T1) / s, s = power of two from max |t| (see f16s_exp below; NC = 2)
+//       three tcgen05.mma per K step, dropped term <= 2^-22 |a||b|, 22-23 bits relative to the TENSOR's scale
+//   Plane products are exact in fp32, so the result differs from an fp32 FMA chain only by how the sums are rounded.
 //   The tensor-memory accumulator TRUNCATES on every tcgen05.mma (measured: results biased towards zero by about
-//   0.3 ulp per accumulation), so with NC > 1 a tile keeps TWO accumulators: MAIN takes only the x0*w0 products
-//   (K/16 accumulations), CORR the 2^-8-times-smaller cross products (whose truncation is then negligible); the
-//   epilogue adds them in float32.  Double-buffered that is 4 x BN tensor-memory columns, hence BN <= 128.
+//   0.3 ulp per accumulation), so with NC > 1 a tile keeps TWO accumulators: MAIN takes only the leading products
+//   (K/16 accumulations), CORR the 2^-8 (bf16) / 2^-11 (fp16) times smaller cross products (whose truncation is then
+//   negligible); the epilogue adds them in float32.  Double-buffered that is 4 x BN tensor-memory columns, hence BN <= 128.
 //
-//   Layout: every operand tensor is stored as (NC, B, L, C) bf16 (plane-major).  One 4-D TMA load per operand and
-//   pipeline stage brings the (128 | BN) rows x 32 channels x NC planes box of one tap (SWIZZLE_64B; K = 32 per stage
-//   so that NC planes of both operands fit three to six stages).  Zero padding, sample boundaries, ragged tails and the
-//   stride-2 sampling come from TMA out-of-bounds fill / traversal stride exactly as in conv1d_tc.cu.
+//   Layout: every operand tensor is stored as (NC, B, L, C) 16-bit (plane-major).  One 4-D TMA load per operand and
+//   pipeline stage brings the (128 | BN) rows x BK channels x NC planes box of one tap (BK = 32: SWIZZLE_64B, three to
+//   six stages; BK = 64: SWIZZLE_128B, three stages, for the two-plane formats).  Zero padding, sample boundaries, ragged
+//   tails and the stride-2 sampling come from TMA out-of-bounds fill / traversal stride exactly as in conv1d_tc.cu.
 //   Warp roles (320 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer, warps 2-9 two epilogue sets
 //   (tcgen05.ld -> bias / activation | activation-derivative mask -> fp32 rows stored straight from registers: a
 //   thread owns 32 consecutive channels of one output row = one full 128-byte line -> optional re-split into the
-//   planes the next convolution consumes -> optional per-channel column sums).  With six MMAs per K step the tensor
-//   pipe is the bound on every layer, so the epilogue needs no shared-memory staging.
+//   bf16 planes the next convolution consumes -> optional per-channel column sums -> optional max |result|).
 //
 //   forward : Y[b,l,co]  = act( sum_{t,ci} X[b, l*s+t-p, ci] * W[t,ci,co] + bias[co] )      A=X   (K-major)  B=Wt[t][co][ci]
 //   dgrad   : dX[b,j,ci] = act'(Xin[b,j,ci]) * sum_{t,co} dY[b,(j+p-t)/s,co] * W[t,ci,co]    A=dY  (K-major)  B=W [t][ci][co]
