@@ -528,8 +528,12 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         fence_barrier_init();
     }
     constexpr int ACC_COLS = (NC > 1 ? 2 : 1) * BN;      // MAIN [+ CORR] accumulator of one unit
-    static_assert(2 * ACC_COLS <= 512, "tensor memory holds 512 columns");
-    if (warp == 1) tmem_alloc<2 * ACC_COLS>(tmem_slot);
+    // two accumulator buffers when they fit the 512 tensor-memory columns; MAIN + CORR at BN = 256 runs single-buffered
+    // (the reductions of a unit are exposed, about a tenth of its 64 iterations, but the 256-wide tile needs a quarter
+    // less operand fetch per MMA than the 128-wide one, which is fetch bound with three MMAs per K step)
+    constexpr int BUFS = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static_assert(BUFS * ACC_COLS <= 512, "tensor memory holds 512 columns");
+    if (warp == 1) tmem_alloc<BUFS * ACC_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -576,7 +580,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         int ul = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
             const Wg3Unit w = decode_wg3_unit<BN>(u, a);
-            const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
+            const int acc = (BUFS == 2) ? (ul & 1) : 0, acc_ph = ((BUFS == 2) ? (ul >> 1) : ul) & 1;
             mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
             tc_fence_after();
             const uint32_t tacc = tmem + (uint32_t)(acc * ACC_COLS);
@@ -613,7 +617,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         int ul = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
             const Wg3Unit w = decode_wg3_unit<BN>(u, a);
-            const int acc = ul & 1, acc_ph = (ul >> 1) & 1;
+            const int acc = (BUFS == 2) ? (ul & 1) : 0, acc_ph = ((BUFS == 2) ? (ul >> 1) : ul) & 1;
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
             const uint32_t tacc = tmem + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(q * 32) << 16);
@@ -656,7 +660,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<2 * ACC_COLS>(tmem);
+        tmem_dealloc<BUFS * ACC_COLS>(tmem);
     }
 }
 
@@ -870,7 +874,7 @@ template <int NC>
 static int dispatch_wgrad_tc3(int BN, bool swap, const CUtensorMap& mX, const CUtensorMap& mDY, const Tc3WgradArgs& a,
                               int grid, cudaStream_t st) {
     if (swap) return launch_wgrad_tc3<64, NC, true>(mX, mDY, a, grid, st);
-    if constexpr (NC == 1) {
+    if constexpr (NC <= 2) {
         if (BN == 256) return launch_wgrad_tc3<256, NC, false>(mX, mDY, a, grid, st);
     }
     if (BN == 128) return launch_wgrad_tc3<128, NC, false>(mX, mDY, a, grid, st);
@@ -1043,7 +1047,10 @@ static int dgrad_tc3(const void* dys, const void* wks, const float* x_in, float*
     if ((rc = check_fmt(f)) != GN_OK) return rc;
     GN_REQUIRE(f.amax_a == nullptr || dxs == nullptr, "the epilogue re-split exists for bf16 planes only");
     CUtensorMap mA, mB;
-    const int BN = pick_bn3(Cin, nc, 0);      // mask, column sums and re-split make this epilogue too long to expose
+    // mask, column sums and re-split make this epilogue long: the single-buffered 256-wide tile pays only for the
+    // two-plane formats (three MMAs per K step leave the 128-wide tile operand-fetch bound) on tiles with >= 160 K steps
+    // (measured: 512<-1024 and 256<-512 stride 1 gain 8-10 %, 256<-512 stride 2 with 80 steps loses 18 %)
+    const int BN = (nc == 2 && Cin % 256 == 0 && k * Cout / 16 / stride >= 160) ? 256 : pick_bn3(Cin, nc, 0);
     // A: dY planes viewed as (Cout, Lout, B, NC), 128 rows, unit traversal stride (parity classes handle the conv stride)
     const int BK = pick_bk3(BN, nc);
     const CUtensorMapSwizzle swz = (BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1113,7 +1120,14 @@ static int wgrad_tc3(const void* xs, const void* dys, const float* dy, float* dw
     a.amax_x = f.amax_a; a.amax_dy = f.amax_b;
     const bool swap = (Cin == 64);
     int m_tiles, BN;
-    if (!swap) { m_tiles = Cin / 128; BN = pick_bn3(Cout, nc, 0); a.n_tiles_n = Cout / BN; }
+    if (!swap) {
+        m_tiles = Cin / 128;
+        BN = pick_bn3(Cout, nc, 0);
+        // two-plane formats: the single-buffered 256-wide tile (a quarter less operand fetch per MMA) beats the
+        // double-buffered 128-wide one on every layer measured (GAN -0.7 ms, PE -0.9 ms per step)
+        if (nc == 2 && Cout % 256 == 0) BN = 256;
+        a.n_tiles_n = Cout / BN;
+    }
     else { m_tiles = Cout / 128; BN = 64; a.n_tiles_n = 1; }
     a.out_tiles = k * m_tiles * a.n_tiles_n;
     const int nsm = num_sms();
