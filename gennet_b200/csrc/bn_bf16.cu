@@ -61,7 +61,14 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 // (tanh.approx.f32: ~2^-11 relative error) instead of the multi-instruction libm forms.
 template <int KIND, bool EXACT>
 __device__ __forceinline__ float chain_act(float h, float p) {
-    if (EXACT) return act_fwd_t<KIND>(h, p);          // float32 activations: the same libm forms as the per-layer kernels
+    if (EXACT) {
+        // float32 activations.  The chain kernels are instruction-issue bound once tanh is a ~30-instruction libm call
+        // (it is evaluated in the forward pass and again in both backward passes), so tanh takes the exponential form
+        // 1 - 2 / (exp(2h) + 1) on the SFU (ex2.approx, rcp.approx): absolute error <= 1.5e-7 for every h (the relative
+        // error of exp(2h), ~2.4e-7 + 1.2e-7 |h|, is scaled by 2e/(e+1)^2 <= 1/2), saturating correctly to +-1.
+        if (KIND == GN_ACT_TANH) return 1.f - __fdividef(2.f, __expf(2.f * h) + 1.f);
+        return act_fwd_t<KIND>(h, p);                 // the same forms as the per-layer kernels
+    }
     if (KIND == GN_ACT_TANH) {
         float y;
         asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(h));
