@@ -296,6 +296,127 @@ __global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const T* __res
     }
 }
 
+// ---- first-layer convolution, ANY filter count and taps up to 16 (float32 only): Conv1D(50, 16) on (out_dim, 1) of the
+// 2_model_version discriminators (no_mode_collapse_network.py:117, subtract_model.py:134), Conv1D(25, 5) on (8192, 1)
+// of train_on_wvf_version/nn.py:95.  With Cin <= 2 the layer is k*Cin FMAs per output and bound by writing y / reading dy;
+// the implicit-GEMM kernels pad K = k*Cin to 16 and Cout to 128 and run it 10-30x below that bound.
+//   fwd  : thread = one output element (row, co), consecutive threads = consecutive co (coalesced store, broadcast x)
+//   wgrad: thread = (co, row lane): k*CIN accumulators in registers, dy read once (coalesced), x by broadcast loads
+//   dgrad: one warp per dy row, k*CIN dot products reduced by shuffles and scattered with atomics (dx zeroed by the caller)
+constexpr int SCG_KMAX = 16;
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_smallcin_gen_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                    const float* __restrict__ bias, float* __restrict__ y,
+                                                                    int B, int L, int Lout, int Cout, int k, int s, int p,
+                                                                    int act, float ap) {
+    extern __shared__ float sw[];     // k*CIN*Cout weights then Cout bias
+    const int nw = k * CIN * Cout;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const long long total = (long long)B * Lout * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int co, l;
+        const long long row = fast_div(i, Cout, co);
+        const int b = (int)fast_div(row, Lout, l);
+        const float* __restrict__ xb = x + (size_t)b * L * CIN;
+        float acc = sw[nw + co];
+        for (int t = 0; t < k; ++t) {
+            const int pos = l * s + t - p;
+            if (pos < 0 || pos >= L) continue;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) acc = fmaf(__ldg(&xb[(size_t)pos * CIN + c]), sw[(t * CIN + c) * Cout + co], acc);
+        }
+        y[i] = act_fwd(acc, act, ap);
+    }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_smallcin_gen_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                      float* __restrict__ dw, float* __restrict__ db, int B,
+                                                                      int L, int Lout, int Cout, int k, int s, int p,
+                                                                      long long rows_per_block) {
+    // block = 64 output channels x 4 row lanes; blockIdx.y = slice of 64 channels
+    __shared__ float red[4][SCG_KMAX * CIN + 1][64];
+    const int cl = threadIdx.x & 63, ry = threadIdx.x >> 6;
+    const int co = blockIdx.y * 64 + cl;
+    const bool live = co < Cout;
+    float acc[SCG_KMAX * CIN], accb = 0.f;
+#pragma unroll
+    for (int i = 0; i < SCG_KMAX * CIN; ++i) acc[i] = 0.f;
+    const long long rows = (long long)B * Lout;
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    if (live) {
+        for (long long row = r0 + ry; row < r1; row += 4) {
+            int l;
+            const int b = (int)fast_div(row, Lout, l);
+            const float g = __ldg(&dy[(size_t)row * Cout + co]);
+            const float* __restrict__ xb = x + (size_t)b * L * CIN;
+            accb += g;
+#pragma unroll
+            for (int t = 0; t < SCG_KMAX; ++t) {
+                const int pos = l * s + t - p;
+                if (t < k && pos >= 0 && pos < L) {
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) acc[t * CIN + c] = fmaf(__ldg(&xb[(size_t)pos * CIN + c]), g, acc[t * CIN + c]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < SCG_KMAX * CIN; ++i) red[ry][i][cl] = acc[i];
+    red[ry][SCG_KMAX * CIN][cl] = accb;
+    __syncthreads();
+    for (int e = threadIdx.x; e < (SCG_KMAX * CIN + 1) * 64; e += blockDim.x) {
+        const int i = e >> 6, c2 = e & 63, cg = blockIdx.y * 64 + c2;
+        if (cg >= Cout || (i < SCG_KMAX * CIN && i >= k * CIN)) continue;
+        const float v = red[0][i][c2] + red[1][i][c2] + red[2][i][c2] + red[3][i][c2];
+        if (i < SCG_KMAX * CIN) atomicAdd(&dw[(size_t)i * Cout + cg], v);
+        else if (db != nullptr) atomicAdd(&db[cg], v);
+    }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_smallcin_gen_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                      float* __restrict__ dx, int B, int L, int Lout, int Cout,
+                                                                      int k, int s, int p) {
+    extern __shared__ float sw[];     // k*CIN*Cout
+    const int nw = k * CIN * Cout;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)B * Lout;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0; row < rows; row += nwarps) {
+        int l;
+        const int b = (int)fast_div(row, Lout, l);
+        float acc[SCG_KMAX * CIN];
+#pragma unroll
+        for (int i = 0; i < SCG_KMAX * CIN; ++i) acc[i] = 0.f;
+        for (int co = lane; co < Cout; co += 32) {
+            const float g = __ldg(&dy[(size_t)row * Cout + co]);
+#pragma unroll
+            for (int i = 0; i < SCG_KMAX * CIN; ++i)
+                if (i < k * CIN) acc[i] = fmaf(g, sw[(size_t)i * Cout + co], acc[i]);
+        }
+        // lane i ends up with the full sum of dot product i (k*CIN <= 32)
+        float mine = 0.f;
+#pragma unroll
+        for (int i = 0; i < SCG_KMAX * CIN; ++i) {
+            float v = acc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (i == lane) mine = v;
+        }
+        if (lane < k * CIN) {
+            const int t = lane / CIN, c = lane - t * CIN;
+            const int pos = l * s + t - p;
+            if (pos >= 0 && pos < L) atomicAdd(&dx[((size_t)b * L + pos) * CIN + c], mine);
+        }
+    }
+}
+
 // ---- Dense with N <= 4 outputs over bf16 features -------------------------------------------------------------
 // fwd: y[m, j] = act(sum_k x[m,k] w[k,j] + b[j]) : one CTA per row m, 128-bit loads, block reduction
 template <int NS, typename T>
@@ -866,10 +987,24 @@ static int smallcin_fwd(const float* x, const float* w, const float* bias, T* yy
                         int k, int stride, int pad_left, int act, float act_param, void* stream) {
     GN_REQUIRE(x && w && yy, "null pointer");
     GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 16 && stride > 0 && pad_left >= 0, "bad geometry");
-    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout % 8 == 0 && Cout <= 1024, "needs Cin in {1,2} and Cout % 8 == 0");
+    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout > 0 && Cout <= 1024, "needs Cin in {1,2} and Cout <= 1024");
+    GN_REQUIRE(Cout % 8 == 0 || sizeof(T) == 4, "bf16 outputs need Cout % 8 == 0");
     if (B == 0) return GN_OK;
     const size_t smem = sizeof(float) * ((size_t)k * Cin * Cout + Cout);
     GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
+    if constexpr (sizeof(T) == 4) {
+        if (Cout % 8 != 0) {      // any filter count: one thread per output element
+            const long long total = (long long)B * Lout * Cout;
+            const unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
+            if (Cin == 1)
+                conv_smallcin_gen_fwd_kernel<1><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (float*)yy, B, L, Lout, Cout, k,
+                                                                                        stride, pad_left, act, act_param);
+            else
+                conv_smallcin_gen_fwd_kernel<2><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (float*)yy, B, L, Lout, Cout, k,
+                                                                                        stride, pad_left, act, act_param);
+            return cuda_status("conv_smallcin_gen_fwd_kernel");
+        }
+    }
     if (k <= 5) {
         // register-resident path: 256 threads = gpb channel groups x row lanes; a run of 32 rows per thread visit
         const int groups = Cout / 8;
@@ -914,14 +1049,31 @@ template <typename T>
 static int smallcin_wgrad(const float* x, const T* dy, float* dw, float* db, int B, int L, int Cin, int Lout, int Cout,
                           int k, int stride, int pad_left, void* stream) {
     GN_REQUIRE(x && dy && dw, "null pointer");
-    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 5 && stride > 0 && pad_left >= 0, "bad geometry (k <= 5)");
-    GN_REQUIRE((Cin == 1 || Cin == 2) && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 2048)),
-               "needs Cin in {1,2} and Cout in {8,16,32,64} or a multiple of 128");
+    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 16 && stride > 0 && pad_left >= 0, "bad geometry (k <= 16)");
+    const bool fast = k <= 5 && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 2048));
+    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout > 0 && (fast || (sizeof(T) == 4 && Cout <= 1024)),
+               "needs Cin in {1,2}; bf16 gradients need k <= 5 and Cout in {8,16,32,64} or a multiple of 128");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * Cin * Cout, st);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st);
     if (B == 0) return GN_OK;
     const long long rows = (long long)B * Lout;
+    if constexpr (sizeof(T) == 4) {
+        if (!fast) {      // any filter count / up to 16 taps
+            long long nb = 4LL * num_sms();
+            long long per = (rows + nb - 1) / nb;
+            if (per < 16) per = 16;
+            nb = (rows + per - 1) / per;
+            dim3 grid((unsigned)nb, (unsigned)((Cout + 63) / 64));
+            if (Cin == 1)
+                conv_smallcin_gen_wgrad_kernel<1><<<grid, 256, 0, st>>>(x, (const float*)dy, dw, db, B, L, Lout, Cout, k, stride,
+                                                                        pad_left, per);
+            else
+                conv_smallcin_gen_wgrad_kernel<2><<<grid, 256, 0, st>>>(x, (const float*)dy, dw, db, B, L, Lout, Cout, k, stride,
+                                                                        pad_left, per);
+            return cuda_status("conv_smallcin_gen_wgrad_kernel");
+        }
+    }
     long long blocks = 2LL * num_sms();      // few blocks: each ends in k*Cin*Cout same-address atomics, which serialise in L2
     long long per = (rows + blocks - 1) / blocks;
     if (per < 64) per = 64;
@@ -943,8 +1095,10 @@ template <typename T>
 static int smallcin_dgrad(const T* dy, const float* w, float* dx, int B, int L, int Cin, int Lout, int Cout, int k,
                           int stride, int pad_left, void* stream) {
     GN_REQUIRE(dy && w && dx, "null pointer");
-    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 5 && stride > 0 && pad_left >= 0, "bad geometry (k <= 5)");
-    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout % 8 == 0, "needs Cin in {1,2} and Cout % 8 == 0");
+    GN_REQUIRE(B >= 0 && L > 0 && Lout > 0 && k > 0 && k <= 16 && stride > 0 && pad_left >= 0, "bad geometry (k <= 16)");
+    const bool fast = k <= 5 && Cout % 8 == 0;
+    GN_REQUIRE((Cin == 1 || Cin == 2) && Cout > 0 && (fast || (sizeof(T) == 4 && k * Cin <= 32)),
+               "needs Cin in {1,2}; bf16 gradients need k <= 5 and Cout % 8 == 0");
     const size_t smem = sizeof(float) * (size_t)k * Cin * Cout;
     GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
     cudaStream_t st = as_stream(stream);
@@ -953,6 +1107,17 @@ static int smallcin_dgrad(const T* dy, const float* w, float* dx, int B, int L, 
     const long long rows = (long long)B * Lout;
     long long blocks = (rows + 7) / 8;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    if constexpr (sizeof(T) == 4) {
+        if (!fast) {
+            if (Cin == 1)
+                conv_smallcin_gen_dgrad_kernel<1><<<(unsigned)blocks, 256, smem, st>>>((const float*)dy, w, dx, B, L, Lout, Cout, k,
+                                                                                       stride, pad_left);
+            else
+                conv_smallcin_gen_dgrad_kernel<2><<<(unsigned)blocks, 256, smem, st>>>((const float*)dy, w, dx, B, L, Lout, Cout, k,
+                                                                                       stride, pad_left);
+            return cuda_status("conv_smallcin_gen_dgrad_kernel");
+        }
+    }
     if (Cin == 1)
         conv_smallcin_dgrad_kernel<1, 5, T><<<(unsigned)blocks, 256, smem, st>>>(dy, w, dx, B, L, Lout, Cout, k, stride, pad_left);
     else

@@ -636,6 +636,10 @@ class Conv1D(Layer):
         if _STATE['dtype'] != 'bfloat16':
             if _split_planes() and tiles and self.k <= 8 and self.s <= 2:
                 return 'tc3'
+            # float32 activations: the streaming first-layer kernels take any filter count and up to 16 taps
+            # (Conv1D(50, 16) / Conv1D(25, 5) on a single input channel: 2_model_version, train_on_wvf_version)
+            edge_in = edge_in or (self.fused_up == 1 and cin <= 2 and self.k <= 16 and co <= 1024 and
+                                  (self.k * cin + 1) * co <= 12000)
             return 'smallcin32' if edge_in else ('cout1_32' if edge_out else 'f32')
         if self.k > 8 or self.s > 2:
             return 'f32'

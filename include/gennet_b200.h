@@ -156,7 +156,11 @@ int gn_conv1d_wgrad_bf16(const void* x, const void* dy, float* dw, float* db, in
                          int Cout, int k, int stride, int pad_left, void* stream);
 
 /* The same bandwidth-bound kernels with FLOAT32 activations (float32 and split-operand modes, whose activations are
- * float32): identical arguments and semantics, every `void*` activation / gradient tensor above is `float*` here. */
+ * float32): identical arguments and semantics, every `void*` activation / gradient tensor above is `float*` here.
+ * The float32 smallcin entry points also take ANY filter count up to 1024 and up to 16 taps (k * Cin * Cout weights must
+ * fit 48 KB of shared memory; dgrad: k * Cin <= 32): Conv1D(50, 16) on (out_dim, 1) of the 2_model_version
+ * discriminators (no_mode_collapse_network.py:117, subtract_model.py:134), Conv1D(25, 5) on (8192, 1) of
+ * train_on_wvf_version/nn.py:95. */
 int gn_conv1d_smallcin_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int L, int Cin,
                                int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param,
                                void* stream);

@@ -20,7 +20,7 @@ def breakdown(f):
     for name, tag, a, b, _args in prof:
         d = tot.setdefault(name, [0.0, 0]); d[0] += a.elapsed_time(b); d[1] += 1
     return ', '.join('%s x%d %.2f' % (k.replace('gn_', ''), v[1], v[0]) for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:6])
-for mode in ('float32', 'bfloat16'):
+for mode in (sys.argv[1:] or ('float32', 'f16x2', 'bfloat16')):
     nn.set_compute_dtype(mode)
     # config 1: burst GAN, n_pix 512, batch 64: D step, residual-moments step, G step
     (g, d, dg, sub_g), _, z, sX, sy, ny = pc.burst_case(512, 64)

@@ -19,7 +19,10 @@ def dev(a):
 
 
 @pytest.mark.parametrize('case', [(3, 200, 1, 64, 5, 2, 'same'), (2, 256, 1, 64, 5, 1, 'same'), (2, 100, 2, 128, 5, 2, 'same'),
-                                  (2, 77, 1, 32, 3, 1, 'valid'), (3, 128, 2, 512, 5, 2, 'same')])
+                                  (2, 77, 1, 32, 3, 1, 'valid'), (3, 128, 2, 512, 5, 2, 'same'),
+                                  # any filter count / up to 16 taps: Conv1D(50, 16), Conv1D(25, 5) on one input channel
+                                  (5, 300, 1, 50, 16, 1, 'valid'), (3, 513, 1, 25, 5, 1, 'valid'), (2, 90, 2, 70, 16, 2, 'same'),
+                                  (2, 64, 1, 64, 16, 1, 'same'), (4, 40, 2, 3, 7, 1, 'valid')])
 def test_first_layer_kernels_f32(case):
     from gennet_b200 import _lib as L_
     B, L, Cin, Cout, k, s, padding = case

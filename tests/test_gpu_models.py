@@ -402,7 +402,7 @@ def test_nw_discriminator_parity(mode):
     try:
         D, od, X, y = pc.nw_disc_case(16)
         if mode != 'float32':
-            assert [l._path() for l in D.all_layers() if isinstance(l, nn.Conv1D)] == ['f32', 'tc3', 'tc3']
+            assert [l._path() for l in D.all_layers() if isinstance(l, nn.Conv1D)] == ['smallcin32', 'tc3', 'tc3']
         pc.assert_close(D.predict(X), od.predict(X), 'D.predict')
         errs, w0 = pc.compare_step(D, od, X, y)
         pc.compare_weights(D, od, w0)
