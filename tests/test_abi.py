@@ -39,6 +39,18 @@ def test_version_and_error_channel():
     assert rc == -1 and b'null pointer' in lib.gn_last_error()
     rc = lib.gn_overlap_sums_f32(None, None, 10, None, None)
     assert rc == -1 and b'null pointer' in lib.gn_last_error()
+    # split-operand tensor-core entry points: scaled fp16 pairs need both scale scalars; channel counts must tile
+    one = ctypes.c_void_p(16)       # never dereferenced: validation fails first
+    rc = lib.gn_split_f32_f16x2(one, one, None, 0, 64, None)
+    assert rc == -1 and b'null pointer' in lib.gn_last_error()
+    rc = lib.gn_conv1d_fwd_f16x2(one, None, one, one, None, one, None, 1, 64, 64, 60, 64, 5, 1, 0, 0, 0.0, None)
+    assert rc == -1 and b'null pointer' in lib.gn_last_error()
+    rc = lib.gn_conv1d_fwd_f16x2(one, one, one, one, None, one, None, 1, 64, 50, 60, 64, 5, 1, 0, 0, 0.0, None)
+    assert rc == -1 and b'multiples of 64' in lib.gn_last_error()
+    rc = lib.gn_conv1d_wgrad_f16x2(one, one, one, one, None, one, None, 1, 64, 64, 60, 64, 5, 1, 0, None)
+    assert rc == -1 and b'Cin % 128' in lib.gn_last_error()
+    rc = lib.gn_dense_dgrad_f16x2(one, one, one, one, None, one, None, 8, 100, 64, 0, 0.0, None)
+    assert rc == -1 and b'K % 64' in lib.gn_last_error()
 
 
 def test_no_cpu_fallback_without_device():
@@ -55,7 +67,11 @@ def test_no_cpu_fallback_without_device():
 
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, 'gennet_b200')
-    for f in os.listdir(pkg):
-        if f.endswith('.py'):
-            src = open(os.path.join(pkg, f)).read()
-            assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+    n = 0
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), os.path.join(d, f)
+                n += 1
+    assert n >= 15
