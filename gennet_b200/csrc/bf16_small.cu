@@ -304,61 +304,104 @@ __global__ void __launch_bounds__(256) conv_smallcin_dgrad_kernel(const T* __res
 //   wgrad: thread = (co, row lane): k*CIN accumulators in registers, dy read once (coalesced), x by broadcast loads
 //   dgrad: one warp per dy row, k*CIN dot products reduced by shuffles and scattered with atomics (dx zeroed by the caller)
 constexpr int SCG_KMAX = 16;
-template <int CIN>
+constexpr int SCG_R = 4;            // consecutive output rows per thread: one input window and one weight read feed all of them
+// fwd: thread = (block of SCG_R consecutive output rows of one sample, co); consecutive threads = consecutive co
+template <int CIN, int S>
 __global__ void __launch_bounds__(256) conv_smallcin_gen_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                     const float* __restrict__ bias, float* __restrict__ y,
-                                                                    int B, int L, int Lout, int Cout, int k, int s, int p,
+                                                                    int B, int L, int Lout, int Cout, int k, int p,
                                                                     int act, float ap) {
     extern __shared__ float sw[];     // k*CIN*Cout weights then Cout bias
     const int nw = k * CIN * Cout;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const long long total = (long long)B * Lout * Cout;
+    constexpr int WIN = (SCG_R - 1) * S + SCG_KMAX;
+    const int nblk = (Lout + SCG_R - 1) / SCG_R;
+    const long long total = (long long)B * nblk * Cout;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int co, l;
-        const long long row = fast_div(i, Cout, co);
-        const int b = (int)fast_div(row, Lout, l);
+        int co, rb;
+        const long long blk = fast_div(i, Cout, co);
+        const int b = (int)fast_div(blk, nblk, rb);
+        const int l0 = rb * SCG_R;
         const float* __restrict__ xb = x + (size_t)b * L * CIN;
-        float acc = sw[nw + co];
-        for (int t = 0; t < k; ++t) {
-            const int pos = l * s + t - p;
-            if (pos < 0 || pos >= L) continue;
+        const int base = l0 * S - p, wlen = (SCG_R - 1) * S + k;
+        float xw[WIN][CIN];
 #pragma unroll
-            for (int c = 0; c < CIN; ++c) acc = fmaf(__ldg(&xb[(size_t)pos * CIN + c]), sw[(t * CIN + c) * Cout + co], acc);
+        for (int j = 0; j < WIN; ++j) {
+            const int pos = base + j;
+            const bool ok = j < wlen && pos >= 0 && pos < L;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) xw[j][c] = ok ? __ldg(&xb[(size_t)pos * CIN + c]) : 0.f;
         }
-        y[i] = act_fwd(acc, act, ap);
+        float acc[SCG_R];
+#pragma unroll
+        for (int r = 0; r < SCG_R; ++r) acc[r] = sw[nw + co];
+#pragma unroll
+        for (int t = 0; t < SCG_KMAX; ++t) {
+            if (t < k) {
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) {
+                    const float wv = sw[(t * CIN + c) * Cout + co];
+#pragma unroll
+                    for (int r = 0; r < SCG_R; ++r) acc[r] = fmaf(xw[r * S + t][c], wv, acc[r]);
+                }
+            }
+        }
+        float* __restrict__ yb = y + ((size_t)b * Lout + l0) * Cout + co;
+#pragma unroll
+        for (int r = 0; r < SCG_R; ++r)
+            if (l0 + r < Lout) yb[(size_t)r * Cout] = act_fwd(acc[r], act, ap);
     }
 }
 
-template <int CIN>
+// wgrad: block = 64 output channels x 4 row lanes (blockIdx.y = slice of 64 channels); a lane takes blocks of SCG_R
+// consecutive rows of one sample: one input window and SCG_R gradient values feed k*CIN*SCG_R FMAs
+template <int CIN, int S>
 __global__ void __launch_bounds__(256) conv_smallcin_gen_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                       float* __restrict__ dw, float* __restrict__ db, int B,
-                                                                      int L, int Lout, int Cout, int k, int s, int p,
-                                                                      long long rows_per_block) {
-    // block = 64 output channels x 4 row lanes; blockIdx.y = slice of 64 channels
+                                                                      int L, int Lout, int Cout, int k, int p,
+                                                                      long long blks_per_block) {
     __shared__ float red[4][SCG_KMAX * CIN + 1][64];
     const int cl = threadIdx.x & 63, ry = threadIdx.x >> 6;
     const int co = blockIdx.y * 64 + cl;
     const bool live = co < Cout;
+    constexpr int WIN = (SCG_R - 1) * S + SCG_KMAX;
     float acc[SCG_KMAX * CIN], accb = 0.f;
 #pragma unroll
     for (int i = 0; i < SCG_KMAX * CIN; ++i) acc[i] = 0.f;
-    const long long rows = (long long)B * Lout;
-    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    const int nblk = (Lout + SCG_R - 1) / SCG_R;
+    const long long nb_total = (long long)B * nblk;
+    const long long q0 = (long long)blockIdx.x * blks_per_block, q1 = min(nb_total, q0 + blks_per_block);
     if (live) {
-        for (long long row = r0 + ry; row < r1; row += 4) {
-            int l;
-            const int b = (int)fast_div(row, Lout, l);
-            const float g = __ldg(&dy[(size_t)row * Cout + co]);
+        for (long long q = q0 + ry; q < q1; q += 4) {
+            int rb;
+            const int b = (int)fast_div(q, nblk, rb);
+            const int l0 = rb * SCG_R;
             const float* __restrict__ xb = x + (size_t)b * L * CIN;
-            accb += g;
+            const float* __restrict__ gp = dy + ((size_t)b * Lout + l0) * Cout + co;
+            float g[SCG_R];
+#pragma unroll
+            for (int r = 0; r < SCG_R; ++r) {
+                g[r] = (l0 + r < Lout) ? __ldg(&gp[(size_t)r * Cout]) : 0.f;
+                accb += g[r];
+            }
+            const int base = l0 * S - p, wlen = (SCG_R - 1) * S + k;
+            float xw[WIN][CIN];
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) {
+                const int pos = base + j;
+                const bool ok = j < wlen && pos >= 0 && pos < L;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) xw[j][c] = ok ? __ldg(&xb[(size_t)pos * CIN + c]) : 0.f;
+            }
 #pragma unroll
             for (int t = 0; t < SCG_KMAX; ++t) {
-                const int pos = l * s + t - p;
-                if (t < k && pos >= 0 && pos < L) {
+                if (t < k) {
 #pragma unroll
-                    for (int c = 0; c < CIN; ++c) acc[t * CIN + c] = fmaf(__ldg(&xb[(size_t)pos * CIN + c]), g, acc[t * CIN + c]);
+                    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                        for (int r = 0; r < SCG_R; ++r) acc[t * CIN + c] = fmaf(xw[r * S + t][c], g[r], acc[t * CIN + c]);
                 }
             }
         }
@@ -994,14 +1037,14 @@ static int smallcin_fwd(const float* x, const float* w, const float* bias, T* yy
     GN_REQUIRE(smem <= 48 * 1024, "weights do not fit shared memory");
     if constexpr (sizeof(T) == 4) {
         if (Cout % 8 != 0) {      // any filter count: one thread per output element
-            const long long total = (long long)B * Lout * Cout;
+            GN_REQUIRE(stride == 1 || stride == 2, "filter counts that are not multiples of 8 need stride 1 or 2");
+            const long long total = (long long)B * ((Lout + SCG_R - 1) / SCG_R) * Cout;
             const unsigned grid = (unsigned)((total + 255) / 256 < 16LL * num_sms() ? (total + 255) / 256 : 16LL * num_sms());
-            if (Cin == 1)
-                conv_smallcin_gen_fwd_kernel<1><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (float*)yy, B, L, Lout, Cout, k,
-                                                                                        stride, pad_left, act, act_param);
-            else
-                conv_smallcin_gen_fwd_kernel<2><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, (float*)yy, B, L, Lout, Cout, k,
-                                                                                        stride, pad_left, act, act_param);
+            cudaStream_t st = as_stream(stream);
+#define GN_SCG_FWD(CI, ST) conv_smallcin_gen_fwd_kernel<CI, ST><<<grid, 256, smem, st>>>(x, w, bias, (float*)yy, B, L, Lout, Cout, k, pad_left, act, act_param)
+            if (Cin == 1) { if (stride == 1) GN_SCG_FWD(1, 1); else GN_SCG_FWD(1, 2); }
+            else { if (stride == 1) GN_SCG_FWD(2, 1); else GN_SCG_FWD(2, 2); }
+#undef GN_SCG_FWD
             return cuda_status("conv_smallcin_gen_fwd_kernel");
         }
     }
@@ -1060,17 +1103,17 @@ static int smallcin_wgrad(const float* x, const T* dy, float* dw, float* db, int
     const long long rows = (long long)B * Lout;
     if constexpr (sizeof(T) == 4) {
         if (!fast) {      // any filter count / up to 16 taps
+            GN_REQUIRE(stride == 1 || stride == 2, "this filter count / tap count needs stride 1 or 2");
+            const long long nblk_total = (long long)B * ((Lout + SCG_R - 1) / SCG_R);
             long long nb = 4LL * num_sms();
-            long long per = (rows + nb - 1) / nb;
-            if (per < 16) per = 16;
-            nb = (rows + per - 1) / per;
+            long long per = (nblk_total + nb - 1) / nb;
+            if (per < 4) per = 4;
+            nb = (nblk_total + per - 1) / per;
             dim3 grid((unsigned)nb, (unsigned)((Cout + 63) / 64));
-            if (Cin == 1)
-                conv_smallcin_gen_wgrad_kernel<1><<<grid, 256, 0, st>>>(x, (const float*)dy, dw, db, B, L, Lout, Cout, k, stride,
-                                                                        pad_left, per);
-            else
-                conv_smallcin_gen_wgrad_kernel<2><<<grid, 256, 0, st>>>(x, (const float*)dy, dw, db, B, L, Lout, Cout, k, stride,
-                                                                        pad_left, per);
+#define GN_SCG_WG(CI, ST) conv_smallcin_gen_wgrad_kernel<CI, ST><<<grid, 256, 0, st>>>(x, (const float*)dy, dw, db, B, L, Lout, Cout, k, pad_left, per)
+            if (Cin == 1) { if (stride == 1) GN_SCG_WG(1, 1); else GN_SCG_WG(1, 2); }
+            else { if (stride == 1) GN_SCG_WG(2, 1); else GN_SCG_WG(2, 2); }
+#undef GN_SCG_WG
             return cuda_status("conv_smallcin_gen_wgrad_kernel");
         }
     }
