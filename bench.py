@@ -161,7 +161,7 @@ def make_inputs(seed, device):
 _CONV_ARGPOS = {'gn_conv1d_fwd_f32': 4, 'gn_conv1d_dgrad_f32': 3, 'gn_conv1d_wgrad_f32': 4,
                 'gn_conv1d_fwd_bf16': 4, 'gn_conv1d_dgrad_bf16': 5, 'gn_conv1d_wgrad_bf16': 4,
                 'gn_conv1d_fwd_bf16x3': 5, 'gn_conv1d_dgrad_bf16x3': 6, 'gn_conv1d_wgrad_bf16x3': 5,
-                'gn_conv1d_fwd_f16x2': 7, 'gn_conv1d_dgrad_f16x2': 8, 'gn_conv1d_wgrad_f16x2': 7,
+                'gn_conv1d_fwd_f16x2': 7, 'gn_conv1d_fwd_stats_f16x2': 7, 'gn_conv1d_dgrad_f16x2': 8, 'gn_conv1d_wgrad_f16x2': 7,
                 'gn_conv1d_smallcin_fwd_bf16': 4, 'gn_conv1d_smallcin_wgrad_bf16': 4, 'gn_conv1d_smallcin_dgrad_bf16': 3,
                 'gn_conv1d_smallcin_fwd_f32': 4, 'gn_conv1d_smallcin_wgrad_f32': 4, 'gn_conv1d_smallcin_dgrad_f32': 3}
 _DENSE_ARGPOS = {'gn_dense_fwd_f32': 4, 'gn_dense_dgrad_f32': 3, 'gn_dense_wgrad_f32': 4,
@@ -169,7 +169,7 @@ _DENSE_ARGPOS = {'gn_dense_fwd_f32': 4, 'gn_dense_dgrad_f32': 3, 'gn_dense_wgrad
                  'gn_dense_fwd_f16x2': 6, 'gn_dense_dgrad_f16x2': 7, 'gn_dense_wgrad_f16x2': 7}
 TENSOR_CORE_CALLS = ('gn_conv1d_fwd_bf16', 'gn_conv1d_dgrad_bf16', 'gn_conv1d_wgrad_bf16', 'gn_conv1d_fwd_bf16x3',
                      'gn_conv1d_dgrad_bf16x3', 'gn_conv1d_wgrad_bf16x3', 'gn_dense_fwd_bf16x3', 'gn_dense_dgrad_bf16x3',
-                     'gn_dense_wgrad_bf16x3', 'gn_conv1d_fwd_f16x2', 'gn_conv1d_dgrad_f16x2', 'gn_conv1d_wgrad_f16x2',
+                     'gn_dense_wgrad_bf16x3', 'gn_conv1d_fwd_f16x2', 'gn_conv1d_fwd_stats_f16x2', 'gn_conv1d_dgrad_f16x2', 'gn_conv1d_wgrad_f16x2',
                      'gn_dense_fwd_f16x2', 'gn_dense_dgrad_f16x2', 'gn_dense_wgrad_f16x2')
 
 

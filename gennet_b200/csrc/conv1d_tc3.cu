@@ -114,6 +114,10 @@ struct Tc3Args {
     const float* amax_a;
     const float* amax_b;
     float* amax_out;                       // optional: max |result| over the valid elements, atomically (bits as uint)
+    // optional (forward): per-channel (sum y, sum y^2) of the stored result, added into 2 * Cout doubles (zeroed by the
+    // launcher) -- the BatchNormalization statistics of the layer that follows, straight from the accumulators.  A CTA
+    // gathers them in shared memory (16 bytes per channel behind the barriers) and flushes once at the end.
+    double* bn_sums;
 };
 
 // operand formats: the instruction descriptor's A / B format fields (bits 7, 10) are 1 for bf16, 0 for fp16
@@ -179,6 +183,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t* tmem_full = empty + STAGES;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    double* sstat = reinterpret_cast<double*>(tiles + STAGES * S::STAGE_BYTES + 256);      // [2][cols] when a.bn_sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npar = (a.mode == 1) ? a.s : 1;
@@ -203,6 +208,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         fence_barrier_init();
     }
+    if (a.bn_sums != nullptr)
+        for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) sstat[i] = 0.0;
     constexpr int ACC_COLS = (NC > 1 ? 2 : 1) * BN;      // MAIN [+ CORR] accumulator of one tile
     // two accumulator buffers (the epilogue of tile i overlaps the MMAs of tile i+1) when they fit the 512 columns;
     // MAIN + CORR at BN = 256 is single-buffered: chosen on the host only for tiles with >= 80 K steps, where the
@@ -427,6 +434,29 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                     atomicAdd(a.colsum + c.n0 + sl * 32 + lane, f[0]);
                 }
+                if (a.bn_sums != nullptr) {
+                    // the same butterfly twice: lane l ends with sum y and sum y^2 of channel l over the warp's 32 rows
+                    // (float32 over 32 values), which go into the CTA's double accumulators
+                    float g[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        f[i] = valid ? f[i] : 0.f;
+                        g[i] = f[i] * f[i];
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float s1 = up ? f[i] : f[i + o], k1 = up ? f[i + o] : f[i];
+                            const float s2 = up ? g[i] : g[i + o], k2 = up ? g[i + o] : g[i];
+                            f[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, o);
+                            g[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, o);
+                        }
+                    }
+                    atomicAdd(&sstat[c.n0 + sl * 32 + lane], (double)f[0]);
+                    atomicAdd(&sstat[cols + c.n0 + sl * 32 + lane], (double)g[0]);
+                }
             }
         }
         if (a.amax_out != nullptr) {
@@ -437,6 +467,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (a.bn_sums != nullptr)
+        for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x)
+            if (sstat[i] != 0.0) atomicAdd(&a.bn_sums[i], sstat[i]);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<BUFS * ACC_COLS>(tmem);
@@ -818,11 +851,14 @@ static int launch_conv_tc3(const CUtensorMap& mA, const CUtensorMap& mB, const T
     static_assert(T3Smem<BN, NC, BK>::STAGES >= 3, "pipeline too shallow");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         attr_set = true;
     }
     const int grid = (int)(total_tiles < (long long)num_sms() ? total_tiles : (long long)num_sms());
-    kfn<<<grid, T3_THREADS, smem, st>>>(mA, mB, a);
+    // the BatchNormalization statistics take 16 bytes of shared memory per output channel behind the barriers
+    const int extra = (a.bn_sums != nullptr) ? 16 * ((a.mode == 0) ? a.Cout : a.Cin) : 0;
+    if (smem + extra > 232448) return fail(GN_ERR_UNSUPPORTED, "statistics accumulators do not fit shared memory%s", "");
+    kfn<<<grid, T3_THREADS, smem + extra, st>>>(mA, mB, a);
     return cuda_status("conv_tc3_kernel");
 }
 
@@ -986,9 +1022,9 @@ static int check_fmt(const Fmt3& f) {
     return GN_OK;
 }
 
-static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, float* y_amax, int B, int L, int Cin,
-                   int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param, Fmt3 f, int kchunks,
-                   void* stream) {
+static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y, void* ys, float* y_amax, double* bn_sums,
+                   int B, int L, int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act, float act_param, Fmt3 f,
+                   int kchunks, void* stream) {
     GN_REQUIRE(xs && wts && (y || ys), "null pointer");
     const int nc = f.nc;
     int rc = check_tc3_geom(B, L, Cin, Lout, Cout, k, stride, pad_left, nc);
@@ -1009,15 +1045,17 @@ static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y,
     a.B = B; a.L = L; a.Lout = Lout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.s = stride; a.p = pad_left;
     a.mode = 0; a.act = act; a.act_param = act_param; a.bias = bias; a.out = y;
     a.planes = (__nv_bfloat16*)ys; a.plane_stride = (long long)B * Lout * Cout;
-    a.amax_a = f.amax_a; a.amax_b = f.amax_b; a.amax_out = y_amax;
+    a.amax_a = f.amax_a; a.amax_b = f.amax_b; a.amax_out = y_amax; a.bn_sums = bn_sums;
     a.m_tiles = (Lout + TC_BM - 1) / TC_BM;
     a.kchunks = kchunks;
     a.kchunk = Cin / kchunks;
-    GN_REQUIRE(kchunks == 1 || (B == 1 && k == 1 && ys == nullptr && y != nullptr && y_amax == nullptr && a.kchunk % BK == 0),
+    GN_REQUIRE(kchunks == 1 || (B == 1 && k == 1 && ys == nullptr && y != nullptr && y_amax == nullptr && bn_sums == nullptr &&
+                                a.kchunk % BK == 0),
                "split-K needs B == 1, k == 1, a float32 output and chunks of whole channel blocks");
     const long long tiles = (long long)(kchunks > 1 ? kchunks : B) * a.m_tiles * (Cout / BN);
     cudaStream_t st = as_stream(stream);
     if (y_amax != nullptr) cudaMemsetAsync(y_amax, 0, sizeof(float), st);
+    if (bn_sums != nullptr) cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout, st);
     if (nc == 3) return dispatch_conv_tc3<3>(BN, false, mA, mB, a, tiles, st);
     if (nc == 2) return dispatch_conv_tc3<2>(BN, false, mA, mB, a, tiles, st);
     return dispatch_conv_tc3<1>(BN, false, mA, mB, a, tiles, st);
@@ -1026,14 +1064,22 @@ static int fwd_tc3(const void* xs, const void* wts, const float* bias, float* y,
 extern "C" int gn_conv1d_fwd_bf16x3(const void* xs, const void* wts, const float* bias, float* y, void* ys, int B, int L,
                                     int Cin, int Lout, int Cout, int k, int stride, int pad_left, int act,
                                     float act_param, int nc, void* stream) {
-    return fwd_tc3(xs, wts, bias, y, ys, nullptr, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param,
+    return fwd_tc3(xs, wts, bias, y, ys, nullptr, nullptr, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param,
                    Fmt3{nc, nullptr, nullptr}, 1, stream);
 }
 extern "C" int gn_conv1d_fwd_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax,
                                    const float* bias, float* y, float* y_amax, int B, int L, int Cin, int Lout, int Cout,
                                    int k, int stride, int pad_left, int act, float act_param, void* stream) {
     GN_REQUIRE(x_amax && w_amax, "null pointer");
-    return fwd_tc3(xs, wts, bias, y, nullptr, y_amax, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param,
+    return fwd_tc3(xs, wts, bias, y, nullptr, y_amax, nullptr, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param,
+                   Fmt3{2, x_amax, w_amax}, 1, stream);
+}
+extern "C" int gn_conv1d_fwd_stats_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax,
+                                         const float* bias, float* y, double* y_sums, int B, int L, int Cin, int Lout,
+                                         int Cout, int k, int stride, int pad_left, int act, float act_param, void* stream) {
+    GN_REQUIRE(x_amax && w_amax && y && y_sums, "null pointer");
+    GN_REQUIRE(Cout <= 1024, "the statistics accumulators hold up to 1024 channels");
+    return fwd_tc3(xs, wts, bias, y, nullptr, nullptr, y_sums, B, L, Cin, Lout, Cout, k, stride, pad_left, act, act_param,
                    Fmt3{2, x_amax, w_amax}, 1, stream);
 }
 
@@ -1207,10 +1253,10 @@ static int dense_fwd_tc3(const void* xs, const void* wts, const float* bias, flo
             if (tiles * c <= 2LL * num_sms() || kc > 4096) chunks = c;
         }
     }
-    if (chunks == 1) return fwd_tc3(xs, wts, bias, y, ys, nullptr, 1, M, Kp, M, N, 1, 1, 0, act, act_param, f, 1, stream);
+    if (chunks == 1) return fwd_tc3(xs, wts, bias, y, ys, nullptr, nullptr, 1, M, Kp, M, N, 1, 1, 0, act, act_param, f, 1, stream);
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, st);
-    int rc = fwd_tc3(xs, wts, nullptr, y, nullptr, nullptr, 1, M, Kp, M, N, 1, 1, 0, GN_ACT_NONE, 0.f, f, chunks, stream);
+    int rc = fwd_tc3(xs, wts, nullptr, y, nullptr, nullptr, nullptr, 1, M, Kp, M, N, 1, 1, 0, GN_ACT_NONE, 0.f, f, chunks, stream);
     if (rc != GN_OK) return rc;
     if (bias != nullptr || act != GN_ACT_NONE) {
         const long long n4 = (long long)M * N / 4;

@@ -165,10 +165,16 @@ def _w_split(w, k, cin, cout, nc):
     return wk, wt
 
 
-def _conv_fwd_split(xs, wt, bias, y, ys, want_amax, geom, code, par, nc):
+def _conv_fwd_split(xs, wt, bias, y, ys, want_amax, geom, code, par, nc, want_stats=False):
     """Forward convolution on the split-operand tensor-core kernels; geom = (B, L, Cin, Lout, Cout, k, stride, pad).
-    want_amax ('f16x2'): the epilogue also accumulates max |y| for the consumer's split."""
-    if _f16s():
+    want_amax ('f16x2'): the epilogue also accumulates max |y| for the consumer's split.  want_stats ('f16x2'): it also
+    produces the per-channel (sum y, sum y^2) the BatchNormalization behind this layer needs (y._gn_bn_sums)."""
+    if _f16s() and want_stats and geom[4] <= 1024:
+        sums = torch.empty(2 * geom[4], dtype=torch.float64, device=y.device)
+        call('gn_conv1d_fwd_stats_f16x2', ptr(xs, F16), ptr(xs._gn_amax), ptr(wt, F16), ptr(wt._gn_amax), bias, ptr(y),
+             ptr(sums, torch.float64), *geom, code, par, stream())
+        y._gn_bn_sums = sums
+    elif _f16s():
         am = _empty((1,)) if want_amax else None
         call('gn_conv1d_fwd_f16x2', ptr(xs, F16), ptr(xs._gn_amax), ptr(wt, F16), ptr(wt._gn_amax), bias, ptr(y), ptr(am),
              *geom, code, par, stream())
@@ -606,6 +612,7 @@ class Conv1D(Layer):
         self.in_act = None       # (code, param) of the fused activation that produced our input
         self.bias_src = None     # the Conv1D that produced our input when in_act is fused (set by _fuse)
         self.plane_consumer = None   # the Conv1D that alone consumes our (activated) output (set by _fuse)
+        self.bn_consumer = None      # the BatchNormalization(axis=-1) that alone consumes our output (set by _fuse)
         self._wcache = None
         self._wsplit = None
 
@@ -698,7 +705,8 @@ class Conv1D(Layer):
         if feeds_tc3 and not _f16s():
             ys = _empty_bf16((nc, B, self.Lout, self.filters))
         _conv_fwd_split(xs, wt, ptr(self.params[1].data), y, ys, feeds_tc3,
-                        (B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad), code, par, nc)
+                        (B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad), code, par, nc,
+                        want_stats=ctx.training and self.bn_consumer is not None)
         if ys is not None:
             y._gn_planes = ys
         self._xs = xs
@@ -1209,10 +1217,14 @@ class BatchNormalization(Layer):
             _chain_fwd(sfx, x, y, dt, ptr(mm), ptr(mv), ptr(g), ptr(b), 1, self.epsilon, code, par, -1, 0.0, None, 0, 0,
                        rows, C)
             return y
-        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
         stats = _empty((2 * C,))
         n_total = float(rows * ctx.world)
-        call('gn_bn_stats_bf16' if dt == BF16 else 'gn_bn_sums_f32', ptr(x, dt), rows, C, ptr(sums, torch.float64), stream())
+        # (sum x, sum x^2): from the epilogue of the convolution that produced x when it gathered them, else one pass
+        sums = getattr(x, '_gn_bn_sums', None)
+        if sums is None or sums.numel() != 2 * C:
+            sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+            call('gn_bn_stats_bf16' if dt == BF16 else 'gn_bn_sums_f32', ptr(x, dt), rows, C, ptr(sums, torch.float64),
+                 stream())
         if ctx.world > 1:
             ctx.dp.all_reduce(sums)
         # centred second moment from the raw one (double): sum (x-mean)^2 = sum x^2 - (sum x)^2 / n
@@ -1858,6 +1870,12 @@ class Model(Layer):
                 if len(u) == 1 and isinstance(u[0].layer, _ActLayer) and u[0].layer.code != _lib.ACT_NONE:
                     n.layer.post_act = (u[0].layer.code, u[0].layer.param)
                     u[0].layer.fused = True
+        # Conv1D -> BatchNormalization(axis=-1) with a single user: the convolution epilogue gathers the statistics
+        for n in self._order:
+            if type(n.layer) is Conv1D and n not in self._out_nodes:
+                u = users.get(id(n), [])
+                if len(u) == 1 and type(u[0].layer) is BatchNormalization and u[0].layer.axis != 1:
+                    n.layer.bn_consumer = u[0].layer
         # Conv (ReLU | LeakyReLU in the epilogue) -> Dropout: the dropout's backward pass applies the activation mask too
         for n in self._order:
             if type(n.layer) in (Conv1D, Conv2D) and n.layer.post_act is not None and \
@@ -1982,7 +2000,7 @@ class Model(Layer):
                     acc = grads[id(src)] = _as_f32(acc)
                 call('gn_axpy_f32', ptr(acc.reshape(-1)), ptr(_as_f32(dx).reshape(-1).contiguous()), 1.0,
                      dx.numel(), stream())
-                acc._gn_amax = acc._gn_planes = None      # side products of the kernel that wrote acc are stale now
+                acc._gn_amax = acc._gn_planes = acc._gn_bn_sums = None      # side products of the kernel that wrote acc are stale now
             else:
                 grads[id(src)] = dx
         return grads.get(id(self._in_node))

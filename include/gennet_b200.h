@@ -240,6 +240,11 @@ int gn_conv_w_split_f16x2(const float* w, void* wk, void* wt, float* amax, int k
 int gn_conv1d_fwd_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax, const float* bias,
                         float* y, float* y_amax, int B, int L, int Cin, int Lout, int Cout, int k, int stride,
                         int pad_left, int act, float act_param, void* stream);
+/* forward with the BatchNormalization statistics of the layer that follows: y_sums (2 * Cout doubles, OVERWRITTEN) =
+ * per-channel (sum y, sum y^2) of the stored result, taken from the accumulators in the epilogue (Cout <= 1024) */
+int gn_conv1d_fwd_stats_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax, const float* bias,
+                              float* y, double* y_sums, int B, int L, int Cin, int Lout, int Cout, int k, int stride,
+                              int pad_left, int act, float act_param, void* stream);
 int gn_conv1d_dgrad_f16x2(const void* dys, const float* dy_amax, const void* wks, const float* w_amax, const float* x_in,
                           float* dx, float* dx_colsum, float* dx_amax, int B, int L, int Cin, int Lout, int Cout, int k,
                           int stride, int pad_left, int in_act, float in_act_param, void* stream);

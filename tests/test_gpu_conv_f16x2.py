@@ -100,6 +100,17 @@ def test_f16x2_conv_fwd_dgrad_wgrad(case, scale_x, scale_w):
     L_.call('gn_conv1d_fwd_f16x2', L_.ptr(xs, H), L_.ptr(x_amax), L_.ptr(wt, H), L_.ptr(w_amax), L_.ptr(bias), L_.ptr(y),
             None, B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_RELU, 0.0, st)
     assert_close(y.cpu().numpy(), torch.relu(yr).detach().cpu().numpy(), 'f16x2 conv fwd+relu', TOL)
+    # the form that also gathers the BatchNormalization statistics of its output in the epilogue
+    if Cout <= 1024:
+        y2 = torch.full((B, Lout, Cout), float('nan'), device='cuda')
+        sums = torch.full((2 * Cout,), float('nan'), dtype=torch.float64, device='cuda')
+        L_.call('gn_conv1d_fwd_stats_f16x2', L_.ptr(xs, H), L_.ptr(x_amax), L_.ptr(wt, H), L_.ptr(w_amax), L_.ptr(bias), L_.ptr(y2),
+                L_.ptr(sums, torch.float64), B, L, Cin, Lout, Cout, k, s, pad, L_.ACT_RELU, 0.0, st)
+        torch.cuda.synchronize()
+        assert torch.equal(y2, y)
+        yd = y.double().reshape(-1, Cout)
+        assert torch.allclose(sums[:Cout], yd.sum(0), rtol=2e-6, atol=2e-6 * float(yd.abs().sum(0).max()))
+        assert torch.allclose(sums[Cout:], (yd * yd).sum(0), rtol=2e-6)
     # backward
     dy = dev(rs.normal(size=(B, Lout, Cout)) * 1e-4)
     (yr * dy.to(rdev).double()).sum().backward()
