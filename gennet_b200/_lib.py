@@ -103,6 +103,7 @@ _SIGS = {
     'gn_chain_bwd_sums_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p, c_p],
     'gn_chain_bwd_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_p, c_p, c_ll, c_i, c_p],
     'gn_chain_fwd_amax_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p, c_p],
+    'gn_chain_fwd_planes_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_ll, c_i, c_p, c_p, c_f, c_p],
     'gn_chain_bwd_amax_f32': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_i, c_f, c_i, c_f, c_p, c_u64, c_u64, c_p, c_p, c_ll, c_i, c_p, c_p],
     'gn_act_fwd_f32': [c_p, c_p, c_ll, c_i, c_f, c_p],
     'gn_act_bwd_f32': [c_p, c_p, c_p, c_ll, c_i, c_f, c_p],

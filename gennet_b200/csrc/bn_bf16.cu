@@ -218,13 +218,18 @@ __device__ __forceinline__ void warp_amax(float* amax, float m) {
 template <int KIND, typename T>
 __global__ void __launch_bounds__(256) chain_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                         ChainArgs a, long long rows, int C, long long lanes,
-                                                        float* __restrict__ amax) {
+                                                        float* __restrict__ amax, uint16_t* __restrict__ planes,
+                                                        float pscale, float pbound) {
+    // planes != nullptr (float32 activations): the result is also written as the scaled fp16 pair the next convolution
+    // consumes, planes (2, rows, C), with the scale of the a-priori bound pbound >= max |y| (bounded activations:
+    // tanh, sigmoid, ReLU(max_value), times the dropout factor), which is stored to amax[0] for the consumer
     constexpr bool EXACT = sizeof(T) == 4;
     const int C8 = C / 8;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = (int)(tid % C8);
     const long long lane = tid / C8;
     float m = 0.f;
+    if (planes != nullptr && tid == 0) amax[0] = pbound;
     if (lane < lanes) {
         float mu[8], is[8], sc[8], sh[8];
         channel_affine(a, cg * 8, mu, is, sc, sh);
@@ -240,9 +245,22 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const T* __restrict__ x,
                 m = fmaxf(m, fabsf(o[e]));
             }
             store8(y + i0, o);
+            if (planes != nullptr) {
+                uint32_t p0[4], p1[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint16_t a0, a1, b0, b1;
+                    split2h(o[2 * e] * pscale, a0, a1);
+                    split2h(o[2 * e + 1] * pscale, b0, b1);
+                    p0[e] = (uint32_t)a0 | ((uint32_t)b0 << 16);
+                    p1[e] = (uint32_t)a1 | ((uint32_t)b1 << 16);
+                }
+                *reinterpret_cast<uint4*>(planes + i0) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+                *reinterpret_cast<uint4*>(planes + (size_t)rows * C + i0) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+            }
         }
     }
-    warp_amax(amax, m);
+    if (planes == nullptr) warp_amax(amax, m);
 }
 
 // ---- backward apply: dx = sc * (g - sum_g/n - xhat * sum_gxhat/n);  without normalisation dx = g ---------------------
@@ -366,17 +384,22 @@ static int bn_stats_t(const T* x, long long rows, int C, double* sums, void* str
 template <typename T>
 static int chain_fwd_t(const T* x, T* y, const float* mean, const float* scale, const float* gamma, const float* beta,
                        int use_var, float eps, int act, float act_param, int noise, float rate, const float* r, uint64_t seed,
-                       uint64_t offset, long long rows, int C, float* amax, void* stream) {
+                       uint64_t offset, long long rows, int C, float* amax, void* stream, void* planes = nullptr,
+                       float bound = 0.f) {
     GN_REQUIRE(x && y && rows >= 0, "null pointer or rows < 0");
+    GN_REQUIRE(planes == nullptr || (sizeof(T) == 4 && amax != nullptr && bound > 0.f),
+               "planes need float32 activations, the scale scalar and a positive bound");
     ChainArgs a{};
     int rc = make_chain(&a, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, C);
     if (rc != GN_OK) return rc;
     cudaStream_t st = as_stream(stream);
-    if (amax != nullptr) cudaMemsetAsync(amax, 0, sizeof(float), st);
+    if (amax != nullptr && planes == nullptr) cudaMemsetAsync(amax, 0, sizeof(float), st);
     if (rows == 0) return GN_OK;
     unsigned grid; long long lanes;
     apply_geometry(rows, C, &grid, &lanes);
-    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, y, a, rows, C, lanes, amax)));
+    const float pscale = planes != nullptr ? ldexpf(1.f, f16s_exp(bound)) : 1.f;
+    GN_CHAIN_DISPATCH((chain_fwd_kernel<K_, T><<<grid, 256, 0, st>>>(x, y, a, rows, C, lanes, amax, (uint16_t*)planes, pscale,
+                                                                   bound)));
     return cuda_status("chain_fwd_kernel");
 }
 
@@ -474,6 +497,14 @@ extern "C" int gn_chain_bwd_f32(const float* x, const float* dy, float* dx, cons
                                 float* dgamma, float* dbeta, long long rows, int C, void* stream) {
     return chain_bwd_t<float>(x, dy, dx, mean, invstd, gamma, beta, sums, n_total, act, act_param, noise, rate, r, seed, offset,
                               dgamma, dbeta, rows, C, nullptr, stream);
+}
+extern "C" int gn_chain_fwd_planes_f32(const float* x, float* y, const float* mean, const float* scale, const float* gamma,
+                                       const float* beta, int use_var, float eps, int act, float act_param, int noise,
+                                       float rate, const float* r, uint64_t seed, uint64_t offset, long long rows, int C,
+                                       void* y_planes, float* y_amax, float bound, void* stream) {
+    GN_REQUIRE(y_planes && y_amax, "null pointer");
+    return chain_fwd_t<float>(x, y, mean, scale, gamma, beta, use_var, eps, act, act_param, noise, rate, r, seed, offset, rows, C,
+                              y_amax, stream, y_planes, bound);
 }
 extern "C" int gn_chain_bwd_amax_f32(const float* x, const float* dy, float* dx, const float* mean, const float* invstd,
                                      const float* gamma, const float* beta, const double* sums, double n_total, int act,

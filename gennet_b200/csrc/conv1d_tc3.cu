@@ -62,25 +62,6 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16 (&p)[3]) {
 //   11 (fp16 is a normal number from 2^-14 up): 22-23 bits of t relative to the TENSOR's scale.  A product needs three
 //   plane products, T0 W0 into MAIN and T0 W1 + T1 W0 into CORR (the dropped T1 W1 is <= 2^-22 |t||w|); the epilogue
 //   forms (MAIN + 2^-11 CORR) / (s_t s_w).
-constexpr float F16S_LO = 2048.f;             // 2^11: weight of the low plane
-__host__ __device__ __forceinline__ int f16s_exp(float amax) {
-#ifdef __CUDA_ARCH__
-    const uint32_t bits = __float_as_uint(amax);
-#else
-    uint32_t bits;
-    memcpy(&bits, &amax, 4);
-#endif
-    int e = (int)((bits >> 23) & 0xffu) - 127;      // floor(log2(amax)) of a normal number
-    if (e < -100) e = -100;                          // zero / tiny tensors: any scale will do, keep 2^se finite
-    return 14 - e;                                   // in [-113, 114]
-}
-__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
-__device__ __forceinline__ void split2h(float xs, uint16_t& h0, uint16_t& h1) {
-    const __half a = __float2half_rn(xs);
-    const __half b = __float2half_rn((xs - __half2float(a)) * F16S_LO);
-    h0 = __half_as_ushort(a);
-    h1 = __half_as_ushort(b);
-}
 // one element -> the 16-bit patterns of its planes in either format (F16S: `scale` = s, NC == 2)
 template <int NC, bool F16S>
 __device__ __forceinline__ void split_bits(float x, float scale, uint16_t (&p)[3]) {

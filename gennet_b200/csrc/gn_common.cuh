@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -144,6 +145,28 @@ __device__ __forceinline__ float act_bwd_from_y(float y, int kind, float a) {
     if (kind == GN_ACT_RELU_MAX) return act_bwd_t<GN_ACT_RELU_MAX>(y, a);
     if (kind == GN_ACT_ELU) return act_bwd_t<GN_ACT_ELU>(y, a);
     return 1.f;
+}
+
+// ---- scaled fp16 pair format of the split-operand tensor-core kernels (conv1d_tc3.cu): a float32 tensor t with
+// max |t| = amax travels as T0 = fp16(t s), T1 = fp16((t s - T0) 2^11) with s = 2^f16s_exp(amax)
+constexpr float F16S_LO = 2048.f;             // 2^11: weight of the low plane
+__host__ __device__ __forceinline__ int f16s_exp(float amax) {
+#ifdef __CUDA_ARCH__
+    const uint32_t bits = __float_as_uint(amax);
+#else
+    uint32_t bits;
+    memcpy(&bits, &amax, 4);
+#endif
+    int e = (int)((bits >> 23) & 0xffu) - 127;      // floor(log2(amax)) of a normal number
+    if (e < -100) e = -100;                          // zero / tiny tensors: any scale will do, keep 2^se finite
+    return 14 - e;                                   // in [-113, 114]
+}
+__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
+__device__ __forceinline__ void split2h(float xs, uint16_t& h0, uint16_t& h1) {
+    const __half a = __float2half_rn(xs);
+    const __half b = __float2half_rn((xs - __half2float(a)) * F16S_LO);
+    h0 = __half_as_ushort(a);
+    h1 = __half_as_ushort(b);
 }
 
 }  // namespace gn

@@ -205,9 +205,17 @@ def _conv_wgrad_split(xs, dys, dy, dw, db, geom, nc):
         call('gn_conv1d_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), dw, db, *geom, nc, stream())
 
 
-def _chain_fwd(sfx, x, y, dt, mean, scale, gamma, beta, use_var, eps, code, par, kind, rate, r, seed, off, rows, C):
-    """gn_chain_fwd_*; in mode 'f16x2' the float32 form also accumulates max |y| (y._gn_amax) for the consumer's split."""
-    if dt == torch.float32 and _f16s():
+def _chain_fwd(sfx, x, y, dt, mean, scale, gamma, beta, use_var, eps, code, par, kind, rate, r, seed, off, rows, C,
+               planes_bound=None):
+    """gn_chain_fwd_*; in mode 'f16x2' the float32 form also accumulates max |y| (y._gn_amax) for the consumer's split,
+    or -- planes_bound = an a-priori bound on |y| -- writes the consumer's operand planes itself (y._gn_planes)."""
+    if dt == torch.float32 and _f16s() and planes_bound is not None:
+        planes = _empty_planes((2,) + tuple(y.shape))
+        planes._gn_amax = _empty((1,))
+        call('gn_chain_fwd_planes_f32', ptr(x), ptr(y), mean, scale, gamma, beta, use_var, eps, code, par, kind, rate, r,
+             seed, off, rows, C, ptr(planes, F16), ptr(planes._gn_amax), float(planes_bound), stream())
+        y._gn_planes = planes
+    elif dt == torch.float32 and _f16s():
         y._gn_amax = _empty((1,))
         call('gn_chain_fwd_amax_f32', ptr(x), ptr(y), mean, scale, gamma, beta, use_var, eps, code, par, kind, rate, r, seed,
              off, rows, C, ptr(y._gn_amax), stream())
@@ -687,7 +695,7 @@ class Conv1D(Layer):
         code, par = self._act()
         xs = getattr(x, '_gn_planes', None)
         x = _as_f32(x).contiguous()
-        if xs is None or xs.shape[0] != nc or xs.dtype != _pdt() or self.fused_up != 1:
+        if xs is None or xs.shape[0] != nc or xs.dtype != _pdt() or tuple(xs.shape[1:]) != tuple(x.shape):
             xs = _split(x, nc)
         if self.fused_up != 1:
             Lp = L // self.fused_up
@@ -1169,6 +1177,7 @@ class BatchNormalization(Layer):
         return in_shape
 
     chain = (None, None)      # (activation layer, dropout layer) directly following, set by Model._fuse
+    planes_consumer = None    # the Conv1D that alone consumes the chain's output, set by Model._fuse
 
     def _finalize(self, ssq, n_total, C, stats, ctx):
         """1/sqrt(var + eps) of the batch and the moving-statistics update of a training-mode call.  Keras 2.2.4 on
@@ -1213,9 +1222,16 @@ class BatchNormalization(Layer):
                 l._chain_skip = True
         code, par, kind, rate = self._chain_codes(ctx)
         y = torch.empty(x.shape, dtype=dt, device=x.device)
+        # bounded activation feeding a split-operand convolution: the apply pass writes that convolution's operand planes
+        bound = None
+        cons = self.planes_consumer
+        if _f16s() and dt == torch.float32 and cons is not None and cons._path() == 'tc3' and \
+                kind in (-1, _lib.NOISE_DROPOUT) and code in (_lib.ACT_TANH, _lib.ACT_SIGMOID, _lib.ACT_RELU_MAX):
+            bound = (par if code == _lib.ACT_RELU_MAX else 1.0) / ((1.0 - rate) if kind >= 0 else 1.0)
+            bound = bound if bound > 0 else None
         if not ctx.training:
             _chain_fwd(sfx, x, y, dt, ptr(mm), ptr(mv), ptr(g), ptr(b), 1, self.epsilon, code, par, -1, 0.0, None, 0, 0,
-                       rows, C)
+                       rows, C, planes_bound=bound)
             return y
         stats = _empty((2 * C,))
         n_total = float(rows * ctx.world)
@@ -1243,7 +1259,7 @@ class BatchNormalization(Layer):
                 _STATE['noise_counter'] += (n + 3) // 4 * 4
                 seed = _STATE['seed']
         _chain_fwd(sfx, x, y, dt, ptr(stats[:C]), ptr(stats[C:]), ptr(g), ptr(b), 0, self.epsilon, code, par, kind, rate,
-                   ptr(r) if r is not None else None, seed, off, rows, C)
+                   ptr(r) if r is not None else None, seed, off, rows, C, planes_bound=bound)
         self._x, self._stats, self._n = x, stats, n_total
         self._chain_state = (code, par, kind, rate, r, seed, off)
         return y
@@ -1895,8 +1911,16 @@ class Model(Layer):
                     act, cur = u[0].layer, u[0]
                     u = users.get(id(cur), [])
                 if len(u) == 1 and isinstance(u[0].layer, (Dropout, GaussianDropout)) and cur not in self._out_nodes:
-                    noise = u[0].layer
+                    noise, cur = u[0].layer, u[0]
+                    u = users.get(id(cur), [])
                 n.layer.chain = (act, noise)
+                # the Conv1D that alone consumes the chain's output (through a fused UpSampling1D): candidate for
+                # operand planes written by the chain's apply pass
+                if len(u) == 1 and isinstance(u[0].layer, UpSampling1D) and u[0].layer.fused and cur not in self._out_nodes:
+                    cur = u[0]
+                    u = users.get(id(cur), [])
+                n.layer.planes_consumer = u[0].layer if (len(u) == 1 and type(u[0].layer) is Conv1D and
+                                                         cur not in self._out_nodes) else None
         # consumer of a fused conv+activation (through views / the now-identity activation layer): it may apply
         # the activation derivative in its own data-gradient epilogue, using its input as the mask source
         for n in self._order:

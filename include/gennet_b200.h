@@ -378,6 +378,13 @@ int gn_chain_bwd_f32(const float* x, const float* dy, float* dx, const float* me
 int gn_chain_fwd_amax_f32(const float* x, float* y, const float* mean, const float* scale, const float* gamma, const float* beta,
                           int use_var, float eps, int act, float act_param, int noise, float rate, const float* r,
                           uint64_t seed, uint64_t offset, long long rows, int C, float* y_amax, void* stream);
+/* forward apply pass that ALSO writes its result as the scaled fp16 pair the next convolution consumes: y_planes fp16
+ * (2, rows, C), scaled for the a-priori bound `bound` >= max |y| (bounded activations: tanh, sigmoid, ReLU(max_value),
+ * times the dropout factor 1 / (1 - rate)); y_amax[0] = bound on return.  Saves the separate split pass over y. */
+int gn_chain_fwd_planes_f32(const float* x, float* y, const float* mean, const float* scale, const float* gamma,
+                            const float* beta, int use_var, float eps, int act, float act_param, int noise, float rate,
+                            const float* r, uint64_t seed, uint64_t offset, long long rows, int C, void* y_planes,
+                            float* y_amax, float bound, void* stream);
 int gn_chain_bwd_amax_f32(const float* x, const float* dy, float* dx, const float* mean, const float* invstd,
                           const float* gamma, const float* beta, const double* sums, double n_total, int act, float act_param,
                           int noise, float rate, const float* r, uint64_t seed, uint64_t offset, float* dgamma, float* dbeta,

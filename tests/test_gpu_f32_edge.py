@@ -175,6 +175,21 @@ def test_f32_bn_act_dropout_chain(rows, C, act, noise):
             L_.ptr(sums, f64), float(rows), act, 0.2, noise, rate, rp, 0, 0, None, None, rows, C, L_.ptr(am_dx), st)
     assert torch.equal(y_a, y) and torch.equal(dx_a, dx)
     assert am_y.item() == y.abs().max().item() and am_dx.item() == dx.abs().max().item()
+    if act == 2 and noise in (-1, 0):
+        # bounded activation: the apply pass also writes the next convolution's operand planes (scaled fp16 pair) with the
+        # scale of the a-priori bound 1 / (1 - rate); they equal the split of y under that scale
+        bound = 1.0 / (1.0 - rate) if noise == 0 else 1.0
+        H = torch.float16
+        y_p = torch.full_like(x, float('nan'))
+        planes = torch.full((2, rows, C), float('nan'), dtype=H, device='cuda')
+        am_p = torch.full((1,), float('nan'), device='cuda')
+        L_.call('gn_chain_fwd_planes_f32', L_.ptr(x), L_.ptr(y_p), L_.ptr(meanf), L_.ptr(invf), L_.ptr(gamma), L_.ptr(beta), 0, eps,
+                act, 0.2, noise, rate, rp, 0, 0, rows, C, L_.ptr(planes, H), L_.ptr(am_p), bound, st)
+        assert torch.equal(y_p, y) and am_p.item() == np.float32(bound)
+        ref = torch.empty((2, rows, C), dtype=H, device='cuda')
+        L_.call('gn_split_f32_f16x2', L_.ptr(y), L_.ptr(ref, H), L_.ptr(am_p), 1, y.numel(), st)
+        assert torch.equal(planes, ref)
+        assert y.abs().max().item() <= bound
     if noise >= 0:
         rr = torch.empty(rows, C, device='cuda')
         L_.call('gn_noise_draw_f32', L_.ptr(rr), rows * C, noise, rate, 77, 1024, st)
