@@ -53,6 +53,7 @@ _SIGS = {
     'gn_dense_wgrad_bf16x3': [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     'gn_amax_f32': [c_p, c_ll, c_p, c_p],
     'gn_split_f32_f16x2': [c_p, c_p, c_p, c_i, c_ll, c_p],
+    'gn_split_colsum_f32_f16x2': [c_p, c_p, c_p, c_i, c_ll, c_i, c_p, c_p],
     'gn_conv_w_split_f16x2': [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     'gn_conv1d_fwd_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     'gn_conv1d_fwd_stats_f16x2': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],

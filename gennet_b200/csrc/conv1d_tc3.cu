@@ -737,6 +737,61 @@ __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict_
     }
 }
 
+// The same split for a gradient tensor dy (rows, C) that ALSO leaves its per-channel column sums = the bias gradient of
+// the layer whose output gradient it is (the weight-gradient call then skips its own pass over the float32 dy).  A thread
+// keeps one group of 8 channels and walks the rows with a stride of `lanes`; the row lanes of a block meet in shared
+// memory, one atomic per (block, channel) onto colsum (zeroed by the launcher).  C % 8 == 0, 256 % (C / 8) == 0 or
+// (C / 8) % 256 == 0.
+__global__ void __launch_bounds__(256) split_colsum_f16s_kernel(const float* __restrict__ x, uint16_t* __restrict__ planes,
+                                                                long long rows, int C, long long lanes,
+                                                                const float* __restrict__ amax, float* __restrict__ colsum) {
+    __shared__ float red[256][9];
+    const float scale = pow2i(f16s_exp(__ldg(amax)));
+    const int C8 = C / 8;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = (int)(tid % C8);
+    const long long lane = tid / C8;
+    const size_t n = (size_t)rows * C;
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    if (lane < lanes) {
+#pragma unroll 2
+        for (long long r = lane; r < rows; r += lanes) {
+            const size_t i0 = (size_t)r * C + (size_t)cg * 8;
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + i0));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + i0) + 1);
+            const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            uint32_t p0[4], p1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint16_t u0, u1, v0, v1;
+                split2h(f[2 * e] * scale, u0, u1);
+                split2h(f[2 * e + 1] * scale, v0, v1);
+                p0[e] = (uint32_t)u0 | ((uint32_t)v0 << 16);
+                p1[e] = (uint32_t)u1 | ((uint32_t)v1 << 16);
+                s[2 * e] += f[2 * e];
+                s[2 * e + 1] += f[2 * e + 1];
+            }
+            *reinterpret_cast<uint4*>(planes + i0) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+            *reinterpret_cast<uint4*>(planes + n + i0) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+        }
+    }
+    // fold the row lanes of this block that share a channel group (threads t, t + C8, t + 2 C8, ... when C8 < 256)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = s[e];
+    __syncthreads();
+    const int per = C8 < 256 ? 256 / C8 : 1;      // row lanes per block
+    const int ngroups = C8 < 256 ? C8 : 256;       // distinct channel groups in this block
+    for (int t = threadIdx.x; t < ngroups * 8; t += blockDim.x) {
+        const int g = t >> 3, e = t & 7;
+        float v = 0.f;
+        for (int q = 0; q < per; ++q) v += red[g + q * C8][e];
+        const int cgo = (int)(((long long)blockIdx.x * blockDim.x + g) % C8);
+        if (v != 0.f) atomicAdd(&colsum[cgo * 8 + e], v);
+    }
+}
+
 // y[r, c] = act(y[r, c] + bias[c]) in place (second pass of a split-K Dense forward); C % 4 == 0
 __global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, long long n4, int C4,
                                                        int act, float ap) {
@@ -963,6 +1018,29 @@ extern "C" int gn_split_f32_f16x2(const float* x, void* planes, float* amax, int
 extern "C" int gn_amax_f32(const float* x, long long n, float* amax, void* stream) {
     GN_REQUIRE(x && amax && n >= 0, "null pointer or n < 0");
     return launch_amax(x, n, amax, as_stream(stream));
+}
+
+extern "C" int gn_split_colsum_f32_f16x2(const float* x, void* planes, float* amax, int have_amax, long long rows, int C,
+                                         float* colsum, void* stream) {
+    GN_REQUIRE(x && planes && amax && colsum && rows >= 0 && C > 0, "null pointer or bad size");
+    GN_REQUIRE(C % 8 == 0 && (256 % (C / 8) == 0 || (C / 8) % 256 == 0),
+               "C / 8 must divide 256 or be a multiple of it");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)C, st);
+    if (rows == 0) return GN_OK;
+    if (!have_amax) {
+        int rc = launch_amax(x, rows * C, amax, st);
+        if (rc != GN_OK) return rc;
+    }
+    // about four CTAs of 256 threads per SM: long-lived threads keep the atomics per channel in the hundreds
+    const long long C8 = C / 8;
+    long long lanes = 4LL * num_sms() * 256 / C8;
+    if (lanes < 1) lanes = 1;
+    if (lanes > rows) lanes = rows;
+    if (C8 < 256) lanes = (lanes + 256 / C8 - 1) / (256 / C8) * (256 / C8);      // whole blocks of row lanes
+    const unsigned grid = (unsigned)((lanes * C8 + 255) / 256);
+    split_colsum_f16s_kernel<<<grid, 256, 0, st>>>(x, (uint16_t*)planes, rows, C, lanes, amax, colsum);
+    return cuda_status("split_colsum_f16s_kernel");
 }
 
 static int w_split_impl(const float* w, void* wk, void* wt, int k, int Cin, int Cout, int Cin_src, int nc, float* amax,

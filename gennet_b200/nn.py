@@ -152,6 +152,24 @@ def _split(x, nc):
     return planes
 
 
+def _split_grad(dy, nc, db):
+    """Operand planes of a gradient tensor dy (..., C); in mode 'f16x2' the same pass also leaves the bias gradient
+    db (C) = column sums of dy when `db` is given and C allows it.  Returns (planes, db_written)."""
+    C = dy.shape[-1]
+    c8 = C // 8
+    if db is not None and _f16s() and C % 8 == 0 and (256 % c8 == 0 or c8 % 256 == 0):
+        planes = _empty_planes((nc,) + tuple(dy.shape))
+        amax = getattr(dy, '_gn_amax', None)
+        have = amax is not None
+        if not have:
+            amax = _empty((1,))
+        call('gn_split_colsum_f32_f16x2', ptr(dy), ptr(planes, F16), ptr(amax), 1 if have else 0, dy.numel() // C, C, ptr(db),
+             stream())
+        planes._gn_amax = amax
+        return planes, True
+    return _split(dy, nc), False
+
+
 def _w_split(w, k, cin, cout, nc):
     """Conv weights f32 (k,cin,cout) -> (wk planes (nc,k,cin,cout), wt planes (nc,k,cout,cin))."""
     wk = _empty_planes((nc, k, cin, cout))
@@ -496,11 +514,12 @@ class Dense(Layer):
         N, Kp = self.units, self._kp()
         dy = _as_f32(dy).contiguous()
         f16 = nc > 1 and _f16s()
-        dys = _split(dy, nc)
-        if id(self) in ctx.trainable_ids:
+        trn = id(self) in ctx.trainable_ids
+        dys, wrote = _split_grad(dy, nc, self.params[1].grad if (f16 and trn) else None)
+        if trn:
             if f16:
                 call('gn_dense_wgrad_f16x2', ptr(xs, F16), ptr(xs._gn_amax), ptr(dys, F16), ptr(dys._gn_amax), ptr(dy),
-                     ptr(self.params[0].grad), ptr(self.params[1].grad), B, K, N, Kp, stream())
+                     ptr(self.params[0].grad), None if wrote else ptr(self.params[1].grad), B, K, N, Kp, stream())
             else:
                 call('gn_dense_wgrad_bf16x3', ptr(xs, BF16), ptr(dys, BF16), ptr(dy), ptr(self.params[0].grad),
                      ptr(self.params[1].grad), B, K, N, Kp, nc, stream())
@@ -729,7 +748,9 @@ class Conv1D(Layer):
         dys = getattr(dy, '_gn_planes', None)
         dy = _as_f32(dy).contiguous()
         if dys is None or dys.shape[0] != nc or dys.dtype != _pdt():
-            dys = _split(dy, nc)
+            # the split pass over dy also yields the bias gradient (column sums) where it can
+            dys, wrote = _split_grad(dy, nc, self.params[1].grad if (tr and not db_done) else None)
+            db_done = db_done or wrote
         geom = (B, L, cin, self.Lout, self.filters, self.k, self.s, self.pad)
         if tr:
             db = None if db_done else ptr(self.params[1].grad)
@@ -1016,10 +1037,12 @@ class Conv2D(Layer):
         if self._mode == 'tc3':
             nc = _split_planes()
             dy = _as_f32(dy).contiguous()
-            dys = _split(dy, nc)
+            d2 = dy.reshape(B, self.Lout, c2)
+            d2._gn_amax = getattr(dy, '_gn_amax', None)
+            dys, wrote = _split_grad(d2, nc, db1 if tr else None)
             geom = (B, H, c1, self.Lout, c2, self.kh, self.sh, self.pad)
             if tr:
-                _conv_wgrad_split(self._xs, dys, dy, ptr(dw1), ptr(db1), geom, nc)
+                _conv_wgrad_split(self._xs, dys, dy, ptr(dw1), None if wrote else ptr(db1), geom, nc)
             if need_dx:
                 wk = self._packed_split(nc)[2]
                 dx = _empty(x.shape)

@@ -237,6 +237,11 @@ int gn_dense_wgrad_bf16x3(const void* xs, const void* dys, const float* dy, floa
 int gn_amax_f32(const float* x, long long n, float* amax, void* stream);
 int gn_split_f32_f16x2(const float* x, void* planes, float* amax, int have_amax, long long n, void* stream);
 int gn_conv_w_split_f16x2(const float* w, void* wk, void* wt, float* amax, int k, int Cin, int Cout, void* stream);
+/* the split of a gradient tensor dy f32 (rows, C) that also leaves colsum f32 (C) OVERWRITTEN = its per-channel column
+ * sums, i.e. the bias gradient of the layer it belongs to (pass db = NULL to the weight-gradient call then);
+ * C % 8 == 0 and C / 8 divides 256 or is a multiple of it */
+int gn_split_colsum_f32_f16x2(const float* x, void* planes, float* amax, int have_amax, long long rows, int C, float* colsum,
+                              void* stream);
 int gn_conv1d_fwd_f16x2(const void* xs, const float* x_amax, const void* wts, const float* w_amax, const float* bias,
                         float* y, float* y_amax, int B, int L, int Cin, int Lout, int Cout, int k, int stride,
                         int pad_left, int act, float act_param, void* stream);

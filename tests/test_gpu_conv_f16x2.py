@@ -58,6 +58,23 @@ def test_f16x2_planes_reconstruct(spread):
     assert az.item() == 0.0 and (z == 0).all()
 
 
+@pytest.mark.parametrize('rows,C', [(1000, 64), (333, 1024), (77, 8), (4096, 2048), (5, 512)])
+def test_f16x2_gradient_split_with_column_sums(rows, C):
+    """gn_split_colsum_f32_f16x2: the planes equal the plain split, colsum = per-channel sums of dy (the bias gradient)."""
+    from gennet_b200 import _lib as L_
+    rs = np.random.RandomState(rows + C)
+    dy = dev(rs.normal(0.1, 1.0, size=(rows, C)) * 1e-3)
+    ref, amax = split_h(dy)
+    p = torch.full((2, rows, C), float('nan'), dtype=H, device='cuda')
+    a2 = torch.full((1,), float('nan'), device='cuda')
+    cs = torch.full((C,), float('nan'), device='cuda')
+    L_.call('gn_split_colsum_f32_f16x2', L_.ptr(dy), L_.ptr(p, H), L_.ptr(a2), 0, rows, C, L_.ptr(cs), L_.stream())
+    assert torch.equal(p, ref) and a2.item() == amax.item()
+    assert_close(cs.cpu().numpy(), dy.double().sum(0).cpu().numpy(), 'column sums of the gradient split', 2e-6)
+    L_.call('gn_split_colsum_f32_f16x2', L_.ptr(dy), L_.ptr(p, H), L_.ptr(amax), 1, rows, C, L_.ptr(cs), L_.stream())
+    assert torch.equal(p, ref)
+
+
 @pytest.mark.parametrize('scale_x,scale_w', [(1.0, 1.0), (3e-9, 5e3)])
 @pytest.mark.parametrize('case', CASES)
 def test_f16x2_conv_fwd_dgrad_wgrad(case, scale_x, scale_w):
