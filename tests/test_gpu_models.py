@@ -408,3 +408,44 @@ def test_nw_discriminator_parity(mode):
         pc.compare_weights(D, od, w0)
     finally:
         nn.set_compute_dtype('float32')
+
+
+@pytest.mark.parametrize('mode', ['f16x2', 'bf16x3'])
+def test_gan_iterations_track_the_float32_path(mode):
+    """Six consecutive device-resident GAN iterations (Philox dropout, Adam updates, moving statistics, cached operand
+    planes of the weights rebuilt every step) in a split-operand tensor-core mode against the float32 SIMT path from the
+    same seed: the loss trajectories stay together (nothing stale is carried from one iteration to the next)."""
+    from gennet_b200 import nn, bbh
+
+    def run(m):
+        nn.clear_session()
+        nn.set_seed(5)
+        nn.set_compute_dtype(m)
+        bbh.n_pix = 256
+        noise_signal = np.random.RandomState(0).normal(size=(256, 1)).astype(np.float32)
+        G, D, DG, _ = bbh.build_gan(noise_signal)
+        ns = torch.as_tensor(noise_signal.reshape(-1)).cuda()
+        g = torch.Generator(device='cuda').manual_seed(1)
+        out = []
+        w0 = [w.copy() for w in G.get_weights()]
+        for it in range(6):
+            real = torch.randn(16, 256, device='cuda', generator=g)
+            z1 = torch.rand(16, 100, device='cuda', generator=g) * 2 - 1
+            z2 = torch.rand(16, 100, device='cuda', generator=g) * 2 - 1
+            rn = torch.randn(16, 256, device='cuda', generator=g)
+            sd, sg = bbh.gan_train_step(G, D, DG, ns, real, z1, rn, z2)
+            out.append([sd[0], sg[0]])
+        return np.array(out), [w.copy() for w in G.get_weights()], w0
+    try:
+        ref, wref, w0 = run('float32')
+        got, wgot, w0b = run(mode)
+    finally:
+        nn.set_compute_dtype('float32')
+    assert all(np.array_equal(a, b) for a, b in zip(w0, w0b))
+    assert np.isfinite(got).all()
+    assert np.allclose(got, ref, rtol=2e-4, atol=2e-5), np.abs(got - ref).max()
+    # the generator's weights after six Adam steps, relative to how far they moved (Adam normalises the update, so a
+    # gradient component near zero turns a 1e-6 difference into a step of the order of the learning rate)
+    num = sum(float(((a - b) ** 2).sum()) for a, b in zip(wgot, wref))
+    den = sum(float(((b - c) ** 2).sum()) for b, c in zip(wref, w0))
+    assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
