@@ -443,9 +443,12 @@ def test_gan_iterations_track_the_float32_path(mode):
         nn.set_compute_dtype('float32')
     assert all(np.array_equal(a, b) for a, b in zip(w0, w0b))
     assert np.isfinite(got).all()
-    assert np.allclose(got, ref, rtol=2e-4, atol=2e-5), np.abs(got - ref).max()
+    # the order of the float atomics differs from run to run: observed 3e-5 .. 2e-4 on losses of ~0.7
+    assert np.allclose(got, ref, rtol=2e-3, atol=2e-4), np.abs(got - ref).max()
     # the generator's weights after six Adam steps, relative to how far they moved (Adam normalises the update, so a
     # gradient component near zero turns a 1e-6 difference into a step of the order of the learning rate)
     num = sum(float(((a - b) ** 2).sum()) for a, b in zip(wgot, wref))
     den = sum(float(((b - c) ** 2).sum()) for b, c in zip(wref, w0))
+    print('%s vs float32 after 6 GAN iterations: max loss difference %.2e, weight difference / movement %.2e' % (
+        mode, np.abs(got - ref).max(), (num / den) ** 0.5))
     assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
