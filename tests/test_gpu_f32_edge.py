@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import keras_oracle as ko
-from tests.parity_cases import assert_close
+from tests.parity_cases import assert_close, case_seed
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,7 @@ def dev(a):
 def test_first_layer_kernels_f32(case):
     from gennet_b200 import _lib as L_
     B, L, Cin, Cout, k, s, padding = case
-    rs = np.random.RandomState(abs(hash(case)) % 2 ** 31)
+    rs = np.random.RandomState(case_seed(case))
     x, w, bias = dev(rs.normal(size=(B, L, Cin))), dev(rs.normal(size=(k, Cin, Cout)) / math.sqrt(k * Cin)), dev(rs.normal(size=Cout))
     xr = x.cpu().double().requires_grad_(True)
     wr = w.cpu().double().requires_grad_(True)
@@ -88,7 +88,7 @@ def test_dense_small_f32(M, K, N):
 def test_cout1_conv_kernels_f32(case):
     from gennet_b200 import _lib as L_
     B, L, Cin, k, padding = case
-    rs = np.random.RandomState(abs(hash(case)) % 2 ** 31)
+    rs = np.random.RandomState(case_seed(case))
     x, w, bias = dev(rs.normal(size=(B, L, Cin))), dev(rs.normal(size=(k, Cin, 1)) / math.sqrt(k * Cin)), dev(rs.normal(size=1))
     xr = x.cpu().double().requires_grad_(True)
     wr = w.cpu().double().requires_grad_(True)
