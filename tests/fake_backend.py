@@ -193,6 +193,123 @@ class Fake:
         if dgamma is not None:
             dgamma.copy_(sums[C:2 * C].float())
 
+    # ---- split-operand tensor-core entry points with scaled fp16 pairs ("f16x2"): the planes are built exactly as the
+    # library builds them (include/gennet_b200.h), the products are taken on the reconstructed operands
+    @staticmethod
+    def _f16s_scale(amax):
+        a = float(amax.reshape(-1)[0])
+        e = math.floor(math.log2(a)) if a > 0 else -100
+        return 2.0 ** (14 - max(e, -100))
+
+    def _split_into(self, x, planes, amax, have):
+        xv = x.reshape(-1).float()
+        if not have:
+            amax.reshape(-1)[0] = xv.abs().max() if xv.numel() else 0.0
+        s = self._f16s_scale(amax)
+        t0 = (xv * s).half()
+        t1 = (((xv * s) - t0.float()) * 2048.0).half()
+        p = planes.reshape(2, -1)
+        p[0].copy_(t0)
+        p[1].copy_(t1)
+
+    def _unsplit(self, planes, amax):
+        p = planes.reshape(2, -1)
+        return ((p[0].double() + p[1].double() / 2048.0) / self._f16s_scale(amax)).float()
+
+    def gn_amax_f32(self, x, n, amax, st):
+        amax.reshape(-1)[0] = x.reshape(-1)[:n].abs().max()
+
+    def gn_split_f32_f16x2(self, x, planes, amax, have, n, st):
+        self._split_into(x, planes, amax, have)
+
+    def gn_split_colsum_f32_f16x2(self, x, planes, amax, have, rows, C, colsum, st):
+        self._split_into(x, planes, amax, have)
+        colsum[:C] = x.reshape(rows, C).sum(0)
+
+    def gn_conv_w_split_f16x2(self, w, wk, wt, amax, k, Cin, Cout, st):
+        self._split_into(w, wk, amax, False)
+        wt.copy_(wk.reshape(2, k, Cin, Cout).permute(0, 1, 3, 2).reshape(wt.shape))
+
+    def gn_upsample1d_fwd_bf16(self, x, y, B, L, C, size, st):      # a 16-bit copy: works on planes of either format
+        y.reshape(B, L * size, C).copy_(x.reshape(B, L, C).repeat_interleave(size, dim=1))
+
+    def _w_from_t(self, wts, wa, k, Cin, Cout):
+        return self._unsplit(wts, wa).reshape(k, Cout, Cin).permute(0, 2, 1).contiguous()
+
+    def gn_conv1d_fwd_f16x2(self, xs, xa, wts, wa, b, y, y_amax, B, L, Cin, Lout, Cout, k, s, p, act, ap, st):
+        x = self._unsplit(xs, xa)
+        self.gn_conv1d_fwd_f32(x, self._w_from_t(wts, wa, k, Cin, Cout), b, y, B, L, Cin, Lout, Cout, k, s, p, 1, act, ap, st)
+        if y_amax is not None:
+            y_amax.reshape(-1)[0] = y.abs().max()
+
+    def gn_conv1d_fwd_stats_f16x2(self, xs, xa, wts, wa, b, y, sums, B, L, Cin, Lout, Cout, k, s, p, act, ap, st):
+        self.gn_conv1d_fwd_f16x2(xs, xa, wts, wa, b, y, None, B, L, Cin, Lout, Cout, k, s, p, act, ap, st)
+        self.gn_bn_sums_f32(y, B * Lout, Cout, sums, st)
+
+    def gn_conv1d_dgrad_f16x2(self, dys, da, wks, wa, x_in, dx, colsum, dx_amax, B, L, Cin, Lout, Cout, k, s, p, in_act, ap, st):
+        dy = self._unsplit(dys, da)
+        self.gn_conv1d_dgrad_f32(dy, self._unsplit(wks, wa), dx, B, L, Cin, Lout, Cout, k, s, p, 1, st)
+        if x_in is not None and in_act != 0:
+            dx.mul_(_act_bwd(x_in.reshape(dx.shape), in_act, ap))
+        if colsum is not None:
+            colsum[:Cin] = dx.reshape(-1, Cin).sum(0)
+        if dx_amax is not None:
+            dx_amax.reshape(-1)[0] = dx.abs().max()
+
+    def gn_conv1d_wgrad_f16x2(self, xs, xa, dys, da, dy, dw, db, B, L, Cin, Lout, Cout, k, s, p, st):
+        self.gn_conv1d_wgrad_f32(self._unsplit(xs, xa), self._unsplit(dys, da), dw, None, B, L, Cin, Lout, Cout, k, s, p, 1, st)
+        if db is not None:
+            db.copy_(dy.reshape(-1, Cout).sum(0))
+
+    def gn_split_pad_f32_f16x2(self, x, planes, amax, rows, K, Kp, st):
+        xp = torch.zeros(rows, Kp)
+        xp[:, :K] = x.reshape(rows, K)
+        amax.reshape(-1)[0] = x.abs().max()
+        self._split_into(xp, planes, amax, True)
+
+    def gn_dense_w_split_f16x2(self, w, wk, wt, amax, K, Kp, N, st):
+        wp = torch.zeros(Kp, N)
+        wp[:K] = w.reshape(K, N)
+        amax.reshape(-1)[0] = w.abs().max()
+        self._split_into(wp, wk, amax, True)
+        wt.copy_(wk.reshape(2, Kp, N).permute(0, 2, 1).reshape(wt.shape))
+
+    def gn_dense_fwd_f16x2(self, xs, xa, wts, wa, b, y, M, Kp, N, act, ap, st):
+        w = self._unsplit(wts, wa).reshape(N, Kp).t().contiguous()
+        self.gn_dense_fwd_f32(self._unsplit(xs, xa), w, b, y, M, Kp, N, act, ap, st)
+
+    def gn_dense_dgrad_f16x2(self, dys, da, wks, wa, x_in, dx, colsum, M, K, N, in_act, ap, st):
+        g = self._unsplit(dys, da).reshape(M, N) @ self._unsplit(wks, wa).reshape(K, N).t()
+        if x_in is not None and in_act != 0:
+            g = g * _act_bwd(x_in.reshape(M, K), in_act, ap)
+        dx.reshape(M, K).copy_(g)
+        if colsum is not None:
+            colsum.copy_(g.reshape(M, K // colsum.numel(), colsum.numel()).sum((0, 1)))
+
+    def gn_dense_wgrad_f16x2(self, xs, xa, dys, da, dy, dw, db, M, K, N, Kp, st):
+        x = self._unsplit(xs, xa).reshape(M, Kp)[:, :K]
+        dw.reshape(K, N).copy_(x.t() @ self._unsplit(dys, da).reshape(M, N))
+        if db is not None:
+            db.copy_(dy.reshape(M, N).sum(0))
+
+    def gn_chain_fwd_amax_f32(self, x, y, mean, scale, gamma, beta, use_var, eps, act, ap, noise, rate, r, seed, off, rows, C,
+                              y_amax, st):
+        self.gn_chain_fwd_f32(x, y, mean, scale, gamma, beta, use_var, eps, act, ap, noise, rate, r, seed, off, rows, C, st)
+        y_amax.reshape(-1)[0] = y.abs().max()
+
+    def gn_chain_fwd_planes_f32(self, x, y, mean, scale, gamma, beta, use_var, eps, act, ap, noise, rate, r, seed, off, rows, C,
+                                planes, y_amax, bound, st):
+        self.gn_chain_fwd_f32(x, y, mean, scale, gamma, beta, use_var, eps, act, ap, noise, rate, r, seed, off, rows, C, st)
+        assert float(y.abs().max()) <= bound * (1 + 1e-6), 'a-priori bound violated'
+        y_amax.reshape(-1)[0] = bound
+        self._split_into(y, planes, y_amax, True)
+
+    def gn_chain_bwd_amax_f32(self, x, dy, dx, mean, invstd, gamma, beta, sums, n, act, ap, noise, rate, r, seed, off, dgamma,
+                              dbeta, rows, C, dx_amax, st):
+        self.gn_chain_bwd_f32(x, dy, dx, mean, invstd, gamma, beta, sums, n, act, ap, noise, rate, r, seed, off, dgamma, dbeta,
+                              rows, C, st)
+        dx_amax.reshape(-1)[0] = dx.abs().max()
+
     def gn_gap_fwd_f32(self, x, y, B, L, C, st):
         y.reshape(B, C).copy_(x.reshape(B, L, C).mean(1))
 

@@ -48,6 +48,49 @@ def test_gan_wiring_matches_oracle(fake):
     pc.compare_weights(g, og, [w for w in w0[:len(gw1)]])
 
 
+@pytest.fixture
+def f16x2(fake):
+    from gennet_b200 import nn
+    nn.set_compute_dtype('f16x2')
+    try:
+        yield nn
+    finally:
+        nn.set_compute_dtype('float32')
+
+
+def test_f16x2_mode_wiring_pe(f16x2):
+    """The benchmark's arithmetic mode on the host side: operand planes with their scale scalars travel between layers
+    (producer-computed max |x|, planes of weights per weight version), bias gradients come out of the data-gradient
+    column sums -- checked at rtol 1e-4 against the oracle with the C ABI answered by the CPU stand-in."""
+    nn = f16x2
+    prod, orc, x, y = pc.pe_case(128, 4)
+    assert sorted(l._path() for l in prod.all_layers() if isinstance(l, nn.Conv1D)) == ['smallcin32'] * 2 + ['tc3'] * 7
+    errs, w0 = pc.compare_step(prod, orc, x, y)
+    pc.compare_weights(prod, orc, w0)
+    pc.resync([(prod, orc)])
+    errs, w0 = pc.compare_step(prod, orc, x, y, check_predict=False)
+    pc.compare_weights(prod, orc, w0)
+
+
+def test_f16x2_mode_wiring_gan(f16x2):
+    """Generator / discriminator in the benchmark's mode: BatchNormalization statistics taken from the convolution that
+    feeds it, operand planes written by the BN-tanh-dropout apply pass under the a-priori bound, bias gradients from the
+    gradient split, dropout applying the fused LeakyReLU mask -- D step and G step through the frozen D."""
+    nn = f16x2
+    (g, d, dg), (og, od, ocomp), z, sX, sy = pc.gan_case(64, 4)
+    bns = [l for l in g.all_layers() if isinstance(l, nn.BatchNormalization)]
+    assert sum(l.planes_consumer is not None for l in bns) >= 4
+    assert sum(getattr(l, 'bn_consumer', None) is not None for l in g.all_layers() if isinstance(l, nn.Conv1D)) >= 4
+    pc.assert_close(g.predict(z), og.predict(z), 'generator.predict')
+    errs, w0 = pc.compare_step(d, od, sX, sy)
+    pc.compare_weights(d, od, w0)
+    pc.resync([(d, od)])
+    dw1 = [w.copy() for w in d.get_weights()]
+    errs, w0 = pc.compare_step(dg, ocomp, z, [1] * 4, check_predict=False)
+    assert all(np.array_equal(a, b) for a, b in zip(dw1, d.get_weights()))
+    pc.compare_weights(g, og, w0[:len(g.get_weights())])
+
+
 def test_burst_three_step_iteration(fake):
     (g, d, dg, sub_g), (og, od, ocomp, osub), z, sX, sy, ny = pc.burst_case(64, 4)
     errs, w0 = pc.compare_step(d, od, sX, sy)
