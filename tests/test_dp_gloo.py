@@ -22,10 +22,11 @@ def _free_port():
     return p
 
 
-def _build(kind, n_pix, seed):
+def _build(kind, n_pix, seed, mode='float32'):
     from gennet_b200 import nn, bbh
     nn.clear_session()
     nn.set_seed(seed)
+    nn.set_compute_dtype(mode)
     bbh.n_pix = n_pix
     if kind == 'pe':
         m = bbh.signal_pe_model()
@@ -55,7 +56,7 @@ def _noise_for(model, B, lo, hi):
     return out
 
 
-def _worker(rank, world, port, kind, n_pix, B, q):
+def _worker(rank, world, port, kind, n_pix, B, q, mode='float32'):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     torch.set_num_threads(1)
@@ -63,7 +64,7 @@ def _worker(rank, world, port, kind, n_pix, B, q):
     fake_backend.install(_MP())
     from gennet_b200 import parallel
     dp = parallel.init_data_parallel('gloo')
-    m = _build(kind, n_pix, 3)
+    m = _build(kind, n_pix, 3, mode)
     parallel.broadcast_weights(m)
     x, y = _data(kind, n_pix, B)
     lo, hi = dp.shard(B)
@@ -74,19 +75,23 @@ def _worker(rank, world, port, kind, n_pix, B, q):
     parallel.shutdown()
 
 
-@pytest.mark.parametrize('kind', ['pe', 'gen'])
-def test_two_rank_step_equals_single_process(kind, monkeypatch):
+@pytest.mark.parametrize('kind,mode', [('pe', 'float32'), ('gen', 'float32'), ('gen', 'f16x2')])
+def test_two_rank_step_equals_single_process(kind, mode, monkeypatch):
+    """mode 'f16x2': the BatchNormalization statistics come out of the convolution that feeds the layer and are
+    all-reduced like the ones of the separate pass; every rank scales its operand planes by its own shard's maximum."""
     n_pix, B = 64, 8
     from tests import fake_backend
+    from gennet_b200 import nn
     fake_backend.install(monkeypatch)
-    m = _build(kind, n_pix, 3)
+    monkeypatch.setitem(nn._STATE, 'dtype', nn._STATE['dtype'])      # restored after the test
+    m = _build(kind, n_pix, 3, mode)
     x, y = _data(kind, n_pix, B)
     r1 = m.train_on_batch(x, y, _noise=_noise_for(m, B, 0, B))
     g1, w1 = m.get_gradients(), m.get_weights()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, n_pix, B, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, n_pix, B, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     r2, g2, w2 = q.get(timeout=300)
